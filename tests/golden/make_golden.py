@@ -1,0 +1,143 @@
+"""Generate the golden vectors in this directory from the UNMODIFIED reference code.
+
+Run in the build container only (the reference is not present on the GPU box):
+
+    cd /root/repo && python tests/golden/make_golden.py [--ref /root/reference]
+
+It imports ``model.CHORETriplaneVisibility`` / ``SMPL_Layer`` straight from the read-only reference tree
+(stubbing the unvendored, unused third-party imports exactly as SURVEY.md appendix B describes), loads the
+seeded synthetic checkpoint of ``vistracker_b200.synth`` and stores inputs-by-seed + reference outputs:
+
+* ``sifnet_keys.json``      -- the reference ``state_dict()`` key order and shapes (706 entries)
+* ``sifnet_small.npz``      -- B=2, 64x64 frames, 301 points: all eight feature maps, all five heads and
+                               d(sum clamp(df_h,2))/d(points), d(sum clamp(df_o,2))/d(points)
+* ``sifnet_c1.npz``         -- BASELINE config 1 (1 frame 512x512, 2000 points): the five heads in full and
+                               every 8th pixel of each feature map
+* ``smpl_small.npz``        -- SMPL_Layer.forward on the synthetic SMPL-H model, B=5, outputs + gradients
+"""
+from __future__ import annotations
+
+import argparse
+import contextlib
+import io
+import json
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REPO = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, REPO)
+sys.dont_write_bytecode = True
+
+
+def _stub(name, **kw):
+    m = types.ModuleType(name)
+    m.__dict__.update(kw)
+    sys.modules[name] = m
+    return m
+
+
+def import_reference(ref_root: str):
+    sk = _stub("skimage"); sk.measure = _stub("skimage.measure")                       # model/mesh_util.py:1
+    ch = _stub("chumpy", Ch=object); ch.ch = _stub("chumpy.ch", MatVecMult=None)
+    ps = _stub("psbody"); ps.mesh = _stub("psbody.mesh", Mesh=object, MeshViewer=object)
+    _stub("psbody.mesh.sphere", Sphere=object)
+    os.chdir(ref_root)                       # PATHS.yml / config/ are opened relative to cwd
+    sys.path.insert(0, ref_root)
+
+
+def sifnet_goldens(out_dir: str):
+    from config.config_loader import load_configs                                     # reference
+    from model import CHORETriplaneVisibility                                         # reference
+    from vistracker_b200.config import resolve_dims
+    from vistracker_b200.synth import synthetic_frames, synthetic_state_dict
+
+    with contextlib.redirect_stdout(io.StringIO()):
+        opt = load_configs("tri-vis-l2")
+        net = CHORETriplaneVisibility(opt).eval()
+    keys = [(k, list(v.shape)) for k, v in net.state_dict().items()]
+    with open(os.path.join(out_dir, "sifnet_keys.json"), "w") as f:
+        json.dump(keys, f)
+    sd = synthetic_state_dict(resolve_dims(opt), seed=0)
+    net.load_state_dict(sd, strict=True)
+    for p in net.parameters():
+        p.requires_grad = False
+
+    def run(images, points, crop, body, with_grad):
+        with torch.no_grad():
+            net.filter(images)
+        maps = {"im_feat": net.im_feat_list[0], "tmpx": net.tmpx}
+        for v in range(3):
+            maps[f"tri_feat{v}"] = net.triplane_feat_list[v][0]
+            maps[f"tri_tmpx{v}"] = net.triplane_tmpx[v]
+        out = {}
+        grads = {}
+        for name, idx in (("grad_h", 0), ("grad_o", 1)):
+            pts = points.clone().requires_grad_(with_grad)
+            net.query(pts, crop_center=crop, body_center=body)
+            df, pca, parts, centers, vis = net.get_preds()
+            if with_grad:
+                torch.clamp(df[:, idx], max=2.0).sum().backward()     # recon/gen/generator.py:88-90
+                grads[name] = pts.grad.detach().numpy().copy()
+        out.update(df=df, pca=pca, parts=parts, centers=centers, vis=vis)
+        out = {k: v.detach().numpy().copy() for k, v in out.items()}
+        out.update(grads)
+        feat, xy = net.query_features(points, crop, body_center=body)
+        out["features"] = feat.detach().numpy().copy()
+        out["xy"] = xy.detach().numpy().copy()
+        return {k: v.detach().numpy().copy() for k, v in maps.items()}, out
+
+    # small case: everything stored
+    images, points, crop, body = synthetic_frames(2, size=64, seed=11, n_points=301, jitter=True)
+    maps, out = run(images, points, crop, body, True)
+    np.savez_compressed(os.path.join(out_dir, "sifnet_small.npz"), **maps, **out)
+    print("sifnet_small:", {k: v.shape for k, v in {**maps, **out}.items()})
+
+    # BASELINE config 1: 1 frame 512x512, 2000 points
+    images, points, crop, body = synthetic_frames(1, size=512, seed=0, n_points=2000, jitter=False)
+    maps, out = run(images, points, crop, body, True)
+    maps = {k: np.ascontiguousarray(v[:, :, ::8, ::8]) for k, v in maps.items()}
+    out.pop("features")
+    np.savez_compressed(os.path.join(out_dir, "sifnet_c1.npz"), **maps, **out)
+    print("sifnet_c1:", {k: v.shape for k, v in {**maps, **out}.items()})
+
+
+def smpl_goldens(out_dir: str):
+    from lib_smpl.smplpytorch.smplpytorch.pytorch.smpl_layer import SMPL_Layer       # reference
+    from vistracker_b200.synth_smpl import synthetic_smplh, synthetic_motion
+
+    model = synthetic_smplh(seed=3)
+    L = SMPL_Layer.__new__(SMPL_Layer)
+    torch.nn.Module.__init__(L)
+    L.hands, L.num_joints, L.kintree_parents = True, 52, list(model["parents"])
+    for k in ("th_betas", "th_shapedirs", "th_posedirs", "th_v_template", "th_J_regressor", "th_weights"):
+        L.register_buffer(k, model[k])
+    pose, betas, trans = synthetic_motion(5, seed=5)
+    pose[0, 3:6] = 0.0            # exercises the theta -> 0 branch of Rodrigues (norm(theta + 1e-8))
+    pose.requires_grad_(True); betas.requires_grad_(True); trans.requires_grad_(True)
+    verts, jtr, v_posed, naked = L(pose, th_betas=betas, th_trans=trans, th_offsets=torch.zeros(5, 6890, 3))
+    rng = np.random.Generator(np.random.PCG64(17))
+    gv = torch.from_numpy(rng.standard_normal(tuple(verts.shape), dtype=np.float32))
+    gj = torch.from_numpy(rng.standard_normal(tuple(jtr.shape), dtype=np.float32))
+    ((verts * gv).sum() + (jtr * gj).sum()).backward()
+    np.savez_compressed(os.path.join(out_dir, "smpl_small.npz"),
+                        verts=verts.detach().numpy(), jtr=jtr.detach().numpy(), v_posed=v_posed.detach().numpy(),
+                        g_pose=pose.grad.numpy(), g_betas=betas.grad.numpy(), g_trans=trans.grad.numpy())
+    print("smpl_small: verts", tuple(verts.shape), "jtr", tuple(jtr.shape))
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--ref", default="/root/reference")
+    ap.add_argument("--only", default="")
+    a = ap.parse_args()
+    import_reference(a.ref)
+    torch.set_num_threads(os.cpu_count())
+    if a.only in ("", "sifnet"):
+        sifnet_goldens(HERE)
+    if a.only in ("", "smpl"):
+        smpl_goldens(HERE)

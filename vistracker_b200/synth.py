@@ -1,0 +1,139 @@
+"""Seeded synthetic checkpoints and inputs.
+
+The reference ships neither its trained checkpoints nor BEHAVE data (README.md:37,42,62), so parity
+and throughput are established on a random-init network with a fixed seed and on synthetic frames
+(SURVEY.md section 8(d)).  Everything here is generated with ``numpy.random.Generator(PCG64(seed))`` in a
+fixed key order so that the build container (where the golden vectors are produced from the real
+reference code) and the GPU box (where only this repo exists) see bit-identical tensors.
+"""
+from __future__ import annotations
+
+from collections import OrderedDict
+from typing import List, Tuple
+
+import numpy as np
+import torch
+
+from .config import EncoderDims, SIFNetDims
+
+Spec = List[Tuple[str, Tuple[int, ...], str]]   # (key, shape, kind) kind in {conv_w, bias, gn_w, gn_b}
+
+
+def _convblock_spec(prefix: str, cin: int, cout: int) -> Spec:
+    """Keys of one ``ConvBlock`` in ``state_dict()`` order (model/net_util.py:346-372): three bias-free
+    3x3 convs, four GroupNorms (``bn4`` exists even when unused) and, when cin != cout, a ``downsample``
+    Sequential that re-lists ``bn4`` as ``downsample.0`` followed by a bias-free 1x1 conv."""
+    half, quarter = cout // 2, cout // 4
+    s: Spec = [
+        (f"{prefix}.conv1.weight", (half, cin, 3, 3), "conv_w"),
+        (f"{prefix}.conv2.weight", (quarter, half, 3, 3), "conv_w"),
+        (f"{prefix}.conv3.weight", (quarter, quarter, 3, 3), "conv_w"),
+    ]
+    for name, c in (("bn1", cin), ("bn2", half), ("bn3", quarter), ("bn4", cin)):
+        s += [(f"{prefix}.{name}.weight", (c,), "gn_w"), (f"{prefix}.{name}.bias", (c,), "gn_b")]
+    if cin != cout:
+        s += [(f"{prefix}.downsample.0.weight", (cin,), "alias:" + f"{prefix}.bn4.weight"),
+              (f"{prefix}.downsample.0.bias", (cin,), "alias:" + f"{prefix}.bn4.bias"),
+              (f"{prefix}.downsample.2.weight", (cout, cin, 1, 1), "conv_w")]
+    return s
+
+
+def _hourglass_spec(prefix: str, level: int, ch: int) -> Spec:
+    """``HourGlass._generate_network`` registration order (model/HGFilters.py:14-24)."""
+    s = _convblock_spec(f"{prefix}.b1_{level}", ch, ch) + _convblock_spec(f"{prefix}.b2_{level}", ch, ch)
+    if level > 1:
+        s += _hourglass_spec(prefix, level - 1, ch)
+    else:
+        s += _convblock_spec(f"{prefix}.b2_plus_{level}", ch, ch)
+    s += _convblock_spec(f"{prefix}.b3_{level}", ch, ch)
+    return s
+
+
+def encoder_spec(prefix: str, d: EncoderDims) -> Spec:
+    """``HGFilter.__init__`` registration order (model/HGFilters.py:118-160)."""
+    f = d.feat_ch
+    s: Spec = [(f"{prefix}.conv1.weight", (d.stem_ch, d.in_ch, 7, 7), "conv_w"),
+               (f"{prefix}.conv1.bias", (d.stem_ch,), "bias"),
+               (f"{prefix}.bn1.weight", (d.stem_ch,), "gn_w"), (f"{prefix}.bn1.bias", (d.stem_ch,), "gn_b")]
+    s += _convblock_spec(f"{prefix}.conv2", d.stem_ch, 128)
+    s += _convblock_spec(f"{prefix}.conv3", 128, 128)
+    s += _convblock_spec(f"{prefix}.conv4", 128, f)
+    for i in range(d.num_stack):
+        s += _hourglass_spec(f"{prefix}.m{i}", d.depth, f)
+        s += _convblock_spec(f"{prefix}.top_m_{i}", f, f)
+        s += [(f"{prefix}.conv_last{i}.weight", (f, f, 1, 1), "conv_w"), (f"{prefix}.conv_last{i}.bias", (f,), "bias"),
+              (f"{prefix}.bn_end{i}.weight", (f,), "gn_w"), (f"{prefix}.bn_end{i}.bias", (f,), "gn_b"),
+              (f"{prefix}.l{i}.weight", (d.out_ch, f, 1, 1), "conv_w"), (f"{prefix}.l{i}.bias", (d.out_ch,), "bias")]
+        if i < d.num_stack - 1:
+            s += [(f"{prefix}.bl{i}.weight", (f, f, 1, 1), "conv_w"), (f"{prefix}.bl{i}.bias", (f,), "bias"),
+                  (f"{prefix}.al{i}.weight", (f, d.out_ch, 1, 1), "conv_w"), (f"{prefix}.al{i}.bias", (f,), "bias")]
+    return s
+
+
+# decoder heads in module-registration order: CHORE.__init__ creates df, part, pca, center
+# (model/chore.py:72-79); init_others re-assigns center_predictor in place and appends visib_predictor
+# (model/chore_tri_vis.py:17-28).  Output widths: df 2, parts 14, pca 9, centers 3, visibility 1.
+DECODER_HEADS = (("df", 2), ("part_predictor", None), ("pca_predictor", 9), ("center_predictor", 3),
+                 ("visib_predictor", 1))
+
+
+def decoder_spec(dims: SIFNetDims) -> Spec:
+    s: Spec = []
+    h = dims.hidden
+    for name, out in DECODER_HEADS:
+        out = dims.num_parts if out is None else out
+        for idx, (co, ci) in zip((0, 2, 4, 6), ((h, dims.feature_size), (h, h), (h, h), (out, h))):
+            s += [(f"{name}.{idx}.weight", (co, ci, 1), "conv_w"), (f"{name}.{idx}.bias", (co,), "bias")]
+    return s
+
+
+def sifnet_spec(dims: SIFNetDims) -> Spec:
+    """All 706 ``CHORETriplaneVisibility.state_dict()`` entries for tri-vis-l2, in order."""
+    return encoder_spec("image_filter", dims.rgb) + decoder_spec(dims) + encoder_spec("triplane_encoder", dims.tri)
+
+
+def synthetic_state_dict(dims: SIFNetDims, seed: int = 0, plain_init: bool = False) -> "OrderedDict[str, torch.Tensor]":
+    """Random checkpoint with the reference's key set.
+
+    ``plain_init=True`` reproduces the *distribution* of ``init_weights`` (N(0, 0.02) weights, zero biases,
+    identity GroupNorm affine; model/net_util.py:230-244).  The default additionally randomises biases and
+    GroupNorm affines so that a kernel that drops one of them cannot pass parity.
+    """
+    rng = np.random.Generator(np.random.PCG64(seed))
+    sd: "OrderedDict[str, torch.Tensor]" = OrderedDict()
+    for key, shape, kind in sifnet_spec(dims):
+        if kind.startswith("alias:"):
+            sd[key] = sd[kind[6:]]
+            continue
+        if kind == "conv_w":
+            a = rng.standard_normal(shape, dtype=np.float32) * np.float32(0.02)
+        elif kind == "bias":
+            a = np.zeros(shape, np.float32) if plain_init else rng.standard_normal(shape, dtype=np.float32) * np.float32(0.05)
+        elif kind == "gn_w":
+            a = np.ones(shape, np.float32) if plain_init else (1 + rng.standard_normal(shape, dtype=np.float32) * np.float32(0.1))
+        elif kind == "gn_b":
+            a = np.zeros(shape, np.float32) if plain_init else rng.standard_normal(shape, dtype=np.float32) * np.float32(0.1)
+        else:
+            raise AssertionError(kind)
+        sd[key] = torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32))
+    return sd
+
+
+def synthetic_frames(batch: int, size: int = 512, seed: int = 0, n_points: int = 2000, jitter: bool = False):
+    """Seeded inputs of SURVEY.md section 8(d): ``images [B,8,S,S]`` with channels 3-7 binarised and RGB masked
+    by (person OR object); query points uniform in the generator's 2 x 3 x 1.2 m box around the body centre
+    (recon/gen/generator_triplane.py:46-53); ``crop_center`` in 2048x1536 pixel space; ``body_center``.
+    """
+    rng = np.random.Generator(np.random.PCG64(seed))
+    img = rng.random((batch, 8, size, size), dtype=np.float32)
+    img[:, 3:] = (img[:, 3:] > 0.5).astype(np.float32)
+    img[:, :3] *= np.maximum(img[:, 3:4], img[:, 4:5])
+    crop = np.tile(np.array([[1024.0, 768.0]], np.float32), (batch, 1))
+    body = np.tile(np.array([[0.0, 0.0, 2.2]], np.float32), (batch, 1))
+    if jitter:
+        crop += rng.uniform(-100, 100, (batch, 2)).astype(np.float32)
+        body += (rng.uniform(-1, 1, (batch, 3)) * np.array([0.3, 0.2, 0.2])).astype(np.float32)
+    pts = rng.random((batch, n_points, 3), dtype=np.float32)
+    pts = pts * np.array([2.0, 3.0, 1.2], np.float32) - np.array([1.0, 1.5, 0.6], np.float32) + body[:, None, :]
+    return (torch.from_numpy(img), torch.from_numpy(pts.astype(np.float32)), torch.from_numpy(crop),
+            torch.from_numpy(body))
