@@ -1,0 +1,95 @@
+/* vistracker_b200 -- C ABI of libvistracker_sm100a.so
+ *
+ * Drop-in boundary for the VisTracker per-frame hot path on NVIDIA B200 (sm_100a).  The reference (xiexh20/VisTracker)
+ * is pure Python over PyTorch; the operators below are what its Python call sites would bind (ctypes stub in
+ * INTEGRATION.md).  Each entry names the reference interface it replaces.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless it says "host"; fp32 unless stated; tensors are NHWC, channel stride
+ *     ("ld*", in elements) given explicitly so channel slices of a wider tensor can be read / written in place;
+ *   - the library never allocates, frees or synchronises device memory: the caller (PyTorch) owns inputs, outputs and
+ *     scratch; kernels are enqueued on `stream` (a cudaStream_t passed as void*; NULL = legacy default stream);
+ *   - return value 0 = enqueued, < 0 = rejected (nothing enqueued); vt_last_error() gives the reason.  No exceptions cross
+ *     the ABI.  Re-entrant; no global mutable state besides the per-thread error string;
+ *   - `stats` arguments: double[n_img][ld_stats][2] per-channel (sum, sum of squares) of the tensor the call WRITES,
+ *     accumulated with atomics (caller zeroes the slot first).  vt_gn_finalize turns them into the GroupNorm affine.
+ */
+#ifndef VISTRACKER_B200_H
+#define VISTRACKER_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- library ---------------------------------------------------------------------------------------------------- */
+const char* vt_last_error(void);          /* host string, valid until the next failing call on this thread */
+int vt_version(void);                     /* ABI version, currently 1 */
+int vt_compiled_arch(void);               /* 100 -> built with -gencode arch=compute_100a,code=sm_100a */
+
+/* ---- stacked-hourglass encoder pieces: model/HGFilters.py:162-203 (HGFilter.forward), :26-50 (HourGlass._forward),
+ *      model/net_util.py:374-396 (ConvBlock.forward) ------------------------------------------------------------------ */
+
+/* conv1 of HGFilter: nn.Conv2d(cin, cout, 7, stride 2, padding 3, bias) (HGFilters.py:120,167) read directly from the
+ * NCHW frame tensor images[B][Ctot][Hin][Win].  Encoder image n = view*B + b uses channels c_off + view*cin + [0,cin).
+ * w: [49*cin][cout] (tap-major, then input channel), out: NHWC [B*n_views][Hin/2][Win/2][cout]. */
+int vt_stem_conv7x7s2(const float* images, int B, int Ctot, int Hin, int Win, int c_off, int cin, int n_views, const float* w,
+                      const float* bias, int cout, float* out, double* stats, int ld_stats, void* stream);
+
+/* nn.GroupNorm(groups, C) statistics -> per-(image, channel) scale/shift so that GN(x) = x*scale + shift
+ * (net_util.py:358-362; eps inside the sqrt, biased variance).  count_per_channel = H*W. */
+int vt_gn_finalize(const double* stats, int ld_stats, const float* gamma, const float* beta, int n_img, int C, int groups,
+                   long long count_per_channel, float eps, float* scale, float* shift, void* stream);
+
+/* out = relu?(x*scale + shift) in fp32 (F.relu(self.bn1(self.conv1(x)), True), HGFilters.py:167).  scale may be NULL. */
+int vt_affine_act(const float* x, int ldx, const float* scale, const float* shift, int relu, int n_img, int HW, int C,
+                  float* out, int ldo, double* stats, int ld_stats, void* stream);
+
+/* GroupNorm-apply + ReLU + fp16 (hi, lo*2^11) split into zero-bordered planes [n][H+2pad][W+2pad][Cpad] (fp16) that
+ * vt_conv_mma consumes.  *overflow is incremented if any |value| exceeded the fp16 range (the caller must then fail). */
+int vt_prep_split(const float* x, int ldx, const float* scale, const float* shift, int relu, int n_img, int H, int W, int C,
+                  int Cpad, int pad, void* hi, void* lo, int* overflow, void* stream);
+
+/* conv3x3 (padding 1, net_util.py:213-216) / 1x1 conv on the tcgen05 tensor cores.  a_hi/a_lo from vt_prep_split,
+ * w_hi/w_lo: fp16 planes [ks*ks][Cout][Cin_pad].  out[pix][0..Cout) = conv + bias + res[pix][0..Cout); res may alias out.
+ * Needs W in {8,16,32,64} or a multiple of 128, and H a multiple of 128/min(W,128). */
+int vt_conv_mma(const void* a_hi, const void* a_lo, int n_img, int H, int W, int Cin_pad, int pad, int ks, const void* w_hi,
+                const void* w_lo, int Cout, const float* bias, const float* res, int ldr, float* out, int ldo, double* stats,
+                int ld_stats, void* stream);
+
+/* Same contract on the fp32 CUDA cores with the GroupNorm affine + ReLU fused into the load: any H, W; w: fp32
+ * [ks*ks][Cin][Cout].  Used where the 128-pixel tensor-core tile does not fit, and as the on-device cross-check. */
+int vt_conv_ffma(const float* x, int ldx, const float* scale, const float* shift, int relu, int n_img, int H, int W, int Cin,
+                 int ks, const float* w, int Cout, const float* bias, const float* res, int ldr, float* out, int ldo,
+                 double* stats, int ld_stats, void* stream);
+
+/* out = a + b (ConvBlock residual, net_util.py:391-394). */
+int vt_add(const float* a, int lda, const float* b, int ldb, int n_img, int HW, int C, float* out, int ldo, double* stats,
+           int ld_stats, void* stream);
+
+/* F.avg_pool2d(x, 2, stride=2) (HGFilters.py:32,170). */
+int vt_avgpool2(const float* x, int n_img, int H, int W, int C, float* out, double* stats, int ld_stats, void* stream);
+
+/* out = up1 + F.interpolate(low, scale_factor=2, mode='bicubic', align_corners=True) (HGFilters.py:47-50). */
+int vt_upsample2x_add(const float* low, const float* up1, int n_img, int Hl, int Wl, int C, float* out, double* stats,
+                      int ld_stats, void* stream);
+
+/* ---- point query: CHORETriplane.query / query_features + CHORETriplaneVisibility.decode
+ *      (model/chore_triplane.py:97-205, model/chore_tri_vis.py:31-50, model/geometry.py:4-14, model/camera.py:45-89) ------ */
+
+/* number of floats of the packed decoder weights (layout in csrc/query.cu, packer in vistracker_b200/weights.py) */
+long long vt_query_wpack_floats(void);
+
+/* points[B][N][3], crop_center[B][2], body_center[B][3]; maps NHWC: im_feat[B][Hf][Wf][c_im], tmpx[B][Ht][Wt][c_tmpx],
+ * tri_tmpx[3][B][Ht][Wt][c_tt], tri_feat[3][B][Hf][Wf][c_tf] (views right, back, top);
+ * cam7 (host) = {fx_px, fy_px, cx_px, cy_px, crop_size, z0, out_dist}.
+ * out[B][29][N] = df 2 | pca 9 | parts 14 | centers 3 | visibility 1 (sigmoid applied, df = out_dist outside the image);
+ * feat_out[B][611][N] (reference channel order) and xy_out[B][2][N] are optional (NULL to skip). */
+int vt_query_fwd(const float* points, const float* crop_center, const float* body_center, int B, int N,
+                 const float* im_feat, const float* tmpx, const float* tri_tmpx, const float* tri_feat, int Hf, int Wf, int Ht,
+                 int Wt, int c_im, int c_tmpx, int c_tt, int c_tf, const float* cam7, const float* wpack, float* out,
+                 float* feat_out, float* xy_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VISTRACKER_B200_H */

@@ -1,0 +1,65 @@
+"""The tcgen05 convolution against fp64 F.conv2d and against the CUDA-core kernel on the same device."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import rel_err
+from test_gpu_ops import chan_stats, dev, nchw, nhwc
+
+pytestmark = pytest.mark.gpu
+
+CASES = [  # ks, cin, cout, n, H, W
+    (1, 64, 32, 1, 32, 32),
+    (3, 64, 64, 2, 32, 32),
+    (3, 32, 32, 1, 64, 64),
+    (3, 128, 64, 2, 64, 64),
+    (3, 256, 128, 1, 128, 128),
+    (1, 256, 256, 1, 128, 128),
+    (3, 64, 64, 1, 8, 256),
+    (1, 128, 256, 3, 16, 16),
+]
+
+
+@pytest.mark.parametrize("ks,cin,cout,n,H,W", CASES)
+def test_conv_mma_matches_fp64(ks, cin, cout, n, H, W):
+    from vistracker_b200 import ops
+    g = torch.Generator().manual_seed(ks * 7919 + cin * 31 + cout + H)
+    x = torch.randn(n, cin, H, W, generator=g)
+    w = torch.randn(cout, cin, ks, ks, generator=g) * 0.05
+    bias = torch.randn(cout, generator=g)
+    res = torch.randn(n, cout, H, W, generator=g)
+    gamma, beta = torch.randn(cin, generator=g), torch.randn(cin, generator=g)
+    sc, sh = ops.gn_finalize(chan_stats(x).to(dev()), gamma.to(dev()), beta.to(dev()), H * W)
+    planes, ovf = ops.prep_split(nhwc(x), sc, sh, True, ks // 2)
+    st = ops.new_stats(n, cout, dev())
+    out = ops.conv_mma(planes, H, W, ks // 2, w, bias.to(dev()), nhwc(res), stats=st)
+    torch.cuda.synchronize()
+    assert int(ovf.item()) == 0
+    a = F.relu(F.group_norm(x.double(), 32, gamma.double(), beta.double(), 1e-5))
+    ref = F.conv2d(a, w.double(), bias.double(), padding=ks // 2) + res.double()
+    assert rel_err(nchw(out), ref) < 5e-6
+    assert rel_err(st.cpu(), chan_stats(ref)) < 1e-5
+    ffma = ops.conv_ffma(nhwc(x), sc, sh, True, w, bias.to(dev()), nhwc(res))
+    assert rel_err(out.cpu(), ffma.cpu()) < 5e-6
+
+
+def test_conv_mma_slice_and_inplace_residual():
+    from vistracker_b200 import ops
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(1, 64, 32, 32, generator=g)
+    w = torch.randn(64, 64, 3, 3, generator=g) * 0.05
+    planes, _ = ops.prep_split(nhwc(x), None, None, False, 1)
+    wide = torch.randn(1, 32, 32, 128, generator=g).to(dev())
+    keep = wide.clone()
+    ops.conv_mma(planes, 32, 32, 1, w, None, wide[..., 64:], out=wide[..., 64:])
+    ref = F.conv2d(x.double(), w.double(), padding=1) + keep[..., 64:].permute(0, 3, 1, 2).double().cpu()
+    assert rel_err(nchw(wide[..., 64:]), ref) < 5e-6
+    assert torch.equal(wide[..., :64], keep[..., :64])
+
+
+def test_conv_mma_rejects_untileable_shapes():
+    from vistracker_b200 import ops
+    x = torch.zeros(1, 12, 12, 64, device=dev())
+    planes, _ = ops.prep_split(x, None, None, False, 1)
+    with pytest.raises(RuntimeError, match="vt_conv_mma"):
+        ops.conv_mma(planes, 12, 12, 1, torch.zeros(64, 64, 3, 3))

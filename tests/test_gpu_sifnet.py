@@ -1,0 +1,98 @@
+"""SIF-Net filter + query on the B200 through the reference-shaped API, against the reference golden vectors
+(tests/golden, produced by the unmodified reference) and against the CPU oracle on fresh seeded inputs.
+
+Tolerance: north_star asks for 1e-4 relative; ``rel_err`` is max|a-b| / max|b| per tensor."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import rel_err
+from oracle import sifnet_ref as R
+from vistracker_b200 import CHORETriplaneVisibility, default_options, resolve_dims
+from vistracker_b200.synth import synthetic_frames, synthetic_state_dict
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+DIMS = resolve_dims(default_options())
+CAM = (DIMS.fx_px, DIMS.fy_px, DIMS.cx_px, DIMS.cy_px, DIMS.crop_size)
+
+
+@pytest.fixture(scope="module")
+def net():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    m = CHORETriplaneVisibility(default_options(), device="cuda:0").eval()
+    m.load_state_dict(synthetic_state_dict(DIMS, seed=0))
+    return m
+
+
+def _maps_nchw(net):
+    return {"im_feat": net.im_feat_list[0], "tmpx": net.tmpx,
+            **{f"tri_feat{v}": net.triplane_feat_list[v][0] for v in range(3)},
+            **{f"tri_tmpx{v}": net.triplane_tmpx[v] for v in range(3)}}
+
+
+def _check_heads(net, g):
+    for name, o in zip(("df", "pca", "parts", "centers", "vis"), net.get_preds()):
+        assert tuple(o.shape) == g[name].shape, name
+        assert rel_err(o.cpu(), g[name]) < TOL, name
+
+
+def test_small_frames_match_reference_golden(net, golden):
+    """64x64 frames: feature maps are too small for 128-pixel tensor-core tiles -> exercises the CUDA-core conv path."""
+    g = golden("sifnet_small.npz")
+    images, points, crop, body = synthetic_frames(2, size=64, seed=11, n_points=301, jitter=True)
+    net.filter(images.cuda())
+    for k, v in _maps_nchw(net).items():
+        assert rel_err(v.cpu(), g[k]) < TOL, k
+    net.query(points.cuda(), crop_center=crop.cuda(), body_center=body.cuda())
+    _check_heads(net, g)
+    assert rel_err(net.points_xy.cpu(), g["xy"]) < 1e-6
+    feat, xy = net.query_features(points.cuda(), crop.cuda(), body_center=body.cuda())
+    assert rel_err(feat.cpu(), g["features"]) < TOL
+    out_of_img = (np.abs(g["xy"]) > 1).any(1)
+    assert out_of_img.any()
+    assert (net.get_preds()[0].cpu().numpy().transpose(0, 2, 1)[out_of_img] == 5.0).all()
+
+
+def test_config1_matches_reference_golden(net, golden):
+    """BASELINE config 1: one 512x512 frame + 2000 points; tcgen05 convolutions everywhere past the stem."""
+    g = golden("sifnet_c1.npz")
+    images, points, crop, body = synthetic_frames(1, size=512, seed=0, n_points=2000)
+    net.filter(images.cuda())
+    for k, v in _maps_nchw(net).items():
+        assert rel_err(v[:, :, ::8, ::8].cpu(), g[k]) < TOL, k
+    net.query(points.cuda(), crop_center=crop.cuda(), body_center=body.cuda())
+    _check_heads(net, g)
+
+
+def test_batch_matches_oracle(net):
+    """B=2 at full resolution with jittered crops / body centres against the CPU oracle (fresh seed, no golden)."""
+    sd = synthetic_state_dict(DIMS, seed=0)
+    images, points, crop, body = synthetic_frames(2, size=512, seed=21, n_points=1500, jitter=True)
+    with torch.no_grad():
+        maps = R.sif_filter(sd, images)
+        ref = R.sif_query(sd, maps, points, crop, body, CAM)
+    net.filter(images.cuda())
+    assert rel_err(net.im_feat_list[0].cpu(), maps["im_feat"]) < TOL
+    assert rel_err(net.tmpx.cpu(), maps["tmpx"]) < TOL
+    for v in range(3):
+        assert rel_err(net.triplane_feat_list[v][0].cpu(), maps["tri_feat"][v]) < TOL
+        assert rel_err(net.triplane_tmpx[v].cpu(), maps["tri_tmpx"][v]) < TOL
+    net.query(points.cuda(), crop_center=crop.cuda(), body_center=body.cuda())
+    for o, r in zip(net.get_preds(), ref):
+        assert rel_err(o.cpu(), r) < TOL
+
+
+def test_query_edge_cases(net):
+    images, points, crop, body = synthetic_frames(1, size=64, seed=3, n_points=33)
+    net.filter(images.cuda())
+    # N not a multiple of the 32-point tile, N = 1, and points behind / on the camera plane
+    for n in (33, 1):
+        net.query(points[:, :n].cuda(), crop_center=crop.cuda(), body_center=body.cuda())
+        assert net.get_preds()[0].shape == (1, 2, n)
+    bad = points[:, :4].clone(); bad[0, 0, 2] = 0.0; bad[0, 1, 2] = -1.0
+    net.query(bad.cuda(), crop_center=crop.cuda(), body_center=body.cuda())
+    assert torch.isfinite(net.get_preds()[2]).all()
+    with pytest.raises(ValueError):
+        net.query(points.repeat(2, 1, 1).cuda(), crop_center=crop.cuda(), body_center=body.cuda())

@@ -1,0 +1,65 @@
+"""ctypes binding of libvistracker_sm100a.so (the C ABI declared in include/vistracker_b200.h).
+
+There is no fallback: if the library is missing or a call is rejected, a RuntimeError is raised.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libvistracker_sm100a.so")
+
+_p, _i, _f, _ll = C.c_void_p, C.c_int, C.c_float, C.c_longlong
+
+# name -> (restype, argtypes); must list every symbol of include/vistracker_b200.h (tests/test_cabi.py checks both ways)
+SIGNATURES = {
+    "vt_last_error": (C.c_char_p, []),
+    "vt_version": (_i, []),
+    "vt_compiled_arch": (_i, []),
+    "vt_stem_conv7x7s2": (_i, [_p, _i, _i, _i, _i, _i, _i, _i, _p, _p, _i, _p, _p, _i, _p]),
+    "vt_gn_finalize": (_i, [_p, _i, _p, _p, _i, _i, _i, _ll, _f, _p, _p, _p]),
+    "vt_affine_act": (_i, [_p, _i, _p, _p, _i, _i, _i, _i, _p, _i, _p, _i, _p]),
+    "vt_prep_split": (_i, [_p, _i, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p]),
+    "vt_conv_mma": (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _p, _p, _i, _p, _p, _i, _p, _i, _p, _i, _p]),
+    "vt_conv_ffma": (_i, [_p, _i, _p, _p, _i, _i, _i, _i, _i, _i, _p, _i, _p, _p, _i, _p, _i, _p, _i, _p]),
+    "vt_add": (_i, [_p, _i, _p, _i, _i, _i, _i, _p, _i, _p, _i, _p]),
+    "vt_avgpool2": (_i, [_p, _i, _i, _i, _i, _p, _p, _i, _p]),
+    "vt_upsample2x_add": (_i, [_p, _p, _i, _i, _i, _i, _p, _p, _i, _p]),
+    "vt_query_wpack_floats": (_ll, []),
+    "vt_query_fwd": (_i, [_p, _p, _p, _i, _i, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p]),
+}
+
+_lib = None
+
+
+def load():
+    """Load the shared library (building is the job of __graft_entry__.build / vistracker_b200.build)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(f"{LIB_PATH} is missing: run `python -m vistracker_b200.build` (there is no CPU fallback)")
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype, fn.argtypes = res, args
+        _lib = lib
+    return _lib
+
+
+def call(name: str, *args):
+    """Invoke an int-returning entry point and raise on rejection."""
+    lib = load()
+    rc = getattr(lib, name)(*args)
+    if rc != 0:
+        raise RuntimeError(f"{name} failed ({rc}): {lib.vt_last_error().decode()}")
+
+
+def ptr(t):
+    """Device pointer of a torch tensor (None -> NULL)."""
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def stream_ptr():
+    import torch
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)

@@ -1,0 +1,344 @@
+// tcgen05 implicit-GEMM convolution (3x3 / 1x1, stride 1) for the stacked-hourglass encoder
+// (model/net_util.py:374-396, model/HGFilters.py:26-50,186-201) -- the dense contraction that is 99.7 % of `filter`.
+//
+// Precision scheme ("fp16x2, 3 MMA"): the reference computes in fp32 and north_star asks for 1e-4 relative parity, which
+// a single fp16/bf16/tf32 pass cannot give (10-bit mantissas -> ~1e-3).  Both operands are therefore pre-split into two
+// fp16 planes, x = hi + lo * 2^-11 with lo scaled back into the normal fp16 range, and each K-step issues three
+// kind::f16 MMAs into two fp32 TMEM accumulators:
+//        acc0 += A_hi * B_hi          acc1 += A_hi * B_lo + A_lo * B_hi          D = acc0 + acc1 * 2^-11
+// (the dropped lo*lo term is 2^-22 relative).  That is 22 mantissa bits at 3/2 the cost of one tf32 pass and half its
+// operand bytes.
+//
+// Data layout: activations live in zero-bordered NHWC fp16 planes [n, H+2p, W+2p, Cpad] written by prep_split_kernel
+// (GroupNorm-apply + ReLU + split fused there).  An output tile is 128 consecutive pixels (bw = min(W,128) columns x
+// bh = 128/bw rows), so for filter tap (dy, dx) the A tile is one contiguous TMA box {64 ch, bw, bh} at (x0+dx, y0+dy)
+// of the padded plane -- no im2col materialisation, the halo is the zero border.  Weights are [tap][Cout][Cin_pad]
+// fp16 planes, B tile = TMA box {64, BN}.  Both land in shared memory in the 128-byte-swizzled K-major layout the UMMA
+// descriptors expect.
+//
+// Roles (192 threads): warps 0-3 epilogue (one TMEM lane = one output pixel each), warp 4 TMA producer, warp 5 MMA
+// issuer.  One output tile per CTA; STAGES-deep mbarrier ring between TMA and MMA.
+#include <cuda.h>
+#include "common.cuh"
+#include "vt_internal.h"
+
+namespace vt {
+
+constexpr int MM_M = 128;       // pixels per tile == UMMA_M == TMEM lanes
+constexpr int MM_KC = 64;       // fp16 channels per K chunk = one 128-byte swizzle row
+constexpr int MM_THREADS = 192;
+
+struct ConvMmaParams {
+  int H, W, pad, ks, kchunks;   // kchunks = Cin_pad / 64
+  int bw, bh, tiles_x;
+  int cout_total;               // rows per tap in the packed weight planes
+  const float* bias; const float* res; int ldr;
+  float* out; int ldo;
+  double* stats; int ld_stats;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug must trap (-> cudaErrorLaunchFailure reported to the caller), never hang the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) { printf("vt conv_mma: mbarrier timeout (block %d,%d,%d thread %d)\n", blockIdx.x, blockIdx.y, blockIdx.z, threadIdx.x); __trap(); }
+  }
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+               ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+               ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem], kind::f16, M=128, single CTA
+__device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// K-major, 128-byte swizzle shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, mma_sm100_desc.hpp): start address
+// >> 4 in bits [0,14), leading byte offset (unused for swizzled K-major, canonical value 1) in [16,30), stride byte offset =
+// 1024 B (one 8-row swizzle atom) >> 4 in [32,46), descriptor version 1 in [46,48), layout type SWIZZLE_128B = 2 in [61,64).
+__device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+template <int BN>
+struct MmaCfg {
+  static constexpr int STAGES = BN == 128 ? 3 : 4;
+  static constexpr int A_BYTES = MM_M * MM_KC * 2;                 // 16 KB per plane
+  static constexpr int B_BYTES = BN * MM_KC * 2;
+  static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024;   // + alignment slack
+  static constexpr int TMEM_COLS = 2 * BN;                         // acc0 | acc1, power of two >= 64
+  // cute::UMMA::InstrDescriptor: c_format F32 (1) @4, a/b format F16 (0) @7/@10, K-major both, N>>3 @17, M>>4 @24
+  static constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(MM_M >> 4) << 24);
+};
+
+template <int BN>
+__global__ void __launch_bounds__(MM_THREADS, 1)
+conv_mma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
+                const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo, const ConvMmaParams p) {
+  using Cfg = MmaCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bar_full[Cfg::STAGES], bar_empty[Cfg::STAGES], bar_accum;
+  __shared__ uint32_t s_tmem_base;
+  __shared__ float s_sum[BN], s_sq[BN];
+
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int img = blockIdx.y, n0 = blockIdx.z * BN;
+  const int tile_y = blockIdx.x / p.tiles_x, tile_x = blockIdx.x % p.tiles_x;
+  const int y0 = tile_y * p.bh, x0 = tile_x * p.bw;
+  const int n_iter = p.ks * p.ks * p.kchunks;
+
+  if (threadIdx.x < BN) { s_sum[threadIdx.x] = 0.f; s_sq[threadIdx.x] = 0.f; }
+  if (warp == 5 && lane == 0) {
+    for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(smem_u32(&bar_full[s]), 1); mbar_init(smem_u32(&bar_empty[s]), 1); }
+    mbar_init(smem_u32(&bar_accum), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 4 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_a_hi) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_a_lo) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_b_hi) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_b_lo) : "memory");
+  }
+  if (warp == 0) {   // TMEM allocation is warp-wide; the same warp frees it at the end
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem_base)), "r"((uint32_t)Cfg::TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = s_tmem_base;
+
+  if (warp == 4) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      const int row0 = img * (p.H + 2 * p.pad) + y0;
+      for (int it = 0; it < n_iter; ++it) {
+        const int s = it % Cfg::STAGES;
+        const uint32_t ph = (uint32_t)(it / Cfg::STAGES) & 1u;
+        mbar_wait(smem_u32(&bar_empty[s]), ph ^ 1u);
+        const uint32_t full = smem_u32(&bar_full[s]);
+        mbar_expect_tx(full, Cfg::STAGE_BYTES);
+        const int tap = it / p.kchunks, kc = it % p.kchunks;
+        const int dy = tap / p.ks, dx = tap % p.ks;
+        const uint32_t sa = smem_base + s * Cfg::STAGE_BYTES;
+        tma_load_3d(sa, &tm_a_hi, full, kc * MM_KC, x0 + dx, row0 + dy);
+        tma_load_3d(sa + Cfg::A_BYTES, &tm_a_lo, full, kc * MM_KC, x0 + dx, row0 + dy);
+        tma_load_2d(sa + 2 * Cfg::A_BYTES, &tm_b_hi, full, kc * MM_KC, tap * p.cout_total + n0);
+        tma_load_2d(sa + 2 * Cfg::A_BYTES + Cfg::B_BYTES, &tm_b_lo, full, kc * MM_KC, tap * p.cout_total + n0);
+      }
+    }
+  } else if (warp == 5) {
+    // ------------------------------------------------------------------ MMA issuer (one thread)
+    if (lane == 0) {
+      const uint32_t acc0 = tmem_base, acc1 = tmem_base + BN;
+      for (int it = 0; it < n_iter; ++it) {
+        const int s = it % Cfg::STAGES;
+        const uint32_t ph = (uint32_t)(it / Cfg::STAGES) & 1u;
+        mbar_wait(smem_u32(&bar_full[s]), ph);
+        tc_fence_after();
+        const uint32_t sa = smem_base + s * Cfg::STAGE_BYTES;
+        const uint64_t a_hi = make_kmajor_sw128_desc(sa), a_lo = make_kmajor_sw128_desc(sa + Cfg::A_BYTES);
+        const uint64_t b_hi = make_kmajor_sw128_desc(sa + 2 * Cfg::A_BYTES), b_lo = make_kmajor_sw128_desc(sa + 2 * Cfg::A_BYTES + Cfg::B_BYTES);
+#pragma unroll
+        for (int k = 0; k < MM_KC / 16; ++k) {
+          const uint64_t adv = (uint64_t)(k * 32 >> 4);          // 16 fp16 = 32 bytes along K inside the swizzle row
+          const uint32_t accum = (it | k) != 0;
+          tc_mma_f16(acc0, a_hi + adv, b_hi + adv, Cfg::IDESC, accum);
+          tc_mma_f16(acc1, a_hi + adv, b_lo + adv, Cfg::IDESC, accum);
+          tc_mma_f16(acc1, a_lo + adv, b_hi + adv, Cfg::IDESC, 1u);
+        }
+        tc_commit(smem_u32(&bar_empty[s]));       // frees the stage once these MMAs have read it
+      }
+      tc_commit(smem_u32(&bar_accum));            // accumulators complete
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue: TMEM -> registers -> global
+    mbar_wait(smem_u32(&bar_accum), 0);
+    tc_fence_after();
+    const int r = warp * 32 + lane;                               // tile row == TMEM lane
+    const int y = y0 + r / p.bw, x = x0 + r % p.bw;
+    const size_t pix = ((size_t)img * p.H + y) * p.W + x;
+    float* orow = p.out + pix * p.ldo + n0;
+    const float* rrow = p.res ? p.res + pix * p.ldr + n0 : nullptr;
+    const uint32_t lane_base = tmem_base + ((uint32_t)(warp * 32) << 16);
+#pragma unroll 1
+    for (int ch = 0; ch < BN / 32; ++ch) {
+      float v[32], w[32];
+      tc_ld32(lane_base + ch * 32, v);
+      tc_ld32(lane_base + BN + ch * 32, w);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = fmaf(w[i], kLoInv, v[i]);
+      if (p.bias) {
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) { float4 b = ld4(p.bias + n0 + ch * 32 + i); v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w; }
+      }
+      if (rrow) {
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) { float4 b = ld4(rrow + ch * 32 + i); v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w; }
+      }
+#pragma unroll
+      for (int i = 0; i < 32; i += 4) st4(orow + ch * 32 + i, make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]));
+      if (p.stats) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) w[i] = v[i] * v[i];
+        float s = warp_transpose_reduce32(v), q = warp_transpose_reduce32(w);
+        atomicAdd(&s_sum[ch * 32 + lane], s);
+        atomicAdd(&s_sq[ch * 32 + lane], q);
+      }
+    }
+    if (p.stats) {
+      asm volatile("bar.sync 1, 128;" ::: "memory");              // the four epilogue warps only
+      if (threadIdx.x < BN) {
+        double* st = p.stats + ((size_t)img * p.ld_stats + n0 + threadIdx.x) * 2;
+        atomicAdd(st, (double)s_sum[threadIdx.x]);
+        atomicAdd(st + 1, (double)s_sq[threadIdx.x]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)Cfg::TMEM_COLS) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)sym;
+  }
+  return fn;
+}
+
+static int make_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
+                    const cuuint32_t* box) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) { set_error("cuTensorMapEncodeTiled is not available from the driver"); return -2; }
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r); return -2; }
+  return 0;
+}
+
+template <int BN>
+static int launch_conv_mma(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi, const CUtensorMap& b_lo,
+                           const ConvMmaParams& p, dim3 grid, cudaStream_t stream) {
+  using Cfg = MmaCfg<BN>;
+  cudaError_t e = cudaFuncSetAttribute(conv_mma_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+  if (e != cudaSuccess) return cuda_fail(e, "conv_mma smem attr");
+  conv_mma_kernel<BN><<<grid, MM_THREADS, Cfg::SMEM_BYTES, stream>>>(a_hi, a_lo, b_hi, b_lo, p);
+  VT_CHECK_LAUNCH("vt_conv_mma");
+  return 0;
+}
+
+}  // namespace vt
+
+using namespace vt;
+
+extern "C" {
+
+int vt_conv_mma(const void* a_hi, const void* a_lo, int n_img, int H, int W, int Cin_pad, int pad, int ks, const void* w_hi,
+                const void* w_lo, int Cout, const float* bias, const float* res, int ldr, float* out, int ldo, double* stats,
+                int ld_stats, void* stream) {
+  VT_CHECK_ARG(ks == 1 || ks == 3, "vt_conv_mma: kernel size %d", ks);
+  VT_CHECK_ARG(pad == ks / 2, "vt_conv_mma: operand planes must carry a border of %d (got %d)", ks / 2, pad);
+  VT_CHECK_ARG(Cin_pad % MM_KC == 0, "vt_conv_mma: Cin_pad=%d is not a multiple of %d", Cin_pad, MM_KC);
+  VT_CHECK_ARG(Cout == 32 || Cout == 64 || Cout % 128 == 0, "vt_conv_mma: Cout=%d (32, 64 or a multiple of 128)", Cout);
+  int bw = W >= 128 ? 128 : W;
+  VT_CHECK_ARG(W % bw == 0 && 128 % bw == 0 && bw >= 8, "vt_conv_mma: W=%d cannot be tiled into 128-pixel strips", W);
+  int bh = 128 / bw;
+  VT_CHECK_ARG(H % bh == 0, "vt_conv_mma: H=%d is not a multiple of the tile height %d", H, bh);
+  VT_CHECK_ARG(ldo % 4 == 0 && (res == nullptr || ldr % 4 == 0), "vt_conv_mma: channel strides must be multiples of 4");
+  const int BN = Cout >= 128 ? 128 : Cout;
+  const int Hp = H + 2 * pad, Wp = W + 2 * pad;
+
+  CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
+  {
+    cuuint64_t dims[3] = {(cuuint64_t)Cin_pad, (cuuint64_t)Wp, (cuuint64_t)n_img * Hp};
+    cuuint64_t strides[2] = {(cuuint64_t)Cin_pad * 2, (cuuint64_t)Wp * Cin_pad * 2};
+    cuuint32_t box[3] = {(cuuint32_t)MM_KC, (cuuint32_t)bw, (cuuint32_t)bh};
+    int rc = make_map(&ma_hi, a_hi, 3, dims, strides, box); if (rc) return rc;
+    rc = make_map(&ma_lo, a_lo, 3, dims, strides, box); if (rc) return rc;
+  }
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)Cin_pad, (cuuint64_t)ks * ks * Cout};
+    cuuint64_t strides[1] = {(cuuint64_t)Cin_pad * 2};
+    cuuint32_t box[2] = {(cuuint32_t)MM_KC, (cuuint32_t)BN};
+    int rc = make_map(&mb_hi, w_hi, 2, dims, strides, box); if (rc) return rc;
+    rc = make_map(&mb_lo, w_lo, 2, dims, strides, box); if (rc) return rc;
+  }
+  ConvMmaParams p;
+  p.H = H; p.W = W; p.pad = pad; p.ks = ks; p.kchunks = Cin_pad / MM_KC;
+  p.bw = bw; p.bh = bh; p.tiles_x = W / bw; p.cout_total = Cout;
+  p.bias = bias; p.res = res; p.ldr = ldr; p.out = out; p.ldo = ldo; p.stats = stats; p.ld_stats = ld_stats;
+  dim3 grid((H / bh) * (W / bw), n_img, Cout / BN);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (BN == 128) return launch_conv_mma<128>(ma_hi, ma_lo, mb_hi, mb_lo, p, grid, s);
+  if (BN == 64) return launch_conv_mma<64>(ma_hi, ma_lo, mb_hi, mb_lo, p, grid, s);
+  return launch_conv_mma<32>(ma_hi, ma_lo, mb_hi, mb_lo, p, grid, s);
+}
+
+}  // extern "C"

@@ -1,0 +1,230 @@
+"""Drop-in for the reference's SIF-Net object on B200.
+
+``CHORETriplaneVisibility`` below keeps the public surface of ``model.CHORETriplaneVisibility``
+(model/chore_tri_vis.py:16, model/chore_triplane.py:16-251, model/chore.py:17-223, model/BasePIFuNet.py:6-70):
+constructor ``(opt, projection_mode, error_term, rank, num_parts, hidden_dim)``, ``load_state_dict`` with the
+reference's 706 checkpoint keys, ``filter(images)``, ``query(points, crop_center=None, body_center=...)``,
+``query_features``, ``get_preds``, ``project_points``, ``triplane_project``, ``OUT_DIST`` and the cached-map attributes.
+All arithmetic runs in the sm_100a kernels of libvistracker_sm100a.so; there is no PyTorch fallback.
+"""
+from __future__ import annotations
+
+import ctypes
+from collections import OrderedDict
+from typing import Dict, Optional
+
+import torch
+
+from . import _lib
+from .config import SIFNetDims, resolve_dims
+from .encoder import HGEncoder
+from .synth import sifnet_spec
+from .weights import pack_decoders
+
+N_OUT = 29          # df 2 | pca 9 | parts 14 | centers 3 | visibility 1
+
+
+class _QueryFn(torch.autograd.Function):
+    """query() is differentiable w.r.t. the points only (network weights are frozen at inference,
+    recon/gen/generator.py:53-54)."""
+
+    @staticmethod
+    def forward(ctx, net: "CHORETriplaneVisibility", points, crop_center, body_center):
+        out, xy = net._query_raw(points, crop_center, body_center, want_xy=True)
+        ctx.net = net
+        ctx.save_for_backward(points, crop_center, body_center)
+        ctx.mark_non_differentiable(xy)
+        return out, xy
+
+    @staticmethod
+    def backward(ctx, g_out, _g_xy):
+        points, crop_center, body_center = ctx.saved_tensors
+        g_pts = ctx.net._query_backward(points, crop_center, body_center, g_out)
+        return None, g_pts, None, None
+
+
+class CHORETriplaneVisibility:
+    """B200-native SIF-Net (tri-vis).  Not an nn.Module: parameters live as kernel-layout device buffers."""
+
+    def __init__(self, opt, projection_mode="perspective", error_term=None, rank=-1, num_parts=14, hidden_dim=128,
+                 device: Optional[torch.device] = None):
+        if projection_mode != "perspective":
+            raise NotImplementedError("only the perspective camera of the tri-vis model is built")
+        self.opt = opt
+        self.name = "chore"
+        self.dims: SIFNetDims = resolve_dims(opt, num_parts)
+        if self.dims.hidden != 128 or self.dims.feature_size != 611:
+            raise NotImplementedError("the fused decoder kernel is built for hidden_dim=128 and the 611-d tri-vis feature")
+        self.device = torch.device(device) if device is not None else torch.device("cuda", int(getattr(opt, "gpu_id", 0)))
+        self.feature_size, self.hidden_dim, self.z_feat = self.dims.feature_size, self.dims.hidden, opt.z_feat
+        self.shared_encoder = True
+        self.OUT_DIST = self.dims.out_dist
+        self.training = False
+        self._expected = OrderedDict((k, tuple(s)) for k, s, _ in sifnet_spec(self.dims))
+        self._rgb: Optional[HGEncoder] = None
+        self._tri: Optional[HGEncoder] = None
+        self._wpack: Optional[torch.Tensor] = None
+        d = self.dims
+        self._cam7 = (ctypes.c_float * 7)(d.fx_px, d.fy_px, d.cx_px, d.cy_px, d.crop_size, d.z0, d.out_dist)
+        # buffers mirrored from the reference object
+        self._maps = None
+        self.preds = None
+        self.intermediate_preds_list = []
+        self.points = self.points_xy = self.crop_center = self.local_feat_list = self.input_images = None
+        self.defer_checks = False
+
+    # ------------------------------------------------------------------ nn.Module-like surface
+    def to(self, device):
+        self.device = torch.device(device)
+        return self
+
+    def cuda(self, device=None):
+        return self.to(torch.device("cuda", 0 if device is None else device))
+
+    def eval(self):
+        self.training = False
+        return self
+
+    def train(self, mode=True):
+        if mode:
+            raise NotImplementedError("training is outside the B200 hot path (SURVEY.md section 2 row 13)")
+        return self
+
+    def parameters(self):
+        return iter(())            # weights are frozen kernel buffers; nothing for an optimiser to touch
+
+    def load_state_dict(self, sd: Dict[str, torch.Tensor], strict: bool = True):
+        """Accepts the reference checkpoint's ``model_state_dict`` (keys as in tests/golden/sifnet_keys.json; a leading
+        ``module.`` from DataParallel training is stripped like recon/gen/generator.py:296-308 does)."""
+        sd = OrderedDict((k[7:] if k.startswith("module.") else k, v) for k, v in sd.items())
+        missing = [k for k in self._expected if k not in sd]
+        unexpected = [k for k in sd if k not in self._expected]
+        if strict and (missing or unexpected):
+            raise RuntimeError(f"Error(s) in loading state_dict: missing {missing[:5]} unexpected {unexpected[:5]}")
+        for k, shape in self._expected.items():
+            if k in sd and tuple(sd[k].shape) != shape:
+                raise RuntimeError(f"size mismatch for {k}: checkpoint {tuple(sd[k].shape)} vs model {shape}")
+        if self.device.type != "cuda":
+            raise RuntimeError("vistracker_b200 has no CPU path: move the model to a CUDA device before loading weights")
+        _lib.load()
+        with torch.cuda.device(self.device):
+            self._rgb = HGEncoder(sd, "image_filter", self.dims.rgb, self.device)
+            self._tri = HGEncoder(sd, "triplane_encoder", self.dims.tri, self.device)
+            self._wpack = pack_decoders(sd, self.device)
+        assert self._wpack.numel() == _lib.load().vt_query_wpack_floats()
+        return self
+
+    # ------------------------------------------------------------------ filter
+    def filter(self, images: torch.Tensor):
+        """CHORETriplane.filter (model/chore_triplane.py:60-95): images [B, 8, H, W] = RGB, person mask, object mask,
+        3 triplane renderings.  The three triplane views go through the shared encoder as one batch of 3B."""
+        assert images.shape[1] == 8, f"given image shape invalide: {images.shape}"
+        if self._rgb is None:
+            raise RuntimeError("load_state_dict() must be called before filter()")
+        images = images.to(self.device, torch.float32).contiguous()
+        with torch.cuda.device(self.device):
+            im_feat, tmpx = self._rgb.forward(images, 0, 1)
+            tri_feat, tri_tmpx = self._tri.forward(images, 5, 3)
+            if not self.defer_checks:
+                self.check()
+        self.input_images = images
+        self._maps = (im_feat, tmpx, tri_tmpx, tri_feat)
+        self.launches_filter = self._rgb.launches + self._tri.launches
+
+    def check(self):
+        self._rgb.check_overflow()
+        self._tri.check_overflow()
+
+    # reference attribute names, as NCHW-shaped views of the NHWC buffers (no copy)
+    @property
+    def im_feat_list(self):
+        return None if self._maps is None else [self._maps[0].permute(0, 3, 1, 2)]
+
+    @property
+    def tmpx(self):
+        return None if self._maps is None else self._maps[1].permute(0, 3, 1, 2)
+
+    @property
+    def triplane_tmpx(self):
+        if self._maps is None:
+            return None
+        B = self._maps[0].shape[0]
+        return [self._maps[2][v * B:(v + 1) * B].permute(0, 3, 1, 2) for v in range(3)]
+
+    @property
+    def triplane_feat_list(self):
+        if self._maps is None:
+            return None
+        B = self._maps[0].shape[0]
+        return [[self._maps[3][v * B:(v + 1) * B].permute(0, 3, 1, 2)] for v in range(3)]
+
+    def get_im_feat(self):
+        return self.im_feat_list[-1]
+
+    # ------------------------------------------------------------------ query
+    def _query_raw(self, points, crop_center, body_center, want_xy=False, want_feat=False):
+        if self._maps is None:
+            raise RuntimeError("filter() must be called before query()")
+        im_feat, tmpx, tri_tmpx, tri_feat = self._maps
+        B, N = points.shape[0], points.shape[1]
+        if B != im_feat.shape[0]:
+            raise ValueError(f"points batch {B} != filtered batch {im_feat.shape[0]}")
+        pts = points.detach().to(self.device, torch.float32).contiguous()
+        cc = crop_center.to(self.device, torch.float32).contiguous()
+        bc = body_center.to(self.device, torch.float32).contiguous()
+        out = torch.empty(B, N_OUT, N, dtype=torch.float32, device=self.device)
+        xy = torch.empty(B, 2, N, dtype=torch.float32, device=self.device) if want_xy else None
+        feat = torch.empty(B, self.feature_size, N, dtype=torch.float32, device=self.device) if want_feat else None
+        d = self.dims
+        with torch.cuda.device(self.device):
+            _lib.call("vt_query_fwd", _lib.ptr(pts), _lib.ptr(cc), _lib.ptr(bc), B, N, _lib.ptr(im_feat), _lib.ptr(tmpx),
+                      _lib.ptr(tri_tmpx), _lib.ptr(tri_feat), im_feat.shape[1], im_feat.shape[2], tmpx.shape[1], tmpx.shape[2],
+                      d.rgb.out_ch, d.rgb.stem_ch, d.tri.stem_ch, d.tri.out_ch, self._cam7, _lib.ptr(self._wpack), _lib.ptr(out),
+                      _lib.ptr(feat), _lib.ptr(xy), _lib.stream_ptr())
+        if want_feat:
+            return feat, xy
+        return out, xy
+
+    def _query_backward(self, points, crop_center, body_center, g_out):
+        raise NotImplementedError("query backward kernel is not built yet")
+
+    def query(self, points, crop_center=None, **kwargs):
+        """CHORETriplane.query (model/chore_triplane.py:97-164).  Stores ``self.preds`` = (df [B,2,N], pca [B,3,3,N],
+        parts [B,14,N], centers [B,3,N], visibility [B,1,N]); differentiable w.r.t. ``points``."""
+        body_center = kwargs.get("body_center")
+        if crop_center is None or body_center is None:
+            raise ValueError("query() needs crop_center and body_center (model/chore_triplane.py:114,130)")
+        self.points, self.crop_center = points, crop_center
+        if points.requires_grad and torch.is_grad_enabled():
+            out, xy = _QueryFn.apply(self, points, crop_center, body_center)
+        else:
+            out, xy = self._query_raw(points, crop_center, body_center, want_xy=True)
+        B, _, N = out.shape
+        df, pca, parts, centers, vis = out[:, 0:2], out[:, 2:11].reshape(B, 3, 3, N), out[:, 11:25], out[:, 25:28], out[:, 28:29]
+        self.points_xy = xy
+        self.preds = (df, pca, parts, centers, vis)
+        self.intermediate_preds_list = [self.preds]
+        self.local_feat_list = None
+
+    def query_features(self, points, crop_center=None, **kwargs):
+        """CHORETriplane.query_features (model/chore_triplane.py:166-205): ([B, 611, N] features, [B, 2, N] xy)."""
+        return self._query_raw(points, crop_center, kwargs.get("body_center"), want_xy=True, want_feat=True)
+
+    def get_preds(self):
+        return self.preds
+
+    def project_points(self, points, offsets):
+        """KinectColorCamera.project_points (model/camera.py:45-50): [B, 3, N] = (nx, ny, z)."""
+        d = self.dims
+        x, y, z = points[..., 0], points[..., 1], points[..., 2]
+        px = d.crop_size / 2 + (d.fx_px * x / z + d.cx_px) - offsets[:, 0:1]
+        py = d.crop_size / 2 + (d.fy_px * y / z + d.cy_px) - offsets[:, 1:2]
+        return torch.stack([2 * px / d.crop_size - 1, 2 * py / d.crop_size - 1, z], 1)
+
+    @staticmethod
+    def triplane_project(points, body_center, fx=1.0, cx=0.0):
+        """model/chore_triplane.py:220-251."""
+        c = points - body_center[:, None, :]
+        return [torch.stack([c[..., 2] * fx + cx, c[..., 1] * fx + cx], 1),
+                torch.stack([-c[..., 0] * fx + cx, c[..., 1] * fx + cx], 1),
+                torch.stack([c[..., 0] * fx + cx, -c[..., 2] * fx + cx], 1)]

@@ -1,0 +1,74 @@
+"""One-time re-packing of a reference checkpoint (``CHORETriplaneVisibility.state_dict()``, 706 tensors, NCHW conv
+weights; layout table in SURVEY.md section 5) into the layouts the sm_100a kernels read."""
+from __future__ import annotations
+
+from typing import Dict, Tuple
+
+import torch
+
+LO_SCALE = 2048.0          # csrc/common.cuh kLoScale
+MMA_KC = 64                # csrc/conv_mma.cu MM_KC
+
+
+def split_f16(x: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """fp32 -> (hi, lo) fp16 planes with x ~= hi + lo * 2^-11 (same rounding as the device-side split)."""
+    x = x.float()
+    if float(x.abs().max()) > 65504.0:
+        raise ValueError("weight magnitude exceeds the fp16 range; the fp16x2 tensor-core path cannot represent it")
+    hi = x.half()
+    lo = ((x - hi.float()) * LO_SCALE).half()
+    return hi.contiguous(), lo.contiguous()
+
+
+def pack_conv(w: torch.Tensor) -> Dict[str, torch.Tensor]:
+    """Conv2d weight [Cout, Cin, k, k] -> {'ffma': fp32 [k*k, Cin, Cout], 'hi'/'lo': fp16 [k*k, Cout, Cin_pad]}."""
+    cout, cin, kh, kw = w.shape
+    assert kh == kw
+    taps = w.permute(2, 3, 0, 1).reshape(kh * kw, cout, cin).float()          # [tap, Cout, Cin]
+    cin_pad = (cin + MMA_KC - 1) // MMA_KC * MMA_KC
+    padded = torch.zeros(kh * kw, cout, cin_pad, dtype=torch.float32, device=w.device)
+    padded[:, :, :cin] = taps
+    hi, lo = split_f16(padded)
+    return {"ffma": taps.transpose(1, 2).contiguous(), "hi": hi, "lo": lo, "ks": kh, "cin": cin, "cout": cout,
+            "cin_pad": cin_pad}
+
+
+def pack_stem(w: torch.Tensor) -> torch.Tensor:
+    """Conv2d(cin, cout, 7, stride 2) weight [Cout, Cin, 7, 7] -> fp32 [49*Cin, Cout] (tap-major, then input channel)."""
+    cout, cin = w.shape[:2]
+    return w.permute(2, 3, 1, 0).reshape(49 * cin, cout).float().contiguous()
+
+
+# ---- decoder packing (csrc/query.cu) ---------------------------------------------------------------------------
+Q_K, Q_H = 616, 128
+HEADS = ("df", "pca_predictor", "part_predictor", "center_predictor", "visib_predictor")   # output order df|pca|parts|centers|vis
+HEAD_NOUT = (2, 9, 14, 3, 1)
+
+
+def feature_permutation(c_im=256, c_tmpx=64, c_tt=32, c_tf=64) -> torch.Tensor:
+    """internal index -> reference feature index.  Reference order (model/chore_triplane.py:139-151):
+    im_feat | x,y,z-2.2 | tmpx | tri_tmpx r,b,t | tri_feat r | b | t ; internal order moves the 3 scalars to the end."""
+    n_rest = c_tmpx + 3 * c_tt + 3 * c_tf
+    ref = list(range(c_im)) + [c_im + 3 + i for i in range(n_rest)] + [c_im, c_im + 1, c_im + 2]
+    return torch.tensor(ref, dtype=torch.long)
+
+
+def pack_decoders(sd: Dict[str, torch.Tensor], device) -> torch.Tensor:
+    """Five Conv1d(k=1) MLPs (model/chore.py:113-126) -> one fp32 buffer, k-major, first layer rows permuted/padded."""
+    perm = feature_permutation()
+    chunks = []
+    for name, nout in zip(HEADS, HEAD_NOUT):
+        w1 = sd[f"{name}.0.weight"][:, :, 0].float()                 # [128, 611]
+        assert w1.shape == (Q_H, perm.numel()), f"{name}.0.weight has shape {tuple(w1.shape)}"
+        w1p = torch.zeros(Q_K, Q_H)
+        w1p[: perm.numel()] = w1[:, perm].t().cpu()
+        chunks += [w1p.reshape(-1), sd[f"{name}.0.bias"].float().cpu()]
+        for idx in (2, 4):
+            chunks += [sd[f"{name}.{idx}.weight"][:, :, 0].float().t().contiguous().cpu().reshape(-1),
+                       sd[f"{name}.{idx}.bias"].float().cpu()]
+        w4 = torch.zeros(Q_H, 16)
+        w4[:, :nout] = sd[f"{name}.6.weight"][:, :, 0].float().t().cpu()
+        b4 = torch.zeros(16)
+        b4[:nout] = sd[f"{name}.6.bias"].float().cpu()
+        chunks += [w4.reshape(-1), b4]
+    return torch.cat(chunks).contiguous().to(device)
