@@ -89,6 +89,16 @@ int vt_query_fwd(const float* points, const float* crop_center, const float* bod
                  int Wt, int c_im, int c_tmpx, int c_tt, int c_tf, const float* cam7, const float* wpack, float* out,
                  float* feat_out, float* xy_out, void* stream);
 
+/* Gradient of sum(g_out * out) w.r.t. the points -- what autograd computes for `df.sum().backward()` in
+ * Generator.approx_surface (recon/gen/generator.py:86-96) and for the df / part / centre losses of the fitters
+ * (recon/recon_fit_behave.py:467-513, recon/recon_fit_trivis_full.py:193-270).  The forward is recomputed on chip.
+ * g_out[B][29][N] (same packing as `out`), g_points[B][N][3].  wpack_bwd: vt_query_wpack_bwd_floats() floats. */
+long long vt_query_wpack_bwd_floats(void);
+int vt_query_bwd(const float* points, const float* crop_center, const float* body_center, int B, int N,
+                 const float* im_feat, const float* tmpx, const float* tri_tmpx, const float* tri_feat, int Hf, int Wf, int Ht,
+                 int Wt, int c_im, int c_tmpx, int c_tt, int c_tf, const float* cam7, const float* wpack, const float* wpack_bwd,
+                 const float* g_out, float* g_points, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

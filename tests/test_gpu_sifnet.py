@@ -96,3 +96,45 @@ def test_query_edge_cases(net):
     assert torch.isfinite(net.get_preds()[2]).all()
     with pytest.raises(ValueError):
         net.query(points.repeat(2, 1, 1).cuda(), crop_center=crop.cuda(), body_center=body.cuda())
+
+
+def _grad_wrt_points(net, points, crop, body, idx):
+    pts = points.cuda().requires_grad_(True)
+    net.query(pts, crop_center=crop.cuda(), body_center=body.cuda())
+    df = net.get_preds()[0]
+    torch.clamp(df[:, idx], max=2.0).sum().backward()         # recon/gen/generator.py:88-90
+    return pts.grad.cpu()
+
+
+def test_query_gradient_matches_reference_golden(net, golden):
+    """d(sum clamp(df, 2))/d(points): the quantity Generator.approx_surface back-propagates 10x per round."""
+    g = golden("sifnet_small.npz")
+    images, points, crop, body = synthetic_frames(2, size=64, seed=11, n_points=301, jitter=True)
+    net.filter(images.cuda())
+    for name, idx in (("grad_h", 0), ("grad_o", 1)):
+        got = _grad_wrt_points(net, points, crop, body, idx)
+        assert rel_err(got, g[name]) < TOL, name
+        out_of_img = (np.abs(g["xy"]) > 1).any(1)
+        assert float(got.numpy()[out_of_img].__abs__().max()) == 0.0      # df is a constant 5.0 there
+    g = golden("sifnet_c1.npz")
+    images, points, crop, body = synthetic_frames(1, size=512, seed=0, n_points=2000)
+    net.filter(images.cuda())
+    for name, idx in (("grad_h", 0), ("grad_o", 1)):
+        assert rel_err(_grad_wrt_points(net, points, crop, body, idx), g[name]) < TOL, name
+
+
+def test_query_gradient_all_heads_matches_oracle(net):
+    """Random cotangents on all 29 outputs (parts / centres / visibility heads are used by the fitters' losses)."""
+    sd = synthetic_state_dict(DIMS, seed=0)
+    images, points, crop, body = synthetic_frames(2, size=64, seed=31, n_points=77, jitter=True)
+    net.filter(images.cuda())
+    cot = [torch.randn(2, c, 77, generator=torch.Generator().manual_seed(40 + c)) for c in (2, 9, 14, 3, 1)]
+    with torch.no_grad():
+        maps = R.sif_filter(sd, images)
+    p_ref = points.clone().requires_grad_(True)
+    outs = R.sif_query(sd, maps, p_ref, crop, body, CAM)
+    sum((o.reshape(2, -1, 77) * c).sum() for o, c in zip(outs, cot)).backward()
+    pts = points.cuda().requires_grad_(True)
+    net.query(pts, crop_center=crop.cuda(), body_center=body.cuda())
+    sum((o.reshape(2, -1, 77) * c.cuda()).sum() for o, c in zip(net.get_preds(), cot)).backward()
+    assert rel_err(pts.grad.cpu(), p_ref.grad) < TOL

@@ -19,7 +19,7 @@ from . import _lib
 from .config import SIFNetDims, resolve_dims
 from .encoder import HGEncoder
 from .synth import sifnet_spec
-from .weights import pack_decoders
+from .weights import pack_decoders, pack_decoders_bwd
 
 N_OUT = 29          # df 2 | pca 9 | parts 14 | centers 3 | visibility 1
 
@@ -111,7 +111,9 @@ class CHORETriplaneVisibility:
             self._rgb = HGEncoder(sd, "image_filter", self.dims.rgb, self.device)
             self._tri = HGEncoder(sd, "triplane_encoder", self.dims.tri, self.device)
             self._wpack = pack_decoders(sd, self.device)
+            self._wpack_bwd = pack_decoders_bwd(sd, self.device)
         assert self._wpack.numel() == _lib.load().vt_query_wpack_floats()
+        assert self._wpack_bwd.numel() == _lib.load().vt_query_wpack_bwd_floats()
         return self
 
     # ------------------------------------------------------------------ filter
@@ -186,7 +188,21 @@ class CHORETriplaneVisibility:
         return out, xy
 
     def _query_backward(self, points, crop_center, body_center, g_out):
-        raise NotImplementedError("query backward kernel is not built yet")
+        """d(sum g_out * out)/d(points) with the maps of the last filter() call (csrc/query.cu: query_bwd_kernel)."""
+        im_feat, tmpx, tri_tmpx, tri_feat = self._maps
+        B, N = points.shape[0], points.shape[1]
+        pts = points.detach().to(self.device, torch.float32).contiguous()
+        cc = crop_center.to(self.device, torch.float32).contiguous()
+        bc = body_center.to(self.device, torch.float32).contiguous()
+        g = g_out.to(self.device, torch.float32).contiguous()
+        g_pts = torch.empty(B, N, 3, dtype=torch.float32, device=self.device)
+        d = self.dims
+        with torch.cuda.device(self.device):
+            _lib.call("vt_query_bwd", _lib.ptr(pts), _lib.ptr(cc), _lib.ptr(bc), B, N, _lib.ptr(im_feat), _lib.ptr(tmpx),
+                      _lib.ptr(tri_tmpx), _lib.ptr(tri_feat), im_feat.shape[1], im_feat.shape[2], tmpx.shape[1], tmpx.shape[2],
+                      d.rgb.out_ch, d.rgb.stem_ch, d.tri.stem_ch, d.tri.out_ch, self._cam7, _lib.ptr(self._wpack),
+                      _lib.ptr(self._wpack_bwd), _lib.ptr(g), _lib.ptr(g_pts), _lib.stream_ptr())
+        return g_pts
 
     def query(self, points, crop_center=None, **kwargs):
         """CHORETriplane.query (model/chore_triplane.py:97-164).  Stores ``self.preds`` = (df [B,2,N], pca [B,3,3,N],

@@ -1,0 +1,57 @@
+"""Synthetic SMPL-H-shaped body model and motions.
+
+The real ``SMPLH_male.pkl`` is licensed and not in the reference repository (README.md:42), so parity and throughput are
+established on a random model of the real SHAPE: V = 6890 vertices, J = 52 joints (22 body + 2 x 15 hand), 10 shape
+directions, 51 x 9 = 459 pose directions, the SMPL-H kinematic tree, skinning weights with 4 non-zeros per vertex
+(as in SMPL) and a sparse-ish joint regressor with rows summing to one.  Buffer names follow
+``SMPL_Layer.__init__`` (lib_smpl/smplpytorch/smplpytorch/pytorch/smpl_layer.py:50-71).
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+NUM_VERTS, NUM_JOINTS, NUM_BETAS = 6890, 52, 10
+# kintree_table[0] of SMPL-H (22 body joints, then 15 left-hand and 15 right-hand joints hanging off the wrists 20 / 21)
+SMPLH_PARENTS = [-1, 0, 0, 0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 9, 9, 12, 13, 14, 16, 17, 18, 19,
+                 20, 22, 23, 20, 25, 26, 20, 28, 29, 20, 31, 32, 20, 34, 35,
+                 21, 37, 38, 21, 40, 41, 21, 43, 44, 21, 46, 47, 21, 49, 50]
+assert len(SMPLH_PARENTS) == NUM_JOINTS
+
+
+def synthetic_smplh(seed: int = 3, num_verts: int = NUM_VERTS):
+    rng = np.random.Generator(np.random.PCG64(seed))
+    V, J = num_verts, NUM_JOINTS
+    f32 = np.float32
+    v_template = (rng.standard_normal((1, V, 3)) * np.array([0.25, 0.45, 0.12])).astype(f32)
+    shapedirs = (rng.standard_normal((V, 3, NUM_BETAS)) * 0.02).astype(f32)
+    posedirs = (rng.standard_normal((V, 3, (J - 1) * 9)) * 0.004).astype(f32)
+    jreg = np.zeros((J, V), f32)
+    for j in range(J):
+        idx = rng.choice(V, size=24, replace=False)
+        w = rng.random(24).astype(f32)
+        jreg[j, idx] = w / w.sum()
+    weights = np.zeros((V, J), f32)
+    for v in range(V):
+        idx = rng.choice(J, size=4, replace=False)
+        w = rng.random(4).astype(f32) + 0.05
+        weights[v, idx] = w / w.sum()
+    faces = rng.integers(0, V, size=(13776, 3)).astype(np.int64)
+    return {"th_betas": torch.zeros(1, NUM_BETAS), "th_shapedirs": torch.from_numpy(shapedirs),
+            "th_posedirs": torch.from_numpy(posedirs), "th_v_template": torch.from_numpy(v_template),
+            "th_J_regressor": torch.from_numpy(jreg), "th_weights": torch.from_numpy(weights),
+            "th_faces": torch.from_numpy(faces), "parents": list(SMPLH_PARENTS)}
+
+
+def synthetic_motion(frames: int, seed: int = 5, sigma: float = 0.02):
+    """Smooth random walk in body pose: pose [T,156], betas [T,10] = (2.2, 0, ...)-like, trans [T,3]."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    pose = np.zeros((frames, 156), np.float32)
+    pose[0, :66] = rng.standard_normal(66) * 0.3
+    pose[0, 66:] = rng.standard_normal(90) * 0.1
+    for t in range(1, frames):
+        pose[t] = pose[t - 1]
+        pose[t, :66] += rng.standard_normal(66) * sigma
+    betas = np.tile((rng.standard_normal(NUM_BETAS) * 0.5).astype(np.float32), (frames, 1))
+    trans = np.array([0.0, 0.0, 2.2], np.float32) + np.cumsum(rng.standard_normal((frames, 3)) * 0.01, 0).astype(np.float32)
+    return torch.from_numpy(pose), torch.from_numpy(betas), torch.from_numpy(trans.astype(np.float32))

@@ -72,3 +72,23 @@ def pack_decoders(sd: Dict[str, torch.Tensor], device) -> torch.Tensor:
         b4[:nout] = sd[f"{name}.6.bias"].float().cpu()
         chunks += [w4.reshape(-1), b4]
     return torch.cat(chunks).contiguous().to(device)
+
+
+Q_KB = 640
+
+
+def pack_decoders_bwd(sd: Dict[str, torch.Tensor], device) -> torch.Tensor:
+    """Transposed copies for the analytic backward pass (csrc/query.cu): per head W1b [128][640] (feature columns in the
+    internal order, zero padded), W2b, W3b [128][128] and W4b [16][128] -- i.e. the torch [out][in] layout."""
+    perm = feature_permutation()
+    chunks = []
+    for name, nout in zip(HEADS, HEAD_NOUT):
+        w1b = torch.zeros(Q_H, Q_KB)
+        w1b[:, : perm.numel()] = sd[f"{name}.0.weight"][:, :, 0].float().cpu()[:, perm]
+        chunks.append(w1b.reshape(-1))
+        for idx in (2, 4):
+            chunks.append(sd[f"{name}.{idx}.weight"][:, :, 0].float().cpu().contiguous().reshape(-1))
+        w4b = torch.zeros(16, Q_H)
+        w4b[:nout] = sd[f"{name}.6.weight"][:, :, 0].float().cpu()
+        chunks.append(w4b.reshape(-1))
+    return torch.cat(chunks).contiguous().to(device)
