@@ -49,7 +49,7 @@ class ClockSampler:
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         self.p = None
         try:
-            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
                                        "-i", str(gpu_index)], stdout=self.f, stderr=subprocess.DEVNULL)
         except OSError:
             pass
@@ -237,12 +237,12 @@ def run_ours(args):
         t_ms = sum(s.elapsed_time(e) for s, e, *_ in spans)
         flops = sum(f * c for (_, _, f, _, _), c in zip(spans, cins))
         pk, src = peaks()
-        achieved = flops / (t_ms * 1e-3) / 1e12
+        achieved = flops / (t_ms * 1e-3) / 1e12 if spans else 0.0
         roof = {"bound": "tensor", "kernel": "conv_mma_kernel (tcgen05 fp16x2-split, 3 MMA per fp32 MAC)", "achieved": achieved,
                 "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": achieved / pk["bf16_tflops_sustained"],
                 "traffic": None, "peak_source": f"{src} bf16 sustained (kernel timed inside a long step)",
                 "executed_mma_frac": 3 * achieved / pk["bf16_tflops_sustained"], "launches": len(spans),
-                "kernel_ms_per_step": t_ms, "share_of_step": t_ms / (ms / args.steps),
+                "kernel_ms_per_step": t_ms, "share_of_step": t_ms / (ms / args.steps) if spans else 0.0,
                 "algorithmic_gflop_per_launch_avg": flops / 1e9 / max(len(spans), 1)}
 
     if rank == 0:
