@@ -99,6 +99,46 @@ int vt_query_bwd(const float* points, const float* crop_center, const float* bod
                  int Wt, int c_im, int c_tmpx, int c_tt, int c_tf, const float* cam7, const float* wpack, const float* wpack_bwd,
                  const float* g_out, float* g_points, void* stream);
 
+/* ---- SMPL-H layer: SMPL_Layer.forward (lib_smpl/smplpytorch/smplpytorch/pytorch/smpl_layer.py:73-176) and its gradient
+ *      w.r.t. pose / betas / trans; landmark regressors (lib_smpl/torch_functions.py:52-76, wrapper_pytorch.py:187-203) ---- */
+
+/* Body model re-packed for the kernels (device pointers; built once by vistracker_b200/smpl.py from the th_* buffers). */
+typedef struct vt_smpl_model {
+  int V, J, n_betas;        /* 6890, 52, 10 for SMPL-H */
+  int kd, kdp;              /* 9*(J-1) + n_betas blend coefficients, padded to a multiple of 4 */
+  int nv3p;                 /* 3*V padded to a multiple of 4 */
+  int nnz;                  /* skinning weights per vertex (ELL width; 4 in SMPL) */
+  const float* templ;       /* [3V]            v_template */
+  const float* dirs;        /* [kdp][nv3p]     rows: posedirs[:, :, k] (k < 9(J-1)), then shapedirs[:, :, k] */
+  const float* dirsT;       /* [nv3p][kdp]     transpose, for the backward GEMM */
+  const float* j_templ;     /* [J][3]          J_regressor * v_template */
+  const float* j_dirs;      /* [J][3][n_betas] J_regressor * shapedirs */
+  const int* parents;       /* [J]             kintree_table[0]; parents[0] is ignored */
+  const int* skin_idx;      /* [V][nnz] */
+  const float* skin_w;      /* [V][nnz] */
+} vt_smpl_model;
+
+/* pose[B][3J] axis-angle, betas[B][n_betas], trans[B][3], offsets[B][V][3] or NULL -> verts[B][V][3], jtr[B][J][3],
+ * naked[B][V][3], v_posed[B][V][3] (only written when offsets != NULL; otherwise v_posed == naked).
+ * coef[B][kdp], R[B][J][9], J[B][J][3], G[B][J][12], A[B][J][12] are outputs the backward call needs again. */
+int vt_smpl_fwd(const vt_smpl_model* model, const float* pose, const float* betas, const float* trans, const float* offsets,
+                float scale, int B, float* coef, float* R, float* J, float* G, float* A, float* naked, float* v_posed,
+                float* verts, float* jtr, void* stream);
+
+/* g_verts[B][V][3] and / or g_jtr[B][J][3] (NULL = zero) -> g_pose[B][3J], g_betas[B][n_betas], g_trans[B][3].
+ * Scratch (caller-owned, overwritten): g_vposed[B][nv3p] (= d/d offsets on return), gA[B][J][12], g_coef[B][kdp],
+ * g_trans_skin[B][3]. */
+int vt_smpl_bwd(const vt_smpl_model* model, const float* pose, const float* R, const float* J, const float* G, const float* A,
+                const float* v_posed, const float* g_verts, const float* g_jtr, float scale, int B, float* g_vposed, float* gA,
+                float* g_coef, float* g_trans_skin, float* g_pose, float* g_betas, float* g_trans, void* stream);
+
+/* out[B][L][3] = regressor^T verts for a sparse [V x L] regressor given as CSR over landmarks (rowptr[L+1], col = vertex). */
+int vt_landmarks_fwd(const float* verts, int B, int V, const int* rowptr, const int* col, const float* val, int L, float* out,
+                     void* stream);
+/* g_verts[B][V][3] += regressor g_out (atomics; the caller initialises g_verts). */
+int vt_landmarks_bwd(const float* g_out, int B, int V, const int* rowptr, const int* col, const float* val, int L, float* g_verts,
+                     void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -130,6 +130,30 @@ def smpl_goldens(out_dir: str):
     print("smpl_small: verts", tuple(verts.shape), "jtr", tuple(jtr.shape))
 
 
+def asset_fixtures(out_dir: str, ref_root: str):
+    """Numeric assets the reference ships for this path, re-serialised without scipy / pickle:
+    the body-25 landmark regressor (COO), the pose / hand priors and the 14-part vertex labels."""
+    import pickle
+    import warnings
+    warnings.filterwarnings("ignore")
+    ld = lambda rel: pickle.load(open(os.path.join(ref_root, "assets", rel), "rb"), encoding="latin1")
+    out = {}
+    for name in ("body25", "face", "hand"):
+        m = ld(f"{name}_regressor.pkl").tocoo()
+        out[f"{name}_row"], out[f"{name}_col"] = m.row.astype(np.int32), m.col.astype(np.int32)
+        out[f"{name}_val"], out[f"{name}_shape"] = m.data.astype(np.float32), np.array(m.shape, np.int32)
+    for name in ("body_prior", "lh_prior", "rh_prior"):
+        d = ld(f"priors/{name}.pkl")
+        out[f"{name}_mean"], out[f"{name}_precision"] = np.asarray(d["mean"], np.float64), np.asarray(d["precision"], np.float64)
+    parts = ld("smpl_parts_dense.pkl")
+    labels = np.full(6890, -1, np.int8)
+    for i, k in enumerate(sorted(parts.keys())):          # dict order == sorted order; label n = n-th key (recon/recon_fit_base.py:315-325)
+        labels[np.asarray(parts[k])] = i
+    out["part_labels"] = labels
+    np.savez_compressed(os.path.join(out_dir, "assets.npz"), **out)
+    print("assets:", {k: v.shape for k, v in out.items()})
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--ref", default="/root/reference")
@@ -141,3 +165,5 @@ if __name__ == "__main__":
         sifnet_goldens(HERE)
     if a.only in ("", "smpl"):
         smpl_goldens(HERE)
+    if a.only in ("", "assets"):
+        asset_fixtures(HERE, a.ref)

@@ -32,6 +32,23 @@ SIGNATURES = {
     "vt_query_bwd": (_i, [_p, _p, _p, _i, _i, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p]),
 }
 
+
+
+class SmplModelStruct(C.Structure):
+    """struct vt_smpl_model (include/vistracker_b200.h)."""
+    _fields_ = [("V", _i), ("J", _i), ("n_betas", _i), ("kd", _i), ("kdp", _i), ("nv3p", _i), ("nnz", _i),
+                ("templ", _p), ("dirs", _p), ("dirsT", _p), ("j_templ", _p), ("j_dirs", _p), ("parents", _p),
+                ("skin_idx", _p), ("skin_w", _p)]
+
+
+_ms = C.POINTER(SmplModelStruct)
+SIGNATURES.update({
+    "vt_smpl_fwd": (_i, [_ms, _p, _p, _p, _p, _f, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "vt_smpl_bwd": (_i, [_ms, _p, _p, _p, _p, _p, _p, _p, _p, _f, _i, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "vt_landmarks_fwd": (_i, [_p, _i, _i, _p, _p, _p, _i, _p, _p]),
+    "vt_landmarks_bwd": (_i, [_p, _i, _i, _p, _p, _p, _i, _p, _p]),
+})
+
 _lib = None
 
 
