@@ -130,6 +130,71 @@ def smpl_goldens(out_dir: str):
     print("smpl_small: verts", tuple(verts.shape), "jtr", tuple(jtr.shape))
 
 
+def fit_smplt_goldens(out_dir: str):
+    """Runs the reference's own compute_loss / sum_dict / optimiser constructors (unbound, on CPU) inside the loop
+    structure of BaseFitter.fit_one_batch (preprocess/fit_SMPLH_kpts.py:131-175) on a 12-frame synthetic problem."""
+    for mod in ("behave", "behave.frame_data", "lib_smpl.smpl_generator"):
+        _stub(mod, FrameDataReader=object, SMPLHGenerator=object)
+    torch.Tensor.cuda = lambda self, *a, **k: self                              # the priors call .cuda() at construction
+    from lib_smpl.smplpytorch.smplpytorch.pytorch.smpl_layer import SMPL_Layer       # reference
+    from lib_smpl.wrapper_pytorch import SMPLPyTorchWrapperBatchSplitParams          # reference
+    from lib_smpl.body_landmark import load_regressors                               # reference
+    from preprocess.fit_SMPLH_30fps import SMPLHFitter30fps                          # reference
+    import lib_smpl.th_hand_prior as hp_mod                                          # reference
+    d = list(hp_mod.HandPrior.__init__.__defaults__)                                  # only the default DEVICE is changed
+    hp_mod.HandPrior.__init__.__defaults__ = tuple("cpu" if x == "cuda:0" else x for x in d)
+
+    sys.path.insert(0, os.path.dirname(HERE))
+    from fit_problem import synthetic_fit_problem                                    # tests/fit_problem.py
+    B = 12
+    model, kpts, pose0, betas0, trans0 = synthetic_fit_problem(B, seed=9)
+    L = SMPL_Layer.__new__(SMPL_Layer); torch.nn.Module.__init__(L)
+    L.hands, L.num_joints, L.kintree_parents = True, 52, list(model["parents"])
+    for k in ("th_betas", "th_shapedirs", "th_posedirs", "th_v_template", "th_J_regressor", "th_weights"):
+        L.register_buffer(k, model[k])
+    S = SMPLPyTorchWrapperBatchSplitParams.__new__(SMPLPyTorchWrapperBatchSplitParams); torch.nn.Module.__init__(S)
+    P = torch.nn.Parameter
+    S.global_pose, S.body_pose, S.hand_pose = P(pose0[:, :3].clone()), P(pose0[:, 3:66].clone()), P(pose0[:, 66:].clone())
+    S.top_betas, S.other_betas, S.trans = P(betas0[:, :2].clone()), P(betas0[:, 2:].clone()), P(trans0.clone())
+    S.offsets = P(torch.zeros(B, 6890, 3))
+    S.smpl = L
+    S.body25_reg_torch, S.face_reg_torch, S.hand_reg_torch = load_regressors("assets", batch_size=B)
+    S.verts = S.jtr = S.tposed = S.naked = None
+    F = SMPLHFitter30fps.__new__(SMPLHFitter30fps)
+    F.fx, F.fy, F.cx, F.cy = 979.7844, 979.840, 1018.952, 779.486
+    weights = F.get_loss_weights()
+    pose_init = pose0.clone()
+    out = {}
+    # step-0 loss terms and gradients
+    ld = F.compute_loss(S, kpts, pose_init)
+    F.sum_dict(ld, weights, 0).backward()
+    for k, v in ld.items():
+        out[f"loss0_{k}"] = np.float64(v.item())
+    out["g0_pose"] = torch.cat([S.global_pose.grad, S.body_pose.grad], 1).numpy().copy()
+    out["g0_betas"] = torch.cat([S.top_betas.grad, S.other_betas.grad], 1).numpy().copy()
+    out["g0_trans"] = S.trans.grad.numpy().copy()
+    # the optimisation loop (no IO, no early stop before it > 30)
+    optimizer = F.init_globalpose_optimizer(S)
+    losses, record = [], (1, 10, 80, 81, 100)
+    step = 0
+    for it in range(10):
+        if it == F.get_globalopt_iters():
+            optimizer = F.init_allpose_optimizer(S)
+        for i in range(10):
+            optimizer.zero_grad()
+            ld = F.compute_loss(S, kpts, pose_init)
+            loss = F.sum_dict(ld, weights, it // 3)
+            loss.backward(); optimizer.step()
+            losses.append(loss.item()); step += 1
+            if step in record:
+                out[f"pose_{step}"] = torch.cat([S.global_pose, S.body_pose, S.hand_pose], 1).detach().numpy().copy()
+                out[f"betas_{step}"] = torch.cat([S.top_betas, S.other_betas], 1).detach().numpy().copy()
+                out[f"trans_{step}"] = S.trans.detach().numpy().copy()
+    out["losses"] = np.array(losses, np.float64)
+    np.savez_compressed(os.path.join(out_dir, "fit_smplt_small.npz"), **out)
+    print("fit_smplt_small: losses", losses[0], "->", losses[-1])
+
+
 def asset_fixtures(out_dir: str, ref_root: str):
     """Numeric assets the reference ships for this path, re-serialised without scipy / pickle:
     the body-25 landmark regressor (COO), the pose / hand priors and the 14-part vertex labels."""
@@ -167,3 +232,5 @@ if __name__ == "__main__":
         smpl_goldens(HERE)
     if a.only in ("", "assets"):
         asset_fixtures(HERE, a.ref)
+    if a.only in ("", "fit"):
+        fit_smplt_goldens(HERE)
