@@ -139,6 +139,32 @@ int vt_landmarks_fwd(const float* verts, int B, int V, const int* rowptr, const 
 int vt_landmarks_bwd(const float* g_out, int B, int V, const int* rowptr, const int* col, const float* val, int L, float* g_verts,
                      void* stream);
 
+/* ---- SMPL-T keypoint pre-fit objective and optimiser: SMPLHFitter30fps.compute_loss (preprocess/fit_SMPLH_30fps.py:153-200),
+ *      BaseFitter.sum_dict / fit_one_batch / init_*_optimizer (preprocess/fit_SMPLH_kpts.py:67-75,114-190), priors
+ *      (lib_smpl/th_smpl_prior.py:25-39, lib_smpl/th_hand_prior.py:46-72).  All state lives on the device:
+ *        ctrl  float[vt_fit_ctrl_words()]: [0..5] weights of kpts,temp,ptemp,pose,hand,pinit ALREADY divided by (1+decay);
+ *              [8] Adam lr; [9] phase (0: trans+global_pose+top_betas, 1: + body_pose + other_betas); [10] Adam step count;
+ *              [11] history row to write next.  The host only rewrites it when the schedule changes.
+ *        acc   double[8] per-step accumulators of the unweighted term sums (zeroed by vt_fit_begin_step)
+ *        hist  double[max_hist][8]: six term means, weighted total, Adam step -- one row per optimisation step ------------- */
+int vt_fit_ctrl_words(void);
+int vt_fit_begin_step(double* acc, void* stream);
+/* J[B][25][3] body-25 landmarks, kpts[B][25][3] = (x, y, confidence); cam4 (host) = {fx, fy, cx, cy};
+ * gJ[B][25][3] = weight * d(mean reprojection error)/dJ. */
+int vt_fit_kpts(const float* J, const float* kpts, int B, int L, const float* cam4, const float* ctrl, float* gJ, double* acc, void* stream);
+/* g_verts[B][n_coords] = weight * d mse(v[1:-1]-v[:-2], v[2:]-v[1:-1]) / d verts  (every element is written). */
+int vt_fit_temporal_verts(const float* verts, int B, int n_coords, const float* ctrl, float* g_verts, double* acc, void* stream);
+/* pose[B][156]: Mahalanobis body prior (mean[63], precision[63][63]), GRAB hand prior value (2 x mean[45], precision[45][45]),
+ * weighted pose second differences (joint_w[66]) and stay-near-init; g_pose[B][156] is overwritten. */
+int vt_fit_pose_terms(const float* pose, const float* pose_init, int B, const float* body_mean, const float* body_prec,
+                      const float* lh_mean, const float* lh_prec, const float* rh_mean, const float* rh_prec, const float* joint_w,
+                      const float* ctrl, float* g_pose, double* acc, void* stream);
+/* torch.optim.Adam (default betas / eps) on the entries the current phase optimises; gradient of pose = g_pose_a + g_pose_b;
+ * m, v: float[B][169] moment buffers (zero them when a new optimiser starts). */
+int vt_fit_adam(float* pose, float* betas, float* trans, const float* g_pose_a, const float* g_pose_b, const float* g_betas,
+                const float* g_trans, float* m, float* v, int B, const float* ctrl, void* stream);
+int vt_fit_end_step(const double* acc, int B, int n_coords, float* ctrl, double* hist, int max_hist, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

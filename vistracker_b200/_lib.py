@@ -47,6 +47,13 @@ SIGNATURES.update({
     "vt_smpl_bwd": (_i, [_ms, _p, _p, _p, _p, _p, _p, _p, _p, _f, _i, _p, _p, _p, _p, _p, _p, _p, _p]),
     "vt_landmarks_fwd": (_i, [_p, _i, _i, _p, _p, _p, _i, _p, _p]),
     "vt_landmarks_bwd": (_i, [_p, _i, _i, _p, _p, _p, _i, _p, _p]),
+    "vt_fit_ctrl_words": (_i, []),
+    "vt_fit_begin_step": (_i, [_p, _p]),
+    "vt_fit_kpts": (_i, [_p, _p, _i, _i, _p, _p, _p, _p, _p]),
+    "vt_fit_temporal_verts": (_i, [_p, _i, _i, _p, _p, _p, _p]),
+    "vt_fit_pose_terms": (_i, [_p, _p, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "vt_fit_adam": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _p, _p]),
+    "vt_fit_end_step": (_i, [_p, _i, _i, _p, _p, _i, _p]),
 })
 
 _lib = None

@@ -1,0 +1,185 @@
+"""SMPL-T keypoint pre-fit on B200: the inner loop of ``SMPLHFitter30fps`` / ``BaseFitter.fit_one_batch``
+(preprocess/fit_SMPLH_30fps.py:54-200, preprocess/fit_SMPLH_kpts.py:84-190) on device-resident tensors.
+
+One optimisation step (SMPL-H forward, body-25 landmarks, 2-D reprojection, vertex / pose smoothness, priors, stay-near-init,
+analytic backward, Adam) is a fixed sequence of kernel launches over pre-allocated buffers, captured once into a CUDA graph
+and replayed; the loss schedule (``w_k / (1 + it // 3)``), the optimiser phase switch at outer iteration 8 and the early-stop
+rule are driven from the host exactly as the reference does, reading back one history row per step only inside the early-stop
+window.  File IO of the reference (mocap json, masks, per-frame pkl) is outside this module: callers pass / receive tensors.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Dict, Optional
+
+import numpy as np
+import torch
+
+from . import _lib
+from .smpl import SMPL_Layer, LandmarkRegressor
+
+P, S = _lib.ptr, _lib.stream_ptr
+
+# preprocess/fit_SMPLH_30fps.py:26-51
+JOINT_WEIGHTS = np.array([1, 1, 1, 10, 10, 10, 10, 10, 10, 10, 10, 10, 5, 5, 5, 5, 5, 5, 10, 10, 10, 1, 1, 1, 1, 1, 1, 10, 10, 10,
+                          1, 1, 1, 1, 1, 1, 5, 10, 10, 5, 5, 5, 5, 5, 5, 5, 5, 5, 5, 5, 5, 5, 5, 5, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1],
+                         np.float32)
+TERMS = ("kpts", "temp", "ptemp", "pose", "hand", "pinit")
+
+
+class SMPLHFitter30fps:
+    """Same objective, schedule and optimiser set-up as the reference class of this name."""
+
+    def __init__(self, smpl: SMPL_Layer, body25: LandmarkRegressor, priors: Dict[str, np.ndarray], icap: bool = False):
+        self.smpl, self.reg, self.device = smpl, body25, smpl.device
+        if icap:      # preprocess/fit_SMPLH_kpts.py:41-47
+            cam = (918.457763671875, 918.4373779296875, 956.9661865234375, 555.944580078125)
+        else:
+            cam = (979.7844, 979.840, 1018.952, 779.486)
+        self._cam4 = (ctypes.c_float * 4)(*cam)
+        f = lambda a: torch.as_tensor(np.asarray(a, np.float32)).contiguous().to(self.device)
+        self._pri = [f(priors["body_prior_mean"]), f(priors["body_prior_precision"]), f(priors["lh_prior_mean"]),
+                     f(priors["lh_prior_precision"]), f(priors["rh_prior_mean"]), f(priors["rh_prior_precision"]), f(JOINT_WEIGHTS)]
+        assert self._pri[1].shape == (63, 63) and self._pri[3].shape == (45, 45)
+        self._B = None
+
+    # ---- reference-named hooks -------------------------------------------------------------------------------------
+    @staticmethod
+    def get_loss_weights():
+        """fit_SMPLH_30fps.py:55-66 (the 'beta' entry is unused by compute_loss)."""
+        return {"pose": 1e-5, "hand": 1e-5, "kpts": 0.3 ** 2, "temp": 30.0 ** 2, "ptemp": 5.0 ** 2, "pinit": 30.0 ** 2}
+
+    @staticmethod
+    def get_globalopt_iters():
+        return 8
+
+    @staticmethod
+    def get_max_iters():
+        return 100
+
+    # ---- buffers + the launch sequence ----------------------------------------------------------------------------------
+    def _alloc(self, B: int, max_hist: int):
+        m, dev = self.smpl, self.device
+        f = lambda *s: torch.empty(*s, dtype=torch.float32, device=dev)
+        self._B, self._max_hist = B, max_hist
+        b = self.buf = {}
+        b["pose"], b["betas"], b["trans"], b["pose_init"], b["kpts"] = f(B, 156), f(B, 10), f(B, 3), f(B, 156), f(B, 25, 3)
+        b["coef"], b["R"], b["J"], b["G"], b["A"] = f(B, m.kdp), f(B, m.J, 9), f(B, m.J, 3), f(B, m.J, 12), f(B, m.J, 12)
+        b["naked"], b["verts"], b["jtr"] = f(B, m.V, 3), f(B, m.V, 3), f(B, m.J, 3)
+        b["J25"], b["gJ25"], b["g_verts"] = f(B, 25, 3), f(B, 25, 3), f(B, m.V, 3)
+        b["g_vposed"], b["gA"], b["g_coef"], b["g_ts"] = f(B, m.nv3p), f(B, m.J, 12), f(B, m.kdp), f(B, 3)
+        b["g_pose"], b["g_pose_d"], b["g_betas"], b["g_trans"] = f(B, 156), f(B, 156), f(B, 10), f(B, 3)
+        b["m"], b["v"] = torch.zeros(B, 169, device=dev), torch.zeros(B, 169, device=dev)
+        b["ctrl"] = torch.zeros(_lib.load().vt_fit_ctrl_words(), dtype=torch.float32, device=dev)
+        b["acc"] = torch.zeros(8, dtype=torch.float64, device=dev)
+        b["hist"] = torch.zeros(max_hist, 8, dtype=torch.float64, device=dev)
+        self._host_ring = [torch.zeros(10, dtype=torch.float32).pin_memory() for _ in range(8)]   # async H2D sources
+        self._ring_i = 0
+        self._graph: Optional[torch.cuda.CUDAGraph] = None
+
+    def _enqueue_step(self, with_update: bool = True):
+        b, m, B, reg = self.buf, self.smpl, self._B, self.reg
+        ms = ctypes.byref(m.struct)
+        _lib.call("vt_fit_begin_step", P(b["acc"]), S())
+        _lib.call("vt_smpl_fwd", ms, P(b["pose"]), P(b["betas"]), P(b["trans"]), None, 1.0, B, P(b["coef"]), P(b["R"]), P(b["J"]),
+                  P(b["G"]), P(b["A"]), P(b["naked"]), P(b["naked"]), P(b["verts"]), P(b["jtr"]), S())
+        _lib.call("vt_landmarks_fwd", P(b["verts"]), B, m.V, P(reg.rowptr), P(reg.col), P(reg.val), reg.L, P(b["J25"]), S())
+        _lib.call("vt_fit_kpts", P(b["J25"]), P(b["kpts"]), B, 25, self._cam4, P(b["ctrl"]), P(b["gJ25"]), P(b["acc"]), S())
+        _lib.call("vt_fit_temporal_verts", P(b["verts"]), B, 3 * m.V, P(b["ctrl"]), P(b["g_verts"]), P(b["acc"]), S())
+        _lib.call("vt_landmarks_bwd", P(b["gJ25"]), B, m.V, P(reg.rowptr), P(reg.col), P(reg.val), reg.L, P(b["g_verts"]), S())
+        _lib.call("vt_fit_pose_terms", P(b["pose"]), P(b["pose_init"]), B, *(P(t) for t in self._pri), P(b["ctrl"]), P(b["g_pose_d"]),
+                  P(b["acc"]), S())
+        _lib.call("vt_smpl_bwd", ms, P(b["pose"]), P(b["R"]), P(b["J"]), P(b["G"]), P(b["A"]), P(b["naked"]), P(b["g_verts"]), None, 1.0, B,
+                  P(b["g_vposed"]), P(b["gA"]), P(b["g_coef"]), P(b["g_ts"]), P(b["g_pose"]), P(b["g_betas"]), P(b["g_trans"]), S())
+        if with_update:
+            _lib.call("vt_fit_adam", P(b["pose"]), P(b["betas"]), P(b["trans"]), P(b["g_pose"]), P(b["g_pose_d"]), P(b["g_betas"]),
+                      P(b["g_trans"]), P(b["m"]), P(b["v"]), B, P(b["ctrl"]), S())
+        _lib.call("vt_fit_end_step", P(b["acc"]), B, 3 * m.V, P(b["ctrl"]), P(b["hist"]), self._max_hist, S())
+
+    LAUNCHES_PER_STEP = 14        # kernels per optimisation step (+ 4 memset nodes inside vt_smpl_bwd)
+
+    def _set_schedule(self, decay: int, phase: int, lr: float):
+        w = self.get_loss_weights()
+        h = self._host_ring[self._ring_i % len(self._host_ring)]
+        self._ring_i += 1
+        for i, k in enumerate(TERMS):
+            h[i] = w[k] / (1 + decay)
+        h[6] = h[7] = 0.0
+        h[8], h[9] = lr, float(phase)
+        self.buf["ctrl"][:10].copy_(h, non_blocking=True)
+
+    def _load(self, pose0, betas0, trans0, kpts, max_hist):
+        B = pose0.shape[0]
+        if B < 3:
+            raise ValueError("the temporal terms need at least 3 frames per batch")
+        if self._B != B or self._max_hist < max_hist:
+            self._alloc(B, max_hist)
+        b, to = self.buf, dict(device=self.device, dtype=torch.float32)
+        b["pose"].copy_(pose0.to(**to)); b["pose_init"].copy_(pose0.to(**to))
+        b["betas"].copy_(betas0.to(**to)); b["trans"].copy_(trans0.to(**to)); b["kpts"].copy_(kpts.to(**to))
+        b["m"].zero_(); b["v"].zero_(); b["ctrl"].zero_(); b["hist"].zero_()
+
+    # ---- public API ------------------------------------------------------------------------------------------------------
+    def compute_loss(self, pose, betas, trans, kpts, pose_init=None, decay: int = 0):
+        """Loss terms (unweighted means, as the reference's ``loss_dict``) and the gradient of the weighted total w.r.t.
+        pose / betas / trans for one evaluation -- SMPLHFitter30fps.compute_loss + sum_dict + backward."""
+        with torch.cuda.device(self.device):
+            self._load(pose if pose_init is None else pose_init, betas, trans, kpts, 4)
+            self.buf["pose"].copy_(pose.to(self.device))
+            self._set_schedule(decay, 1, 0.0)
+            self._enqueue_step(with_update=False)
+            row = self.buf["hist"][0].cpu()
+        b = self.buf
+        losses = {k: float(row[i]) for i, k in enumerate(TERMS)}
+        losses["total"] = float(row[6])
+        return losses, (b["g_pose"] + b["g_pose_d"]).clone(), b["g_betas"].clone(), b["g_trans"].clone()
+
+    def fit_batch(self, pose0, betas0, trans0, kpts, max_iter: Optional[int] = None, steps_per_iter: int = 10,
+                  early_stop: bool = True, use_graph: bool = True, record=()):
+        """BaseFitter.fit_one_batch without file IO.  Returns dict(pose, betas, trans, losses [n_steps], terms [n_steps, 6],
+        steps, stopped_early, snapshots {step: (pose, betas, trans)})."""
+        max_iter = self.get_max_iters() if max_iter is None else max_iter
+        iter_for_global = self.get_globalopt_iters()
+        n_max = max_iter * steps_per_iter
+        snaps, stopped, step = {}, False, 0
+        with torch.cuda.device(self.device):
+            self._load(pose0, betas0, trans0, kpts, n_max)
+            b = self.buf
+            self._set_schedule(0, 0, 0.01)                      # init_globalpose_optimizer: Adam lr 0.01
+            if use_graph and self._graph is None:
+                # capture once per batch size; buffers are static so the graph stays valid across batches
+                side = torch.cuda.Stream()
+                side.wait_stream(torch.cuda.current_stream())
+                keep = {k: b[k].clone() for k in ("pose", "betas", "trans", "m", "v", "ctrl", "hist")}
+                with torch.cuda.stream(side):
+                    self._enqueue_step()                        # warm-up outside capture (module load, attribute set-up)
+                torch.cuda.current_stream().wait_stream(side)
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._enqueue_step()
+                for k, v in keep.items():
+                    b[k].copy_(v)
+                self._graph = g
+            run = self._graph.replay if use_graph else self._enqueue_step
+            prev_loss = 0.0
+            for it in range(max_iter):
+                if it == iter_for_global:                       # init_allpose_optimizer: a NEW Adam, lr 0.001
+                    b["m"].zero_(); b["v"].zero_(); b["ctrl"][10:11].zero_()
+                self._set_schedule(it // 3, 0 if it < iter_for_global else 1, 0.01 if it < iter_for_global else 0.001)
+                for _ in range(steps_per_iter):
+                    run()
+                    step += 1
+                    if step in record:
+                        snaps[step] = (b["pose"].clone(), b["betas"].clone(), b["trans"].clone())
+                    if early_stop and it >= int(0.3 * max_iter):
+                        # the reference compares consecutive totals every step but only acts when it > 0.3 * max_iter
+                        loss = float(b["hist"][step - 1, 6].item())
+                        if it > 0.3 * max_iter and prev_loss > 0 and abs(prev_loss - loss) / prev_loss < prev_loss * 0.001:
+                            stopped = True
+                            break
+                        prev_loss = loss
+                if stopped:
+                    break
+            hist = b["hist"][:step].cpu()
+        return {"pose": b["pose"].clone(), "betas": b["betas"].clone(), "trans": b["trans"].clone(), "losses": hist[:, 6].numpy(),
+                "terms": hist[:, :6].numpy(), "steps": step, "stopped_early": stopped, "snapshots": snaps}
