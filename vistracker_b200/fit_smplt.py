@@ -148,9 +148,9 @@ class SMPLHFitter30fps:
             self._set_schedule(0, 0, 0.01)                      # init_globalpose_optimizer: Adam lr 0.01
             if use_graph and self._graph is None:
                 # capture once per batch size; buffers are static so the graph stays valid across batches
-                side = torch.cuda.Stream()
-                side.wait_stream(torch.cuda.current_stream())
                 keep = {k: b[k].clone() for k in ("pose", "betas", "trans", "m", "v", "ctrl", "hist")}
+                side = torch.cuda.Stream()
+                side.wait_stream(torch.cuda.current_stream())       # after the clones: the warm-up step mutates the state
                 with torch.cuda.stream(side):
                     self._enqueue_step()                        # warm-up outside capture (module load, attribute set-up)
                 torch.cuda.current_stream().wait_stream(side)
