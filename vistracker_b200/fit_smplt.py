@@ -73,8 +73,7 @@ class SMPLHFitter30fps:
         b["ctrl"] = torch.zeros(_lib.load().vt_fit_ctrl_words(), dtype=torch.float32, device=dev)
         b["acc"] = torch.zeros(8, dtype=torch.float64, device=dev)
         b["hist"] = torch.zeros(max_hist, 8, dtype=torch.float64, device=dev)
-        self._host_ring = [torch.zeros(10, dtype=torch.float32).pin_memory() for _ in range(8)]   # async H2D sources
-        self._ring_i = 0
+        self._sched = {}          # (decay, phase, lr) -> device row; copied device-to-device so the host can run ahead
         self._graph: Optional[torch.cuda.CUDAGraph] = None
 
     def _enqueue_step(self, with_update: bool = True):
@@ -99,14 +98,12 @@ class SMPLHFitter30fps:
     LAUNCHES_PER_STEP = 14        # kernels per optimisation step (+ 4 memset nodes inside vt_smpl_bwd)
 
     def _set_schedule(self, decay: int, phase: int, lr: float):
-        w = self.get_loss_weights()
-        h = self._host_ring[self._ring_i % len(self._host_ring)]
-        self._ring_i += 1
-        for i, k in enumerate(TERMS):
-            h[i] = w[k] / (1 + decay)
-        h[6] = h[7] = 0.0
-        h[8], h[9] = lr, float(phase)
-        self.buf["ctrl"][:10].copy_(h, non_blocking=True)
+        key = (decay, phase, lr)
+        if key not in self._sched:
+            w = self.get_loss_weights()
+            row = [w[k] / (1 + decay) for k in TERMS] + [0.0, 0.0, lr, float(phase)]
+            self._sched[key] = torch.tensor(row, dtype=torch.float32).to(self.device)     # synchronous upload, once per key
+        self.buf["ctrl"][:10].copy_(self._sched[key])
 
     def _load(self, pose0, betas0, trans0, kpts, max_hist):
         B = pose0.shape[0]
