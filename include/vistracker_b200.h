@@ -165,6 +165,22 @@ int vt_fit_adam(float* pose, float* betas, float* trans, const float* g_pose_a, 
                 const float* g_trans, float* m, float* v, int B, const float* ctrl, void* stream);
 int vt_fit_end_step(const double* acc, int B, int n_coords, float* ctrl, double* hist, int max_hist, void* stream);
 
+/* ---- joint optimisation helpers ------------------------------------------------------------------------------------------- */
+
+/* ReconFitterBase.project_so3 (recon/recon_fit_base.py:178-199): R[B][3][3] = U diag(1,1,det(UV^T)) V^T of M[B][3][3], and the
+ * vector-Jacobian product gM = (dR/dM)^T gR (what autograd derives through torch.svd / det / matmul there). */
+int vt_so3_project_fwd(const float* M, int B, float* R, void* stream);
+int vt_so3_project_bwd(const float* M, const float* gR, int B, float* gM, void* stream);
+
+/* pytorch3d.loss.chamfer_distance(Pointclouds(xs), Pointclouds(ys)) with default reductions, as called by compute_contact_loss
+ * (recon/recon_fit_trivis_full.py:452-456): N ragged cloud pairs, x[sum_n][3] with x_off[N+1] row offsets (same for y).
+ * loss[1] = mean_n ( mean_i min_j |x_i-y_j|^2 + mean_j min_i |y_j-x_i|^2 ); nn_x / nn_y receive the arg-min rows for backward.
+ * vt_chamfer_bwd ACCUMULATES into gx / gy (caller zeroes them). */
+int vt_chamfer_fwd(const float* x, const int* x_off, const float* y, const int* y_off, int N, int* nn_x, int* nn_y, float* loss,
+                   void* stream);
+int vt_chamfer_bwd(const float* x, const int* x_off, const float* y, const int* y_off, int N, const int* nn_x, const int* nn_y,
+                   const float* g_loss, float* gx, float* gy, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -54,6 +54,10 @@ SIGNATURES.update({
     "vt_fit_pose_terms": (_i, [_p, _p, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
     "vt_fit_adam": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _p, _p]),
     "vt_fit_end_step": (_i, [_p, _i, _i, _p, _p, _i, _p]),
+    "vt_so3_project_fwd": (_i, [_p, _i, _p, _p]),
+    "vt_so3_project_bwd": (_i, [_p, _p, _i, _p, _p]),
+    "vt_chamfer_fwd": (_i, [_p, _p, _p, _p, _i, _p, _p, _p, _p]),
+    "vt_chamfer_bwd": (_i, [_p, _p, _p, _p, _i, _p, _p, _p, _p, _p, _p]),
 })
 
 _lib = None

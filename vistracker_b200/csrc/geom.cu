@@ -1,0 +1,194 @@
+// Small geometric operators of the joint human-object optimisation:
+//  * SO(3) projection of a free 3x3 matrix, R = U diag(1, 1, det(U V^T)) V^T (recon/recon_fit_base.py:178-199), forward and
+//    analytic backward, one thread per matrix (the reference calls torch.svd -> cuSOLVER plus det / cat / matmul, 1550x per batch);
+//  * bidirectional squared-L2 Chamfer distance between ragged lists of small point clouds, as
+//    pytorch3d.loss.chamfer_distance(Pointclouds, Pointclouds) with its defaults computes it (point mean, batch mean, sum of the
+//    two directions) -- recon/recon_fit_trivis_full.py:452-456.  Brute-force nearest neighbour: the contact sets are tens to a few
+//    hundred points per (frame, body part) pair.
+#include "common.cuh"
+#include "vt_internal.h"
+
+namespace vt {
+
+// ------------------------------------------------------------------------------------------------ SO(3) projection
+// The maximiser of tr(R^T M) over SO(3) equals U diag(1,1,det(UV^T)) V^T.  It is found as the dominant eigenvector (a unit
+// quaternion) of Horn's symmetric 4x4 matrix N(M), by cyclic Jacobi sweeps in double precision.
+__device__ void jacobi_eig4(double (&A)[4][4], double (&V)[4][4]) {
+  for (int i = 0; i < 4; ++i)
+    for (int j = 0; j < 4; ++j) V[i][j] = i == j ? 1.0 : 0.0;
+  for (int sweep = 0; sweep < 24; ++sweep) {
+    double off = 0;
+    for (int p = 0; p < 4; ++p)
+      for (int q = p + 1; q < 4; ++q) off += A[p][q] * A[p][q];
+    if (off < 1e-30) break;
+    for (int p = 0; p < 4; ++p)
+      for (int q = p + 1; q < 4; ++q) {
+        if (fabs(A[p][q]) < 1e-300) continue;
+        const double theta = (A[q][q] - A[p][p]) / (2.0 * A[p][q]);
+        const double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+        const double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
+        for (int k = 0; k < 4; ++k) { const double akp = A[k][p], akq = A[k][q]; A[k][p] = c * akp - s * akq; A[k][q] = s * akp + c * akq; }
+        for (int k = 0; k < 4; ++k) { const double apk = A[p][k], aqk = A[q][k]; A[p][k] = c * apk - s * aqk; A[q][k] = s * apk + c * aqk; }
+        for (int k = 0; k < 4; ++k) { const double vkp = V[k][p], vkq = V[k][q]; V[k][p] = c * vkp - s * vkq; V[k][q] = s * vkp + c * vkq; }
+      }
+  }
+}
+
+__device__ void so3_project(const float* M, double (&R)[9]) {
+  const double m00 = M[0], m01 = M[1], m02 = M[2], m10 = M[3], m11 = M[4], m12 = M[5], m20 = M[6], m21 = M[7], m22 = M[8];
+  // tr(R(q)^T M) = q^T N q
+  double N[4][4] = {{m00 + m11 + m22, m21 - m12, m02 - m20, m10 - m01},
+                    {m21 - m12, m00 - m11 - m22, m01 + m10, m02 + m20},
+                    {m02 - m20, m01 + m10, -m00 + m11 - m22, m12 + m21},
+                    {m10 - m01, m02 + m20, m12 + m21, -m00 - m11 + m22}};
+  double V[4][4];
+  jacobi_eig4(N, V);
+  int best = 0;
+  for (int i = 1; i < 4; ++i) if (N[i][i] > N[best][best]) best = i;
+  double w = V[0][best], x = V[1][best], y = V[2][best], z = V[3][best];
+  const double n = sqrt(w * w + x * x + y * y + z * z);
+  w /= n; x /= n; y /= n; z /= n;
+  R[0] = w * w + x * x - y * y - z * z; R[1] = 2 * (x * y - w * z);           R[2] = 2 * (x * z + w * y);
+  R[3] = 2 * (x * y + w * z);           R[4] = w * w - x * x + y * y - z * z; R[5] = 2 * (y * z - w * x);
+  R[6] = 2 * (x * z - w * y);           R[7] = 2 * (y * z + w * x);           R[8] = w * w - x * x - y * y + z * z;
+}
+
+__global__ void so3_fwd_kernel(const float* __restrict__ M, int B, float* __restrict__ Rout) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  double R[9];
+  so3_project(M + (size_t)b * 9, R);
+  for (int e = 0; e < 9; ++e) Rout[(size_t)b * 9 + e] = (float)R[e];
+}
+
+// dL/dM = R [c]x with c = (tr(P) I - P)^-1 b, P = sym(R^T M), b = axial(R^T G - G^T R)
+__global__ void so3_bwd_kernel(const float* __restrict__ M, const float* __restrict__ G, int B, float* __restrict__ gM) {
+  const int bi = blockIdx.x * blockDim.x + threadIdx.x;
+  if (bi >= B) return;
+  double R[9], P[9], A[9];
+  const float* m = M + (size_t)bi * 9;
+  const float* g = G + (size_t)bi * 9;
+  so3_project(m, R);
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) {
+      double p = 0, a = 0;
+      for (int k = 0; k < 3; ++k) { p += R[k * 3 + i] * (double)m[k * 3 + j]; a += R[k * 3 + i] * (double)g[k * 3 + j]; }
+      P[i * 3 + j] = p; A[i * 3 + j] = a;
+    }
+  for (int i = 0; i < 3; ++i)
+    for (int j = i + 1; j < 3; ++j) { const double s = 0.5 * (P[i * 3 + j] + P[j * 3 + i]); P[i * 3 + j] = P[j * 3 + i] = s; }
+  const double b[3] = {A[7] - A[5], A[2] - A[6], A[3] - A[1]};
+  const double tr = P[0] + P[4] + P[8];
+  double K[9];
+  for (int i = 0; i < 9; ++i) K[i] = -P[i];
+  K[0] += tr; K[4] += tr; K[8] += tr;
+  // c = K^-1 b by cofactors (K is symmetric)
+  const double c00 = K[4] * K[8] - K[5] * K[7], c01 = K[5] * K[6] - K[3] * K[8], c02 = K[3] * K[7] - K[4] * K[6];
+  const double det = K[0] * c00 + K[1] * c01 + K[2] * c02;
+  const double c11 = K[0] * K[8] - K[2] * K[6], c12 = K[1] * K[6] - K[0] * K[7], c22 = K[0] * K[4] - K[1] * K[3];
+  const double inv = 1.0 / det;
+  const double c[3] = {(c00 * b[0] + c01 * b[1] + c02 * b[2]) * inv, (c01 * b[0] + c11 * b[1] + c12 * b[2]) * inv,
+                       (c02 * b[0] + c12 * b[1] + c22 * b[2]) * inv};
+  const double C[9] = {0, -c[2], c[1], c[2], 0, -c[0], -c[1], c[0], 0};
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) {
+      double s = 0;
+      for (int k = 0; k < 3; ++k) s += R[i * 3 + k] * C[k * 3 + j];
+      gM[(size_t)bi * 9 + i * 3 + j] = (float)s;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ ragged Chamfer
+// One CTA per cloud pair n; x points of pair n are rows [xo[n], xo[n+1]) of the packed [sum, 3] array.
+// loss += (1/N) * ( mean_i min_j |x_i - y_j|^2 + mean_j min_i |y_j - x_i|^2 )
+__global__ void __launch_bounds__(128) chamfer_fwd_kernel(const float* __restrict__ x, const int* __restrict__ xo, const float* __restrict__ y,
+                                                          const int* __restrict__ yo, int N, int* __restrict__ nn_x, int* __restrict__ nn_y,
+                                                          float* __restrict__ loss) {
+  const int n = blockIdx.x;
+  const int x0 = xo[n], x1 = xo[n + 1], y0 = yo[n], y1 = yo[n + 1];
+  float part = 0.f;
+  for (int dir = 0; dir < 2; ++dir) {
+    const float* a = dir == 0 ? x : y;  const float* b = dir == 0 ? y : x;
+    const int a0 = dir == 0 ? x0 : y0, a1 = dir == 0 ? x1 : y1, b0 = dir == 0 ? y0 : x0, b1 = dir == 0 ? y1 : x1;
+    int* nn = dir == 0 ? nn_x : nn_y;
+    const float scale = (a1 > a0) ? 1.f / (float)(a1 - a0) : 0.f;
+    for (int i = a0 + threadIdx.x; i < a1; i += blockDim.x) {
+      const float px = a[i * 3], py = a[i * 3 + 1], pz = a[i * 3 + 2];
+      float best = 3.4e38f; int bj = -1;
+      for (int j = b0; j < b1; ++j) {
+        const float dx = px - b[j * 3], dy = py - b[j * 3 + 1], dz = pz - b[j * 3 + 2];
+        const float d = dx * dx + dy * dy + dz * dz;
+        if (d < best) { best = d; bj = j; }
+      }
+      nn[i] = bj;
+      if (bj >= 0) part += best * scale;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+  if ((threadIdx.x & 31) == 0 && part != 0.f) atomicAdd(loss, part / (float)N);
+}
+
+__global__ void __launch_bounds__(128) chamfer_bwd_kernel(const float* __restrict__ x, const int* __restrict__ xo, const float* __restrict__ y,
+                                                          const int* __restrict__ yo, int N, const int* __restrict__ nn_x,
+                                                          const int* __restrict__ nn_y, const float* __restrict__ g_loss,
+                                                          float* __restrict__ gx, float* __restrict__ gy) {
+  const int n = blockIdx.x;
+  const float g = g_loss[0] / (float)N;
+  for (int dir = 0; dir < 2; ++dir) {
+    const float* a = dir == 0 ? x : y;  const float* b = dir == 0 ? y : x;
+    float* ga = dir == 0 ? gx : gy;  float* gb = dir == 0 ? gy : gx;
+    const int a0 = dir == 0 ? xo[n] : yo[n], a1 = dir == 0 ? xo[n + 1] : yo[n + 1];
+    const int* nn = dir == 0 ? nn_x : nn_y;
+    const float scale = (a1 > a0) ? 2.f * g / (float)(a1 - a0) : 0.f;
+    for (int i = a0 + threadIdx.x; i < a1; i += blockDim.x) {
+      const int j = nn[i];
+      if (j < 0) continue;
+      for (int c = 0; c < 3; ++c) {
+        const float d = (a[i * 3 + c] - b[j * 3 + c]) * scale;
+        atomicAdd(ga + i * 3 + c, d);
+        atomicAdd(gb + j * 3 + c, -d);
+      }
+    }
+  }
+}
+
+}  // namespace vt
+
+using namespace vt;
+
+extern "C" {
+
+int vt_so3_project_fwd(const float* M, int B, float* R, void* stream) {
+  if (B <= 0) return 0;
+  so3_fwd_kernel<<<ceil_div(B, 64), 64, 0, (cudaStream_t)stream>>>(M, B, R);
+  VT_CHECK_LAUNCH("vt_so3_project_fwd");
+  return 0;
+}
+
+int vt_so3_project_bwd(const float* M, const float* gR, int B, float* gM, void* stream) {
+  if (B <= 0) return 0;
+  so3_bwd_kernel<<<ceil_div(B, 64), 64, 0, (cudaStream_t)stream>>>(M, gR, B, gM);
+  VT_CHECK_LAUNCH("vt_so3_project_bwd");
+  return 0;
+}
+
+int vt_chamfer_fwd(const float* x, const int* x_off, const float* y, const int* y_off, int N, int* nn_x, int* nn_y, float* loss,
+                   void* stream) {
+  if (N <= 0) return 0;
+  cudaError_t e = cudaMemsetAsync(loss, 0, sizeof(float), (cudaStream_t)stream);
+  if (e != cudaSuccess) return cuda_fail(e, "vt_chamfer_fwd memset");
+  chamfer_fwd_kernel<<<N, 128, 0, (cudaStream_t)stream>>>(x, x_off, y, y_off, N, nn_x, nn_y, loss);
+  VT_CHECK_LAUNCH("vt_chamfer_fwd");
+  return 0;
+}
+
+int vt_chamfer_bwd(const float* x, const int* x_off, const float* y, const int* y_off, int N, const int* nn_x, const int* nn_y,
+                   const float* g_loss, float* gx, float* gy, void* stream) {
+  if (N <= 0) return 0;
+  chamfer_bwd_kernel<<<N, 128, 0, (cudaStream_t)stream>>>(x, x_off, y, y_off, N, nn_x, nn_y, g_loss, gx, gy);
+  VT_CHECK_LAUNCH("vt_chamfer_bwd");
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,81 @@
+"""Differentiable wrappers of the joint-optimisation helpers (csrc/geom.cu): SO(3) projection, rigid object transform and the
+ragged Chamfer distance of the contact loss."""
+from __future__ import annotations
+
+from typing import List
+
+import torch
+
+from . import _lib
+
+P, S = _lib.ptr, _lib.stream_ptr
+
+
+class _So3Fn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, mat):
+        m = mat.detach().float().contiguous()
+        out = torch.empty_like(m)
+        with torch.cuda.device(m.device):
+            _lib.call("vt_so3_project_fwd", P(m), m.shape[0], P(out), S())
+        ctx.save_for_backward(m)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        (m,) = ctx.saved_tensors
+        g = g.float().contiguous()
+        gm = torch.empty_like(m)
+        with torch.cuda.device(m.device):
+            _lib.call("vt_so3_project_bwd", P(m), P(g), m.shape[0], P(gm), S())
+        return gm
+
+
+def project_so3(mat: torch.Tensor) -> torch.Tensor:
+    """ReconFitterBase.project_so3 (recon/recon_fit_base.py:178-199) for mat [B, 3, 3] on a CUDA device."""
+    assert mat.shape[1:] == (3, 3), f"invalid shape {mat.shape}"
+    if not mat.is_cuda:
+        raise RuntimeError("vistracker_b200 has no CPU path")
+    return _So3Fn.apply(mat)
+
+
+def decopose_axis(rot: torch.Tensor, no_rand: bool = False, noise: torch.Tensor = None) -> torch.Tensor:
+    """ReconFitterBase.decopose_axis (recon_fit_base.py:461-469): SO(3) projection of ``rot + 1e-4 * U(0,1)``.  ``noise``
+    lets the caller inject the uniform tensor (parity runs replay the oracle's draws)."""
+    if no_rand:
+        return project_so3(rot)
+    if noise is None:
+        noise = torch.rand(rot.shape[0], 3, 3, device=rot.device)
+    return project_so3(rot + 1e-4 * noise)
+
+
+class _ChamferFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, y, x_off, y_off):
+        xc, yc = x.detach().float().contiguous(), y.detach().float().contiguous()
+        n = x_off.numel() - 1
+        nn_x = torch.empty(xc.shape[0], dtype=torch.int32, device=xc.device)
+        nn_y = torch.empty(yc.shape[0], dtype=torch.int32, device=xc.device)
+        loss = torch.empty(1, dtype=torch.float32, device=xc.device)
+        with torch.cuda.device(xc.device):
+            _lib.call("vt_chamfer_fwd", P(xc), P(x_off), P(yc), P(y_off), n, P(nn_x), P(nn_y), P(loss), S())
+        ctx.save_for_backward(xc, yc, x_off, y_off, nn_x, nn_y)
+        return loss[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        xc, yc, x_off, y_off, nn_x, nn_y = ctx.saved_tensors
+        gx, gy = torch.zeros_like(xc), torch.zeros_like(yc)
+        gl = g.reshape(1).float().contiguous()
+        with torch.cuda.device(xc.device):
+            _lib.call("vt_chamfer_bwd", P(xc), P(x_off), P(yc), P(y_off), x_off.numel() - 1, P(nn_x), P(nn_y), P(gl), P(gx), P(gy), S())
+        return gx, gy, None, None
+
+
+def chamfer_distance_ragged(xs: List[torch.Tensor], ys: List[torch.Tensor]) -> torch.Tensor:
+    """pytorch3d.loss.chamfer_distance(Pointclouds(xs), Pointclouds(ys))[0] with default reductions, for lists of [n_i, 3]
+    clouds (recon/recon_fit_trivis_full.py:452-456).  Differentiable w.r.t. every cloud."""
+    assert len(xs) == len(ys) and len(xs) > 0
+    dev = xs[0].device
+    off = lambda cl: torch.tensor([0] + list(torch.tensor([c.shape[0] for c in cl]).cumsum(0)), dtype=torch.int32, device=dev)
+    return _ChamferFn.apply(torch.cat(xs, 0), torch.cat(ys, 0), off(xs), off(ys))
