@@ -181,6 +181,20 @@ int vt_chamfer_fwd(const float* x, const int* x_off, const float* y, const int* 
 int vt_chamfer_bwd(const float* x, const int* x_off, const float* y, const int* y_off, int N, const int* nn_x, const int* nn_y,
                    const float* g_loss, float* gx, float* gy, void* stream);
 
+/* ---- rasteriser with neural_renderer semantics (third-party, un-vendored: restated from the upstream algorithm, PARITY
+ *      UNPINNED): silhouettes for SilLossROI (recon/obj_pose_roi.py:87-94,183-202) and orthographic depth / occupancy for the
+ *      triplane renderings (render/render_triplane_nr.py:25-30,88-110).  fill_back = True, near 0.1, far 100, no anti-aliasing. ---- */
+
+/* verts[B][V][3] camera-space, faces[F][3] (shared); mode 0: nr.projection with K4[B][4] = (fx, fy, cx, cy) normalised to the ROI
+ * (orig_size 1), mode 1: orthographic (x, y in [-1, 1] rasterised directly).  Outputs: faces_ndc[B][2F][9] and face_index[B][S][S]
+ * (kept for backward), alpha[B][S][S] and / or depth[B][S][S] (either may be NULL). */
+int vt_raster_fwd(const float* verts, const int* faces, int B, int V, int F, int mode, const float* K4, int image_size,
+                  float* faces_ndc, int* face_index, float* alpha, float* depth, void* stream);
+/* NMR pseudo-gradient: g_alpha[B][S][S] -> g_verts[B][V][3] (overwritten); g_faces[B][2F][9] is scratch. */
+int vt_raster_bwd(const float* verts, const int* faces, int B, int V, int F, int mode, const float* K4, int image_size,
+                  const float* faces_ndc, const int* face_index, const float* alpha, const float* g_alpha, float* g_faces,
+                  float* g_verts, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

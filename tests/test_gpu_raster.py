@@ -1,0 +1,94 @@
+"""Rasteriser kernels on the B200 against the numpy restatement of neural_renderer's algorithm (oracle/raster_ref.py; parity
+UNPINNED: the third-party package itself is not available, see the oracle's header)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import rel_err
+from oracle import raster_ref as R
+
+pytestmark = pytest.mark.gpu
+
+
+def _need_gpu():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+
+
+def _mesh(seed, n=10):
+    """A closed triangulated surface: convex hull of random points on an ellipsoid."""
+    from scipy.spatial import ConvexHull
+    rng = np.random.Generator(np.random.PCG64(seed))
+    p = rng.standard_normal((n, 3)); p /= np.linalg.norm(p, axis=1, keepdims=True)
+    p *= np.array([0.5, 0.35, 0.4])
+    hull = ConvexHull(p)
+    return p.astype(np.float32), hull.simplices.astype(np.int64)
+
+
+def _pose(verts, seed):
+    rng = np.random.Generator(np.random.PCG64(seed))
+    a = rng.uniform(-0.6, 0.6, 3)
+    Rx = np.array([[1, 0, 0], [0, np.cos(a[0]), -np.sin(a[0])], [0, np.sin(a[0]), np.cos(a[0])]])
+    Ry = np.array([[np.cos(a[1]), 0, np.sin(a[1])], [0, 1, 0], [-np.sin(a[1]), 0, np.cos(a[1])]])
+    return (verts @ (Rx @ Ry).T + np.array([rng.uniform(-0.1, 0.1), rng.uniform(-0.1, 0.1), 2.4])).astype(np.float32)
+
+
+def test_silhouette_forward_and_pseudo_gradient_match_the_restatement():
+    _need_gpu()
+    from vistracker_b200.render import SilhouetteRenderer
+    size = 40
+    verts0, faces = _mesh(0)
+    K4 = np.array([1.9, 1.9, 0.5, 0.5])
+    K = torch.tensor([[K4[0], 0, K4[2]], [0, K4[1], K4[3]], [0, 0, 1]], dtype=torch.float32)
+    batch = [_pose(verts0, s) for s in (1, 2)]
+    ref_img = [R.rasterize(R.faces_of(R.project(_pose(verts0, s + 10).astype(np.float64), K4), faces), size)[1] for s in (1, 2)]
+    rend = SilhouetteRenderer(faces, size, K[None].repeat(2, 1, 1), "cuda:0")
+    v = torch.from_numpy(np.stack(batch)).cuda().requires_grad_(True)
+    img = rend(v)
+    keep = torch.ones(2, size, size, device="cuda"); keep[:, :6] = 0           # an occluder strip
+    target = torch.from_numpy(np.stack(ref_img)).float().cuda()
+    loss = ((keep * img - target) ** 2).sum()
+    loss.backward()
+    for b in range(2):
+        vb = batch[b].astype(np.float64)
+        fv = R.faces_of(R.project(vb, K4), faces)
+        idx, alpha, _ = R.rasterize(fv, size)
+        assert 30 < alpha.sum() < size * size / 2
+        assert np.array_equal(img[b].detach().cpu().numpy(), alpha.astype(np.float32)), "coverage differs"
+        g_alpha = 2 * (keep[b].cpu().numpy() * alpha - ref_img[b]) * keep[b].cpu().numpy()
+        g_faces = R.backward_faces(fv, idx, alpha, g_alpha, size)
+        g_ref = R.backward_verts(g_faces, vb, faces, K4)
+        assert np.abs(g_ref).max() > 0
+        assert rel_err(v.grad[b].cpu(), g_ref) < 2e-3
+
+
+def test_triplane_occupancy_matches_the_restatement():
+    _need_gpu()
+    from vistracker_b200.render import TriplaneNrRenderer
+    verts, faces = _mesh(4, n=14)
+    verts = verts * 1.3
+    tr = TriplaneNrRenderer(image_size=24, device="cuda:0")
+    masks = tr.render_3views(faces, torch.from_numpy(verts)[None])
+    assert masks.shape == (1, 3, 24, 24) and masks.dtype == torch.uint8
+    for vi, view in enumerate(("right", "back", "top")):
+        local = TriplaneNrRenderer.transform_view(torch.from_numpy(verts), view).numpy().astype(np.float64)
+        _, alpha, depth = R.rasterize(R.faces_of(local, faces), 48)
+        ref = (depth.reshape(24, 2, 24, 2).mean((1, 3)) < R.FAR)          # average-pooled depth < far  (anti_aliasing=True)
+        assert np.array_equal(masks[0, vi].cpu().numpy().astype(bool), ref), view
+        assert 20 < ref.sum() < 24 * 24
+
+
+def test_axis_aligned_square_is_rendered_with_flipped_rows():
+    _need_gpu()
+    from vistracker_b200.render import SilhouetteRenderer
+    # orthographic: a quad covering x in [-0.5, 0.25], y in [0.0, 0.75] (NDC, y up) at depth 5
+    verts = torch.tensor([[[-0.5, 0.0, 5.0], [0.25, 0.0, 5.0], [0.25, 0.75, 5.0], [-0.5, 0.75, 5.0]]], device="cuda")
+    faces = np.array([[0, 1, 2], [0, 2, 3]])
+    img = SilhouetteRenderer(faces, 16, None, "cuda:0")(verts)[0].cpu().numpy()
+    xs = (2 * np.arange(16) + 1 - 16) / 16
+    exp = np.zeros((16, 16), np.float32)
+    for r in range(16):
+        for c in range(16):
+            yp, xp = xs[15 - r], xs[c]                      # image row 0 is the top (y = +1)
+            exp[r, c] = float(-0.5 <= xp <= 0.25 and 0.0 <= yp <= 0.75)
+    assert np.array_equal(img, exp)
