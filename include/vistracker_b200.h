@@ -99,6 +99,14 @@ int vt_query_bwd(const float* points, const float* crop_center, const float* bod
                  int Wt, int c_im, int c_tmpx, int c_tt, int c_tf, const float* cam7, const float* wpack, const float* wpack_bwd,
                  const float* g_out, float* g_points, void* stream);
 
+/* One step of Generator.approx_surface (recon/gen/generator.py:72-104) fused into one launch: predictions at `points`
+ * (written to out[B][29][N] when not NULL), d sum(clamp(df[df_idx], max=threshold)) / d points (g_points, optional) and
+ * points_out = points - normalize(grad, eps 1e-12) * clamp(df[df_idx], max=threshold). */
+int vt_query_project_step(const float* points, const float* crop_center, const float* body_center, int B, int N,
+                          const float* im_feat, const float* tmpx, const float* tri_tmpx, const float* tri_feat, int Hf, int Wf, int Ht,
+                          int Wt, int c_im, int c_tmpx, int c_tt, int c_tf, const float* cam7, const float* wpack, const float* wpack_bwd,
+                          int df_idx, float threshold, float* points_out, float* out, float* g_points, void* stream);
+
 /* ---- SMPL-H layer: SMPL_Layer.forward (lib_smpl/smplpytorch/smplpytorch/pytorch/smpl_layer.py:73-176) and its gradient
  *      w.r.t. pose / betas / trans; landmark regressors (lib_smpl/torch_functions.py:52-76, wrapper_pytorch.py:187-203) ---- */
 

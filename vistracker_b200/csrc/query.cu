@@ -262,7 +262,13 @@ __global__ void __launch_bounds__(256, 1) query_bwd_kernel(const float* __restri
                                                            QueryCam cam, const float* __restrict__ wpack,
                                                            const float* __restrict__ wpack_bwd,
                                                            const float* __restrict__ g_out /*[B][29][N]*/,
-                                                           float* __restrict__ g_points /*[B][N][3]*/) {
+                                                           float* __restrict__ g_points /*[B][N][3]*/,
+                                                           int mode, int df_idx, float threshold,
+                                                           float* __restrict__ out /*[B][29][N] or null*/,
+                                                           float* __restrict__ points_out /*[B][N][3] (mode 1)*/) {
+  // mode 0: generic vector-Jacobian product with the cotangent g_out.
+  // mode 1: one step of Generator.approx_surface (recon/gen/generator.py:86-98): cotangent = d sum(clamp(df[df_idx], max=thr)),
+  //         points_out = p - normalize(grad) * clamp(df, max=thr); `out` (optional) receives the predictions at p.
   extern __shared__ float smem[];
   float* featT = smem;                       // [616][33]
   float* gfeatT = featT + QK * QLD;          // [616][33]   gradient w.r.t. the features, summed over the heads
@@ -271,6 +277,7 @@ __global__ void __launch_bounds__(256, 1) query_bwd_kernel(const float* __restri
   float* sW = hB + QH * QLD;                 // [32][128]
   float* g4s = sW + QKC * QH;                // [16][33]
   __shared__ int s_in_img[QP];
+  __shared__ float s_df[QP];
   const int b = blockIdx.y, n0 = blockIdx.x * QP;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
@@ -279,6 +286,7 @@ __global__ void __launch_bounds__(256, 1) query_bwd_kernel(const float* __restri
   __syncthreads();
 
   for (int h = 0; h < Q_NHEAD; ++h) {
+    if (mode == 1 && h > 0 && !out) break;            // only the distance head carries gradient in a projection step
     const HeadW w = head_weights(wpack, h);
     const float* W1b = wpack_bwd + (size_t)h * q_head_stride_bwd();
     const float* W2b = W1b + QH * QKB;
@@ -293,19 +301,27 @@ __global__ void __launch_bounds__(256, 1) query_bwd_kernel(const float* __restri
     for (int c = warp; c < 16; c += 8) {
       float g = 0.f;
       if (c < nout && n0 + lane < N) {
-        g = g_out[((size_t)b * Q_NOUT + off + c) * N + n0 + lane];
-        if (h == 4) {
+        float val = 0.f;
+        if (h == 4 || mode == 1) {                    // the head output itself is needed
           float acc = w.b4[c];
 #pragma unroll 8
           for (int k = 0; k < QH; ++k) acc = fmaf(hA[(size_t)k * QLD + lane], w.W4[k * 16 + c], acc);
-          const float s = 1.f / (1.f + expf(-acc));
-          g *= s * (1.f - s);
+          val = h == 4 ? 1.f / (1.f + expf(-acc)) : acc;
+          if (h == 0 && !s_in_img[lane]) val = cam.out_dist;
+        }
+        if (mode == 0) {
+          g = g_out[((size_t)b * Q_NOUT + off + c) * N + n0 + lane];
+          if (h == 4) g *= val * (1.f - val);
+        } else {
+          if (out) out[((size_t)b * Q_NOUT + off + c) * N + n0 + lane] = val;
+          if (h == 0 && c == df_idx) { g = val <= threshold ? 1.f : 0.f; s_df[lane] = fminf(val, threshold); }
         }
         if (h == 0 && !s_in_img[lane]) g = 0.f;
       }
       g4s[c * QLD + lane] = g;
     }
     __syncthreads();
+    if (mode == 1 && h > 0) continue;                 // forward-only heads (predictions requested)
     // layer 4 backward: gh3[k] = relu'(h3[k]) * sum_c g4[c] * W4b[c][k]
     {
       float acc[16];
@@ -382,10 +398,13 @@ __global__ void __launch_bounds__(256, 1) query_bwd_kernel(const float* __restri
       gx += __shfl_xor_sync(0xffffffffu, gx, o); gy += __shfl_xor_sync(0xffffffffu, gy, o); gz += __shfl_xor_sync(0xffffffffu, gz, o);
     }
     if (lane == 0) {
-      float* gp = g_points + ((size_t)b * N + n) * 3;
-      gp[0] = gx + gfeatT[(size_t)(src + 0) * QLD + pp];
-      gp[1] = gy + gfeatT[(size_t)(src + 1) * QLD + pp];
-      gp[2] = gz + gfeatT[(size_t)(src + 2) * QLD + pp];
+      gx += gfeatT[(size_t)(src + 0) * QLD + pp]; gy += gfeatT[(size_t)(src + 1) * QLD + pp]; gz += gfeatT[(size_t)(src + 2) * QLD + pp];
+      if (g_points) { float* gp = g_points + ((size_t)b * N + n) * 3; gp[0] = gx; gp[1] = gy; gp[2] = gz; }
+      if (mode == 1) {     // samples - F.normalize(gradient, dim=2) * df_target   (eps 1e-12, generator.py:96)
+        const float inv = 1.f / fmaxf(sqrtf(gx * gx + gy * gy + gz * gz), 1e-12f), d = s_df[pp];
+        float* po = points_out + ((size_t)b * N + n) * 3;
+        po[0] = q.x - gx * inv * d; po[1] = q.y - gy * inv * d; po[2] = q.z - gz * inv * d;
+      }
     }
   }
 }
@@ -434,8 +453,29 @@ int vt_query_bwd(const float* points, const float* crop_center, const float* bod
   cudaError_t e = cudaFuncSetAttribute(query_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return cuda_fail(e, "vt_query_bwd smem attr");
   dim3 grid(ceil_div(N, QP), B);
-  query_bwd_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(points, crop_center, body_center, B, N, m, cam, wpack, wpack_bwd, g_out, g_points);
+  query_bwd_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(points, crop_center, body_center, B, N, m, cam, wpack, wpack_bwd, g_out, g_points,
+                                                              0, 0, 0.f, nullptr, nullptr);
   VT_CHECK_LAUNCH("vt_query_bwd");
+  return 0;
+}
+
+int vt_query_project_step(const float* points, const float* crop_center, const float* body_center, int B, int N,
+                          const float* im_feat, const float* tmpx, const float* tri_tmpx, const float* tri_feat, int Hf, int Wf, int Ht,
+                          int Wt, int c_im, int c_tmpx, int c_tt, int c_tf, const float* cam7, const float* wpack, const float* wpack_bwd,
+                          int df_idx, float threshold, float* points_out, float* out, float* g_points, void* stream) {
+  if (int rc = check_layout("vt_query_project_step", c_im, c_tmpx, c_tt, c_tf)) return rc;
+  VT_CHECK_ARG(df_idx == 0 || df_idx == 1, "vt_query_project_step: df_idx %d (0 human, 1 object)", df_idx);
+  VT_CHECK_ARG(points_out != nullptr, "vt_query_project_step: points_out is required");
+  if (B <= 0 || N <= 0) return 0;
+  QueryMaps m{im_feat, tmpx, tri_tmpx, tri_feat, Hf, Wf, Ht, Wt, c_im, c_tmpx, c_tt, c_tf};
+  QueryCam cam{cam7[0], cam7[1], cam7[2], cam7[3], cam7[4], cam7[5], cam7[6]};
+  size_t smem = (size_t)(2 * QK * QLD + 2 * QH * QLD + QKC * QH + 16 * QLD) * sizeof(float);
+  cudaError_t e = cudaFuncSetAttribute(query_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return cuda_fail(e, "vt_query_project_step smem attr");
+  dim3 grid(ceil_div(N, QP), B);
+  query_bwd_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(points, crop_center, body_center, B, N, m, cam, wpack, wpack_bwd, nullptr, g_points,
+                                                              1, df_idx, threshold, out, points_out);
+  VT_CHECK_LAUNCH("vt_query_project_step");
   return 0;
 }
 
