@@ -195,6 +195,106 @@ def fit_smplt_goldens(out_dir: str):
     print("fit_smplt_small: losses", losses[0], "->", losses[-1])
 
 
+def recon_goldens(out_dir: str):
+    """forward_smpl (phase 'kpts') and forward_step (phases 'object only', 'joint') of the UNMODIFIED reference fitter classes,
+    called unbound on CPU with a bare ``self`` (recon/recon_fit_behave.py:467-513, recon/recon_fit_trivis_full.py:193-270).
+    pytorch3d's chamfer_distance is not installable -> the contact term goes through oracle.geom_ref.chamfer_ragged."""
+    from argparse import Namespace
+    for n in ("trimesh", "igl", "open3d", "zstd", "neural_renderer"):
+        _stub(n)
+    from oracle.geom_ref import chamfer_ragged
+
+    class Pointclouds:                                   # stand-in for pytorch3d.structures.Pointclouds
+        def __init__(self, pts): self.pts = pts
+    _stub("pytorch3d"); _stub("pytorch3d.loss", chamfer_distance=lambda a, b: (chamfer_ragged(a.pts, b.pts), None))
+    _stub("pytorch3d.structures", Pointclouds=Pointclouds, Meshes=None); _stub("pytorch3d.ops", knn_points=None, sample_points_from_meshes=None)
+    _stub("mesh_intersection"); _stub("mesh_intersection.bvh_search_tree", BVH=object); _stub("mesh_intersection.loss")
+    _stub("detectron2"); _stub("detectron2.structures", BitMasks=object, BoxMode=object, Boxes=object); _stub("detectron2.structures.boxes", BoxMode=object)
+    for m in list(sys.modules):
+        if m.startswith(("psbody", "pytorch3d", "detectron2", "mesh_intersection", "skimage", "chumpy")):
+            sys.modules[m].__path__ = []
+    sys.modules["psbody.mesh"].MeshViewers = object
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    import lib_smpl.th_hand_prior as hp_mod
+    hp_mod.HandPrior.__init__.__defaults__ = tuple("cpu" if x == "cuda:0" else x for x in hp_mod.HandPrior.__init__.__defaults__)
+    from config.config_loader import load_configs
+    from model import CHORETriplaneVisibility
+    from model.camera import KinectColorCamera
+    from lib_smpl.smplpytorch.smplpytorch.pytorch.smpl_layer import SMPL_Layer
+    from lib_smpl.wrapper_pytorch import SMPLPyTorchWrapperBatchSplitParams
+    from lib_smpl.body_landmark import load_regressors
+    import recon.recon_fit_trivis_full as M                                                # reference
+    import recon.recon_fit_base as MB
+    MB.chamfer_distance = M.chamfer_distance = sys.modules["pytorch3d.loss"].chamfer_distance
+    MB.Pointclouds = M.Pointclouds = Pointclouds
+    from vistracker_b200.config import resolve_dims
+    from vistracker_b200.synth import synthetic_state_dict
+    sys.path.insert(0, os.path.dirname(HERE))
+    from recon_problem import B, make_problem
+
+    d = make_problem()
+    with contextlib.redirect_stdout(io.StringIO()):
+        opt = load_configs("tri-vis-l2")
+        net = CHORETriplaneVisibility(opt).eval()
+    net.load_state_dict(synthetic_state_dict(resolve_dims(opt), seed=0))
+    for p in net.parameters():
+        p.requires_grad = False
+    with torch.no_grad():
+        net.filter(d["images"])
+    L = SMPL_Layer.__new__(SMPL_Layer); torch.nn.Module.__init__(L)
+    L.hands, L.num_joints, L.kintree_parents = True, 52, list(d["model"]["parents"])
+    for k in ("th_betas", "th_shapedirs", "th_posedirs", "th_v_template", "th_J_regressor", "th_weights"):
+        L.register_buffer(k, d["model"][k])
+
+    def make_smpl():
+        S = SMPLPyTorchWrapperBatchSplitParams.__new__(SMPLPyTorchWrapperBatchSplitParams); torch.nn.Module.__init__(S)
+        P = torch.nn.Parameter
+        S.global_pose, S.body_pose, S.hand_pose = P(d["pose"][:, :3].clone()), P(d["pose"][:, 3:66].clone()), P(d["pose"][:, 66:].clone())
+        S.top_betas, S.other_betas, S.trans = P(d["betas"][:, :2].clone()), P(d["betas"][:, 2:].clone()), P(d["trans"].clone())
+        S.offsets = P(torch.zeros(B, 6890, 3)); S.smpl = L; S.faces = None
+        S.body25_reg_torch, S.face_reg_torch, S.hand_reg_torch = load_regressors("assets", batch_size=B)
+        S.verts = S.jtr = S.tposed = S.naked = None
+        S.betas = torch.cat([S.top_betas, S.other_betas], 1); S.pose = torch.cat([S.global_pose, S.body_pose, S.hand_pose], 1)
+        return S
+
+    F = M.ReconFitterTriVisFull.__new__(M.ReconFitterTriVisFull)
+    F.camera, F.net_in_size, F.debug, F.z_0, F.device, F.obj_scale = KinectColorCamera(1200), 512, False, 2.2, "cpu", 1.0
+    F.part_labels, F.collision_loss, F.args = d["labels"], False, Namespace(model_name="chore-triplane-vis")
+    F.part_names = [str(i) for i in range(14)]
+    weights = F.get_loss_weights()
+    qd = {"crop_center": d["crop"], "body_center": d["body_center"]}
+    out = {}
+    # ---- forward_smpl, phase 'kpts'
+    S = make_smpl()
+    dd = {"part_labels": d["labels"][None].repeat(B, 1), "net": net, "query_dict": qd, "pose_init": d["pose_init"], "body_kpts": d["body_kpts"]}
+    ld = F.forward_smpl(S, dd, "kpts")
+    F.sum_dict(ld, weights, 2 / 3).backward()
+    for k, v in ld.items():
+        out[f"smpl_{k}"] = np.float64(v.item())
+    out["smpl_g_pose"] = torch.cat([S.global_pose.grad, S.body_pose.grad], 1).numpy().copy()
+    out["smpl_g_betas"] = torch.cat([S.top_betas.grad, S.other_betas.grad], 1).numpy().copy()
+    out["smpl_g_trans"] = S.trans.grad.numpy().copy()
+    # ---- forward_step, phases 'object only' and 'joint'
+    for phase in ("object only", "joint"):
+        S = make_smpl()
+        R_, t_ = d["obj_R"].clone().requires_grad_(True), d["obj_t"].clone().requires_grad_(True)
+        dd = {"objects": d["objects"], "query_dict": qd, "occ_ratios": d["occ"], "smpl_center": d["smpl_center"],
+              "df_obj_h": d["df_obj_h"], "df_hum_o": d["df_hum_o"], "parts_obj": d["parts_obj"]}
+        real_rand = torch.rand
+        torch.rand = lambda *a, **k: d["noise"].clone()            # decopose_axis: rot + 1e-4 * torch.rand(B, 3, 3)
+        try:
+            ld = F.forward_step(net, S, dd, R_, t_, d["obj_s"], phase)
+        finally:
+            torch.rand = real_rand
+        F.sum_dict(ld, weights, 1 if phase == "object only" else 4 / 3).backward()
+        tag = "obj" if phase == "object only" else "joint"
+        for k, v in ld.items():
+            out[f"{tag}_{k}"] = np.float64(v.item())
+        out[f"{tag}_g_R"], out[f"{tag}_g_t"] = R_.grad.numpy().copy(), t_.grad.numpy().copy()
+    np.savez_compressed(os.path.join(out_dir, "recon_small.npz"), **out)
+    print("recon_small:", {k: (float(v) if np.ndim(v) == 0 else v.shape) for k, v in out.items()})
+
+
 def asset_fixtures(out_dir: str, ref_root: str):
     """Numeric assets the reference ships for this path, re-serialised without scipy / pickle:
     the body-25 landmark regressor (COO), the pose / hand priors and the 14-part vertex labels."""
@@ -234,3 +334,5 @@ if __name__ == "__main__":
         asset_fixtures(HERE, a.ref)
     if a.only in ("", "fit"):
         fit_smplt_goldens(HERE)
+    if a.only in ("", "recon"):
+        recon_goldens(HERE)
