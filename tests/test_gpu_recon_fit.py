@@ -96,7 +96,7 @@ def test_optimisation_loops_run_and_reduce_the_loss(ctx):
           "silhouette": sil}
     fitter.get_opt_iters = staticmethod(lambda: {"sil": 2, "object": 2})
     _, R_out, t_out, hist = fitter.optimize_smpl_object(smpl, dd, joint_iter=1, steps_per_iter=2, max_iter=1)
-    assert len(hist) == 12 and np.isfinite(hist).all()
+    assert 8 <= len(hist) <= 12 and np.isfinite(hist).all()          # 6 outer x 2 steps unless the joint-phase early stop fires
     assert "trans_init" in dd and "df_obj_h" in dd
     Rf = fitter.final_rotation(R_out)
     assert rel_err((Rf @ Rf.transpose(1, 2)).cpu(), torch.eye(3).expand(B, 3, 3)) < 1e-5
