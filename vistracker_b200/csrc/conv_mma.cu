@@ -19,6 +19,7 @@
 // Roles (192 threads): warps 0-3 epilogue (one TMEM lane = one output pixel each), warp 4 TMA producer, warp 5 MMA
 // issuer.  One output tile per CTA; STAGES-deep mbarrier ring between TMA and MMA.
 #include <cuda.h>
+#include <stdlib.h>
 #include "common.cuh"
 #include "vt_internal.h"
 
@@ -111,9 +112,72 @@ __device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t saddr) {
   return d;
 }
 
+// Epilogue shared by both kernels (warps 0-3).  Every TMA load has landed and every MMA has retired (bar_accum), so the pipeline
+// buffers are free: the fp32 tile is staged there so that global stores / residual loads are whole, coalesced pixel rows.
+template <int BN>
+__device__ __forceinline__ void conv_epilogue(const ConvMmaParams& p, uint32_t bar_accum_addr, uint32_t tmem_base, float* stile,
+                                              float* s_sum, float* s_sq, int img, int n0, int y0, int x0) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  mbar_wait(bar_accum_addr, 0);
+  tc_fence_after();
+  constexpr int LDT = BN + 4;
+  {
+    const int r = warp * 32 + lane;                             // tile row == TMEM lane
+    const uint32_t lane_base = tmem_base + ((uint32_t)(warp * 32) << 16);
+#pragma unroll 1
+    for (int ch = 0; ch < BN / 32; ++ch) {
+      float v[32], w[32];
+      tc_ld32(lane_base + ch * 32, v);
+      tc_ld32(lane_base + BN + ch * 32, w);
+#pragma unroll
+      for (int i = 0; i < 32; i += 4)
+        *reinterpret_cast<float4*>(&stile[r * LDT + ch * 32 + i]) =
+            make_float4(fmaf(w[i], kLoInv, v[i]), fmaf(w[i + 1], kLoInv, v[i + 1]), fmaf(w[i + 2], kLoInv, v[i + 2]), fmaf(w[i + 3], kLoInv, v[i + 3]));
+    }
+  }
+  asm volatile("bar.sync 1, 128;" ::: "memory");                // the four epilogue warps only
+  constexpr int LPR = BN / 4;                                   // lanes per pixel row (float4 each)
+  constexpr int RPI = 32 / LPR;                                 // pixel rows per warp iteration
+  const int cl = lane % LPR, rsub = lane / LPR;
+  float4 bz = make_float4(0, 0, 0, 0);
+  if (p.bias) bz = ld4(p.bias + n0 + cl * 4);
+  float4 s4 = make_float4(0, 0, 0, 0), q4 = s4;
+#pragma unroll 4
+  for (int rr = warp * 32 + rsub; rr < warp * 32 + 32; rr += RPI) {
+    const int y = y0 + rr / p.bw, x = x0 + rr % p.bw;
+    const size_t pix = ((size_t)img * p.H + y) * p.W + x;
+    float4 v = *reinterpret_cast<const float4*>(&stile[rr * LDT + cl * 4]);
+    v.x += bz.x; v.y += bz.y; v.z += bz.z; v.w += bz.w;
+    if (p.res) { const float4 rv = ld4(p.res + pix * p.ldr + n0 + cl * 4); v.x += rv.x; v.y += rv.y; v.z += rv.z; v.w += rv.w; }
+    st4(p.out + pix * p.ldo + n0 + cl * 4, v);
+    s4.x += v.x; s4.y += v.y; s4.z += v.z; s4.w += v.w;
+    q4.x += v.x * v.x; q4.y += v.y * v.y; q4.z += v.z * v.z; q4.w += v.w * v.w;
+  }
+  if (p.stats) {
+#pragma unroll
+    for (int o = LPR; o < 32; o <<= 1) {                        // fold the RPI row groups of the warp
+      s4.x += __shfl_xor_sync(0xffffffffu, s4.x, o); s4.y += __shfl_xor_sync(0xffffffffu, s4.y, o);
+      s4.z += __shfl_xor_sync(0xffffffffu, s4.z, o); s4.w += __shfl_xor_sync(0xffffffffu, s4.w, o);
+      q4.x += __shfl_xor_sync(0xffffffffu, q4.x, o); q4.y += __shfl_xor_sync(0xffffffffu, q4.y, o);
+      q4.z += __shfl_xor_sync(0xffffffffu, q4.z, o); q4.w += __shfl_xor_sync(0xffffffffu, q4.w, o);
+    }
+    if (rsub == 0) {
+      atomicAdd(&s_sum[cl * 4 + 0], s4.x); atomicAdd(&s_sum[cl * 4 + 1], s4.y); atomicAdd(&s_sum[cl * 4 + 2], s4.z); atomicAdd(&s_sum[cl * 4 + 3], s4.w);
+      atomicAdd(&s_sq[cl * 4 + 0], q4.x); atomicAdd(&s_sq[cl * 4 + 1], q4.y); atomicAdd(&s_sq[cl * 4 + 2], q4.z); atomicAdd(&s_sq[cl * 4 + 3], q4.w);
+    }
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    if (threadIdx.x < BN) {
+      double* st = p.stats + ((size_t)img * p.ld_stats + n0 + threadIdx.x) * 2;
+      atomicAdd(st, (double)s_sum[threadIdx.x]);
+      atomicAdd(st + 1, (double)s_sq[threadIdx.x]);
+    }
+  }
+}
+
 template <int BN>
 struct MmaCfg {
-  static constexpr int STAGES = BN == 128 ? 3 : 4;
+  static constexpr int STAGES = BN == 128 ? 3 : 2;                 // BN <= 64: two CTAs per SM share the shared memory
+  static constexpr int MIN_CTAS = BN == 128 ? 1 : 2;
   static constexpr int A_BYTES = MM_M * MM_KC * 2;                 // 16 KB per plane
   static constexpr int B_BYTES = BN * MM_KC * 2;
   static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
@@ -124,7 +188,7 @@ struct MmaCfg {
 };
 
 template <int BN>
-__global__ void __launch_bounds__(MM_THREADS, 1)
+__global__ void __launch_bounds__(MM_THREADS, MmaCfg<BN>::MIN_CTAS)
 conv_mma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                 const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo, const ConvMmaParams p) {
   using Cfg = MmaCfg<BN>;
@@ -205,48 +269,8 @@ conv_mma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
       tc_commit(smem_u32(&bar_accum));            // accumulators complete
     }
   } else {
-    // ------------------------------------------------------------------ epilogue: TMEM -> registers -> global
-    mbar_wait(smem_u32(&bar_accum), 0);
-    tc_fence_after();
-    const int r = warp * 32 + lane;                               // tile row == TMEM lane
-    const int y = y0 + r / p.bw, x = x0 + r % p.bw;
-    const size_t pix = ((size_t)img * p.H + y) * p.W + x;
-    float* orow = p.out + pix * p.ldo + n0;
-    const float* rrow = p.res ? p.res + pix * p.ldr + n0 : nullptr;
-    const uint32_t lane_base = tmem_base + ((uint32_t)(warp * 32) << 16);
-#pragma unroll 1
-    for (int ch = 0; ch < BN / 32; ++ch) {
-      float v[32], w[32];
-      tc_ld32(lane_base + ch * 32, v);
-      tc_ld32(lane_base + BN + ch * 32, w);
-#pragma unroll
-      for (int i = 0; i < 32; ++i) v[i] = fmaf(w[i], kLoInv, v[i]);
-      if (p.bias) {
-#pragma unroll
-        for (int i = 0; i < 32; i += 4) { float4 b = ld4(p.bias + n0 + ch * 32 + i); v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w; }
-      }
-      if (rrow) {
-#pragma unroll
-        for (int i = 0; i < 32; i += 4) { float4 b = ld4(rrow + ch * 32 + i); v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w; }
-      }
-#pragma unroll
-      for (int i = 0; i < 32; i += 4) st4(orow + ch * 32 + i, make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]));
-      if (p.stats) {
-#pragma unroll
-        for (int i = 0; i < 32; ++i) w[i] = v[i] * v[i];
-        float s = warp_transpose_reduce32(v), q = warp_transpose_reduce32(w);
-        atomicAdd(&s_sum[ch * 32 + lane], s);
-        atomicAdd(&s_sq[ch * 32 + lane], q);
-      }
-    }
-    if (p.stats) {
-      asm volatile("bar.sync 1, 128;" ::: "memory");              // the four epilogue warps only
-      if (threadIdx.x < BN) {
-        double* st = p.stats + ((size_t)img * p.ld_stats + n0 + threadIdx.x) * 2;
-        atomicAdd(st, (double)s_sum[threadIdx.x]);
-        atomicAdd(st + 1, (double)s_sq[threadIdx.x]);
-      }
-    }
+    conv_epilogue<BN>(p, smem_u32(&bar_accum), tmem_base, reinterpret_cast<float*>(smem_raw + (smem_base - smem_u32(smem_raw))), s_sum, s_sq,
+                      img, n0, y0, x0);
   }
   tc_fence_before();
   __syncthreads();
@@ -254,6 +278,132 @@ conv_mma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)Cfg::TMEM_COLS) : "memory");
   }
 }
+
+// ------------------------------------------------------------------------------------------------ A-strip variant (3x3, W >= 128)
+// The plain kernel is L2->SMEM bound: it fetches a fresh 128-pixel A tile for each of the 9 taps.  Here one (bw+2)-pixel strip
+// per (dy, K-chunk) serves the three dx taps: tap dx is the same shared-memory strip read through a UMMA descriptor whose start
+// address is advanced by dx rows (128 B each).  Measured on B200: the 128-byte swizzle is a function of the ABSOLUTE shared-memory
+// address bits, so the descriptor's matrix-base-offset field must stay 0 even though the start is not 1024-byte aligned (setting
+// it to (start >> 7) & 7 gives wrong results; tests/test_gpu_conv_mma.py).  A bytes per tile drop 2.76x; weights keep their own,
+// deeper ring.
+template <int BN>
+struct StripCfg {
+  static constexpr int STRIP_ROWS = MM_M + 2;                         // 130 pixels
+  static constexpr int STRIP_BYTES = STRIP_ROWS * 128;                // per plane, what TMA writes
+  static constexpr int A_SLOT = 2 * 17408;                            // two planes, each padded to a 1024-byte multiple (17 KB)
+  static constexpr int B_PLANE = BN * MM_KC * 2;
+  static constexpr int B_SLOT = 2 * B_PLANE;
+  static constexpr int NA = BN == 128 ? 2 : 3;
+  static constexpr int NB = BN == 128 ? 4 : 6;
+  static constexpr int SMEM_BYTES = NA * A_SLOT + NB * B_SLOT + 1024;
+  static constexpr int TMEM_COLS = 2 * BN;
+  static constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(MM_M >> 4) << 24);
+};
+
+template <int BN>
+__global__ void __launch_bounds__(MM_THREADS, 1)
+conv_mma_strip_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
+                      const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo, const ConvMmaParams p) {
+  using Cfg = StripCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t a_full[Cfg::NA], a_empty[Cfg::NA], b_full[Cfg::NB], b_empty[Cfg::NB], bar_accum;
+  __shared__ uint32_t s_tmem_base;
+  __shared__ float s_sum[BN], s_sq[BN];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t b_base = smem_base + Cfg::NA * Cfg::A_SLOT;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int img = blockIdx.y, n0 = blockIdx.z * BN;
+  const int y0 = blockIdx.x / p.tiles_x, x0 = (blockIdx.x % p.tiles_x) * MM_M;     // bh == 1: one image row per tile
+  const int n_strips = 3 * p.kchunks;
+
+  if (threadIdx.x < BN) { s_sum[threadIdx.x] = 0.f; s_sq[threadIdx.x] = 0.f; }
+  if (warp == 5 && lane == 0) {
+    for (int s = 0; s < Cfg::NA; ++s) { mbar_init(smem_u32(&a_full[s]), 1); mbar_init(smem_u32(&a_empty[s]), 1); }
+    for (int s = 0; s < Cfg::NB; ++s) { mbar_init(smem_u32(&b_full[s]), 1); mbar_init(smem_u32(&b_empty[s]), 1); }
+    mbar_init(smem_u32(&bar_accum), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 4 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_a_hi) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_a_lo) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_b_hi) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_b_lo) : "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem_base)), "r"((uint32_t)Cfg::TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = s_tmem_base;
+
+  if (warp == 4) {
+    if (lane == 0) {     // ---------------- TMA producer: strip (kc, dy) then its three weight tiles
+      const int row0 = img * (p.H + 2) + y0;
+      int ib = 0;
+      for (int is = 0; is < n_strips; ++is) {
+        const int kc = is / 3, dy = is % 3;
+        const int sa = is % Cfg::NA;
+        mbar_wait(smem_u32(&a_empty[sa]), ((uint32_t)(is / Cfg::NA) & 1u) ^ 1u);
+        const uint32_t af = smem_u32(&a_full[sa]);
+        mbar_expect_tx(af, 2 * Cfg::STRIP_BYTES);
+        const uint32_t adst = smem_base + sa * Cfg::A_SLOT;
+        tma_load_3d(adst, &tm_a_hi, af, kc * MM_KC, x0, row0 + dy);
+        tma_load_3d(adst + Cfg::A_SLOT / 2, &tm_a_lo, af, kc * MM_KC, x0, row0 + dy);
+        for (int dx = 0; dx < 3; ++dx, ++ib) {
+          const int sb = ib % Cfg::NB;
+          mbar_wait(smem_u32(&b_empty[sb]), ((uint32_t)(ib / Cfg::NB) & 1u) ^ 1u);
+          const uint32_t bf = smem_u32(&b_full[sb]);
+          mbar_expect_tx(bf, Cfg::B_SLOT);
+          const uint32_t bdst = b_base + sb * Cfg::B_SLOT;
+          const int tap = dy * 3 + dx;
+          tma_load_2d(bdst, &tm_b_hi, bf, kc * MM_KC, tap * p.cout_total + n0);
+          tma_load_2d(bdst + Cfg::B_PLANE, &tm_b_lo, bf, kc * MM_KC, tap * p.cout_total + n0);
+        }
+      }
+    }
+  } else if (warp == 5) {
+    if (lane == 0) {     // ---------------- MMA issuer
+      const uint32_t acc0 = tmem_base, acc1 = tmem_base + BN;
+      int ib = 0;
+      for (int is = 0; is < n_strips; ++is) {
+        const int sa = is % Cfg::NA;
+        mbar_wait(smem_u32(&a_full[sa]), (uint32_t)(is / Cfg::NA) & 1u);
+        const uint32_t abase = smem_base + sa * Cfg::A_SLOT;
+        for (int dx = 0; dx < 3; ++dx, ++ib) {
+          const int sb = ib % Cfg::NB;
+          mbar_wait(smem_u32(&b_full[sb]), (uint32_t)(ib / Cfg::NB) & 1u);
+          tc_fence_after();
+          const uint64_t a_hi = make_kmajor_sw128_desc(abase + dx * 128);
+          const uint64_t a_lo = make_kmajor_sw128_desc(abase + Cfg::A_SLOT / 2 + dx * 128);
+          const uint32_t bbase = b_base + sb * Cfg::B_SLOT;
+          const uint64_t b_hi = make_kmajor_sw128_desc(bbase), b_lo = make_kmajor_sw128_desc(bbase + Cfg::B_PLANE);
+#pragma unroll
+          for (int k = 0; k < MM_KC / 16; ++k) {
+            const uint64_t adv = (uint64_t)(k * 32 >> 4);
+            const uint32_t accum = (ib | k) != 0;
+            tc_mma_f16(acc0, a_hi + adv, b_hi + adv, Cfg::IDESC, accum);
+            tc_mma_f16(acc1, a_hi + adv, b_lo + adv, Cfg::IDESC, accum);
+            tc_mma_f16(acc1, a_lo + adv, b_hi + adv, Cfg::IDESC, 1u);
+          }
+          tc_commit(smem_u32(&b_empty[sb]));
+        }
+        tc_commit(smem_u32(&a_empty[sa]));
+      }
+      tc_commit(smem_u32(&bar_accum));
+    }
+  } else {
+    conv_epilogue<BN>(p, smem_u32(&bar_accum), tmem_base, reinterpret_cast<float*>(smem_raw + (smem_base - smem_u32(smem_raw))), s_sum, s_sq,
+                      img, n0, y0, x0);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)Cfg::TMEM_COLS) : "memory");
+  }
+}
+
 
 // ------------------------------------------------------------------------------------------------ host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -280,6 +430,17 @@ static int make_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r); return -2; }
+  return 0;
+}
+
+template <int BN>
+static int launch_conv_strip(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi, const CUtensorMap& b_lo,
+                             const ConvMmaParams& p, dim3 grid, cudaStream_t stream) {
+  using Cfg = StripCfg<BN>;
+  cudaError_t e = cudaFuncSetAttribute(conv_mma_strip_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+  if (e != cudaSuccess) return cuda_fail(e, "conv_mma_strip smem attr");
+  conv_mma_strip_kernel<BN><<<grid, MM_THREADS, Cfg::SMEM_BYTES, stream>>>(a_hi, a_lo, b_hi, b_lo, p);
+  VT_CHECK_LAUNCH("vt_conv_mma(strip)");
   return 0;
 }
 
@@ -315,11 +476,14 @@ int vt_conv_mma(const void* a_hi, const void* a_lo, int n_img, int H, int W, int
   const int BN = Cout >= 128 ? 128 : Cout;
   const int Hp = H + 2 * pad, Wp = W + 2 * pad;
 
+  // A-strip variant: 3x3 on maps at least 128 wide (one image row per tile).  VT_CONV_STRIP=0 selects the plain kernel (A/B runs).
+  static const int strip_env = [] { const char* e = getenv("VT_CONV_STRIP"); return e ? atoi(e) : 1; }();
+  const bool strip = ks == 3 && bh == 1 && strip_env != 0 && BN >= 64;
   CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
   {
     cuuint64_t dims[3] = {(cuuint64_t)Cin_pad, (cuuint64_t)Wp, (cuuint64_t)n_img * Hp};
     cuuint64_t strides[2] = {(cuuint64_t)Cin_pad * 2, (cuuint64_t)Wp * Cin_pad * 2};
-    cuuint32_t box[3] = {(cuuint32_t)MM_KC, (cuuint32_t)bw, (cuuint32_t)bh};
+    cuuint32_t box[3] = {(cuuint32_t)MM_KC, (cuuint32_t)(strip ? bw + 2 : bw), (cuuint32_t)bh};
     int rc = make_map(&ma_hi, a_hi, 3, dims, strides, box); if (rc) return rc;
     rc = make_map(&ma_lo, a_lo, 3, dims, strides, box); if (rc) return rc;
   }
@@ -336,6 +500,10 @@ int vt_conv_mma(const void* a_hi, const void* a_lo, int n_img, int H, int W, int
   p.bias = bias; p.res = res; p.ldr = ldr; p.out = out; p.ldo = ldo; p.stats = stats; p.ld_stats = ld_stats;
   dim3 grid((H / bh) * (W / bw), n_img, Cout / BN);
   cudaStream_t s = (cudaStream_t)stream;
+  if (strip) {
+    if (BN == 128) return launch_conv_strip<128>(ma_hi, ma_lo, mb_hi, mb_lo, p, grid, s);
+    return launch_conv_strip<64>(ma_hi, ma_lo, mb_hi, mb_lo, p, grid, s);
+  }
   if (BN == 128) return launch_conv_mma<128>(ma_hi, ma_lo, mb_hi, mb_lo, p, grid, s);
   if (BN == 64) return launch_conv_mma<64>(ma_hi, ma_lo, mb_hi, mb_lo, p, grid, s);
   return launch_conv_mma<32>(ma_hi, ma_lo, mb_hi, mb_lo, p, grid, s);
