@@ -20,9 +20,18 @@ CASES = [  # ks, cin, cout, n, H, W
 ]
 
 
+@pytest.fixture(params=["plain", "strip"])
+def variant(request, monkeypatch):
+    """'strip' = the opt-in kernel that reuses one A strip for the three dx taps (VT_CONV_STRIP=1; 3x3, W >= 128 only)."""
+    monkeypatch.setenv("VT_CONV_STRIP", "1" if request.param == "strip" else "0")
+    return request.param
+
+
 @pytest.mark.parametrize("ks,cin,cout,n,H,W", CASES)
-def test_conv_mma_matches_fp64(ks, cin, cout, n, H, W):
+def test_conv_mma_matches_fp64(ks, cin, cout, n, H, W, variant):
     from vistracker_b200 import ops
+    if variant == "strip" and not (ks == 3 and W >= 128):
+        pytest.skip("the strip kernel only serves 3x3 convolutions on maps at least 128 wide")
     g = torch.Generator().manual_seed(ks * 7919 + cin * 31 + cout + H)
     x = torch.randn(n, cin, H, W, generator=g)
     w = torch.randn(cout, cin, ks, ks, generator=g) * 0.05

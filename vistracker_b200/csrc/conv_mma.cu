@@ -476,9 +476,12 @@ int vt_conv_mma(const void* a_hi, const void* a_lo, int n_img, int H, int W, int
   const int BN = Cout >= 128 ? 128 : Cout;
   const int Hp = H + 2 * pad, Wp = W + 2 * pad;
 
-  // A-strip variant: 3x3 on maps at least 128 wide (one image row per tile).  VT_CONV_STRIP=0 selects the plain kernel (A/B runs).
-  static const int strip_env = [] { const char* e = getenv("VT_CONV_STRIP"); return e ? atoi(e) : 1; }();
-  const bool strip = ks == 3 && bh == 1 && strip_env != 0 && BN >= 64;
+  // A-strip variant (3x3 on maps at least 128 wide): opt-in with VT_CONV_STRIP=1.  It cuts TMA bytes 1.5-1.7x but measured no
+  // faster (BN=128) or slower (BN=64, one CTA/SM) than the plain kernel on B200: with ~190 KB of shared memory the pipeline is bound
+  // by L2->SMEM LATENCY x bytes-in-flight, not by bytes (profiles/r01d_conv_strip_vs_plain.txt), so it is kept for round 2's
+  // persistent / 2-CTA redesign and exercised by tests/test_gpu_conv_mma.py only.
+  const char* strip_e = getenv("VT_CONV_STRIP");
+  const bool strip = ks == 3 && bh == 1 && strip_e != nullptr && atoi(strip_e) == 1 && BN >= 64;
   CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
   {
     cuuint64_t dims[3] = {(cuuint64_t)Cin_pad, (cuuint64_t)Wp, (cuuint64_t)n_img * Hp};
