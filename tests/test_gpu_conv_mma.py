@@ -16,22 +16,26 @@ CASES = [  # ks, cin, cout, n, H, W
     (3, 256, 128, 1, 128, 128),
     (1, 256, 256, 1, 128, 128),
     (3, 64, 64, 1, 8, 256),
+    (3, 128, 128, 2, 4, 128),
     (1, 128, 256, 3, 16, 16),
 ]
 
 
-@pytest.fixture(params=["plain", "strip"])
+@pytest.fixture(params=["plain", "strip", "pair"])
 def variant(request, monkeypatch):
-    """'strip' = the opt-in kernel that reuses one A strip for the three dx taps (VT_CONV_STRIP=1; 3x3, W >= 128 only)."""
-    monkeypatch.setenv("VT_CONV_STRIP", "1" if request.param == "strip" else "0")
+    """VT_CONV_STRIP: 0 = plain kernel, 1 = one A strip serves the three dx taps, 2 (default) = strip + two images per CTA sharing the
+    weight tiles.  The strip kernels serve 3x3 convolutions on maps at least 128 wide ('pair' needs an even image count)."""
+    monkeypatch.setenv("VT_CONV_STRIP", {"plain": "0", "strip": "1", "pair": "2"}[request.param])
     return request.param
 
 
 @pytest.mark.parametrize("ks,cin,cout,n,H,W", CASES)
 def test_conv_mma_matches_fp64(ks, cin, cout, n, H, W, variant):
     from vistracker_b200 import ops
-    if variant == "strip" and not (ks == 3 and W >= 128):
-        pytest.skip("the strip kernel only serves 3x3 convolutions on maps at least 128 wide")
+    if variant != "plain" and not (ks == 3 and W >= 128):
+        pytest.skip("the strip kernels only serve 3x3 convolutions on maps at least 128 wide")
+    if variant == "pair":
+        n = 2 * n
     g = torch.Generator().manual_seed(ks * 7919 + cin * 31 + cout + H)
     x = torch.randn(n, cin, H, W, generator=g)
     w = torch.randn(cout, cin, ks, ks, generator=g) * 0.05

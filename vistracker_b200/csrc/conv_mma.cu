@@ -286,37 +286,41 @@ conv_mma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
 // address bits, so the descriptor's matrix-base-offset field must stay 0 even though the start is not 1024-byte aligned (setting
 // it to (start >> 7) & 7 gives wrong results; tests/test_gpu_conv_mma.py).  A bytes per tile drop 2.76x; weights keep their own,
 // deeper ring.
-template <int BN>
+// T = 2 ("pair"): one CTA also owns the SAME tile of the next image, so every weight tile feeds two M tiles (four TMEM accumulators
+// = 4 * BN columns).  Per (dy, K-chunk) that is 2 strips + 3 weight tiles for 72 MMAs: ~36 B/clk (BN=128) instead of 85 B/clk for
+// the plain kernel -- below what the latency-bound TMA ring can deliver (~50 B/clk with ~130 KB in flight).
+template <int BN, int T>
 struct StripCfg {
   static constexpr int STRIP_ROWS = MM_M + 2;                         // 130 pixels
   static constexpr int STRIP_BYTES = STRIP_ROWS * 128;                // per plane, what TMA writes
-  static constexpr int A_SLOT = 2 * 17408;                            // two planes, each padded to a 1024-byte multiple (17 KB)
+  static constexpr int STRIP_SLOT = 2 * 17408;                        // two planes, each padded to a 1024-byte multiple (17 KB)
+  static constexpr int A_SLOT = T * STRIP_SLOT;
   static constexpr int B_PLANE = BN * MM_KC * 2;
   static constexpr int B_SLOT = 2 * B_PLANE;
-  static constexpr int NA = BN == 128 ? 2 : 3;
-  static constexpr int NB = BN == 128 ? 4 : 6;
+  static constexpr int NA = T == 2 ? 2 : (BN == 128 ? 2 : 3);
+  static constexpr int NB = T == 2 ? (BN == 128 ? 2 : 4) : (BN == 128 ? 4 : 6);
   static constexpr int SMEM_BYTES = NA * A_SLOT + NB * B_SLOT + 1024;
-  static constexpr int TMEM_COLS = 2 * BN;
+  static constexpr int TMEM_COLS = 2 * BN * T;
   static constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(MM_M >> 4) << 24);
 };
 
-template <int BN>
+template <int BN, int T>
 __global__ void __launch_bounds__(MM_THREADS, 1)
 conv_mma_strip_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                       const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo, const ConvMmaParams p) {
-  using Cfg = StripCfg<BN>;
+  using Cfg = StripCfg<BN, T>;
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t a_full[Cfg::NA], a_empty[Cfg::NA], b_full[Cfg::NB], b_empty[Cfg::NB], bar_accum;
   __shared__ uint32_t s_tmem_base;
-  __shared__ float s_sum[BN], s_sq[BN];
+  __shared__ float s_sum[T][BN], s_sq[T][BN];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t b_base = smem_base + Cfg::NA * Cfg::A_SLOT;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int img = blockIdx.y, n0 = blockIdx.z * BN;
+  const int img0 = blockIdx.y * T, n0 = blockIdx.z * BN;
   const int y0 = blockIdx.x / p.tiles_x, x0 = (blockIdx.x % p.tiles_x) * MM_M;     // bh == 1: one image row per tile
   const int n_strips = 3 * p.kchunks;
 
-  if (threadIdx.x < BN) { s_sum[threadIdx.x] = 0.f; s_sq[threadIdx.x] = 0.f; }
+  for (int i = threadIdx.x; i < T * BN; i += MM_THREADS) { (&s_sum[0][0])[i] = 0.f; (&s_sq[0][0])[i] = 0.f; }
   if (warp == 5 && lane == 0) {
     for (int s = 0; s < Cfg::NA; ++s) { mbar_init(smem_u32(&a_full[s]), 1); mbar_init(smem_u32(&a_empty[s]), 1); }
     for (int s = 0; s < Cfg::NB; ++s) { mbar_init(smem_u32(&b_full[s]), 1); mbar_init(smem_u32(&b_empty[s]), 1); }
@@ -339,18 +343,21 @@ conv_mma_strip_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_
   const uint32_t tmem_base = s_tmem_base;
 
   if (warp == 4) {
-    if (lane == 0) {     // ---------------- TMA producer: strip (kc, dy) then its three weight tiles
-      const int row0 = img * (p.H + 2) + y0;
+    if (lane == 0) {     // ---------------- TMA producer: the T strips of (kc, dy), then the three weight tiles they share
       int ib = 0;
       for (int is = 0; is < n_strips; ++is) {
         const int kc = is / 3, dy = is % 3;
         const int sa = is % Cfg::NA;
         mbar_wait(smem_u32(&a_empty[sa]), ((uint32_t)(is / Cfg::NA) & 1u) ^ 1u);
         const uint32_t af = smem_u32(&a_full[sa]);
-        mbar_expect_tx(af, 2 * Cfg::STRIP_BYTES);
-        const uint32_t adst = smem_base + sa * Cfg::A_SLOT;
-        tma_load_3d(adst, &tm_a_hi, af, kc * MM_KC, x0, row0 + dy);
-        tma_load_3d(adst + Cfg::A_SLOT / 2, &tm_a_lo, af, kc * MM_KC, x0, row0 + dy);
+        mbar_expect_tx(af, T * 2 * Cfg::STRIP_BYTES);
+#pragma unroll
+        for (int t = 0; t < T; ++t) {
+          const uint32_t adst = smem_base + sa * Cfg::A_SLOT + t * Cfg::STRIP_SLOT;
+          const int row = (img0 + t) * (p.H + 2) + y0 + dy;
+          tma_load_3d(adst, &tm_a_hi, af, kc * MM_KC, x0, row);
+          tma_load_3d(adst + Cfg::STRIP_SLOT / 2, &tm_a_lo, af, kc * MM_KC, x0, row);
+        }
         for (int dx = 0; dx < 3; ++dx, ++ib) {
           const int sb = ib % Cfg::NB;
           mbar_wait(smem_u32(&b_empty[sb]), ((uint32_t)(ib / Cfg::NB) & 1u) ^ 1u);
@@ -365,27 +372,30 @@ conv_mma_strip_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_
     }
   } else if (warp == 5) {
     if (lane == 0) {     // ---------------- MMA issuer
-      const uint32_t acc0 = tmem_base, acc1 = tmem_base + BN;
       int ib = 0;
       for (int is = 0; is < n_strips; ++is) {
         const int sa = is % Cfg::NA;
         mbar_wait(smem_u32(&a_full[sa]), (uint32_t)(is / Cfg::NA) & 1u);
-        const uint32_t abase = smem_base + sa * Cfg::A_SLOT;
         for (int dx = 0; dx < 3; ++dx, ++ib) {
           const int sb = ib % Cfg::NB;
           mbar_wait(smem_u32(&b_full[sb]), (uint32_t)(ib / Cfg::NB) & 1u);
           tc_fence_after();
-          const uint64_t a_hi = make_kmajor_sw128_desc(abase + dx * 128);
-          const uint64_t a_lo = make_kmajor_sw128_desc(abase + Cfg::A_SLOT / 2 + dx * 128);
           const uint32_t bbase = b_base + sb * Cfg::B_SLOT;
           const uint64_t b_hi = make_kmajor_sw128_desc(bbase), b_lo = make_kmajor_sw128_desc(bbase + Cfg::B_PLANE);
 #pragma unroll
-          for (int k = 0; k < MM_KC / 16; ++k) {
-            const uint64_t adv = (uint64_t)(k * 32 >> 4);
-            const uint32_t accum = (ib | k) != 0;
-            tc_mma_f16(acc0, a_hi + adv, b_hi + adv, Cfg::IDESC, accum);
-            tc_mma_f16(acc1, a_hi + adv, b_lo + adv, Cfg::IDESC, accum);
-            tc_mma_f16(acc1, a_lo + adv, b_hi + adv, Cfg::IDESC, 1u);
+          for (int t = 0; t < T; ++t) {
+            const uint32_t abase = smem_base + sa * Cfg::A_SLOT + t * Cfg::STRIP_SLOT;
+            const uint64_t a_hi = make_kmajor_sw128_desc(abase + dx * 128);
+            const uint64_t a_lo = make_kmajor_sw128_desc(abase + Cfg::STRIP_SLOT / 2 + dx * 128);
+            const uint32_t acc0 = tmem_base + t * 2 * BN, acc1 = acc0 + BN;
+#pragma unroll
+            for (int k = 0; k < MM_KC / 16; ++k) {
+              const uint64_t adv = (uint64_t)(k * 32 >> 4);
+              const uint32_t accum = (ib | k) != 0;
+              tc_mma_f16(acc0, a_hi + adv, b_hi + adv, Cfg::IDESC, accum);
+              tc_mma_f16(acc1, a_hi + adv, b_lo + adv, Cfg::IDESC, accum);
+              tc_mma_f16(acc1, a_lo + adv, b_hi + adv, Cfg::IDESC, 1u);
+            }
           }
           tc_commit(smem_u32(&b_empty[sb]));
         }
@@ -394,8 +404,11 @@ conv_mma_strip_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_
       tc_commit(smem_u32(&bar_accum));
     }
   } else {
-    conv_epilogue<BN>(p, smem_u32(&bar_accum), tmem_base, reinterpret_cast<float*>(smem_raw + (smem_base - smem_u32(smem_raw))), s_sum, s_sq,
-                      img, n0, y0, x0);
+    // each warp stages and drains only its own 32 rows, so the two tiles can reuse the staging buffer back to back
+#pragma unroll
+    for (int t = 0; t < T; ++t)
+      conv_epilogue<BN>(p, smem_u32(&bar_accum), tmem_base + t * 2 * BN, reinterpret_cast<float*>(smem_raw + (smem_base - smem_u32(smem_raw))),
+                        s_sum[t], s_sq[t], img0 + t, n0, y0, x0);
   }
   tc_fence_before();
   __syncthreads();
@@ -403,7 +416,6 @@ conv_mma_strip_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)Cfg::TMEM_COLS) : "memory");
   }
 }
-
 
 // ------------------------------------------------------------------------------------------------ host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -433,13 +445,15 @@ static int make_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t
   return 0;
 }
 
-template <int BN>
+template <int BN, int T>
 static int launch_conv_strip(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi, const CUtensorMap& b_lo,
                              const ConvMmaParams& p, dim3 grid, cudaStream_t stream) {
-  using Cfg = StripCfg<BN>;
-  cudaError_t e = cudaFuncSetAttribute(conv_mma_strip_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+  using Cfg = StripCfg<BN, T>;
+  static_assert(Cfg::SMEM_BYTES <= 227 * 1024 && Cfg::TMEM_COLS <= 512, "strip configuration exceeds the SM");
+  cudaError_t e = cudaFuncSetAttribute(conv_mma_strip_kernel<BN, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
   if (e != cudaSuccess) return cuda_fail(e, "conv_mma_strip smem attr");
-  conv_mma_strip_kernel<BN><<<grid, MM_THREADS, Cfg::SMEM_BYTES, stream>>>(a_hi, a_lo, b_hi, b_lo, p);
+  grid.y /= T;
+  conv_mma_strip_kernel<BN, T><<<grid, MM_THREADS, Cfg::SMEM_BYTES, stream>>>(a_hi, a_lo, b_hi, b_lo, p);
   VT_CHECK_LAUNCH("vt_conv_mma(strip)");
   return 0;
 }
@@ -481,7 +495,9 @@ int vt_conv_mma(const void* a_hi, const void* a_lo, int n_img, int H, int W, int
   // by L2->SMEM LATENCY x bytes-in-flight, not by bytes (profiles/r01d_conv_strip_vs_plain.txt), so it is kept for round 2's
   // persistent / 2-CTA redesign and exercised by tests/test_gpu_conv_mma.py only.
   const char* strip_e = getenv("VT_CONV_STRIP");
-  const bool strip = ks == 3 && bh == 1 && strip_e != nullptr && atoi(strip_e) == 1 && BN >= 64;
+  const int strip_mode = strip_e ? atoi(strip_e) : 2;       // 0 plain, 1 strip (one tile / CTA), 2 strip + image pairs (default)
+  const bool strip = ks == 3 && bh == 1 && strip_mode != 0 && BN >= 64 && !(strip_mode == 2 && (n_img % 2)) ;
+  const bool pair = strip && strip_mode == 2;
   CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
   {
     cuuint64_t dims[3] = {(cuuint64_t)Cin_pad, (cuuint64_t)Wp, (cuuint64_t)n_img * Hp};
@@ -503,9 +519,13 @@ int vt_conv_mma(const void* a_hi, const void* a_lo, int n_img, int H, int W, int
   p.bias = bias; p.res = res; p.ldr = ldr; p.out = out; p.ldo = ldo; p.stats = stats; p.ld_stats = ld_stats;
   dim3 grid((H / bh) * (W / bw), n_img, Cout / BN);
   cudaStream_t s = (cudaStream_t)stream;
+  if (pair) {
+    if (BN == 128) return launch_conv_strip<128, 2>(ma_hi, ma_lo, mb_hi, mb_lo, p, grid, s);
+    return launch_conv_strip<64, 2>(ma_hi, ma_lo, mb_hi, mb_lo, p, grid, s);
+  }
   if (strip) {
-    if (BN == 128) return launch_conv_strip<128>(ma_hi, ma_lo, mb_hi, mb_lo, p, grid, s);
-    return launch_conv_strip<64>(ma_hi, ma_lo, mb_hi, mb_lo, p, grid, s);
+    if (BN == 128) return launch_conv_strip<128, 1>(ma_hi, ma_lo, mb_hi, mb_lo, p, grid, s);
+    return launch_conv_strip<64, 1>(ma_hi, ma_lo, mb_hi, mb_lo, p, grid, s);
   }
   if (BN == 128) return launch_conv_mma<128>(ma_hi, ma_lo, mb_hi, mb_lo, p, grid, s);
   if (BN == 64) return launch_conv_mma<64>(ma_hi, ma_lo, mb_hi, mb_lo, p, grid, s);
