@@ -490,13 +490,15 @@ int vt_conv_mma(const void* a_hi, const void* a_lo, int n_img, int H, int W, int
   const int BN = Cout >= 128 ? 128 : Cout;
   const int Hp = H + 2 * pad, Wp = W + 2 * pad;
 
-  // A-strip variant (3x3 on maps at least 128 wide): opt-in with VT_CONV_STRIP=1.  It cuts TMA bytes 1.5-1.7x but measured no
-  // faster (BN=128) or slower (BN=64, one CTA/SM) than the plain kernel on B200: with ~190 KB of shared memory the pipeline is bound
-  // by L2->SMEM LATENCY x bytes-in-flight, not by bytes (profiles/r01d_conv_strip_vs_plain.txt), so it is kept for round 2's
-  // persistent / 2-CTA redesign and exercised by tests/test_gpu_conv_mma.py only.
+  // A-strip variants (3x3 on maps at least 128 wide) are opt-in: VT_CONV_STRIP=1 (one strip serves the three dx taps) or =2 (strip +
+  // two images per CTA sharing the weight tiles).  They cut TMA bytes per MMA 1.5x / 2.4x and are bit-identical, but measured no
+  // faster than the plain kernel on B200 (profiles/r01d_conv_strip_vs_plain.txt): at M=128 x N=128 the three MMAs of a K-step already
+  // read 24 KB of operands from shared memory per 192 tensor cycles (= the 128 B/clk shared-memory port) and the kernel runs at
+  // ~1.2 PFLOP/s executed = 0.72 of the measured cuBLAS bf16 burst peak / 0.85 of the sustained one; fewer global->shared bytes do
+  // not relieve that.  Kept (and tested) as the basis for round 2's A-from-TMEM / 2-CTA work.
   const char* strip_e = getenv("VT_CONV_STRIP");
-  const int strip_mode = strip_e ? atoi(strip_e) : 2;       // 0 plain, 1 strip (one tile / CTA), 2 strip + image pairs (default)
-  const bool strip = ks == 3 && bh == 1 && strip_mode != 0 && BN >= 64 && !(strip_mode == 2 && (n_img % 2)) ;
+  const int strip_mode = strip_e ? atoi(strip_e) : 0;
+  const bool strip = ks == 3 && bh == 1 && strip_mode != 0 && BN >= 64 && !(strip_mode == 2 && (n_img % 2));
   const bool pair = strip && strip_mode == 2;
   CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
   {
