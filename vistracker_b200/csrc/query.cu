@@ -156,24 +156,38 @@ __device__ __forceinline__ void gather_tile(const float* __restrict__ points, co
 }
 
 // acc[i] = bias[col0+16w+i] + sum_k inT[k][lane] * W[k][col0 + 16w + i]: warp w owns 16 output columns, lane = point.
-// W rows are staged through shared memory QKC at a time (broadcast reads), inT is read conflict-free.
+// W rows are staged through shared memory QKC at a time (broadcast reads), double-buffered with cp.async so the L2 latency of
+// chunk c+1 hides behind the FMAs of chunk c (one CTA per SM: there is no other CTA to hide it); inT is read conflict-free.
+__device__ __forceinline__ void stage_weights(float* dst, const float* __restrict__ Wg, int ldw, int col0, int k0, int kc) {
+  for (int i = threadIdx.x; i < kc * (QH / 4); i += 256) {
+    const int r = i / (QH / 4), c4 = i % (QH / 4);
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst + (size_t)i * 4);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(Wg + (size_t)(k0 + r) * ldw + col0 + c4 * 4) : "memory");
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+}
+
 __device__ __forceinline__ void dense16(const float* inT, int K, const float* __restrict__ Wg, int ldw, int col0,
-                                        const float* __restrict__ bias, float* sW, float (&acc)[16]) {
+                                        const float* __restrict__ bias, float* sW /*[2][QKC][QH]*/, float (&acc)[16]) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 #pragma unroll
   for (int i = 0; i < 16; ++i) acc[i] = bias ? bias[col0 + warp * 16 + i] : 0.f;
-  for (int k0 = 0; k0 < K; k0 += QKC) {
-    const int kc = min(QKC, K - k0);
-    __syncthreads();                                    // previous chunk fully consumed (also orders earlier tile writes)
-    for (int i = tid; i < kc * (QH / 4); i += 256) {
-      const int r = i / (QH / 4), c4 = i % (QH / 4);
-      reinterpret_cast<float4*>(sW)[i] = *reinterpret_cast<const float4*>(Wg + (size_t)(k0 + r) * ldw + col0 + c4 * 4);
+  const int nchunks = (K + QKC - 1) / QKC;
+  stage_weights(sW, Wg, ldw, col0, 0, min(QKC, K));
+  for (int c = 0; c < nchunks; ++c) {
+    const int k0 = c * QKC, kc = min(QKC, K - k0);
+    if (c + 1 < nchunks) {
+      stage_weights(sW + ((c + 1) & 1) * QKC * QH, Wg, ldw, col0, k0 + QKC, min(QKC, K - k0 - QKC));
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
     }
-    __syncthreads();
+    __syncthreads();                                    // chunk c landed for every thread (also orders earlier tile writes)
+    const float* w = sW + (c & 1) * QKC * QH;
 #pragma unroll 4
     for (int kk = 0; kk < kc; ++kk) {
       const float a = inT[(size_t)(k0 + kk) * QLD + lane];
-      const float4* wr = reinterpret_cast<const float4*>(sW + kk * QH + warp * 16);
+      const float4* wr = reinterpret_cast<const float4*>(w + kk * QH + warp * 16);
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const float4 ww = wr[j];
@@ -181,6 +195,7 @@ __device__ __forceinline__ void dense16(const float* inT, int K, const float* __
         acc[j * 4 + 2] = fmaf(a, ww.z, acc[j * 4 + 2]); acc[j * 4 + 3] = fmaf(a, ww.w, acc[j * 4 + 3]);
       }
     }
+    __syncthreads();                                    // buffer (c & 1) may be refilled by the next iteration's prefetch
   }
 }
 
@@ -220,7 +235,7 @@ __global__ void __launch_bounds__(256, 1) query_fwd_kernel(const float* __restri
   float* featT = smem;                       // [616][33]
   float* hA = featT + QK * QLD;              // [128][33]
   float* hB = hA + QH * QLD;                 // [128][33]
-  float* sW = hB + QH * QLD;                 // [32][128]
+  float* sW = hB + QH * QLD;                 // [2][32][128]
   __shared__ int s_in_img[QP];
   const int b = blockIdx.y, n0 = blockIdx.x * QP;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -274,8 +289,8 @@ __global__ void __launch_bounds__(256, 1) query_bwd_kernel(const float* __restri
   float* gfeatT = featT + QK * QLD;          // [616][33]   gradient w.r.t. the features, summed over the heads
   float* hA = gfeatT + QK * QLD;             // [128][33]
   float* hB = hA + QH * QLD;                 // [128][33]
-  float* sW = hB + QH * QLD;                 // [32][128]
-  float* g4s = sW + QKC * QH;                // [16][33]
+  float* sW = hB + QH * QLD;                 // [2][32][128]
+  float* g4s = sW + 2 * QKC * QH;            // [16][33]
   __shared__ int s_in_img[QP];
   __shared__ float s_df[QP];
   const int b = blockIdx.y, n0 = blockIdx.x * QP;
@@ -432,7 +447,7 @@ int vt_query_fwd(const float* points, const float* crop_center, const float* bod
   if (B <= 0 || N <= 0) return 0;
   QueryMaps m{im_feat, tmpx, tri_tmpx, tri_feat, Hf, Wf, Ht, Wt, c_im, c_tmpx, c_tt, c_tf};
   QueryCam cam{cam7[0], cam7[1], cam7[2], cam7[3], cam7[4], cam7[5], cam7[6]};
-  size_t smem = (size_t)(QK * QLD + 2 * QH * QLD + QKC * QH) * sizeof(float);
+  size_t smem = (size_t)(QK * QLD + 2 * QH * QLD + 2 * QKC * QH) * sizeof(float);
   cudaError_t e = cudaFuncSetAttribute(query_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return cuda_fail(e, "vt_query_fwd smem attr");
   dim3 grid(ceil_div(N, QP), B);
@@ -449,7 +464,7 @@ int vt_query_bwd(const float* points, const float* crop_center, const float* bod
   if (B <= 0 || N <= 0) return 0;
   QueryMaps m{im_feat, tmpx, tri_tmpx, tri_feat, Hf, Wf, Ht, Wt, c_im, c_tmpx, c_tt, c_tf};
   QueryCam cam{cam7[0], cam7[1], cam7[2], cam7[3], cam7[4], cam7[5], cam7[6]};
-  size_t smem = (size_t)(2 * QK * QLD + 2 * QH * QLD + QKC * QH + 16 * QLD) * sizeof(float);
+  size_t smem = (size_t)(2 * QK * QLD + 2 * QH * QLD + 2 * QKC * QH + 16 * QLD) * sizeof(float);
   cudaError_t e = cudaFuncSetAttribute(query_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return cuda_fail(e, "vt_query_bwd smem attr");
   dim3 grid(ceil_div(N, QP), B);
@@ -469,7 +484,7 @@ int vt_query_project_step(const float* points, const float* crop_center, const f
   if (B <= 0 || N <= 0) return 0;
   QueryMaps m{im_feat, tmpx, tri_tmpx, tri_feat, Hf, Wf, Ht, Wt, c_im, c_tmpx, c_tt, c_tf};
   QueryCam cam{cam7[0], cam7[1], cam7[2], cam7[3], cam7[4], cam7[5], cam7[6]};
-  size_t smem = (size_t)(2 * QK * QLD + 2 * QH * QLD + QKC * QH + 16 * QLD) * sizeof(float);
+  size_t smem = (size_t)(2 * QK * QLD + 2 * QH * QLD + 2 * QKC * QH + 16 * QLD) * sizeof(float);
   cudaError_t e = cudaFuncSetAttribute(query_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return cuda_fail(e, "vt_query_project_step smem attr");
   dim3 grid(ceil_div(N, QP), B);
