@@ -56,6 +56,13 @@ int vt_conv_mma(const void* a_hi, const void* a_lo, int n_img, int H, int W, int
                 const void* w_lo, int Cout, const float* bias, const float* res, int ldr, float* out, int ldo, double* stats,
                 int ld_stats, void* stream);
 
+/* vt_conv_mma plus a second output written by the same epilogue: out2 = out + res2 with its own statistics.  Used by ConvBlocks with
+ * an identity residual: `out` keeps the raw conv slice for the next GroupNorm, `out2` is the block output slice
+ * (torch.cat((out1, out2, out3), 1) + residual, net_util.py:389-394) -- no separate add pass over HBM. */
+int vt_conv_mma_dual(const void* a_hi, const void* a_lo, int n_img, int H, int W, int Cin_pad, int pad, int ks, const void* w_hi,
+                     const void* w_lo, int Cout, const float* bias, const float* res, int ldr, float* out, int ldo, double* stats,
+                     int ld_stats, float* out2, int ldo2, const float* res2, int ldr2, double* stats2, int ld_stats2, void* stream);
+
 /* Same contract on the fp32 CUDA cores with the GroupNorm affine + ReLU fused into the load: any H, W; w: fp32
  * [ks*ks][Cin][Cout].  Used where the 128-pixel tensor-core tile does not fit, and as the on-device cross-check. */
 int vt_conv_ffma(const float* x, int ldx, const float* scale, const float* shift, int relu, int n_img, int H, int W, int Cin,

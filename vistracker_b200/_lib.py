@@ -22,6 +22,7 @@ SIGNATURES = {
     "vt_affine_act": (_i, [_p, _i, _p, _p, _i, _i, _i, _i, _p, _i, _p, _i, _p]),
     "vt_prep_split": (_i, [_p, _i, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p]),
     "vt_conv_mma": (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _p, _p, _i, _p, _p, _i, _p, _i, _p, _i, _p]),
+    "vt_conv_mma_dual": (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _p, _p, _i, _p, _p, _i, _p, _i, _p, _i, _p, _i, _p, _i, _p, _i, _p]),
     "vt_conv_ffma": (_i, [_p, _i, _p, _p, _i, _i, _i, _i, _i, _i, _p, _i, _p, _p, _i, _p, _i, _p, _i, _p]),
     "vt_add": (_i, [_p, _i, _p, _i, _i, _i, _i, _p, _i, _p, _i, _p]),
     "vt_avgpool2": (_i, [_p, _i, _i, _i, _i, _p, _p, _i, _p]),

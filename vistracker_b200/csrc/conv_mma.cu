@@ -36,6 +36,9 @@ struct ConvMmaParams {
   const float* bias; const float* res; int ldr;
   float* out; int ldo;
   double* stats; int ld_stats;
+  // optional second output: out2 = conv + bias (+ res) + res2, with its own statistics (ConvBlock identity residual fused into
+  // the conv that produces the slice: the raw slice feeds the next GroupNorm, the summed slice is the block output)
+  float* out2; int ldo2; const float* res2; int ldr2; double* stats2; int ld_stats2;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -116,7 +119,7 @@ __device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t saddr) {
 // buffers are free: the fp32 tile is staged there so that global stores / residual loads are whole, coalesced pixel rows.
 template <int BN>
 __device__ __forceinline__ void conv_epilogue(const ConvMmaParams& p, uint32_t bar_accum_addr, uint32_t tmem_base, float* stile,
-                                              float* s_sum, float* s_sq, int img, int n0, int y0, int x0) {
+                                              float* s_sum, float* s_sq, float* s_sum2, float* s_sq2, int img, int n0, int y0, int x0) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   mbar_wait(bar_accum_addr, 0);
   tc_fence_after();
@@ -141,7 +144,7 @@ __device__ __forceinline__ void conv_epilogue(const ConvMmaParams& p, uint32_t b
   const int cl = lane % LPR, rsub = lane / LPR;
   float4 bz = make_float4(0, 0, 0, 0);
   if (p.bias) bz = ld4(p.bias + n0 + cl * 4);
-  float4 s4 = make_float4(0, 0, 0, 0), q4 = s4;
+  float4 s4 = make_float4(0, 0, 0, 0), q4 = s4, t4 = s4, u4 = s4;
 #pragma unroll 4
   for (int rr = warp * 32 + rsub; rr < warp * 32 + 32; rr += RPI) {
     const int y = y0 + rr / p.bw, x = x0 + rr % p.bw;
@@ -152,6 +155,32 @@ __device__ __forceinline__ void conv_epilogue(const ConvMmaParams& p, uint32_t b
     st4(p.out + pix * p.ldo + n0 + cl * 4, v);
     s4.x += v.x; s4.y += v.y; s4.z += v.z; s4.w += v.w;
     q4.x += v.x * v.x; q4.y += v.y * v.y; q4.z += v.z * v.z; q4.w += v.w * v.w;
+    if (p.out2) {
+      const float4 r2 = ld4(p.res2 + pix * p.ldr2 + n0 + cl * 4);
+      v.x += r2.x; v.y += r2.y; v.z += r2.z; v.w += r2.w;
+      st4(p.out2 + pix * p.ldo2 + n0 + cl * 4, v);
+      t4.x += v.x; t4.y += v.y; t4.z += v.z; t4.w += v.w;
+      u4.x += v.x * v.x; u4.y += v.y * v.y; u4.z += v.z * v.z; u4.w += v.w * v.w;
+    }
+  }
+  if (p.out2 && p.stats2) {
+#pragma unroll
+    for (int o = LPR; o < 32; o <<= 1) {
+      t4.x += __shfl_xor_sync(0xffffffffu, t4.x, o); t4.y += __shfl_xor_sync(0xffffffffu, t4.y, o);
+      t4.z += __shfl_xor_sync(0xffffffffu, t4.z, o); t4.w += __shfl_xor_sync(0xffffffffu, t4.w, o);
+      u4.x += __shfl_xor_sync(0xffffffffu, u4.x, o); u4.y += __shfl_xor_sync(0xffffffffu, u4.y, o);
+      u4.z += __shfl_xor_sync(0xffffffffu, u4.z, o); u4.w += __shfl_xor_sync(0xffffffffu, u4.w, o);
+    }
+    if (rsub == 0) {
+      atomicAdd(&s_sum2[cl * 4 + 0], t4.x); atomicAdd(&s_sum2[cl * 4 + 1], t4.y); atomicAdd(&s_sum2[cl * 4 + 2], t4.z); atomicAdd(&s_sum2[cl * 4 + 3], t4.w);
+      atomicAdd(&s_sq2[cl * 4 + 0], u4.x); atomicAdd(&s_sq2[cl * 4 + 1], u4.y); atomicAdd(&s_sq2[cl * 4 + 2], u4.z); atomicAdd(&s_sq2[cl * 4 + 3], u4.w);
+    }
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    if (threadIdx.x < BN) {
+      double* st = p.stats2 + ((size_t)img * p.ld_stats2 + n0 + threadIdx.x) * 2;
+      atomicAdd(st, (double)s_sum2[threadIdx.x]);
+      atomicAdd(st + 1, (double)s_sq2[threadIdx.x]);
+    }
   }
   if (p.stats) {
 #pragma unroll
@@ -195,7 +224,7 @@ conv_mma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bar_full[Cfg::STAGES], bar_empty[Cfg::STAGES], bar_accum;
   __shared__ uint32_t s_tmem_base;
-  __shared__ float s_sum[BN], s_sq[BN];
+  __shared__ float s_sum[BN], s_sq[BN], s_sum2[BN], s_sq2[BN];
 
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -204,7 +233,7 @@ conv_mma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
   const int y0 = tile_y * p.bh, x0 = tile_x * p.bw;
   const int n_iter = p.ks * p.ks * p.kchunks;
 
-  if (threadIdx.x < BN) { s_sum[threadIdx.x] = 0.f; s_sq[threadIdx.x] = 0.f; }
+  if (threadIdx.x < BN) { s_sum[threadIdx.x] = 0.f; s_sq[threadIdx.x] = 0.f; s_sum2[threadIdx.x] = 0.f; s_sq2[threadIdx.x] = 0.f; }
   if (warp == 5 && lane == 0) {
     for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(smem_u32(&bar_full[s]), 1); mbar_init(smem_u32(&bar_empty[s]), 1); }
     mbar_init(smem_u32(&bar_accum), 1);
@@ -270,7 +299,7 @@ conv_mma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
     }
   } else {
     conv_epilogue<BN>(p, smem_u32(&bar_accum), tmem_base, reinterpret_cast<float*>(smem_raw + (smem_base - smem_u32(smem_raw))), s_sum, s_sq,
-                      img, n0, y0, x0);
+                      s_sum2, s_sq2, img, n0, y0, x0);
   }
   tc_fence_before();
   __syncthreads();
@@ -312,7 +341,7 @@ conv_mma_strip_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t a_full[Cfg::NA], a_empty[Cfg::NA], b_full[Cfg::NB], b_empty[Cfg::NB], bar_accum;
   __shared__ uint32_t s_tmem_base;
-  __shared__ float s_sum[T][BN], s_sq[T][BN];
+  __shared__ float s_sum[T][BN], s_sq[T][BN], s_sum2[T][BN], s_sq2[T][BN];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t b_base = smem_base + Cfg::NA * Cfg::A_SLOT;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -320,7 +349,7 @@ conv_mma_strip_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_
   const int y0 = blockIdx.x / p.tiles_x, x0 = (blockIdx.x % p.tiles_x) * MM_M;     // bh == 1: one image row per tile
   const int n_strips = 3 * p.kchunks;
 
-  for (int i = threadIdx.x; i < T * BN; i += MM_THREADS) { (&s_sum[0][0])[i] = 0.f; (&s_sq[0][0])[i] = 0.f; }
+  for (int i = threadIdx.x; i < T * BN; i += MM_THREADS) { (&s_sum[0][0])[i] = 0.f; (&s_sq[0][0])[i] = 0.f; (&s_sum2[0][0])[i] = 0.f; (&s_sq2[0][0])[i] = 0.f; }
   if (warp == 5 && lane == 0) {
     for (int s = 0; s < Cfg::NA; ++s) { mbar_init(smem_u32(&a_full[s]), 1); mbar_init(smem_u32(&a_empty[s]), 1); }
     for (int s = 0; s < Cfg::NB; ++s) { mbar_init(smem_u32(&b_full[s]), 1); mbar_init(smem_u32(&b_empty[s]), 1); }
@@ -408,7 +437,7 @@ conv_mma_strip_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_
 #pragma unroll
     for (int t = 0; t < T; ++t)
       conv_epilogue<BN>(p, smem_u32(&bar_accum), tmem_base + t * 2 * BN, reinterpret_cast<float*>(smem_raw + (smem_base - smem_u32(smem_raw))),
-                        s_sum[t], s_sq[t], img0 + t, n0, y0, x0);
+                        s_sum[t], s_sq[t], s_sum2[t], s_sq2[t], img0 + t, n0, y0, x0);
   }
   tc_fence_before();
   __syncthreads();
@@ -478,6 +507,14 @@ extern "C" {
 int vt_conv_mma(const void* a_hi, const void* a_lo, int n_img, int H, int W, int Cin_pad, int pad, int ks, const void* w_hi,
                 const void* w_lo, int Cout, const float* bias, const float* res, int ldr, float* out, int ldo, double* stats,
                 int ld_stats, void* stream) {
+  return vt_conv_mma_dual(a_hi, a_lo, n_img, H, W, Cin_pad, pad, ks, w_hi, w_lo, Cout, bias, res, ldr, out, ldo, stats, ld_stats,
+                          nullptr, 0, nullptr, 0, nullptr, 0, stream);
+}
+
+int vt_conv_mma_dual(const void* a_hi, const void* a_lo, int n_img, int H, int W, int Cin_pad, int pad, int ks, const void* w_hi,
+                     const void* w_lo, int Cout, const float* bias, const float* res, int ldr, float* out, int ldo, double* stats,
+                     int ld_stats, float* out2, int ldo2, const float* res2, int ldr2, double* stats2, int ld_stats2, void* stream) {
+  VT_CHECK_ARG(out2 == nullptr || (res2 != nullptr && ldo2 % 4 == 0 && ldr2 % 4 == 0), "vt_conv_mma_dual: out2 needs res2 and 4-aligned strides");
   VT_CHECK_ARG(ks == 1 || ks == 3, "vt_conv_mma: kernel size %d", ks);
   VT_CHECK_ARG(pad == ks / 2, "vt_conv_mma: operand planes must carry a border of %d (got %d)", ks / 2, pad);
   VT_CHECK_ARG(Cin_pad % MM_KC == 0, "vt_conv_mma: Cin_pad=%d is not a multiple of %d", Cin_pad, MM_KC);
@@ -519,6 +556,7 @@ int vt_conv_mma(const void* a_hi, const void* a_lo, int n_img, int H, int W, int
   p.H = H; p.W = W; p.pad = pad; p.ks = ks; p.kchunks = Cin_pad / MM_KC;
   p.bw = bw; p.bh = bh; p.tiles_x = W / bw; p.cout_total = Cout;
   p.bias = bias; p.res = res; p.ldr = ldr; p.out = out; p.ldo = ldo; p.stats = stats; p.ld_stats = ld_stats;
+  p.out2 = out2; p.ldo2 = ldo2; p.res2 = res2; p.ldr2 = ldr2; p.stats2 = stats2; p.ld_stats2 = ld_stats2;
   dim3 grid((H / bh) * (W / bw), n_img, Cout / BN);
   cudaStream_t s = (cudaStream_t)stream;
   if (pair) {

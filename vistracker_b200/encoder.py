@@ -121,7 +121,9 @@ class HGEncoder:
         self.launches += 1
         return Operand(act, ss[0], ss[1], True)
 
-    def _conv(self, op: Operand, name: str, out: Act, bias: Optional[str] = None, res: Optional[Act] = None, stats=None):
+    def _conv(self, op: Operand, name: str, out: Act, bias: Optional[str] = None, res: Optional[Act] = None, stats=None,
+              out2: Optional[Act] = None, res2: Optional[Act] = None):
+        """out = conv(op) + bias (+ res); optionally also out2 = out + res2 (tensor-core path only), each with its statistics."""
         pk = self.conv[name]
         a = op.act
         n, H, W = a.n, a.H, a.W
@@ -140,10 +142,17 @@ class HGEncoder:
                 self.launches += 1
                 op.planes[pad] = planes
             planes = op.planes[pad]
-            _lib.call("vt_conv_mma", _lib.ptr(planes[0]), _lib.ptr(planes[1]), n, H, W, pk["cin_pad"], pad, ks,
-                      _lib.ptr(pk["hi"]), _lib.ptr(pk["lo"]), pk["cout"], b, rp, rld, _lib.ptr(out.t), out.ld, sp, sld,
-                      _lib.stream_ptr())
+            if out2 is None:
+                _lib.call("vt_conv_mma", _lib.ptr(planes[0]), _lib.ptr(planes[1]), n, H, W, pk["cin_pad"], pad, ks,
+                          _lib.ptr(pk["hi"]), _lib.ptr(pk["lo"]), pk["cout"], b, rp, rld, _lib.ptr(out.t), out.ld, sp, sld,
+                          _lib.stream_ptr())
+            else:
+                sp2, sld2 = self._st(out2.stats)
+                _lib.call("vt_conv_mma_dual", _lib.ptr(planes[0]), _lib.ptr(planes[1]), n, H, W, pk["cin_pad"], pad, ks,
+                          _lib.ptr(pk["hi"]), _lib.ptr(pk["lo"]), pk["cout"], b, rp, rld, _lib.ptr(out.t), out.ld, sp, sld,
+                          _lib.ptr(out2.t), out2.ld, _lib.ptr(res2.t), res2.ld, sp2, sld2, _lib.stream_ptr())
         else:
+            assert out2 is None, "the fused second output exists on the tensor-core path only"
             _lib.call("vt_conv_ffma", _lib.ptr(a.t), a.ld, _lib.ptr(op.scale), _lib.ptr(op.shift), int(op.relu), n, H, W, a.C,
                       ks, _lib.ptr(pk["ffma"]), pk["cout"], b, rp, rld, _lib.ptr(out.t), out.ld, sp, sld, _lib.stream_ptr())
         self.launches += 1
@@ -159,6 +168,17 @@ class HGEncoder:
         half, quarter = cout // 2, cout // 4
         out = self._new(n, H, W, cout)                      # out.stats: statistics of the block OUTPUT (after residual)
         raw_stats = self.arena.take(n, cout)                # statistics of the raw conv1 / conv2 outputs (bn2 / bn3 inputs)
+        if f"{name}.downsample.2" not in self.conv and mma_tileable(H, W) and not self.force_ffma:
+            # identity residual, tensor-core path: every conv epilogue also writes its slice of (cat + x) -- no add pass
+            raw = torch.empty(n, H, W, half + quarter, dtype=torch.float32, device=self.dev)
+            r1 = Act(raw[..., :half], raw_stats[:, :half])
+            r2 = Act(raw[..., half:], raw_stats[:, half:half + quarter])
+            self._conv(self._gn(x, f"{name}.bn1"), f"{name}.conv1", r1, stats=r1.stats, out2=out.slice(0, half), res2=x.slice(0, half))
+            self._conv(self._gn(r1, f"{name}.bn2"), f"{name}.conv2", r2, stats=r2.stats, out2=out.slice(half, half + quarter),
+                       res2=x.slice(half, half + quarter))
+            o3 = out.slice(half + quarter, cout)
+            self._conv(self._gn(r2, f"{name}.bn3"), f"{name}.conv3", o3, res=x.slice(half + quarter, cout), stats=o3.stats)
+            return out
         o1 = Act(out.t[..., :half], raw_stats[:, :half])
         o2 = Act(out.t[..., half:half + quarter], raw_stats[:, half:half + quarter])
         o3 = Act(out.t[..., half + quarter:], None)
