@@ -76,3 +76,44 @@ def test_conv_mma_rejects_untileable_shapes():
     planes, _ = ops.prep_split(x, None, None, False, 1)
     with pytest.raises(RuntimeError, match="vt_conv_mma"):
         ops.conv_mma(planes, 12, 12, 1, torch.zeros(64, 64, 3, 3))
+
+
+def test_conv_mma_dual_output_fuses_the_identity_residual():
+    """vt_conv_mma_dual: `out` keeps the raw conv slice (+ its statistics), `out2 = out + res2` is the ConvBlock output slice."""
+    from vistracker_b200 import _lib, ops
+    from vistracker_b200.weights import pack_conv
+    g = torch.Generator().manual_seed(11)
+    n, H, W, cin, cout = 2, 32, 64, 128, 64
+    x = torch.randn(n, cin, H, W, generator=g)
+    w = torch.randn(cout, cin, 3, 3, generator=g) * 0.05
+    res2 = torch.randn(n, cout, H, W, generator=g)
+    planes, _ = ops.prep_split(nhwc(x), None, None, False, 1)
+    pk = pack_conv(w.to(dev()))
+    out, out2 = torch.empty(n, H, W, cout, device=dev()), torch.empty(n, H, W, cout, device=dev())
+    st, st2 = ops.new_stats(n, cout, dev()), ops.new_stats(n, cout, dev())
+    r2 = nhwc(res2)
+    P = _lib.ptr
+    _lib.call("vt_conv_mma_dual", P(planes[0]), P(planes[1]), n, H, W, pk["cin_pad"], 1, 3, P(pk["hi"]), P(pk["lo"]), cout, None, None, 0,
+              P(out), cout, P(st), cout, P(out2), cout, P(r2), cout, P(st2), cout, _lib.stream_ptr())
+    ref = F.conv2d(x.double(), w.double(), padding=1)
+    assert rel_err(nchw(out), ref) < 5e-6 and rel_err(st.cpu(), chan_stats(ref)) < 1e-5
+    assert rel_err(nchw(out2), ref + res2.double()) < 5e-6 and rel_err(st2.cpu(), chan_stats(ref + res2.double())) < 1e-5
+
+
+def test_encoder_plan_with_fused_residual_matches_oracle(monkeypatch):
+    """VT_FUSE_RESIDUAL=1 routes equal-width ConvBlocks through the dual-output epilogue; results must not change."""
+    monkeypatch.setenv("VT_FUSE_RESIDUAL", "1")
+    from oracle import sifnet_ref as R
+    from vistracker_b200 import CHORETriplaneVisibility, default_options, resolve_dims
+    from vistracker_b200.synth import synthetic_frames, synthetic_state_dict
+    dims = resolve_dims(default_options())
+    sd = synthetic_state_dict(dims, seed=0)
+    net = CHORETriplaneVisibility(default_options(), device="cuda:0").eval()
+    net.load_state_dict(sd)
+    assert net._rgb.fuse_residual
+    images, *_ = synthetic_frames(1, size=512, seed=77, n_points=4)
+    net.filter(images.cuda())
+    with torch.no_grad():
+        maps = R.sif_filter(sd, images)
+    assert rel_err(net.im_feat_list[0].cpu(), maps["im_feat"]) < 1e-4
+    assert rel_err(net.triplane_feat_list[2][0].cpu(), maps["tri_feat"][2]) < 1e-4
