@@ -96,6 +96,15 @@ int vt_query_fwd(const float* points, const float* crop_center, const float* bod
                  int Wt, int c_im, int c_tmpx, int c_tt, int c_tf, const float* cam7, const float* wpack, float* out,
                  float* feat_out, float* xy_out, void* stream);
 
+/* vt_query_fwd with the five decoder MLPs on the tcgen05 tensor cores (fp16 hi/lo split, fp32 TMEM accumulators; 128 points per
+ * CTA).  w1_hi/lo: fp16 [5*128][640], w23_hi/lo: fp16 [2*5*128][128] (vistracker_b200/weights.py: pack_decoders_tc); `wpack` is the
+ * fp32 pack of vt_query_fwd (biases and the last layer are read from it).  *overflow counts values beyond the fp16 range.
+ * Channel counts are fixed to the tri-vis layout (256 / 64 / 32 / 64). */
+int vt_query_fwd_tc(const float* points, const float* crop_center, const float* body_center, int B, int N, const float* im_feat,
+                    const float* tmpx, const float* tri_tmpx, const float* tri_feat, int Hf, int Wf, int Ht, int Wt, const float* cam7,
+                    const float* wpack, const void* w1_hi, const void* w1_lo, const void* w23_hi, const void* w23_lo, float* out,
+                    float* xy_out, int* overflow, void* stream);
+
 /* Gradient of sum(g_out * out) w.r.t. the points -- what autograd computes for `df.sum().backward()` in
  * Generator.approx_surface (recon/gen/generator.py:86-96) and for the df / part / centre losses of the fitters
  * (recon/recon_fit_behave.py:467-513, recon/recon_fit_trivis_full.py:193-270).  The forward is recomputed on chip.

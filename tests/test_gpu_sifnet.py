@@ -138,3 +138,20 @@ def test_query_gradient_all_heads_matches_oracle(net):
     net.query(pts, crop_center=crop.cuda(), body_center=body.cuda())
     sum((o.reshape(2, -1, 77) * c.cuda()).sum() for o, c in zip(net.get_preds(), cot)).backward()
     assert rel_err(pts.grad.cpu(), p_ref.grad) < TOL
+
+
+def test_tensor_core_and_cuda_core_decoders_agree(net):
+    """query_fwd_tc_kernel (tcgen05, default) against query_fwd_kernel (fp32 FFMA) on the same maps; N not a multiple of 128."""
+    images, points, crop, body = synthetic_frames(2, size=64, seed=41, n_points=777, jitter=True)
+    net.filter(images.cuda())
+    assert not net.query_on_cuda_cores
+    out_tc, xy_tc = net._query_raw(points.cuda(), crop.cuda(), body.cuda(), want_xy=True)
+    net.query_on_cuda_cores = True
+    try:
+        out_cc, xy_cc = net._query_raw(points.cuda(), crop.cuda(), body.cuda(), want_xy=True)
+    finally:
+        net.query_on_cuda_cores = False
+    net.check()
+    assert torch.equal(xy_tc, xy_cc)
+    for lo, hi in ((0, 2), (2, 11), (11, 25), (25, 28), (28, 29)):
+        assert rel_err(out_tc[:, lo:hi].cpu(), out_cc[:, lo:hi].cpu()) < 2e-5

@@ -29,6 +29,7 @@ SIGNATURES = {
     "vt_upsample2x_add": (_i, [_p, _p, _i, _i, _i, _i, _p, _p, _i, _p]),
     "vt_query_wpack_floats": (_ll, []),
     "vt_query_fwd": (_i, [_p, _p, _p, _i, _i, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p]),
+    "vt_query_fwd_tc": (_i, [_p, _p, _p, _i, _i, _p, _p, _p, _p, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
     "vt_query_wpack_bwd_floats": (_ll, []),
     "vt_query_bwd": (_i, [_p, _p, _p, _i, _i, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p]),
 }

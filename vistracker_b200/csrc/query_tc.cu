@@ -1,0 +1,427 @@
+// SIF-Net point query, forward, with the five decoder MLPs on the tcgen05 tensor cores
+// (model/chore_triplane.py:97-164, model/chore_tri_vis.py:31-50 -- same contract as query_fwd_kernel in query.cu, which stays
+// as the CUDA-core cross-check and as the forward recompute inside the backward kernel).
+//
+// One CTA = 128 query points = the M dimension of every MMA.  fp32 parity comes from the same fp16 split as the convolution
+// (x = hi + lo, three MMAs per K-step: hi*hi + hi*lo + lo*hi); here lo is NOT rescaled (features and weights are O(1e-2..1e1),
+// so lo stays at or just below the fp16 normal range and its absolute error is <= 2^-25), which lets all three MMAs accumulate
+// into ONE fp32 TMEM accumulator per head: 128 columns per head, four heads fill the 512 TMEM columns.  The kernel therefore
+// makes two passes over the feature chunks: heads {df, pca, parts, centers}, then {visibility}.
+//
+// Warp roles (448 threads):
+//   warps 0-3   epilogue: TMEM -> registers, bias + ReLU, fp16 split, write the next layer's A operand into shared memory in the
+//               UMMA K-major 128-byte-swizzled layout; the last layer (128 -> <=14 outputs) runs on the CUDA cores from registers
+//   warp  4     TMA producer: weight tiles [128 out x 64 in] (hi and lo planes) through a 2-slot ring
+//   warp  5     MMA issuer (one thread)
+//   warps 6-13  gather: projections once, then per 64-feature chunk 4 bilinear taps per point from the NHWC maps, split, and
+//               store straight into the swizzled A-operand slot (2-slot ring)
+// Feature order for this kernel (10 chunks of 64, every chunk maps to whole channel runs of one or two maps):
+//   [ im_feat 4x64 | tmpx 64 | tri_feat right 64 | back 64 | top 64 | tri_tmpx right 32, back 32 | tri_tmpx top 32, x, y, z-2.2, 0... ]
+#include <cuda.h>
+#include "common.cuh"
+#include "vt_internal.h"
+
+namespace vt {
+
+constexpr int TQ_M = 128;                 // points per CTA
+constexpr int TQ_KC = 64;                 // features per chunk
+constexpr int TQ_NCHUNK = 10;             // 640 padded features
+constexpr int TQ_H = 128;                 // hidden width
+constexpr int TQ_THREADS = 448;
+constexpr int TQ_GATHER_WARPS = 8;
+constexpr int TQ_PLANE = TQ_M * TQ_KC * 2;      // 16 KB: one fp16 plane of a [128 x 64] operand tile
+constexpr int TQ_SLOT = 2 * TQ_PLANE;           // hi + lo
+constexpr int TQ_NF = 2, TQ_NW = 2;             // feature-ring and weight-ring depths
+constexpr int TQ_SMEM = TQ_NF * TQ_SLOT + TQ_NW * TQ_SLOT + 2 * TQ_SLOT + 1024;   // rings + activation buffer (two K chunks)
+constexpr uint32_t TQ_IDESC = (1u << 4) | ((uint32_t)(TQ_H >> 3) << 17) | ((uint32_t)(TQ_M >> 4) << 24);
+
+struct TqMaps {
+  const float* im_feat; const float* tmpx; const float* tri_tmpx; const float* tri_feat;
+  int Hf, Wf, Ht, Wt;
+};
+struct TqCam { float fx, fy, cx, cy, crop, z0, out_dist; };
+
+__device__ __forceinline__ uint32_t tq_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void tq_mbar_init(uint32_t bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count)); }
+__device__ __forceinline__ void tq_mbar_arrive(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
+__device__ __forceinline__ void tq_mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool tq_mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+               : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void tq_mbar_wait(uint32_t bar, uint32_t parity) {
+  long long t0 = clock64();
+  while (!tq_mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) { printf("vt query_tc: mbarrier timeout (block %d,%d thread %d)\n", blockIdx.x, blockIdx.y, threadIdx.x); __trap(); }
+  }
+}
+__device__ __forceinline__ void tq_tma_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+               ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tq_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tq_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tq_fence_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tq_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tq_mma(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t accumulate) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+               ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(TQ_IDESC), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ uint64_t tq_desc(uint32_t saddr) {      // K-major, SWIZZLE_128B, SBO 1024 B, version 1
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+__device__ __forceinline__ void tq_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// byte offset of element (row, k) inside one [128 x 64] fp16 plane in the K-major 128-byte-swizzled layout
+__device__ __forceinline__ uint32_t tq_sw_off(int row, int k) {
+  return (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + ((((k >> 3) ^ (row & 7)) & 7) << 4) + (k & 7) * 2);
+}
+__device__ __forceinline__ void tq_split(float x, __half& hi, __half& lo, int& sat) {
+  if (fabsf(x) > 65504.f) { sat = 1; x = copysignf(65504.f, x); }
+  hi = __float2half_rn(x);
+  lo = __float2half_rn(x - __half2float(hi));
+}
+
+struct TqProj { float nx, ny, tu0, tv0, tu1, tv1, tu2, tv2; };
+
+// bilinear sample of 2 consecutive channels (c, c+1) at (u, v) in [-1, 1]; grid_sample(align_corners=True, zeros padding)
+__device__ __forceinline__ float2 tq_sample2(const float* __restrict__ map, int H, int W, int C, int c, float u, float v) {
+  float ix = __fmul_rn(__fmul_rn(__fadd_rn(u, 1.f), 0.5f), (float)(W - 1));
+  float iy = __fmul_rn(__fmul_rn(__fadd_rn(v, 1.f), 0.5f), (float)(H - 1));
+  float fx0 = floorf(ix), fy0 = floorf(iy);
+  float tx = ix - fx0, ty = iy - fy0;
+  bool finite = (fabsf(ix) < 1e9f) && (fabsf(iy) < 1e9f);
+  int x0 = finite ? (int)fx0 : -10, y0 = finite ? (int)fy0 : -10;
+  bool vx0 = x0 >= 0 && x0 < W, vx1 = x0 + 1 >= 0 && x0 + 1 < W, vy0 = y0 >= 0 && y0 < H, vy1 = y0 + 1 >= 0 && y0 + 1 < H;
+  const float* b00 = map + ((long long)y0 * W + x0) * C + c;
+  float2 a = make_float2(0.f, 0.f);
+  float w;
+  if (vy0 && vx0) { float2 t = *reinterpret_cast<const float2*>(b00); w = (1.f - tx) * (1.f - ty); a.x += t.x * w; a.y += t.y * w; }
+  if (vy0 && vx1) { float2 t = *reinterpret_cast<const float2*>(b00 + C); w = tx * (1.f - ty); a.x += t.x * w; a.y += t.y * w; }
+  if (vy1 && vx0) { float2 t = *reinterpret_cast<const float2*>(b00 + (long long)W * C); w = (1.f - tx) * ty; a.x += t.x * w; a.y += t.y * w; }
+  if (vy1 && vx1) { float2 t = *reinterpret_cast<const float2*>(b00 + (long long)W * C + C); w = tx * ty; a.x += t.x * w; a.y += t.y * w; }
+  return a;
+}
+
+__global__ void __launch_bounds__(TQ_THREADS, 1)
+query_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_constant__ CUtensorMap tm_w1_lo,
+                    const __grid_constant__ CUtensorMap tm_w23_hi, const __grid_constant__ CUtensorMap tm_w23_lo,
+                    const float* __restrict__ points, const float* __restrict__ crop_center, const float* __restrict__ body_center,
+                    int B, int N, TqMaps m, TqCam cam, const float* __restrict__ wpack /*fp32 pack of query.cu: biases + W4*/,
+                    int wpack_head_stride, float* __restrict__ out, float* __restrict__ xy_out, int* __restrict__ overflow) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t feat_full[TQ_NF], feat_empty[TQ_NF], w_full[TQ_NW], w_empty[TQ_NW], acc_full, act_full;
+  __shared__ uint32_t s_tmem_base;
+  __shared__ TqProj s_proj[TQ_M];
+  __shared__ float s_xyz[TQ_M][3];
+  __shared__ int s_in_img[TQ_M];
+
+  const uint32_t smem_base = (tq_smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_al = smem_raw + (smem_base - tq_smem_u32(smem_raw));
+  const uint32_t feat_base = smem_base, w_base = smem_base + TQ_NF * TQ_SLOT, act_base = w_base + TQ_NW * TQ_SLOT;
+  uint8_t* feat_ptr = smem_al;
+  uint8_t* act_ptr = smem_al + TQ_NF * TQ_SLOT + TQ_NW * TQ_SLOT;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.y, n0 = blockIdx.x * TQ_M;
+
+  if (warp == 5 && lane == 0) {
+    for (int s = 0; s < TQ_NF; ++s) { tq_mbar_init(tq_smem_u32(&feat_full[s]), TQ_GATHER_WARPS); tq_mbar_init(tq_smem_u32(&feat_empty[s]), 1); }
+    for (int s = 0; s < TQ_NW; ++s) { tq_mbar_init(tq_smem_u32(&w_full[s]), 1); tq_mbar_init(tq_smem_u32(&w_empty[s]), 1); }
+    tq_mbar_init(tq_smem_u32(&acc_full), 1);
+    tq_mbar_init(tq_smem_u32(&act_full), 4);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 4 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_w1_hi) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_w1_lo) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_w23_hi) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_w23_lo) : "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tq_smem_u32(&s_tmem_base)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  // projections of the tile's points (gather warps, one thread per point)
+  if (warp >= 6 && (threadIdx.x - 6 * 32) < TQ_M) {
+    const int pp = threadIdx.x - 6 * 32, n = n0 + pp;
+    TqProj q; float x = 0.f, y = 0.f, z = 1.f; int in_img = 1;
+    if (n < N) {
+      const float* pt = points + ((size_t)b * N + n) * 3;
+      x = pt[0]; y = pt[1]; z = pt[2];
+      float px = __fadd_rn(__fdiv_rn(__fmul_rn(cam.fx, x), z), cam.cx);
+      float py = __fadd_rn(__fdiv_rn(__fmul_rn(cam.fy, y), z), cam.cy);
+      px = __fadd_rn(__fadd_rn(cam.crop * 0.5f, px), -crop_center[b * 2 + 0]);
+      py = __fadd_rn(__fadd_rn(cam.crop * 0.5f, py), -crop_center[b * 2 + 1]);
+      q.nx = __fadd_rn(__fdiv_rn(__fmul_rn(2.f, px), cam.crop), -1.f);
+      q.ny = __fadd_rn(__fdiv_rn(__fmul_rn(2.f, py), cam.crop), -1.f);
+      in_img = (q.nx >= -1.f && q.nx <= 1.f && q.ny >= -1.f && q.ny <= 1.f) ? 1 : 0;
+      const float cx = __fadd_rn(x, -body_center[b * 3 + 0]), cy = __fadd_rn(y, -body_center[b * 3 + 1]), cz = __fadd_rn(z, -body_center[b * 3 + 2]);
+      q.tu0 = cz; q.tv0 = cy; q.tu1 = -cx; q.tv1 = cy; q.tu2 = cx; q.tv2 = -cz;
+      if (xy_out) { xy_out[((size_t)b * 2 + 0) * N + n] = q.nx; xy_out[((size_t)b * 2 + 1) * N + n] = q.ny; }
+    } else {
+      q.nx = q.ny = q.tu0 = q.tv0 = q.tu1 = q.tv1 = q.tu2 = q.tv2 = 1e30f;       // every tap out of range -> zero features
+    }
+    s_proj[pp] = q; s_xyz[pp][0] = x; s_xyz[pp][1] = y; s_xyz[pp][2] = __fadd_rn(z, -cam.z0); s_in_img[pp] = in_img;
+  }
+  tq_fence_before();
+  __syncthreads();
+  tq_fence_after();
+  const uint32_t tmem_base = s_tmem_base;
+
+  // head groups of the two passes: {0,1,2,3} then {4}; accumulator of head g in the group sits at column 128 * g
+  if (warp >= 6) {
+    // ================================================================== gather warps
+    const int gw = warp - 6;
+    int sat = 0, it = 0;
+    for (int pass = 0; pass < 2; ++pass) {
+      for (int c = 0; c < TQ_NCHUNK; ++c, ++it) {
+        const int slot = it % TQ_NF;
+        tq_mbar_wait(tq_smem_u32(&feat_empty[slot]), ((uint32_t)(it / TQ_NF) & 1u) ^ 1u);
+        uint8_t* dst = feat_ptr + slot * TQ_SLOT;
+        for (int i = 0; i < TQ_M / TQ_GATHER_WARPS; ++i) {
+          const int pp = gw * (TQ_M / TQ_GATHER_WARPS) + i;
+          const TqProj q = s_proj[pp];
+          const int k = 2 * lane;                         // this lane produces features k, k+1 of the chunk
+          float2 v = make_float2(0.f, 0.f);
+          if (c < 4) {
+            v = tq_sample2(m.im_feat + (size_t)b * m.Hf * m.Wf * 256, m.Hf, m.Wf, 256, c * 64 + k, q.nx, q.ny);
+          } else if (c == 4) {
+            v = tq_sample2(m.tmpx + (size_t)b * m.Ht * m.Wt * 64, m.Ht, m.Wt, 64, k, q.nx, q.ny);
+          } else if (c < 8) {
+            const int view = c - 5;
+            const float u = view == 0 ? q.tu0 : view == 1 ? q.tu1 : q.tu2, w = view == 0 ? q.tv0 : view == 1 ? q.tv1 : q.tv2;
+            v = tq_sample2(m.tri_feat + ((size_t)view * B + b) * m.Hf * m.Wf * 64, m.Hf, m.Wf, 64, k, u, w);
+          } else if (c == 8) {
+            const int view = k >> 5;                      // lanes 0-15: right, 16-31: back
+            const float u = view == 0 ? q.tu0 : q.tu1, w = view == 0 ? q.tv0 : q.tv1;
+            v = tq_sample2(m.tri_tmpx + ((size_t)view * B + b) * m.Ht * m.Wt * 32, m.Ht, m.Wt, 32, k & 31, u, w);
+          } else {
+            if (k < 32) v = tq_sample2(m.tri_tmpx + ((size_t)2 * B + b) * m.Ht * m.Wt * 32, m.Ht, m.Wt, 32, k, q.tu2, q.tv2);
+            else if (k == 32) v = make_float2(s_xyz[pp][0], s_xyz[pp][1]);
+            else if (k == 34) v = make_float2(s_xyz[pp][2], 0.f);
+          }
+          __half h0, l0, h1, l1;
+          tq_split(v.x, h0, l0, sat); tq_split(v.y, h1, l1, sat);
+          const uint32_t off = tq_sw_off(pp, k);
+          *reinterpret_cast<__half2*>(dst + off) = __halves2half2(h0, h1);
+          *reinterpret_cast<__half2*>(dst + TQ_PLANE + off) = __halves2half2(l0, l1);
+        }
+        tq_fence_async();                                 // generic-proxy writes -> visible to the tensor core (async proxy)
+        __syncwarp();
+        if (lane == 0) tq_mbar_arrive(tq_smem_u32(&feat_full[slot]));
+      }
+    }
+    if (sat) atomicAdd(overflow, 1);
+  } else if (warp == 4) {
+    // ================================================================== TMA producer (weights)
+    if (lane == 0) {
+      int iw = 0;
+      auto load = [&](const CUtensorMap* hi, const CUtensorMap* lo, int col, int row) {
+        const int s = iw % TQ_NW;
+        tq_mbar_wait(tq_smem_u32(&w_empty[s]), ((uint32_t)(iw / TQ_NW) & 1u) ^ 1u);
+        const uint32_t full = tq_smem_u32(&w_full[s]);
+        tq_mbar_expect_tx(full, TQ_SLOT);
+        tq_tma_2d(w_base + s * TQ_SLOT, hi, full, col, row);
+        tq_tma_2d(w_base + s * TQ_SLOT + TQ_PLANE, lo, full, col, row);
+        ++iw;
+      };
+      for (int pass = 0; pass < 2; ++pass) {
+        const int h0 = pass == 0 ? 0 : 4, nh = pass == 0 ? 4 : 1;
+        for (int c = 0; c < TQ_NCHUNK; ++c)
+          for (int g = 0; g < nh; ++g) load(&tm_w1_hi, &tm_w1_lo, c * TQ_KC, (h0 + g) * TQ_H);
+        for (int g = 0; g < nh; ++g)
+          for (int layer = 0; layer < 2; ++layer)
+            for (int kc = 0; kc < 2; ++kc) load(&tm_w23_hi, &tm_w23_lo, kc * TQ_KC, (layer * 5 + h0 + g) * TQ_H);
+      }
+    }
+  } else if (warp == 5) {
+    // ================================================================== MMA issuer
+    if (lane == 0) {
+      int it = 0, iw = 0, iact = 0;
+      auto mma_tile = [&](uint32_t a_addr, uint32_t acc, bool first) {
+        const int s = iw % TQ_NW;
+        tq_mbar_wait(tq_smem_u32(&w_full[s]), (uint32_t)(iw / TQ_NW) & 1u);
+        tq_fence_after();
+        const uint64_t a_hi = tq_desc(a_addr), a_lo = tq_desc(a_addr + TQ_PLANE);
+        const uint64_t b_hi = tq_desc(w_base + s * TQ_SLOT), b_lo = tq_desc(w_base + s * TQ_SLOT + TQ_PLANE);
+#pragma unroll
+        for (int k = 0; k < TQ_KC / 16; ++k) {
+          const uint64_t adv = (uint64_t)(k * 32 >> 4);
+          tq_mma(acc, a_hi + adv, b_hi + adv, (first && k == 0) ? 0u : 1u);
+          tq_mma(acc, a_hi + adv, b_lo + adv, 1u);
+          tq_mma(acc, a_lo + adv, b_hi + adv, 1u);
+        }
+        tq_commit(tq_smem_u32(&w_empty[s]));
+        ++iw;
+      };
+      for (int pass = 0; pass < 2; ++pass) {
+        const int nh = pass == 0 ? 4 : 1;
+        for (int c = 0; c < TQ_NCHUNK; ++c, ++it) {
+          const int slot = it % TQ_NF;
+          tq_mbar_wait(tq_smem_u32(&feat_full[slot]), (uint32_t)(it / TQ_NF) & 1u);
+          tq_fence_after();
+          for (int g = 0; g < nh; ++g) mma_tile(feat_base + slot * TQ_SLOT, tmem_base + g * TQ_H, c == 0);
+          tq_commit(tq_smem_u32(&feat_empty[slot]));
+        }
+        tq_commit(tq_smem_u32(&acc_full));                 // layer 1 of the whole group is complete
+        for (int g = 0; g < nh; ++g)
+          for (int layer = 0; layer < 2; ++layer) {
+            tq_mbar_wait(tq_smem_u32(&act_full), (uint32_t)iact & 1u); ++iact;     // epilogue wrote this layer's input
+            tq_fence_after();
+            for (int kc = 0; kc < 2; ++kc) mma_tile(act_base + kc * TQ_SLOT, tmem_base + g * TQ_H, kc == 0);
+            tq_commit(tq_smem_u32(&acc_full));
+          }
+      }
+    }
+  } else {
+    // ================================================================== epilogue warps: thread = point row = TMEM lane
+    const int r = warp * 32 + lane, n = n0 + r;
+    const uint32_t lane_base = tmem_base + ((uint32_t)(warp * 32) << 16);
+    int iacc = 0, sat = 0;
+    const int head_nout[5] = {2, 9, 14, 3, 1}, head_off[5] = {0, 2, 11, 25, 28};
+    for (int pass = 0; pass < 2; ++pass) {
+      const int h0 = pass == 0 ? 0 : 4, nh = pass == 0 ? 4 : 1;
+      tq_mbar_wait(tq_smem_u32(&acc_full), (uint32_t)iacc & 1u); ++iacc;            // layer 1 done
+      tq_fence_after();
+      for (int g = 0; g < nh; ++g) {
+        const int h = h0 + g;
+        const float* hw = wpack + (size_t)h * wpack_head_stride;
+        const float* b1 = hw + 616 * 128;
+        const float* b2 = b1 + 128 + 128 * 128;
+        const float* b3 = b2 + 128 + 128 * 128;
+        const float* W4 = b3 + 128;
+        const float* b4 = W4 + 128 * 16;
+        for (int layer = 0; layer < 3; ++layer) {
+          if (layer > 0) { tq_mbar_wait(tq_smem_u32(&acc_full), (uint32_t)iacc & 1u); ++iacc; tq_fence_after(); }
+          const float* bias = layer == 0 ? b1 : layer == 1 ? b2 : b3;
+          float o[14];
+#pragma unroll
+          for (int c = 0; c < 14; ++c) o[c] = 0.f;
+#pragma unroll 1
+          for (int ch = 0; ch < 4; ++ch) {
+            float v[32];
+            tq_ld32(lane_base + g * TQ_H + ch * 32, v);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i] + __ldg(bias + ch * 32 + i), 0.f);
+            if (layer < 2) {
+              // next layer's A operand: K index = ch*32 + i -> chunk kc = ch / 2, k = (ch & 1) * 32 + i
+              uint8_t* dst = act_ptr + (ch >> 1) * TQ_SLOT;
+#pragma unroll
+              for (int i = 0; i < 32; i += 8) {
+                __align__(16) __half hh[8];
+                __align__(16) __half ll[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) tq_split(v[i + j], hh[j], ll[j], sat);
+                const uint32_t off = tq_sw_off(r, (ch & 1) * 32 + i);
+                *reinterpret_cast<uint4*>(dst + off) = *reinterpret_cast<const uint4*>(hh);
+                *reinterpret_cast<uint4*>(dst + TQ_PLANE + off) = *reinterpret_cast<const uint4*>(ll);
+              }
+            } else {
+              // last layer on the CUDA cores: out[c] += h3[k] * W4[k][c]
+#pragma unroll 4
+              for (int i = 0; i < 32; ++i) {
+                const float* wr = W4 + (ch * 32 + i) * 16;
+#pragma unroll
+                for (int c = 0; c < 14; ++c) o[c] = fmaf(v[i], __ldg(wr + c), o[c]);
+              }
+            }
+          }
+          if (layer < 2) {
+            tq_fence_before();                             // TMEM reads of this accumulator are done before the MMA overwrites it
+            tq_fence_async();
+            __syncwarp();
+            if (lane == 0) tq_mbar_arrive(tq_smem_u32(&act_full));
+          } else if (n < N) {
+            for (int c = 0; c < head_nout[h]; ++c) {
+              float a = o[c] + __ldg(b4 + c);
+              if (h == 4) a = 1.f / (1.f + expf(-a));
+              if (h == 0 && !s_in_img[r]) a = cam.out_dist;
+              out[((size_t)b * 29 + head_off[h] + c) * N + n] = a;
+            }
+          }
+        }
+      }
+      // the group's accumulators are drained: order these TMEM reads before the next pass's first MMAs
+      tq_fence_before();
+    }
+    if (sat) atomicAdd(overflow, 1);
+  }
+  tq_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+typedef CUresult (*TqEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                               const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static int tq_make_map(CUtensorMap* m, const void* base, int k_cols, int rows) {
+  static TqEncodeFn fn = nullptr;
+  if (!fn) {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = (TqEncodeFn)sym;
+  }
+  if (!fn) { set_error("cuTensorMapEncodeTiled is not available from the driver"); return -2; }
+  cuuint64_t dims[2] = {(cuuint64_t)k_cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)k_cols * 2};
+  cuuint32_t box[2] = {(cuuint32_t)TQ_KC, (cuuint32_t)TQ_H}, estr[2] = {1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r); return -2; }
+  return 0;
+}
+
+}  // namespace vt
+
+using namespace vt;
+
+extern "C" {
+
+int vt_query_fwd_tc(const float* points, const float* crop_center, const float* body_center, int B, int N, const float* im_feat,
+                    const float* tmpx, const float* tri_tmpx, const float* tri_feat, int Hf, int Wf, int Ht, int Wt, const float* cam7,
+                    const float* wpack, const void* w1_hi, const void* w1_lo, const void* w23_hi, const void* w23_lo, float* out,
+                    float* xy_out, int* overflow, void* stream) {
+  if (B <= 0 || N <= 0) return 0;
+  CUtensorMap m1h, m1l, m2h, m2l;
+  int rc;
+  if ((rc = tq_make_map(&m1h, w1_hi, TQ_NCHUNK * TQ_KC, 5 * TQ_H))) return rc;
+  if ((rc = tq_make_map(&m1l, w1_lo, TQ_NCHUNK * TQ_KC, 5 * TQ_H))) return rc;
+  if ((rc = tq_make_map(&m2h, w23_hi, TQ_H, 2 * 5 * TQ_H))) return rc;
+  if ((rc = tq_make_map(&m2l, w23_lo, TQ_H, 2 * 5 * TQ_H))) return rc;
+  TqMaps m{im_feat, tmpx, tri_tmpx, tri_feat, Hf, Wf, Ht, Wt};
+  TqCam cam{cam7[0], cam7[1], cam7[2], cam7[3], cam7[4], cam7[5], cam7[6]};
+  cudaError_t e = cudaFuncSetAttribute(query_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TQ_SMEM);
+  if (e != cudaSuccess) return cuda_fail(e, "vt_query_fwd_tc smem attr");
+  dim3 grid(ceil_div(N, TQ_M), B);
+  const int head_stride = 616 * 128 + 128 + 2 * (128 * 128 + 128) + 128 * 16 + 16;
+  query_fwd_tc_kernel<<<grid, TQ_THREADS, TQ_SMEM, (cudaStream_t)stream>>>(m1h, m1l, m2h, m2l, points, crop_center, body_center, B, N, m, cam,
+                                                                          wpack, head_stride, out, xy_out, overflow);
+  VT_CHECK_LAUNCH("vt_query_fwd_tc");
+  return 0;
+}
+
+}  // extern "C"

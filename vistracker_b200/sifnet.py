@@ -19,7 +19,7 @@ from . import _lib
 from .config import SIFNetDims, resolve_dims
 from .encoder import HGEncoder
 from .synth import sifnet_spec
-from .weights import pack_decoders, pack_decoders_bwd
+from .weights import pack_decoders, pack_decoders_bwd, pack_decoders_tc
 
 N_OUT = 29          # df 2 | pca 9 | parts 14 | centers 3 | visibility 1
 
@@ -72,6 +72,8 @@ class CHORETriplaneVisibility:
         self.intermediate_preds_list = []
         self.points = self.points_xy = self.crop_center = self.local_feat_list = self.input_images = None
         self.defer_checks = False
+        import os
+        self.query_on_cuda_cores = os.environ.get("VT_QUERY", "") == "ffma"      # cross-check switch; default = tensor cores
 
     # ------------------------------------------------------------------ nn.Module-like surface
     def to(self, device):
@@ -112,6 +114,8 @@ class CHORETriplaneVisibility:
             self._tri = HGEncoder(sd, "triplane_encoder", self.dims.tri, self.device)
             self._wpack = pack_decoders(sd, self.device)
             self._wpack_bwd = pack_decoders_bwd(sd, self.device)
+            self._wtc = pack_decoders_tc(sd, self.device)
+            self._q_overflow = torch.zeros(1, dtype=torch.int32, device=self.device)
         assert self._wpack.numel() == _lib.load().vt_query_wpack_floats()
         assert self._wpack_bwd.numel() == _lib.load().vt_query_wpack_bwd_floats()
         return self
@@ -136,6 +140,9 @@ class CHORETriplaneVisibility:
     def check(self):
         self._rgb.check_overflow()
         self._tri.check_overflow()
+        if int(self._q_overflow.item()) != 0:
+            self._q_overflow.zero_()
+            raise RuntimeError("a feature / activation exceeded the fp16 range in the tensor-core decoder path")
 
     # reference attribute names, as NCHW-shaped views of the NHWC buffers (no copy)
     @property
@@ -178,6 +185,14 @@ class CHORETriplaneVisibility:
         xy = torch.empty(B, 2, N, dtype=torch.float32, device=self.device) if want_xy else None
         feat = torch.empty(B, self.feature_size, N, dtype=torch.float32, device=self.device) if want_feat else None
         d = self.dims
+        if not want_feat and not self.query_on_cuda_cores:
+            # decoders on the tensor cores (csrc/query_tc.cu); the feature dump only exists in the CUDA-core kernel
+            with torch.cuda.device(self.device):
+                _lib.call("vt_query_fwd_tc", _lib.ptr(pts), _lib.ptr(cc), _lib.ptr(bc), B, N, _lib.ptr(im_feat), _lib.ptr(tmpx),
+                          _lib.ptr(tri_tmpx), _lib.ptr(tri_feat), im_feat.shape[1], im_feat.shape[2], tmpx.shape[1], tmpx.shape[2],
+                          self._cam7, _lib.ptr(self._wpack), *(_lib.ptr(t) for t in self._wtc), _lib.ptr(out), _lib.ptr(xy),
+                          _lib.ptr(self._q_overflow), _lib.stream_ptr())
+            return out, xy
         with torch.cuda.device(self.device):
             _lib.call("vt_query_fwd", _lib.ptr(pts), _lib.ptr(cc), _lib.ptr(bc), B, N, _lib.ptr(im_feat), _lib.ptr(tmpx),
                       _lib.ptr(tri_tmpx), _lib.ptr(tri_feat), im_feat.shape[1], im_feat.shape[2], tmpx.shape[1], tmpx.shape[2],

@@ -92,3 +92,36 @@ def pack_decoders_bwd(sd: Dict[str, torch.Tensor], device) -> torch.Tensor:
         w4b[:nout] = sd[f"{name}.6.weight"][:, :, 0].float().cpu()
         chunks.append(w4b.reshape(-1))
     return torch.cat(chunks).contiguous().to(device)
+
+
+def feature_permutation_tc() -> torch.Tensor:
+    """tensor-core kernel feature index (csrc/query_tc.cu, 640 padded) -> reference feature index, -1 for zero padding:
+    im_feat 256 | tmpx 64 | tri_feat r, b, t 3x64 | tri_tmpx r 32, b 32 | tri_tmpx t 32, x, y, z-2.2, 29 zeros."""
+    ref = list(range(256)) + list(range(259, 323)) + list(range(419, 611)) + list(range(323, 387)) + list(range(387, 419)) + [256, 257, 258]
+    return torch.tensor(ref + [-1] * (640 - len(ref)), dtype=torch.long)
+
+
+def split_f16_unscaled(x: torch.Tensor):
+    """x ~= hi + lo with lo NOT rescaled (single-accumulator scheme of csrc/query_tc.cu)."""
+    x = x.float()
+    if float(x.abs().max()) > 65504.0:
+        raise ValueError("weight magnitude exceeds the fp16 range")
+    hi = x.half()
+    return hi.contiguous(), (x - hi.float()).half().contiguous()
+
+
+def pack_decoders_tc(sd: Dict[str, torch.Tensor], device):
+    """fp16 hi/lo planes for the tcgen05 decoder kernel: W1 [5*128, 640] (rows = head, unit; columns in the kernel's feature
+    order) and W2|W3 [2*5*128, 128] (layer-major, then head) -- torch's [out][in] layout, i.e. K-major B operands."""
+    perm = feature_permutation_tc()
+    w1 = torch.zeros(5 * Q_H, 640)
+    w23 = torch.zeros(2 * 5 * Q_H, Q_H)
+    valid = perm >= 0
+    for h, name in enumerate(HEADS):
+        w = sd[f"{name}.0.weight"][:, :, 0].float().cpu()
+        w1[h * Q_H:(h + 1) * Q_H][:, valid] = w[:, perm[valid]]
+        for li, idx in enumerate((2, 4)):
+            w23[(li * 5 + h) * Q_H:(li * 5 + h + 1) * Q_H] = sd[f"{name}.{idx}.weight"][:, :, 0].float().cpu()
+    w1h, w1l = split_f16_unscaled(w1)
+    w2h, w2l = split_f16_unscaled(w23)
+    return tuple(t.to(device) for t in (w1h, w1l, w2h, w2l))
