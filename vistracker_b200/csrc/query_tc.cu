@@ -104,8 +104,12 @@ __device__ __forceinline__ void tq_split(float x, __half& hi, __half& lo, int& s
 
 struct TqProj { float nx, ny, tu0, tv0, tu1, tv1, tu2, tv2; };
 
-// bilinear sample of 2 consecutive channels (c, c+1) at (u, v) in [-1, 1]; grid_sample(align_corners=True, zeros padding)
-__device__ __forceinline__ float2 tq_sample2(const float* __restrict__ map, int H, int W, int C, int c, float u, float v) {
+// bilinear sample of 2 consecutive channels at (u, v) in [-1, 1] -- grid_sample(align_corners=True, zeros padding) -- split into an
+// address/weight set-up and the loads, so that the taps of several points can be in flight together (the gather is latency-bound).
+struct TqTap { const float* p; float w00, w01, w10, w11; int rowstride; int C; unsigned valid; };
+
+__device__ __forceinline__ TqTap tq_tap_setup(const float* __restrict__ map, int H, int W, int C, int c, float u, float v) {
+  TqTap t;
   float ix = __fmul_rn(__fmul_rn(__fadd_rn(u, 1.f), 0.5f), (float)(W - 1));
   float iy = __fmul_rn(__fmul_rn(__fadd_rn(v, 1.f), 0.5f), (float)(H - 1));
   float fx0 = floorf(ix), fy0 = floorf(iy);
@@ -113,14 +117,12 @@ __device__ __forceinline__ float2 tq_sample2(const float* __restrict__ map, int 
   bool finite = (fabsf(ix) < 1e9f) && (fabsf(iy) < 1e9f);
   int x0 = finite ? (int)fx0 : -10, y0 = finite ? (int)fy0 : -10;
   bool vx0 = x0 >= 0 && x0 < W, vx1 = x0 + 1 >= 0 && x0 + 1 < W, vy0 = y0 >= 0 && y0 < H, vy1 = y0 + 1 >= 0 && y0 + 1 < H;
-  const float* b00 = map + ((long long)y0 * W + x0) * C + c;
-  float2 a = make_float2(0.f, 0.f);
-  float w;
-  if (vy0 && vx0) { float2 t = *reinterpret_cast<const float2*>(b00); w = (1.f - tx) * (1.f - ty); a.x += t.x * w; a.y += t.y * w; }
-  if (vy0 && vx1) { float2 t = *reinterpret_cast<const float2*>(b00 + C); w = tx * (1.f - ty); a.x += t.x * w; a.y += t.y * w; }
-  if (vy1 && vx0) { float2 t = *reinterpret_cast<const float2*>(b00 + (long long)W * C); w = (1.f - tx) * ty; a.x += t.x * w; a.y += t.y * w; }
-  if (vy1 && vx1) { float2 t = *reinterpret_cast<const float2*>(b00 + (long long)W * C + C); w = tx * ty; a.x += t.x * w; a.y += t.y * w; }
-  return a;
+  t.valid = (vy0 && vx0 ? 1u : 0u) | (vy0 && vx1 ? 2u : 0u) | (vy1 && vx0 ? 4u : 0u) | (vy1 && vx1 ? 8u : 0u);
+  // clamp the base so that even masked-out taps would be in-bounds addresses (they are not dereferenced)
+  t.p = map + ((long long)y0 * W + x0) * C + c;
+  t.w00 = (1.f - tx) * (1.f - ty); t.w01 = tx * (1.f - ty); t.w10 = (1.f - tx) * ty; t.w11 = tx * ty;
+  t.rowstride = W * C; t.C = C;
+  return t;
 }
 
 __global__ void __launch_bounds__(TQ_THREADS, 1)
@@ -135,6 +137,7 @@ query_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_c
   __shared__ TqProj s_proj[TQ_M];
   __shared__ float s_xyz[TQ_M][3];
   __shared__ int s_in_img[TQ_M];
+  __shared__ __align__(16) float s_w4[TQ_H * 16 + 16];      // last layer of the current head: W4[128][16] + b4[16]
 
   const uint32_t smem_base = (tq_smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_al = smem_raw + (smem_base - tq_smem_u32(smem_raw));
@@ -198,33 +201,62 @@ query_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_c
         const int slot = it % TQ_NF;
         tq_mbar_wait(tq_smem_u32(&feat_empty[slot]), ((uint32_t)(it / TQ_NF) & 1u) ^ 1u);
         uint8_t* dst = feat_ptr + slot * TQ_SLOT;
-        for (int i = 0; i < TQ_M / TQ_GATHER_WARPS; ++i) {
-          const int pp = gw * (TQ_M / TQ_GATHER_WARPS) + i;
-          const TqProj q = s_proj[pp];
-          const int k = 2 * lane;                         // this lane produces features k, k+1 of the chunk
-          float2 v = make_float2(0.f, 0.f);
-          if (c < 4) {
-            v = tq_sample2(m.im_feat + (size_t)b * m.Hf * m.Wf * 256, m.Hf, m.Wf, 256, c * 64 + k, q.nx, q.ny);
-          } else if (c == 4) {
-            v = tq_sample2(m.tmpx + (size_t)b * m.Ht * m.Wt * 64, m.Ht, m.Wt, 64, k, q.nx, q.ny);
-          } else if (c < 8) {
-            const int view = c - 5;
-            const float u = view == 0 ? q.tu0 : view == 1 ? q.tu1 : q.tu2, w = view == 0 ? q.tv0 : view == 1 ? q.tv1 : q.tv2;
-            v = tq_sample2(m.tri_feat + ((size_t)view * B + b) * m.Hf * m.Wf * 64, m.Hf, m.Wf, 64, k, u, w);
-          } else if (c == 8) {
-            const int view = k >> 5;                      // lanes 0-15: right, 16-31: back
-            const float u = view == 0 ? q.tu0 : q.tu1, w = view == 0 ? q.tv0 : q.tv1;
-            v = tq_sample2(m.tri_tmpx + ((size_t)view * B + b) * m.Ht * m.Wt * 32, m.Ht, m.Wt, 32, k & 31, u, w);
-          } else {
-            if (k < 32) v = tq_sample2(m.tri_tmpx + ((size_t)2 * B + b) * m.Ht * m.Wt * 32, m.Ht, m.Wt, 32, k, q.tu2, q.tv2);
-            else if (k == 32) v = make_float2(s_xyz[pp][0], s_xyz[pp][1]);
-            else if (k == 34) v = make_float2(s_xyz[pp][2], 0.f);
+        const int k = 2 * lane;                           // this lane produces features k, k+1 of the chunk
+        constexpr int PB = 4;                             // points in flight per warp
+        for (int i0 = 0; i0 < TQ_M / TQ_GATHER_WARPS; i0 += PB) {
+          TqTap tap[PB];
+          float2 direct[PB];
+          bool sampled = true;
+#pragma unroll
+          for (int j = 0; j < PB; ++j) {
+            const int pp = gw * (TQ_M / TQ_GATHER_WARPS) + i0 + j;
+            const TqProj q = s_proj[pp];
+            direct[j] = make_float2(0.f, 0.f);
+            if (c < 4) {
+              tap[j] = tq_tap_setup(m.im_feat + (size_t)b * m.Hf * m.Wf * 256, m.Hf, m.Wf, 256, c * 64 + k, q.nx, q.ny);
+            } else if (c == 4) {
+              tap[j] = tq_tap_setup(m.tmpx + (size_t)b * m.Ht * m.Wt * 64, m.Ht, m.Wt, 64, k, q.nx, q.ny);
+            } else if (c < 8) {
+              const int view = c - 5;
+              const float u = view == 0 ? q.tu0 : view == 1 ? q.tu1 : q.tu2, w = view == 0 ? q.tv0 : view == 1 ? q.tv1 : q.tv2;
+              tap[j] = tq_tap_setup(m.tri_feat + ((size_t)view * B + b) * m.Hf * m.Wf * 64, m.Hf, m.Wf, 64, k, u, w);
+            } else if (c == 8) {
+              const int view = k >> 5;                    // lanes 0-15: right, 16-31: back
+              const float u = view == 0 ? q.tu0 : q.tu1, w = view == 0 ? q.tv0 : q.tv1;
+              tap[j] = tq_tap_setup(m.tri_tmpx + ((size_t)view * B + b) * m.Ht * m.Wt * 32, m.Ht, m.Wt, 32, k & 31, u, w);
+            } else {
+              tap[j] = tq_tap_setup(m.tri_tmpx + ((size_t)2 * B + b) * m.Ht * m.Wt * 32, m.Ht, m.Wt, 32, k & 31, q.tu2, q.tv2);
+              if (k >= 32) {
+                tap[j].valid = 0u; sampled = false;
+                if (k == 32) direct[j] = make_float2(s_xyz[pp][0], s_xyz[pp][1]);
+                else if (k == 34) direct[j] = make_float2(s_xyz[pp][2], 0.f);
+              }
+            }
           }
-          __half h0, l0, h1, l1;
-          tq_split(v.x, h0, l0, sat); tq_split(v.y, h1, l1, sat);
-          const uint32_t off = tq_sw_off(pp, k);
-          *reinterpret_cast<__half2*>(dst + off) = __halves2half2(h0, h1);
-          *reinterpret_cast<__half2*>(dst + TQ_PLANE + off) = __halves2half2(l0, l1);
+          float2 t00[PB], t01[PB], t10[PB], t11[PB];
+#pragma unroll
+          for (int j = 0; j < PB; ++j) {                  // all loads first
+            const float2 z = make_float2(0.f, 0.f);
+            t00[j] = (tap[j].valid & 1u) ? *reinterpret_cast<const float2*>(tap[j].p) : z;
+            t01[j] = (tap[j].valid & 2u) ? *reinterpret_cast<const float2*>(tap[j].p + tap[j].C) : z;
+            t10[j] = (tap[j].valid & 4u) ? *reinterpret_cast<const float2*>(tap[j].p + tap[j].rowstride) : z;
+            t11[j] = (tap[j].valid & 8u) ? *reinterpret_cast<const float2*>(tap[j].p + tap[j].rowstride + tap[j].C) : z;
+          }
+#pragma unroll
+          for (int j = 0; j < PB; ++j) {
+            const int pp = gw * (TQ_M / TQ_GATHER_WARPS) + i0 + j;
+            float2 v;
+            v.x = t00[j].x * tap[j].w00; v.y = t00[j].y * tap[j].w00;          // same accumulation order as the CUDA-core kernel
+            v.x += t01[j].x * tap[j].w01; v.y += t01[j].y * tap[j].w01;
+            v.x += t10[j].x * tap[j].w10; v.y += t10[j].y * tap[j].w10;
+            v.x += t11[j].x * tap[j].w11; v.y += t11[j].y * tap[j].w11;
+            if (!sampled) v = direct[j];
+            __half h0, l0, h1, l1;
+            tq_split(v.x, h0, l0, sat); tq_split(v.y, h1, l1, sat);
+            const uint32_t off = tq_sw_off(pp, k);
+            *reinterpret_cast<__half2*>(dst + off) = __halves2half2(h0, h1);
+            *reinterpret_cast<__half2*>(dst + TQ_PLANE + off) = __halves2half2(l0, l1);
+          }
         }
         tq_fence_async();                                 // generic-proxy writes -> visible to the tensor core (async proxy)
         __syncwarp();
@@ -310,7 +342,10 @@ query_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_c
         const float* b2 = b1 + 128 + 128 * 128;
         const float* b3 = b2 + 128 + 128 * 128;
         const float* W4 = b3 + 128;
-        const float* b4 = W4 + 128 * 16;
+        asm volatile("bar.sync 2, 128;" ::: "memory");      // previous head's last layer has finished reading s_w4
+        for (int i = threadIdx.x; i < (TQ_H * 16 + 16) / 4; i += 128)
+          reinterpret_cast<float4*>(s_w4)[i] = __ldg(reinterpret_cast<const float4*>(W4) + i);     // W4 and b4 are contiguous in the pack
+        asm volatile("bar.sync 2, 128;" ::: "memory");
         for (int layer = 0; layer < 3; ++layer) {
           if (layer > 0) { tq_mbar_wait(tq_smem_u32(&acc_full), (uint32_t)iacc & 1u); ++iacc; tq_fence_after(); }
           const float* bias = layer == 0 ? b1 : layer == 1 ? b2 : b3;
@@ -340,9 +375,12 @@ query_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_c
               // last layer on the CUDA cores: out[c] += h3[k] * W4[k][c]
 #pragma unroll 4
               for (int i = 0; i < 32; ++i) {
-                const float* wr = W4 + (ch * 32 + i) * 16;
-#pragma unroll
-                for (int c = 0; c < 14; ++c) o[c] = fmaf(v[i], __ldg(wr + c), o[c]);
+                const float4* wr = reinterpret_cast<const float4*>(s_w4 + (ch * 32 + i) * 16);
+                const float4 w0 = wr[0], w1 = wr[1], w2 = wr[2], w3 = wr[3];
+                o[0] = fmaf(v[i], w0.x, o[0]); o[1] = fmaf(v[i], w0.y, o[1]); o[2] = fmaf(v[i], w0.z, o[2]); o[3] = fmaf(v[i], w0.w, o[3]);
+                o[4] = fmaf(v[i], w1.x, o[4]); o[5] = fmaf(v[i], w1.y, o[5]); o[6] = fmaf(v[i], w1.z, o[6]); o[7] = fmaf(v[i], w1.w, o[7]);
+                o[8] = fmaf(v[i], w2.x, o[8]); o[9] = fmaf(v[i], w2.y, o[9]); o[10] = fmaf(v[i], w2.z, o[10]); o[11] = fmaf(v[i], w2.w, o[11]);
+                o[12] = fmaf(v[i], w3.x, o[12]); o[13] = fmaf(v[i], w3.y, o[13]);
               }
             }
           }
@@ -353,7 +391,7 @@ query_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_c
             if (lane == 0) tq_mbar_arrive(tq_smem_u32(&act_full));
           } else if (n < N) {
             for (int c = 0; c < head_nout[h]; ++c) {
-              float a = o[c] + __ldg(b4 + c);
+              float a = o[c] + s_w4[TQ_H * 16 + c];
               if (h == 4) a = 1.f / (1.f + expf(-a));
               if (h == 0 && !s_in_img[r]) a = cam.out_dist;
               out[((size_t)b * 29 + head_off[h] + c) * N + n] = a;
