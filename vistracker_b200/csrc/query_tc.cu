@@ -13,8 +13,8 @@
 //               UMMA K-major 128-byte-swizzled layout; the last layer (128 -> <=14 outputs) runs on the CUDA cores from registers
 //   warp  4     TMA producer: weight tiles [128 out x 64 in] (hi and lo planes) through a 2-slot ring
 //   warp  5     MMA issuer (one thread)
-//   warps 6-13  gather: projections once, then per 64-feature chunk 4 bilinear taps per point from the NHWC maps, split, and
-//               store straight into the swizzled A-operand slot (2-slot ring)
+//   warps 6-13  gather: projections once, then per 64-feature chunk 4 bilinear taps per point from the NHWC maps (half a warp per
+//               point, 16-byte loads, four point pairs in flight), split, and store straight into the swizzled A-operand slot
 // Feature order for this kernel (10 chunks of 64, every chunk maps to whole channel runs of one or two maps):
 //   [ im_feat 4x64 | tmpx 64 | tri_feat right 64 | back 64 | top 64 | tri_tmpx right 32, back 32 | tri_tmpx top 32, x, y, z-2.2, 0... ]
 #include <cuda.h>
@@ -201,17 +201,18 @@ query_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_c
         const int slot = it % TQ_NF;
         tq_mbar_wait(tq_smem_u32(&feat_empty[slot]), ((uint32_t)(it / TQ_NF) & 1u) ^ 1u);
         uint8_t* dst = feat_ptr + slot * TQ_SLOT;
-        const int k = 2 * lane;                           // this lane produces features k, k+1 of the chunk
-        constexpr int PB = 4;                             // points in flight per warp
-        for (int i0 = 0; i0 < TQ_M / TQ_GATHER_WARPS; i0 += PB) {
+        // half a warp per point: lane -> (point of the pair, 4 consecutive features k..k+3 of the chunk), 16-byte tap loads
+        const int sub = lane >> 4, k = (lane & 15) * 4;
+        constexpr int PB = 4;                             // point PAIRS in flight per warp
+        for (int i0 = 0; i0 < TQ_M / TQ_GATHER_WARPS; i0 += 2 * PB) {
           TqTap tap[PB];
-          float2 direct[PB];
+          float4 direct[PB];
           bool sampled = true;
 #pragma unroll
           for (int j = 0; j < PB; ++j) {
-            const int pp = gw * (TQ_M / TQ_GATHER_WARPS) + i0 + j;
+            const int pp = gw * (TQ_M / TQ_GATHER_WARPS) + i0 + 2 * j + sub;
             const TqProj q = s_proj[pp];
-            direct[j] = make_float2(0.f, 0.f);
+            direct[j] = make_float4(0.f, 0.f, 0.f, 0.f);
             if (c < 4) {
               tap[j] = tq_tap_setup(m.im_feat + (size_t)b * m.Hf * m.Wf * 256, m.Hf, m.Wf, 256, c * 64 + k, q.nx, q.ny);
             } else if (c == 4) {
@@ -221,41 +222,43 @@ query_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_c
               const float u = view == 0 ? q.tu0 : view == 1 ? q.tu1 : q.tu2, w = view == 0 ? q.tv0 : view == 1 ? q.tv1 : q.tv2;
               tap[j] = tq_tap_setup(m.tri_feat + ((size_t)view * B + b) * m.Hf * m.Wf * 64, m.Hf, m.Wf, 64, k, u, w);
             } else if (c == 8) {
-              const int view = k >> 5;                    // lanes 0-15: right, 16-31: back
+              const int view = k >> 5;                    // features 0-31: right, 32-63: back
               const float u = view == 0 ? q.tu0 : q.tu1, w = view == 0 ? q.tv0 : q.tv1;
               tap[j] = tq_tap_setup(m.tri_tmpx + ((size_t)view * B + b) * m.Ht * m.Wt * 32, m.Ht, m.Wt, 32, k & 31, u, w);
             } else {
               tap[j] = tq_tap_setup(m.tri_tmpx + ((size_t)2 * B + b) * m.Ht * m.Wt * 32, m.Ht, m.Wt, 32, k & 31, q.tu2, q.tv2);
               if (k >= 32) {
                 tap[j].valid = 0u; sampled = false;
-                if (k == 32) direct[j] = make_float2(s_xyz[pp][0], s_xyz[pp][1]);
-                else if (k == 34) direct[j] = make_float2(s_xyz[pp][2], 0.f);
+                if (k == 32) direct[j] = make_float4(s_xyz[pp][0], s_xyz[pp][1], s_xyz[pp][2], 0.f);
               }
             }
           }
-          float2 t00[PB], t01[PB], t10[PB], t11[PB];
+          float4 t00[PB], t01[PB], t10[PB], t11[PB];
 #pragma unroll
           for (int j = 0; j < PB; ++j) {                  // all loads first
-            const float2 z = make_float2(0.f, 0.f);
-            t00[j] = (tap[j].valid & 1u) ? *reinterpret_cast<const float2*>(tap[j].p) : z;
-            t01[j] = (tap[j].valid & 2u) ? *reinterpret_cast<const float2*>(tap[j].p + tap[j].C) : z;
-            t10[j] = (tap[j].valid & 4u) ? *reinterpret_cast<const float2*>(tap[j].p + tap[j].rowstride) : z;
-            t11[j] = (tap[j].valid & 8u) ? *reinterpret_cast<const float2*>(tap[j].p + tap[j].rowstride + tap[j].C) : z;
+            const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+            t00[j] = (tap[j].valid & 1u) ? ld4(tap[j].p) : z;
+            t01[j] = (tap[j].valid & 2u) ? ld4(tap[j].p + tap[j].C) : z;
+            t10[j] = (tap[j].valid & 4u) ? ld4(tap[j].p + tap[j].rowstride) : z;
+            t11[j] = (tap[j].valid & 8u) ? ld4(tap[j].p + tap[j].rowstride + tap[j].C) : z;
           }
 #pragma unroll
           for (int j = 0; j < PB; ++j) {
-            const int pp = gw * (TQ_M / TQ_GATHER_WARPS) + i0 + j;
-            float2 v;
-            v.x = t00[j].x * tap[j].w00; v.y = t00[j].y * tap[j].w00;          // same accumulation order as the CUDA-core kernel
-            v.x += t01[j].x * tap[j].w01; v.y += t01[j].y * tap[j].w01;
-            v.x += t10[j].x * tap[j].w10; v.y += t10[j].y * tap[j].w10;
-            v.x += t11[j].x * tap[j].w11; v.y += t11[j].y * tap[j].w11;
-            if (!sampled) v = direct[j];
-            __half h0, l0, h1, l1;
-            tq_split(v.x, h0, l0, sat); tq_split(v.y, h1, l1, sat);
+            const int pp = gw * (TQ_M / TQ_GATHER_WARPS) + i0 + 2 * j + sub;
+            float v[4];
+            // same accumulation order as the CUDA-core kernel
+            v[0] = t00[j].x * tap[j].w00; v[1] = t00[j].y * tap[j].w00; v[2] = t00[j].z * tap[j].w00; v[3] = t00[j].w * tap[j].w00;
+            v[0] += t01[j].x * tap[j].w01; v[1] += t01[j].y * tap[j].w01; v[2] += t01[j].z * tap[j].w01; v[3] += t01[j].w * tap[j].w01;
+            v[0] += t10[j].x * tap[j].w10; v[1] += t10[j].y * tap[j].w10; v[2] += t10[j].z * tap[j].w10; v[3] += t10[j].w * tap[j].w10;
+            v[0] += t11[j].x * tap[j].w11; v[1] += t11[j].y * tap[j].w11; v[2] += t11[j].z * tap[j].w11; v[3] += t11[j].w * tap[j].w11;
+            if (!sampled) { v[0] = direct[j].x; v[1] = direct[j].y; v[2] = direct[j].z; v[3] = direct[j].w; }
+            __align__(8) __half hh[4];
+            __align__(8) __half ll[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) tq_split(v[e], hh[e], ll[e], sat);
             const uint32_t off = tq_sw_off(pp, k);
-            *reinterpret_cast<__half2*>(dst + off) = __halves2half2(h0, h1);
-            *reinterpret_cast<__half2*>(dst + TQ_PLANE + off) = __halves2half2(l0, l1);
+            *reinterpret_cast<uint2*>(dst + off) = *reinterpret_cast<const uint2*>(hh);
+            *reinterpret_cast<uint2*>(dst + TQ_PLANE + off) = *reinterpret_cast<const uint2*>(ll);
           }
         }
         tq_fence_async();                                 // generic-proxy writes -> visible to the tensor core (async proxy)
