@@ -79,3 +79,8 @@ def chamfer_distance_ragged(xs: List[torch.Tensor], ys: List[torch.Tensor]) -> t
     dev = xs[0].device
     off = lambda cl: torch.tensor([0] + list(torch.tensor([c.shape[0] for c in cl]).cumsum(0)), dtype=torch.int32, device=dev)
     return _ChamferFn.apply(torch.cat(xs, 0), torch.cat(ys, 0), off(xs), off(ys))
+
+
+def chamfer_distance_packed(x: torch.Tensor, y: torch.Tensor, x_off: torch.Tensor, y_off: torch.Tensor) -> torch.Tensor:
+    """Same operator on already-packed clouds: x [sum n_i, 3], y [sum m_i, 3] with int32 row offsets [N + 1] each."""
+    return _ChamferFn.apply(x, y, x_off, y_off)

@@ -17,7 +17,7 @@ import numpy as np
 import torch
 import torch.nn.functional as F
 
-from .geom import chamfer_distance_ragged, decopose_axis, project_so3
+from .geom import chamfer_distance_packed, chamfer_distance_ragged, decopose_axis, project_so3
 from .sifnet import CHORETriplaneVisibility
 from .smpl import LandmarkRegressor, SMPL_Layer
 
@@ -174,25 +174,45 @@ class ReconFitterTriVisFull:
         loss_dict["otemp"] = F.mse_loss(v1, v2) * weight
         loss_dict["ovtemp"] = F.mse_loss(obj_verts[1:], obj_verts[:-1]) * weight
 
-    def compute_contact_loss(self, df_hum_o, df_obj_h, object, smpl_verts, loss_dict, part_o, cont_thres=0.08):
-        """recon_fit_trivis_full.py:393-457: per frame and body part, pull human contact vertices and object contact points
-        together with a bidirectional Chamfer distance (ragged lists -> one kernel launch)."""
+    def contact_pairs(self, df_hum_o, df_obj_h, part_o, cont_thres=0.08):
+        """The (frame, body part) pairing of recon_fit_trivis_full.py:405-449 as index lists.  The contact masks are frozen after
+        the first joint step (:242-253), so the pairing is computed ONCE per batch and every later step is two gathers + one
+        Chamfer launch (the reference re-runs the Python double loop with GPU->CPU syncs on each of its ~1100 joint steps)."""
         mask_o, mask_h = df_obj_h < cont_thres, df_hum_o < cont_thres
         if part_o.dim() == 3:
             part_o = torch.argmax(part_o, 1)
-        hs, os_ = [], []
-        for hum, obj, mh, mo, po in zip(smpl_verts, object, mask_h, mask_o, part_o):
+        B, Nh, No = mask_h.shape[0], mask_h.shape[1], mask_o.shape[1]
+        dev = mask_h.device
+        hi, oi, hoff, ooff = [], [], [0], [0]
+        mask_h_c, mask_o_c, part_o_c, labels_c = mask_h.cpu(), mask_o.cpu(), part_o.cpu(), self.part_labels.cpu()
+        for b in range(B):
+            mh, mo = mask_h_c[b], mask_o_c[b]
             if int(mh.sum()) == 0 or int(mo.sum()) == 0:
                 continue
-            obj_v, label_o, hum_v, label_h = obj[mo], po[mo], hum[mh], self.part_labels[mh]
-            present = set(label_h.unique().tolist()) & set(label_o.unique().tolist())
+            hv, ov = torch.nonzero(mh)[:, 0], torch.nonzero(mo)[:, 0]
+            lh, lo = labels_c[hv], part_o_c[b][ov]
             for i in range(SMPL_PARTS_NUM):
-                if i not in present:
+                sh, so = hv[lh == i], ov[lo == i]
+                if sh.numel() == 0 or so.numel() == 0:
                     continue
-                hs.append(hum_v[label_h == i]); os_.append(obj_v[label_o == i])
-        if not os_:
+                hi.append(sh + b * Nh); oi.append(so + b * No)
+                hoff.append(hoff[-1] + sh.numel()); ooff.append(ooff[-1] + so.numel())
+        if not hi:
+            return None
+        return (torch.cat(hi).to(dev), torch.cat(oi).to(dev), torch.tensor(hoff, dtype=torch.int32, device=dev),
+                torch.tensor(ooff, dtype=torch.int32, device=dev))
+
+    def compute_contact_loss(self, df_hum_o, df_obj_h, object, smpl_verts, loss_dict, part_o, cont_thres=0.08, pairs="build"):
+        """recon_fit_trivis_full.py:393-457: per frame and body part, pull human contact vertices and object contact points
+        together with a bidirectional Chamfer distance over the ragged (frame, part) clouds -- one kernel launch."""
+        if pairs == "build":
+            pairs = self.contact_pairs(df_hum_o, df_obj_h, part_o, cont_thres)
+        if pairs is None:
             return
-        loss_dict["contact"] = chamfer_distance_ragged(hs, os_)
+        h_idx, o_idx, h_off, o_off = pairs
+        hs = smpl_verts.reshape(-1, 3).index_select(0, h_idx)
+        os_ = object.reshape(-1, 3).index_select(0, o_idx)
+        loss_dict["contact"] = chamfer_distance_packed(hs, os_, h_off, o_off)
 
     def forward_step(self, smpl: SMPLParams, data_dict, obj_R, obj_t, obj_s, phase, noise: Optional[torch.Tensor] = None):
         """recon_fit_trivis_full.py:193-270.  ``noise`` replays the U(0,1) tensor of decopose_axis (parity runs)."""
@@ -223,8 +243,10 @@ class ReconFitterTriVisFull:
                     data_dict["df_obj_h"] = df_obj_h.detach()
                     data_dict["df_hum_o"] = self.model.get_preds()[0][:, 1, :].detach()
                     data_dict["parts_obj"] = part_o.detach()
+                if "contact_pairs" not in data_dict:
+                    data_dict["contact_pairs"] = self.contact_pairs(data_dict["df_hum_o"], data_dict["df_obj_h"], data_dict["parts_obj"])
                 self.compute_contact_loss(data_dict["df_hum_o"], data_dict["df_obj_h"], object, smpl_verts, loss_dict,
-                                          part_o=data_dict["parts_obj"])
+                                          part_o=data_dict["parts_obj"], pairs=data_dict["contact_pairs"])
                 if self.collision_loss:
                     raise NotImplementedError("the BVH collision term is dead on this path (hostname switch) and is not built")
         return loss_dict
