@@ -115,6 +115,13 @@ int vt_query_bwd(const float* points, const float* crop_center, const float* bod
                  int Wt, int c_im, int c_tmpx, int c_tt, int c_tf, const float* cam7, const float* wpack, const float* wpack_bwd,
                  const float* g_out, float* g_points, void* stream);
 
+/* vt_query_bwd restricted to the heads whose bit is set in head_mask (bit 0 df, 1 pca, 2 parts, 3 centers, 4 visibility): heads
+ * with an identically-zero cotangent cost nothing (the fitters differentiate through one or two heads only). */
+int vt_query_bwd_heads(const float* points, const float* crop_center, const float* body_center, int B, int N,
+                       const float* im_feat, const float* tmpx, const float* tri_tmpx, const float* tri_feat, int Hf, int Wf, int Ht,
+                       int Wt, int c_im, int c_tmpx, int c_tt, int c_tf, const float* cam7, const float* wpack, const float* wpack_bwd,
+                       const float* g_out, int head_mask, float* g_points, void* stream);
+
 /* One step of Generator.approx_surface (recon/gen/generator.py:72-104) fused into one launch: predictions at `points`
  * (written to out[B][29][N] when not NULL), d sum(clamp(df[df_idx], max=threshold)) / d points (g_points, optional) and
  * points_out = points - normalize(grad, eps 1e-12) * clamp(df[df_idx], max=threshold). */

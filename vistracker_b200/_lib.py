@@ -60,6 +60,7 @@ SIGNATURES.update({
     "vt_so3_project_bwd": (_i, [_p, _p, _i, _p, _p]),
     "vt_chamfer_fwd": (_i, [_p, _p, _p, _p, _i, _p, _p, _p, _p]),
     "vt_chamfer_bwd": (_i, [_p, _p, _p, _p, _i, _p, _p, _p, _p, _p, _p]),
+    "vt_query_bwd_heads": (_i, [_p, _p, _p, _i, _i, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _i, _p, _p]),
     "vt_query_project_step": (_i, [_p, _p, _p, _i, _i, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _i, _f, _p, _p, _p, _p]),
     "vt_raster_fwd": (_i, [_p, _p, _i, _i, _i, _i, _p, _i, _p, _p, _p, _p, _p]),
     "vt_raster_bwd": (_i, [_p, _p, _i, _i, _i, _i, _p, _i, _p, _p, _p, _p, _p, _p, _p]),

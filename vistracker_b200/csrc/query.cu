@@ -278,7 +278,7 @@ __global__ void __launch_bounds__(256, 1) query_bwd_kernel(const float* __restri
                                                            const float* __restrict__ wpack_bwd,
                                                            const float* __restrict__ g_out /*[B][29][N]*/,
                                                            float* __restrict__ g_points /*[B][N][3]*/,
-                                                           int mode, int df_idx, float threshold,
+                                                           int mode, int df_idx, float threshold, int head_mask,
                                                            float* __restrict__ out /*[B][29][N] or null*/,
                                                            float* __restrict__ points_out /*[B][N][3] (mode 1)*/) {
   // mode 0: generic vector-Jacobian product with the cotangent g_out.
@@ -302,6 +302,7 @@ __global__ void __launch_bounds__(256, 1) query_bwd_kernel(const float* __restri
 
   for (int h = 0; h < Q_NHEAD; ++h) {
     if (mode == 1 && h > 0 && !out) break;            // only the distance head carries gradient in a projection step
+    if (mode == 0 && !((head_mask >> h) & 1)) continue;       // heads whose cotangent is identically zero are skipped
     const HeadW w = head_weights(wpack, h);
     const float* W1b = wpack_bwd + (size_t)h * q_head_stride_bwd();
     const float* W2b = W1b + QH * QKB;
@@ -469,8 +470,27 @@ int vt_query_bwd(const float* points, const float* crop_center, const float* bod
   if (e != cudaSuccess) return cuda_fail(e, "vt_query_bwd smem attr");
   dim3 grid(ceil_div(N, QP), B);
   query_bwd_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(points, crop_center, body_center, B, N, m, cam, wpack, wpack_bwd, g_out, g_points,
-                                                              0, 0, 0.f, nullptr, nullptr);
+                                                              0, 0, 0.f, 31, nullptr, nullptr);
   VT_CHECK_LAUNCH("vt_query_bwd");
+  return 0;
+}
+
+int vt_query_bwd_heads(const float* points, const float* crop_center, const float* body_center, int B, int N,
+                       const float* im_feat, const float* tmpx, const float* tri_tmpx, const float* tri_feat, int Hf, int Wf, int Ht,
+                       int Wt, int c_im, int c_tmpx, int c_tt, int c_tf, const float* cam7, const float* wpack, const float* wpack_bwd,
+                       const float* g_out, int head_mask, float* g_points, void* stream) {
+  if (int rc = check_layout("vt_query_bwd_heads", c_im, c_tmpx, c_tt, c_tf)) return rc;
+  VT_CHECK_ARG(head_mask >= 0 && head_mask < 32, "vt_query_bwd_heads: head mask %d", head_mask);
+  if (B <= 0 || N <= 0) return 0;
+  QueryMaps m{im_feat, tmpx, tri_tmpx, tri_feat, Hf, Wf, Ht, Wt, c_im, c_tmpx, c_tt, c_tf};
+  QueryCam cam{cam7[0], cam7[1], cam7[2], cam7[3], cam7[4], cam7[5], cam7[6]};
+  size_t smem = (size_t)(2 * QK * QLD + 2 * QH * QLD + 2 * QKC * QH + 16 * QLD) * sizeof(float);
+  cudaError_t e = cudaFuncSetAttribute(query_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return cuda_fail(e, "vt_query_bwd_heads smem attr");
+  dim3 grid(ceil_div(N, QP), B);
+  query_bwd_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(points, crop_center, body_center, B, N, m, cam, wpack, wpack_bwd, g_out, g_points,
+                                                              0, 0, 0.f, head_mask, nullptr, nullptr);
+  VT_CHECK_LAUNCH("vt_query_bwd_heads");
   return 0;
 }
 
@@ -489,7 +509,7 @@ int vt_query_project_step(const float* points, const float* crop_center, const f
   if (e != cudaSuccess) return cuda_fail(e, "vt_query_project_step smem attr");
   dim3 grid(ceil_div(N, QP), B);
   query_bwd_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(points, crop_center, body_center, B, N, m, cam, wpack, wpack_bwd, nullptr, g_points,
-                                                              1, df_idx, threshold, out, points_out);
+                                                              1, df_idx, threshold, 31, out, points_out);
   VT_CHECK_LAUNCH("vt_query_project_step");
   return 0;
 }

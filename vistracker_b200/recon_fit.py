@@ -234,8 +234,11 @@ class ReconFitterTriVisFull:
         else:
             loss_dict["object"] = (torch.mean(torch.clamp(df_pred[:, 1, :], max=0.8), -1) * data_dict["occ_ratios"]).mean()
             loss_dict["scale"] = torch.mean((obj_s - self.obj_scale) ** 2)
-            oc = torch.mean(object, 1)
-            loss_dict["ocent"] = (F.mse_loss(oc, obj_center_pred, reduction="none").sum(-1) * data_dict["occ_ratios"]).mean()
+            # weight 0 in get_loss_weights ("no loss anymore"): the value is reported, but building its graph would drag the
+            # centre head through the query backward for an identically-zero gradient
+            with torch.no_grad():
+                oc = torch.mean(object, 1)
+                loss_dict["ocent"] = (F.mse_loss(oc, obj_center_pred, reduction="none").sum(-1) * data_dict["occ_ratios"]).mean()
             if phase == "joint":
                 if "df_obj_h" not in data_dict:      # contact masks are computed once, on the first joint step (:242-253)
                     df_obj_h = df_pred[:, 0, :]

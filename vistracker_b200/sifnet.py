@@ -24,22 +24,35 @@ from .weights import pack_decoders, pack_decoders_bwd, pack_decoders_tc
 N_OUT = 29          # df 2 | pca 9 | parts 14 | centers 3 | visibility 1
 
 
+HEAD_SLICES = ((0, 2), (2, 11), (11, 25), (25, 28), (28, 29))      # df | pca | parts | centers | visibility in the packed output
+
+
 class _QueryFn(torch.autograd.Function):
     """query() is differentiable w.r.t. the points only (network weights are frozen at inference,
-    recon/gen/generator.py:53-54)."""
+    recon/gen/generator.py:53-54).  The five heads are separate outputs so that autograd tells us which ones carry a cotangent:
+    the backward kernel recomputes and back-propagates only those."""
 
     @staticmethod
     def forward(ctx, net: "CHORETriplaneVisibility", points, crop_center, body_center):
         out, xy = net._query_raw(points, crop_center, body_center, want_xy=True)
         ctx.net = net
         ctx.save_for_backward(points, crop_center, body_center)
+        ctx.set_materialize_grads(False)
         ctx.mark_non_differentiable(xy)
-        return out, xy
+        return tuple(out[:, lo:hi] for lo, hi in HEAD_SLICES) + (xy,)
 
     @staticmethod
-    def backward(ctx, g_out, _g_xy):
+    def backward(ctx, *grads):
         points, crop_center, body_center = ctx.saved_tensors
-        g_pts = ctx.net._query_backward(points, crop_center, body_center, g_out)
+        mask = sum(1 << h for h in range(5) if grads[h] is not None)
+        if mask == 0:
+            return None, torch.zeros_like(points), None, None
+        B, N = points.shape[0], points.shape[1]
+        g_out = torch.zeros(B, N_OUT, N, dtype=torch.float32, device=points.device)
+        for h, (lo, hi) in enumerate(HEAD_SLICES):
+            if grads[h] is not None:
+                g_out[:, lo:hi] = grads[h]
+        g_pts = ctx.net._query_backward(points, crop_center, body_center, g_out, head_mask=mask)
         return None, g_pts, None, None
 
 
@@ -202,8 +215,9 @@ class CHORETriplaneVisibility:
             return feat, xy
         return out, xy
 
-    def _query_backward(self, points, crop_center, body_center, g_out):
-        """d(sum g_out * out)/d(points) with the maps of the last filter() call (csrc/query.cu: query_bwd_kernel)."""
+    def _query_backward(self, points, crop_center, body_center, g_out, head_mask: int = 31):
+        """d(sum g_out * out)/d(points) with the maps of the last filter() call (csrc/query.cu: query_bwd_kernel), restricted to
+        the heads in ``head_mask`` (bit h set = head h has a non-zero cotangent)."""
         im_feat, tmpx, tri_tmpx, tri_feat = self._maps
         B, N = points.shape[0], points.shape[1]
         pts = points.detach().to(self.device, torch.float32).contiguous()
@@ -213,10 +227,10 @@ class CHORETriplaneVisibility:
         g_pts = torch.empty(B, N, 3, dtype=torch.float32, device=self.device)
         d = self.dims
         with torch.cuda.device(self.device):
-            _lib.call("vt_query_bwd", _lib.ptr(pts), _lib.ptr(cc), _lib.ptr(bc), B, N, _lib.ptr(im_feat), _lib.ptr(tmpx),
+            _lib.call("vt_query_bwd_heads", _lib.ptr(pts), _lib.ptr(cc), _lib.ptr(bc), B, N, _lib.ptr(im_feat), _lib.ptr(tmpx),
                       _lib.ptr(tri_tmpx), _lib.ptr(tri_feat), im_feat.shape[1], im_feat.shape[2], tmpx.shape[1], tmpx.shape[2],
                       d.rgb.out_ch, d.rgb.stem_ch, d.tri.stem_ch, d.tri.out_ch, self._cam7, _lib.ptr(self._wpack),
-                      _lib.ptr(self._wpack_bwd), _lib.ptr(g), _lib.ptr(g_pts), _lib.stream_ptr())
+                      _lib.ptr(self._wpack_bwd), _lib.ptr(g), int(head_mask), _lib.ptr(g_pts), _lib.stream_ptr())
         return g_pts
 
     def query(self, points, crop_center=None, **kwargs):
@@ -226,12 +240,13 @@ class CHORETriplaneVisibility:
         if crop_center is None or body_center is None:
             raise ValueError("query() needs crop_center and body_center (model/chore_triplane.py:114,130)")
         self.points, self.crop_center = points, crop_center
+        B, N = points.shape[0], points.shape[1]
         if points.requires_grad and torch.is_grad_enabled():
-            out, xy = _QueryFn.apply(self, points, crop_center, body_center)
+            df, pca, parts, centers, vis, xy = _QueryFn.apply(self, points, crop_center, body_center)
         else:
             out, xy = self._query_raw(points, crop_center, body_center, want_xy=True)
-        B, _, N = out.shape
-        df, pca, parts, centers, vis = out[:, 0:2], out[:, 2:11].reshape(B, 3, 3, N), out[:, 11:25], out[:, 25:28], out[:, 28:29]
+            df, pca, parts, centers, vis = (out[:, lo:hi] for lo, hi in HEAD_SLICES)
+        pca = pca.reshape(B, 3, 3, N)
         self.points_xy = xy
         self.preds = (df, pca, parts, centers, vis)
         self.intermediate_preds_list = [self.preds]
