@@ -18,21 +18,28 @@ CASES = [  # ks, cin, cout, n, H, W
     (3, 64, 64, 1, 8, 256),
     (3, 128, 128, 2, 4, 128),
     (1, 128, 256, 3, 16, 16),
+    # more tiles than SMs: the persistent kernel walks 2-5 tiles per CTA (both accumulator sets, phase bits flip twice)
+    (1, 64, 64, 4, 128, 128),
+    (3, 64, 128, 2, 128, 128),
+    (3, 64, 32, 5, 128, 128),
+    (1, 256, 256, 3, 128, 128),
 ]
 
 
-@pytest.fixture(params=["plain", "strip", "pair"])
+@pytest.fixture(params=["persist", "plain", "strip", "pair"])
 def variant(request, monkeypatch):
-    """VT_CONV_STRIP: 0 = plain kernel, 1 = one A strip serves the three dx taps, 2 (default) = strip + two images per CTA sharing the
-    weight tiles.  The strip kernels serve 3x3 convolutions on maps at least 128 wide ('pair' needs an even image count)."""
-    monkeypatch.setenv("VT_CONV_STRIP", {"plain": "0", "strip": "1", "pair": "2"}[request.param])
+    """persist (the default path) = one CTA per SM walking tiles with double-buffered TMEM accumulators and the merged N = 2 BN MMA;
+    plain (VT_CONV_PERSIST=0) = one tile per CTA; VT_CONV_STRIP=1 = one A strip serves the three dx taps, =2 = strip + two images per
+    CTA sharing the weight tiles.  The strip kernels serve 3x3 convolutions on maps at least 128 wide ('pair' needs an even image count)."""
+    monkeypatch.setenv("VT_CONV_STRIP", {"persist": "0", "plain": "0", "strip": "1", "pair": "2"}[request.param])
+    monkeypatch.setenv("VT_CONV_PERSIST", "1" if request.param == "persist" else "0")
     return request.param
 
 
 @pytest.mark.parametrize("ks,cin,cout,n,H,W", CASES)
 def test_conv_mma_matches_fp64(ks, cin, cout, n, H, W, variant):
     from vistracker_b200 import ops
-    if variant != "plain" and not (ks == 3 and W >= 128):
+    if variant in ("strip", "pair") and not (ks == 3 and W >= 128):
         pytest.skip("the strip kernels only serve 3x3 convolutions on maps at least 128 wide")
     if variant == "pair":
         n = 2 * n
@@ -78,12 +85,14 @@ def test_conv_mma_rejects_untileable_shapes():
         ops.conv_mma(planes, 12, 12, 1, torch.zeros(64, 64, 3, 3))
 
 
-def test_conv_mma_dual_output_fuses_the_identity_residual():
+@pytest.mark.parametrize("persist", ["1", "0"])
+def test_conv_mma_dual_output_fuses_the_identity_residual(persist, monkeypatch):
     """vt_conv_mma_dual: `out` keeps the raw conv slice (+ its statistics), `out2 = out + res2` is the ConvBlock output slice."""
+    monkeypatch.setenv("VT_CONV_PERSIST", persist)
     from vistracker_b200 import _lib, ops
     from vistracker_b200.weights import pack_conv
     g = torch.Generator().manual_seed(11)
-    n, H, W, cin, cout = 2, 32, 64, 128, 64
+    n, H, W, cin, cout = 6, 64, 64, 128, 64            # 192 tiles: more than one per CTA on the persistent path
     x = torch.randn(n, cin, H, W, generator=g)
     w = torch.randn(cout, cin, 3, 3, generator=g) * 0.05
     res2 = torch.randn(n, cout, H, W, generator=g)
@@ -100,9 +109,11 @@ def test_conv_mma_dual_output_fuses_the_identity_residual():
     assert rel_err(nchw(out2), ref + res2.double()) < 5e-6 and rel_err(st2.cpu(), chan_stats(ref + res2.double())) < 1e-5
 
 
-def test_encoder_plan_with_fused_residual_matches_oracle(monkeypatch):
-    """VT_FUSE_RESIDUAL=1 routes equal-width ConvBlocks through the dual-output epilogue; results must not change."""
-    monkeypatch.setenv("VT_FUSE_RESIDUAL", "1")
+@pytest.mark.parametrize("fuse", ["1", "0"])
+def test_encoder_plan_with_and_without_fused_residual_matches_oracle(fuse, monkeypatch):
+    """VT_FUSE_RESIDUAL=1 (default) routes equal-width ConvBlocks through the dual-output epilogue, =0 through vt_add; results must
+    not change."""
+    monkeypatch.setenv("VT_FUSE_RESIDUAL", fuse)
     from oracle import sifnet_ref as R
     from vistracker_b200 import CHORETriplaneVisibility, default_options, resolve_dims
     from vistracker_b200.synth import synthetic_frames, synthetic_state_dict
@@ -110,7 +121,7 @@ def test_encoder_plan_with_fused_residual_matches_oracle(monkeypatch):
     sd = synthetic_state_dict(dims, seed=0)
     net = CHORETriplaneVisibility(default_options(), device="cuda:0").eval()
     net.load_state_dict(sd)
-    assert net._rgb.fuse_residual
+    assert net._rgb.fuse_residual == (fuse == "1")
     images, *_ = synthetic_frames(1, size=512, seed=77, n_points=4)
     net.filter(images.cuda())
     with torch.no_grad():

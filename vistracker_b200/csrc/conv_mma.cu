@@ -31,7 +31,7 @@ constexpr int MM_THREADS = 192;
 
 struct ConvMmaParams {
   int H, W, pad, ks, kchunks;   // kchunks = Cin_pad / 64
-  int bw, bh, tiles_x;
+  int bw, bh, tiles_x, bw_shift;   // bw is a power of two: pixel r of a tile sits at (y0 + (r >> bw_shift), x0 + (r & (bw-1)))
   int cout_total;               // rows per tap in the packed weight planes
   const float* bias; const float* res; int ldr;
   float* out; int ldo;
@@ -64,6 +64,9 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
     if (clock64() - t0 > 4000000000LL) { printf("vt conv_mma: mbarrier timeout (block %d,%d,%d thread %d)\n", blockIdx.x, blockIdx.y, blockIdx.z, threadIdx.x); __trap(); }
   }
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
   asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
@@ -308,6 +311,304 @@ conv_mma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
   }
 }
 
+// ------------------------------------------------------------------------------------------------ persistent variant (default)
+// One CTA per SM walks a contiguous range of tiles (pixel tiles of an image in raster order, then the next Cout tile, then the next
+// image), so halo rows are re-read from L2 and consecutive tiles share (image, Cout tile): the per-channel statistics are kept in
+// shared memory and flushed to the fp64 slots only when that pair changes -- ~10x fewer same-address L2 atomics.  Two TMEM accumulator sets (2 x [acc0 | acc1] = 4*BN columns) let the epilogue warps drain tile i while the MMA warp
+// already accumulates tile i+1, and the TMA ring runs ahead across tile boundaries; TMEM allocation, barrier init and tensor-map
+// prefetch are paid once per CTA instead of once per tile.
+// The three MMAs of the fp16x2 scheme are issued as two: the weight planes B_hi | B_lo are adjacent in the stage and acc0 | acc1 are
+// adjacent in TMEM, so   [acc0 | acc1] += A_hi * [B_hi | B_lo]   is ONE N = 2*BN instruction, followed by   acc1 += A_lo * B_hi.
+// Same products, same accumulation order, but A_hi is read from shared memory once instead of twice (24 -> 20 KB per K-step at
+// BN = 128, 18 -> 14 KB at BN = 64: the shared-memory port is what bounds the N <= 64 tiles).
+// The epilogue stages one 32-row x 32-channel block per warp in a private 4.5 KB buffer, so every global access is a whole 128-byte
+// pixel-channel run and no tile-sized staging buffer has to be carved out of the pipeline.
+template <int BN>
+struct PersistCfg {
+  static constexpr int STAGES = BN == 128 ? 3 : (BN == 64 ? 4 : 5);
+  static constexpr int A_BYTES = MM_M * MM_KC * 2;
+  static constexpr int B_BYTES = BN * MM_KC * 2;
+  static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
+  static constexpr int EPI_LD = 36;                                  // floats per staged row: 32 + 4 keeps float4 rows conflict-free
+  static constexpr int EPI_BYTES = 4 * 32 * EPI_LD * 4;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 1024;
+  static constexpr int TMEM_COLS = 4 * BN;
+  static constexpr uint32_t IDESC_WIDE = (1u << 4) | ((uint32_t)(2 * BN >> 3) << 17) | ((uint32_t)(MM_M >> 4) << 24);
+  static constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(MM_M >> 4) << 24);
+  static_assert(SMEM_BYTES <= 227 * 1024 && TMEM_COLS <= 512, "persistent configuration exceeds the SM");
+};
+
+struct TileCoord { int img, n0, y0, x0; };
+// tiles [first, last) of CTA b out of g: balanced contiguous split
+__device__ __forceinline__ void tile_range(int total, int& first, int& last) {
+  const int base = total / (int)gridDim.x, rem = total % (int)gridDim.x, b = (int)blockIdx.x;
+  first = b * base + min(b, rem);
+  last = first + base + (b < rem ? 1 : 0);
+}
+__device__ __forceinline__ TileCoord decode_tile(const ConvMmaParams& p, int t, int n_tiles_n, int tiles_per_img, int BN) {
+  TileCoord c;                                   // order: image, then Cout tile, then pixel tile (raster)
+  const int per_img = tiles_per_img * n_tiles_n;
+  c.img = t / per_img;
+  const int rem = t - c.img * per_img;
+  const int nt = rem / tiles_per_img, tl = rem - nt * tiles_per_img;
+  c.n0 = nt * BN;
+  c.y0 = (tl / p.tiles_x) * p.bh;
+  c.x0 = (tl % p.tiles_x) * p.bw;
+  return c;
+}
+
+__device__ __forceinline__ void tc_ld32_issue(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr) : "memory");
+}
+
+template <int BN>
+__global__ void __launch_bounds__(MM_THREADS, 1)
+conv_mma_persist_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
+                        const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo, const ConvMmaParams p,
+                        int tiles_per_img, int n_tiles_n, int total_tiles) {
+  using Cfg = PersistCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bar_full[Cfg::STAGES], bar_empty[Cfg::STAGES], acc_full[2], acc_empty[2];
+  __shared__ uint32_t s_tmem_base;
+  __shared__ float s_sum[BN], s_sq[BN], s_sum2[BN], s_sq2[BN];
+
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_iter = p.ks * p.ks * p.kchunks;
+
+  if (threadIdx.x < BN) { s_sum[threadIdx.x] = 0.f; s_sq[threadIdx.x] = 0.f; s_sum2[threadIdx.x] = 0.f; s_sq2[threadIdx.x] = 0.f; }
+  if (warp == 5 && lane == 0) {
+    for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(smem_u32(&bar_full[s]), 1); mbar_init(smem_u32(&bar_empty[s]), 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(smem_u32(&acc_full[s]), 1); mbar_init(smem_u32(&acc_empty[s]), 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 4 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_a_hi) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_a_lo) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_b_hi) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_b_lo) : "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem_base)), "r"((uint32_t)Cfg::TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = s_tmem_base;
+  int t_first, t_last;
+  tile_range(total_tiles, t_first, t_last);
+
+  if (warp == 4) {
+    // ------------------------------------------------------------------ TMA producer: the ring runs across tile boundaries
+    if (lane == 0) {
+      uint32_t g = 0;
+      for (int t = t_first; t < t_last; ++t) {
+        const TileCoord c = decode_tile(p, t, n_tiles_n, tiles_per_img, BN);
+        const int row0 = c.img * (p.H + 2 * p.pad) + c.y0;
+        for (int it = 0; it < n_iter; ++it, ++g) {
+          const int s = g % Cfg::STAGES;
+          const uint32_t ph = (g / Cfg::STAGES) & 1u;
+          mbar_wait(smem_u32(&bar_empty[s]), ph ^ 1u);
+          const uint32_t full = smem_u32(&bar_full[s]);
+          mbar_expect_tx(full, Cfg::STAGE_BYTES);
+          const int tap = it / p.kchunks, kc = it % p.kchunks;
+          const int dy = tap / p.ks, dx = tap % p.ks;
+          const uint32_t sa = smem_base + s * Cfg::STAGE_BYTES;
+          tma_load_3d(sa, &tm_a_hi, full, kc * MM_KC, c.x0 + dx, row0 + dy);
+          tma_load_3d(sa + Cfg::A_BYTES, &tm_a_lo, full, kc * MM_KC, c.x0 + dx, row0 + dy);
+          tma_load_2d(sa + 2 * Cfg::A_BYTES, &tm_b_hi, full, kc * MM_KC, tap * p.cout_total + c.n0);
+          tma_load_2d(sa + 2 * Cfg::A_BYTES + Cfg::B_BYTES, &tm_b_lo, full, kc * MM_KC, tap * p.cout_total + c.n0);
+        }
+      }
+    }
+  } else if (warp == 5) {
+    // ------------------------------------------------------------------ MMA issuer (one thread)
+    if (lane == 0) {
+      uint32_t g = 0, i = 0;
+      for (int t = t_first; t < t_last; ++t, ++i) {
+        const uint32_t set = i & 1u;
+        mbar_wait(smem_u32(&acc_empty[set]), ((i >> 1) & 1u) ^ 1u);      // the epilogue has drained this accumulator set
+        tc_fence_after();
+        const uint32_t acc0 = tmem_base + set * 2 * BN, acc1 = acc0 + BN;
+        for (int it = 0; it < n_iter; ++it, ++g) {
+          const int s = g % Cfg::STAGES;
+          const uint32_t ph = (g / Cfg::STAGES) & 1u;
+          mbar_wait(smem_u32(&bar_full[s]), ph);
+          tc_fence_after();
+          const uint32_t sa = smem_base + s * Cfg::STAGE_BYTES;
+          const uint64_t a_hi = make_kmajor_sw128_desc(sa), a_lo = make_kmajor_sw128_desc(sa + Cfg::A_BYTES);
+          const uint64_t b_hi = make_kmajor_sw128_desc(sa + 2 * Cfg::A_BYTES);     // rows [0, BN) = B_hi, rows [BN, 2 BN) = B_lo
+#pragma unroll
+          for (int k = 0; k < MM_KC / 16; ++k) {
+            const uint64_t adv = (uint64_t)(k * 32 >> 4);
+            tc_mma_f16(acc0, a_hi + adv, b_hi + adv, Cfg::IDESC_WIDE, (it | k) != 0);
+            tc_mma_f16(acc1, a_lo + adv, b_hi + adv, Cfg::IDESC, 1u);
+          }
+          tc_commit(smem_u32(&bar_empty[s]));
+        }
+        tc_commit(smem_u32(&acc_full[set]));
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue warps 0-3 (TMEM lanes 32*warp .. +31)
+    float* wstage = reinterpret_cast<float*>(smem_raw + (smem_base - smem_u32(smem_raw)) + Cfg::STAGES * Cfg::STAGE_BYTES) + warp * 32 * Cfg::EPI_LD;
+    const int cl = lane & 7, rsub = lane >> 3;
+    const bool st1 = p.stats != nullptr, st2 = p.out2 != nullptr && p.stats2 != nullptr;
+    constexpr int NCH = BN / 32;
+    // pixel offsets of this lane's 8 rows inside a tile (tile-invariant)
+    int roff[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { const int r = warp * 32 + rsub + 4 * j; roff[j] = (r >> p.bw_shift) * p.W + (r & (p.bw - 1)); }
+    uint32_t i = 0;
+    int stats_img = -1, stats_n0 = 0;
+    auto flush_stats = [&]() {       // block partials (fp32, <= a few thousand values per channel) -> fp64 slots of image stats_img
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (threadIdx.x < BN) {
+        if (st1) {
+          double* st = p.stats + ((size_t)stats_img * p.ld_stats + stats_n0 + threadIdx.x) * 2;
+          atomicAdd(st, (double)s_sum[threadIdx.x]);
+          atomicAdd(st + 1, (double)s_sq[threadIdx.x]);
+          s_sum[threadIdx.x] = 0.f; s_sq[threadIdx.x] = 0.f;
+        }
+        if (st2) {
+          double* st = p.stats2 + ((size_t)stats_img * p.ld_stats2 + stats_n0 + threadIdx.x) * 2;
+          atomicAdd(st, (double)s_sum2[threadIdx.x]);
+          atomicAdd(st + 1, (double)s_sq2[threadIdx.x]);
+          s_sum2[threadIdx.x] = 0.f; s_sq2[threadIdx.x] = 0.f;
+        }
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+    };
+    for (int t = t_first; t < t_last; ++t, ++i) {
+      const TileCoord c = decode_tile(p, t, n_tiles_n, tiles_per_img, BN);
+      if ((st1 || st2) && (c.img != stats_img || c.n0 != stats_n0)) {
+        if (stats_img >= 0) flush_stats();
+        stats_img = c.img; stats_n0 = c.n0;
+      }
+      const size_t pix0 = ((size_t)c.img * p.H + c.y0) * p.W + c.x0;
+      const int cbase = c.n0 + cl * 4;
+      // residual operands are fetched one 32-channel chunk ahead (the first one before the accumulator is even ready): the loads
+      // must not sit between dependent stores, or every row pays a full HBM round trip (out may alias res, so the compiler keeps
+      // the program order)
+      float4 rv[8], rw[8];
+      if (p.res) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) rv[j] = ld4(p.res + (pix0 + roff[j]) * p.ldr + cbase);
+      }
+      if (p.out2) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) rw[j] = ld4(p.res2 + (pix0 + roff[j]) * p.ldr2 + cbase);
+      }
+      const uint32_t set = i & 1u;
+      mbar_wait(smem_u32(&acc_full[set]), (i >> 1) & 1u);
+      tc_fence_after();
+      const uint32_t lane_base = tmem_base + set * 2 * BN + ((uint32_t)(warp * 32) << 16);
+#pragma unroll
+      for (int ch = 0; ch < NCH; ++ch) {
+        {
+          uint32_t v[32], w[32];
+          tc_ld32_issue(lane_base + ch * 32, v);
+          tc_ld32_issue(lane_base + BN + ch * 32, w);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          if (ch == NCH - 1) {                                           // this warp's last TMEM read of the tile: hand the set back
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&acc_empty[set]));
+          }
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            *reinterpret_cast<float4*>(&wstage[lane * Cfg::EPI_LD + j]) =
+                make_float4(fmaf(__uint_as_float(w[j]), kLoInv, __uint_as_float(v[j])), fmaf(__uint_as_float(w[j + 1]), kLoInv, __uint_as_float(v[j + 1])),
+                            fmaf(__uint_as_float(w[j + 2]), kLoInv, __uint_as_float(v[j + 2])), fmaf(__uint_as_float(w[j + 3]), kLoInv, __uint_as_float(v[j + 3])));
+        }
+        __syncwarp();
+        const int cc = ch * 32 + cl * 4;                                 // channel inside the tile
+        float4 bz = make_float4(0, 0, 0, 0);
+        if (p.bias) bz = ld4(p.bias + c.n0 + cc);
+        float4 val[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float4 v = *reinterpret_cast<const float4*>(&wstage[(rsub + 4 * j) * Cfg::EPI_LD + cl * 4]);
+          v.x += bz.x; v.y += bz.y; v.z += bz.z; v.w += bz.w;
+          if (p.res) { v.x += rv[j].x; v.y += rv[j].y; v.z += rv[j].z; v.w += rv[j].w; }
+          val[j] = v;
+        }
+        __syncwarp();                                                    // wstage is rewritten by the next chunk
+        float4 nv[8], nw[8];
+        if (ch + 1 < NCH) {                                              // next chunk's residuals: in flight during this chunk's stores
+          if (p.res) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) nv[j] = ld4(p.res + (pix0 + roff[j]) * p.ldr + cbase + (ch + 1) * 32);
+          }
+          if (p.out2) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) nw[j] = ld4(p.res2 + (pix0 + roff[j]) * p.ldr2 + cbase + (ch + 1) * 32);
+          }
+        }
+        float4 s4 = make_float4(0, 0, 0, 0), q4 = s4, t4 = s4, u4 = s4;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float4 v = val[j];
+          st4(p.out + (pix0 + roff[j]) * p.ldo + c.n0 + cc, v);
+          s4.x += v.x; s4.y += v.y; s4.z += v.z; s4.w += v.w;
+          q4.x += v.x * v.x; q4.y += v.y * v.y; q4.z += v.z * v.z; q4.w += v.w * v.w;
+          if (p.out2) {
+            v.x += rw[j].x; v.y += rw[j].y; v.z += rw[j].z; v.w += rw[j].w;
+            st4(p.out2 + (pix0 + roff[j]) * p.ldo2 + c.n0 + cc, v);
+            t4.x += v.x; t4.y += v.y; t4.z += v.z; t4.w += v.w;
+            u4.x += v.x * v.x; u4.y += v.y * v.y; u4.z += v.z * v.z; u4.w += v.w * v.w;
+          }
+        }
+        if (ch + 1 < NCH) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { rv[j] = nv[j]; rw[j] = nw[j]; }
+        }
+        if (st1) {
+#pragma unroll
+          for (int o = 8; o < 32; o <<= 1) {
+            s4.x += __shfl_xor_sync(0xffffffffu, s4.x, o); s4.y += __shfl_xor_sync(0xffffffffu, s4.y, o);
+            s4.z += __shfl_xor_sync(0xffffffffu, s4.z, o); s4.w += __shfl_xor_sync(0xffffffffu, s4.w, o);
+            q4.x += __shfl_xor_sync(0xffffffffu, q4.x, o); q4.y += __shfl_xor_sync(0xffffffffu, q4.y, o);
+            q4.z += __shfl_xor_sync(0xffffffffu, q4.z, o); q4.w += __shfl_xor_sync(0xffffffffu, q4.w, o);
+          }
+          if (rsub == 0) {
+            atomicAdd(&s_sum[cc + 0], s4.x); atomicAdd(&s_sum[cc + 1], s4.y); atomicAdd(&s_sum[cc + 2], s4.z); atomicAdd(&s_sum[cc + 3], s4.w);
+            atomicAdd(&s_sq[cc + 0], q4.x); atomicAdd(&s_sq[cc + 1], q4.y); atomicAdd(&s_sq[cc + 2], q4.z); atomicAdd(&s_sq[cc + 3], q4.w);
+          }
+        }
+        if (st2) {
+#pragma unroll
+          for (int o = 8; o < 32; o <<= 1) {
+            t4.x += __shfl_xor_sync(0xffffffffu, t4.x, o); t4.y += __shfl_xor_sync(0xffffffffu, t4.y, o);
+            t4.z += __shfl_xor_sync(0xffffffffu, t4.z, o); t4.w += __shfl_xor_sync(0xffffffffu, t4.w, o);
+            u4.x += __shfl_xor_sync(0xffffffffu, u4.x, o); u4.y += __shfl_xor_sync(0xffffffffu, u4.y, o);
+            u4.z += __shfl_xor_sync(0xffffffffu, u4.z, o); u4.w += __shfl_xor_sync(0xffffffffu, u4.w, o);
+          }
+          if (rsub == 0) {
+            atomicAdd(&s_sum2[cc + 0], t4.x); atomicAdd(&s_sum2[cc + 1], t4.y); atomicAdd(&s_sum2[cc + 2], t4.z); atomicAdd(&s_sum2[cc + 3], t4.w);
+            atomicAdd(&s_sq2[cc + 0], u4.x); atomicAdd(&s_sq2[cc + 1], u4.y); atomicAdd(&s_sq2[cc + 2], u4.z); atomicAdd(&s_sq2[cc + 3], u4.w);
+          }
+        }
+      }
+    }
+    if ((st1 || st2) && stats_img >= 0) flush_stats();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)Cfg::TMEM_COLS) : "memory");
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ A-strip variant (3x3, W >= 128)
 // The plain kernel is L2->SMEM bound: it fetches a fresh 128-pixel A tile for each of the 9 taps.  Here one (bw+2)-pixel strip
 // per (dy, K-chunk) serves the three dx taps: tap dx is the same shared-memory strip read through a UMMA descriptor whose start
@@ -487,6 +788,33 @@ static int launch_conv_strip(const CUtensorMap& a_hi, const CUtensorMap& a_lo, c
   return 0;
 }
 
+static int num_sms() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = kNumSMs;
+  }
+  return n;
+}
+
+template <int BN>
+static int launch_conv_persist(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi, const CUtensorMap& b_lo,
+                               const ConvMmaParams& p, dim3 grid, cudaStream_t stream) {
+  using Cfg = PersistCfg<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv_mma_persist_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) return cuda_fail(e, "conv_mma_persist smem attr");
+    attr_set = true;
+  }
+  const int tiles_per_img = (int)grid.x, n_tiles_n = (int)grid.z;
+  const int total = tiles_per_img * (int)grid.y * n_tiles_n;
+  const int ctas = total < num_sms() ? total : num_sms();
+  conv_mma_persist_kernel<BN><<<ctas, MM_THREADS, Cfg::SMEM_BYTES, stream>>>(a_hi, a_lo, b_hi, b_lo, p, tiles_per_img, n_tiles_n, total);
+  VT_CHECK_LAUNCH("vt_conv_mma(persistent)");
+  return 0;
+}
+
 template <int BN>
 static int launch_conv_mma(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi, const CUtensorMap& b_lo,
                            const ConvMmaParams& p, dim3 grid, cudaStream_t stream) {
@@ -555,6 +883,7 @@ int vt_conv_mma_dual(const void* a_hi, const void* a_lo, int n_img, int H, int W
   ConvMmaParams p;
   p.H = H; p.W = W; p.pad = pad; p.ks = ks; p.kchunks = Cin_pad / MM_KC;
   p.bw = bw; p.bh = bh; p.tiles_x = W / bw; p.cout_total = Cout;
+  p.bw_shift = 0; while ((1 << p.bw_shift) < bw) ++p.bw_shift;
   p.bias = bias; p.res = res; p.ldr = ldr; p.out = out; p.ldo = ldo; p.stats = stats; p.ld_stats = ld_stats;
   p.out2 = out2; p.ldo2 = ldo2; p.res2 = res2; p.ldr2 = ldr2; p.stats2 = stats2; p.ld_stats2 = ld_stats2;
   dim3 grid((H / bh) * (W / bw), n_img, Cout / BN);
@@ -566,6 +895,13 @@ int vt_conv_mma_dual(const void* a_hi, const void* a_lo, int n_img, int H, int W
   if (strip) {
     if (BN == 128) return launch_conv_strip<128, 1>(ma_hi, ma_lo, mb_hi, mb_lo, p, grid, s);
     return launch_conv_strip<64, 1>(ma_hi, ma_lo, mb_hi, mb_lo, p, grid, s);
+  }
+  // default: persistent kernel (overlapped epilogue, merged N = 2*BN MMA); VT_CONV_PERSIST=0 selects the one-tile-per-CTA kernel
+  const char* persist_e = getenv("VT_CONV_PERSIST");
+  if (!persist_e || atoi(persist_e) != 0) {
+    if (BN == 128) return launch_conv_persist<128>(ma_hi, ma_lo, mb_hi, mb_lo, p, grid, s);
+    if (BN == 64) return launch_conv_persist<64>(ma_hi, ma_lo, mb_hi, mb_lo, p, grid, s);
+    return launch_conv_persist<32>(ma_hi, ma_lo, mb_hi, mb_lo, p, grid, s);
   }
   if (BN == 128) return launch_conv_mma<128>(ma_hi, ma_lo, mb_hi, mb_lo, p, grid, s);
   if (BN == 64) return launch_conv_mma<64>(ma_hi, ma_lo, mb_hi, mb_lo, p, grid, s);

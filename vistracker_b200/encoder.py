@@ -105,7 +105,7 @@ class HGEncoder:
         self.overflow = torch.zeros(1, dtype=torch.int32, device=device)
         self.arena: Optional[StatsArena] = None
         self.force_ffma = os.environ.get("VT_CONV_ALGO", "") == "ffma"
-        self.fuse_residual = os.environ.get("VT_FUSE_RESIDUAL", "") == "1"
+        self.fuse_residual = os.environ.get("VT_FUSE_RESIDUAL", "1") != "0"
         self.launches = 0
 
     # ------------------------------------------------------------------ primitive launches
@@ -171,8 +171,8 @@ class HGEncoder:
         raw_stats = self.arena.take(n, cout)                # statistics of the raw conv1 / conv2 outputs (bn2 / bn3 inputs)
         if self.fuse_residual and f"{name}.downsample.2" not in self.conv and mma_tileable(H, W) and not self.force_ffma:
             # identity residual, tensor-core path: every conv epilogue also writes its slice of (cat + x) -- no add pass.
-            # Opt-in (VT_FUSE_RESIDUAL=1): measured 3 ms / step SLOWER on B200 than the separate add kernel, because the
-            # one-tile-per-CTA conv does not overlap its epilogue with the next tile's mainloop (profiles/r01e_*).
+            # Default since the persistent conv kernel overlaps its epilogue with the next tile's mainloop (2.2 ms / step faster on
+            # B200; with the one-tile-per-CTA kernel it was 3 ms slower, profiles/r01e_*).  VT_FUSE_RESIDUAL=0 restores vt_add.
             raw = torch.empty(n, H, W, half + quarter, dtype=torch.float32, device=self.dev)
             r1 = Act(raw[..., :half], raw_stats[:, :half])
             r2 = Act(raw[..., half:], raw_stats[:, half:half + quarter])
