@@ -49,6 +49,13 @@ int vt_affine_act(const float* x, int ldx, const float* scale, const float* shif
 int vt_prep_split(const float* x, int ldx, const float* scale, const float* shift, int relu, int n_img, int H, int W, int C,
                   int Cpad, int pad, void* hi, void* lo, int* overflow, void* stream);
 
+/* vt_gn_finalize + vt_prep_split in one launch: the GroupNorm(groups, C) affine (net_util.py:358-362, 376-388: F.relu(bnK(x)) feeding
+ * convK) is derived inside the kernel from the producer-accumulated statistics (same fp64 arithmetic as vt_gn_finalize -> identical
+ * planes), so a normalised conv operand costs one pass and no scale/shift buffers.  C <= 1024. */
+int vt_prep_split_gn(const float* x, int ldx, const double* stats, int ld_stats, const float* gamma, const float* beta, int groups,
+                     long long count_per_channel, float eps, int relu, int n_img, int H, int W, int C, int Cpad, int pad, void* hi,
+                     void* lo, int* overflow, void* stream);
+
 /* conv3x3 (padding 1, net_util.py:213-216) / 1x1 conv on the tcgen05 tensor cores.  a_hi/a_lo from vt_prep_split,
  * w_hi/w_lo: fp16 planes [ks*ks][Cout][Cin_pad].  out[pix][0..Cout) = conv + bias + res[pix][0..Cout); res may alias out.
  * Needs W in {8,16,32,64} or a multiple of 128, and H a multiple of 128/min(W,128). */

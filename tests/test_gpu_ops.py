@@ -120,3 +120,24 @@ def test_prep_split_planes():
     assert rel_err(inner, y) < 2e-6
     _, ovf = ops.prep_split(nhwc(x * 1e5), None, None, False, 0)
     assert int(ovf.item()) > 0
+
+
+@pytest.mark.parametrize("C", [32, 64, 128, 256])
+def test_prep_split_gn_is_bit_identical_to_finalize_then_split(C):
+    """vt_prep_split_gn derives the GroupNorm affine in-kernel; the planes must equal vt_gn_finalize -> vt_prep_split exactly,
+    also when the normalised tensor is a channel slice of a wider one (strided statistics)."""
+    from vistracker_b200 import ops
+    g = torch.Generator().manual_seed(100 + C)
+    n, H, W = 3, 8, 16
+    wide = torch.randn(n, 2 * C, H, W, generator=g) * 2 + 0.3
+    gamma, beta = torch.randn(C, generator=g), torch.randn(C, generator=g)
+    xw = nhwc(wide)
+    x = xw[..., C // 2:C // 2 + C]                                  # channel slice, ld = 2C
+    stats_w = chan_stats(wide).to(dev())
+    stats = stats_w[:, C // 2:C // 2 + C]
+    sc, sh = ops.gn_finalize(stats, gamma.to(dev()), beta.to(dev()), H * W)
+    ref, _ = ops.prep_split(x, sc, sh, True, 1)
+    got, ovf = ops.prep_split_gn(x, stats, gamma.to(dev()), beta.to(dev()), True, 1)
+    torch.cuda.synchronize()
+    assert int(ovf.item()) == 0
+    assert torch.equal(ref.view(torch.int16), got.view(torch.int16))

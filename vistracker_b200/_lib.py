@@ -21,6 +21,7 @@ SIGNATURES = {
     "vt_gn_finalize": (_i, [_p, _i, _p, _p, _i, _i, _i, _ll, _f, _p, _p, _p]),
     "vt_affine_act": (_i, [_p, _i, _p, _p, _i, _i, _i, _i, _p, _i, _p, _i, _p]),
     "vt_prep_split": (_i, [_p, _i, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p]),
+    "vt_prep_split_gn": (_i, [_p, _i, _p, _i, _p, _p, _i, _ll, _f, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p]),
     "vt_conv_mma": (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _p, _p, _i, _p, _p, _i, _p, _i, _p, _i, _p]),
     "vt_conv_mma_dual": (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _p, _p, _i, _p, _p, _i, _p, _i, _p, _i, _p, _i, _p, _i, _p, _i, _p]),
     "vt_conv_ffma": (_i, [_p, _i, _p, _p, _i, _i, _i, _i, _i, _i, _p, _i, _p, _p, _i, _p, _i, _p, _i, _p]),

@@ -508,6 +508,19 @@ conv_mma_persist_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __gri
 #pragma unroll
         for (int j = 0; j < 8; ++j) rw[j] = ld4(p.res2 + (pix0 + roff[j]) * p.ldr2 + cbase);
       }
+      // ... and the NEXT tile's residual lines are pulled into L2 now, a whole mainloop ahead of their use (one lane per 128-byte run)
+      if ((p.res || p.out2) && cl == 0 && t + 1 < t_last) {
+        const TileCoord cn = decode_tile(p, t + 1, n_tiles_n, tiles_per_img, BN);
+        const size_t pixn = ((size_t)cn.img * p.H + cn.y0) * p.W + cn.x0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+#pragma unroll
+          for (int ch = 0; ch < NCH; ++ch) {
+            if (p.res) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.res + (pixn + roff[j]) * p.ldr + cn.n0 + ch * 32));
+            if (p.out2) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.res2 + (pixn + roff[j]) * p.ldr2 + cn.n0 + ch * 32));
+          }
+        }
+      }
       const uint32_t set = i & 1u;
       mbar_wait(smem_u32(&acc_full[set]), (i >> 1) & 1u);
       tc_fence_after();

@@ -9,6 +9,7 @@
 namespace vt {
 
 constexpr int EW_THREADS = 256;
+constexpr int EW_MAX_C = 1024;     // widest tensor vt_prep_split_gn normalises
 
 // Block-level commit of per-thread float4 partial sums.  Thread t owns channel group (t % lanes) where
 // lanes = C/4; threads with equal (t % lanes) are summed through shared memory and one thread per channel
@@ -89,8 +90,10 @@ __global__ void affine_act_kernel(const float* __restrict__ x, int ldx, const fl
 // Operand preparation for the tcgen05 convolution: y = relu?(x*scale+shift) split into fp16 (hi, lo*2^11)
 // and written into a zero-bordered NHWC buffer [n, H+2p, W+2p, Cpad].  The kernel walks the PADDED domain
 // and writes every byte (borders and channel padding as zeros), so recycled buffers need no memset.
-__global__ void prep_split_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ scale,
-                                  const float* __restrict__ shift, int relu, int H, int W, int C, int Cpad, int pad,
+struct GnArgs { const double* stats; int ld_stats; const float* gamma; const float* beta; int groups; double count; float eps; };
+
+__global__ void __launch_bounds__(EW_THREADS, 3) prep_split_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ scale,
+                                  const float* __restrict__ shift, const GnArgs gn, int relu, int H, int W, int C, int Cpad, int pad,
                                   __half* __restrict__ hi, __half* __restrict__ lo, int* __restrict__ overflow) {
   const int img = blockIdx.y, lanes = Cpad / 8, cg = threadIdx.x % lanes, row = threadIdx.x / lanes, rows = EW_THREADS / lanes;
   const int Wp = W + 2 * pad, Hp = H + 2 * pad, HWp = Hp * Wp;
@@ -105,30 +108,66 @@ __global__ void prep_split_kernel(const float* __restrict__ x, int ldx, const fl
     float4 c = ld4(shift + (size_t)img * C + cg * 8), d = ld4(shift + (size_t)img * C + cg * 8 + 4);
     sc[0] = a.x; sc[1] = a.y; sc[2] = a.z; sc[3] = a.w; sc[4] = b.x; sc[5] = b.y; sc[6] = b.z; sc[7] = b.w;
     sh[0] = c.x; sh[1] = c.y; sh[2] = c.z; sh[3] = c.w; sh[4] = d.x; sh[5] = d.y; sh[6] = d.z; sh[7] = d.w;
+  } else if (gn.stats) {
+    // GroupNorm finalisation in place (same fp64 arithmetic and summation order as gn_finalize_kernel), once per CTA: thread t
+    // derives the affine of channel t into shared memory (the statistics are a few KB, always L2 hits; one latency chain per CTA)
+    __shared__ float s_sc[EW_MAX_C], s_sh[EW_MAX_C];
+    const int cpg = C / gn.groups;
+    for (int ch = threadIdx.x; ch < C; ch += EW_THREADS) {
+      const double* st = gn.stats + ((size_t)img * gn.ld_stats + (size_t)(ch / cpg) * cpg) * 2;
+      double s = 0, q = 0;
+      for (int c = 0; c < cpg; ++c) { s += st[2 * c]; q += st[2 * c + 1]; }
+      const double mean = s / gn.count;
+      double var = q / gn.count - mean * mean;
+      if (var < 0) var = 0;
+      const double scd = (1.0 / sqrt(var + (double)gn.eps)) * (double)gn.gamma[ch];
+      s_sc[ch] = (float)scd;
+      s_sh[ch] = (float)((double)gn.beta[ch] - mean * scd);
+    }
+    __syncthreads();
+    if (ch_valid) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { sc[i] = s_sc[cg * 8 + i]; sh[i] = s_sh[cg * 8 + i]; }
+    }
   }
   int sat = 0;
-  for (int p = p0 + row; p < p1; p += rows) {
-    int yy = p / Wp, xx = p % Wp;
-    int y = yy - pad, xq = xx - pad;
-    __align__(16) __half h[8];
-    __align__(16) __half l[8];
-    if (ch_valid && y >= 0 && y < H && xq >= 0 && xq < W) {
-      const float* src = x + ((size_t)img * H * W + (size_t)y * W + xq) * ldx + cg * 8;
-      float4 a = ld4(src), b = ld4(src + 4);
-      float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+  constexpr int U = 4;            // pixels in flight per thread: 4 x 32 B of loads before the first dependent instruction
+  for (int pb = p0 + row; pb < p1; pb += U * rows) {
+    float4 a[U], b[U];
+    bool inside[U];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        float t = fmaf(v[i], sc[i], sh[i]);
-        if (relu) t = fmaxf(t, 0.f);
-        split_f16(t, h[i], l[i], sat);
+    for (int u = 0; u < U; ++u) {
+      const int p = pb + u * rows;
+      const int yy = p / Wp, xx = p - yy * Wp;
+      const int y = yy - pad, xq = xx - pad;
+      inside[u] = p < p1 && ch_valid && y >= 0 && y < H && xq >= 0 && xq < W;
+      if (inside[u]) {
+        const float* src = x + ((size_t)img * H * W + (size_t)y * W + xq) * ldx + cg * 8;
+        a[u] = ld4(src); b[u] = ld4(src + 4);
       }
-    } else {
-#pragma unroll
-      for (int i = 0; i < 8; ++i) { h[i] = __float2half_rn(0.f); l[i] = h[i]; }
     }
-    size_t o = ((size_t)img * HWp + p) * Cpad + cg * 8;
-    *reinterpret_cast<uint4*>(hi + o) = *reinterpret_cast<const uint4*>(h);
-    *reinterpret_cast<uint4*>(lo + o) = *reinterpret_cast<const uint4*>(l);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int p = pb + u * rows;
+      if (p >= p1) break;
+      __align__(16) __half h[8];
+      __align__(16) __half l[8];
+      if (inside[u]) {
+        float v[8] = {a[u].x, a[u].y, a[u].z, a[u].w, b[u].x, b[u].y, b[u].z, b[u].w};
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          float t = fmaf(v[i], sc[i], sh[i]);
+          if (relu) t = fmaxf(t, 0.f);
+          split_f16(t, h[i], l[i], sat);
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { h[i] = __float2half_rn(0.f); l[i] = h[i]; }
+      }
+      size_t o = ((size_t)img * HWp + p) * Cpad + cg * 8;
+      *reinterpret_cast<uint4*>(hi + o) = *reinterpret_cast<const uint4*>(h);
+      *reinterpret_cast<uint4*>(lo + o) = *reinterpret_cast<const uint4*>(l);
+    }
   }
   if (sat) atomicAdd(overflow, 1);
 }
@@ -183,39 +222,73 @@ __device__ __forceinline__ void cubic_coeffs(float t, float (&w)[4]) {
   x = 2.f - t;        w[3] = ((A * x - 5.f * A) * x + 8.f * A) * x - 4.f * A;
 }
 
-__global__ void upsample2x_add_kernel(const float* __restrict__ low, const float* __restrict__ up1, int Hl, int Wl, int C,
-                                      int px_per_cta, float* __restrict__ out, double* __restrict__ stats, int ld_stats) {
+// One thread = one 2x2 block of output pixels x 4 channels: the four outputs read a shared 5x5 source window (25 16-byte loads
+// instead of 4 x 16), the horizontal pass is shared by the two output rows, and every output keeps ATen's arithmetic order
+// (horizontal taps first, then vertical).
+__device__ __forceinline__ float4 sel4(bool c, float4 a, float4 b) { return c ? a : b; }
+
+__global__ void __launch_bounds__(EW_THREADS) upsample2x_add_kernel(const float* __restrict__ low, const float* __restrict__ up1, int Hl, int Wl, int C,
+                                                                     int blk_per_cta, float* __restrict__ out, double* __restrict__ stats, int ld_stats) {
   const int img = blockIdx.y, lanes = C / 4, cg = threadIdx.x % lanes, row = threadIdx.x / lanes, rows = EW_THREADS / lanes;
-  const int Ho = 2 * Hl, Wo = 2 * Wl, HWo = Ho * Wo;
-  const int p0 = blockIdx.x * px_per_cta, p1 = min(p0 + px_per_cta, HWo);
+  const int Ho = 2 * Hl, Wo = 2 * Wl, nblk = Hl * Wl;
+  const int q0 = blockIdx.x * blk_per_cta, q1 = min(q0 + blk_per_cta, nblk);
   const float sy = Ho > 1 ? (float)(Hl - 1) / (float)(Ho - 1) : 0.f;
   const float sx = Wo > 1 ? (float)(Wl - 1) / (float)(Wo - 1) : 0.f;
   float4 s = make_float4(0, 0, 0, 0), q = s;
-  for (int p = p0 + row; p < p1; p += rows) {
-    int yo = p / Wo, xo = p % Wo;
-    float ry = sy * yo, rx = sx * xo;
-    int iy = (int)floorf(ry), ix = (int)floorf(rx);
-    float wy[4], wx[4];
-    cubic_coeffs(ry - iy, wy);
-    cubic_coeffs(rx - ix, wx);
-    float4 acc = make_float4(0, 0, 0, 0);
+  for (int blk = q0 + row; blk < q1; blk += rows) {
+    const int Y = blk / Wl, X = blk % Wl;
+    float wy[2][4], wx[2][4];
+    int iy[2], ix[2];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      int yy = min(max(iy - 1 + j, 0), Hl - 1);
-      float4 r = make_float4(0, 0, 0, 0);
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        int xx = min(max(ix - 1 + i, 0), Wl - 1);
-        float4 v = ld4(low + (((size_t)img * Hl + yy) * Wl + xx) * C + cg * 4);
-        r.x += v.x * wx[i]; r.y += v.y * wx[i]; r.z += v.z * wx[i]; r.w += v.w * wx[i];
-      }
-      acc.x += r.x * wy[j]; acc.y += r.y * wy[j]; acc.z += r.z * wy[j]; acc.w += r.w * wy[j];
+    for (int a = 0; a < 2; ++a) {
+      const float ry = sy * (float)(2 * Y + a), rx = sx * (float)(2 * X + a);
+      iy[a] = (int)floorf(ry); ix[a] = (int)floorf(rx);
+      cubic_coeffs(ry - iy[a], wy[a]);
+      cubic_coeffs(rx - ix[a], wx[a]);
     }
-    size_t o = ((size_t)img * HWo + p) * C + cg * 4;
-    float4 u = ld4(up1 + o);
-    u.x += acc.x; u.y += acc.y; u.z += acc.z; u.w += acc.w;
-    st4(out + o, u);
-    acc4(s, q, u);
+    const bool dy1 = iy[1] != iy[0], dx1 = ix[1] != ix[0];          // the second row / column of the block starts one source texel later
+    const float* base = low + (size_t)img * Hl * Wl * C + cg * 4;
+    float4 v[5][5];
+#pragma unroll
+    for (int j = 0; j < 5; ++j) {
+      const int yy = min(max(iy[0] - 1 + j, 0), Hl - 1);
+#pragma unroll
+      for (int i = 0; i < 5; ++i) {
+        const int xx = min(max(ix[0] - 1 + i, 0), Wl - 1);
+        v[j][i] = ld4(base + ((size_t)yy * Wl + xx) * C);
+      }
+    }
+    float4 h[5][2];
+#pragma unroll
+    for (int j = 0; j < 5; ++j) {
+#pragma unroll
+      for (int b = 0; b < 2; ++b) {
+        float4 r = make_float4(0, 0, 0, 0);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float4 t = b == 0 ? v[j][i] : sel4(dx1, v[j][i + 1], v[j][i]);
+          r.x += t.x * wx[b][i]; r.y += t.y * wx[b][i]; r.z += t.z * wx[b][i]; r.w += t.w * wx[b][i];
+        }
+        h[j][b] = r;
+      }
+    }
+#pragma unroll
+    for (int a = 0; a < 2; ++a) {
+#pragma unroll
+      for (int b = 0; b < 2; ++b) {
+        float4 acc = make_float4(0, 0, 0, 0);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float4 r = a == 0 ? h[j][b] : sel4(dy1, h[j + 1][b], h[j][b]);
+          acc.x += r.x * wy[a][j]; acc.y += r.y * wy[a][j]; acc.z += r.z * wy[a][j]; acc.w += r.w * wy[a][j];
+        }
+        const size_t o = (((size_t)img * Ho + 2 * Y + a) * Wo + 2 * X + b) * C + cg * 4;
+        float4 u = ld4(up1 + o);
+        u.x += acc.x; u.y += acc.y; u.z += acc.z; u.w += acc.w;
+        st4(out + o, u);
+        acc4(s, q, u);
+      }
+    }
   }
   if (stats) commit_stats4(s, q, lanes, lanes, stats + (size_t)img * ld_stats * 2);
 }
@@ -261,9 +334,27 @@ int vt_prep_split(const float* x, int ldx, const float* scale, const float* shif
   int HWp = (H + 2 * pad) * (W + 2 * pad);
   int px = pick_px_per_cta(HWp, n_img, Cpad / 8);
   dim3 grid(ceil_div(HWp, px), n_img);
-  prep_split_kernel<<<grid, EW_THREADS, 0, (cudaStream_t)stream>>>(x, ldx, scale, shift, relu, H, W, C, Cpad, pad,
+  GnArgs gn{nullptr, 0, nullptr, nullptr, 1, 1.0, 0.f};
+  prep_split_kernel<<<grid, EW_THREADS, 0, (cudaStream_t)stream>>>(x, ldx, scale, shift, gn, relu, H, W, C, Cpad, pad,
                                                                    (__half*)hi, (__half*)lo, overflow);
   VT_CHECK_LAUNCH("vt_prep_split");
+  return 0;
+}
+
+int vt_prep_split_gn(const float* x, int ldx, const double* stats, int ld_stats, const float* gamma, const float* beta, int groups,
+                     long long count_per_channel, float eps, int relu, int n_img, int H, int W, int C, int Cpad, int pad, void* hi,
+                     void* lo, int* overflow, void* stream) {
+  VT_CHECK_ARG(C % 8 == 0 && Cpad % 8 == 0 && Cpad >= C && EW_THREADS % (Cpad / 8) == 0, "vt_prep_split_gn: unsupported C=%d Cpad=%d", C, Cpad);
+  VT_CHECK_ARG(stats && gamma && beta && groups > 0 && C % groups == 0, "vt_prep_split_gn: C=%d not divisible by groups=%d", C, groups);
+  const int cpg = C / groups;
+  VT_CHECK_ARG(C <= EW_MAX_C, "vt_prep_split_gn: C=%d exceeds %d", C, EW_MAX_C);
+  int HWp = (H + 2 * pad) * (W + 2 * pad);
+  int px = pick_px_per_cta(HWp, n_img, Cpad / 8);
+  dim3 grid(ceil_div(HWp, px), n_img);
+  GnArgs gn{stats, ld_stats, gamma, beta, groups, (double)count_per_channel * cpg, eps};
+  prep_split_kernel<<<grid, EW_THREADS, 0, (cudaStream_t)stream>>>(x, ldx, nullptr, nullptr, gn, relu, H, W, C, Cpad, pad,
+                                                                   (__half*)hi, (__half*)lo, overflow);
+  VT_CHECK_LAUNCH("vt_prep_split_gn");
   return 0;
 }
 
@@ -290,10 +381,12 @@ int vt_avgpool2(const float* x, int n_img, int H, int W, int C, float* out, doub
 int vt_upsample2x_add(const float* low, const float* up1, int n_img, int Hl, int Wl, int C, float* out, double* stats,
                       int ld_stats, void* stream) {
   VT_CHECK_ARG(C % 4 == 0 && EW_THREADS % (C / 4) == 0, "vt_upsample2x_add: unsupported C=%d", C);
-  int HWo = 4 * Hl * Wl;
-  int px = pick_px_per_cta(HWo, n_img, C / 4);
-  dim3 grid(ceil_div(HWo, px), n_img);
-  upsample2x_add_kernel<<<grid, EW_THREADS, 0, (cudaStream_t)stream>>>(low, up1, Hl, Wl, C, px, out, stats, ld_stats);
+  int nblk = Hl * Wl;                                        // 2x2 output blocks
+  int rows = EW_THREADS / (C / 4);
+  int per = rows;                                            // one block per thread: 25 independent loads each already fill the pipes
+  while ((long)ceil_div(nblk, per) * n_img > 148L * 16 && per < 8 * rows) per += rows;
+  dim3 grid(ceil_div(nblk, per), n_img);
+  upsample2x_add_kernel<<<grid, EW_THREADS, 0, (cudaStream_t)stream>>>(low, up1, Hl, Wl, C, per, out, stats, ld_stats);
   VT_CHECK_LAUNCH("vt_upsample2x_add");
   return 0;
 }

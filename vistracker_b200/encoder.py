@@ -48,11 +48,13 @@ class Act:
 
 
 class Operand:
-    """Input of a convolution: x (raw), optional GroupNorm affine, ReLU flag.  The fp16 planes for the tensor-core
-    path are prepared once and shared by every conv that reads the same normalised tensor (e.g. l{i} and bl{i})."""
+    """Input of a convolution: x (raw), optional GroupNorm (the name of its affine parameters; statistics come with the Act), ReLU
+    flag.  The fp16 planes for the tensor-core path are prepared once and shared by every conv that reads the same normalised
+    tensor (e.g. l{i} and bl{i}); the per-(image, channel) scale/shift buffers only exist if a CUDA-core kernel asks for them."""
 
-    def __init__(self, act: Act, scale=None, shift=None, relu=False):
-        self.act, self.scale, self.shift, self.relu = act, scale, shift, relu
+    def __init__(self, act: Act, bn: Optional[str] = None, relu=False):
+        self.act, self.bn, self.relu = act, bn, relu
+        self.scale = self.shift = None
         self.planes = {}
 
 
@@ -114,13 +116,21 @@ class HGEncoder:
 
     def _gn(self, act: Act, bn: str) -> Operand:
         """GroupNorm(32, C) of `act` with affine `bn` + ReLU, as a conv operand (not materialised)."""
-        n, C = act.n, act.C
-        ss = torch.empty(2, n, C, dtype=torch.float32, device=self.dev)
-        sp, ld = self._st(act.stats)
-        _lib.call("vt_gn_finalize", sp, ld, _lib.ptr(self.vec[bn + ".weight"]), _lib.ptr(self.vec[bn + ".bias"]), n, C, GROUPS,
-                  act.H * act.W, GN_EPS, _lib.ptr(ss[0]), _lib.ptr(ss[1]), _lib.stream_ptr())
-        self.launches += 1
-        return Operand(act, ss[0], ss[1], True)
+        return Operand(act, bn, True)
+
+    def _affine(self, op: Operand):
+        """scale/shift buffers of a normalised operand (vt_gn_finalize) for the CUDA-core kernels; the tensor-core path derives the
+        affine inside vt_prep_split_gn instead."""
+        if op.bn is not None and op.scale is None:
+            act = op.act
+            n, C = act.n, act.C
+            ss = torch.empty(2, n, C, dtype=torch.float32, device=self.dev)
+            sp, ld = self._st(act.stats)
+            _lib.call("vt_gn_finalize", sp, ld, _lib.ptr(self.vec[op.bn + ".weight"]), _lib.ptr(self.vec[op.bn + ".bias"]), n, C, GROUPS,
+                      act.H * act.W, GN_EPS, _lib.ptr(ss[0]), _lib.ptr(ss[1]), _lib.stream_ptr())
+            self.launches += 1
+            op.scale, op.shift = ss[0], ss[1]
+        return op.scale, op.shift
 
     def _conv(self, op: Operand, name: str, out: Act, bias: Optional[str] = None, res: Optional[Act] = None, stats=None,
               out2: Optional[Act] = None, res2: Optional[Act] = None):
@@ -138,8 +148,15 @@ class HGEncoder:
             if pad not in op.planes:
                 cpad = pk["cin_pad"]
                 planes = torch.empty(2, n, H + 2 * pad, W + 2 * pad, cpad, dtype=torch.float16, device=self.dev)
-                _lib.call("vt_prep_split", _lib.ptr(a.t), a.ld, _lib.ptr(op.scale), _lib.ptr(op.shift), int(op.relu), n, H, W,
-                          a.C, cpad, pad, _lib.ptr(planes[0]), _lib.ptr(planes[1]), _lib.ptr(self.overflow), _lib.stream_ptr())
+                if op.bn is not None:
+                    sp_in, ld_in = self._st(a.stats)
+                    _lib.call("vt_prep_split_gn", _lib.ptr(a.t), a.ld, sp_in, ld_in, _lib.ptr(self.vec[op.bn + ".weight"]),
+                              _lib.ptr(self.vec[op.bn + ".bias"]), GROUPS, H * W, GN_EPS, int(op.relu), n, H, W, a.C, cpad, pad,
+                              _lib.ptr(planes[0]), _lib.ptr(planes[1]), _lib.ptr(self.overflow), _lib.stream_ptr())
+                else:
+                    sc, sh = self._affine(op)
+                    _lib.call("vt_prep_split", _lib.ptr(a.t), a.ld, _lib.ptr(sc), _lib.ptr(sh), int(op.relu), n, H, W,
+                              a.C, cpad, pad, _lib.ptr(planes[0]), _lib.ptr(planes[1]), _lib.ptr(self.overflow), _lib.stream_ptr())
                 self.launches += 1
                 op.planes[pad] = planes
             planes = op.planes[pad]
@@ -154,7 +171,8 @@ class HGEncoder:
                           _lib.ptr(out2.t), out2.ld, _lib.ptr(res2.t), res2.ld, sp2, sld2, _lib.stream_ptr())
         else:
             assert out2 is None, "the fused second output exists on the tensor-core path only"
-            _lib.call("vt_conv_ffma", _lib.ptr(a.t), a.ld, _lib.ptr(op.scale), _lib.ptr(op.shift), int(op.relu), n, H, W, a.C,
+            sc, sh = self._affine(op)
+            _lib.call("vt_conv_ffma", _lib.ptr(a.t), a.ld, _lib.ptr(sc), _lib.ptr(sh), int(op.relu), n, H, W, a.C,
                       ks, _lib.ptr(pk["ffma"]), pk["cout"], b, rp, rld, _lib.ptr(out.t), out.ld, sp, sld, _lib.stream_ptr())
         self.launches += 1
 
@@ -238,10 +256,10 @@ class HGEncoder:
         sp, sld = self._st(raw0.stats)
         _lib.call("vt_stem_conv7x7s2", _lib.ptr(images), B, Ctot, H, W, c_off, d.in_ch, n_views, _lib.ptr(self.stem_w),
                   _lib.ptr(self.vec["conv1.bias"]), d.stem_ch, _lib.ptr(raw0.t), sp, sld, _lib.stream_ptr())
-        g = self._gn(raw0, "bn1")
+        g_sc, g_sh = self._affine(self._gn(raw0, "bn1"))
         tmpx = self._new(n, H // 2, W // 2, d.stem_ch)
         sp, sld = self._st(tmpx.stats)
-        _lib.call("vt_affine_act", _lib.ptr(raw0.t), raw0.ld, _lib.ptr(g.scale), _lib.ptr(g.shift), 1, n, raw0.H * raw0.W,
+        _lib.call("vt_affine_act", _lib.ptr(raw0.t), raw0.ld, _lib.ptr(g_sc), _lib.ptr(g_sh), 1, n, raw0.H * raw0.W,
                   d.stem_ch, _lib.ptr(tmpx.t), tmpx.ld, sp, sld, _lib.stream_ptr())
         self.launches += 2
         x = self.pool(self.conv_block(tmpx, "conv2", 128))

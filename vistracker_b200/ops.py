@@ -54,6 +54,17 @@ def prep_split(x, scale, shift, relu, pad, cpad=None):
     return planes, ovf
 
 
+def prep_split_gn(x, stats, gamma, beta, relu, pad, groups=32, eps=1e-5, cpad=None):
+    """GroupNorm finalisation + apply + ReLU + split in one launch (vt_prep_split_gn)."""
+    n, H, W, C = x.shape
+    cpad = cpad or (C + 63) // 64 * 64
+    planes = torch.empty(2, n, H + 2 * pad, W + 2 * pad, cpad, dtype=torch.float16, device=x.device)
+    ovf = torch.zeros(1, dtype=torch.int32, device=x.device)
+    _lib.call("vt_prep_split_gn", P(x), x.stride(2), P(stats), stats.stride(0) // 2, P(gamma), P(beta), groups, H * W, eps, int(relu),
+              n, H, W, C, cpad, pad, P(planes[0]), P(planes[1]), P(ovf), S())
+    return planes, ovf
+
+
 def conv_mma(planes, H, W, pad, weight, bias=None, res=None, out=None, stats=None):
     pk = pack_conv(weight.to(planes.device))
     n = planes.shape[1]

@@ -87,6 +87,8 @@ class CHORETriplaneVisibility:
         self.defer_checks = False
         import os
         self.query_on_cuda_cores = os.environ.get("VT_QUERY", "") == "ffma"      # cross-check switch; default = tensor cores
+        self.filter_streams = int(os.environ.get("VT_FILTER_STREAMS", "1"))   # 2 = encoders on two streams (measured slower: static tile ranges)
+        self._side_stream = None
 
     # ------------------------------------------------------------------ nn.Module-like surface
     def to(self, device):
@@ -142,8 +144,21 @@ class CHORETriplaneVisibility:
             raise RuntimeError("load_state_dict() must be called before filter()")
         images = images.to(self.device, torch.float32).contiguous()
         with torch.cuda.device(self.device):
-            im_feat, tmpx = self._rgb.forward(images, 0, 1)
-            tri_feat, tri_tmpx = self._tri.forward(images, 5, 3)
+            if self.filter_streams > 1:
+                # the RGB encoder (n = B) and the shared triplane encoder (n = 3B) are independent until query(): run them on two
+                # streams so the small-map layers of one fill the SMs the other leaves idle and HBM-bound passes overlap MMA-bound ones
+                main = torch.cuda.current_stream()
+                if self._side_stream is None:
+                    self._side_stream = torch.cuda.Stream(device=self.device)
+                side = self._side_stream
+                side.wait_stream(main)
+                with torch.cuda.stream(side):
+                    im_feat, tmpx = self._rgb.forward(images, 0, 1)
+                tri_feat, tri_tmpx = self._tri.forward(images, 5, 3)
+                main.wait_stream(side)
+            else:
+                im_feat, tmpx = self._rgb.forward(images, 0, 1)
+                tri_feat, tri_tmpx = self._tri.forward(images, 5, 3)
             if not self.defer_checks:
                 self.check()
         self.input_images = images
