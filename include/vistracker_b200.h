@@ -137,6 +137,22 @@ int vt_query_project_step(const float* points, const float* crop_center, const f
                           int Wt, int c_im, int c_tmpx, int c_tt, int c_tf, const float* cam7, const float* wpack, const float* wpack_bwd,
                           int df_idx, float threshold, float* points_out, float* out, float* g_points, void* stream);
 
+/* vt_query_bwd_heads / vt_query_project_step with the decoder MLPs on the tcgen05 tensor cores (csrc/query_bwd_tc.cu): 128 points per
+ * CTA, forward recompute + analytic backward + second tap gather in one launch.  w1/w23 planes as for vt_query_fwd_tc; w23t_hi/lo:
+ * fp16 [2*5*128][128] = W2^T | W3^T, w1t_hi/lo: fp16 [5*640][128] = W1^T in the kernel's feature order
+ * (vistracker_b200/weights.py: pack_decoders_tc_bwd).  g_out[B][29][N], g_points[B][N][3]; *overflow counts fp16 range overflows.
+ * The projection step does not return the predictions (call vt_query_fwd_tc at the same points for those). */
+int vt_query_bwd_tc(const float* points, const float* crop_center, const float* body_center, int B, int N, const float* im_feat,
+                    const float* tmpx, const float* tri_tmpx, const float* tri_feat, int Hf, int Wf, int Ht, int Wt, const float* cam7,
+                    const float* wpack, const void* w1_hi, const void* w1_lo, const void* w23_hi, const void* w23_lo, const void* w23t_hi,
+                    const void* w23t_lo, const void* w1t_hi, const void* w1t_lo, const float* g_out, int head_mask, float* g_points,
+                    int* overflow, void* stream);
+int vt_query_project_step_tc(const float* points, const float* crop_center, const float* body_center, int B, int N, const float* im_feat,
+                             const float* tmpx, const float* tri_tmpx, const float* tri_feat, int Hf, int Wf, int Ht, int Wt,
+                             const float* cam7, const float* wpack, const void* w1_hi, const void* w1_lo, const void* w23_hi,
+                             const void* w23_lo, const void* w23t_hi, const void* w23t_lo, const void* w1t_hi, const void* w1t_lo,
+                             int df_idx, float threshold, float* points_out, float* g_points, int* overflow, void* stream);
+
 /* ---- SMPL-H layer: SMPL_Layer.forward (lib_smpl/smplpytorch/smplpytorch/pytorch/smpl_layer.py:73-176) and its gradient
  *      w.r.t. pose / betas / trans; landmark regressors (lib_smpl/torch_functions.py:52-76, wrapper_pytorch.py:187-203) ---- */
 

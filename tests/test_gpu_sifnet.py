@@ -155,3 +155,51 @@ def test_tensor_core_and_cuda_core_decoders_agree(net):
     assert torch.equal(xy_tc, xy_cc)
     for lo, hi in ((0, 2), (2, 11), (11, 25), (25, 28), (28, 29)):
         assert rel_err(out_tc[:, lo:hi].cpu(), out_cc[:, lo:hi].cpu()) < 2e-5
+
+
+@pytest.mark.parametrize("head_mask,scale", [(31, 1.0), (1, 1.0), (5, 3e-8), (16, 1e3), (10, 1.0)])
+def test_tensor_core_and_cuda_core_backward_agree(net, head_mask, scale):
+    """query_bwd_tc_kernel (tcgen05, default) against query_bwd_kernel (fp32 FFMA): head subsets, N not a multiple of 128 and
+    cotangents as small as a mean over 1e7 elements would make them (the per-point power-of-two renormalisation must keep them
+    out of the fp16 underflow range)."""
+    B, N = 2, 333
+    images, points, crop, body = synthetic_frames(B, size=64, seed=51, n_points=N, jitter=True)
+    net.filter(images.cuda())
+    g = torch.randn(B, 29, N, generator=torch.Generator().manual_seed(head_mask)) * scale
+    for h, (lo, hi) in enumerate(((0, 2), (2, 11), (11, 25), (25, 28), (28, 29))):
+        if not (head_mask >> h) & 1:
+            g[:, lo:hi] = 0
+    args = (points.cuda(), crop.cuda(), body.cuda(), g.cuda())
+    assert not net.query_on_cuda_cores
+    got = net._query_backward(*args, head_mask=head_mask)
+    net.query_on_cuda_cores = True
+    try:
+        ref = net._query_backward(*args, head_mask=head_mask)
+    finally:
+        net.query_on_cuda_cores = False
+    net.check()
+    assert float(ref.abs().max()) > 0
+    assert rel_err(got.cpu(), ref.cpu()) < 2e-5
+
+
+def test_tensor_core_projection_step_matches_cuda_core_step(net):
+    """vt_query_project_step_tc against vt_query_project_step (one Generator.approx_surface step, both distance channels)."""
+    from vistracker_b200.generator import GeneratorTriplaneVis
+    B, N = 2, 500
+    images, points, crop, body = synthetic_frames(B, size=64, seed=61, n_points=N, jitter=True)
+    net.filter(images.cuda())
+    gen = GeneratorTriplaneVis(net, threshold=2.0)
+    qi = {"crop_center": crop.cuda(), "body_center": body.cuda()}
+    for df_idx in (0, 1):
+        new_tc, out_tc = gen._project_step(points.cuda(), qi, df_idx, True)
+        net.query_on_cuda_cores = True
+        try:
+            new_cc, out_cc = gen._project_step(points.cuda(), qi, df_idx, True)
+        finally:
+            net.query_on_cuda_cores = False
+        net.check()
+        assert rel_err(out_tc.cpu(), out_cc.cpu()) < 2e-5
+        # the update direction is normalize(grad): compare where the gradient is not vanishing (flat random-init UDF regions)
+        step_tc, step_cc = (new_tc - points.cuda()).cpu(), (new_cc - points.cuda()).cpu()
+        err = (step_tc - step_cc).abs().max(-1).values / step_cc.abs().max()
+        assert float((err < 1e-3).float().mean()) > 0.97

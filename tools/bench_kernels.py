@@ -61,12 +61,20 @@ ms = timeit(lambda: net._query_raw(pts, cc, bc))
 row("query_fwd_kernel", ms, 8 * 10000, "points", 9856, 1.117e6, "B=8, N=10k; 9 856 B / point, 1.117 MFLOP / point")
 g = torch.randn(8, 29, 10000, device=dev)
 ms = timeit(lambda: net._query_backward(pts, cc, bc, g))
-row("query_bwd_kernel (all heads)", ms, 8 * 10000, "points", 2 * 9728 + 12 + 116 + 12, 3.35e6, "fwd recompute + bwd to points")
+row("query_bwd_tc_kernel (all heads)", ms, 8 * 10000, "points", 2 * 9728 + 12 + 116 + 12, 3.35e6, "fwd recompute + bwd to points; one gather pair per head")
+ms = timeit(lambda: net._query_backward(pts, cc, bc, g, head_mask=5))
+row("query_bwd_tc_kernel (df + parts heads: optimize_smpl)", ms, 8 * 10000, "points", 2 * 9728 + 12 + 116 + 12, 2 * 3.35e6 / 5, "head_mask=5")
+net.query_on_cuda_cores = True
+ms = timeit(lambda: net._query_backward(pts, cc, bc, g))
+row("query_bwd_kernel (fp32 FFMA cross-check, all heads)", ms, 8 * 10000, "points", 2 * 9728 + 12 + 116 + 12, 3.35e6, "")
+ms = timeit(lambda: net._query_backward(pts, cc, bc, g, head_mask=5))
+row("query_bwd_kernel (fp32 FFMA cross-check, df + parts)", ms, 8 * 10000, "points", 2 * 9728 + 12 + 116 + 12, 2 * 3.35e6 / 5, "")
+net.query_on_cuda_cores = False
 from vistracker_b200.generator import GeneratorTriplaneVis  # noqa: E402
 gen = GeneratorTriplaneVis(net)
 qi = {"crop_center": cc, "body_center": bc}
 ms = timeit(lambda: gen._project_step(pts, qi, 0, False))
-row("query_bwd_kernel (projection step, df head only)", ms, 8 * 10000, "points", 2 * 9728 + 24, None, "one approx_surface step")
+row("query_bwd_tc_kernel (projection step, df head only)", ms, 8 * 10000, "points", 2 * 9728 + 24, None, "one approx_surface step")
 ms = timeit(lambda: net.filter(images.to(dev)), iters=5)
 row("filter (2 encoders, whole launch plan)", ms, 8, "frames", None, 613.46e9, "B=8 512x512; conv-only 613.46 GFLOP / frame")
 

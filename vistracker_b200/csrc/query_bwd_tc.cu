@@ -1,0 +1,612 @@
+// SIF-Net point query, gradient w.r.t. the points, with the decoder MLPs on the tcgen05 tensor cores -- the operator behind
+// `df.sum().backward()` in Generator.approx_surface (recon/gen/generator.py:86-98) and behind the df / part / centre losses of the
+// fitters (recon/recon_fit_behave.py:467-513, recon/recon_fit_trivis_full.py:193-270).  Same contract as query_bwd_kernel in
+// query.cu (which stays as the CUDA-core cross-check); the reference builds an autograd graph over 8 grid_sample + ~10 cat + 20
+// Conv1d launches for the same result.
+//
+// One CTA = 128 query points (M of every MMA), one decoder head at a time:
+//   forward   F1  acc  = feat[128 x 640] * W1^T      (10 gathered feature chunks, fp16 hi/lo split, 3 MMAs per K-step)
+//             F2/F3    = relu(.)*W2^T, relu(.)*W3^T  (ReLU masks stay in the epilogue threads' registers: 3 x 128 bits per point)
+//   cotangent g4       = g_out (x sigmoid' for visibility) or d clamp(df, thr) for a projection step; g3 = mask3 . (W4^T g4) on CUDA cores
+//   backward  B3/B2    = g3 * W3, g2 * W2            (transposed weight planes; each vector is renormalised per point by a power of
+//                                                     two before the fp16 split, so tiny loss scalings cannot underflow; the
+//                                                     exponent travels with the point and is re-applied at the end -- the map is linear)
+//             B1  gf   = g1[128 x 128] * W1          (640 feature-gradient columns, five N=128 groups through a 3-slot TMEM ring)
+//   gather-dot         the epilogue drains gf into a shared fp32 staging ring (the idle feature ring), the gather warps re-read the
+//                      four bilinear taps of every feature and contract gf with d(feature)/d(u, v), then with the projection Jacobians.
+// Warp roles (448 threads) as in query_tc.cu: warps 0-3 epilogue (thread = point = TMEM lane), warp 4 TMA weight producer, warp 5
+// MMA issuer, warps 6-13 gather (half a warp per point, 16-byte tap loads, four point pairs in flight).
+#include "query_tc_common.cuh"
+#include "vt_internal.h"
+
+namespace vt {
+
+constexpr int TB_THREADS = 448;
+constexpr int TB_NGF = 3;                                  // TMEM slots of 128 columns for gf, after the 128-column working accumulator
+constexpr int TB_SMEM = 2 * TQ_SLOT /*features | gf staging*/ + TQ_NW * TQ_SLOT /*weights*/ + 2 * TQ_SLOT /*activations*/ + 1024;
+
+struct TbParams {
+  const float* g_out;      // [B][29][N] cotangent (mode 0)
+  float* g_points;         // [B][N][3] (optional in mode 1)
+  float* points_out;       // [B][N][3] (mode 1)
+  int mode, df_idx, head_mask;
+  float threshold;
+};
+
+// tap of feature k (multiple of 4) of chunk c for the point with projections q; `direct` marks the (x, y, z - z0) lane of chunk 9
+__device__ __forceinline__ TqTap tb_chunk_tap(int c, int k, const TqProj& q, const TqMaps& m, int b, int B, int& view, bool& direct) {
+  TqTap t;
+  direct = false;
+  if (c < 4) {
+    view = -1;
+    t = tq_tap_setup(m.im_feat + (size_t)b * m.Hf * m.Wf * 256, m.Hf, m.Wf, 256, c * 64 + k, q.nx, q.ny);
+  } else if (c == 4) {
+    view = -1;
+    t = tq_tap_setup(m.tmpx + (size_t)b * m.Ht * m.Wt * 64, m.Ht, m.Wt, 64, k, q.nx, q.ny);
+  } else if (c < 8) {
+    view = c - 5;
+    const float u = view == 0 ? q.tu0 : view == 1 ? q.tu1 : q.tu2, w = view == 0 ? q.tv0 : view == 1 ? q.tv1 : q.tv2;
+    t = tq_tap_setup(m.tri_feat + ((size_t)view * B + b) * m.Hf * m.Wf * 64, m.Hf, m.Wf, 64, k, u, w);
+  } else if (c == 8) {
+    view = k >> 5;
+    const float u = view == 0 ? q.tu0 : q.tu1, w = view == 0 ? q.tv0 : q.tv1;
+    t = tq_tap_setup(m.tri_tmpx + ((size_t)view * B + b) * m.Ht * m.Wt * 32, m.Ht, m.Wt, 32, k & 31, u, w);
+  } else {
+    view = 2;
+    t = tq_tap_setup(m.tri_tmpx + ((size_t)2 * B + b) * m.Ht * m.Wt * 32, m.Ht, m.Wt, 32, k & 31, q.tu2, q.tv2);
+    if (k >= 32) { t.valid = 0u; direct = (k == 32); view = 3; }
+  }
+  return t;
+}
+
+// power-of-two normalisation of a non-negative maximum: returns e with 2^-e * m in [0.5, 1) (0 for m == 0 / non-finite)
+__device__ __forceinline__ int tb_norm_exp(float m) {
+  if (!(m > 0.f) || !(m < 3.0e38f)) return 0;
+  int e;
+  frexpf(m, &e);
+  return max(e, -100);
+}
+
+__global__ void __launch_bounds__(TB_THREADS, 1)
+query_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_constant__ CUtensorMap tm_w1_lo,
+                    const __grid_constant__ CUtensorMap tm_w23_hi, const __grid_constant__ CUtensorMap tm_w23_lo,
+                    const __grid_constant__ CUtensorMap tm_w23t_hi, const __grid_constant__ CUtensorMap tm_w23t_lo,
+                    const __grid_constant__ CUtensorMap tm_w1t_hi, const __grid_constant__ CUtensorMap tm_w1t_lo,
+                    const float* __restrict__ points, const float* __restrict__ crop_center, const float* __restrict__ body_center,
+                    int B, int N, TqMaps m, TqCam cam, const float* __restrict__ wpack, int wpack_head_stride, TbParams prm,
+                    int* __restrict__ overflow) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t feat_full[2], feat_empty[2], w_full[TQ_NW], w_empty[TQ_NW], acc_full, act_full, gf_full[TB_NGF],
+      gf_empty[TB_NGF], stg_full[2], stg_empty[2];
+  __shared__ uint32_t s_tmem_base;
+  __shared__ TqProj s_proj[TQ_M];
+  __shared__ float s_xyz[TQ_M][4];                          // x, y, z - z0, z
+  __shared__ int s_in_img[TQ_M];
+  __shared__ int s_scale_e[TQ_M];                           // exponent of the per-point renormalisation of the current head
+  __shared__ float s_dfc[TQ_M];                             // clamp(df, max=threshold) (projection step)
+  __shared__ uint32_t s_mask[3][4][TQ_M];                   // ReLU masks of the three hidden layers of the current head (128 bits per point)
+  __shared__ float s_gacc[TQ_M][3];                         // d/d(x, y, z) of every point, summed over chunks and heads
+  __shared__ __align__(16) float s_w4[TQ_H * 16 + 16];
+
+  const uint32_t smem_base = (tq_smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_al = smem_raw + (smem_base - tq_smem_u32(smem_raw));
+  const uint32_t feat_base = smem_base, w_base = smem_base + 2 * TQ_SLOT, act_base = w_base + TQ_NW * TQ_SLOT;
+  uint8_t* feat_ptr = smem_al;                              // also the gf staging ring: slot = fp32 [128 points][64 features]
+  uint8_t* act_ptr = smem_al + 2 * TQ_SLOT + TQ_NW * TQ_SLOT;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.y, n0 = blockIdx.x * TQ_M;
+  const int heads = prm.mode == 1 ? 1 : prm.head_mask;
+
+  if (warp == 5 && lane == 0) {
+    for (int s = 0; s < 2; ++s) {
+      tq_mbar_init(tq_smem_u32(&feat_full[s]), TQ_GATHER_WARPS); tq_mbar_init(tq_smem_u32(&feat_empty[s]), 1);
+      tq_mbar_init(tq_smem_u32(&stg_full[s]), 4); tq_mbar_init(tq_smem_u32(&stg_empty[s]), TQ_GATHER_WARPS);
+    }
+    for (int s = 0; s < TQ_NW; ++s) { tq_mbar_init(tq_smem_u32(&w_full[s]), 1); tq_mbar_init(tq_smem_u32(&w_empty[s]), 1); }
+    for (int s = 0; s < TB_NGF; ++s) { tq_mbar_init(tq_smem_u32(&gf_full[s]), 1); tq_mbar_init(tq_smem_u32(&gf_empty[s]), 4); }
+    tq_mbar_init(tq_smem_u32(&acc_full), 1);
+    tq_mbar_init(tq_smem_u32(&act_full), 4);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 4 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_w1_hi) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_w1_lo) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_w23_hi) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_w23_lo) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_w23t_hi) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_w23t_lo) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_w1t_hi) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_w1t_lo) : "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tq_smem_u32(&s_tmem_base)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  // projections of the tile's points (gather warps, one thread per point) -- same arithmetic as query_fwd_tc_kernel
+  if (warp >= 6 && (threadIdx.x - 6 * 32) < TQ_M) {
+    const int pp = threadIdx.x - 6 * 32, n = n0 + pp;
+    TqProj q; float x = 0.f, y = 0.f, z = 1.f; int in_img = 1;
+    if (n < N) {
+      const float* pt = points + ((size_t)b * N + n) * 3;
+      x = pt[0]; y = pt[1]; z = pt[2];
+      float px = __fadd_rn(__fdiv_rn(__fmul_rn(cam.fx, x), z), cam.cx);
+      float py = __fadd_rn(__fdiv_rn(__fmul_rn(cam.fy, y), z), cam.cy);
+      px = __fadd_rn(__fadd_rn(cam.crop * 0.5f, px), -crop_center[b * 2 + 0]);
+      py = __fadd_rn(__fadd_rn(cam.crop * 0.5f, py), -crop_center[b * 2 + 1]);
+      q.nx = __fadd_rn(__fdiv_rn(__fmul_rn(2.f, px), cam.crop), -1.f);
+      q.ny = __fadd_rn(__fdiv_rn(__fmul_rn(2.f, py), cam.crop), -1.f);
+      in_img = (q.nx >= -1.f && q.nx <= 1.f && q.ny >= -1.f && q.ny <= 1.f) ? 1 : 0;
+      const float cx = __fadd_rn(x, -body_center[b * 3 + 0]), cy = __fadd_rn(y, -body_center[b * 3 + 1]), cz = __fadd_rn(z, -body_center[b * 3 + 2]);
+      q.tu0 = cz; q.tv0 = cy; q.tu1 = -cx; q.tv1 = cy; q.tu2 = cx; q.tv2 = -cz;
+    } else {
+      q.nx = q.ny = q.tu0 = q.tv0 = q.tu1 = q.tv1 = q.tu2 = q.tv2 = 1e30f;       // every tap out of range -> zero features
+    }
+    s_proj[pp] = q; s_xyz[pp][0] = x; s_xyz[pp][1] = y; s_xyz[pp][2] = __fadd_rn(z, -cam.z0); s_xyz[pp][3] = z; s_in_img[pp] = in_img;
+  }
+  tq_fence_before();
+  __syncthreads();
+  tq_fence_after();
+  const uint32_t tmem_base = s_tmem_base;
+
+  if (warp >= 6) {
+    // ================================================================== gather warps
+    const int gw = warp - 6;
+    const int sub = lane >> 4, k = (lane & 15) * 4;
+    constexpr int PB = 4;                                   // point PAIRS in flight per warp
+    constexpr int PW = TQ_M / TQ_GATHER_WARPS;              // 16 points per warp
+    constexpr int PBB = 2;                                  // ... and in the backward contraction (more live registers per point)
+    for (int i = lane; i < PW * 3; i += 32) (&s_gacc[gw * PW][0])[i] = 0.f;      // each warp owns the rows of its 16 points
+    __syncwarp();
+    int sat = 0, it = 0, sc = 0;
+    for (int h = 0; h < 5; ++h) {
+      if (!((heads >> h) & 1)) continue;
+      asm volatile("bar.sync 3, 256;" ::: "memory");       // every gather warp is done reading the previous head's staging slots
+      // ---- forward: 10 feature chunks into the A-operand ring
+      for (int c = 0; c < TQ_NCHUNK; ++c, ++it) {
+        const int slot = it & 1;
+        tq_mbar_wait(tq_smem_u32(&feat_empty[slot]), ((uint32_t)(it >> 1) & 1u) ^ 1u);
+        uint8_t* dst = feat_ptr + slot * TQ_SLOT;
+#pragma unroll
+        for (int i0 = 0; i0 < PW; i0 += 2 * PB) {
+          TqTap tap[PB];
+          bool direct[PB];
+#pragma unroll
+          for (int j = 0; j < PB; ++j) {
+            const int pp = gw * PW + i0 + 2 * j + sub;
+            int view;
+            tap[j] = tb_chunk_tap(c, k, s_proj[pp], m, b, B, view, direct[j]);
+          }
+          float4 t00[PB], t01[PB], t10[PB], t11[PB];
+#pragma unroll
+          for (int j = 0; j < PB; ++j) {
+            const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+            t00[j] = (tap[j].valid & 1u) ? ld4(tap[j].p) : z;
+            t01[j] = (tap[j].valid & 2u) ? ld4(tap[j].p + tap[j].C) : z;
+            t10[j] = (tap[j].valid & 4u) ? ld4(tap[j].p + tap[j].rowstride) : z;
+            t11[j] = (tap[j].valid & 8u) ? ld4(tap[j].p + tap[j].rowstride + tap[j].C) : z;
+          }
+#pragma unroll
+          for (int j = 0; j < PB; ++j) {
+            const int pp = gw * PW + i0 + 2 * j + sub;
+            float v[4];
+            v[0] = t00[j].x * tap[j].w00; v[1] = t00[j].y * tap[j].w00; v[2] = t00[j].z * tap[j].w00; v[3] = t00[j].w * tap[j].w00;
+            v[0] += t01[j].x * tap[j].w01; v[1] += t01[j].y * tap[j].w01; v[2] += t01[j].z * tap[j].w01; v[3] += t01[j].w * tap[j].w01;
+            v[0] += t10[j].x * tap[j].w10; v[1] += t10[j].y * tap[j].w10; v[2] += t10[j].z * tap[j].w10; v[3] += t10[j].w * tap[j].w10;
+            v[0] += t11[j].x * tap[j].w11; v[1] += t11[j].y * tap[j].w11; v[2] += t11[j].z * tap[j].w11; v[3] += t11[j].w * tap[j].w11;
+            if (c == TQ_NCHUNK - 1 && k >= 32) {
+              v[0] = v[1] = v[2] = v[3] = 0.f;
+              if (direct[j]) { v[0] = s_xyz[pp][0]; v[1] = s_xyz[pp][1]; v[2] = s_xyz[pp][2]; }
+            }
+            __align__(8) __half hh[4];
+            __align__(8) __half ll[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) tq_split(v[e], hh[e], ll[e], sat);
+            const uint32_t off = tq_sw_off(pp, k);
+            *reinterpret_cast<uint2*>(dst + off) = *reinterpret_cast<const uint2*>(hh);
+            *reinterpret_cast<uint2*>(dst + TQ_PLANE + off) = *reinterpret_cast<const uint2*>(ll);
+          }
+        }
+        tq_fence_async();
+        __syncwarp();
+        if (lane == 0) tq_mbar_arrive(tq_smem_u32(&feat_full[slot]));
+      }
+      // ---- backward: contract the staged feature gradients with d(feature)/d(u, v) (second gather of the same taps)
+      for (int c = 0; c < TQ_NCHUNK; ++c, ++sc) {
+        const int slot = sc & 1;
+        tq_mbar_wait(tq_smem_u32(&stg_full[slot]), (uint32_t)(sc >> 1) & 1u);
+        const uint8_t* stg = feat_ptr + slot * TQ_SLOT;
+        const bool full_res = (c < 4) || (c >= 5 && c < 8);                // im_feat / tri_feat maps (Hf x Wf); else tmpx-sized maps
+        const float su = 0.5f * (float)((full_res ? m.Wf : m.Wt) - 1), sv = 0.5f * (float)((full_res ? m.Hf : m.Ht) - 1);
+#pragma unroll 1
+        for (int i0 = 0; i0 < PW; i0 += 2 * PBB) {
+          TqTap tap[PBB];
+          bool direct[PBB];
+          int view[PBB];
+          float4 g[PBB];
+#pragma unroll
+          for (int j = 0; j < PBB; ++j) {
+            const int pp = gw * PW + i0 + 2 * j + sub;
+            tap[j] = tb_chunk_tap(c, k, s_proj[pp], m, b, B, view[j], direct[j]);
+            g[j] = *reinterpret_cast<const float4*>(stg + pp * 256 + (((lane & 15) ^ (pp & 15)) << 4));
+          }
+          float4 t00[PBB], t01[PBB], t10[PBB], t11[PBB];
+#pragma unroll
+          for (int j = 0; j < PBB; ++j) {
+            const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+            t00[j] = (tap[j].valid & 1u) ? ld4(tap[j].p) : z;
+            t01[j] = (tap[j].valid & 2u) ? ld4(tap[j].p + tap[j].C) : z;
+            t10[j] = (tap[j].valid & 4u) ? ld4(tap[j].p + tap[j].rowstride) : z;
+            t11[j] = (tap[j].valid & 8u) ? ld4(tap[j].p + tap[j].rowstride + tap[j].C) : z;
+          }
+#pragma unroll
+          for (int j = 0; j < PBB; ++j) {
+            const int pp = gw * PW + i0 + 2 * j + sub;
+            const float scale = ldexpf(1.f, s_scale_e[pp]);
+            const float tx = tap[j].tx, ty = tap[j].ty;
+            float dix = g[j].x * ((t01[j].x - t00[j].x) * (1.f - ty) + (t11[j].x - t10[j].x) * ty) +
+                        g[j].y * ((t01[j].y - t00[j].y) * (1.f - ty) + (t11[j].y - t10[j].y) * ty) +
+                        g[j].z * ((t01[j].z - t00[j].z) * (1.f - ty) + (t11[j].z - t10[j].z) * ty) +
+                        g[j].w * ((t01[j].w - t00[j].w) * (1.f - ty) + (t11[j].w - t10[j].w) * ty);
+            float diy = g[j].x * ((t10[j].x - t00[j].x) * (1.f - tx) + (t11[j].x - t01[j].x) * tx) +
+                        g[j].y * ((t10[j].y - t00[j].y) * (1.f - tx) + (t11[j].y - t01[j].y) * tx) +
+                        g[j].z * ((t10[j].z - t00[j].z) * (1.f - tx) + (t11[j].z - t01[j].z) * tx) +
+                        g[j].w * ((t10[j].w - t00[j].w) * (1.f - tx) + (t11[j].w - t01[j].w) * tx);
+            const float gu = dix * su * scale, gv = diy * sv * scale;
+            float gx = 0.f, gy = 0.f, gz = 0.f;
+            if (view[j] < 0) {           // perspective: nx = 2 (crop/2 + fx x / z + cx - ccx) / crop - 1
+              const float kk = 2.f / cam.crop, x = s_xyz[pp][0], y = s_xyz[pp][1], iz = 1.f / s_xyz[pp][3];
+              gx = gu * kk * cam.fx * iz;
+              gy = gv * kk * cam.fy * iz;
+              gz = -gu * kk * cam.fx * x * iz * iz - gv * kk * cam.fy * y * iz * iz;
+            } else if (view[j] == 0) {   // right: (z, y)
+              gz = gu; gy = gv;
+            } else if (view[j] == 1) {   // back: (-x, y)
+              gx = -gu; gy = gv;
+            } else if (view[j] == 2) {   // top: (x, -z)
+              gx = gu; gz = -gv;
+            } else if (direct[j]) {      // the (x, y, z - z0) inputs themselves
+              gx = g[j].x * scale; gy = g[j].y * scale; gz = g[j].z * scale;
+            }
+#pragma unroll
+            for (int o = 8; o >= 1; o >>= 1) {                           // sum over the 16 lanes (features) of this half-warp
+              gx += __shfl_xor_sync(0xffffffffu, gx, o); gy += __shfl_xor_sync(0xffffffffu, gy, o); gz += __shfl_xor_sync(0xffffffffu, gz, o);
+            }
+            if ((lane & 15) == 0) { s_gacc[pp][0] += gx; s_gacc[pp][1] += gy; s_gacc[pp][2] += gz; }
+          }
+        }
+        __syncwarp();
+        if (lane == 0) tq_mbar_arrive(tq_smem_u32(&stg_empty[slot]));
+      }
+    }
+    // ---- write the point gradients / the projected points (one lane per point)
+    __syncwarp();
+    if (lane < PW) {
+      const int pp = gw * PW + lane, n = n0 + pp;
+      if (n < N) {
+        const float gx = s_gacc[pp][0], gy = s_gacc[pp][1], gz = s_gacc[pp][2];
+        if (prm.g_points) { float* gp = prm.g_points + ((size_t)b * N + n) * 3; gp[0] = gx; gp[1] = gy; gp[2] = gz; }
+        if (prm.mode == 1) {     // samples - F.normalize(gradient, dim=2) * df_target   (eps 1e-12, generator.py:96)
+          const float inv = 1.f / fmaxf(sqrtf(gx * gx + gy * gy + gz * gz), 1e-12f), dd = s_dfc[pp];
+          float* po = prm.points_out + ((size_t)b * N + n) * 3;
+          po[0] = s_xyz[pp][0] - gx * inv * dd; po[1] = s_xyz[pp][1] - gy * inv * dd; po[2] = s_xyz[pp][3] - gz * inv * dd;
+        }
+      }
+    }
+    if (sat) atomicAdd(overflow, 1);
+  } else if (warp == 4) {
+    // ================================================================== TMA producer (weights), same order as the MMA issuer
+    if (lane == 0) {
+      int iw = 0;
+      auto load = [&](const CUtensorMap* hi, const CUtensorMap* lo, int col, int row) {
+        const int s = iw % TQ_NW;
+        tq_mbar_wait(tq_smem_u32(&w_empty[s]), ((uint32_t)(iw / TQ_NW) & 1u) ^ 1u);
+        const uint32_t full = tq_smem_u32(&w_full[s]);
+        tq_mbar_expect_tx(full, TQ_SLOT);
+        tq_tma_2d(w_base + s * TQ_SLOT, hi, full, col, row);
+        tq_tma_2d(w_base + s * TQ_SLOT + TQ_PLANE, lo, full, col, row);
+        ++iw;
+      };
+      for (int h = 0; h < 5; ++h) {
+        if (!((heads >> h) & 1)) continue;
+        for (int c = 0; c < TQ_NCHUNK; ++c) load(&tm_w1_hi, &tm_w1_lo, c * TQ_KC, h * TQ_H);
+        for (int layer = 0; layer < 2; ++layer)
+          for (int kc = 0; kc < 2; ++kc) load(&tm_w23_hi, &tm_w23_lo, kc * TQ_KC, (layer * 5 + h) * TQ_H);
+        for (int layer = 1; layer >= 0; --layer)
+          for (int kc = 0; kc < 2; ++kc) load(&tm_w23t_hi, &tm_w23t_lo, kc * TQ_KC, (layer * 5 + h) * TQ_H);
+        for (int u = 0; u < TQ_NCHUNK / 2; ++u)
+          for (int kc = 0; kc < 2; ++kc) load(&tm_w1t_hi, &tm_w1t_lo, kc * TQ_KC, h * TQ_NCHUNK * TQ_KC + u * TQ_H);
+      }
+    }
+  } else if (warp == 5) {
+    // ================================================================== MMA issuer
+    if (lane == 0) {
+      int it = 0, iw = 0, iact = 0, gfi = 0;
+      auto mma_tile = [&](uint32_t a_addr, uint32_t acc, bool first) {
+        const int s = iw % TQ_NW;
+        tq_mbar_wait(tq_smem_u32(&w_full[s]), (uint32_t)(iw / TQ_NW) & 1u);
+        tq_fence_after();
+        const uint64_t a_hi = tq_desc(a_addr), a_lo = tq_desc(a_addr + TQ_PLANE);
+        const uint64_t b_hi = tq_desc(w_base + s * TQ_SLOT), b_lo = tq_desc(w_base + s * TQ_SLOT + TQ_PLANE);
+#pragma unroll
+        for (int kk = 0; kk < TQ_KC / 16; ++kk) {
+          const uint64_t adv = (uint64_t)(kk * 32 >> 4);
+          tq_mma(acc, a_hi + adv, b_hi + adv, (first && kk == 0) ? 0u : 1u);
+          tq_mma(acc, a_hi + adv, b_lo + adv, 1u);
+          tq_mma(acc, a_lo + adv, b_hi + adv, 1u);
+        }
+        tq_commit(tq_smem_u32(&w_empty[s]));
+        ++iw;
+      };
+      for (int h = 0; h < 5; ++h) {
+        if (!((heads >> h) & 1)) continue;
+        for (int c = 0; c < TQ_NCHUNK; ++c, ++it) {                     // F1
+          const int slot = it & 1;
+          tq_mbar_wait(tq_smem_u32(&feat_full[slot]), (uint32_t)(it >> 1) & 1u);
+          tq_fence_after();
+          mma_tile(feat_base + slot * TQ_SLOT, tmem_base, c == 0);
+          tq_commit(tq_smem_u32(&feat_empty[slot]));
+        }
+        tq_commit(tq_smem_u32(&acc_full));
+        for (int stage = 0; stage < 4; ++stage) {                       // F2, F3, B3, B2: act buffer -> working accumulator
+          tq_mbar_wait(tq_smem_u32(&act_full), (uint32_t)iact & 1u); ++iact;
+          tq_fence_after();
+          for (int kc = 0; kc < 2; ++kc) mma_tile(act_base + kc * TQ_SLOT, tmem_base, kc == 0);
+          tq_commit(tq_smem_u32(&acc_full));
+        }
+        tq_mbar_wait(tq_smem_u32(&act_full), (uint32_t)iact & 1u); ++iact;     // g1 is in the act buffer
+        tq_fence_after();
+        for (int u = 0; u < TQ_NCHUNK / 2; ++u, ++gfi) {                // B1: five groups of 128 feature-gradient columns
+          const int gs = gfi % TB_NGF;
+          tq_mbar_wait(tq_smem_u32(&gf_empty[gs]), ((uint32_t)(gfi / TB_NGF) & 1u) ^ 1u);
+          tq_fence_after();
+          for (int kc = 0; kc < 2; ++kc) mma_tile(act_base + kc * TQ_SLOT, tmem_base + TQ_H + gs * TQ_H, kc == 0);
+          tq_commit(tq_smem_u32(&gf_full[gs]));
+        }
+      }
+    }
+  } else {
+    // ================================================================== epilogue warps: thread = point row = TMEM lane
+    const int r = warp * 32 + lane, n = n0 + r;
+    const uint32_t lane_base = tmem_base + ((uint32_t)(warp * 32) << 16);
+    int iacc = 0, sat = 0, gfi = 0, sc = 0;
+    // write 32 values (K index ch*32 + i of a 128-wide layer) of this point as the next MMA's A operand
+    auto store_act = [&](const float (&v)[32], int ch) {
+      uint8_t* dst = act_ptr + (ch >> 1) * TQ_SLOT;
+#pragma unroll
+      for (int i = 0; i < 32; i += 8) {
+        __align__(16) __half hh[8];
+        __align__(16) __half ll[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) tq_split(v[i + j], hh[j], ll[j], sat);
+        const uint32_t off = tq_sw_off(r, (ch & 1) * 32 + i);
+        *reinterpret_cast<uint4*>(dst + off) = *reinterpret_cast<const uint4*>(hh);
+        *reinterpret_cast<uint4*>(dst + TQ_PLANE + off) = *reinterpret_cast<const uint4*>(ll);
+      }
+    };
+    auto publish_act = [&]() {
+      tq_fence_before();                                   // TMEM reads of the accumulator are done before the MMA overwrites it
+      tq_fence_async();
+      __syncwarp();
+      if (lane == 0) tq_mbar_arrive(tq_smem_u32(&act_full));
+    };
+    for (int h = 0; h < 5; ++h) {
+      if (!((heads >> h) & 1)) continue;
+      const float* hw = wpack + (size_t)h * wpack_head_stride;
+      const float* b1 = hw + 616 * 128;
+      const float* b2 = b1 + 128 + 128 * 128;
+      const float* b3 = b2 + 128 + 128 * 128;
+      const float* W4 = b3 + 128;
+      asm volatile("bar.sync 2, 128;" ::: "memory");      // the previous head has finished reading s_w4
+      for (int i = threadIdx.x; i < (TQ_H * 16 + 16) / 4; i += 128)
+        reinterpret_cast<float4*>(s_w4)[i] = __ldg(reinterpret_cast<const float4*>(W4) + i);
+      asm volatile("bar.sync 2, 128;" ::: "memory");
+      float o[14];
+#pragma unroll
+      for (int c = 0; c < 14; ++c) o[c] = 0.f;
+      // ---- forward epilogues E1, E2, E3 (ReLU masks -> s_mask; the loops stay rolled, every v[] index is a compile-time constant)
+#pragma unroll 1
+      for (int layer = 0; layer < 3; ++layer) {
+        tq_mbar_wait(tq_smem_u32(&acc_full), (uint32_t)iacc & 1u); ++iacc;
+        tq_fence_after();
+        const float* bias = layer == 0 ? b1 : layer == 1 ? b2 : b3;
+#pragma unroll 1
+        for (int ch = 0; ch < 4; ++ch) {
+          float v[32];
+          tq_ld32(lane_base + ch * 32, v);
+          uint32_t mk = 0;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const float t = v[i] + __ldg(bias + ch * 32 + i);
+            mk |= (t > 0.f ? 1u : 0u) << i;
+            v[i] = fmaxf(t, 0.f);
+          }
+          s_mask[layer][ch][r] = mk;
+          if (layer < 2) {
+            store_act(v, ch);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const float4* wr = reinterpret_cast<const float4*>(s_w4 + (ch * 32 + i) * 16);
+              const float4 w0 = wr[0], w1 = wr[1], w2 = wr[2], w3 = wr[3];
+              o[0] = fmaf(v[i], w0.x, o[0]); o[1] = fmaf(v[i], w0.y, o[1]); o[2] = fmaf(v[i], w0.z, o[2]); o[3] = fmaf(v[i], w0.w, o[3]);
+              o[4] = fmaf(v[i], w1.x, o[4]); o[5] = fmaf(v[i], w1.y, o[5]); o[6] = fmaf(v[i], w1.z, o[6]); o[7] = fmaf(v[i], w1.w, o[7]);
+              o[8] = fmaf(v[i], w2.x, o[8]); o[9] = fmaf(v[i], w2.y, o[9]); o[10] = fmaf(v[i], w2.z, o[10]); o[11] = fmaf(v[i], w2.w, o[11]);
+              o[12] = fmaf(v[i], w3.x, o[12]); o[13] = fmaf(v[i], w3.y, o[13]);
+            }
+          }
+        }
+        if (layer < 2) publish_act();
+      }
+      // ---- cotangent at the head outputs, normalised per point
+      float g4[14];
+      float gmax = 0.f;
+      const int nout = h == 0 ? 2 : h == 1 ? 9 : h == 2 ? 14 : h == 3 ? 3 : 1;
+      const int hoff = h == 0 ? 0 : h == 1 ? 2 : h == 2 ? 11 : h == 3 ? 25 : 28;
+#pragma unroll
+      for (int c = 0; c < 14; ++c) {
+        float g = 0.f;
+        if (c < nout && n < N) {
+          float val = o[c] + s_w4[TQ_H * 16 + c];
+          if (h == 4) val = 1.f / (1.f + expf(-val));
+          if (h == 0 && !s_in_img[r]) val = cam.out_dist;
+          if (prm.mode == 0) {
+            g = prm.g_out[((size_t)b * 29 + hoff + c) * N + n];
+            if (h == 4) g *= val * (1.f - val);
+          } else if (c == prm.df_idx) {
+            g = val <= prm.threshold ? 1.f : 0.f;
+            s_dfc[r] = fminf(val, prm.threshold);
+          }
+          if (h == 0 && !s_in_img[r]) g = 0.f;
+        }
+        g4[c] = g;
+        gmax = fmaxf(gmax, fabsf(g));
+      }
+      int e_total = tb_norm_exp(gmax);
+      {
+        const float inv = ldexpf(1.f, -e_total);
+#pragma unroll
+        for (int c = 0; c < 14; ++c) g4[c] *= inv;
+      }
+      // g3 = relu'(h3) . (W4^T g4): 128 x <=14 on the CUDA cores, straight into the A operand of B3
+#pragma unroll 1
+      for (int ch = 0; ch < 4; ++ch) {
+        float v[32];
+        const uint32_t mk = s_mask[2][ch][r];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const float4* wr = reinterpret_cast<const float4*>(s_w4 + (ch * 32 + i) * 16);
+          const float4 w0 = wr[0], w1 = wr[1], w2 = wr[2], w3 = wr[3];
+          float a = g4[0] * w0.x;
+          a = fmaf(g4[1], w0.y, a); a = fmaf(g4[2], w0.z, a); a = fmaf(g4[3], w0.w, a);
+          a = fmaf(g4[4], w1.x, a); a = fmaf(g4[5], w1.y, a); a = fmaf(g4[6], w1.z, a); a = fmaf(g4[7], w1.w, a);
+          a = fmaf(g4[8], w2.x, a); a = fmaf(g4[9], w2.y, a); a = fmaf(g4[10], w2.z, a); a = fmaf(g4[11], w2.w, a);
+          a = fmaf(g4[12], w3.x, a); a = fmaf(g4[13], w3.y, a);
+          v[i] = ((mk >> i) & 1u) ? a : 0.f;
+        }
+        store_act(v, ch);
+      }
+      publish_act();
+      // ---- backward epilogues EB3 (mask of layer 2), EB2 (mask of layer 1): renormalise, mask, split
+#pragma unroll 1
+      for (int bl = 1; bl >= 0; --bl) {
+        tq_mbar_wait(tq_smem_u32(&acc_full), (uint32_t)iacc & 1u); ++iacc;
+        tq_fence_after();
+        float vmax = 0.f;
+#pragma unroll 1
+        for (int ch = 0; ch < 4; ++ch) {
+          float v[32];
+          tq_ld32(lane_base + ch * 32, v);
+          const uint32_t mk = s_mask[bl][ch][r];
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if ((mk >> i) & 1u) vmax = fmaxf(vmax, fabsf(v[i]));
+        }
+        const int e = tb_norm_exp(vmax);
+        e_total += e;
+        const float inv = ldexpf(1.f, -e);
+#pragma unroll 1
+        for (int ch = 0; ch < 4; ++ch) {
+          float v[32];
+          tq_ld32(lane_base + ch * 32, v);
+          const uint32_t mk = s_mask[bl][ch][r];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = ((mk >> i) & 1u) ? v[i] * inv : 0.f;
+          store_act(v, ch);
+        }
+        if (bl == 0) s_scale_e[r] = e_total;               // read by the gather warps after the first staging chunk is published
+        publish_act();
+      }
+      // ---- drain gf (five 128-column groups) into the fp32 staging ring for the gather warps
+      for (int u = 0; u < TQ_NCHUNK / 2; ++u, ++gfi) {
+        const int gs = gfi % TB_NGF;
+        tq_mbar_wait(tq_smem_u32(&gf_full[gs]), (uint32_t)(gfi / TB_NGF) & 1u);
+        tq_fence_after();
+#pragma unroll 1
+        for (int ch = 0; ch < 4; ++ch) {
+          if ((ch & 1) == 0) {
+            tq_mbar_wait(tq_smem_u32(&stg_empty[sc & 1]), ((uint32_t)(sc >> 1) & 1u) ^ 1u);
+          }
+          float v[32];
+          tq_ld32(lane_base + TQ_H + gs * TQ_H + ch * 32, v);
+          uint8_t* stg = feat_ptr + (sc & 1) * TQ_SLOT + r * 256;
+#pragma unroll
+          for (int q4 = 0; q4 < 8; ++q4)
+            *reinterpret_cast<float4*>(stg + ((((ch & 1) * 8 + q4) ^ (r & 15)) << 4)) = make_float4(v[q4 * 4], v[q4 * 4 + 1], v[q4 * 4 + 2], v[q4 * 4 + 3]);
+          if ((ch & 1) == 1) {
+            __syncwarp();
+            if (lane == 0) tq_mbar_arrive(tq_smem_u32(&stg_full[sc & 1]));
+            ++sc;
+          }
+        }
+        tq_fence_before();
+        __syncwarp();
+        if (lane == 0) tq_mbar_arrive(tq_smem_u32(&gf_empty[gs]));
+      }
+    }
+    if (sat) atomicAdd(overflow, 1);
+  }
+  tq_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+static int launch_bwd_tc(const float* points, const float* crop_center, const float* body_center, int B, int N, const float* im_feat,
+                         const float* tmpx, const float* tri_tmpx, const float* tri_feat, int Hf, int Wf, int Ht, int Wt, const float* cam7,
+                         const float* wpack, const void* const* planes /*w1 hi lo, w23 hi lo, w23t hi lo, w1t hi lo*/, const TbParams& prm,
+                         int* overflow, cudaStream_t stream, const char* who) {
+  CUtensorMap mp[8];
+  int rc;
+  const int kcols[4] = {TQ_NCHUNK * TQ_KC, TQ_H, TQ_H, TQ_H};
+  const int rows[4] = {5 * TQ_H, 2 * 5 * TQ_H, 2 * 5 * TQ_H, 5 * TQ_NCHUNK * TQ_KC};
+  for (int i = 0; i < 8; ++i)
+    if ((rc = tq_make_map(&mp[i], planes[i], kcols[i / 2], rows[i / 2]))) return rc;
+  TqMaps m{im_feat, tmpx, tri_tmpx, tri_feat, Hf, Wf, Ht, Wt};
+  TqCam cam{cam7[0], cam7[1], cam7[2], cam7[3], cam7[4], cam7[5], cam7[6]};
+  cudaError_t e = cudaFuncSetAttribute(query_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TB_SMEM);
+  if (e != cudaSuccess) return cuda_fail(e, who);
+  dim3 grid(ceil_div(N, TQ_M), B);
+  const int head_stride = 616 * 128 + 128 + 2 * (128 * 128 + 128) + 128 * 16 + 16;
+  query_bwd_tc_kernel<<<grid, TB_THREADS, TB_SMEM, stream>>>(mp[0], mp[1], mp[2], mp[3], mp[4], mp[5], mp[6], mp[7], points, crop_center,
+                                                             body_center, B, N, m, cam, wpack, head_stride, prm, overflow);
+  VT_CHECK_LAUNCH(who);
+  return 0;
+}
+
+}  // namespace vt
+
+using namespace vt;
+
+extern "C" {
+
+int vt_query_bwd_tc(const float* points, const float* crop_center, const float* body_center, int B, int N, const float* im_feat,
+                    const float* tmpx, const float* tri_tmpx, const float* tri_feat, int Hf, int Wf, int Ht, int Wt, const float* cam7,
+                    const float* wpack, const void* w1_hi, const void* w1_lo, const void* w23_hi, const void* w23_lo, const void* w23t_hi,
+                    const void* w23t_lo, const void* w1t_hi, const void* w1t_lo, const float* g_out, int head_mask, float* g_points,
+                    int* overflow, void* stream) {
+  VT_CHECK_ARG(head_mask >= 0 && head_mask < 32, "vt_query_bwd_tc: head mask %d", head_mask);
+  VT_CHECK_ARG(g_out != nullptr && g_points != nullptr && overflow != nullptr, "vt_query_bwd_tc: g_out, g_points and overflow are required");
+  if (B <= 0 || N <= 0) return 0;
+  if (head_mask == 0) return cudaMemsetAsync(g_points, 0, (size_t)B * N * 3 * sizeof(float), (cudaStream_t)stream) == cudaSuccess ? 0 : -3;
+  const void* planes[8] = {w1_hi, w1_lo, w23_hi, w23_lo, w23t_hi, w23t_lo, w1t_hi, w1t_lo};
+  TbParams prm{g_out, g_points, nullptr, 0, 0, head_mask, 0.f};
+  return launch_bwd_tc(points, crop_center, body_center, B, N, im_feat, tmpx, tri_tmpx, tri_feat, Hf, Wf, Ht, Wt, cam7, wpack, planes, prm,
+                       overflow, (cudaStream_t)stream, "vt_query_bwd_tc");
+}
+
+int vt_query_project_step_tc(const float* points, const float* crop_center, const float* body_center, int B, int N, const float* im_feat,
+                             const float* tmpx, const float* tri_tmpx, const float* tri_feat, int Hf, int Wf, int Ht, int Wt,
+                             const float* cam7, const float* wpack, const void* w1_hi, const void* w1_lo, const void* w23_hi,
+                             const void* w23_lo, const void* w23t_hi, const void* w23t_lo, const void* w1t_hi, const void* w1t_lo,
+                             int df_idx, float threshold, float* points_out, float* g_points, int* overflow, void* stream) {
+  VT_CHECK_ARG(df_idx == 0 || df_idx == 1, "vt_query_project_step_tc: df_idx %d (0 human, 1 object)", df_idx);
+  VT_CHECK_ARG(points_out != nullptr && overflow != nullptr, "vt_query_project_step_tc: points_out and overflow are required");
+  if (B <= 0 || N <= 0) return 0;
+  const void* planes[8] = {w1_hi, w1_lo, w23_hi, w23_lo, w23t_hi, w23t_lo, w1t_hi, w1t_lo};
+  TbParams prm{nullptr, g_points, points_out, 1, df_idx, 1, threshold};
+  return launch_bwd_tc(points, crop_center, body_center, B, N, im_feat, tmpx, tri_tmpx, tri_feat, Hf, Wf, Ht, Wt, cam7, wpack, planes, prm,
+                       overflow, (cudaStream_t)stream, "vt_query_project_step_tc");
+}
+
+}  // extern "C"

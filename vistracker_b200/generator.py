@@ -55,6 +55,18 @@ class GeneratorTriplaneVis:
         out = torch.empty(B, N_OUT, N, device=self.device) if want_preds else None
         d = net.dims
         with torch.cuda.device(self.device):
+            if not net.query_on_cuda_cores:
+                # tensor-core path (csrc/query_bwd_tc.cu): the step evaluates the distance head only; the predictions of the final
+                # step come from one forward launch at the same points
+                _lib.call("vt_query_project_step_tc", P(pts), P(query_input["crop_center"]), P(query_input["body_center"]), B, N,
+                          P(im_feat), P(tmpx), P(tri_tmpx), P(tri_feat), im_feat.shape[1], im_feat.shape[2], tmpx.shape[1],
+                          tmpx.shape[2], net._cam7, P(net._wpack), *(P(t) for t in net._wtc), *(P(t) for t in net._wtc_bwd), df_idx,
+                          float(self.threshold), P(new), None, P(net._q_overflow), S())
+                if want_preds:
+                    _lib.call("vt_query_fwd_tc", P(pts), P(query_input["crop_center"]), P(query_input["body_center"]), B, N, P(im_feat),
+                              P(tmpx), P(tri_tmpx), P(tri_feat), im_feat.shape[1], im_feat.shape[2], tmpx.shape[1], tmpx.shape[2],
+                              net._cam7, P(net._wpack), *(P(t) for t in net._wtc), P(out), None, P(net._q_overflow), S())
+                return new, out
             _lib.call("vt_query_project_step", P(pts), P(query_input["crop_center"]), P(query_input["body_center"]), B, N, P(im_feat),
                       P(tmpx), P(tri_tmpx), P(tri_feat), im_feat.shape[1], im_feat.shape[2], tmpx.shape[1], tmpx.shape[2], d.rgb.out_ch,
                       d.rgb.stem_ch, d.tri.stem_ch, d.tri.out_ch, net._cam7, P(net._wpack), P(net._wpack_bwd), df_idx,

@@ -19,7 +19,7 @@ from . import _lib
 from .config import SIFNetDims, resolve_dims
 from .encoder import HGEncoder
 from .synth import sifnet_spec
-from .weights import pack_decoders, pack_decoders_bwd, pack_decoders_tc
+from .weights import pack_decoders, pack_decoders_bwd, pack_decoders_tc, pack_decoders_tc_bwd
 
 N_OUT = 29          # df 2 | pca 9 | parts 14 | centers 3 | visibility 1
 
@@ -130,6 +130,7 @@ class CHORETriplaneVisibility:
             self._wpack = pack_decoders(sd, self.device)
             self._wpack_bwd = pack_decoders_bwd(sd, self.device)
             self._wtc = pack_decoders_tc(sd, self.device)
+            self._wtc_bwd = pack_decoders_tc_bwd(sd, self.device)
             self._q_overflow = torch.zeros(1, dtype=torch.int32, device=self.device)
         assert self._wpack.numel() == _lib.load().vt_query_wpack_floats()
         assert self._wpack_bwd.numel() == _lib.load().vt_query_wpack_bwd_floats()
@@ -242,6 +243,12 @@ class CHORETriplaneVisibility:
         g_pts = torch.empty(B, N, 3, dtype=torch.float32, device=self.device)
         d = self.dims
         with torch.cuda.device(self.device):
+            if not self.query_on_cuda_cores:
+                _lib.call("vt_query_bwd_tc", _lib.ptr(pts), _lib.ptr(cc), _lib.ptr(bc), B, N, _lib.ptr(im_feat), _lib.ptr(tmpx),
+                          _lib.ptr(tri_tmpx), _lib.ptr(tri_feat), im_feat.shape[1], im_feat.shape[2], tmpx.shape[1], tmpx.shape[2],
+                          self._cam7, _lib.ptr(self._wpack), *(_lib.ptr(t) for t in self._wtc), *(_lib.ptr(t) for t in self._wtc_bwd),
+                          _lib.ptr(g), int(head_mask), _lib.ptr(g_pts), _lib.ptr(self._q_overflow), _lib.stream_ptr())
+                return g_pts
             _lib.call("vt_query_bwd_heads", _lib.ptr(pts), _lib.ptr(cc), _lib.ptr(bc), B, N, _lib.ptr(im_feat), _lib.ptr(tmpx),
                       _lib.ptr(tri_tmpx), _lib.ptr(tri_feat), im_feat.shape[1], im_feat.shape[2], tmpx.shape[1], tmpx.shape[2],
                       d.rgb.out_ch, d.rgb.stem_ch, d.tri.stem_ch, d.tri.out_ch, self._cam7, _lib.ptr(self._wpack),

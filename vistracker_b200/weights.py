@@ -125,3 +125,23 @@ def pack_decoders_tc(sd: Dict[str, torch.Tensor], device):
     w1h, w1l = split_f16_unscaled(w1)
     w2h, w2l = split_f16_unscaled(w23)
     return tuple(t.to(device) for t in (w1h, w1l, w2h, w2l))
+
+
+def pack_decoders_tc_bwd(sd: Dict[str, torch.Tensor], device):
+    """Transposed fp16 hi/lo planes for the tcgen05 backward kernel (csrc/query_bwd_tc.cu): W2^T | W3^T [2*5*128, 128] (rows = input
+    unit j, columns = output unit k: the B operand of g_in[j] = sum_k g_out[k] W[k][j]) and W1^T [5*640, 128] (rows = feature in the
+    kernel's order, zero rows for the padding)."""
+    perm = feature_permutation_tc()
+    valid = perm >= 0
+    w23t = torch.zeros(2 * 5 * Q_H, Q_H)
+    w1t = torch.zeros(5 * 640, Q_H)
+    for h, name in enumerate(HEADS):
+        w = sd[f"{name}.0.weight"][:, :, 0].float().cpu()                     # [128 out, 611 in]
+        blk = torch.zeros(640, Q_H)
+        blk[valid] = w[:, perm[valid]].t()
+        w1t[h * 640:(h + 1) * 640] = blk
+        for li, idx in enumerate((2, 4)):
+            w23t[(li * 5 + h) * Q_H:(li * 5 + h + 1) * Q_H] = sd[f"{name}.{idx}.weight"][:, :, 0].float().cpu().t()
+    a, b = split_f16_unscaled(w23t)
+    c, d = split_f16_unscaled(w1t)
+    return tuple(t.to(device) for t in (a, b, c, d))
