@@ -18,3 +18,10 @@ for _ in range(int(sys.argv[1]) if len(sys.argv) > 1 else 5):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(); net._query_raw(pts, cc, bc); e1.record(); torch.cuda.synchronize()
     print(f"query 8 x 10000 points: {e0.elapsed_time(e1):.3f} ms")
+if "--bwd" in sys.argv:
+    g = torch.randn(8, 29, 10000, device=dev)
+    for mask in (5, 1):
+        for _ in range(3):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); net._query_backward(pts, cc, bc, g, head_mask=mask); e1.record(); torch.cuda.synchronize()
+            print(f"query backward 8 x 10000 points, head mask {mask}: {e0.elapsed_time(e1):.3f} ms")

@@ -87,6 +87,7 @@ query_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_c
   __shared__ uint32_t s_mask[3][4][TQ_M];                   // ReLU masks of the three hidden layers of the current head (128 bits per point)
   __shared__ float s_gacc[TQ_M][3];                         // d/d(x, y, z) of every point, summed over chunks and heads
   __shared__ __align__(16) float s_w4[TQ_H * 16 + 16];
+  __shared__ __align__(16) float s_bias[3][TQ_H];           // b1, b2, b3 of the current head
 
   const uint32_t smem_base = (tq_smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_al = smem_raw + (smem_base - tq_smem_u32(smem_raw));
@@ -157,7 +158,8 @@ query_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_c
     constexpr int PBB = 2;                                  // ... and in the backward contraction (more live registers per point)
     for (int i = lane; i < PW * 3; i += 32) (&s_gacc[gw * PW][0])[i] = 0.f;      // each warp owns the rows of its 16 points
     __syncwarp();
-    int sat = 0, it = 0, sc = 0;
+    int it = 0, sc = 0;
+    float amax = 0.f;
     for (int h = 0; h < 5; ++h) {
       if (!((heads >> h) & 1)) continue;
       asm volatile("bar.sync 3, 256;" ::: "memory");       // every gather warp is done reading the previous head's staging slots
@@ -197,13 +199,12 @@ query_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_c
               v[0] = v[1] = v[2] = v[3] = 0.f;
               if (direct[j]) { v[0] = s_xyz[pp][0]; v[1] = s_xyz[pp][1]; v[2] = s_xyz[pp][2]; }
             }
-            __align__(8) __half hh[4];
-            __align__(8) __half ll[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) tq_split(v[e], hh[e], ll[e], sat);
+            uint2 hh, ll;
+            tq_split2(v[0], v[1], hh.x, ll.x, amax);
+            tq_split2(v[2], v[3], hh.y, ll.y, amax);
             const uint32_t off = tq_sw_off(pp, k);
-            *reinterpret_cast<uint2*>(dst + off) = *reinterpret_cast<const uint2*>(hh);
-            *reinterpret_cast<uint2*>(dst + TQ_PLANE + off) = *reinterpret_cast<const uint2*>(ll);
+            *reinterpret_cast<uint2*>(dst + off) = hh;
+            *reinterpret_cast<uint2*>(dst + TQ_PLANE + off) = ll;
           }
         }
         tq_fence_async();
@@ -292,7 +293,7 @@ query_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_c
         }
       }
     }
-    if (sat) atomicAdd(overflow, 1);
+    if (amax > 65504.f) atomicAdd(overflow, 1);
   } else if (warp == 4) {
     // ================================================================== TMA producer (weights), same order as the MMA issuer
     if (lane == 0) {
@@ -368,19 +369,19 @@ query_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_c
     // ================================================================== epilogue warps: thread = point row = TMEM lane
     const int r = warp * 32 + lane, n = n0 + r;
     const uint32_t lane_base = tmem_base + ((uint32_t)(warp * 32) << 16);
-    int iacc = 0, sat = 0, gfi = 0, sc = 0;
+    int iacc = 0, gfi = 0, sc = 0;
+    float amax = 0.f;
     // write 32 values (K index ch*32 + i of a 128-wide layer) of this point as the next MMA's A operand
     auto store_act = [&](const float (&v)[32], int ch) {
       uint8_t* dst = act_ptr + (ch >> 1) * TQ_SLOT;
 #pragma unroll
       for (int i = 0; i < 32; i += 8) {
-        __align__(16) __half hh[8];
-        __align__(16) __half ll[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) tq_split(v[i + j], hh[j], ll[j], sat);
+        uint4 hh, ll;
+        tq_split2(v[i], v[i + 1], hh.x, ll.x, amax); tq_split2(v[i + 2], v[i + 3], hh.y, ll.y, amax);
+        tq_split2(v[i + 4], v[i + 5], hh.z, ll.z, amax); tq_split2(v[i + 6], v[i + 7], hh.w, ll.w, amax);
         const uint32_t off = tq_sw_off(r, (ch & 1) * 32 + i);
-        *reinterpret_cast<uint4*>(dst + off) = *reinterpret_cast<const uint4*>(hh);
-        *reinterpret_cast<uint4*>(dst + TQ_PLANE + off) = *reinterpret_cast<const uint4*>(ll);
+        *reinterpret_cast<uint4*>(dst + off) = hh;
+        *reinterpret_cast<uint4*>(dst + TQ_PLANE + off) = ll;
       }
     };
     auto publish_act = [&]() {
@@ -399,6 +400,10 @@ query_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_c
       asm volatile("bar.sync 2, 128;" ::: "memory");      // the previous head has finished reading s_w4
       for (int i = threadIdx.x; i < (TQ_H * 16 + 16) / 4; i += 128)
         reinterpret_cast<float4*>(s_w4)[i] = __ldg(reinterpret_cast<const float4*>(W4) + i);
+      if (threadIdx.x < 96) {
+        const int l = threadIdx.x >> 5, q = threadIdx.x & 31;
+        reinterpret_cast<float4*>(s_bias[l])[q] = __ldg(reinterpret_cast<const float4*>(l == 0 ? b1 : l == 1 ? b2 : b3) + q);
+      }
       asm volatile("bar.sync 2, 128;" ::: "memory");
       float o[14];
 #pragma unroll
@@ -408,17 +413,18 @@ query_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_c
       for (int layer = 0; layer < 3; ++layer) {
         tq_mbar_wait(tq_smem_u32(&acc_full), (uint32_t)iacc & 1u); ++iacc;
         tq_fence_after();
-        const float* bias = layer == 0 ? b1 : layer == 1 ? b2 : b3;
+        const float* bias = s_bias[layer];
 #pragma unroll 1
         for (int ch = 0; ch < 4; ++ch) {
           float v[32];
           tq_ld32(lane_base + ch * 32, v);
           uint32_t mk = 0;
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const float t = v[i] + __ldg(bias + ch * 32 + i);
-            mk |= (t > 0.f ? 1u : 0u) << i;
-            v[i] = fmaxf(t, 0.f);
+          for (int i = 0; i < 32; i += 4) {
+            const float4 bb = *reinterpret_cast<const float4*>(bias + ch * 32 + i);
+            const float t0 = v[i] + bb.x, t1 = v[i + 1] + bb.y, t2 = v[i + 2] + bb.z, t3 = v[i + 3] + bb.w;
+            mk |= ((t0 > 0.f ? 1u : 0u) | (t1 > 0.f ? 2u : 0u) | (t2 > 0.f ? 4u : 0u) | (t3 > 0.f ? 8u : 0u)) << i;
+            v[i] = fmaxf(t0, 0.f); v[i + 1] = fmaxf(t1, 0.f); v[i + 2] = fmaxf(t2, 0.f); v[i + 3] = fmaxf(t3, 0.f);
           }
           s_mask[layer][ch][r] = mk;
           if (layer < 2) {
@@ -543,7 +549,7 @@ query_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_c
         if (lane == 0) tq_mbar_arrive(tq_smem_u32(&gf_empty[gs]));
       }
     }
-    if (sat) atomicAdd(overflow, 1);
+    if (amax > 65504.f) atomicAdd(overflow, 1);
   }
   tq_fence_before();
   __syncthreads();

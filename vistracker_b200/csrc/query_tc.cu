@@ -35,6 +35,7 @@ query_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_c
   __shared__ float s_xyz[TQ_M][3];
   __shared__ int s_in_img[TQ_M];
   __shared__ __align__(16) float s_w4[TQ_H * 16 + 16];      // last layer of the current head: W4[128][16] + b4[16]
+  __shared__ __align__(16) float s_bias[3][TQ_H];           // b1, b2, b3 of the current head
 
   const uint32_t smem_base = (tq_smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_al = smem_raw + (smem_base - tq_smem_u32(smem_raw));
@@ -92,7 +93,8 @@ query_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_c
   if (warp >= 6) {
     // ================================================================== gather warps
     const int gw = warp - 6;
-    int sat = 0, it = 0;
+    int it = 0;
+    float amax = 0.f;
     for (int pass = 0; pass < 2; ++pass) {
       for (int c = 0; c < TQ_NCHUNK; ++c, ++it) {
         const int slot = it % TQ_NF;
@@ -149,13 +151,12 @@ query_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_c
             v[0] += t10[j].x * tap[j].w10; v[1] += t10[j].y * tap[j].w10; v[2] += t10[j].z * tap[j].w10; v[3] += t10[j].w * tap[j].w10;
             v[0] += t11[j].x * tap[j].w11; v[1] += t11[j].y * tap[j].w11; v[2] += t11[j].z * tap[j].w11; v[3] += t11[j].w * tap[j].w11;
             if (!sampled) { v[0] = direct[j].x; v[1] = direct[j].y; v[2] = direct[j].z; v[3] = direct[j].w; }
-            __align__(8) __half hh[4];
-            __align__(8) __half ll[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) tq_split(v[e], hh[e], ll[e], sat);
+            uint2 hh, ll;
+            tq_split2(v[0], v[1], hh.x, ll.x, amax);
+            tq_split2(v[2], v[3], hh.y, ll.y, amax);
             const uint32_t off = tq_sw_off(pp, k);
-            *reinterpret_cast<uint2*>(dst + off) = *reinterpret_cast<const uint2*>(hh);
-            *reinterpret_cast<uint2*>(dst + TQ_PLANE + off) = *reinterpret_cast<const uint2*>(ll);
+            *reinterpret_cast<uint2*>(dst + off) = hh;
+            *reinterpret_cast<uint2*>(dst + TQ_PLANE + off) = ll;
           }
         }
         tq_fence_async();                                 // generic-proxy writes -> visible to the tensor core (async proxy)
@@ -163,7 +164,7 @@ query_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_c
         if (lane == 0) tq_mbar_arrive(tq_smem_u32(&feat_full[slot]));
       }
     }
-    if (sat) atomicAdd(overflow, 1);
+    if (amax > 65504.f) atomicAdd(overflow, 1);
   } else if (warp == 4) {
     // ================================================================== TMA producer (weights)
     if (lane == 0) {
@@ -229,8 +230,8 @@ query_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_c
     // ================================================================== epilogue warps: thread = point row = TMEM lane
     const int r = warp * 32 + lane, n = n0 + r;
     const uint32_t lane_base = tmem_base + ((uint32_t)(warp * 32) << 16);
-    int iacc = 0, sat = 0;
-    const int head_nout[5] = {2, 9, 14, 3, 1}, head_off[5] = {0, 2, 11, 25, 28};
+    int iacc = 0;
+    float amax = 0.f;
     for (int pass = 0; pass < 2; ++pass) {
       const int h0 = pass == 0 ? 0 : 4, nh = pass == 0 ? 4 : 1;
       tq_mbar_wait(tq_smem_u32(&acc_full), (uint32_t)iacc & 1u); ++iacc;            // layer 1 done
@@ -245,10 +246,14 @@ query_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_c
         asm volatile("bar.sync 2, 128;" ::: "memory");      // previous head's last layer has finished reading s_w4
         for (int i = threadIdx.x; i < (TQ_H * 16 + 16) / 4; i += 128)
           reinterpret_cast<float4*>(s_w4)[i] = __ldg(reinterpret_cast<const float4*>(W4) + i);     // W4 and b4 are contiguous in the pack
+        if (threadIdx.x < 96) {
+          const int l = threadIdx.x >> 5, q = threadIdx.x & 31;
+          reinterpret_cast<float4*>(s_bias[l])[q] = __ldg(reinterpret_cast<const float4*>(l == 0 ? b1 : l == 1 ? b2 : b3) + q);
+        }
         asm volatile("bar.sync 2, 128;" ::: "memory");
         for (int layer = 0; layer < 3; ++layer) {
           if (layer > 0) { tq_mbar_wait(tq_smem_u32(&acc_full), (uint32_t)iacc & 1u); ++iacc; tq_fence_after(); }
-          const float* bias = layer == 0 ? b1 : layer == 1 ? b2 : b3;
+          const float* bias = s_bias[layer];
           float o[14];
 #pragma unroll
           for (int c = 0; c < 14; ++c) o[c] = 0.f;
@@ -257,23 +262,26 @@ query_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_c
             float v[32];
             tq_ld32(lane_base + g * TQ_H + ch * 32, v);
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i] + __ldg(bias + ch * 32 + i), 0.f);
+            for (int i = 0; i < 32; i += 4) {
+              const float4 bb = *reinterpret_cast<const float4*>(bias + ch * 32 + i);
+              v[i] = fmaxf(v[i] + bb.x, 0.f); v[i + 1] = fmaxf(v[i + 1] + bb.y, 0.f);
+              v[i + 2] = fmaxf(v[i + 2] + bb.z, 0.f); v[i + 3] = fmaxf(v[i + 3] + bb.w, 0.f);
+            }
             if (layer < 2) {
               // next layer's A operand: K index = ch*32 + i -> chunk kc = ch / 2, k = (ch & 1) * 32 + i
               uint8_t* dst = act_ptr + (ch >> 1) * TQ_SLOT;
 #pragma unroll
               for (int i = 0; i < 32; i += 8) {
-                __align__(16) __half hh[8];
-                __align__(16) __half ll[8];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) tq_split(v[i + j], hh[j], ll[j], sat);
+                uint4 hh, ll;
+                tq_split2(v[i], v[i + 1], hh.x, ll.x, amax); tq_split2(v[i + 2], v[i + 3], hh.y, ll.y, amax);
+                tq_split2(v[i + 4], v[i + 5], hh.z, ll.z, amax); tq_split2(v[i + 6], v[i + 7], hh.w, ll.w, amax);
                 const uint32_t off = tq_sw_off(r, (ch & 1) * 32 + i);
-                *reinterpret_cast<uint4*>(dst + off) = *reinterpret_cast<const uint4*>(hh);
-                *reinterpret_cast<uint4*>(dst + TQ_PLANE + off) = *reinterpret_cast<const uint4*>(ll);
+                *reinterpret_cast<uint4*>(dst + off) = hh;
+                *reinterpret_cast<uint4*>(dst + TQ_PLANE + off) = ll;
               }
             } else {
               // last layer on the CUDA cores: out[c] += h3[k] * W4[k][c]
-#pragma unroll 4
+#pragma unroll
               for (int i = 0; i < 32; ++i) {
                 const float4* wr = reinterpret_cast<const float4*>(s_w4 + (ch * 32 + i) * 16);
                 const float4 w0 = wr[0], w1 = wr[1], w2 = wr[2], w3 = wr[3];
@@ -290,11 +298,15 @@ query_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_c
             __syncwarp();
             if (lane == 0) tq_mbar_arrive(tq_smem_u32(&act_full));
           } else if (n < N) {
-            for (int c = 0; c < head_nout[h]; ++c) {
+            const int nout = h == 0 ? 2 : h == 1 ? 9 : h == 2 ? 14 : h == 3 ? 3 : 1;
+            const int hoff = h == 0 ? 0 : h == 1 ? 2 : h == 2 ? 11 : h == 3 ? 25 : 28;
+#pragma unroll
+            for (int c = 0; c < 14; ++c) {
+              if (c >= nout) break;
               float a = o[c] + s_w4[TQ_H * 16 + c];
               if (h == 4) a = 1.f / (1.f + expf(-a));
               if (h == 0 && !s_in_img[r]) a = cam.out_dist;
-              out[((size_t)b * 29 + head_off[h] + c) * N + n] = a;
+              out[((size_t)b * 29 + hoff + c) * N + n] = a;
             }
           }
         }
@@ -302,7 +314,7 @@ query_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_c
       // the group's accumulators are drained: order these TMEM reads before the next pass's first MMAs
       tq_fence_before();
     }
-    if (sat) atomicAdd(overflow, 1);
+    if (amax > 65504.f) atomicAdd(overflow, 1);
   }
   tq_fence_before();
   __syncthreads();
