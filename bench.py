@@ -28,6 +28,8 @@ sys.path.insert(0, ROOT)
 BATCH, NPTS, SIZE = 8, 10000, 512
 # conv-only 2*MAC per frame: 163.01 RGB encoder + 3 x 150.15 triplane encoder
 GFLOP_FILTER_PER_FRAME = 613.46
+# ncu dram__bytes_read.sum + dram__bytes_write.sum over the 186 tensor-core conv launches of one step, per launch (profiles/r01i_*)
+CONV_DRAM_BYTES_PER_LAUNCH = 228.9e6
 METRIC, UNIT = "frames/sec", "frames/s"
 WORKLOAD = f"sifnet-tri-vis-l2 filter+query, batch={BATCH} frames 512x512x8ch, {NPTS} query points/frame"
 
@@ -201,7 +203,7 @@ def run_ours(args):
     # ---- roofline of the dominant kernel (tcgen05 conv): events around every vt_conv_mma launch of one extra step
     roof = None
     if rank == 0:
-        spans = []
+        spans, conv_bytes = [], []
         orig_call = enc_mod._lib.call
 
         def traced(name, *a):
@@ -210,6 +212,12 @@ def run_ours(args):
             s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             s.record(); orig_call(name, *a); e.record()
             n_img, H, W, cin_pad, _pad, ks, cout = a[2], a[3], a[4], a[5], a[6], a[7], a[10]
+            # compulsory bytes of this launch: both fp16 operand planes and weight planes once, the fp32 output, residual reads and
+            # (vt_conv_mma_dual) the second output + its residual
+            n_out = 1 + (a[12] is not None) + (2 if name == "vt_conv_mma_dual" and a[18] is not None else 0)
+            nbytes = (2 * n_img * (H + 2 * _pad) * (W + 2 * _pad) * cin_pad * 2 + 2 * ks * ks * cout * cin_pad * 2
+                      + n_out * n_img * H * W * cout * 4)
+            conv_bytes.append(nbytes)
             spans.append((s, e, 2.0 * n_img * H * W * cout * ks * ks, cin_pad, name))
             return None
 
@@ -240,7 +248,10 @@ def run_ours(args):
         achieved = flops / (t_ms * 1e-3) / 1e12 if spans else 0.0
         roof = {"bound": "tensor", "kernel": "conv_mma_persist_kernel (tcgen05 fp16x2-split: 3 MMA-equivalents per fp32 MAC)", "achieved": achieved,
                 "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": achieved / pk["bf16_tflops_sustained"],
-                "traffic": None, "peak_source": f"{src} bf16 sustained (kernel timed inside a long step)",
+                "traffic": CONV_DRAM_BYTES_PER_LAUNCH, "traffic_unit": "bytes per launch (ncu dram__bytes_read+write, average of the 186 launches of one step)",
+                "traffic_source": "profiles/r01i_conv_dram_traffic.txt",
+                "algorithmic_bytes_per_launch_avg": sum(conv_bytes) / max(len(conv_bytes), 1),
+                "peak_source": f"{src} bf16 sustained (kernel timed inside a long step)",
                 "executed_mma_frac": 3 * achieved / pk["bf16_tflops_sustained"], "launches": len(spans),
                 "kernel_ms_per_step": t_ms, "share_of_step": t_ms / (ms / args.steps) if spans else 0.0,
                 "algorithmic_gflop_per_launch_avg": flops / 1e9 / max(len(spans), 1)}
