@@ -26,7 +26,11 @@ def arg(name, default):
 B = int(arg("--batch", 8))
 modes = arg("--modes", "persist,plain").split(",")
 iters = int(arg("--iters", 7))
-MODE_ENV = {"persist": {"VT_CONV_PERSIST": "1", "VT_CONV_STRIP": "0"}, "plain": {"VT_CONV_PERSIST": "0", "VT_CONV_STRIP": "0"},
+MODE_ENV = {"persist": {"VT_CONV_PERSIST": "1", "VT_CONV_STRIP": "0", "VT_CONV_PREFETCH": "0"},
+            "pf2": {"VT_CONV_PERSIST": "1", "VT_CONV_STRIP": "0", "VT_CONV_PREFETCH": "2"},
+            "pf4": {"VT_CONV_PERSIST": "1", "VT_CONV_STRIP": "0", "VT_CONV_PREFETCH": "4"},
+            "nores": {"VT_CONV_PERSIST": "2", "VT_CONV_STRIP": "0", "VT_CONV_PREFETCH": "0"},
+            "plain": {"VT_CONV_PERSIST": "0", "VT_CONV_STRIP": "0"},
             "strip": {"VT_CONV_PERSIST": "0", "VT_CONV_STRIP": "1"}, "pair": {"VT_CONV_PERSIST": "0", "VT_CONV_STRIP": "2"}}
 
 dev = torch.device("cuda", 0)

@@ -31,6 +31,7 @@ constexpr int MM_THREADS = 192;
 
 struct ConvMmaParams {
   int H, W, pad, ks, kchunks;   // kchunks = Cin_pad / 64
+  int prefetch;                 // persistent kernel: tiles of A-operand L2 prefetch distance (0 = off)
   int bw, bh, tiles_x, bw_shift;   // bw is a power of two: pixel r of a tile sits at (y0 + (r >> bw_shift), x0 + (r & (bw-1)))
   int cout_total;               // rows per tap in the packed weight planes
   const float* bias; const float* res; int ldr;
@@ -71,6 +72,10 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
   asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
                ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+// L2 prefetch of a TMA box: no shared memory, no barrier -- HBM requests in flight are no longer bounded by the ring depth
+__device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap* map, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global [%0, {%1, %2, %3}];" ::"l"(map), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
@@ -323,15 +328,21 @@ conv_mma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
 // BN = 128, 18 -> 14 KB at BN = 64: the shared-memory port is what bounds the N <= 64 tiles).
 // The epilogue stages one 32-row x 32-channel block per warp in a private 4.5 KB buffer, so every global access is a whole 128-byte
 // pixel-channel run and no tile-sized staging buffer has to be carved out of the pipeline.
-template <int BN>
+// RESB ("resident B", 1x1 convolutions with Cin <= 256): the whole weight panel of one Cout tile (<= 4 K-chunks x hi/lo) stays in
+// shared memory while the CTA walks pixel tiles of that (image, Cout tile) run; the ring then carries A stages only.  A 1x1 conv
+// has as many weight bytes as activation bytes per tile, so this halves its L2 -> SM traffic and gives the HBM-facing A stream the
+// whole ring.
+template <int BN, bool RESB = false>
 struct PersistCfg {
-  static constexpr int STAGES = BN == 128 ? 3 : (BN == 64 ? 4 : 5);
   static constexpr int A_BYTES = MM_M * MM_KC * 2;
   static constexpr int B_BYTES = BN * MM_KC * 2;
-  static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
+  static constexpr int PANEL_CHUNKS = 4;
+  static constexpr int PANEL_BYTES = RESB ? PANEL_CHUNKS * 2 * B_BYTES : 0;
+  static constexpr int STAGES = RESB ? (BN == 128 ? 2 : (BN == 64 ? 4 : 5)) : (BN == 128 ? 3 : (BN == 64 ? 4 : 5));
+  static constexpr int STAGE_BYTES = RESB ? 2 * A_BYTES : 2 * A_BYTES + 2 * B_BYTES;
   static constexpr int EPI_LD = 36;                                  // floats per staged row: 32 + 4 keeps float4 rows conflict-free
   static constexpr int EPI_BYTES = 4 * 32 * EPI_LD * 4;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 1024;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + PANEL_BYTES + EPI_BYTES + 1024;
   static constexpr int TMEM_COLS = 4 * BN;
   static constexpr uint32_t IDESC_WIDE = (1u << 4) | ((uint32_t)(2 * BN >> 3) << 17) | ((uint32_t)(MM_M >> 4) << 24);
   static constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(MM_M >> 4) << 24);
@@ -369,25 +380,28 @@ __device__ __forceinline__ void tc_ld32_issue(uint32_t taddr, uint32_t (&r)[32])
       : "r"(taddr) : "memory");
 }
 
-template <int BN>
+template <int BN, bool RESB>
 __global__ void __launch_bounds__(MM_THREADS, 1)
 conv_mma_persist_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                         const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo, const ConvMmaParams p,
                         int tiles_per_img, int n_tiles_n, int total_tiles) {
-  using Cfg = PersistCfg<BN>;
+  using Cfg = PersistCfg<BN, RESB>;
   extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t bar_full[Cfg::STAGES], bar_empty[Cfg::STAGES], acc_full[2], acc_empty[2];
+  __shared__ __align__(8) uint64_t bar_full[Cfg::STAGES], bar_empty[Cfg::STAGES], acc_full[2], acc_empty[2], panel_full, panel_empty;
   __shared__ uint32_t s_tmem_base;
-  __shared__ float s_sum[BN], s_sq[BN], s_sum2[BN], s_sq2[BN];
+  // per-warp partial statistics [warp][channel]: exactly one lane owns a slot, so the running sums are plain read-modify-writes (a
+  // shared-memory fp32 atomicAdd is a CAS loop, and four warps contending on it cost more than the rest of the chunk)
+  __shared__ __align__(16) float s_sum[4][BN], s_sq[4][BN], s_sum2[4][BN], s_sq2[4][BN];
 
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_iter = p.ks * p.ks * p.kchunks;
 
-  if (threadIdx.x < BN) { s_sum[threadIdx.x] = 0.f; s_sq[threadIdx.x] = 0.f; s_sum2[threadIdx.x] = 0.f; s_sq2[threadIdx.x] = 0.f; }
+  for (int i = threadIdx.x; i < 4 * BN; i += MM_THREADS) { (&s_sum[0][0])[i] = 0.f; (&s_sq[0][0])[i] = 0.f; (&s_sum2[0][0])[i] = 0.f; (&s_sq2[0][0])[i] = 0.f; }
   if (warp == 5 && lane == 0) {
     for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(smem_u32(&bar_full[s]), 1); mbar_init(smem_u32(&bar_empty[s]), 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(smem_u32(&acc_full[s]), 1); mbar_init(smem_u32(&acc_empty[s]), 4); }
+    mbar_init(smem_u32(&panel_full), 1); mbar_init(smem_u32(&panel_empty), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 4 && lane == 0) {
@@ -410,10 +424,37 @@ conv_mma_persist_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __gri
   if (warp == 4) {
     // ------------------------------------------------------------------ TMA producer: the ring runs across tile boundaries
     if (lane == 0) {
-      uint32_t g = 0;
+      uint32_t g = 0, pg = 0;
+      int panel_n0 = -1;
+      const uint32_t panel_base = smem_base + Cfg::STAGES * Cfg::STAGE_BYTES;
       for (int t = t_first; t < t_last; ++t) {
         const TileCoord c = decode_tile(p, t, n_tiles_n, tiles_per_img, BN);
         const int row0 = c.img * (p.H + 2 * p.pad) + c.y0;
+        // HBM-streaming shapes (1x1 convs, Cin <= 64): the ring alone keeps ~100 KB in flight per SM, not enough to cover DRAM
+        // latency at full bandwidth -- pull the A boxes of the tile `prefetch` tiles ahead into L2 now
+        if (p.prefetch > 0) {
+          for (int tp = (t == t_first ? t + 1 : t + p.prefetch); tp <= t + p.prefetch && tp < t_last; ++tp) {
+            const TileCoord cp = decode_tile(p, tp, n_tiles_n, tiles_per_img, BN);
+            const int rowp = cp.img * (p.H + 2 * p.pad) + cp.y0;
+            for (int it = 0; it < n_iter; ++it) {
+              const int tap = it / p.kchunks, kc = it % p.kchunks;
+              const int dy = tap / p.ks, dx = tap % p.ks;
+              if (p.ks == 3 && dx == 1) continue;          // the dx = 0 and dx = 2 boxes already cover the 130-pixel row
+              tma_prefetch_3d(&tm_a_hi, kc * MM_KC, cp.x0 + dx, rowp + dy);
+              tma_prefetch_3d(&tm_a_lo, kc * MM_KC, cp.x0 + dx, rowp + dy);
+            }
+          }
+        }
+        if (RESB && c.n0 != panel_n0) {                    // (re)load the weight panel of this Cout tile once the old one is unused
+          if (pg > 0) mbar_wait(smem_u32(&panel_empty), (pg - 1) & 1u);
+          const uint32_t pf = smem_u32(&panel_full);
+          mbar_expect_tx(pf, (uint32_t)p.kchunks * 2 * Cfg::B_BYTES);
+          for (int kc = 0; kc < p.kchunks; ++kc) {
+            tma_load_2d(panel_base + kc * 2 * Cfg::B_BYTES, &tm_b_hi, pf, kc * MM_KC, c.n0);
+            tma_load_2d(panel_base + kc * 2 * Cfg::B_BYTES + Cfg::B_BYTES, &tm_b_lo, pf, kc * MM_KC, c.n0);
+          }
+          panel_n0 = c.n0; ++pg;
+        }
         for (int it = 0; it < n_iter; ++it, ++g) {
           const int s = g % Cfg::STAGES;
           const uint32_t ph = (g / Cfg::STAGES) & 1u;
@@ -425,19 +466,29 @@ conv_mma_persist_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __gri
           const uint32_t sa = smem_base + s * Cfg::STAGE_BYTES;
           tma_load_3d(sa, &tm_a_hi, full, kc * MM_KC, c.x0 + dx, row0 + dy);
           tma_load_3d(sa + Cfg::A_BYTES, &tm_a_lo, full, kc * MM_KC, c.x0 + dx, row0 + dy);
-          tma_load_2d(sa + 2 * Cfg::A_BYTES, &tm_b_hi, full, kc * MM_KC, tap * p.cout_total + c.n0);
-          tma_load_2d(sa + 2 * Cfg::A_BYTES + Cfg::B_BYTES, &tm_b_lo, full, kc * MM_KC, tap * p.cout_total + c.n0);
+          if (!RESB) {
+            tma_load_2d(sa + 2 * Cfg::A_BYTES, &tm_b_hi, full, kc * MM_KC, tap * p.cout_total + c.n0);
+            tma_load_2d(sa + 2 * Cfg::A_BYTES + Cfg::B_BYTES, &tm_b_lo, full, kc * MM_KC, tap * p.cout_total + c.n0);
+          }
         }
       }
     }
   } else if (warp == 5) {
     // ------------------------------------------------------------------ MMA issuer (one thread)
     if (lane == 0) {
-      uint32_t g = 0, i = 0;
+      uint32_t g = 0, i = 0, pg = 0;
+      int panel_n0 = -1;
+      const uint32_t panel_base = smem_base + Cfg::STAGES * Cfg::STAGE_BYTES;
       for (int t = t_first; t < t_last; ++t, ++i) {
         const uint32_t set = i & 1u;
         mbar_wait(smem_u32(&acc_empty[set]), ((i >> 1) & 1u) ^ 1u);      // the epilogue has drained this accumulator set
         tc_fence_after();
+        int n0 = 0, n0_next = -1;
+        if (RESB) {
+          n0 = decode_tile(p, t, n_tiles_n, tiles_per_img, BN).n0;
+          if (t + 1 < t_last) n0_next = decode_tile(p, t + 1, n_tiles_n, tiles_per_img, BN).n0;
+          if (n0 != panel_n0) { mbar_wait(smem_u32(&panel_full), pg & 1u); tc_fence_after(); panel_n0 = n0; ++pg; }
+        }
         const uint32_t acc0 = tmem_base + set * 2 * BN, acc1 = acc0 + BN;
         for (int it = 0; it < n_iter; ++it, ++g) {
           const int s = g % Cfg::STAGES;
@@ -446,7 +497,8 @@ conv_mma_persist_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __gri
           tc_fence_after();
           const uint32_t sa = smem_base + s * Cfg::STAGE_BYTES;
           const uint64_t a_hi = make_kmajor_sw128_desc(sa), a_lo = make_kmajor_sw128_desc(sa + Cfg::A_BYTES);
-          const uint64_t b_hi = make_kmajor_sw128_desc(sa + 2 * Cfg::A_BYTES);     // rows [0, BN) = B_hi, rows [BN, 2 BN) = B_lo
+          // rows [0, BN) = B_hi, rows [BN, 2 BN) = B_lo; 1x1: it == K-chunk index into the resident panel
+          const uint64_t b_hi = make_kmajor_sw128_desc(RESB ? panel_base + it * 2 * Cfg::B_BYTES : sa + 2 * Cfg::A_BYTES);
 #pragma unroll
           for (int k = 0; k < MM_KC / 16; ++k) {
             const uint64_t adv = (uint64_t)(k * 32 >> 4);
@@ -456,11 +508,12 @@ conv_mma_persist_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __gri
           tc_commit(smem_u32(&bar_empty[s]));
         }
         tc_commit(smem_u32(&acc_full[set]));
+        if (RESB && n0_next != n0) tc_commit(smem_u32(&panel_empty));   // last tile of this panel (the producer may overwrite it)
       }
     }
   } else {
     // ------------------------------------------------------------------ epilogue warps 0-3 (TMEM lanes 32*warp .. +31)
-    float* wstage = reinterpret_cast<float*>(smem_raw + (smem_base - smem_u32(smem_raw)) + Cfg::STAGES * Cfg::STAGE_BYTES) + warp * 32 * Cfg::EPI_LD;
+    float* wstage = reinterpret_cast<float*>(smem_raw + (smem_base - smem_u32(smem_raw)) + Cfg::STAGES * Cfg::STAGE_BYTES + Cfg::PANEL_BYTES) + warp * 32 * Cfg::EPI_LD;
     const int cl = lane & 7, rsub = lane >> 3;
     const bool st1 = p.stats != nullptr, st2 = p.out2 != nullptr && p.stats2 != nullptr;
     constexpr int NCH = BN / 32;
@@ -475,15 +528,19 @@ conv_mma_persist_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __gri
       if (threadIdx.x < BN) {
         if (st1) {
           double* st = p.stats + ((size_t)stats_img * p.ld_stats + stats_n0 + threadIdx.x) * 2;
-          atomicAdd(st, (double)s_sum[threadIdx.x]);
-          atomicAdd(st + 1, (double)s_sq[threadIdx.x]);
-          s_sum[threadIdx.x] = 0.f; s_sq[threadIdx.x] = 0.f;
+          const int c = threadIdx.x;
+          atomicAdd(st, (double)((s_sum[0][c] + s_sum[1][c]) + (s_sum[2][c] + s_sum[3][c])));
+          atomicAdd(st + 1, (double)((s_sq[0][c] + s_sq[1][c]) + (s_sq[2][c] + s_sq[3][c])));
+#pragma unroll
+          for (int w = 0; w < 4; ++w) { s_sum[w][c] = 0.f; s_sq[w][c] = 0.f; }
         }
         if (st2) {
           double* st = p.stats2 + ((size_t)stats_img * p.ld_stats2 + stats_n0 + threadIdx.x) * 2;
-          atomicAdd(st, (double)s_sum2[threadIdx.x]);
-          atomicAdd(st + 1, (double)s_sq2[threadIdx.x]);
-          s_sum2[threadIdx.x] = 0.f; s_sq2[threadIdx.x] = 0.f;
+          const int c = threadIdx.x;
+          atomicAdd(st, (double)((s_sum2[0][c] + s_sum2[1][c]) + (s_sum2[2][c] + s_sum2[3][c])));
+          atomicAdd(st + 1, (double)((s_sq2[0][c] + s_sq2[1][c]) + (s_sq2[2][c] + s_sq2[3][c])));
+#pragma unroll
+          for (int w = 0; w < 4; ++w) { s_sum2[w][c] = 0.f; s_sq2[w][c] = 0.f; }
         }
       }
       asm volatile("bar.sync 1, 128;" ::: "memory");
@@ -594,8 +651,10 @@ conv_mma_persist_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __gri
             q4.z += __shfl_xor_sync(0xffffffffu, q4.z, o); q4.w += __shfl_xor_sync(0xffffffffu, q4.w, o);
           }
           if (rsub == 0) {
-            atomicAdd(&s_sum[cc + 0], s4.x); atomicAdd(&s_sum[cc + 1], s4.y); atomicAdd(&s_sum[cc + 2], s4.z); atomicAdd(&s_sum[cc + 3], s4.w);
-            atomicAdd(&s_sq[cc + 0], q4.x); atomicAdd(&s_sq[cc + 1], q4.y); atomicAdd(&s_sq[cc + 2], q4.z); atomicAdd(&s_sq[cc + 3], q4.w);
+            float4 a = *reinterpret_cast<float4*>(&s_sum[warp][cc]), bq = *reinterpret_cast<float4*>(&s_sq[warp][cc]);
+            a.x += s4.x; a.y += s4.y; a.z += s4.z; a.w += s4.w;
+            bq.x += q4.x; bq.y += q4.y; bq.z += q4.z; bq.w += q4.w;
+            *reinterpret_cast<float4*>(&s_sum[warp][cc]) = a; *reinterpret_cast<float4*>(&s_sq[warp][cc]) = bq;
           }
         }
         if (st2) {
@@ -607,8 +666,10 @@ conv_mma_persist_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __gri
             u4.z += __shfl_xor_sync(0xffffffffu, u4.z, o); u4.w += __shfl_xor_sync(0xffffffffu, u4.w, o);
           }
           if (rsub == 0) {
-            atomicAdd(&s_sum2[cc + 0], t4.x); atomicAdd(&s_sum2[cc + 1], t4.y); atomicAdd(&s_sum2[cc + 2], t4.z); atomicAdd(&s_sum2[cc + 3], t4.w);
-            atomicAdd(&s_sq2[cc + 0], u4.x); atomicAdd(&s_sq2[cc + 1], u4.y); atomicAdd(&s_sq2[cc + 2], u4.z); atomicAdd(&s_sq2[cc + 3], u4.w);
+            float4 a = *reinterpret_cast<float4*>(&s_sum2[warp][cc]), bq = *reinterpret_cast<float4*>(&s_sq2[warp][cc]);
+            a.x += t4.x; a.y += t4.y; a.z += t4.z; a.w += t4.w;
+            bq.x += u4.x; bq.y += u4.y; bq.z += u4.z; bq.w += u4.w;
+            *reinterpret_cast<float4*>(&s_sum2[warp][cc]) = a; *reinterpret_cast<float4*>(&s_sq2[warp][cc]) = bq;
           }
         }
       }
@@ -810,20 +871,24 @@ static int num_sms() {
   return n;
 }
 
-template <int BN>
+template <int BN, bool RESB>
 static int launch_conv_persist(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi, const CUtensorMap& b_lo,
                                const ConvMmaParams& p, dim3 grid, cudaStream_t stream) {
-  using Cfg = PersistCfg<BN>;
+  using Cfg = PersistCfg<BN, RESB>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_mma_persist_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(conv_mma_persist_kernel<BN, RESB>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return cuda_fail(e, "conv_mma_persist smem attr");
     attr_set = true;
   }
   const int tiles_per_img = (int)grid.x, n_tiles_n = (int)grid.z;
   const int total = tiles_per_img * (int)grid.y * n_tiles_n;
-  const int ctas = total < num_sms() ? total : num_sms();
-  conv_mma_persist_kernel<BN><<<ctas, MM_THREADS, Cfg::SMEM_BYTES, stream>>>(a_hi, a_lo, b_hi, b_lo, p, tiles_per_img, n_tiles_n, total);
+  // VT_CONV_MAX_CTAS caps the persistent grid (experiments with a second stream: leave SMs to concurrent HBM-bound kernels)
+  static int max_ctas = -1;
+  if (max_ctas < 0) { const char* e = getenv("VT_CONV_MAX_CTAS"); max_ctas = e && atoi(e) > 0 ? atoi(e) : num_sms(); }
+  const int cap = max_ctas < num_sms() ? max_ctas : num_sms();
+  const int ctas = total < cap ? total : cap;
+  conv_mma_persist_kernel<BN, RESB><<<ctas, MM_THREADS, Cfg::SMEM_BYTES, stream>>>(a_hi, a_lo, b_hi, b_lo, p, tiles_per_img, n_tiles_n, total);
   VT_CHECK_LAUNCH("vt_conv_mma(persistent)");
   return 0;
 }
@@ -897,6 +962,10 @@ int vt_conv_mma_dual(const void* a_hi, const void* a_lo, int n_img, int H, int W
   p.H = H; p.W = W; p.pad = pad; p.ks = ks; p.kchunks = Cin_pad / MM_KC;
   p.bw = bw; p.bh = bh; p.tiles_x = W / bw; p.cout_total = Cout;
   p.bw_shift = 0; while ((1 << p.bw_shift) < bw) ++p.bw_shift;
+  {
+    const char* pf = getenv("VT_CONV_PREFETCH");       // tiles of L2 prefetch distance for the HBM-streaming shapes; default off: measured 5-25 % SLOWER on B200 (profiles/r01k_*)
+    p.prefetch = (ks == 1 || p.kchunks == 1) ? (pf ? atoi(pf) : 0) : 0;
+  }
   p.bias = bias; p.res = res; p.ldr = ldr; p.out = out; p.ldo = ldo; p.stats = stats; p.ld_stats = ld_stats;
   p.out2 = out2; p.ldo2 = ldo2; p.res2 = res2; p.ldr2 = ldr2; p.stats2 = stats2; p.ld_stats2 = ld_stats2;
   dim3 grid((H / bh) * (W / bw), n_img, Cout / BN);
@@ -912,9 +981,15 @@ int vt_conv_mma_dual(const void* a_hi, const void* a_lo, int n_img, int H, int W
   // default: persistent kernel (overlapped epilogue, merged N = 2*BN MMA); VT_CONV_PERSIST=0 selects the one-tile-per-CTA kernel
   const char* persist_e = getenv("VT_CONV_PERSIST");
   if (!persist_e || atoi(persist_e) != 0) {
-    if (BN == 128) return launch_conv_persist<128>(ma_hi, ma_lo, mb_hi, mb_lo, p, grid, s);
-    if (BN == 64) return launch_conv_persist<64>(ma_hi, ma_lo, mb_hi, mb_lo, p, grid, s);
-    return launch_conv_persist<32>(ma_hi, ma_lo, mb_hi, mb_lo, p, grid, s);
+    // 1x1 convolutions with Cin <= 256 keep the weight panel of a Cout tile resident in shared memory (VT_CONV_PERSIST=2 disables)
+    if (ks == 1 && p.kchunks <= 4 && !(persist_e && atoi(persist_e) == 2)) {
+      if (BN == 128) return launch_conv_persist<128, true>(ma_hi, ma_lo, mb_hi, mb_lo, p, grid, s);
+      if (BN == 64) return launch_conv_persist<64, true>(ma_hi, ma_lo, mb_hi, mb_lo, p, grid, s);
+      return launch_conv_persist<32, true>(ma_hi, ma_lo, mb_hi, mb_lo, p, grid, s);
+    }
+    if (BN == 128) return launch_conv_persist<128, false>(ma_hi, ma_lo, mb_hi, mb_lo, p, grid, s);
+    if (BN == 64) return launch_conv_persist<64, false>(ma_hi, ma_lo, mb_hi, mb_lo, p, grid, s);
+    return launch_conv_persist<32, false>(ma_hi, ma_lo, mb_hi, mb_lo, p, grid, s);
   }
   if (BN == 128) return launch_conv_mma<128>(ma_hi, ma_lo, mb_hi, mb_lo, p, grid, s);
   if (BN == 64) return launch_conv_mma<64>(ma_hi, ma_lo, mb_hi, mb_lo, p, grid, s);

@@ -145,7 +145,32 @@ class CHORETriplaneVisibility:
             raise RuntimeError("load_state_dict() must be called before filter()")
         images = images.to(self.device, torch.float32).contiguous()
         with torch.cuda.device(self.device):
-            if self.filter_streams > 1:
+            if self.filter_streams >= 4:
+                # experiment: RGB encoder + the three triplane views as four independent n = B chains on four streams, so that the
+                # HBM-bound passes of one chain overlap the tensor-bound convolutions of the others
+                import copy
+                main = torch.cuda.current_stream()
+                if self._side_stream is None:
+                    self._side_stream = [torch.cuda.Stream(device=self.device) for _ in range(3)]
+                    self._tri_views = []
+                    for _ in range(3):
+                        e = copy.copy(self._tri)
+                        e.arena, e.overflow = None, torch.zeros(1, dtype=torch.int32, device=self.device)
+                        self._tri_views.append(e)
+                outs = []
+                for v, (st, enc) in enumerate(zip(self._side_stream, self._tri_views)):
+                    st.wait_stream(main)
+                    with torch.cuda.stream(st):
+                        outs.append(enc.forward(images, 5 + v, 1))
+                im_feat, tmpx = self._rgb.forward(images, 0, 1)
+                for st in self._side_stream:
+                    main.wait_stream(st)
+                for o in outs:                              # allocated on a side stream, consumed on the caller's stream
+                    o[0].record_stream(main); o[1].record_stream(main)
+                tri_feat = torch.cat([o[0] for o in outs], 0)
+                tri_tmpx = torch.cat([o[1] for o in outs], 0)
+                self._tri.launches = sum(e.launches for e in self._tri_views)
+            elif self.filter_streams > 1:
                 # the RGB encoder (n = B) and the shared triplane encoder (n = 3B) are independent until query(): run them on two
                 # streams so the small-map layers of one fill the SMs the other leaves idle and HBM-bound passes overlap MMA-bound ones
                 main = torch.cuda.current_stream()
@@ -169,6 +194,8 @@ class CHORETriplaneVisibility:
     def check(self):
         self._rgb.check_overflow()
         self._tri.check_overflow()
+        for e in getattr(self, "_tri_views", []):
+            e.check_overflow()
         if int(self._q_overflow.item()) != 0:
             self._q_overflow.zero_()
             raise RuntimeError("a feature / activation exceeded the fp16 range in the tensor-core decoder path")
