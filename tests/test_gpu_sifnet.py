@@ -203,3 +203,23 @@ def test_tensor_core_projection_step_matches_cuda_core_step(net):
         step_tc, step_cc = (new_tc - points.cuda()).cpu(), (new_cc - points.cuda()).cpu()
         err = (step_tc - step_cc).abs().max(-1).values / step_cc.abs().max()
         assert float((err < 1e-3).float().mean()) > 0.97
+
+
+def test_graph_replay_matches_eager_filter(net):
+    """filter() replays a CUDA graph captured on the first call of a shape; a later call with other images must give what an eager
+    pass gives for THOSE images (statistics are summed with fp64 atomics, so equality is to fp32 rounding through ~100 layers, not bitwise)."""
+    assert net.use_graph
+    a, *_ = synthetic_frames(2, size=64, seed=71, n_points=4)
+    b, *_ = synthetic_frames(2, size=64, seed=72, n_points=4)
+    net.filter(a.cuda())                       # capture (or reuse) on images a
+    net.filter(b.cuda())                       # replay on images b
+    got = [t.clone() for t in net._maps]
+    net.use_graph = False
+    try:
+        net.filter(b.cuda())
+        ref = [t.clone() for t in net._maps]
+    finally:
+        net.use_graph = True
+    for g, r in zip(got, ref):
+        assert rel_err(g.cpu(), r.cpu()) < 1e-5
+    assert rel_err(got[0].cpu(), net.im_feat_list[0].permute(0, 2, 3, 1).cpu()) < 1e-5

@@ -52,6 +52,7 @@ def spy(self, op, name, out, bias=None, res=None, stats=None, out2=None, res2=No
 
 
 E.HGEncoder._conv = spy
+net.use_graph = False
 net.filter(images.to(dev))
 torch.cuda.synchronize()
 E.HGEncoder._conv = orig
