@@ -112,6 +112,13 @@ int vt_query_fwd_tc(const float* points, const float* crop_center, const float* 
                     const float* wpack, const void* w1_hi, const void* w1_lo, const void* w23_hi, const void* w23_lo, float* out,
                     float* xy_out, int* overflow, void* stream);
 
+/* vt_query_fwd_tc restricted to the heads in head_mask (bit 0 df, 1 pca, 2 parts, 3 centers, 4 visibility): rows of `out` that belong
+ * to other heads are left untouched.  One feature-gather pass serves up to four heads, so e.g. {df, centers} costs ~1/3 of all five. */
+int vt_query_fwd_tc_heads(const float* points, const float* crop_center, const float* body_center, int B, int N, const float* im_feat,
+                          const float* tmpx, const float* tri_tmpx, const float* tri_feat, int Hf, int Wf, int Ht, int Wt, const float* cam7,
+                          const float* wpack, const void* w1_hi, const void* w1_lo, const void* w23_hi, const void* w23_lo, int head_mask,
+                          float* out, float* xy_out, int* overflow, void* stream);
+
 /* Gradient of sum(g_out * out) w.r.t. the points -- what autograd computes for `df.sum().backward()` in
  * Generator.approx_surface (recon/gen/generator.py:86-96) and for the df / part / centre losses of the fitters
  * (recon/recon_fit_behave.py:467-513, recon/recon_fit_trivis_full.py:193-270).  The forward is recomputed on chip.
@@ -152,6 +159,18 @@ int vt_query_project_step_tc(const float* points, const float* crop_center, cons
                              const float* cam7, const float* wpack, const void* w1_hi, const void* w1_lo, const void* w23_hi,
                              const void* w23_lo, const void* w23t_hi, const void* w23t_lo, const void* w1t_hi, const void* w1t_lo,
                              int df_idx, float threshold, float* points_out, float* g_points, int* overflow, void* stream);
+
+/* The two query-dependent loss terms of the fitters, fused: values AND point gradients in ONE launch (no separate forward, no [B,29,N]
+ * round trip).  vals_df[B][N] = clamp(df[df_idx], max=clamp_max) -- `torch.clamp(df_pred[:, 0:1], max=0.1)` of forward_smpl
+ * (recon/recon_fit_behave.py:471) and `torch.clamp(df_pred[:, 1], max=0.8)` of forward_step (recon/recon_fit_trivis_full.py:235) --
+ * with g_df[B][N][3] = d vals_df / d point; when part_labels[B][N] (int64) is given, vals_ce[B][N] = F.cross_entropy(parts, labels,
+ * reduction='none') (recon_fit_behave.py:476) with g_ce[B][N][3] = d vals_ce / d point.  Reductions and loss weights are linear in these
+ * and stay with the caller. */
+int vt_query_losses_tc(const float* points, const float* crop_center, const float* body_center, int B, int N, const float* im_feat,
+                       const float* tmpx, const float* tri_tmpx, const float* tri_feat, int Hf, int Wf, int Ht, int Wt, const float* cam7,
+                       const float* wpack, const void* w1_hi, const void* w1_lo, const void* w23_hi, const void* w23_lo, const void* w23t_hi,
+                       const void* w23t_lo, const void* w1t_hi, const void* w1t_lo, int df_idx, float clamp_max, const long long* part_labels,
+                       float* vals_df, float* g_df, float* vals_ce, float* g_ce, int* overflow, void* stream);
 
 /* ---- SMPL-H layer: SMPL_Layer.forward (lib_smpl/smplpytorch/smplpytorch/pytorch/smpl_layer.py:73-176) and its gradient
  *      w.r.t. pose / betas / trans; landmark regressors (lib_smpl/torch_functions.py:52-76, wrapper_pytorch.py:187-203) ---- */

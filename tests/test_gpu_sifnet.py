@@ -223,3 +223,47 @@ def test_graph_replay_matches_eager_filter(net):
     for g, r in zip(got, ref):
         assert rel_err(g.cpu(), r.cpu()) < 1e-5
     assert rel_err(got[0].cpu(), net.im_feat_list[0].permute(0, 2, 3, 1).cpu()) < 1e-5
+
+
+@pytest.mark.parametrize("df_channel,clamp_max,with_parts", [(0, 0.1, True), (1, 0.8, False), (0, 2.0, True)])
+def test_fused_fitting_losses_match_query_plus_autograd(net, df_channel, clamp_max, with_parts):
+    """vt_query_losses_tc (values + point gradients in one launch) against query() + torch.clamp / F.cross_entropy + autograd on the
+    fp32 CUDA-core kernels, with per-frame weights on the distance term as forward_step applies them."""
+    B, N = 2, 419
+    images, points, crop, body = synthetic_frames(B, size=64, seed=81, n_points=N, jitter=True)
+    net.filter(images.cuda())
+    labels = torch.randint(0, 14, (B, N), generator=torch.Generator().manual_seed(5)).cuda() if with_parts else None
+    w = torch.tensor([0.3, 1.7]).cuda()
+
+    def total(vals_df, vals_ce):
+        t = (vals_df.mean(-1) * w).mean()
+        return t + (0.01 * vals_ce.sum(-1).mean() if vals_ce is not None else 0.0)
+
+    res = {}
+    for cuda_cores in (False, True):
+        net.query_on_cuda_cores = cuda_cores
+        try:
+            pts = points.cuda().requires_grad_(True)
+            vals_df, vals_ce = net.query_losses(pts, crop_center=crop.cuda(), body_center=body.cuda(), df_channel=df_channel,
+                                                clamp_max=clamp_max, part_labels=labels)
+            total(vals_df, vals_ce).backward()
+            res[cuda_cores] = (vals_df.detach().cpu(), None if vals_ce is None else vals_ce.detach().cpu(), pts.grad.cpu())
+        finally:
+            net.query_on_cuda_cores = False
+    net.check()
+    assert rel_err(res[False][0], res[True][0]) < 2e-5
+    if with_parts:
+        assert rel_err(res[False][1], res[True][1]) < 2e-5
+    assert float(res[True][2].abs().max()) > 0
+    assert rel_err(res[False][2], res[True][2]) < 5e-5
+
+
+def test_query_heads_subset_matches_full_query(net):
+    images, points, crop, body = synthetic_frames(2, size=64, seed=91, n_points=300, jitter=True)
+    net.filter(images.cuda())
+    net.query(points.cuda(), crop_center=crop.cuda(), body_center=body.cuda())
+    full = dict(zip(("df", "pca", "parts", "centers", "visibility"), net.get_preds()))
+    for heads in (("centers",), ("df", "parts"), ("visibility", "pca", "df", "centers", "parts")):
+        sub = net.query_heads(points.cuda(), heads, crop_center=crop.cuda(), body_center=body.cuda())
+        for h in heads:
+            assert torch.equal(sub[h], full[h]), h

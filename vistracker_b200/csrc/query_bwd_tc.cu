@@ -27,10 +27,16 @@ constexpr int TB_SMEM = 2 * TQ_SLOT /*features | gf staging*/ + TQ_NW * TQ_SLOT 
 
 struct TbParams {
   const float* g_out;      // [B][29][N] cotangent (mode 0)
-  float* g_points;         // [B][N][3] (optional in mode 1)
+  float* g_points;         // [B][N][3] (optional in mode 1; mode 2: d clamp(df) / d point)
   float* points_out;       // [B][N][3] (mode 1)
   int mode, df_idx, head_mask;
-  float threshold;
+  float threshold;         // clamp maximum of the distance term (modes 1 and 2)
+  // mode 2 (fused fitting losses, recon_fit_behave.py:471-476 / recon_fit_trivis_full.py:226-235): per-point loss values and the
+  // gradient of each term w.r.t. its point with a unit cotangent; the caller applies the reduction weights (the map is linear)
+  const long long* labels; // [B][N] part labels or null (no cross-entropy term)
+  float* vals_df;          // [B][N] clamp(df[df_idx], max=threshold)
+  float* vals_ce;          // [B][N] cross-entropy of the 14 part logits against labels
+  float* g_points2;        // [B][N][3] d CE / d point
 };
 
 // tap of feature k (multiple of 4) of chunk c for the point with projections q; `direct` marks the (x, y, z - z0) lane of chunk 9
@@ -96,7 +102,7 @@ query_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_c
   uint8_t* act_ptr = smem_al + 2 * TQ_SLOT + TQ_NW * TQ_SLOT;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.y, n0 = blockIdx.x * TQ_M;
-  const int heads = prm.mode == 1 ? 1 : prm.head_mask;
+  const int heads = prm.mode == 1 ? 1 : prm.mode == 2 ? (prm.labels ? 5 : 1) : prm.head_mask;
 
   if (warp == 5 && lane == 0) {
     for (int s = 0; s < 2; ++s) {
@@ -278,10 +284,22 @@ query_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_c
         __syncwarp();
         if (lane == 0) tq_mbar_arrive(tq_smem_u32(&stg_empty[slot]));
       }
+      if (prm.mode == 2) {        // one gradient tensor per loss term: write this head's and start the next from zero
+        __syncwarp();
+        if (lane < PW) {
+          const int pp = gw * PW + lane, n = n0 + pp;
+          if (n < N) {
+            float* gp = (h == 0 ? prm.g_points : prm.g_points2) + ((size_t)b * N + n) * 3;
+            gp[0] = s_gacc[pp][0]; gp[1] = s_gacc[pp][1]; gp[2] = s_gacc[pp][2];
+          }
+          s_gacc[pp][0] = 0.f; s_gacc[pp][1] = 0.f; s_gacc[pp][2] = 0.f;
+        }
+        __syncwarp();
+      }
     }
     // ---- write the point gradients / the projected points (one lane per point)
     __syncwarp();
-    if (lane < PW) {
+    if (prm.mode != 2 && lane < PW) {
       const int pp = gw * PW + lane, n = n0 + pp;
       if (n < N) {
         const float gx = s_gacc[pp][0], gy = s_gacc[pp][1], gz = s_gacc[pp][2];
@@ -458,14 +476,36 @@ query_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_c
           if (prm.mode == 0) {
             g = prm.g_out[((size_t)b * 29 + hoff + c) * N + n];
             if (h == 4) g *= val * (1.f - val);
-          } else if (c == prm.df_idx) {
+          } else if (h == 0 && c == prm.df_idx) {
             g = val <= prm.threshold ? 1.f : 0.f;
             s_dfc[r] = fminf(val, prm.threshold);
+            if (prm.mode == 2) prm.vals_df[(size_t)b * N + n] = fminf(val, prm.threshold);
+          } else if (h == 2) {
+            g = val;                                       // mode 2: keep the logit, turned into softmax - onehot below
           }
           if (h == 0 && !s_in_img[r]) g = 0.f;
         }
         g4[c] = g;
         gmax = fmaxf(gmax, fabsf(g));
+      }
+      if (prm.mode == 2 && h == 2) {                       // F.cross_entropy(parts, labels, reduction='none') and its logit gradient
+        gmax = 0.f;
+        if (n < N) {
+          const int lab = (int)prm.labels[(size_t)b * N + n];
+          float mx = g4[0];
+#pragma unroll
+          for (int c = 1; c < 14; ++c) mx = fmaxf(mx, g4[c]);
+          float sum = 0.f, l_lab = 0.f;
+#pragma unroll
+          for (int c = 0; c < 14; ++c) { if (c == lab) l_lab = g4[c]; g4[c] = expf(g4[c] - mx); sum += g4[c]; }
+          prm.vals_ce[(size_t)b * N + n] = logf(sum) - (l_lab - mx);
+          const float inv_sum = 1.f / sum;
+#pragma unroll
+          for (int c = 0; c < 14; ++c) { g4[c] = g4[c] * inv_sum - (c == lab ? 1.f : 0.f); gmax = fmaxf(gmax, fabsf(g4[c])); }
+        } else {
+#pragma unroll
+          for (int c = 0; c < 14; ++c) g4[c] = 0.f;
+        }
       }
       int e_total = tb_norm_exp(gmax);
       {
@@ -596,7 +636,7 @@ int vt_query_bwd_tc(const float* points, const float* crop_center, const float* 
   if (B <= 0 || N <= 0) return 0;
   if (head_mask == 0) return cudaMemsetAsync(g_points, 0, (size_t)B * N * 3 * sizeof(float), (cudaStream_t)stream) == cudaSuccess ? 0 : -3;
   const void* planes[8] = {w1_hi, w1_lo, w23_hi, w23_lo, w23t_hi, w23t_lo, w1t_hi, w1t_lo};
-  TbParams prm{g_out, g_points, nullptr, 0, 0, head_mask, 0.f};
+  TbParams prm{g_out, g_points, nullptr, 0, 0, head_mask, 0.f, nullptr, nullptr, nullptr, nullptr};
   return launch_bwd_tc(points, crop_center, body_center, B, N, im_feat, tmpx, tri_tmpx, tri_feat, Hf, Wf, Ht, Wt, cam7, wpack, planes, prm,
                        overflow, (cudaStream_t)stream, "vt_query_bwd_tc");
 }
@@ -610,9 +650,24 @@ int vt_query_project_step_tc(const float* points, const float* crop_center, cons
   VT_CHECK_ARG(points_out != nullptr && overflow != nullptr, "vt_query_project_step_tc: points_out and overflow are required");
   if (B <= 0 || N <= 0) return 0;
   const void* planes[8] = {w1_hi, w1_lo, w23_hi, w23_lo, w23t_hi, w23t_lo, w1t_hi, w1t_lo};
-  TbParams prm{nullptr, g_points, points_out, 1, df_idx, 1, threshold};
+  TbParams prm{nullptr, g_points, points_out, 1, df_idx, 1, threshold, nullptr, nullptr, nullptr, nullptr};
   return launch_bwd_tc(points, crop_center, body_center, B, N, im_feat, tmpx, tri_tmpx, tri_feat, Hf, Wf, Ht, Wt, cam7, wpack, planes, prm,
                        overflow, (cudaStream_t)stream, "vt_query_project_step_tc");
+}
+
+int vt_query_losses_tc(const float* points, const float* crop_center, const float* body_center, int B, int N, const float* im_feat,
+                       const float* tmpx, const float* tri_tmpx, const float* tri_feat, int Hf, int Wf, int Ht, int Wt, const float* cam7,
+                       const float* wpack, const void* w1_hi, const void* w1_lo, const void* w23_hi, const void* w23_lo, const void* w23t_hi,
+                       const void* w23t_lo, const void* w1t_hi, const void* w1t_lo, int df_idx, float clamp_max, const long long* part_labels,
+                       float* vals_df, float* g_df, float* vals_ce, float* g_ce, int* overflow, void* stream) {
+  VT_CHECK_ARG(df_idx == 0 || df_idx == 1, "vt_query_losses_tc: df_idx %d (0 human, 1 object)", df_idx);
+  VT_CHECK_ARG(vals_df != nullptr && g_df != nullptr && overflow != nullptr, "vt_query_losses_tc: vals_df, g_df and overflow are required");
+  VT_CHECK_ARG(part_labels == nullptr || (vals_ce != nullptr && g_ce != nullptr), "vt_query_losses_tc: part_labels need vals_ce and g_ce");
+  if (B <= 0 || N <= 0) return 0;
+  const void* planes[8] = {w1_hi, w1_lo, w23_hi, w23_lo, w23t_hi, w23t_lo, w1t_hi, w1t_lo};
+  TbParams prm{nullptr, g_df, nullptr, 2, df_idx, 0, clamp_max, part_labels, vals_df, vals_ce, g_ce};
+  return launch_bwd_tc(points, crop_center, body_center, B, N, im_feat, tmpx, tri_tmpx, tri_feat, Hf, Wf, Ht, Wt, cam7, wpack, planes, prm,
+                       overflow, (cudaStream_t)stream, "vt_query_losses_tc");
 }
 
 }  // extern "C"

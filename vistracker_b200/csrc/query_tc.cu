@@ -27,7 +27,7 @@ query_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_c
                     const __grid_constant__ CUtensorMap tm_w23_hi, const __grid_constant__ CUtensorMap tm_w23_lo,
                     const float* __restrict__ points, const float* __restrict__ crop_center, const float* __restrict__ body_center,
                     int B, int N, TqMaps m, TqCam cam, const float* __restrict__ wpack /*fp32 pack of query.cu: biases + W4*/,
-                    int wpack_head_stride, float* __restrict__ out, float* __restrict__ xy_out, int* __restrict__ overflow) {
+                    int wpack_head_stride, float* __restrict__ out, float* __restrict__ xy_out, int* __restrict__ overflow, int head_mask) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t feat_full[TQ_NF], feat_empty[TQ_NF], w_full[TQ_NW], w_empty[TQ_NW], acc_full, act_full;
   __shared__ uint32_t s_tmem_base;
@@ -44,6 +44,10 @@ query_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_c
   uint8_t* act_ptr = smem_al + TQ_NF * TQ_SLOT + TQ_NW * TQ_SLOT;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.y, n0 = blockIdx.x * TQ_M;
+  // active heads (bit h of head_mask), four per pass: the g-th head of pass p is the (4p+g+1)-th set bit
+  const int n_heads = __popc((unsigned)head_mask), n_pass = (n_heads + 3) >> 2;
+  auto pass_heads = [&](int pass) { return min(4, n_heads - 4 * pass); };
+  auto head_of = [&](int pass, int g) { return (int)__fns((unsigned)head_mask, 0, 4 * pass + g + 1); };
 
   if (warp == 5 && lane == 0) {
     for (int s = 0; s < TQ_NF; ++s) { tq_mbar_init(tq_smem_u32(&feat_full[s]), TQ_GATHER_WARPS); tq_mbar_init(tq_smem_u32(&feat_empty[s]), 1); }
@@ -95,7 +99,7 @@ query_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_c
     const int gw = warp - 6;
     int it = 0;
     float amax = 0.f;
-    for (int pass = 0; pass < 2; ++pass) {
+    for (int pass = 0; pass < n_pass; ++pass) {
       for (int c = 0; c < TQ_NCHUNK; ++c, ++it) {
         const int slot = it % TQ_NF;
         tq_mbar_wait(tq_smem_u32(&feat_empty[slot]), ((uint32_t)(it / TQ_NF) & 1u) ^ 1u);
@@ -178,13 +182,13 @@ query_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_c
         tq_tma_2d(w_base + s * TQ_SLOT + TQ_PLANE, lo, full, col, row);
         ++iw;
       };
-      for (int pass = 0; pass < 2; ++pass) {
-        const int h0 = pass == 0 ? 0 : 4, nh = pass == 0 ? 4 : 1;
+      for (int pass = 0; pass < n_pass; ++pass) {
+        const int nh = pass_heads(pass);
         for (int c = 0; c < TQ_NCHUNK; ++c)
-          for (int g = 0; g < nh; ++g) load(&tm_w1_hi, &tm_w1_lo, c * TQ_KC, (h0 + g) * TQ_H);
+          for (int g = 0; g < nh; ++g) load(&tm_w1_hi, &tm_w1_lo, c * TQ_KC, head_of(pass, g) * TQ_H);
         for (int g = 0; g < nh; ++g)
           for (int layer = 0; layer < 2; ++layer)
-            for (int kc = 0; kc < 2; ++kc) load(&tm_w23_hi, &tm_w23_lo, kc * TQ_KC, (layer * 5 + h0 + g) * TQ_H);
+            for (int kc = 0; kc < 2; ++kc) load(&tm_w23_hi, &tm_w23_lo, kc * TQ_KC, (layer * 5 + head_of(pass, g)) * TQ_H);
       }
     }
   } else if (warp == 5) {
@@ -207,8 +211,8 @@ query_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_c
         tq_commit(tq_smem_u32(&w_empty[s]));
         ++iw;
       };
-      for (int pass = 0; pass < 2; ++pass) {
-        const int nh = pass == 0 ? 4 : 1;
+      for (int pass = 0; pass < n_pass; ++pass) {
+        const int nh = pass_heads(pass);
         for (int c = 0; c < TQ_NCHUNK; ++c, ++it) {
           const int slot = it % TQ_NF;
           tq_mbar_wait(tq_smem_u32(&feat_full[slot]), (uint32_t)(it / TQ_NF) & 1u);
@@ -232,12 +236,12 @@ query_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_c
     const uint32_t lane_base = tmem_base + ((uint32_t)(warp * 32) << 16);
     int iacc = 0;
     float amax = 0.f;
-    for (int pass = 0; pass < 2; ++pass) {
-      const int h0 = pass == 0 ? 0 : 4, nh = pass == 0 ? 4 : 1;
+    for (int pass = 0; pass < n_pass; ++pass) {
+      const int nh = pass_heads(pass);
       tq_mbar_wait(tq_smem_u32(&acc_full), (uint32_t)iacc & 1u); ++iacc;            // layer 1 done
       tq_fence_after();
       for (int g = 0; g < nh; ++g) {
-        const int h = h0 + g;
+        const int h = head_of(pass, g);
         const float* hw = wpack + (size_t)h * wpack_head_stride;
         const float* b1 = hw + 616 * 128;
         const float* b2 = b1 + 128 + 128 * 128;
@@ -333,6 +337,15 @@ int vt_query_fwd_tc(const float* points, const float* crop_center, const float* 
                     const float* tmpx, const float* tri_tmpx, const float* tri_feat, int Hf, int Wf, int Ht, int Wt, const float* cam7,
                     const float* wpack, const void* w1_hi, const void* w1_lo, const void* w23_hi, const void* w23_lo, float* out,
                     float* xy_out, int* overflow, void* stream) {
+  return vt_query_fwd_tc_heads(points, crop_center, body_center, B, N, im_feat, tmpx, tri_tmpx, tri_feat, Hf, Wf, Ht, Wt, cam7, wpack, w1_hi,
+                               w1_lo, w23_hi, w23_lo, 31, out, xy_out, overflow, stream);
+}
+
+int vt_query_fwd_tc_heads(const float* points, const float* crop_center, const float* body_center, int B, int N, const float* im_feat,
+                          const float* tmpx, const float* tri_tmpx, const float* tri_feat, int Hf, int Wf, int Ht, int Wt, const float* cam7,
+                          const float* wpack, const void* w1_hi, const void* w1_lo, const void* w23_hi, const void* w23_lo, int head_mask,
+                          float* out, float* xy_out, int* overflow, void* stream) {
+  VT_CHECK_ARG(head_mask > 0 && head_mask < 32, "vt_query_fwd_tc_heads: head mask %d", head_mask);
   if (B <= 0 || N <= 0) return 0;
   CUtensorMap m1h, m1l, m2h, m2l;
   int rc;
@@ -347,7 +360,7 @@ int vt_query_fwd_tc(const float* points, const float* crop_center, const float* 
   dim3 grid(ceil_div(N, TQ_M), B);
   const int head_stride = 616 * 128 + 128 + 2 * (128 * 128 + 128) + 128 * 16 + 16;
   query_fwd_tc_kernel<<<grid, TQ_THREADS, TQ_SMEM, (cudaStream_t)stream>>>(m1h, m1l, m2h, m2l, points, crop_center, body_center, B, N, m, cam,
-                                                                          wpack, head_stride, out, xy_out, overflow);
+                                                                          wpack, head_stride, out, xy_out, overflow, head_mask);
   VT_CHECK_LAUNCH("vt_query_fwd_tc");
   return 0;
 }

@@ -117,12 +117,14 @@ class ReconFitterTriVisFull:
         """recon_fit_behave.py:467-513 with the tri-vis overrides (no smplz term; stemp from trivis_full.py:170-177)."""
         loss_dict = {}
         smpl_verts, _, _, _ = smpl()
-        self.model.query(smpl_verts, **data_dict["query_dict"])
-        df_pred, _, parts_pred, _ = self.model.get_preds()[:4]
-        loss_dict["df_h"] = torch.clamp(df_pred[:, 0:1, :], max=0.1).mean()
+        # torch.clamp(df_pred[:, 0:1], max=0.1).mean() and F.cross_entropy(parts_pred, labels, 'none').sum(-1).mean() of the reference,
+        # as per-point terms + point gradients from ONE fused launch (vt_query_losses_tc) instead of query() + autograd
+        vals_df, vals_ce = self.model.query_losses(smpl_verts, df_channel=0, clamp_max=0.1, part_labels=data_dict["part_labels"],
+                                                   **data_dict["query_dict"])
+        loss_dict["df_h"] = vals_df.mean()
         loss_dict["pose"] = torch.mean(self.priors.pose(smpl.pose))
         loss_dict["hand"] = torch.mean(self.priors.hand(smpl.pose))
-        loss_dict["part"] = F.cross_entropy(parts_pred, data_dict["part_labels"], reduction="none").sum(-1).mean()
+        loss_dict["part"] = vals_ce.sum(-1).mean()
         smpl.get_landmarks()                     # the reference runs a second SMPL forward here (smplz_loss is a no-op in tri-vis)
         loss_dict["pinit"] = torch.mean(torch.sum((smpl.pose[:, 3:SMPL_POSE_PRAMS_NUM] - data_dict["pose_init"]) ** 2, -1))
         if phase == "kpts":
@@ -220,9 +222,19 @@ class ReconFitterTriVisFull:
         loss_dict = {}
         R = decopose_axis(obj_R, noise=noise)
         object = self.transform_obj_verts(data_dict["objects"], R, obj_t, obj_s)
-        self.model.query(object, **data_dict["query_dict"])
-        preds = self.model.get_preds()
-        df_pred, centers_pred_o, part_o = preds[0], preds[3], preds[2]
+        first_joint = phase == "joint" and "df_obj_h" not in data_dict
+        if phase == "sil" or first_joint:
+            # every head is needed (sil: no distance term at all; first joint step: df_h and parts at the object points)
+            self.model.query(object, **data_dict["query_dict"])
+            preds = self.model.get_preds()
+            df_pred, centers_pred_o, part_o = preds[0], preds[3], preds[2]
+            vals_df_o = torch.clamp(df_pred[:, 1, :], max=0.8)
+        else:
+            # distance term + its gradient from the fused launch; the centre head (reported only, weight 0) forward-only
+            vals_df_o, _ = self.model.query_losses(object, df_channel=1, clamp_max=0.8, **data_dict["query_dict"])
+            with torch.no_grad():
+                centers_pred_o = self.model.query_heads(object, ("centers",), **data_dict["query_dict"])["centers"]
+            df_pred = part_o = None
         obj_center_pred = data_dict["smpl_center"] + torch.mean(centers_pred_o, -1)               # recon_fit_behave.py:370-380
         self.temporal_loss_joint(object, loss_dict, phase)
         if phase == "sil":
@@ -232,7 +244,7 @@ class ReconFitterTriVisFull:
             loss_dict["scale"] = torch.mean((obj_s - self.obj_scale) ** 2)
             loss_dict["trans"] = torch.mean((obj_t - data_dict["trans_init"]) ** 2)
         else:
-            loss_dict["object"] = (torch.mean(torch.clamp(df_pred[:, 1, :], max=0.8), -1) * data_dict["occ_ratios"]).mean()
+            loss_dict["object"] = (torch.mean(vals_df_o, -1) * data_dict["occ_ratios"]).mean()
             loss_dict["scale"] = torch.mean((obj_s - self.obj_scale) ** 2)
             # weight 0 in get_loss_weights ("no loss anymore"): the value is reported, but building its graph would drag the
             # centre head through the query backward for an identically-zero gradient
