@@ -17,6 +17,7 @@
 // Warp roles (448 threads) as in query_tc.cu: warps 0-3 epilogue (thread = point = TMEM lane), warp 4 TMA weight producer, warp 5
 // MMA issuer, warps 6-13 gather (half a warp per point, 16-byte tap loads, four point pairs in flight).
 #include "query_tc_common.cuh"
+#include <stdlib.h>
 #include "vt_internal.h"
 
 namespace vt {
@@ -37,6 +38,7 @@ struct TbParams {
   float* vals_df;          // [B][N] clamp(df[df_idx], max=threshold)
   float* vals_ce;          // [B][N] cross-entropy of the 14 part logits against labels
   float* g_points2;        // [B][N][3] d CE / d point
+  long long* trace;        // debug (VT_QUERY_TRACE=1): clock64 stamps of CTA (0,0): [0..15] epilogue thread 0, [16..31] gather warp 0
 };
 
 // tap of feature k (multiple of 4) of chunk c for the point with projections q; `direct` marks the (x, y, z - z0) lane of chunk 9
@@ -166,6 +168,10 @@ query_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_c
     __syncwarp();
     int it = 0, sc = 0;
     float amax = 0.f;
+    int trg = 16;
+    const bool tracing_g = prm.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && gw == 0 && lane == 0;
+#define TB_STAMP_G() do { if (tracing_g && trg < 32) prm.trace[trg++] = clock64(); } while (0)
+    TB_STAMP_G();
     for (int h = 0; h < 5; ++h) {
       if (!((heads >> h) & 1)) continue;
       asm volatile("bar.sync 3, 256;" ::: "memory");       // every gather warp is done reading the previous head's staging slots
@@ -217,10 +223,12 @@ query_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_c
         __syncwarp();
         if (lane == 0) tq_mbar_arrive(tq_smem_u32(&feat_full[slot]));
       }
+      TB_STAMP_G();
       // ---- backward: contract the staged feature gradients with d(feature)/d(u, v) (second gather of the same taps)
       for (int c = 0; c < TQ_NCHUNK; ++c, ++sc) {
         const int slot = sc & 1;
         tq_mbar_wait(tq_smem_u32(&stg_full[slot]), (uint32_t)(sc >> 1) & 1u);
+        if (c == 0) TB_STAMP_G();
         const uint8_t* stg = feat_ptr + slot * TQ_SLOT;
         const bool full_res = (c < 4) || (c >= 5 && c < 8);                // im_feat / tri_feat maps (Hf x Wf); else tmpx-sized maps
         const float su = 0.5f * (float)((full_res ? m.Wf : m.Wt) - 1), sv = 0.5f * (float)((full_res ? m.Hf : m.Ht) - 1);
@@ -284,6 +292,7 @@ query_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_c
         __syncwarp();
         if (lane == 0) tq_mbar_arrive(tq_smem_u32(&stg_empty[slot]));
       }
+      TB_STAMP_G();
       if (prm.mode == 2) {        // one gradient tensor per loss term: write this head's and start the next from zero
         __syncwarp();
         if (lane < PW) {
@@ -389,6 +398,10 @@ query_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_c
     const uint32_t lane_base = tmem_base + ((uint32_t)(warp * 32) << 16);
     int iacc = 0, gfi = 0, sc = 0;
     float amax = 0.f;
+    int tr = 0;
+    const bool tracing = prm.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0;
+#define TB_STAMP() do { if (tracing && tr < 16) prm.trace[tr++] = clock64(); } while (0)
+    TB_STAMP();
     // write 32 values (K index ch*32 + i of a 128-wide layer) of this point as the next MMA's A operand
     auto store_act = [&](const float (&v)[32], int ch) {
       uint8_t* dst = act_ptr + (ch >> 1) * TQ_SLOT;
@@ -460,6 +473,7 @@ query_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_c
           }
         }
         if (layer < 2) publish_act();
+        TB_STAMP();
       }
       // ---- cotangent at the head outputs, normalised per point
       float g4[14];
@@ -532,6 +546,7 @@ query_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_c
         store_act(v, ch);
       }
       publish_act();
+      TB_STAMP();
       // ---- backward epilogues EB3 (mask of layer 2), EB2 (mask of layer 1): renormalise, mask, split
 #pragma unroll 1
       for (int bl = 1; bl >= 0; --bl) {
@@ -561,6 +576,7 @@ query_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_c
         }
         if (bl == 0) s_scale_e[r] = e_total;               // read by the gather warps after the first staging chunk is published
         publish_act();
+        TB_STAMP();
       }
       // ---- drain gf (five 128-column groups) into the fp32 staging ring for the gather warps
       for (int u = 0; u < TQ_NCHUNK / 2; ++u, ++gfi) {
@@ -588,6 +604,7 @@ query_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_c
         __syncwarp();
         if (lane == 0) tq_mbar_arrive(tq_smem_u32(&gf_empty[gs]));
       }
+      TB_STAMP();
     }
     if (amax > 65504.f) atomicAdd(overflow, 1);
   }
@@ -614,9 +631,23 @@ static int launch_bwd_tc(const float* points, const float* crop_center, const fl
   if (e != cudaSuccess) return cuda_fail(e, who);
   dim3 grid(ceil_div(N, TQ_M), B);
   const int head_stride = 616 * 128 + 128 + 2 * (128 * 128 + 128) + 128 * 16 + 16;
+  TbParams prm2 = prm;
+  const bool trace = getenv("VT_QUERY_TRACE") != nullptr;       // debug only: synchronises and prints the phase stamps of CTA (0,0)
+  if (trace) { cudaMalloc(&prm2.trace, 32 * sizeof(long long)); cudaMemset(prm2.trace, 0, 32 * sizeof(long long)); }
   query_bwd_tc_kernel<<<grid, TB_THREADS, TB_SMEM, stream>>>(mp[0], mp[1], mp[2], mp[3], mp[4], mp[5], mp[6], mp[7], points, crop_center,
-                                                             body_center, B, N, m, cam, wpack, head_stride, prm, overflow);
+                                                             body_center, B, N, m, cam, wpack, head_stride, prm2, overflow);
   VT_CHECK_LAUNCH(who);
+  if (trace) {
+    long long h[32];
+    cudaDeviceSynchronize();
+    cudaMemcpy(h, prm2.trace, sizeof(h), cudaMemcpyDeviceToHost);
+    cudaFree(prm2.trace);
+    fprintf(stderr, "[%s trace, cycles since CTA start] epilogue:", who);
+    for (int i = 1; i < 16 && h[i]; ++i) fprintf(stderr, " %lld", h[i] - h[0]);
+    fprintf(stderr, " | gather:");
+    for (int i = 17; i < 32 && h[i]; ++i) fprintf(stderr, " %lld", h[i] - h[0]);
+    fprintf(stderr, "\n");
+  }
   return 0;
 }
 
@@ -636,7 +667,7 @@ int vt_query_bwd_tc(const float* points, const float* crop_center, const float* 
   if (B <= 0 || N <= 0) return 0;
   if (head_mask == 0) return cudaMemsetAsync(g_points, 0, (size_t)B * N * 3 * sizeof(float), (cudaStream_t)stream) == cudaSuccess ? 0 : -3;
   const void* planes[8] = {w1_hi, w1_lo, w23_hi, w23_lo, w23t_hi, w23t_lo, w1t_hi, w1t_lo};
-  TbParams prm{g_out, g_points, nullptr, 0, 0, head_mask, 0.f, nullptr, nullptr, nullptr, nullptr};
+  TbParams prm{g_out, g_points, nullptr, 0, 0, head_mask, 0.f, nullptr, nullptr, nullptr, nullptr, nullptr};
   return launch_bwd_tc(points, crop_center, body_center, B, N, im_feat, tmpx, tri_tmpx, tri_feat, Hf, Wf, Ht, Wt, cam7, wpack, planes, prm,
                        overflow, (cudaStream_t)stream, "vt_query_bwd_tc");
 }
@@ -650,7 +681,7 @@ int vt_query_project_step_tc(const float* points, const float* crop_center, cons
   VT_CHECK_ARG(points_out != nullptr && overflow != nullptr, "vt_query_project_step_tc: points_out and overflow are required");
   if (B <= 0 || N <= 0) return 0;
   const void* planes[8] = {w1_hi, w1_lo, w23_hi, w23_lo, w23t_hi, w23t_lo, w1t_hi, w1t_lo};
-  TbParams prm{nullptr, g_points, points_out, 1, df_idx, 1, threshold, nullptr, nullptr, nullptr, nullptr};
+  TbParams prm{nullptr, g_points, points_out, 1, df_idx, 1, threshold, nullptr, nullptr, nullptr, nullptr, nullptr};
   return launch_bwd_tc(points, crop_center, body_center, B, N, im_feat, tmpx, tri_tmpx, tri_feat, Hf, Wf, Ht, Wt, cam7, wpack, planes, prm,
                        overflow, (cudaStream_t)stream, "vt_query_project_step_tc");
 }
@@ -665,7 +696,7 @@ int vt_query_losses_tc(const float* points, const float* crop_center, const floa
   VT_CHECK_ARG(part_labels == nullptr || (vals_ce != nullptr && g_ce != nullptr), "vt_query_losses_tc: part_labels need vals_ce and g_ce");
   if (B <= 0 || N <= 0) return 0;
   const void* planes[8] = {w1_hi, w1_lo, w23_hi, w23_lo, w23t_hi, w23t_lo, w1t_hi, w1t_lo};
-  TbParams prm{nullptr, g_df, nullptr, 2, df_idx, 0, clamp_max, part_labels, vals_df, vals_ce, g_ce};
+  TbParams prm{nullptr, g_df, nullptr, 2, df_idx, 0, clamp_max, part_labels, vals_df, vals_ce, g_ce, nullptr};
   return launch_bwd_tc(points, crop_center, body_center, B, N, im_feat, tmpx, tri_tmpx, tri_feat, Hf, Wf, Ht, Wt, cam7, wpack, planes, prm,
                        overflow, (cudaStream_t)stream, "vt_query_losses_tc");
 }
