@@ -267,3 +267,16 @@ def test_query_heads_subset_matches_full_query(net):
         sub = net.query_heads(points.cuda(), heads, crop_center=crop.cuda(), body_center=body.cuda())
         for h in heads:
             assert torch.equal(sub[h], full[h]), h
+
+
+def test_maps_of_an_earlier_filter_call_stay_valid(net):
+    """filter() on a second batch of the same shape must not overwrite the maps handed out for the first (graph replay copies out)."""
+    a, *_ = synthetic_frames(2, size=64, seed=101, n_points=4)
+    b, *_ = synthetic_frames(2, size=64, seed=102, n_points=4)
+    net.filter(a.cuda())
+    kept = net._maps
+    snapshot = [t.clone() for t in kept]
+    net.filter(b.cuda())
+    for t, s in zip(kept, snapshot):
+        assert torch.equal(t, s)
+    assert not torch.equal(net._maps[0], kept[0])

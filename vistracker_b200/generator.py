@@ -100,27 +100,32 @@ class GeneratorTriplaneVis:
             samples_surface, preds = self.approx_surface(samples, num_steps, query_input, df_type)
             df_target = torch.clamp(preds[0][:, df_idx, :], max=self.threshold)
             mask = (df_target < self.filter_val) & (samples_surface[:, :, 2] > 1.0)
+            # ONE host sync per round: the per-frame counts.  `order` lists the surviving sample positions of every frame first (stable),
+            # so frame i's survivors are order[i, :counts[i]] -- the boolean-mask indexing of the reference without a sync per frame
+            counts = mask.sum(1).cpu().tolist()
+            order = torch.argsort((~mask).to(torch.uint8), dim=1, stable=True)
             if it > 0:
-                counts = []
                 for i in range(batch_size):
-                    out_dict["points"][i].append(samples_surface[i, mask[i]].cpu())
+                    keep = order[i, :counts[i]]
+                    out_dict["points"][i].append(samples_surface[i].index_select(0, keep))
                     for name, pred in zip(out_names[1:], preds[1:]):
-                        out_dict[name][i].append(pred[i, ..., mask[i]].cpu())
-                    counts.append(int(mask[i].sum().item()))
+                        out_dict[name][i].append(pred[i].index_select(-1, keep))
                 samples_count += int(np.min(counts))
                 if not mute:
                     print("{} points".format(samples_count))
             samples_new = []
             for i in range(batch_size):
-                samples_i = samples[i, mask[i], :].unsqueeze(0)
-                if samples_i.shape[1] > 1:
-                    indices = torch.randint(samples_i.shape[1], (1, sample_num))
-                    samples_i = samples_i[[[0, ] * sample_num], indices.to(self.device)]
-                    samples_i = samples_i + (self.threshold / 3) * torch.randn(samples_i.shape).to(self.device)
+                # the random draws come from torch's CPU generator in the reference's order and shapes (identical samples for equal seeds)
+                if counts[i] > 1:
+                    indices = torch.randint(counts[i], (1, sample_num))
+                    noise = (self.threshold / 3) * torch.randn(1, sample_num, 3)
+                    src = samples[i].index_select(0, order[i, :counts[i]].index_select(0, indices[0].to(self.device, non_blocking=True)))
+                    samples_i = src.unsqueeze(0) + noise.to(self.device, non_blocking=True)
                 else:
                     indices = torch.randint(samples_init.shape[1], (1, sample_num))
-                    samples_i = samples_init[[[i, ] * sample_num], indices.to(samples_init.device)].clone().to(self.device)
-                    samples_i = samples_i + 0.5 * torch.randn(1, sample_num, 3).to(self.device)
+                    noise = 0.5 * torch.randn(1, sample_num, 3)
+                    src = samples_init[i].to(self.device).index_select(0, indices[0].to(self.device, non_blocking=True))
+                    samples_i = src.unsqueeze(0) + noise.to(self.device, non_blocking=True)
                 samples_new.append(samples_i)
             samples = torch.cat(samples_new, 0).detach()
             it += 1
@@ -145,7 +150,7 @@ class GeneratorTriplaneVis:
                 elif name in ("centers", "visibility"):
                     o = torch.mean(o, -1)
                 comb.append(o)
-            out_dict[name] = torch.stack(comb, 0)
+            out_dict[name] = torch.stack(comb, 0).cpu()           # the reference collects on the host (generator.py:119-125)
         nan_values = torch.zeros_like(out_dict["centers"]) + float("nan")
         out_dict["centers"] = torch.cat([nan_values, out_dict["centers"]], 1)
         return out_dict

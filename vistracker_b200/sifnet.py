@@ -166,8 +166,8 @@ class CHORETriplaneVisibility:
         3 triplane renderings.  The three triplane views go through the shared encoder as one batch of 3B.
 
         The ~440 kernel launches of the two encoders are captured once per input shape in a CUDA graph and replayed (static input
-        buffer, graph-private activations): same kernels, same results, no host launch cost and ~1 us instead of ~3 us between
-        dependent kernels.  VT_FILTER_GRAPH=0 launches eagerly."""
+        buffer, graph-private activations, outputs copied out): same kernels, same results, no host launch cost and ~1 us instead
+        of ~3 us between dependent kernels.  VT_FILTER_GRAPH=0 launches eagerly."""
         assert images.shape[1] == 8, f"given image shape invalide: {images.shape}"
         if self._rgb is None:
             raise RuntimeError("load_state_dict() must be called before filter()")
@@ -188,10 +188,13 @@ class CHORETriplaneVisibility:
                     if len(self._graphs) >= 4:                          # bound the memory held by graph-private pools
                         self._graphs.pop(next(iter(self._graphs)))
                     self._graphs[key] = entry
-                graph, static_in, maps, launches = entry
+                graph, static_in, static_maps, launches = entry
                 static_in.copy_(images)
                 graph.replay()
-                self.launches_filter = launches
+                # the graph writes into its private buffers; hand out copies so that maps kept from an earlier filter() call stay valid,
+                # as with the reference's freshly allocated tensors (0.57 GB at B = 8: ~0.2 ms, < 1 % of the step)
+                maps = tuple(t.clone() for t in static_maps)
+                self.launches_filter = launches + len(maps)
             else:
                 maps = self._filter_eager(images)
                 self.launches_filter = self._rgb.launches + self._tri.launches
