@@ -26,13 +26,15 @@ CASES = [  # ks, cin, cout, n, H, W
 ]
 
 
-@pytest.fixture(params=["persist", "plain", "strip", "pair"])
+@pytest.fixture(params=["persist", "persist_nostrip", "plain", "strip", "pair"])
 def variant(request, monkeypatch):
-    """persist (the default path) = one CTA per SM walking tiles with double-buffered TMEM accumulators and the merged N = 2 BN MMA;
+    """persist (the default path) = one CTA per SM walking tiles with double-buffered TMEM accumulators and the merged N = 2 BN MMA,
+    A strips for 3x3 on maps >= 128 wide (VT_CONV_PERSIST=4: for every BN; the default uses them for BN = 128 only) and a resident
+    weight panel for 1x1; persist_nostrip (VT_CONV_PERSIST=3) = the same without strips;
     plain (VT_CONV_PERSIST=0) = one tile per CTA; VT_CONV_STRIP=1 = one A strip serves the three dx taps, =2 = strip + two images per
     CTA sharing the weight tiles.  The strip kernels serve 3x3 convolutions on maps at least 128 wide ('pair' needs an even image count)."""
-    monkeypatch.setenv("VT_CONV_STRIP", {"persist": "0", "plain": "0", "strip": "1", "pair": "2"}[request.param])
-    monkeypatch.setenv("VT_CONV_PERSIST", "1" if request.param == "persist" else "0")
+    monkeypatch.setenv("VT_CONV_STRIP", {"persist": "0", "persist_nostrip": "0", "plain": "0", "strip": "1", "pair": "2"}[request.param])
+    monkeypatch.setenv("VT_CONV_PERSIST", {"persist": "4", "persist_nostrip": "3"}.get(request.param, "0"))
     return request.param
 
 

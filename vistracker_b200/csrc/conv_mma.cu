@@ -32,6 +32,7 @@ constexpr int MM_THREADS = 192;
 struct ConvMmaParams {
   int H, W, pad, ks, kchunks;   // kchunks = Cin_pad / 64
   int prefetch;                 // persistent kernel: tiles of A-operand L2 prefetch distance (0 = off)
+  long long* trace;             // debug (VT_CONV_TRACE=1): clock64 stamps of CTA 0: per tile [wait start, accumulator ready, tile drained]
   int bw, bh, tiles_x, bw_shift;   // bw is a power of two: pixel r of a tile sits at (y0 + (r >> bw_shift), x0 + (r & (bw-1)))
   int cout_total;               // rows per tap in the packed weight planes
   const float* bias; const float* res; int ldr;
@@ -332,7 +333,12 @@ conv_mma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
 // shared memory while the CTA walks pixel tiles of that (image, Cout tile) run; the ring then carries A stages only.  A 1x1 conv
 // has as many weight bytes as activation bytes per tile, so this halves its L2 -> SM traffic and gives the HBM-facing A stream the
 // whole ring.
-template <int BN, bool RESB = false>
+// STRIP (3x3 convolutions on maps at least 128 wide, one image row per tile): every 3x3 shape of the step turned out to be paced by
+// L2 -> shared-memory delivery (~60-70 B/clk per SM, VT_CONV_TRACE), not by the tensor pipe, because the ring fetches a fresh
+// 128-pixel A tile for each of the 9 taps.  Here one 130-pixel strip per (K-chunk, dy) serves the three dx taps through UMMA
+// descriptor row offsets (as in conv_mma_strip_kernel below), with separate A-strip and weight rings: 1.5x (BN = 128) to 1.8x
+// (BN = 64) fewer bytes per MMA.
+template <int BN, bool RESB = false, bool STRIP = false>
 struct PersistCfg {
   static constexpr int A_BYTES = MM_M * MM_KC * 2;
   static constexpr int B_BYTES = BN * MM_KC * 2;
@@ -340,13 +346,22 @@ struct PersistCfg {
   static constexpr int PANEL_BYTES = RESB ? PANEL_CHUNKS * 2 * B_BYTES : 0;
   static constexpr int STAGES = RESB ? (BN == 128 ? 2 : (BN == 64 ? 4 : 5)) : (BN == 128 ? 3 : (BN == 64 ? 4 : 5));
   static constexpr int STAGE_BYTES = RESB ? 2 * A_BYTES : 2 * A_BYTES + 2 * B_BYTES;
+  // strip mode: separate rings
+  static constexpr int STRIP_BYTES = (MM_M + 2) * 128;               // one plane of a 130-pixel strip, what TMA writes
+  static constexpr int STRIP_PLANE = 17408;                          // padded to a multiple of 1024
+  static constexpr int STRIP_SLOT = 2 * STRIP_PLANE;
+  static constexpr int B_SLOT = 2 * B_BYTES;
+  static constexpr int NA = STRIP ? (BN == 128 ? 2 : 3) : 1;
+  static constexpr int NB = STRIP ? (BN == 128 ? 4 : (BN == 64 ? 6 : 9)) : 1;
+  static constexpr int RING_BYTES = STRIP ? NA * STRIP_SLOT + NB * B_SLOT : STAGES * STAGE_BYTES + PANEL_BYTES;
   static constexpr int EPI_LD = 36;                                  // floats per staged row: 32 + 4 keeps float4 rows conflict-free
   static constexpr int EPI_BYTES = 4 * 32 * EPI_LD * 4;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + PANEL_BYTES + EPI_BYTES + 1024;
+  static constexpr int SMEM_BYTES = RING_BYTES + EPI_BYTES + 1024;
   static constexpr int TMEM_COLS = 4 * BN;
   static constexpr uint32_t IDESC_WIDE = (1u << 4) | ((uint32_t)(2 * BN >> 3) << 17) | ((uint32_t)(MM_M >> 4) << 24);
   static constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(MM_M >> 4) << 24);
-  static_assert(SMEM_BYTES <= 227 * 1024 && TMEM_COLS <= 512, "persistent configuration exceeds the SM");
+  static_assert(!(RESB && STRIP), "resident panel is for 1x1, strips for 3x3");
+  static_assert(SMEM_BYTES + 16 * BN * 4 + 1024 <= 227 * 1024 && TMEM_COLS <= 512, "persistent configuration (dynamic + static shared memory) exceeds the SM");
 };
 
 struct TileCoord { int img, n0, y0, x0; };
@@ -380,14 +395,15 @@ __device__ __forceinline__ void tc_ld32_issue(uint32_t taddr, uint32_t (&r)[32])
       : "r"(taddr) : "memory");
 }
 
-template <int BN, bool RESB>
+template <int BN, bool RESB, bool STRIP>
 __global__ void __launch_bounds__(MM_THREADS, 1)
 conv_mma_persist_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                         const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo, const ConvMmaParams p,
                         int tiles_per_img, int n_tiles_n, int total_tiles) {
-  using Cfg = PersistCfg<BN, RESB>;
+  using Cfg = PersistCfg<BN, RESB, STRIP>;
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bar_full[Cfg::STAGES], bar_empty[Cfg::STAGES], acc_full[2], acc_empty[2], panel_full, panel_empty;
+  __shared__ __align__(8) uint64_t a_full[Cfg::NA], a_empty[Cfg::NA], b_full[Cfg::NB], b_empty[Cfg::NB];      // strip mode rings
   __shared__ uint32_t s_tmem_base;
   // per-warp partial statistics [warp][channel]: exactly one lane owns a slot, so the running sums are plain read-modify-writes (a
   // shared-memory fp32 atomicAdd is a CAS loop, and four warps contending on it cost more than the rest of the chunk)
@@ -402,6 +418,8 @@ conv_mma_persist_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __gri
     for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(smem_u32(&bar_full[s]), 1); mbar_init(smem_u32(&bar_empty[s]), 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(smem_u32(&acc_full[s]), 1); mbar_init(smem_u32(&acc_empty[s]), 4); }
     mbar_init(smem_u32(&panel_full), 1); mbar_init(smem_u32(&panel_empty), 1);
+    for (int s = 0; s < Cfg::NA; ++s) { mbar_init(smem_u32(&a_full[s]), 1); mbar_init(smem_u32(&a_empty[s]), 1); }
+    for (int s = 0; s < Cfg::NB; ++s) { mbar_init(smem_u32(&b_full[s]), 1); mbar_init(smem_u32(&b_empty[s]), 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 4 && lane == 0) {
@@ -424,51 +442,81 @@ conv_mma_persist_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __gri
   if (warp == 4) {
     // ------------------------------------------------------------------ TMA producer: the ring runs across tile boundaries
     if (lane == 0) {
-      uint32_t g = 0, pg = 0;
-      int panel_n0 = -1;
-      const uint32_t panel_base = smem_base + Cfg::STAGES * Cfg::STAGE_BYTES;
-      for (int t = t_first; t < t_last; ++t) {
-        const TileCoord c = decode_tile(p, t, n_tiles_n, tiles_per_img, BN);
-        const int row0 = c.img * (p.H + 2 * p.pad) + c.y0;
-        // HBM-streaming shapes (1x1 convs, Cin <= 64): the ring alone keeps ~100 KB in flight per SM, not enough to cover DRAM
-        // latency at full bandwidth -- pull the A boxes of the tile `prefetch` tiles ahead into L2 now
-        if (p.prefetch > 0) {
-          for (int tp = (t == t_first ? t + 1 : t + p.prefetch); tp <= t + p.prefetch && tp < t_last; ++tp) {
-            const TileCoord cp = decode_tile(p, tp, n_tiles_n, tiles_per_img, BN);
-            const int rowp = cp.img * (p.H + 2 * p.pad) + cp.y0;
-            for (int it = 0; it < n_iter; ++it) {
-              const int tap = it / p.kchunks, kc = it % p.kchunks;
-              const int dy = tap / p.ks, dx = tap % p.ks;
-              if (p.ks == 3 && dx == 1) continue;          // the dx = 0 and dx = 2 boxes already cover the 130-pixel row
-              tma_prefetch_3d(&tm_a_hi, kc * MM_KC, cp.x0 + dx, rowp + dy);
-              tma_prefetch_3d(&tm_a_lo, kc * MM_KC, cp.x0 + dx, rowp + dy);
+      if constexpr (STRIP) {
+        uint32_t ga = 0, gb = 0;
+        const uint32_t b_base = smem_base + Cfg::NA * Cfg::STRIP_SLOT;
+        const int n_strips = 3 * p.kchunks;
+        for (int t = t_first; t < t_last; ++t) {
+          const TileCoord c = decode_tile(p, t, n_tiles_n, tiles_per_img, BN);
+          for (int is = 0; is < n_strips; ++is, ++ga) {
+            const int kc = is / 3, dy = is % 3;
+            const int sa = ga % Cfg::NA;
+            mbar_wait(smem_u32(&a_empty[sa]), ((ga / Cfg::NA) & 1u) ^ 1u);
+            const uint32_t af = smem_u32(&a_full[sa]);
+            mbar_expect_tx(af, 2 * Cfg::STRIP_BYTES);
+            const uint32_t adst = smem_base + sa * Cfg::STRIP_SLOT;
+            const int row = c.img * (p.H + 2) + c.y0 + dy;
+            tma_load_3d(adst, &tm_a_hi, af, kc * MM_KC, c.x0, row);
+            tma_load_3d(adst + Cfg::STRIP_PLANE, &tm_a_lo, af, kc * MM_KC, c.x0, row);
+            for (int dx = 0; dx < 3; ++dx, ++gb) {
+              const int sb = gb % Cfg::NB;
+              mbar_wait(smem_u32(&b_empty[sb]), ((gb / Cfg::NB) & 1u) ^ 1u);
+              const uint32_t bf = smem_u32(&b_full[sb]);
+              mbar_expect_tx(bf, Cfg::B_SLOT);
+              const uint32_t bdst = b_base + sb * Cfg::B_SLOT;
+              const int tap = dy * 3 + dx;
+              tma_load_2d(bdst, &tm_b_hi, bf, kc * MM_KC, tap * p.cout_total + c.n0);
+              tma_load_2d(bdst + Cfg::B_BYTES, &tm_b_lo, bf, kc * MM_KC, tap * p.cout_total + c.n0);
             }
           }
         }
-        if (RESB && c.n0 != panel_n0) {                    // (re)load the weight panel of this Cout tile once the old one is unused
-          if (pg > 0) mbar_wait(smem_u32(&panel_empty), (pg - 1) & 1u);
-          const uint32_t pf = smem_u32(&panel_full);
-          mbar_expect_tx(pf, (uint32_t)p.kchunks * 2 * Cfg::B_BYTES);
-          for (int kc = 0; kc < p.kchunks; ++kc) {
-            tma_load_2d(panel_base + kc * 2 * Cfg::B_BYTES, &tm_b_hi, pf, kc * MM_KC, c.n0);
-            tma_load_2d(panel_base + kc * 2 * Cfg::B_BYTES + Cfg::B_BYTES, &tm_b_lo, pf, kc * MM_KC, c.n0);
+      } else {
+        uint32_t g = 0, pg = 0;
+        int panel_n0 = -1;
+        const uint32_t panel_base = smem_base + Cfg::STAGES * Cfg::STAGE_BYTES;
+        for (int t = t_first; t < t_last; ++t) {
+          const TileCoord c = decode_tile(p, t, n_tiles_n, tiles_per_img, BN);
+          const int row0 = c.img * (p.H + 2 * p.pad) + c.y0;
+          // HBM-streaming shapes (1x1 convs, Cin <= 64): the ring alone keeps ~100 KB in flight per SM, not enough to cover DRAM
+          // latency at full bandwidth -- pull the A boxes of the tile `prefetch` tiles ahead into L2 now
+          if (p.prefetch > 0) {
+            for (int tp = (t == t_first ? t + 1 : t + p.prefetch); tp <= t + p.prefetch && tp < t_last; ++tp) {
+              const TileCoord cp = decode_tile(p, tp, n_tiles_n, tiles_per_img, BN);
+              const int rowp = cp.img * (p.H + 2 * p.pad) + cp.y0;
+              for (int it = 0; it < n_iter; ++it) {
+                const int tap = it / p.kchunks, kc = it % p.kchunks;
+                const int dy = tap / p.ks, dx = tap % p.ks;
+                if (p.ks == 3 && dx == 1) continue;          // the dx = 0 and dx = 2 boxes already cover the 130-pixel row
+                tma_prefetch_3d(&tm_a_hi, kc * MM_KC, cp.x0 + dx, rowp + dy);
+                tma_prefetch_3d(&tm_a_lo, kc * MM_KC, cp.x0 + dx, rowp + dy);
+              }
+            }
           }
-          panel_n0 = c.n0; ++pg;
-        }
-        for (int it = 0; it < n_iter; ++it, ++g) {
-          const int s = g % Cfg::STAGES;
-          const uint32_t ph = (g / Cfg::STAGES) & 1u;
-          mbar_wait(smem_u32(&bar_empty[s]), ph ^ 1u);
-          const uint32_t full = smem_u32(&bar_full[s]);
-          mbar_expect_tx(full, Cfg::STAGE_BYTES);
-          const int tap = it / p.kchunks, kc = it % p.kchunks;
-          const int dy = tap / p.ks, dx = tap % p.ks;
-          const uint32_t sa = smem_base + s * Cfg::STAGE_BYTES;
-          tma_load_3d(sa, &tm_a_hi, full, kc * MM_KC, c.x0 + dx, row0 + dy);
-          tma_load_3d(sa + Cfg::A_BYTES, &tm_a_lo, full, kc * MM_KC, c.x0 + dx, row0 + dy);
-          if (!RESB) {
-            tma_load_2d(sa + 2 * Cfg::A_BYTES, &tm_b_hi, full, kc * MM_KC, tap * p.cout_total + c.n0);
-            tma_load_2d(sa + 2 * Cfg::A_BYTES + Cfg::B_BYTES, &tm_b_lo, full, kc * MM_KC, tap * p.cout_total + c.n0);
+          if (RESB && c.n0 != panel_n0) {                    // (re)load the weight panel of this Cout tile once the old one is unused
+            if (pg > 0) mbar_wait(smem_u32(&panel_empty), (pg - 1) & 1u);
+            const uint32_t pf = smem_u32(&panel_full);
+            mbar_expect_tx(pf, (uint32_t)p.kchunks * 2 * Cfg::B_BYTES);
+            for (int kc = 0; kc < p.kchunks; ++kc) {
+              tma_load_2d(panel_base + kc * 2 * Cfg::B_BYTES, &tm_b_hi, pf, kc * MM_KC, c.n0);
+              tma_load_2d(panel_base + kc * 2 * Cfg::B_BYTES + Cfg::B_BYTES, &tm_b_lo, pf, kc * MM_KC, c.n0);
+            }
+            panel_n0 = c.n0; ++pg;
+          }
+          for (int it = 0; it < n_iter; ++it, ++g) {
+            const int s = g % Cfg::STAGES;
+            const uint32_t ph = (g / Cfg::STAGES) & 1u;
+            mbar_wait(smem_u32(&bar_empty[s]), ph ^ 1u);
+            const uint32_t full = smem_u32(&bar_full[s]);
+            mbar_expect_tx(full, Cfg::STAGE_BYTES);
+            const int tap = it / p.kchunks, kc = it % p.kchunks;
+            const int dy = tap / p.ks, dx = tap % p.ks;
+            const uint32_t sa = smem_base + s * Cfg::STAGE_BYTES;
+            tma_load_3d(sa, &tm_a_hi, full, kc * MM_KC, c.x0 + dx, row0 + dy);
+            tma_load_3d(sa + Cfg::A_BYTES, &tm_a_lo, full, kc * MM_KC, c.x0 + dx, row0 + dy);
+            if (!RESB) {
+              tma_load_2d(sa + 2 * Cfg::A_BYTES, &tm_b_hi, full, kc * MM_KC, tap * p.cout_total + c.n0);
+              tma_load_2d(sa + 2 * Cfg::A_BYTES + Cfg::B_BYTES, &tm_b_lo, full, kc * MM_KC, tap * p.cout_total + c.n0);
+            }
           }
         }
       }
@@ -476,44 +524,80 @@ conv_mma_persist_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __gri
   } else if (warp == 5) {
     // ------------------------------------------------------------------ MMA issuer (one thread)
     if (lane == 0) {
-      uint32_t g = 0, i = 0, pg = 0;
-      int panel_n0 = -1;
-      const uint32_t panel_base = smem_base + Cfg::STAGES * Cfg::STAGE_BYTES;
-      for (int t = t_first; t < t_last; ++t, ++i) {
-        const uint32_t set = i & 1u;
-        mbar_wait(smem_u32(&acc_empty[set]), ((i >> 1) & 1u) ^ 1u);      // the epilogue has drained this accumulator set
-        tc_fence_after();
-        int n0 = 0, n0_next = -1;
-        if (RESB) {
-          n0 = decode_tile(p, t, n_tiles_n, tiles_per_img, BN).n0;
-          if (t + 1 < t_last) n0_next = decode_tile(p, t + 1, n_tiles_n, tiles_per_img, BN).n0;
-          if (n0 != panel_n0) { mbar_wait(smem_u32(&panel_full), pg & 1u); tc_fence_after(); panel_n0 = n0; ++pg; }
-        }
-        const uint32_t acc0 = tmem_base + set * 2 * BN, acc1 = acc0 + BN;
-        for (int it = 0; it < n_iter; ++it, ++g) {
-          const int s = g % Cfg::STAGES;
-          const uint32_t ph = (g / Cfg::STAGES) & 1u;
-          mbar_wait(smem_u32(&bar_full[s]), ph);
+      if constexpr (STRIP) {
+        uint32_t ga = 0, gb = 0, i = 0;
+        const uint32_t b_base = smem_base + Cfg::NA * Cfg::STRIP_SLOT;
+        const int n_strips = 3 * p.kchunks;
+        for (int t = t_first; t < t_last; ++t, ++i) {
+          const uint32_t set = i & 1u;
+          mbar_wait(smem_u32(&acc_empty[set]), ((i >> 1) & 1u) ^ 1u);
           tc_fence_after();
-          const uint32_t sa = smem_base + s * Cfg::STAGE_BYTES;
-          const uint64_t a_hi = make_kmajor_sw128_desc(sa), a_lo = make_kmajor_sw128_desc(sa + Cfg::A_BYTES);
-          // rows [0, BN) = B_hi, rows [BN, 2 BN) = B_lo; 1x1: it == K-chunk index into the resident panel
-          const uint64_t b_hi = make_kmajor_sw128_desc(RESB ? panel_base + it * 2 * Cfg::B_BYTES : sa + 2 * Cfg::A_BYTES);
+          const uint32_t acc0 = tmem_base + set * 2 * BN, acc1 = acc0 + BN;
+          uint32_t started = 0;
+          for (int is = 0; is < n_strips; ++is, ++ga) {
+            const int sa = ga % Cfg::NA;
+            mbar_wait(smem_u32(&a_full[sa]), (ga / Cfg::NA) & 1u);
+            const uint32_t abase = smem_base + sa * Cfg::STRIP_SLOT;
+            for (int dx = 0; dx < 3; ++dx, ++gb) {
+              const int sb = gb % Cfg::NB;
+              mbar_wait(smem_u32(&b_full[sb]), (gb / Cfg::NB) & 1u);
+              tc_fence_after();
+              // tap dx = the same strip read from row dx on (128 B per pixel row; the matrix-base-offset field stays 0, see below)
+              const uint64_t a_hi = make_kmajor_sw128_desc(abase + dx * 128), a_lo = make_kmajor_sw128_desc(abase + Cfg::STRIP_PLANE + dx * 128);
+              const uint64_t b_hi = make_kmajor_sw128_desc(b_base + sb * Cfg::B_SLOT);     // rows [0, BN) = B_hi, [BN, 2 BN) = B_lo
 #pragma unroll
-          for (int k = 0; k < MM_KC / 16; ++k) {
-            const uint64_t adv = (uint64_t)(k * 32 >> 4);
-            tc_mma_f16(acc0, a_hi + adv, b_hi + adv, Cfg::IDESC_WIDE, (it | k) != 0);
-            tc_mma_f16(acc1, a_lo + adv, b_hi + adv, Cfg::IDESC, 1u);
+              for (int k = 0; k < MM_KC / 16; ++k) {
+                const uint64_t adv = (uint64_t)(k * 32 >> 4);
+                tc_mma_f16(acc0, a_hi + adv, b_hi + adv, Cfg::IDESC_WIDE, started);
+                tc_mma_f16(acc1, a_lo + adv, b_hi + adv, Cfg::IDESC, 1u);
+                started = 1u;
+              }
+              tc_commit(smem_u32(&b_empty[sb]));
+            }
+            tc_commit(smem_u32(&a_empty[sa]));
           }
-          tc_commit(smem_u32(&bar_empty[s]));
+          tc_commit(smem_u32(&acc_full[set]));
         }
-        tc_commit(smem_u32(&acc_full[set]));
-        if (RESB && n0_next != n0) tc_commit(smem_u32(&panel_empty));   // last tile of this panel (the producer may overwrite it)
+      } else {
+        uint32_t g = 0, i = 0, pg = 0;
+        int panel_n0 = -1;
+        const uint32_t panel_base = smem_base + Cfg::STAGES * Cfg::STAGE_BYTES;
+        for (int t = t_first; t < t_last; ++t, ++i) {
+          const uint32_t set = i & 1u;
+          mbar_wait(smem_u32(&acc_empty[set]), ((i >> 1) & 1u) ^ 1u);      // the epilogue has drained this accumulator set
+          tc_fence_after();
+          int n0 = 0, n0_next = -1;
+          if (RESB) {
+            n0 = decode_tile(p, t, n_tiles_n, tiles_per_img, BN).n0;
+            if (t + 1 < t_last) n0_next = decode_tile(p, t + 1, n_tiles_n, tiles_per_img, BN).n0;
+            if (n0 != panel_n0) { mbar_wait(smem_u32(&panel_full), pg & 1u); tc_fence_after(); panel_n0 = n0; ++pg; }
+          }
+          const uint32_t acc0 = tmem_base + set * 2 * BN, acc1 = acc0 + BN;
+          for (int it = 0; it < n_iter; ++it, ++g) {
+            const int s = g % Cfg::STAGES;
+            const uint32_t ph = (g / Cfg::STAGES) & 1u;
+            mbar_wait(smem_u32(&bar_full[s]), ph);
+            tc_fence_after();
+            const uint32_t sa = smem_base + s * Cfg::STAGE_BYTES;
+            const uint64_t a_hi = make_kmajor_sw128_desc(sa), a_lo = make_kmajor_sw128_desc(sa + Cfg::A_BYTES);
+            // rows [0, BN) = B_hi, rows [BN, 2 BN) = B_lo; 1x1: it == K-chunk index into the resident panel
+            const uint64_t b_hi = make_kmajor_sw128_desc(RESB ? panel_base + it * 2 * Cfg::B_BYTES : sa + 2 * Cfg::A_BYTES);
+  #pragma unroll
+            for (int k = 0; k < MM_KC / 16; ++k) {
+              const uint64_t adv = (uint64_t)(k * 32 >> 4);
+              tc_mma_f16(acc0, a_hi + adv, b_hi + adv, Cfg::IDESC_WIDE, (it | k) != 0);
+              tc_mma_f16(acc1, a_lo + adv, b_hi + adv, Cfg::IDESC, 1u);
+            }
+            tc_commit(smem_u32(&bar_empty[s]));
+          }
+          tc_commit(smem_u32(&acc_full[set]));
+          if (RESB && n0_next != n0) tc_commit(smem_u32(&panel_empty));   // last tile of this panel (the producer may overwrite it)
+        }
       }
     }
   } else {
     // ------------------------------------------------------------------ epilogue warps 0-3 (TMEM lanes 32*warp .. +31)
-    float* wstage = reinterpret_cast<float*>(smem_raw + (smem_base - smem_u32(smem_raw)) + Cfg::STAGES * Cfg::STAGE_BYTES + Cfg::PANEL_BYTES) + warp * 32 * Cfg::EPI_LD;
+    float* wstage = reinterpret_cast<float*>(smem_raw + (smem_base - smem_u32(smem_raw)) + Cfg::RING_BYTES) + warp * 32 * Cfg::EPI_LD;
     const int cl = lane & 7, rsub = lane >> 3;
     const bool st1 = p.stats != nullptr, st2 = p.out2 != nullptr && p.stats2 != nullptr;
     constexpr int NCH = BN / 32;
@@ -579,8 +663,11 @@ conv_mma_persist_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __gri
         }
       }
       const uint32_t set = i & 1u;
+      const bool tracing = p.trace != nullptr && blockIdx.x == 0 && threadIdx.x == 0 && i < 10;
+      if (tracing) p.trace[3 * i] = clock64();
       mbar_wait(smem_u32(&acc_full[set]), (i >> 1) & 1u);
       tc_fence_after();
+      if (tracing) p.trace[3 * i + 1] = clock64();
       const uint32_t lane_base = tmem_base + set * 2 * BN + ((uint32_t)(warp * 32) << 16);
 #pragma unroll
       for (int ch = 0; ch < NCH; ++ch) {
@@ -673,6 +760,7 @@ conv_mma_persist_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __gri
           }
         }
       }
+      if (tracing) p.trace[3 * i + 2] = clock64();
     }
     if ((st1 || st2) && stats_img >= 0) flush_stats();
   }
@@ -871,13 +959,13 @@ static int num_sms() {
   return n;
 }
 
-template <int BN, bool RESB>
+template <int BN, bool RESB, bool STRIP = false>
 static int launch_conv_persist(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi, const CUtensorMap& b_lo,
                                const ConvMmaParams& p, dim3 grid, cudaStream_t stream) {
-  using Cfg = PersistCfg<BN, RESB>;
+  using Cfg = PersistCfg<BN, RESB, STRIP>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_mma_persist_kernel<BN, RESB>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(conv_mma_persist_kernel<BN, RESB, STRIP>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return cuda_fail(e, "conv_mma_persist smem attr");
     attr_set = true;
   }
@@ -888,8 +976,20 @@ static int launch_conv_persist(const CUtensorMap& a_hi, const CUtensorMap& a_lo,
   if (max_ctas < 0) { const char* e = getenv("VT_CONV_MAX_CTAS"); max_ctas = e && atoi(e) > 0 ? atoi(e) : num_sms(); }
   const int cap = max_ctas < num_sms() ? max_ctas : num_sms();
   const int ctas = total < cap ? total : cap;
-  conv_mma_persist_kernel<BN, RESB><<<ctas, MM_THREADS, Cfg::SMEM_BYTES, stream>>>(a_hi, a_lo, b_hi, b_lo, p, tiles_per_img, n_tiles_n, total);
+  ConvMmaParams p2 = p;
+  const bool trace = getenv("VT_CONV_TRACE") != nullptr;         // debug only: synchronises and prints the epilogue stamps of CTA 0
+  if (trace) { cudaMalloc(&p2.trace, 32 * sizeof(long long)); cudaMemset(p2.trace, 0, 32 * sizeof(long long)); }
+  conv_mma_persist_kernel<BN, RESB, STRIP><<<ctas, MM_THREADS, Cfg::SMEM_BYTES, stream>>>(a_hi, a_lo, b_hi, b_lo, p2, tiles_per_img, n_tiles_n, total);
   VT_CHECK_LAUNCH("vt_conv_mma(persistent)");
+  if (trace) {
+    long long h[32];
+    cudaDeviceSynchronize();
+    cudaMemcpy(h, p2.trace, sizeof(h), cudaMemcpyDeviceToHost);
+    cudaFree(p2.trace);
+    fprintf(stderr, "[conv_mma_persist<%d,%d,%d> trace: per tile wait / drain cycles]", BN, (int)RESB, (int)STRIP);
+    for (int i = 0; i < 10 && h[3 * i + 2]; ++i) fprintf(stderr, " %lld/%lld", h[3 * i + 1] - h[3 * i], h[3 * i + 2] - h[3 * i + 1]);
+    fprintf(stderr, "\n");
+  }
   return 0;
 }
 
@@ -941,8 +1041,14 @@ int vt_conv_mma_dual(const void* a_hi, const void* a_lo, int n_img, int H, int W
   // not relieve that.  Kept (and tested) as the basis for round 2's A-from-TMEM / 2-CTA work.
   const char* strip_e = getenv("VT_CONV_STRIP");
   const int strip_mode = strip_e ? atoi(strip_e) : 0;
-  const bool strip = ks == 3 && bh == 1 && strip_mode != 0 && BN >= 64 && !(strip_mode == 2 && (n_img % 2));
-  const bool pair = strip && strip_mode == 2;
+  const char* persist_e = getenv("VT_CONV_PERSIST");
+  const int persist_mode = persist_e ? atoi(persist_e) : 1;         // 1 = persistent (default), 0 = one tile per CTA, 2 / 3 = persistent
+                                                                    // without the resident 1x1 panel / without the 3x3 strips
+  // persistent + strip: the default for 3x3 convolutions with Cout >= 128 on maps at least 128 wide (+3 % there; for BN <= 64 it is
+  // 1-3 % slower than the plain ring, profiles/r01l_*; VT_CONV_PERSIST=4 forces it for every BN)
+  const bool pstrip = persist_mode != 0 && persist_mode != 3 && strip_mode == 0 && ks == 3 && bh == 1 && (BN == 128 || persist_mode == 4);
+  const bool strip = pstrip || (ks == 3 && bh == 1 && strip_mode != 0 && BN >= 64 && !(strip_mode == 2 && (n_img % 2)));
+  const bool pair = !pstrip && strip && strip_mode == 2;
   CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
   {
     cuuint64_t dims[3] = {(cuuint64_t)Cin_pad, (cuuint64_t)Wp, (cuuint64_t)n_img * Hp};
@@ -962,6 +1068,7 @@ int vt_conv_mma_dual(const void* a_hi, const void* a_lo, int n_img, int H, int W
   p.H = H; p.W = W; p.pad = pad; p.ks = ks; p.kchunks = Cin_pad / MM_KC;
   p.bw = bw; p.bh = bh; p.tiles_x = W / bw; p.cout_total = Cout;
   p.bw_shift = 0; while ((1 << p.bw_shift) < bw) ++p.bw_shift;
+  p.trace = nullptr;
   {
     const char* pf = getenv("VT_CONV_PREFETCH");       // tiles of L2 prefetch distance for the HBM-streaming shapes; default off: measured 5-25 % SLOWER on B200 (profiles/r01k_*)
     p.prefetch = (ks == 1 || p.kchunks == 1) ? (pf ? atoi(pf) : 0) : 0;
@@ -974,15 +1081,19 @@ int vt_conv_mma_dual(const void* a_hi, const void* a_lo, int n_img, int H, int W
     if (BN == 128) return launch_conv_strip<128, 2>(ma_hi, ma_lo, mb_hi, mb_lo, p, grid, s);
     return launch_conv_strip<64, 2>(ma_hi, ma_lo, mb_hi, mb_lo, p, grid, s);
   }
-  if (strip) {
+  if (strip && !pstrip) {
     if (BN == 128) return launch_conv_strip<128, 1>(ma_hi, ma_lo, mb_hi, mb_lo, p, grid, s);
     return launch_conv_strip<64, 1>(ma_hi, ma_lo, mb_hi, mb_lo, p, grid, s);
   }
   // default: persistent kernel (overlapped epilogue, merged N = 2*BN MMA); VT_CONV_PERSIST=0 selects the one-tile-per-CTA kernel
-  const char* persist_e = getenv("VT_CONV_PERSIST");
-  if (!persist_e || atoi(persist_e) != 0) {
+  if (pstrip) {
+    if (BN == 128) return launch_conv_persist<128, false, true>(ma_hi, ma_lo, mb_hi, mb_lo, p, grid, s);
+    if (BN == 64) return launch_conv_persist<64, false, true>(ma_hi, ma_lo, mb_hi, mb_lo, p, grid, s);
+    return launch_conv_persist<32, false, true>(ma_hi, ma_lo, mb_hi, mb_lo, p, grid, s);
+  }
+  if (persist_mode != 0) {
     // 1x1 convolutions with Cin <= 256 keep the weight panel of a Cout tile resident in shared memory (VT_CONV_PERSIST=2 disables)
-    if (ks == 1 && p.kchunks <= 4 && !(persist_e && atoi(persist_e) == 2)) {
+    if (ks == 1 && p.kchunks <= 4 && persist_mode != 2) {
       if (BN == 128) return launch_conv_persist<128, true>(ma_hi, ma_lo, mb_hi, mb_lo, p, grid, s);
       if (BN == 64) return launch_conv_persist<64, true>(ma_hi, ma_lo, mb_hi, mb_lo, p, grid, s);
       return launch_conv_persist<32, true>(ma_hi, ma_lo, mb_hi, mb_lo, p, grid, s);
