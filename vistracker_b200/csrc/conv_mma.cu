@@ -671,11 +671,14 @@ conv_mma_persist_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __gri
       const uint32_t lane_base = tmem_base + set * 2 * BN + ((uint32_t)(warp * 32) << 16);
 #pragma unroll
       for (int ch = 0; ch < NCH; ++ch) {
+        const bool micro = tracing && i == 2 && ch == 0;
+        if (micro) p.trace[32] = clock64();
         {
           uint32_t v[32], w[32];
           tc_ld32_issue(lane_base + ch * 32, v);
           tc_ld32_issue(lane_base + BN + ch * 32, w);
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          if (micro) p.trace[33] = clock64();
           if (ch == NCH - 1) {                                           // this warp's last TMEM read of the tile: hand the set back
             tc_fence_before();
             __syncwarp();
@@ -688,6 +691,7 @@ conv_mma_persist_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __gri
                             fmaf(__uint_as_float(w[j + 2]), kLoInv, __uint_as_float(v[j + 2])), fmaf(__uint_as_float(w[j + 3]), kLoInv, __uint_as_float(v[j + 3])));
         }
         __syncwarp();
+        if (micro) p.trace[34] = clock64();
         const int cc = ch * 32 + cl * 4;                                 // channel inside the tile
         float4 bz = make_float4(0, 0, 0, 0);
         if (p.bias) bz = ld4(p.bias + c.n0 + cc);
@@ -700,6 +704,7 @@ conv_mma_persist_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __gri
           val[j] = v;
         }
         __syncwarp();                                                    // wstage is rewritten by the next chunk
+        if (micro) p.trace[35] = clock64();
         float4 nv[8], nw[8];
         if (ch + 1 < NCH) {                                              // next chunk's residuals: in flight during this chunk's stores
           if (p.res) {
@@ -711,6 +716,7 @@ conv_mma_persist_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __gri
             for (int j = 0; j < 8; ++j) nw[j] = ld4(p.res2 + (pix0 + roff[j]) * p.ldr2 + cbase + (ch + 1) * 32);
           }
         }
+        if (micro) p.trace[36] = clock64();
         float4 s4 = make_float4(0, 0, 0, 0), q4 = s4, t4 = s4, u4 = s4;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -729,6 +735,7 @@ conv_mma_persist_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __gri
 #pragma unroll
           for (int j = 0; j < 8; ++j) { rv[j] = nv[j]; rw[j] = nw[j]; }
         }
+        if (micro) p.trace[37] = clock64();
         if (st1) {
 #pragma unroll
           for (int o = 8; o < 32; o <<= 1) {
@@ -759,6 +766,7 @@ conv_mma_persist_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __gri
             *reinterpret_cast<float4*>(&s_sum2[warp][cc]) = a; *reinterpret_cast<float4*>(&s_sq2[warp][cc]) = bq;
           }
         }
+        if (micro) p.trace[38] = clock64();
       }
       if (tracing) p.trace[3 * i + 2] = clock64();
     }
@@ -978,16 +986,18 @@ static int launch_conv_persist(const CUtensorMap& a_hi, const CUtensorMap& a_lo,
   const int ctas = total < cap ? total : cap;
   ConvMmaParams p2 = p;
   const bool trace = getenv("VT_CONV_TRACE") != nullptr;         // debug only: synchronises and prints the epilogue stamps of CTA 0
-  if (trace) { cudaMalloc(&p2.trace, 32 * sizeof(long long)); cudaMemset(p2.trace, 0, 32 * sizeof(long long)); }
+  if (trace) { cudaMalloc(&p2.trace, 48 * sizeof(long long)); cudaMemset(p2.trace, 0, 48 * sizeof(long long)); }
   conv_mma_persist_kernel<BN, RESB, STRIP><<<ctas, MM_THREADS, Cfg::SMEM_BYTES, stream>>>(a_hi, a_lo, b_hi, b_lo, p2, tiles_per_img, n_tiles_n, total);
   VT_CHECK_LAUNCH("vt_conv_mma(persistent)");
   if (trace) {
-    long long h[32];
+    long long h[48];
     cudaDeviceSynchronize();
     cudaMemcpy(h, p2.trace, sizeof(h), cudaMemcpyDeviceToHost);
     cudaFree(p2.trace);
     fprintf(stderr, "[conv_mma_persist<%d,%d,%d> trace: per tile wait / drain cycles]", BN, (int)RESB, (int)STRIP);
     for (int i = 0; i < 10 && h[3 * i + 2]; ++i) fprintf(stderr, " %lld/%lld", h[3 * i + 1] - h[3 * i], h[3 * i + 2] - h[3 * i + 1]);
+    fprintf(stderr, " | chunk 0 of tile 2: tmem-ld %lld, combine+sts %lld, lds+bias+res %lld, prefetch-issue %lld, stg+stats-acc %lld, stats-reduce %lld",
+            h[33] - h[32], h[34] - h[33], h[35] - h[34], h[36] - h[35], h[37] - h[36], h[38] - h[37]);
     fprintf(stderr, "\n");
   }
   return 0;
