@@ -70,6 +70,18 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
+// Same, for waits that are expected to be long (a whole mainloop or epilogue): back off with nanosleep so that the spinning thread
+// does not take issue slots from the warp that shares its scheduler (warps 0/1 share SMSPs with the TMA / MMA warps).
+__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  long long t0 = clock64();
+  unsigned ns = 32;
+  while (!mbar_try_wait(bar, parity)) {
+    __nanosleep(ns);
+    if (ns < 256) ns <<= 1;
+    if (clock64() - t0 > 4000000000LL) { printf("vt conv_mma: mbarrier timeout (block %d thread %d)\n", blockIdx.x, threadIdx.x); __trap(); }
+  }
+}
 __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
   asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
                ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
@@ -451,7 +463,7 @@ conv_mma_persist_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __gri
           for (int is = 0; is < n_strips; ++is, ++ga) {
             const int kc = is / 3, dy = is % 3;
             const int sa = ga % Cfg::NA;
-            mbar_wait(smem_u32(&a_empty[sa]), ((ga / Cfg::NA) & 1u) ^ 1u);
+            mbar_wait_relaxed(smem_u32(&a_empty[sa]), ((ga / Cfg::NA) & 1u) ^ 1u);
             const uint32_t af = smem_u32(&a_full[sa]);
             mbar_expect_tx(af, 2 * Cfg::STRIP_BYTES);
             const uint32_t adst = smem_base + sa * Cfg::STRIP_SLOT;
@@ -460,7 +472,7 @@ conv_mma_persist_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __gri
             tma_load_3d(adst + Cfg::STRIP_PLANE, &tm_a_lo, af, kc * MM_KC, c.x0, row);
             for (int dx = 0; dx < 3; ++dx, ++gb) {
               const int sb = gb % Cfg::NB;
-              mbar_wait(smem_u32(&b_empty[sb]), ((gb / Cfg::NB) & 1u) ^ 1u);
+              mbar_wait_relaxed(smem_u32(&b_empty[sb]), ((gb / Cfg::NB) & 1u) ^ 1u);
               const uint32_t bf = smem_u32(&b_full[sb]);
               mbar_expect_tx(bf, Cfg::B_SLOT);
               const uint32_t bdst = b_base + sb * Cfg::B_SLOT;
@@ -493,7 +505,7 @@ conv_mma_persist_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __gri
             }
           }
           if (RESB && c.n0 != panel_n0) {                    // (re)load the weight panel of this Cout tile once the old one is unused
-            if (pg > 0) mbar_wait(smem_u32(&panel_empty), (pg - 1) & 1u);
+            if (pg > 0) mbar_wait_relaxed(smem_u32(&panel_empty), (pg - 1) & 1u);
             const uint32_t pf = smem_u32(&panel_full);
             mbar_expect_tx(pf, (uint32_t)p.kchunks * 2 * Cfg::B_BYTES);
             for (int kc = 0; kc < p.kchunks; ++kc) {
@@ -505,7 +517,7 @@ conv_mma_persist_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __gri
           for (int it = 0; it < n_iter; ++it, ++g) {
             const int s = g % Cfg::STAGES;
             const uint32_t ph = (g / Cfg::STAGES) & 1u;
-            mbar_wait(smem_u32(&bar_empty[s]), ph ^ 1u);
+            mbar_wait_relaxed(smem_u32(&bar_empty[s]), ph ^ 1u);
             const uint32_t full = smem_u32(&bar_full[s]);
             mbar_expect_tx(full, Cfg::STAGE_BYTES);
             const int tap = it / p.kchunks, kc = it % p.kchunks;
@@ -530,7 +542,7 @@ conv_mma_persist_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __gri
         const int n_strips = 3 * p.kchunks;
         for (int t = t_first; t < t_last; ++t, ++i) {
           const uint32_t set = i & 1u;
-          mbar_wait(smem_u32(&acc_empty[set]), ((i >> 1) & 1u) ^ 1u);
+          mbar_wait_relaxed(smem_u32(&acc_empty[set]), ((i >> 1) & 1u) ^ 1u);
           tc_fence_after();
           const uint32_t acc0 = tmem_base + set * 2 * BN, acc1 = acc0 + BN;
           uint32_t started = 0;
@@ -564,7 +576,7 @@ conv_mma_persist_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __gri
         const uint32_t panel_base = smem_base + Cfg::STAGES * Cfg::STAGE_BYTES;
         for (int t = t_first; t < t_last; ++t, ++i) {
           const uint32_t set = i & 1u;
-          mbar_wait(smem_u32(&acc_empty[set]), ((i >> 1) & 1u) ^ 1u);      // the epilogue has drained this accumulator set
+          mbar_wait_relaxed(smem_u32(&acc_empty[set]), ((i >> 1) & 1u) ^ 1u);      // the epilogue has drained this accumulator set
           tc_fence_after();
           int n0 = 0, n0_next = -1;
           if (RESB) {
@@ -665,7 +677,7 @@ conv_mma_persist_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __gri
       const uint32_t set = i & 1u;
       const bool tracing = p.trace != nullptr && blockIdx.x == 0 && threadIdx.x == 0 && i < 10;
       if (tracing) p.trace[3 * i] = clock64();
-      mbar_wait(smem_u32(&acc_full[set]), (i >> 1) & 1u);
+      mbar_wait_relaxed(smem_u32(&acc_full[set]), (i >> 1) & 1u);
       tc_fence_after();
       if (tracing) p.trace[3 * i + 1] = clock64();
       const uint32_t lane_base = tmem_base + set * 2 * BN + ((uint32_t)(warp * 32) << 16);

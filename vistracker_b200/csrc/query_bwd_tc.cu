@@ -41,32 +41,6 @@ struct TbParams {
   long long* trace;        // debug (VT_QUERY_TRACE=1): clock64 stamps of CTA (0,0): [0..15] epilogue thread 0, [16..31] gather warp 0
 };
 
-// tap of feature k (multiple of 4) of chunk c for the point with projections q; `direct` marks the (x, y, z - z0) lane of chunk 9
-__device__ __forceinline__ TqTap tb_chunk_tap(int c, int k, const TqProj& q, const TqMaps& m, int b, int B, int& view, bool& direct) {
-  TqTap t;
-  direct = false;
-  if (c < 4) {
-    view = -1;
-    t = tq_tap_setup(m.im_feat + (size_t)b * m.Hf * m.Wf * 256, m.Hf, m.Wf, 256, c * 64 + k, q.nx, q.ny);
-  } else if (c == 4) {
-    view = -1;
-    t = tq_tap_setup(m.tmpx + (size_t)b * m.Ht * m.Wt * 64, m.Ht, m.Wt, 64, k, q.nx, q.ny);
-  } else if (c < 8) {
-    view = c - 5;
-    const float u = view == 0 ? q.tu0 : view == 1 ? q.tu1 : q.tu2, w = view == 0 ? q.tv0 : view == 1 ? q.tv1 : q.tv2;
-    t = tq_tap_setup(m.tri_feat + ((size_t)view * B + b) * m.Hf * m.Wf * 64, m.Hf, m.Wf, 64, k, u, w);
-  } else if (c == 8) {
-    view = k >> 5;
-    const float u = view == 0 ? q.tu0 : q.tu1, w = view == 0 ? q.tv0 : q.tv1;
-    t = tq_tap_setup(m.tri_tmpx + ((size_t)view * B + b) * m.Ht * m.Wt * 32, m.Ht, m.Wt, 32, k & 31, u, w);
-  } else {
-    view = 2;
-    t = tq_tap_setup(m.tri_tmpx + ((size_t)2 * B + b) * m.Ht * m.Wt * 32, m.Ht, m.Wt, 32, k & 31, q.tu2, q.tv2);
-    if (k >= 32) { t.valid = 0u; direct = (k == 32); view = 3; }
-  }
-  return t;
-}
-
 // power-of-two normalisation of a non-negative maximum: returns e with 2^-e * m in [0.5, 1) (0 for m == 0 / non-finite)
 __device__ __forceinline__ int tb_norm_exp(float m) {
   if (!(m > 0.f) || !(m < 3.0e38f)) return 0;
@@ -87,7 +61,7 @@ query_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_c
   __shared__ __align__(8) uint64_t feat_full[2], feat_empty[2], w_full[TQ_NW], w_empty[TQ_NW], acc_full, act_full, gf_full[TB_NGF],
       gf_empty[TB_NGF], stg_full[2], stg_empty[2];
   __shared__ uint32_t s_tmem_base;
-  __shared__ TqProj s_proj[TQ_M];
+  __shared__ TqTapTable s_tap;
   __shared__ float s_xyz[TQ_M][4];                          // x, y, z - z0, z
   __shared__ int s_in_img[TQ_M];
   __shared__ int s_scale_e[TQ_M];                           // exponent of the per-point renormalisation of the current head
@@ -150,7 +124,7 @@ query_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_c
     } else {
       q.nx = q.ny = q.tu0 = q.tv0 = q.tu1 = q.tv1 = q.tu2 = q.tv2 = 1e30f;       // every tap out of range -> zero features
     }
-    s_proj[pp] = q; s_xyz[pp][0] = x; s_xyz[pp][1] = y; s_xyz[pp][2] = __fadd_rn(z, -cam.z0); s_xyz[pp][3] = z; s_in_img[pp] = in_img;
+    tq_tap_fill(s_tap, pp, q, m); s_xyz[pp][0] = x; s_xyz[pp][1] = y; s_xyz[pp][2] = __fadd_rn(z, -cam.z0); s_xyz[pp][3] = z; s_in_img[pp] = in_img;
   }
   tq_fence_before();
   __syncthreads();
@@ -180,16 +154,12 @@ query_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_c
         const int slot = it & 1;
         tq_mbar_wait(tq_smem_u32(&feat_empty[slot]), ((uint32_t)(it >> 1) & 1u) ^ 1u);
         uint8_t* dst = feat_ptr + slot * TQ_SLOT;
+        const TqChunkSrc src = tq_chunk_src(c, k, m, b, B);
 #pragma unroll
         for (int i0 = 0; i0 < PW; i0 += 2 * PB) {
           TqTap tap[PB];
-          bool direct[PB];
 #pragma unroll
-          for (int j = 0; j < PB; ++j) {
-            const int pp = gw * PW + i0 + 2 * j + sub;
-            int view;
-            tap[j] = tb_chunk_tap(c, k, s_proj[pp], m, b, B, view, direct[j]);
-          }
+          for (int j = 0; j < PB; ++j) tap[j] = tq_tap_get(s_tap, src, gw * PW + i0 + 2 * j + sub);
           float4 t00[PB], t01[PB], t10[PB], t11[PB];
 #pragma unroll
           for (int j = 0; j < PB; ++j) {
@@ -207,9 +177,9 @@ query_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_c
             v[0] += t01[j].x * tap[j].w01; v[1] += t01[j].y * tap[j].w01; v[2] += t01[j].z * tap[j].w01; v[3] += t01[j].w * tap[j].w01;
             v[0] += t10[j].x * tap[j].w10; v[1] += t10[j].y * tap[j].w10; v[2] += t10[j].z * tap[j].w10; v[3] += t10[j].w * tap[j].w10;
             v[0] += t11[j].x * tap[j].w11; v[1] += t11[j].y * tap[j].w11; v[2] += t11[j].z * tap[j].w11; v[3] += t11[j].w * tap[j].w11;
-            if (c == TQ_NCHUNK - 1 && k >= 32) {
+            if (!src.sampled) {
               v[0] = v[1] = v[2] = v[3] = 0.f;
-              if (direct[j]) { v[0] = s_xyz[pp][0]; v[1] = s_xyz[pp][1]; v[2] = s_xyz[pp][2]; }
+              if (src.direct) { v[0] = s_xyz[pp][0]; v[1] = s_xyz[pp][1]; v[2] = s_xyz[pp][2]; }
             }
             uint2 hh, ll;
             tq_split2(v[0], v[1], hh.x, ll.x, amax);
@@ -230,18 +200,17 @@ query_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_c
         tq_mbar_wait(tq_smem_u32(&stg_full[slot]), (uint32_t)(sc >> 1) & 1u);
         if (c == 0) TB_STAMP_G();
         const uint8_t* stg = feat_ptr + slot * TQ_SLOT;
+        const TqChunkSrc src = tq_chunk_src(c, k, m, b, B);
         const bool full_res = (c < 4) || (c >= 5 && c < 8);                // im_feat / tri_feat maps (Hf x Wf); else tmpx-sized maps
         const float su = 0.5f * (float)((full_res ? m.Wf : m.Wt) - 1), sv = 0.5f * (float)((full_res ? m.Hf : m.Ht) - 1);
 #pragma unroll 1
         for (int i0 = 0; i0 < PW; i0 += 2 * PBB) {
           TqTap tap[PBB];
-          bool direct[PBB];
-          int view[PBB];
           float4 g[PBB];
 #pragma unroll
           for (int j = 0; j < PBB; ++j) {
             const int pp = gw * PW + i0 + 2 * j + sub;
-            tap[j] = tb_chunk_tap(c, k, s_proj[pp], m, b, B, view[j], direct[j]);
+            tap[j] = tq_tap_get(s_tap, src, pp);
             g[j] = *reinterpret_cast<const float4*>(stg + pp * 256 + (((lane & 15) ^ (pp & 15)) << 4));
           }
           float4 t00[PBB], t01[PBB], t10[PBB], t11[PBB];
@@ -268,18 +237,18 @@ query_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_c
                         g[j].w * ((t10[j].w - t00[j].w) * (1.f - tx) + (t11[j].w - t01[j].w) * tx);
             const float gu = dix * su * scale, gv = diy * sv * scale;
             float gx = 0.f, gy = 0.f, gz = 0.f;
-            if (view[j] < 0) {           // perspective: nx = 2 (crop/2 + fx x / z + cx - ccx) / crop - 1
+            if (src.view < 0) {           // perspective: nx = 2 (crop/2 + fx x / z + cx - ccx) / crop - 1
               const float kk = 2.f / cam.crop, x = s_xyz[pp][0], y = s_xyz[pp][1], iz = 1.f / s_xyz[pp][3];
               gx = gu * kk * cam.fx * iz;
               gy = gv * kk * cam.fy * iz;
               gz = -gu * kk * cam.fx * x * iz * iz - gv * kk * cam.fy * y * iz * iz;
-            } else if (view[j] == 0) {   // right: (z, y)
+            } else if (src.view == 0) {   // right: (z, y)
               gz = gu; gy = gv;
-            } else if (view[j] == 1) {   // back: (-x, y)
+            } else if (src.view == 1) {   // back: (-x, y)
               gx = -gu; gy = gv;
-            } else if (view[j] == 2) {   // top: (x, -z)
+            } else if (src.view == 2) {   // top: (x, -z)
               gx = gu; gz = -gv;
-            } else if (direct[j]) {      // the (x, y, z - z0) inputs themselves
+            } else if (src.direct) {      // the (x, y, z - z0) inputs themselves
               gx = g[j].x * scale; gy = g[j].y * scale; gz = g[j].z * scale;
             }
 #pragma unroll

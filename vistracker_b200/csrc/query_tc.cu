@@ -31,7 +31,7 @@ query_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_c
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t feat_full[TQ_NF], feat_empty[TQ_NF], w_full[TQ_NW], w_empty[TQ_NW], acc_full, act_full;
   __shared__ uint32_t s_tmem_base;
-  __shared__ TqProj s_proj[TQ_M];
+  __shared__ TqTapTable s_tap;
   __shared__ float s_xyz[TQ_M][3];
   __shared__ int s_in_img[TQ_M];
   __shared__ __align__(16) float s_w4[TQ_H * 16 + 16];      // last layer of the current head: W4[128][16] + b4[16]
@@ -86,7 +86,7 @@ query_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_c
     } else {
       q.nx = q.ny = q.tu0 = q.tv0 = q.tu1 = q.tv1 = q.tu2 = q.tv2 = 1e30f;       // every tap out of range -> zero features
     }
-    s_proj[pp] = q; s_xyz[pp][0] = x; s_xyz[pp][1] = y; s_xyz[pp][2] = __fadd_rn(z, -cam.z0); s_in_img[pp] = in_img;
+    tq_tap_fill(s_tap, pp, q, m); s_xyz[pp][0] = x; s_xyz[pp][1] = y; s_xyz[pp][2] = __fadd_rn(z, -cam.z0); s_in_img[pp] = in_img;
   }
   tq_fence_before();
   __syncthreads();
@@ -106,35 +106,17 @@ query_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_c
         uint8_t* dst = feat_ptr + slot * TQ_SLOT;
         // half a warp per point: lane -> (point of the pair, 4 consecutive features k..k+3 of the chunk), 16-byte tap loads
         const int sub = lane >> 4, k = (lane & 15) * 4;
+        const TqChunkSrc src = tq_chunk_src(c, k, m, b, B);
+        const bool sampled = src.sampled;
         constexpr int PB = 4;                             // point PAIRS in flight per warp
         for (int i0 = 0; i0 < TQ_M / TQ_GATHER_WARPS; i0 += 2 * PB) {
           TqTap tap[PB];
           float4 direct[PB];
-          bool sampled = true;
 #pragma unroll
           for (int j = 0; j < PB; ++j) {
             const int pp = gw * (TQ_M / TQ_GATHER_WARPS) + i0 + 2 * j + sub;
-            const TqProj q = s_proj[pp];
-            direct[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (c < 4) {
-              tap[j] = tq_tap_setup(m.im_feat + (size_t)b * m.Hf * m.Wf * 256, m.Hf, m.Wf, 256, c * 64 + k, q.nx, q.ny);
-            } else if (c == 4) {
-              tap[j] = tq_tap_setup(m.tmpx + (size_t)b * m.Ht * m.Wt * 64, m.Ht, m.Wt, 64, k, q.nx, q.ny);
-            } else if (c < 8) {
-              const int view = c - 5;
-              const float u = view == 0 ? q.tu0 : view == 1 ? q.tu1 : q.tu2, w = view == 0 ? q.tv0 : view == 1 ? q.tv1 : q.tv2;
-              tap[j] = tq_tap_setup(m.tri_feat + ((size_t)view * B + b) * m.Hf * m.Wf * 64, m.Hf, m.Wf, 64, k, u, w);
-            } else if (c == 8) {
-              const int view = k >> 5;                    // features 0-31: right, 32-63: back
-              const float u = view == 0 ? q.tu0 : q.tu1, w = view == 0 ? q.tv0 : q.tv1;
-              tap[j] = tq_tap_setup(m.tri_tmpx + ((size_t)view * B + b) * m.Ht * m.Wt * 32, m.Ht, m.Wt, 32, k & 31, u, w);
-            } else {
-              tap[j] = tq_tap_setup(m.tri_tmpx + ((size_t)2 * B + b) * m.Ht * m.Wt * 32, m.Ht, m.Wt, 32, k & 31, q.tu2, q.tv2);
-              if (k >= 32) {
-                tap[j].valid = 0u; sampled = false;
-                if (k == 32) direct[j] = make_float4(s_xyz[pp][0], s_xyz[pp][1], s_xyz[pp][2], 0.f);
-              }
-            }
+            tap[j] = tq_tap_get(s_tap, src, pp);
+            direct[j] = src.direct ? make_float4(s_xyz[pp][0], s_xyz[pp][1], s_xyz[pp][2], 0.f) : make_float4(0.f, 0.f, 0.f, 0.f);
           }
           float4 t00[PB], t01[PB], t10[PB], t11[PB];
 #pragma unroll

@@ -112,6 +112,69 @@ __device__ __forceinline__ TqTap tq_tap_setup(const float* __restrict__ map, int
   return t;
 }
 
+// ---- per-point tap table: the bilinear footprint of a point depends on the (map size, projection) pair only -- 8 combinations:
+// im_feat, tmpx (perspective xy) and tri_feat / tri_tmpx for the three views -- not on the feature chunk, so it is computed once per
+// point in the prologue (12 KB of shared memory per 128 points) instead of once per point AND 64-feature chunk in the gather loops.
+constexpr int TQ_NCOMBO = 8;
+struct TqTapTable {
+  uint32_t offv[TQ_NCOMBO][TQ_M];        // (y0 * W + x0 + W + 1) | valid-mask << 28
+  float tx[TQ_NCOMBO][TQ_M], ty[TQ_NCOMBO][TQ_M];
+};
+
+__device__ __forceinline__ void tq_tap_coords(int H, int W, float u, float v, uint32_t& offv, float& tx, float& ty) {
+  float ix = __fmul_rn(__fmul_rn(__fadd_rn(u, 1.f), 0.5f), (float)(W - 1));
+  float iy = __fmul_rn(__fmul_rn(__fadd_rn(v, 1.f), 0.5f), (float)(H - 1));
+  float fx0 = floorf(ix), fy0 = floorf(iy);
+  tx = ix - fx0; ty = iy - fy0;
+  bool finite = (fabsf(ix) < 1e9f) && (fabsf(iy) < 1e9f);
+  int x0 = finite ? (int)fx0 : -10, y0 = finite ? (int)fy0 : -10;
+  bool vx0 = x0 >= 0 && x0 < W, vx1 = x0 + 1 >= 0 && x0 + 1 < W, vy0 = y0 >= 0 && y0 < H, vy1 = y0 + 1 >= 0 && y0 + 1 < H;
+  const uint32_t valid = (vy0 && vx0 ? 1u : 0u) | (vy0 && vx1 ? 2u : 0u) | (vy1 && vx0 ? 4u : 0u) | (vy1 && vx1 ? 8u : 0u);
+  const int off = valid ? y0 * W + x0 + W + 1 : 0;          // >= 0 whenever a tap is valid (x0, y0 >= -1)
+  offv = (uint32_t)off | (valid << 28);
+}
+
+__device__ __forceinline__ void tq_tap_fill(TqTapTable& T, int pp, const TqProj& q, const TqMaps& m) {
+  tq_tap_coords(m.Hf, m.Wf, q.nx, q.ny, T.offv[0][pp], T.tx[0][pp], T.ty[0][pp]);
+  tq_tap_coords(m.Ht, m.Wt, q.nx, q.ny, T.offv[1][pp], T.tx[1][pp], T.ty[1][pp]);
+  tq_tap_coords(m.Hf, m.Wf, q.tu0, q.tv0, T.offv[2][pp], T.tx[2][pp], T.ty[2][pp]);
+  tq_tap_coords(m.Hf, m.Wf, q.tu1, q.tv1, T.offv[3][pp], T.tx[3][pp], T.ty[3][pp]);
+  tq_tap_coords(m.Hf, m.Wf, q.tu2, q.tv2, T.offv[4][pp], T.tx[4][pp], T.ty[4][pp]);
+  tq_tap_coords(m.Ht, m.Wt, q.tu0, q.tv0, T.offv[5][pp], T.tx[5][pp], T.ty[5][pp]);
+  tq_tap_coords(m.Ht, m.Wt, q.tu1, q.tv1, T.offv[6][pp], T.tx[6][pp], T.ty[6][pp]);
+  tq_tap_coords(m.Ht, m.Wt, q.tu2, q.tv2, T.offv[7][pp], T.tx[7][pp], T.ty[7][pp]);
+}
+
+// where feature k (multiple of 4) of chunk c comes from -- depends on (chunk, lane) only, hoisted out of the point loops.
+// view: -1 perspective xy, 0 / 1 / 2 triplane right / back / top, 3 none (padding or the direct x, y, z - z0 lane)
+struct TqChunkSrc { const float* base; int combo, W, C, ch, view; bool sampled, direct; };
+
+__device__ __forceinline__ TqChunkSrc tq_chunk_src(int c, int k, const TqMaps& m, int b, int B) {
+  TqChunkSrc s;
+  s.sampled = true; s.direct = false;
+  if (c < 4)       { s.combo = 0; s.base = m.im_feat + (size_t)b * m.Hf * m.Wf * 256; s.W = m.Wf; s.C = 256; s.ch = c * 64 + k; s.view = -1; }
+  else if (c == 4) { s.combo = 1; s.base = m.tmpx + (size_t)b * m.Ht * m.Wt * 64;    s.W = m.Wt; s.C = 64;  s.ch = k;          s.view = -1; }
+  else if (c < 8)  { const int v = c - 5; s.combo = 2 + v; s.base = m.tri_feat + ((size_t)v * B + b) * m.Hf * m.Wf * 64; s.W = m.Wf; s.C = 64; s.ch = k; s.view = v; }
+  else if (c == 8) { const int v = k >> 5; s.combo = 5 + v; s.base = m.tri_tmpx + ((size_t)v * B + b) * m.Ht * m.Wt * 32; s.W = m.Wt; s.C = 32; s.ch = k & 31; s.view = v; }
+  else {
+    s.combo = 7; s.base = m.tri_tmpx + ((size_t)2 * B + b) * m.Ht * m.Wt * 32; s.W = m.Wt; s.C = 32; s.ch = k & 31; s.view = 2;
+    if (k >= 32) { s.sampled = false; s.direct = (k == 32); s.view = 3; }
+  }
+  return s;
+}
+
+__device__ __forceinline__ TqTap tq_tap_get(const TqTapTable& T, const TqChunkSrc& s, int pp) {
+  TqTap t;
+  const uint32_t offv = T.offv[s.combo][pp];
+  const float tx = T.tx[s.combo][pp], ty = T.ty[s.combo][pp];
+  t.valid = s.sampled ? (offv >> 28) : 0u;
+  const int off = (int)(offv & 0x0FFFFFFFu) - (s.W + 1);
+  t.p = s.base + ((long long)off * s.C + s.ch);
+  t.w00 = (1.f - tx) * (1.f - ty); t.w01 = tx * (1.f - ty); t.w10 = (1.f - tx) * ty; t.w11 = tx * ty;
+  t.rowstride = s.W * s.C; t.C = s.C; t.tx = tx; t.ty = ty;
+  return t;
+}
+
 // ---- host side: 2-D tensor map over an fp16 [rows][k_cols] weight plane, box {64, 128}, 128-byte swizzle
 typedef CUresult (*TqEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
