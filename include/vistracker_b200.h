@@ -268,6 +268,35 @@ int vt_raster_bwd(const float* verts, const int* faces, int B, int V, int F, int
                   const float* faces_ndc, const int* face_index, const float* alpha, const float* g_alpha, float* g_faces,
                   float* g_verts, void* stream);
 
+/* ---- SmoothNet stage: smoothnet/smooth_smplt.py, smooth_objrot.py, smooth_base.py, models/smoothnet*.py,
+ *      utils/utils.py:63-103, utils/geometry_utils.py -- the trajectory stays in device memory between the fitting stages ---- */
+
+/* floats of one packed SmoothNet (k-major): We[64][512] be[512] { W1[512][16] b1[16] W2[16][512] b2[512] } x n_blocks Wd[512][64] bd[64] */
+long long vt_smoothnet_pack_floats(int n_blocks);
+
+/* SMPLTSmoother.preprocess_input (smooth_smplt.py:73-101) without the windowing: poses[L][72|156] axis-angle (SMPL-H reduced to the 24
+ * SMPL joints) -> 6-D rotations, seq[L][157] = [pose6d 144 | betas 10 | trans 3]. */
+int vt_smooth_pack_smplt(const float* poses, int pose_dim, const float* betas, const float* trans, int L, float* seq, void* stream);
+
+/* SmoothNet.forward (models/smoothnet.py:125-141, eval mode) on every (sliding window, channel) row of channels [c0, c0+nC) of seq[L][D]:
+ * clips[b][t][c] for b in [0, L-window], window step 1 (smooth_base.py:45-73).  relative != 0: the window's first frame is subtracted from
+ * the input and added back to the output (SMPL translation, smooth_smplt.py:88-91 and 39-42).  Built for window 64 / hidden 512 / residual
+ * 16 (smoothnet/configs/pw3d_spin_3D.yaml).  clips: [L-window+1][window][D], only the selected channels are written. */
+int vt_smoothnet_clips(const float* seq, int L, int D, int c0, int nC, int relative, int window, int hidden, int res_hidden, int n_blocks,
+                       const float* wpack, float* clips, void* stream);
+
+/* slide_window_to_sequence / clips2seq_fast for step 1 (utils/utils.py:63-103): out[l][c] = mean of clips[b][l-b][c] over the windows that
+ * contain frame l; channels [pass0, pass0+passN) are taken from seq instead (betas are not smoothed, models/smoothnet_smpl.py:38-45). */
+int vt_smooth_window_mean(const float* clips, const float* seq, int L, int D, int window, int pass0, int passN, float* out, void* stream);
+
+/* SMPLTSmoother.post_processing (smooth_smplt.py:43-47): rot6D_to_axis on the 24 joints (Gram-Schmidt, kornia rotation-matrix ->
+ * quaternion -> angle-axis, NaN -> 0), betas and translation split out.  seq[L][157] -> poses[L][72], betas[L][10], trans[L][3]. */
+int vt_smooth_unpack_smplt(const float* seq, int L, float* poses, float* betas, float* trans, void* stream);
+
+/* rot6d_to_rotmat (geometry_utils.py:63-77) on rot6d[L][6]; transposed != 0 writes R^T as ObjrotSmoother.post_processing stores
+ * `obj_angles` (smooth_objrot.py:104-112). */
+int vt_smooth_rot6d_to_rotmat(const float* rot6d, int L, int transposed, float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -14,6 +14,8 @@ seeded synthetic checkpoint of ``vistracker_b200.synth`` and stores inputs-by-se
 * ``sifnet_c1.npz``         -- BASELINE config 1 (1 frame 512x512, 2000 points): the five heads in full and
                                every 8th pixel of each feature map
 * ``smpl_small.npz``        -- SMPL_Layer.forward on the synthetic SMPL-H model, B=5, outputs + gradients
+* ``smooth_small.npz``      -- (``--only smooth``) SmoothNetSMPL / SmoothNet through SMPLTSmoother / ObjrotSmoother pre- and
+                               post-processing on a 90-frame synthetic trajectory, window 64, + the rotation conversions
 """
 from __future__ import annotations
 
@@ -295,6 +297,78 @@ def recon_goldens(out_dir: str):
     print("recon_small:", {k: (float(v) if np.ndim(v) == 0 else v.shape) for k, v in out.items()})
 
 
+def smooth_goldens(out_dir: str):
+    """SmoothNet stage: the reference's SmoothNetSMPL / SmoothNet modules (seeded init, eval mode) driven through the
+    unbound SMPLTSmoother / ObjrotSmoother preprocess_input + post_processing and slide_window_to_sequence -> smooth_small.npz."""
+    y = _stub("yacs"); y.config = _stub("yacs.config", CfgNode=dict)
+    _stub("smoothnet.core.evaluate_config", parse_args=None)                         # needs yacs; only parse_args is imported from it
+    b = _stub("behave"); b.frame_data = _stub("behave.frame_data", FrameDataReader=object)
+    b.utils = _stub("behave.utils", load_template=None)
+    _stub("recon.pca_util", PCAUtil=object)
+    from smoothnet.models import SmoothNet, SmoothNetSMPL                             # reference
+    from smoothnet.smooth_base import SmootherBase                                    # reference
+    from smoothnet.smooth_smplt import SMPLTSmoother                                  # reference
+    from smoothnet.smooth_objrot import ObjrotSmoother                                # reference
+    import smoothnet.utils.geometry_utils as G                                       # reference
+
+    W = 64
+
+    def shim(cls):
+        s = types.SimpleNamespace(slide_window_size=W, slide_window_step=1, device="cpu")
+        for name in ("seq2batches", "merge_paths", "smplh2smpl_pose"):
+            if hasattr(cls, name):
+                setattr(s, name, types.MethodType(getattr(cls, name), s))
+        return s
+
+    rng = np.random.default_rng(7)
+    L = 90
+    t = np.arange(L)[:, None] / 15.0
+    poses = (0.4 * np.sin(t * rng.uniform(0.5, 2.0, (1, 156)) + rng.uniform(0, 6, (1, 156))) + 0.05 * rng.standard_normal((L, 156))).astype(np.float32)
+    poses[:, :3] += np.array([2.6, 0.3, -0.2], np.float32)                            # a global orientation near pi: the quaternion branches
+    poses[5, 3:6] = 0.0                                                               # an exactly-zero joint rotation
+    betas = (rng.standard_normal((1, 10)) * 0.5 + 0.01 * rng.standard_normal((L, 10))).astype(np.float32)
+    trans = (np.array([[0.1, -0.2, 2.3]]) + 0.3 * np.sin(t * np.array([[0.7, 1.1, 0.4]])) + 0.01 * rng.standard_normal((L, 3))).astype(np.float32)
+    frames = np.array([f"t{i:04d}.000" for i in range(L)])
+
+    torch.manual_seed(11)
+    net = SmoothNetSMPL(window_size=W, output_size=W, hidden_size=512, res_hidden_size=16, num_blocks=1, dropout=0.5).eval()
+    for p in net.parameters():
+        p.data.mul_(3.0)                                                              # make the residual path matter at random init
+    s = shim(SMPLTSmoother)
+    data = SMPLTSmoother.preprocess_input(s, {"poses": poses, "betas": betas, "trans": trans, "frames": frames})
+    with torch.no_grad():
+        inp = data["input_data"]
+        den = net(inp.permute(0, 2, 1)).permute(0, 2, 1)
+    rec = SMPLTSmoother.post_processing(s, data, den.clone(), inp.clone())
+    out = {"L": L, "W": W, "poses_in": poses, "betas_in": betas, "trans_in": trans, "input_data": inp.numpy(), "denoised_clips": den.numpy(),
+           "poses_out": rec["poses"], "betas_out": rec["betas"], "trans_out": rec["trans"]}
+    for k, v in net.state_dict().items():
+        out["smplt." + k] = v.numpy()
+
+    torch.manual_seed(12)
+    onet = SmoothNet(window_size=W, output_size=W, hidden_size=512, res_hidden_size=16, num_blocks=1, dropout=0.5).eval()
+    for p in onet.parameters():
+        p.data.mul_(3.0)
+    aa = (np.array([[0.3, 1.2, -0.4]]) + 0.5 * np.sin(t * np.array([[0.9, 0.6, 1.3]])) + 0.05 * rng.standard_normal((L, 3))).astype(np.float32)
+    rot = G.batch_rodrigues(torch.from_numpy(aa)).numpy()                             # "real" rotation matrices [L, 3, 3]
+    so = shim(ObjrotSmoother)
+    odata = ObjrotSmoother.preprocess_input(so, {"obj_rot": rot, "neural_visibility": np.zeros(L), "frames": frames})
+    with torch.no_grad():
+        oin = odata["input_data"]
+        oden = onet(oin.permute(0, 2, 1)).permute(0, 2, 1)
+    orec = ObjrotSmoother.post_processing(so, odata, oden.clone(), oin.clone())
+    out.update({"obj_rot_in": rot, "obj_input_data": oin.numpy(), "obj_denoised_clips": oden.numpy(), "obj_angles_out": orec["obj_angles"]})
+    for k, v in onet.state_dict().items():
+        out["objrot." + k] = v.numpy()
+    # conversion functions on their own (branch coverage of rotation_matrix_to_quaternion)
+    aa_t = torch.from_numpy(np.concatenate([rng.uniform(-3.1, 3.1, (200, 3)), np.zeros((1, 3)), [[np.pi, 0, 0], [0, np.pi - 1e-3, 0], [0, 0, 3.0]]]).astype(np.float32))
+    r6 = G.axis_to_rot6D(aa_t).reshape(-1, 6)
+    out.update({"conv_axis": aa_t.numpy(), "conv_rot6d": r6.numpy(), "conv_axis_back": G.rot6D_to_axis(r6.clone()).numpy(),
+                "conv_np_rot6d": G.numpy_axis_to_rot6D(aa_t.numpy()).reshape(-1, 6)})
+    np.savez_compressed(os.path.join(out_dir, "smooth_small.npz"), **out)
+    print("smooth_small.npz:", {k: getattr(v, "shape", v) for k, v in out.items() if not k.startswith(("smplt.", "objrot."))})
+
+
 def asset_fixtures(out_dir: str, ref_root: str):
     """Numeric assets the reference ships for this path, re-serialised without scipy / pickle:
     the body-25 landmark regressor (COO), the pose / hand priors and the 14-part vertex labels."""
@@ -336,3 +410,5 @@ if __name__ == "__main__":
         fit_smplt_goldens(HERE)
     if a.only in ("", "recon"):
         recon_goldens(HERE)
+    if a.only == "smooth":                  # stubs `behave` / `yacs`: run on its own
+        smooth_goldens(HERE)

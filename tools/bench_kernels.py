@@ -140,4 +140,14 @@ row("ragged chamfer, 400 cloud pairs of 20-300 points (incl. host packing)", ms,
 M = torch.randn(96, 3, 3, device=dev)
 ms = timeit(lambda: project_so3(M))
 row("so3 projection B=96", ms, 96, "matrices", 72, None, "latency-bound: one thread per matrix")
+# ---------------------------------------------------------------- SmoothNet stage (8(f) N1): 1500-frame trajectory
+from vistracker_b200.smooth import SMPLTSmoother, ObjrotSmoother, WINDOW  # noqa: E402
+_g = np.load(os.path.join(ROOT, "tests", "golden", "smooth_small.npz"))
+_sm = SMPLTSmoother({k[6:]: torch.from_numpy(_g[k]) for k in _g.files if k.startswith("smplt.")}, device=dev)
+_T = 1500
+_poses, _betas, _trans = torch.randn(_T, 156, device=dev) * 0.3, torch.randn(_T, 10, device=dev), torch.randn(_T, 3, device=dev)
+ms = timeit(lambda: _sm.smooth(_poses, _betas, _trans))
+_rows = (_T - WINDOW + 1) * 147
+row("SmoothNet SMPL-T smoothing, 1500 frames (pack + 2 x clips MLP + window mean + unpack)", ms, _T, "frames", None, _rows * 2 * 81920 / _T,
+    f"{_rows} (window, channel) rows x 81.9 kMAC, fp32 FFMA")
 print(json.dumps({"peaks": peaks, "rows": rows}, indent=1))

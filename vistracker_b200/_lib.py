@@ -67,6 +67,12 @@ SIGNATURES.update({
     "vt_chamfer_bwd": (_i, [_p, _p, _p, _p, _i, _p, _p, _p, _p, _p, _p]),
     "vt_query_bwd_heads": (_i, [_p, _p, _p, _i, _i, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _i, _p, _p]),
     "vt_query_project_step": (_i, [_p, _p, _p, _i, _i, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _i, _f, _p, _p, _p, _p]),
+    "vt_smoothnet_pack_floats": (_ll, [_i]),
+    "vt_smooth_pack_smplt": (_i, [_p, _i, _p, _p, _i, _p, _p]),
+    "vt_smoothnet_clips": (_i, [_p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p]),
+    "vt_smooth_window_mean": (_i, [_p, _p, _i, _i, _i, _i, _i, _p, _p]),
+    "vt_smooth_unpack_smplt": (_i, [_p, _i, _p, _p, _p, _p]),
+    "vt_smooth_rot6d_to_rotmat": (_i, [_p, _i, _i, _p, _p]),
     "vt_raster_fwd": (_i, [_p, _p, _i, _i, _i, _i, _p, _i, _p, _p, _p, _p, _p]),
     "vt_raster_bwd": (_i, [_p, _p, _i, _i, _i, _i, _p, _i, _p, _p, _p, _p, _p, _p, _p]),
 })
