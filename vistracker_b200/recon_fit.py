@@ -125,10 +125,11 @@ class ReconFitterTriVisFull:
         loss_dict["pose"] = torch.mean(self.priors.pose(smpl.pose))
         loss_dict["hand"] = torch.mean(self.priors.hand(smpl.pose))
         loss_dict["part"] = vals_ce.sum(-1).mean()
-        smpl.get_landmarks()                     # the reference runs a second SMPL forward here (smplz_loss is a no-op in tri-vis)
+        # the reference runs a second (and in the 'kpts' phase a third) SMPL forward here through get_landmarks() -- smplz_loss is a
+        # no-op in tri-vis and the parameters have not changed since smpl() above, so the cached vertices give the same landmarks
         loss_dict["pinit"] = torch.mean(torch.sum((smpl.pose[:, 3:SMPL_POSE_PRAMS_NUM] - data_dict["pose_init"]) ** 2, -1))
         if phase == "kpts":
-            J, _, _ = smpl.get_landmarks()
+            J, _, _ = smpl.get_landmarks(use_cache=True)
             loss_dict["j2d"] = self.projection_loss(J, data_dict["body_kpts"], data_dict["query_dict"]["crop_center"])
         if smpl_verts.shape[0] >= 4:
             v1, v2 = smpl_verts[1:-1] - smpl_verts[:-2], smpl_verts[2:] - smpl_verts[1:-1]
@@ -218,7 +219,9 @@ class ReconFitterTriVisFull:
 
     def forward_step(self, smpl: SMPLParams, data_dict, obj_R, obj_t, obj_s, phase, noise: Optional[torch.Tensor] = None):
         """recon_fit_trivis_full.py:193-270.  ``noise`` replays the U(0,1) tensor of decopose_axis (parity runs)."""
-        smpl_verts, _, _, _ = smpl()
+        # the SMPL parameters are frozen throughout optimize_smpl_object (its optimisers hold obj_R / obj_t only): the driver computes
+        # the vertices once and every step reuses them -- same values as the reference's per-step SMPL forward
+        smpl_verts = data_dict["_smpl_verts_frozen"] if "_smpl_verts_frozen" in data_dict else smpl()[0]
         loss_dict = {}
         R = decopose_axis(obj_R, noise=noise)
         object = self.transform_obj_verts(data_dict["objects"], R, obj_t, obj_s)
@@ -281,6 +284,8 @@ class ReconFitterTriVisFull:
         it_sil, it_obj = self.get_opt_iters()["sil"], self.get_opt_iters()["object"]
         prev_loss, phase, hist = 300.0, "object only", []
         data_dict["smpl_center"] = self.compute_smpl_center_pred(smpl)
+        with torch.no_grad():
+            data_dict["_smpl_verts_frozen"] = smpl()[0].detach()
         for it in range(joint_iter + it_obj + max_iter + it_sil):
             if it < it_obj:
                 phase = "object only"
@@ -306,8 +311,10 @@ class ReconFitterTriVisFull:
                 lv = float(loss)
                 hist.append(lv)
                 if (abs(prev_loss - lv) / prev_loss < prev_loss * 0.0001) and (it > 0.25 * max_iter) and phase == "joint":
+                    data_dict.pop("_smpl_verts_frozen", None)
                     return smpl, obj_R, obj_t, hist
                 prev_loss = lv
+        data_dict.pop("_smpl_verts_frozen", None)
         return smpl, obj_R, obj_t, hist
 
     def final_rotation(self, obj_R):
