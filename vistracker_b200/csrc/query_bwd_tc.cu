@@ -23,7 +23,7 @@
 namespace vt {
 
 constexpr int TB_THREADS = 448;
-constexpr int TB_NGF = 3;                                  // TMEM slots of 128 columns for gf, after the 128-column working accumulator
+constexpr int TB_NGF = 2;                                  // TMEM slots of 128 columns for gf, after the two 128-column head accumulators
 constexpr int TB_SMEM = 2 * TQ_SLOT /*features | gf staging*/ + TQ_NW * TQ_SLOT /*weights*/ + 2 * TQ_SLOT /*activations*/ + 1024;
 
 struct TbParams {
@@ -79,6 +79,10 @@ query_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_c
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.y, n0 = blockIdx.x * TQ_M;
   const int heads = prm.mode == 1 ? 1 : prm.mode == 2 ? (prm.labels ? 5 : 1) : prm.head_mask;
+  // heads are processed in pairs that share ONE forward gather: both first layers accumulate from the same feature chunks (TMEM
+  // columns 0-127 and 128-255), then each head runs its own forward / backward chain and backward gather; gf slots start at column 256
+  const int n_heads = __popc((unsigned)heads), n_pairs = (n_heads + 1) >> 1;
+  auto pair_head = [&](int pi, int j) { return 2 * pi + j < n_heads ? (int)__fns((unsigned)heads, 0, 2 * pi + j + 1) : -1; };
 
   if (warp == 5 && lane == 0) {
     for (int s = 0; s < 2; ++s) {
@@ -146,10 +150,9 @@ query_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_c
     const bool tracing_g = prm.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && gw == 0 && lane == 0;
 #define TB_STAMP_G() do { if (tracing_g && trg < 32) prm.trace[trg++] = clock64(); } while (0)
     TB_STAMP_G();
-    for (int h = 0; h < 5; ++h) {
-      if (!((heads >> h) & 1)) continue;
+    for (int pi = 0; pi < n_pairs; ++pi) {
       asm volatile("bar.sync 3, 256;" ::: "memory");       // every gather warp is done reading the previous head's staging slots
-      // ---- forward: 10 feature chunks into the A-operand ring
+      // ---- forward: 10 feature chunks into the A-operand ring (once per pair of heads)
       for (int c = 0; c < TQ_NCHUNK; ++c, ++it) {
         const int slot = it & 1;
         tq_mbar_wait(tq_smem_u32(&feat_empty[slot]), ((uint32_t)(it >> 1) & 1u) ^ 1u);
@@ -194,6 +197,9 @@ query_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_c
         if (lane == 0) tq_mbar_arrive(tq_smem_u32(&feat_full[slot]));
       }
       TB_STAMP_G();
+      for (int pj = 0; pj < 2; ++pj) {
+      const int h = pair_head(pi, pj);
+      if (h < 0) break;
       // ---- backward: contract the staged feature gradients with d(feature)/d(u, v) (second gather of the same taps)
       for (int c = 0; c < TQ_NCHUNK; ++c, ++sc) {
         const int slot = sc & 1;
@@ -274,6 +280,7 @@ query_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_c
         }
         __syncwarp();
       }
+      }   // heads of the pair
     }
     // ---- write the point gradients / the projected points (one lane per point)
     __syncwarp();
@@ -303,15 +310,22 @@ query_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_c
         tq_tma_2d(w_base + s * TQ_SLOT + TQ_PLANE, lo, full, col, row);
         ++iw;
       };
-      for (int h = 0; h < 5; ++h) {
-        if (!((heads >> h) & 1)) continue;
-        for (int c = 0; c < TQ_NCHUNK; ++c) load(&tm_w1_hi, &tm_w1_lo, c * TQ_KC, h * TQ_H);
-        for (int layer = 0; layer < 2; ++layer)
-          for (int kc = 0; kc < 2; ++kc) load(&tm_w23_hi, &tm_w23_lo, kc * TQ_KC, (layer * 5 + h) * TQ_H);
-        for (int layer = 1; layer >= 0; --layer)
-          for (int kc = 0; kc < 2; ++kc) load(&tm_w23t_hi, &tm_w23t_lo, kc * TQ_KC, (layer * 5 + h) * TQ_H);
-        for (int u = 0; u < TQ_NCHUNK / 2; ++u)
-          for (int kc = 0; kc < 2; ++kc) load(&tm_w1t_hi, &tm_w1t_lo, kc * TQ_KC, h * TQ_NCHUNK * TQ_KC + u * TQ_H);
+      for (int pi = 0; pi < n_pairs; ++pi) {
+        const int hA = pair_head(pi, 0), hB = pair_head(pi, 1);
+        for (int c = 0; c < TQ_NCHUNK; ++c) {
+          load(&tm_w1_hi, &tm_w1_lo, c * TQ_KC, hA * TQ_H);
+          if (hB >= 0) load(&tm_w1_hi, &tm_w1_lo, c * TQ_KC, hB * TQ_H);
+        }
+        for (int pj = 0; pj < 2; ++pj) {
+          const int h = pj == 0 ? hA : hB;
+          if (h < 0) break;
+          for (int layer = 0; layer < 2; ++layer)
+            for (int kc = 0; kc < 2; ++kc) load(&tm_w23_hi, &tm_w23_lo, kc * TQ_KC, (layer * 5 + h) * TQ_H);
+          for (int layer = 1; layer >= 0; --layer)
+            for (int kc = 0; kc < 2; ++kc) load(&tm_w23t_hi, &tm_w23t_lo, kc * TQ_KC, (layer * 5 + h) * TQ_H);
+          for (int u = 0; u < TQ_NCHUNK / 2; ++u)
+            for (int kc = 0; kc < 2; ++kc) load(&tm_w1t_hi, &tm_w1t_lo, kc * TQ_KC, h * TQ_NCHUNK * TQ_KC + u * TQ_H);
+        }
       }
     }
   } else if (warp == 5) {
@@ -334,30 +348,34 @@ query_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_c
         tq_commit(tq_smem_u32(&w_empty[s]));
         ++iw;
       };
-      for (int h = 0; h < 5; ++h) {
-        if (!((heads >> h) & 1)) continue;
-        for (int c = 0; c < TQ_NCHUNK; ++c, ++it) {                     // F1
+      for (int pi = 0; pi < n_pairs; ++pi) {
+        const bool two = pair_head(pi, 1) >= 0;
+        for (int c = 0; c < TQ_NCHUNK; ++c, ++it) {                     // F1 of both heads of the pair from the same feature chunk
           const int slot = it & 1;
           tq_mbar_wait(tq_smem_u32(&feat_full[slot]), (uint32_t)(it >> 1) & 1u);
           tq_fence_after();
           mma_tile(feat_base + slot * TQ_SLOT, tmem_base, c == 0);
+          if (two) mma_tile(feat_base + slot * TQ_SLOT, tmem_base + TQ_H, c == 0);
           tq_commit(tq_smem_u32(&feat_empty[slot]));
         }
         tq_commit(tq_smem_u32(&acc_full));
-        for (int stage = 0; stage < 4; ++stage) {                       // F2, F3, B3, B2: act buffer -> working accumulator
-          tq_mbar_wait(tq_smem_u32(&act_full), (uint32_t)iact & 1u); ++iact;
+        for (int pj = 0; pj < (two ? 2 : 1); ++pj) {
+          const uint32_t acc = tmem_base + pj * TQ_H;
+          for (int stage = 0; stage < 4; ++stage) {                     // F2, F3, B3, B2: act buffer -> this head's accumulator
+            tq_mbar_wait(tq_smem_u32(&act_full), (uint32_t)iact & 1u); ++iact;
+            tq_fence_after();
+            for (int kc = 0; kc < 2; ++kc) mma_tile(act_base + kc * TQ_SLOT, acc, kc == 0);
+            tq_commit(tq_smem_u32(&acc_full));
+          }
+          tq_mbar_wait(tq_smem_u32(&act_full), (uint32_t)iact & 1u); ++iact;   // g1 is in the act buffer
           tq_fence_after();
-          for (int kc = 0; kc < 2; ++kc) mma_tile(act_base + kc * TQ_SLOT, tmem_base, kc == 0);
-          tq_commit(tq_smem_u32(&acc_full));
-        }
-        tq_mbar_wait(tq_smem_u32(&act_full), (uint32_t)iact & 1u); ++iact;     // g1 is in the act buffer
-        tq_fence_after();
-        for (int u = 0; u < TQ_NCHUNK / 2; ++u, ++gfi) {                // B1: five groups of 128 feature-gradient columns
-          const int gs = gfi % TB_NGF;
-          tq_mbar_wait(tq_smem_u32(&gf_empty[gs]), ((uint32_t)(gfi / TB_NGF) & 1u) ^ 1u);
-          tq_fence_after();
-          for (int kc = 0; kc < 2; ++kc) mma_tile(act_base + kc * TQ_SLOT, tmem_base + TQ_H + gs * TQ_H, kc == 0);
-          tq_commit(tq_smem_u32(&gf_full[gs]));
+          for (int u = 0; u < TQ_NCHUNK / 2; ++u, ++gfi) {              // B1: five groups of 128 feature-gradient columns
+            const int gs = gfi % TB_NGF;
+            tq_mbar_wait(tq_smem_u32(&gf_empty[gs]), ((uint32_t)(gfi / TB_NGF) & 1u) ^ 1u);
+            tq_fence_after();
+            for (int kc = 0; kc < 2; ++kc) mma_tile(act_base + kc * TQ_SLOT, tmem_base + 2 * TQ_H + gs * TQ_H, kc == 0);
+            tq_commit(tq_smem_u32(&gf_full[gs]));
+          }
         }
       }
     }
@@ -390,8 +408,9 @@ query_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_c
       __syncwarp();
       if (lane == 0) tq_mbar_arrive(tq_smem_u32(&act_full));
     };
-    for (int h = 0; h < 5; ++h) {
-      if (!((heads >> h) & 1)) continue;
+    for (int hi = 0; hi < n_heads; ++hi) {
+      const int h = (int)__fns((unsigned)heads, 0, hi + 1), pj = hi & 1;        // pj: which accumulator of the pair
+      const uint32_t acc_base = lane_base + pj * TQ_H;
       const float* hw = wpack + (size_t)h * wpack_head_stride;
       const float* b1 = hw + 616 * 128;
       const float* b2 = b1 + 128 + 128 * 128;
@@ -411,13 +430,15 @@ query_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_c
       // ---- forward epilogues E1, E2, E3 (ReLU masks -> s_mask; the loops stay rolled, every v[] index is a compile-time constant)
 #pragma unroll 1
       for (int layer = 0; layer < 3; ++layer) {
-        tq_mbar_wait(tq_smem_u32(&acc_full), (uint32_t)iacc & 1u); ++iacc;
+        if (!(layer == 0 && pj == 1)) {          // the second head's first layer was completed together with the first head's
+          tq_mbar_wait(tq_smem_u32(&acc_full), (uint32_t)iacc & 1u); ++iacc;
+        }
         tq_fence_after();
         const float* bias = s_bias[layer];
 #pragma unroll 1
         for (int ch = 0; ch < 4; ++ch) {
           float v[32];
-          tq_ld32(lane_base + ch * 32, v);
+          tq_ld32(acc_base + ch * 32, v);
           uint32_t mk = 0;
 #pragma unroll
           for (int i = 0; i < 32; i += 4) {
@@ -525,7 +546,7 @@ query_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_c
 #pragma unroll 1
         for (int ch = 0; ch < 4; ++ch) {
           float v[32];
-          tq_ld32(lane_base + ch * 32, v);
+          tq_ld32(acc_base + ch * 32, v);
           const uint32_t mk = s_mask[bl][ch][r];
 #pragma unroll
           for (int i = 0; i < 32; ++i)
@@ -537,7 +558,7 @@ query_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_c
 #pragma unroll 1
         for (int ch = 0; ch < 4; ++ch) {
           float v[32];
-          tq_ld32(lane_base + ch * 32, v);
+          tq_ld32(acc_base + ch * 32, v);
           const uint32_t mk = s_mask[bl][ch][r];
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] = ((mk >> i) & 1u) ? v[i] * inv : 0.f;
@@ -558,7 +579,7 @@ query_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_c
             tq_mbar_wait(tq_smem_u32(&stg_empty[sc & 1]), ((uint32_t)(sc >> 1) & 1u) ^ 1u);
           }
           float v[32];
-          tq_ld32(lane_base + TQ_H + gs * TQ_H + ch * 32, v);
+          tq_ld32(lane_base + 2 * TQ_H + gs * TQ_H + ch * 32, v);
           uint8_t* stg = feat_ptr + (sc & 1) * TQ_SLOT + r * 256;
 #pragma unroll
           for (int q4 = 0; q4 < 8; ++q4)
