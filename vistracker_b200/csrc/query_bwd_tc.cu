@@ -141,7 +141,8 @@ query_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_c
     const int sub = lane >> 4, k = (lane & 15) * 4;
     constexpr int PB = 4;                                   // point PAIRS in flight per warp
     constexpr int PW = TQ_M / TQ_GATHER_WARPS;              // 16 points per warp
-    constexpr int PBB = 2;                                  // ... and in the backward contraction (more live registers per point)
+    constexpr int PBB = 2;                                  // ... and in the backward contraction (more live registers per point);
+    static_assert(PBB == 2, "the butterfly reduction below handles exactly two points per half-warp");
     for (int i = lane; i < PW * 3; i += 32) (&s_gacc[gw * PW][0])[i] = 0.f;      // each warp owns the rows of its 16 points
     __syncwarp();
     int it = 0, sc = 0;
@@ -228,6 +229,8 @@ query_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_c
             t10[j] = (tap[j].valid & 4u) ? ld4(tap[j].p + tap[j].rowstride) : z;
             t11[j] = (tap[j].valid & 8u) ? ld4(tap[j].p + tap[j].rowstride + tap[j].C) : z;
           }
+          float red[8];                                              // (gx, gy, gz) of the two points of this half-warp + 2 pads
+          red[6] = 0.f; red[7] = 0.f;
 #pragma unroll
           for (int j = 0; j < PBB; ++j) {
             const int pp = gw * PW + i0 + 2 * j + sub;
@@ -257,11 +260,29 @@ query_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_c
             } else if (src.direct) {      // the (x, y, z - z0) inputs themselves
               gx = g[j].x * scale; gy = g[j].y * scale; gz = g[j].z * scale;
             }
+            red[3 * j] = gx; red[3 * j + 1] = gy; red[3 * j + 2] = gz;
+          }
+          // sum the 6 values over the 16 lanes (features) of the half-warp with a halving butterfly: 8 shuffles instead of 24; lane l ends
+          // up owning value index 4*bit3 + 2*bit2 + bit1
+          {
+            const bool u8 = (lane & 8) != 0, u4 = (lane & 4) != 0, u2 = (lane & 2) != 0;
 #pragma unroll
-            for (int o = 8; o >= 1; o >>= 1) {                           // sum over the 16 lanes (features) of this half-warp
-              gx += __shfl_xor_sync(0xffffffffu, gx, o); gy += __shfl_xor_sync(0xffffffffu, gy, o); gz += __shfl_xor_sync(0xffffffffu, gz, o);
+            for (int i = 0; i < 4; ++i) {
+              const float send = u8 ? red[i] : red[i + 4], keep = u8 ? red[i + 4] : red[i];
+              red[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
             }
-            if ((lane & 15) == 0) { s_gacc[pp][0] += gx; s_gacc[pp][1] += gy; s_gacc[pp][2] += gz; }
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+              const float send = u4 ? red[i] : red[i + 2], keep = u4 ? red[i + 2] : red[i];
+              red[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+            }
+            {
+              const float send = u2 ? red[0] : red[1], keep = u2 ? red[1] : red[0];
+              red[0] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+            }
+            red[0] += __shfl_xor_sync(0xffffffffu, red[0], 1);
+            const int idx = (u8 ? 4 : 0) + (u4 ? 2 : 0) + (u2 ? 1 : 0);
+            if ((lane & 1) == 0 && idx < 6) s_gacc[gw * PW + i0 + 2 * (idx / 3) + sub][idx % 3] += red[0];
           }
         }
         __syncwarp();
