@@ -448,6 +448,7 @@ query_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_c
       float o[14];
 #pragma unroll
       for (int c = 0; c < 14; ++c) o[c] = 0.f;
+      const bool narrow = h == 0 || h == 3 || h == 4;       // <= 4 outputs: W4 columns 4..15 are zero padding
       // ---- forward epilogues E1, E2, E3 (ReLU masks -> s_mask; the loops stay rolled, every v[] index is a compile-time constant)
 #pragma unroll 1
       for (int layer = 0; layer < 3; ++layer) {
@@ -471,6 +472,12 @@ query_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_c
           s_mask[layer][ch][r] = mk;
           if (layer < 2) {
             store_act(v, ch);
+          } else if (narrow) {                   // heads with <= 4 outputs (df, centers, visibility): one 16-byte weight load per unit
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const float4 w0 = *reinterpret_cast<const float4*>(s_w4 + (ch * 32 + i) * 16);
+              o[0] = fmaf(v[i], w0.x, o[0]); o[1] = fmaf(v[i], w0.y, o[1]); o[2] = fmaf(v[i], w0.z, o[2]); o[3] = fmaf(v[i], w0.w, o[3]);
+            }
           } else {
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
@@ -543,6 +550,15 @@ query_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_c
       for (int ch = 0; ch < 4; ++ch) {
         float v[32];
         const uint32_t mk = s_mask[2][ch][r];
+        if (narrow) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const float4 w0 = *reinterpret_cast<const float4*>(s_w4 + (ch * 32 + i) * 16);
+            float a = g4[0] * w0.x;
+            a = fmaf(g4[1], w0.y, a); a = fmaf(g4[2], w0.z, a); a = fmaf(g4[3], w0.w, a);
+            v[i] = ((mk >> i) & 1u) ? a : 0.f;
+          }
+        } else
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
           const float4* wr = reinterpret_cast<const float4*>(s_w4 + (ch * 32 + i) * 16);

@@ -265,6 +265,13 @@ query_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_c
                 *reinterpret_cast<uint4*>(dst + off) = hh;
                 *reinterpret_cast<uint4*>(dst + TQ_PLANE + off) = ll;
               }
+            } else if (h == 0 || h == 3 || h == 4) {
+              // last layer on the CUDA cores, heads with <= 4 outputs (W4 columns 4..15 are zero padding): one 16-byte load per unit
+#pragma unroll
+              for (int i = 0; i < 32; ++i) {
+                const float4 w0 = *reinterpret_cast<const float4*>(s_w4 + (ch * 32 + i) * 16);
+                o[0] = fmaf(v[i], w0.x, o[0]); o[1] = fmaf(v[i], w0.y, o[1]); o[2] = fmaf(v[i], w0.z, o[2]); o[3] = fmaf(v[i], w0.w, o[3]);
+              }
             } else {
               // last layer on the CUDA cores: out[c] += h3[k] * W4[k][c]
 #pragma unroll
