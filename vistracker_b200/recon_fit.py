@@ -2,7 +2,7 @@
 ``forward_smpl`` (recon/recon_fit_behave.py:393-513) and ``ReconFitterTriVisFull.optimize_smpl_object`` / ``forward_step``
 (recon/recon_fit_trivis_full.py:124-457) over the hand-written kernels of this package:
 
-    SMPL-H layer fwd/bwd (csrc/smpl.cu) · landmark regressors · SIF-Net query fwd/bwd (csrc/query.cu) ·
+    SMPL-H layer fwd/bwd (csrc/smpl.cu) · landmark regressors · SIF-Net fused query losses / query fwd (csrc/query_bwd_tc.cu, query_tc.cu) ·
     SO(3) projection, ragged Chamfer (csrc/geom.cu) · silhouette rasteriser fwd/bwd (csrc/raster.cu)
 
 Each of those is a ``torch.autograd.Function`` around one or two kernel launches; the scalar glue between them (clamps, means,
@@ -226,8 +226,12 @@ class ReconFitterTriVisFull:
         R = decopose_axis(obj_R, noise=noise)
         object = self.transform_obj_verts(data_dict["objects"], R, obj_t, obj_s)
         first_joint = phase == "joint" and "df_obj_h" not in data_dict
-        if phase == "sil" or first_joint:
-            # every head is needed (sil: no distance term at all; first joint step: df_h and parts at the object points)
+        if phase == "sil":
+            # the reference still queries the network here (recon_fit_trivis_full.py:199-204), but no 'sil' loss term reads a prediction
+            # (mask / scale / trans / temporal only): the launch is skipped
+            df_pred = part_o = None
+        elif first_joint:
+            # first joint step: df_h and the part logits at the object points are needed for the contact masks
             self.model.query(object, **data_dict["query_dict"])
             preds = self.model.get_preds()
             df_pred, centers_pred_o, part_o = preds[0], preds[3], preds[2]
@@ -238,7 +242,8 @@ class ReconFitterTriVisFull:
             with torch.no_grad():
                 centers_pred_o = self.model.query_heads(object, ("centers",), **data_dict["query_dict"])["centers"]
             df_pred = part_o = None
-        obj_center_pred = data_dict["smpl_center"] + torch.mean(centers_pred_o, -1)               # recon_fit_behave.py:370-380
+        if phase != "sil":
+            obj_center_pred = data_dict["smpl_center"] + torch.mean(centers_pred_o, -1)           # recon_fit_behave.py:370-380
         self.temporal_loss_joint(object, loss_dict, phase)
         if phase == "sil":
             sil = data_dict["silhouette"]
