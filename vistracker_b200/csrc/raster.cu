@@ -122,18 +122,20 @@ __global__ void __launch_bounds__(RT * RT) raster_fwd_kernel(const float* __rest
   }
 }
 
-// NMR pseudo-gradient of the silhouette w.r.t. the (x, y) of every face vertex.  One thread per (frame, face).
-__global__ void raster_bwd_kernel(const float* __restrict__ faces_ndc, const int* __restrict__ face_index,
+// NMR pseudo-gradient of the silhouette w.r.t. the (x, y) of every face vertex.  One WARP per (frame, face): the lanes split the
+// pixel columns / rows an edge crosses (the upstream kernel walks them in one thread: up to `is` iterations, each with an inner walk of
+// up to `is` pixels -- latency-bound), partial sums are combined with shuffles at the end.
+__global__ void __launch_bounds__(128) raster_bwd_kernel(const float* __restrict__ faces_ndc, const int* __restrict__ face_index,
                                   const float* __restrict__ alpha /*image rows*/, const float* __restrict__ g_alpha /*image rows*/,
                                   int B, int nf, int is, float* __restrict__ g_faces /*[B][nf][9]*/) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (i >= B * nf) return;
   const int bn = i / nf, fn = i % nf;
   const float* face = faces_ndc + (size_t)i * 9;
   float grad_face[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
   float* out = g_faces + (size_t)i * 9;
   if ((face[7] - face[1]) * (face[3] - face[0]) < (face[4] - face[1]) * (face[6] - face[0])) {   // back side
-    for (int k = 0; k < 9; ++k) out[k] = 0.f;
+    if (lane < 9) out[lane] = 0.f;
     return;
   }
   // internal maps are y-up: internal (row = y index, col = x index) lives at image row is-1-row
@@ -155,7 +157,7 @@ __global__ void raster_bwd_kernel(const float* __restrict__ faces_ndc, const int
       else direction = (p[0][0] < p[1][0]) ? 1 : -1;
       const int d0_from = (int)fmaxf(ceilf(fminf(p[0][0], p[1][0])), 0.f);
       const int d0_to = (int)fminf(fmaxf(p[0][0], p[1][0]), (float)(is - 1));
-      for (int d0 = d0_from; d0 <= d0_to; ++d0) {
+      for (int d0 = d0_from + lane; d0 <= d0_to; d0 += 32) {
         const float d1_cross = (p[1][1] - p[0][1]) / (p[1][0] - p[0][0]) * (d0 - p[0][0]) + p[0][1];
         const int d1_in = direction > 0 ? (int)floorf(d1_cross) : (int)ceilf(d1_cross);
         const int d1_out = d1_in + direction;
@@ -212,7 +214,13 @@ __global__ void raster_bwd_kernel(const float* __restrict__ faces_ndc, const int
       }
     }
   }
-  for (int k = 0; k < 9; ++k) out[k] = grad_face[k];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) {
+    float v = grad_face[k];
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) out[k] = v;
+  }
 }
 
 // g_faces (NDC x, y per face vertex) -> camera-space vertex gradients through vertices_to_faces and the projection
@@ -270,7 +278,7 @@ int vt_raster_bwd(const float* verts, const int* faces, int B, int V, int F, int
   cudaStream_t s = (cudaStream_t)stream;
   cudaError_t e = cudaMemsetAsync(g_verts, 0, (size_t)B * V * 3 * sizeof(float), s);
   if (e != cudaSuccess) return cuda_fail(e, "vt_raster_bwd memset");
-  raster_bwd_kernel<<<ceil_div(B * 2 * F, 128), 128, 0, s>>>(faces_ndc, face_index, alpha, g_alpha, B, 2 * F, image_size, g_faces);
+  raster_bwd_kernel<<<ceil_div(B * 2 * F, 4), 128, 0, s>>>(faces_ndc, face_index, alpha, g_alpha, B, 2 * F, image_size, g_faces);   // one warp per face
   VT_CHECK_LAUNCH("vt_raster_bwd");
   raster_bwd_verts_kernel<<<ceil_div(B * 2 * F, 256), 256, 0, s>>>(g_faces, verts, faces, B, V, F, mode, K4, g_verts);
   VT_CHECK_LAUNCH("vt_raster_bwd(verts)");
