@@ -165,12 +165,13 @@ int vt_query_project_step_tc(const float* points, const float* crop_center, cons
  * (recon/recon_fit_behave.py:471) and `torch.clamp(df_pred[:, 1], max=0.8)` of forward_step (recon/recon_fit_trivis_full.py:235) --
  * with g_df[B][N][3] = d vals_df / d point; when part_labels[B][N] (int64) is given, vals_ce[B][N] = F.cross_entropy(parts, labels,
  * reduction='none') (recon_fit_behave.py:476) with g_ce[B][N][3] = d vals_ce / d point.  Reductions and loss weights are linear in these
- * and stay with the caller. */
+ * and stay with the caller.  fwd_mask: further heads to evaluate forward-only in the same launch (they share the feature gather), written
+ * into the packed prediction buffer out_fwd[B][29][N] (e.g. bit 3: the centre head forward_step reports, recon_fit_behave.py:370-380). */
 int vt_query_losses_tc(const float* points, const float* crop_center, const float* body_center, int B, int N, const float* im_feat,
                        const float* tmpx, const float* tri_tmpx, const float* tri_feat, int Hf, int Wf, int Ht, int Wt, const float* cam7,
                        const float* wpack, const void* w1_hi, const void* w1_lo, const void* w23_hi, const void* w23_lo, const void* w23t_hi,
                        const void* w23t_lo, const void* w1t_hi, const void* w1t_lo, int df_idx, float clamp_max, const long long* part_labels,
-                       float* vals_df, float* g_df, float* vals_ce, float* g_ce, int* overflow, void* stream);
+                       float* vals_df, float* g_df, float* vals_ce, float* g_ce, int fwd_mask, float* out_fwd, int* overflow, void* stream);
 
 /* ---- SMPL-H layer: SMPL_Layer.forward (lib_smpl/smplpytorch/smplpytorch/pytorch/smpl_layer.py:73-176) and its gradient
  *      w.r.t. pose / betas / trans; landmark regressors (lib_smpl/torch_functions.py:52-76, wrapper_pytorch.py:187-203) ---- */

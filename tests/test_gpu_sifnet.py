@@ -280,3 +280,26 @@ def test_maps_of_an_earlier_filter_call_stay_valid(net):
     for t, s in zip(kept, snapshot):
         assert torch.equal(t, s)
     assert not torch.equal(net._maps[0], kept[0])
+
+
+@pytest.mark.parametrize("with_parts,also", [(False, ("centers",)), (True, ("centers", "visibility")), (False, ("pca", "parts", "centers", "visibility"))])
+def test_fused_losses_with_forward_only_heads(net, with_parts, also):
+    """query_losses(also=...) evaluates extra heads forward-only in the same launch (they share the feature gather with the loss heads):
+    values equal query()'s, the loss terms and their gradient are unchanged by the extra heads."""
+    B, N = 2, 257
+    images, points, crop, body = synthetic_frames(B, size=64, seed=111, n_points=N, jitter=True)
+    net.filter(images.cuda())
+    labels = torch.randint(0, 14, (B, N), generator=torch.Generator().manual_seed(9)).cuda() if with_parts else None
+    kw = dict(crop_center=crop.cuda(), body_center=body.cuda(), df_channel=1, clamp_max=0.8, part_labels=labels)
+    p0 = points.cuda().requires_grad_(True)
+    v0, c0 = net.query_losses(p0, **kw)
+    (v0.sum() + (c0.sum() if c0 is not None else 0.0)).backward()
+    p1 = points.cuda().requires_grad_(True)
+    v1, c1, extra = net.query_losses(p1, also=also, **kw)
+    (v1.sum() + (c1.sum() if c1 is not None else 0.0)).backward()
+    net.check()
+    assert torch.equal(v0, v1) and torch.equal(p0.grad, p1.grad)
+    net.query(points.cuda(), crop_center=crop.cuda(), body_center=body.cuda())
+    full = dict(zip(("df", "pca", "parts", "centers", "visibility"), net.get_preds()))
+    for h in also:
+        assert torch.equal(extra[h], full[h]), h

@@ -38,6 +38,8 @@ struct TbParams {
   float* vals_df;          // [B][N] clamp(df[df_idx], max=threshold)
   float* vals_ce;          // [B][N] cross-entropy of the 14 part logits against labels
   float* g_points2;        // [B][N][3] d CE / d point
+  int fwd_mask;            // mode 2: heads evaluated forward-only (they share the gather; no backward) ...
+  float* out_fwd;          // ... into the packed [B][29][N] prediction buffer
   long long* trace;        // debug (VT_QUERY_TRACE=1): clock64 stamps of CTA (0,0): [0..15] epilogue thread 0, [16..31] gather warp 0
 };
 
@@ -78,7 +80,8 @@ query_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_c
   uint8_t* act_ptr = smem_al + 2 * TQ_SLOT + TQ_NW * TQ_SLOT;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.y, n0 = blockIdx.x * TQ_M;
-  const int heads = prm.mode == 1 ? 1 : prm.mode == 2 ? (prm.labels ? 5 : 1) : prm.head_mask;
+  const int heads = prm.mode == 1 ? 1 : prm.mode == 2 ? ((prm.labels ? 5 : 1) | prm.fwd_mask) : prm.head_mask;
+  auto fwd_only = [&](int h) { return prm.mode == 2 && ((prm.fwd_mask >> h) & 1) != 0; };
   // heads are processed in pairs that share ONE forward gather: both first layers accumulate from the same feature chunks (TMEM
   // columns 0-127 and 128-255), then each head runs its own forward / backward chain and backward gather; gf slots start at column 256
   const int n_heads = __popc((unsigned)heads), n_pairs = (n_heads + 1) >> 1;
@@ -201,6 +204,7 @@ query_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_c
       for (int pj = 0; pj < 2; ++pj) {
       const int h = pair_head(pi, pj);
       if (h < 0) break;
+      if (fwd_only(h)) continue;
       // ---- backward: contract the staged feature gradients with d(feature)/d(u, v) (second gather of the same taps)
       for (int c = 0; c < TQ_NCHUNK; ++c, ++sc) {
         const int slot = sc & 1;
@@ -342,6 +346,7 @@ query_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_c
           if (h < 0) break;
           for (int layer = 0; layer < 2; ++layer)
             for (int kc = 0; kc < 2; ++kc) load(&tm_w23_hi, &tm_w23_lo, kc * TQ_KC, (layer * 5 + h) * TQ_H);
+          if (fwd_only(h)) continue;
           for (int layer = 1; layer >= 0; --layer)
             for (int kc = 0; kc < 2; ++kc) load(&tm_w23t_hi, &tm_w23t_lo, kc * TQ_KC, (layer * 5 + h) * TQ_H);
           for (int u = 0; u < TQ_NCHUNK / 2; ++u)
@@ -382,14 +387,16 @@ query_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_c
         tq_commit(tq_smem_u32(&acc_full));
         for (int pj = 0; pj < (two ? 2 : 1); ++pj) {
           const uint32_t acc = tmem_base + pj * TQ_H;
-          for (int stage = 0; stage < 4; ++stage) {                     // F2, F3, B3, B2: act buffer -> this head's accumulator
+          const bool fo = fwd_only(pair_head(pi, pj));
+          for (int stage = 0; stage < (fo ? 2 : 4); ++stage) {          // F2, F3, B3, B2: act buffer -> this head's accumulator
             tq_mbar_wait(tq_smem_u32(&act_full), (uint32_t)iact & 1u); ++iact;
             tq_fence_after();
             for (int kc = 0; kc < 2; ++kc) mma_tile(act_base + kc * TQ_SLOT, acc, kc == 0);
             tq_commit(tq_smem_u32(&acc_full));
           }
-          tq_mbar_wait(tq_smem_u32(&act_full), (uint32_t)iact & 1u); ++iact;   // g1 is in the act buffer
-          tq_fence_after();
+          tq_mbar_wait(tq_smem_u32(&act_full), (uint32_t)iact & 1u); ++iact;   // g1 is in the act buffer (forward-only head: its
+          tq_fence_after();                                                    // accumulator has been read out and may be reused)
+          if (fo) continue;
           for (int u = 0; u < TQ_NCHUNK / 2; ++u, ++gfi) {              // B1: five groups of 128 feature-gradient columns
             const int gs = gfi % TB_NGF;
             tq_mbar_wait(tq_smem_u32(&gf_empty[gs]), ((uint32_t)(gfi / TB_NGF) & 1u) ^ 1u);
@@ -493,11 +500,25 @@ query_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_c
         if (layer < 2) publish_act();
         TB_STAMP();
       }
+      const int nout = h == 0 ? 2 : h == 1 ? 9 : h == 2 ? 14 : h == 3 ? 3 : 1;
+      const int hoff = h == 0 ? 0 : h == 1 ? 2 : h == 2 ? 11 : h == 3 ? 25 : 28;
+      if (fwd_only(h)) {                         // predictions only: write them, hand the accumulator back, next head
+        if (n < N) {
+#pragma unroll
+          for (int c = 0; c < 14; ++c) {
+            if (c >= nout) break;
+            float val = o[c] + s_w4[TQ_H * 16 + c];
+            if (h == 4) val = 1.f / (1.f + expf(-val));
+            if (h == 0 && !s_in_img[r]) val = cam.out_dist;
+            prm.out_fwd[((size_t)b * 29 + hoff + c) * N + n] = val;
+          }
+        }
+        publish_act();
+        continue;
+      }
       // ---- cotangent at the head outputs, normalised per point
       float g4[14];
       float gmax = 0.f;
-      const int nout = h == 0 ? 2 : h == 1 ? 9 : h == 2 ? 14 : h == 3 ? 3 : 1;
-      const int hoff = h == 0 ? 0 : h == 1 ? 2 : h == 2 ? 11 : h == 3 ? 25 : 28;
 #pragma unroll
       for (int c = 0; c < 14; ++c) {
         float g = 0.f;
@@ -694,7 +715,7 @@ int vt_query_bwd_tc(const float* points, const float* crop_center, const float* 
   if (B <= 0 || N <= 0) return 0;
   if (head_mask == 0) return cudaMemsetAsync(g_points, 0, (size_t)B * N * 3 * sizeof(float), (cudaStream_t)stream) == cudaSuccess ? 0 : -3;
   const void* planes[8] = {w1_hi, w1_lo, w23_hi, w23_lo, w23t_hi, w23t_lo, w1t_hi, w1t_lo};
-  TbParams prm{g_out, g_points, nullptr, 0, 0, head_mask, 0.f, nullptr, nullptr, nullptr, nullptr, nullptr};
+  TbParams prm{g_out, g_points, nullptr, 0, 0, head_mask, 0.f, nullptr, nullptr, nullptr, nullptr, 0, nullptr, nullptr};
   return launch_bwd_tc(points, crop_center, body_center, B, N, im_feat, tmpx, tri_tmpx, tri_feat, Hf, Wf, Ht, Wt, cam7, wpack, planes, prm,
                        overflow, (cudaStream_t)stream, "vt_query_bwd_tc");
 }
@@ -708,7 +729,7 @@ int vt_query_project_step_tc(const float* points, const float* crop_center, cons
   VT_CHECK_ARG(points_out != nullptr && overflow != nullptr, "vt_query_project_step_tc: points_out and overflow are required");
   if (B <= 0 || N <= 0) return 0;
   const void* planes[8] = {w1_hi, w1_lo, w23_hi, w23_lo, w23t_hi, w23t_lo, w1t_hi, w1t_lo};
-  TbParams prm{nullptr, g_points, points_out, 1, df_idx, 1, threshold, nullptr, nullptr, nullptr, nullptr, nullptr};
+  TbParams prm{nullptr, g_points, points_out, 1, df_idx, 1, threshold, nullptr, nullptr, nullptr, nullptr, 0, nullptr, nullptr};
   return launch_bwd_tc(points, crop_center, body_center, B, N, im_feat, tmpx, tri_tmpx, tri_feat, Hf, Wf, Ht, Wt, cam7, wpack, planes, prm,
                        overflow, (cudaStream_t)stream, "vt_query_project_step_tc");
 }
@@ -717,13 +738,15 @@ int vt_query_losses_tc(const float* points, const float* crop_center, const floa
                        const float* tmpx, const float* tri_tmpx, const float* tri_feat, int Hf, int Wf, int Ht, int Wt, const float* cam7,
                        const float* wpack, const void* w1_hi, const void* w1_lo, const void* w23_hi, const void* w23_lo, const void* w23t_hi,
                        const void* w23t_lo, const void* w1t_hi, const void* w1t_lo, int df_idx, float clamp_max, const long long* part_labels,
-                       float* vals_df, float* g_df, float* vals_ce, float* g_ce, int* overflow, void* stream) {
+                       float* vals_df, float* g_df, float* vals_ce, float* g_ce, int fwd_mask, float* out_fwd, int* overflow, void* stream) {
   VT_CHECK_ARG(df_idx == 0 || df_idx == 1, "vt_query_losses_tc: df_idx %d (0 human, 1 object)", df_idx);
+  VT_CHECK_ARG(fwd_mask >= 0 && fwd_mask < 32 && !(fwd_mask & 1) && !(part_labels && (fwd_mask & 4)) && (fwd_mask == 0 || out_fwd != nullptr),
+               "vt_query_losses_tc: forward-only head mask %d (not the loss heads; needs out_fwd)", fwd_mask);
   VT_CHECK_ARG(vals_df != nullptr && g_df != nullptr && overflow != nullptr, "vt_query_losses_tc: vals_df, g_df and overflow are required");
   VT_CHECK_ARG(part_labels == nullptr || (vals_ce != nullptr && g_ce != nullptr), "vt_query_losses_tc: part_labels need vals_ce and g_ce");
   if (B <= 0 || N <= 0) return 0;
   const void* planes[8] = {w1_hi, w1_lo, w23_hi, w23_lo, w23t_hi, w23t_lo, w1t_hi, w1t_lo};
-  TbParams prm{nullptr, g_df, nullptr, 2, df_idx, 0, clamp_max, part_labels, vals_df, vals_ce, g_ce, nullptr};
+  TbParams prm{nullptr, g_df, nullptr, 2, df_idx, 0, clamp_max, part_labels, vals_df, vals_ce, g_ce, fwd_mask, out_fwd, nullptr};
   return launch_bwd_tc(points, crop_center, body_center, B, N, im_feat, tmpx, tri_tmpx, tri_feat, Hf, Wf, Ht, Wt, cam7, wpack, planes, prm,
                        overflow, (cudaStream_t)stream, "vt_query_losses_tc");
 }

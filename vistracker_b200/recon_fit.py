@@ -237,10 +237,9 @@ class ReconFitterTriVisFull:
             df_pred, centers_pred_o, part_o = preds[0], preds[3], preds[2]
             vals_df_o = torch.clamp(df_pred[:, 1, :], max=0.8)
         else:
-            # distance term + its gradient from the fused launch; the centre head (reported only, weight 0) forward-only
-            vals_df_o, _ = self.model.query_losses(object, df_channel=1, clamp_max=0.8, **data_dict["query_dict"])
-            with torch.no_grad():
-                centers_pred_o = self.model.query_heads(object, ("centers",), **data_dict["query_dict"])["centers"]
+            # distance term + its gradient from the fused launch; the centre head (reported only, weight 0) rides along forward-only
+            vals_df_o, _, extra = self.model.query_losses(object, df_channel=1, clamp_max=0.8, also=("centers",), **data_dict["query_dict"])
+            centers_pred_o = extra["centers"]
             df_pred = part_o = None
         if phase != "sil":
             obj_center_pred = data_dict["smpl_center"] + torch.mean(centers_pred_o, -1)           # recon_fit_behave.py:370-380

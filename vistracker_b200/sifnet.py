@@ -60,22 +60,26 @@ class _QueryLossFn(torch.autograd.Function):
     """Per-point fitting-loss terms with their point gradients from ONE launch (vt_query_losses_tc); backward is two multiplies."""
 
     @staticmethod
-    def forward(ctx, net: "CHORETriplaneVisibility", points, crop_center, body_center, df_channel, clamp_max, part_labels):
-        vals_df, g_df, vals_ce, g_ce = net._query_losses_raw(points, crop_center, body_center, df_channel, clamp_max, part_labels)
+    def forward(ctx, net: "CHORETriplaneVisibility", points, crop_center, body_center, df_channel, clamp_max, part_labels, fwd_mask):
+        vals_df, g_df, vals_ce, g_ce, out_fwd = net._query_losses_raw(points, crop_center, body_center, df_channel, clamp_max, part_labels,
+                                                                      fwd_mask)
         ctx.has_ce = vals_ce is not None
         ctx.save_for_backward(*((g_df, g_ce) if ctx.has_ce else (g_df,)))
         if not ctx.has_ce:
             vals_ce = vals_df.new_zeros(())
             ctx.mark_non_differentiable(vals_ce)
-        return vals_df, vals_ce
+        if out_fwd is None:
+            out_fwd = vals_df.new_zeros(())
+        ctx.mark_non_differentiable(out_fwd)
+        return vals_df, vals_ce, out_fwd
 
     @staticmethod
-    def backward(ctx, grad_df, grad_ce):
+    def backward(ctx, grad_df, grad_ce, _grad_out):
         saved = ctx.saved_tensors
         g = grad_df.unsqueeze(-1) * saved[0]
         if ctx.has_ce and grad_ce is not None:
             g = g + grad_ce.unsqueeze(-1) * saved[1]
-        return None, g, None, None, None, None, None
+        return None, g, None, None, None, None, None, None
 
 
 class CHORETriplaneVisibility:
@@ -338,7 +342,7 @@ class CHORETriplaneVisibility:
                       _lib.ptr(self._wpack_bwd), _lib.ptr(g), int(head_mask), _lib.ptr(g_pts), _lib.stream_ptr())
         return g_pts
 
-    def _query_losses_raw(self, points, crop_center, body_center, df_channel, clamp_max, part_labels):
+    def _query_losses_raw(self, points, crop_center, body_center, df_channel, clamp_max, part_labels, fwd_mask=0):
         im_feat, tmpx, tri_tmpx, tri_feat = self._maps
         B, N = points.shape[0], points.shape[1]
         pts = points.detach().to(self.device, torch.float32).contiguous()
@@ -352,25 +356,28 @@ class CHORETriplaneVisibility:
             if tuple(labels.shape) != (B, N):
                 raise ValueError(f"part_labels must be [B, N] = {(B, N)}, got {tuple(labels.shape)}")
             vals_ce, g_ce = torch.empty_like(vals_df), torch.empty_like(g_df)
+        out_fwd = torch.empty(B, N_OUT, N, dtype=torch.float32, device=self.device) if fwd_mask else None
         with torch.cuda.device(self.device):
             _lib.call("vt_query_losses_tc", _lib.ptr(pts), _lib.ptr(cc), _lib.ptr(bc), B, N, _lib.ptr(im_feat), _lib.ptr(tmpx),
                       _lib.ptr(tri_tmpx), _lib.ptr(tri_feat), im_feat.shape[1], im_feat.shape[2], tmpx.shape[1], tmpx.shape[2],
                       self._cam7, _lib.ptr(self._wpack), *(_lib.ptr(t) for t in self._wtc), *(_lib.ptr(t) for t in self._wtc_bwd),
                       int(df_channel), float(clamp_max), _lib.ptr(labels), _lib.ptr(vals_df), _lib.ptr(g_df), _lib.ptr(vals_ce),
-                      _lib.ptr(g_ce), _lib.ptr(self._q_overflow), _lib.stream_ptr())
-        return vals_df, g_df, vals_ce, g_ce
+                      _lib.ptr(g_ce), int(fwd_mask), _lib.ptr(out_fwd), _lib.ptr(self._q_overflow), _lib.stream_ptr())
+        return vals_df, g_df, vals_ce, g_ce, out_fwd
 
-    def query_losses(self, points, crop_center=None, df_channel=0, clamp_max=0.1, part_labels=None, **kwargs):
+    def query_losses(self, points, crop_center=None, df_channel=0, clamp_max=0.1, part_labels=None, also=(), **kwargs):
         """The query-dependent loss terms of the fitters as per-point tensors, differentiable w.r.t. ``points``:
         ``clamp(df[:, df_channel], max=clamp_max)`` [B, N] and (with ``part_labels`` [B, N]) ``F.cross_entropy(parts, labels,
         reduction='none')`` [B, N] -- the quantities of recon_fit_behave.py:471-476 / recon_fit_trivis_full.py:235, computed with their
         gradients by one fused launch instead of query() + autograd (an extension of the reference interface; results match
-        ``query()`` followed by the same torch expressions)."""
+        ``query()`` followed by the same torch expressions).  ``also``: names of further heads ('pca', 'parts', 'centers', 'visibility')
+        whose predictions are wanted without gradient; they ride on the same launch and come back as a third value, a dict."""
         body_center = kwargs.get("body_center")
         if crop_center is None or body_center is None:
             raise ValueError("query_losses() needs crop_center and body_center")
         if self._maps is None:
             raise RuntimeError("filter() must be called before query_losses()")
+        names = ("df", "pca", "parts", "centers", "visibility")
         if self.query_on_cuda_cores:             # cross-check path: compose the same terms from query() + autograd
             self.query(points, crop_center=crop_center, body_center=body_center)
             df, _, parts = self.preds[0], self.preds[1], self.preds[2]
@@ -378,9 +385,21 @@ class CHORETriplaneVisibility:
             vals_ce = None
             if part_labels is not None:
                 vals_ce = torch.nn.functional.cross_entropy(parts, part_labels.to(parts.device), reduction="none")
+            if also:
+                full = dict(zip(names, self.preds))
+                return vals_df, vals_ce, {h: full[h].detach() for h in also}
             return vals_df, vals_ce
-        vals_df, vals_ce = _QueryLossFn.apply(self, points, crop_center, body_center, df_channel, clamp_max, part_labels)
-        return vals_df, (vals_ce if part_labels is not None else None)
+        fwd_mask = sum(1 << names.index(h) for h in also)
+        vals_df, vals_ce, out_fwd = _QueryLossFn.apply(self, points, crop_center, body_center, df_channel, clamp_max, part_labels, fwd_mask)
+        vals_ce = vals_ce if part_labels is not None else None
+        if also:
+            B, N = points.shape[0], points.shape[1]
+            extra = {}
+            for h in also:
+                lo, hi = HEAD_SLICES[names.index(h)]
+                extra[h] = out_fwd[:, lo:hi].reshape(B, 3, 3, N) if h == "pca" else out_fwd[:, lo:hi]
+            return vals_df, vals_ce, extra
+        return vals_df, vals_ce
 
     def query_heads(self, points, heads, crop_center=None, **kwargs):
         """Forward-only query of a subset of the decoder heads (names from 'df', 'pca', 'parts', 'centers', 'visibility'): returns a
