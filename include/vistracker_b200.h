@@ -269,6 +269,11 @@ int vt_raster_bwd(const float* verts, const int* faces, int B, int V, int F, int
                   const float* faces_ndc, const int* face_index, const float* alpha, const float* g_alpha, float* g_faces,
                   float* g_verts, void* stream);
 
+/* Evaluation Chamfer (the "Chamfer vs ref" half of the metric): per-point Euclidean nearest-neighbour distances between
+ * dense clouds, both directions -- recon/eval/chamfer_distance.py:10-52 is mean(dist_x) + mean(dist_y) per frame (sklearn kd-tree there).
+ * x[B][nx][3], y[B][ny][3] -> dist_x[B][nx] (every x_i to its nearest y), dist_y[B][ny]. */
+int vt_nn_dist(const float* x, int nx, const float* y, int ny, int B, float* dist_x, float* dist_y, void* stream);
+
 /* ---- SmoothNet stage: smoothnet/smooth_smplt.py, smooth_objrot.py, smooth_base.py, models/smoothnet*.py,
  *      utils/utils.py:63-103, utils/geometry_utils.py -- the trajectory stays in device memory between the fitting stages ---- */
 

@@ -35,3 +35,14 @@ def chamfer_ragged(xs: List[torch.Tensor], ys: List[torch.Tensor]) -> torch.Tens
         d = ((x[:, None, :] - y[None, :, :]) ** 2).sum(-1)
         total = total + d.min(1).values.mean() + d.min(0).values.mean()
     return total / n
+
+
+def eval_chamfer(x, y, direction="bi"):
+    """recon/eval/chamfer_distance.py:10-52 restated with a brute-force float64 nearest neighbour (the reference uses an exact sklearn
+    kd-tree on the same metric, so the two agree to rounding): mean Euclidean NN distance, both directions summed for 'bi'.
+    Pinned by tests/golden/eval_chamfer.npz (the reference function itself, run by tests/golden/make_golden.py --only eval)."""
+    import numpy as np
+    x, y = np.asarray(x, np.float64), np.asarray(y, np.float64)
+    d = np.sqrt(((x[:, None, :] - y[None, :, :]) ** 2).sum(-1))
+    x_to_y, y_to_x = d.min(1).mean(), d.min(0).mean()
+    return {"bi": x_to_y + y_to_x, "x_to_y": x_to_y, "y_to_x": y_to_x}[direction]

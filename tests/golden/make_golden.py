@@ -14,6 +14,7 @@ seeded synthetic checkpoint of ``vistracker_b200.synth`` and stores inputs-by-se
 * ``sifnet_c1.npz``         -- BASELINE config 1 (1 frame 512x512, 2000 points): the five heads in full and
                                every 8th pixel of each feature map
 * ``smpl_small.npz``        -- SMPL_Layer.forward on the synthetic SMPL-H model, B=5, outputs + gradients
+* ``eval_chamfer.npz``      -- recon/eval/chamfer_distance.py (sklearn kd-tree) on three cloud pairs, all three directions
 * ``smooth_small.npz``      -- (``--only smooth``) SmoothNetSMPL / SmoothNet through SMPLTSmoother / ObjrotSmoother pre- and
                                post-processing on a 90-frame synthetic trajectory, window 64, + the rotation conversions
 """
@@ -369,6 +370,21 @@ def smooth_goldens(out_dir: str):
     print("smooth_small.npz:", {k: getattr(v, "shape", v) for k, v in out.items() if not k.startswith(("smplt.", "objrot."))})
 
 
+def eval_goldens(out_dir: str):
+    """Evaluation Chamfer: recon/eval/chamfer_distance.py run as is (sklearn kd-tree) -> eval_chamfer.npz."""
+    from recon.eval.chamfer_distance import chamfer_distance                          # reference
+    rng = np.random.default_rng(21)
+    out = {}
+    for i, (n, m) in enumerate(((700, 900), (1, 50), (1500, 1500))):
+        x = rng.standard_normal((n, 3)).astype(np.float32) * 0.4
+        y = (x[rng.integers(0, n, m)] + 0.02 * rng.standard_normal((m, 3))).astype(np.float32) if i != 1 else rng.standard_normal((m, 3)).astype(np.float32)
+        out[f"x{i}"], out[f"y{i}"] = x, y
+        for d in ("bi", "x_to_y", "y_to_x"):
+            out[f"cd{i}_{d}"] = np.float64(chamfer_distance(x, y, direction=d))
+    np.savez_compressed(os.path.join(out_dir, "eval_chamfer.npz"), **out)
+    print("eval_chamfer.npz:", {k: float(v) for k, v in out.items() if k.startswith("cd")})
+
+
 def asset_fixtures(out_dir: str, ref_root: str):
     """Numeric assets the reference ships for this path, re-serialised without scipy / pickle:
     the body-25 landmark regressor (COO), the pose / hand priors and the 14-part vertex labels."""
@@ -410,5 +426,7 @@ if __name__ == "__main__":
         fit_smplt_goldens(HERE)
     if a.only in ("", "recon"):
         recon_goldens(HERE)
+    if a.only in ("", "eval"):
+        eval_goldens(HERE)
     if a.only == "smooth":                  # stubs `behave` / `yacs`: run on its own
         smooth_goldens(HERE)

@@ -65,3 +65,31 @@ def test_ragged_chamfer_forward_backward():
     assert abs(float(out) - float(ref)) < 1e-5 * abs(float(ref))
     for a, b in zip(gx + gy, rx + ry):
         assert rel_err(a.grad.cpu(), b.grad) < 1e-5
+
+
+def test_eval_chamfer_matches_reference_golden_and_oracle():
+    """vt_nn_dist through geom.eval_chamfer_distance: the reference function's values (sklearn kd-tree, eval_chamfer.npz), all three
+    directions, single clouds and a batch of BASELINE-sized clouds (10 000 samples) against the float64 restatement."""
+    import os
+    import numpy as np
+    from oracle import geom_ref as GR
+    from vistracker_b200.geom import eval_chamfer_distance
+    _need_gpu()
+    dev = lambda: torch.device("cuda", 0)
+    gold = np.load(os.path.join(os.path.dirname(__file__), "golden", "eval_chamfer.npz"))
+    for i in range(3):
+        x, y = torch.from_numpy(gold[f"x{i}"]).to(dev()), torch.from_numpy(gold[f"y{i}"]).to(dev())
+        for d in ("bi", "x_to_y", "y_to_x"):
+            got, ref = float(eval_chamfer_distance(x, y, d)), float(gold[f"cd{i}_{d}"])
+            assert abs(got - ref) <= 2e-6 * max(1.0, abs(ref)), (i, d, got, ref)
+    g = torch.Generator().manual_seed(5)
+    xb = torch.randn(3, 10000, 3, generator=g) * 0.5
+    yb = xb[:, torch.randperm(10000, generator=g)[:9000]] + 0.01 * torch.randn(3, 9000, 3, generator=g)
+    got = eval_chamfer_distance(xb.to(dev()), yb.to(dev())).cpu()
+    for b in range(3):
+        ref = GR.eval_chamfer(xb[b, ::1].numpy()[:2000], yb[b].numpy(), "x_to_y")          # float64 brute force on a slice (memory)
+        sub = float(eval_chamfer_distance(xb[b, :2000].to(dev()), yb[b].to(dev()), "x_to_y"))
+        assert abs(sub - ref) <= 2e-6 * max(1.0, ref)
+    assert got.shape == (3,) and bool((got > 0).all())
+    with pytest.raises(ValueError, match="Invalid direction"):
+        eval_chamfer_distance(xb[0].to(dev()), yb[0].to(dev()), "xy")

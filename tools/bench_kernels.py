@@ -150,4 +150,10 @@ ms = timeit(lambda: _sm.smooth(_poses, _betas, _trans))
 _rows = (_T - WINDOW + 1) * 147
 row("SmoothNet SMPL-T smoothing, 1500 frames (pack + 2 x clips MLP + window mean + unpack)", ms, _T, "frames", None, _rows * 2 * 81920 / _T,
     f"{_rows} (window, channel) rows x 81.9 kMAC, fp32 FFMA")
+# ---------------------------------------------------------------- evaluation Chamfer (8(f) N4): 10 000 samples per mesh
+from vistracker_b200.geom import eval_chamfer_distance  # noqa: E402
+_xa, _ya = torch.randn(16, 10000, 3, device=dev), torch.randn(16, 10000, 3, device=dev)
+ms = timeit(lambda: eval_chamfer_distance(_xa, _ya))
+row("evaluation Chamfer, 16 frames x (10 000 vs 10 000 points), both directions", ms, 16, "frames", 2 * 10000 * 12 + 2 * 10000 * 4, 2 * 1e8 * 8,
+    "brute force, other cloud streamed through shared memory; 8 flop per pair")
 print(json.dumps({"peaks": peaks, "rows": rows}, indent=1))

@@ -153,6 +153,37 @@ __global__ void __launch_bounds__(128) chamfer_bwd_kernel(const float* __restric
   }
 }
 
+// ------------------------------------------------------------------------------------------------ evaluation Chamfer (dense clouds)
+// recon/eval/chamfer_distance.py:10-52: mean Euclidean (NOT squared) nearest-neighbour distance, evaluated on 10 000 surface samples per
+// mesh (recon/eval/evaluate.py:43,126-154).  One thread per query point, the other cloud streamed through shared memory in 256-point tiles;
+// blockIdx.z = direction (0: every x_i against y, 1: every y_j against x).  Writes the per-point distances; the means stay with the caller.
+__global__ void __launch_bounds__(256) nn_dist_kernel(const float* __restrict__ x, int nx, const float* __restrict__ y, int ny,
+                                                      float* __restrict__ dx_out, float* __restrict__ dy_out) {
+  __shared__ float sp[256 * 3];
+  const int b = blockIdx.y, dir = blockIdx.z;
+  const float* q = (dir == 0 ? x + (size_t)b * nx * 3 : y + (size_t)b * ny * 3);
+  const float* r = (dir == 0 ? y + (size_t)b * ny * 3 : x + (size_t)b * nx * 3);
+  const int nq = dir == 0 ? nx : ny, nr = dir == 0 ? ny : nx;
+  float* out = dir == 0 ? dx_out + (size_t)b * nx : dy_out + (size_t)b * ny;
+  if ((int)(blockIdx.x * 256) >= nq) return;                 // whole block beyond this direction's cloud
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  const bool live = i < nq;
+  const float px = live ? q[i * 3] : 0.f, py = live ? q[i * 3 + 1] : 0.f, pz = live ? q[i * 3 + 2] : 0.f;
+  float best = 3.4e38f;
+  for (int j0 = 0; j0 < nr; j0 += 256) {
+    const int cnt = min(256, nr - j0);
+    __syncthreads();
+    for (int t = threadIdx.x; t < cnt * 3; t += 256) sp[t] = r[(size_t)j0 * 3 + t];
+    __syncthreads();
+#pragma unroll 4
+    for (int j = 0; j < cnt; ++j) {
+      const float ddx = px - sp[j * 3], ddy = py - sp[j * 3 + 1], ddz = pz - sp[j * 3 + 2];
+      best = fminf(best, ddx * ddx + ddy * ddy + ddz * ddz);
+    }
+  }
+  if (live) out[i] = sqrtf(best);
+}
+
 }  // namespace vt
 
 using namespace vt;
@@ -188,6 +219,16 @@ int vt_chamfer_bwd(const float* x, const int* x_off, const float* y, const int* 
   if (N <= 0) return 0;
   chamfer_bwd_kernel<<<N, 128, 0, (cudaStream_t)stream>>>(x, x_off, y, y_off, N, nn_x, nn_y, g_loss, gx, gy);
   VT_CHECK_LAUNCH("vt_chamfer_bwd");
+  return 0;
+}
+
+int vt_nn_dist(const float* x, int nx, const float* y, int ny, int B, float* dist_x, float* dist_y, void* stream) {
+  VT_CHECK_ARG(nx > 0 && ny > 0 && B > 0, "vt_nn_dist: empty clouds (%d x %d points, batch %d)", nx, ny, B);
+  VT_CHECK_ARG(dist_x != nullptr && dist_y != nullptr, "vt_nn_dist: both outputs are required");
+  const int n = nx > ny ? nx : ny;
+  dim3 grid(ceil_div(n, 256), B, 2);
+  nn_dist_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, nx, y, ny, dist_x, dist_y);
+  VT_CHECK_LAUNCH("vt_nn_dist");
   return 0;
 }
 

@@ -84,3 +84,23 @@ def chamfer_distance_ragged(xs: List[torch.Tensor], ys: List[torch.Tensor]) -> t
 def chamfer_distance_packed(x: torch.Tensor, y: torch.Tensor, x_off: torch.Tensor, y_off: torch.Tensor) -> torch.Tensor:
     """Same operator on already-packed clouds: x [sum n_i, 3], y [sum m_i, 3] with int32 row offsets [N + 1] each."""
     return _ChamferFn.apply(x, y, x_off, y_off)
+
+
+def eval_chamfer_distance(x: torch.Tensor, y: torch.Tensor, direction: str = "bi") -> torch.Tensor:
+    """``chamfer_distance`` of recon/eval/chamfer_distance.py:10-52 for batches of dense clouds x [B, n, 3], y [B, m, 3] (or single
+    [n, 3] clouds): mean Euclidean nearest-neighbour distance, 'x_to_y', 'y_to_x' or 'bi' (the sum of both) -- one value per frame,
+    in the input's units (the reference reports it x100 as centimetres, recon/eval/evaluate.py:126-154)."""
+    from . import _lib
+    if direction not in ("bi", "x_to_y", "y_to_x"):
+        raise ValueError("Invalid direction type. Supported types: 'y_x', 'x_y', 'bi'")
+    single = x.dim() == 2
+    xb, yb = (x[None] if single else x).float().contiguous(), (y[None] if single else y).float().contiguous()
+    if not xb.is_cuda:
+        raise RuntimeError("vistracker_b200 has no CPU path: eval_chamfer_distance needs CUDA tensors")
+    B, n, m = xb.shape[0], xb.shape[1], yb.shape[1]
+    dx, dy = torch.empty(B, n, device=xb.device), torch.empty(B, m, device=xb.device)
+    with torch.cuda.device(xb.device):
+        _lib.call("vt_nn_dist", _lib.ptr(xb), n, _lib.ptr(yb), m, B, _lib.ptr(dx), _lib.ptr(dy), _lib.stream_ptr())
+    out = {"x_to_y": dx.mean(1), "y_to_x": dy.mean(1)}
+    res = out["x_to_y"] + out["y_to_x"] if direction == "bi" else out[direction]
+    return res[0] if single else res
