@@ -274,6 +274,12 @@ int vt_raster_bwd(const float* verts, const int* faces, int B, int V, int F, int
  * x[B][nx][3], y[B][ny][3] -> dist_x[B][nx] (every x_i to its nearest y), dist_y[B][ny]. */
 int vt_nn_dist(const float* x, int nx, const float* y, int ny, int B, float* dist_x, float* dist_y, void* stream);
 
+/* compute_transform (recon/eval/pose_utils.py:153-198): the similarity transform (scale, R, t) that takes cloud S1 closest to S2 in the
+ * least-squares sense (orthogonal Procrustes with det R = +1), per pair of clouds S1/S2[B][N][3].  workspace: 16 doubles per pair (zeroed
+ * by the call).  R[B][9] row-major, t[B][3], scale[B].  vt_similarity_apply: out = scale * R p + t (pose_utils.py:31). */
+int vt_procrustes(const float* S1, const float* S2, int N, int B, double* workspace, float* R, float* t, float* scale, void* stream);
+int vt_similarity_apply(const float* points, int n, int B, const float* R, const float* t, const float* scale, float* out, void* stream);
+
 /* ---- SmoothNet stage: smoothnet/smooth_smplt.py, smooth_objrot.py, smooth_base.py, models/smoothnet*.py,
  *      utils/utils.py:63-103, utils/geometry_utils.py -- the trajectory stays in device memory between the fitting stages ---- */
 

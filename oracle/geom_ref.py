@@ -46,3 +46,53 @@ def eval_chamfer(x, y, direction="bi"):
     d = np.sqrt(((x[:, None, :] - y[None, :, :]) ** 2).sum(-1))
     x_to_y, y_to_x = d.min(1).mean(), d.min(0).mean()
     return {"bi": x_to_y + y_to_x, "x_to_y": x_to_y, "y_to_x": y_to_x}[direction]
+
+
+def compute_transform(S1, S2):
+    """recon/eval/pose_utils.py:153-198 restated (float64 numpy SVD): (R, t, scale) with scale * R @ p + t taking S1 [N, 3] onto S2."""
+    import numpy as np
+    S1, S2 = np.asarray(S1, np.float64).T, np.asarray(S2, np.float64).T
+    mu1, mu2 = S1.mean(axis=1, keepdims=True), S2.mean(axis=1, keepdims=True)
+    X1, X2 = S1 - mu1, S2 - mu2
+    var1 = np.sum(X1 ** 2)
+    K = X1.dot(X2.T)
+    U, s, Vh = np.linalg.svd(K)
+    V = Vh.T
+    Z = np.eye(3)
+    Z[-1, -1] *= np.sign(np.linalg.det(U.dot(V.T)))
+    R = V.dot(Z.dot(U.T))
+    scale = np.trace(R.dot(K)) / var1
+    t = mu2 - scale * (R.dot(mu1))
+    return R, t[:, 0], scale
+
+
+def evaluate_sequence(sverts_recon, overts_recon, sverts_gt, overts_gt, window, recon_exist=None, smpl_only=False):
+    """The alignment-window loop of VideoPackedEvaluator.eva_seq (recon/eval/evalvideo_packed.py:100-147) restated on plain arrays, with
+    the Chamfer distance evaluated on the vertices (the reference's trimesh surface samples are unseeded random draws): rows of
+    (Chamfer SMPL, Chamfer object, v2v SMPL, v2v object) in cm for every frame that has a reconstruction."""
+    import numpy as np
+    L = len(sverts_gt)
+    exist = np.ones(L, bool) if recon_exist is None else np.asarray(recon_exist, bool)
+    count, arot, out = 0, None, []
+    for i in range(L):
+        count += 1
+        rec = [np.asarray(sverts_recon[i], np.float64), np.asarray(overts_recon[i], np.float64)]
+        if window > 0:
+            if arot is None or count % window == 0:
+                idx = np.arange(i, min(L, i + window))
+                idx = idx[exist[idx]]
+                if len(idx) == 0:
+                    continue
+                if smpl_only:
+                    g, r = np.concatenate(sverts_gt[idx], 0), np.concatenate(sverts_recon[idx], 0)
+                else:
+                    g = np.concatenate([np.concatenate(x[idx], 0) for x in (sverts_gt, overts_gt)], 0)
+                    r = np.concatenate([np.concatenate(x[idx], 0) for x in (sverts_recon, overts_recon)], 0)
+                arot, atrans, ascale = compute_transform(r, g)
+            rec = [(ascale * arot.dot(m.T) + atrans[:, None]).T for m in rec]
+        if not exist[i]:
+            continue
+        gt = [np.asarray(sverts_gt[i], np.float64), np.asarray(overts_gt[i], np.float64)]
+        row = [eval_chamfer(g, r) * 100.0 for g, r in zip(gt, rec)] + [np.sqrt(((g - r) ** 2).sum(-1)).mean() * 100.0 for g, r in zip(gt, rec)]
+        out.append(row)
+    return np.asarray(out)

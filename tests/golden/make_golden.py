@@ -381,6 +381,21 @@ def eval_goldens(out_dir: str):
         out[f"x{i}"], out[f"y{i}"] = x, y
         for d in ("bi", "x_to_y", "y_to_x"):
             out[f"cd{i}_{d}"] = np.float64(chamfer_distance(x, y, direction=d))
+    # Procrustes alignment: compute_transform / compute_similarity_transform of recon/eval/pose_utils.py (psbody is only imported there)
+    _stub("psbody"); _stub("psbody.mesh", Mesh=object)
+    from recon.eval.pose_utils import compute_similarity_transform, compute_transform    # reference
+    for i, n in enumerate((500, 9466)):
+        src = rng.standard_normal((n, 3)) * np.array([0.3, 0.8, 0.2]) + np.array([0.1, -0.2, 2.4])
+        ang = rng.standard_normal(3); ang *= (0.5 + i) / np.linalg.norm(ang)
+        from scipy.spatial.transform import Rotation
+        Rt = Rotation.from_rotvec(ang).as_matrix()
+        dst = (1.0 + 0.2 * i) * src.dot(Rt.T) + np.array([0.4, 0.1, -0.3]) + 0.01 * rng.standard_normal((n, 3))
+        if i == 1:
+            dst[:, 0] *= -1.0                                                          # a reflection: the determinant fix must kick in
+        R, t, sc, _ = compute_transform(src.astype(np.float32).astype(np.float64), dst.astype(np.float32).astype(np.float64))
+        out[f"pa_src{i}"], out[f"pa_dst{i}"] = src.astype(np.float32), dst.astype(np.float32)
+        out[f"pa_R{i}"], out[f"pa_t{i}"], out[f"pa_s{i}"] = R, t[:, 0], np.float64(sc)
+        out[f"pa_hat{i}"] = compute_similarity_transform(src.astype(np.float32).astype(np.float64), dst.astype(np.float32).astype(np.float64))
     np.savez_compressed(os.path.join(out_dir, "eval_chamfer.npz"), **out)
     print("eval_chamfer.npz:", {k: float(v) for k, v in out.items() if k.startswith("cd")})
 

@@ -93,3 +93,26 @@ def test_eval_chamfer_matches_reference_golden_and_oracle():
     assert got.shape == (3,) and bool((got > 0).all())
     with pytest.raises(ValueError, match="Invalid direction"):
         eval_chamfer_distance(xb[0].to(dev()), yb[0].to(dev()), "xy")
+
+
+def test_procrustes_matches_reference_golden():
+    """vt_procrustes / vt_similarity_apply against compute_transform / compute_similarity_transform of recon/eval/pose_utils.py (goldens),
+    including a reflected target (determinant fix) and a batch."""
+    import os
+    import numpy as np
+    from vistracker_b200.geom import apply_similarity, procrustes_transform
+    _need_gpu()
+    dev = torch.device("cuda", 0)
+    gold = np.load(os.path.join(os.path.dirname(__file__), "golden", "eval_chamfer.npz"))
+    for i in range(2):
+        src, dst = torch.from_numpy(gold[f"pa_src{i}"]).to(dev), torch.from_numpy(gold[f"pa_dst{i}"]).to(dev)
+        R, t, s = procrustes_transform(src, dst)
+        assert np.abs(R.cpu().numpy() - gold[f"pa_R{i}"]).max() < 2e-5
+        assert np.abs(t.cpu().numpy() - gold[f"pa_t{i}"]).max() < 5e-5 and abs(float(s) - float(gold[f"pa_s{i}"])) < 2e-5
+        assert abs(float(torch.linalg.det(R.double().cpu())) - 1.0) < 1e-5
+        hat = apply_similarity(src, R, t, s)
+        assert rel_err(hat.cpu(), gold[f"pa_hat{i}"]) < 2e-5
+    a = torch.stack([torch.from_numpy(gold["pa_src0"]), torch.from_numpy(gold["pa_src0"]).flip(0)]).to(dev)
+    b = torch.stack([torch.from_numpy(gold["pa_dst0"]), torch.from_numpy(gold["pa_dst0"]).flip(0)]).to(dev)
+    Rb, tb, sb = procrustes_transform(a, b)
+    assert rel_err(Rb[0].cpu(), Rb[1].cpu()) < 1e-5 and rel_err(Rb[0].cpu(), gold["pa_R0"]) < 2e-5

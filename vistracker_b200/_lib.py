@@ -67,6 +67,8 @@ SIGNATURES.update({
     "vt_chamfer_bwd": (_i, [_p, _p, _p, _p, _i, _p, _p, _p, _p, _p, _p]),
     "vt_query_bwd_heads": (_i, [_p, _p, _p, _i, _i, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _i, _p, _p]),
     "vt_query_project_step": (_i, [_p, _p, _p, _i, _i, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _i, _f, _p, _p, _p, _p]),
+    "vt_procrustes": (_i, [_p, _p, _i, _i, _p, _p, _p, _p, _p]),
+    "vt_similarity_apply": (_i, [_p, _i, _i, _p, _p, _p, _p, _p]),
     "vt_nn_dist": (_i, [_p, _i, _p, _i, _i, _p, _p, _p]),
     "vt_smoothnet_pack_floats": (_ll, [_i]),
     "vt_smooth_pack_smplt": (_i, [_p, _i, _p, _p, _i, _p, _p]),

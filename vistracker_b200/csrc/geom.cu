@@ -184,6 +184,89 @@ __global__ void __launch_bounds__(256) nn_dist_kernel(const float* __restrict__ 
   if (live) out[i] = sqrtf(best);
 }
 
+// ------------------------------------------------------------------------------------------------ Procrustes (similarity) alignment
+// compute_transform (recon/eval/pose_utils.py:153-198): scale, rotation and translation that take point set S1 closest to S2 -- the
+// alignment ProcrusteAlign / VideoPackedEvaluator compute once per window of frames from the combined SMPL + object vertices
+// (pose_utils.py:22-69, evalvideo_packed.py:108-131).  The reference centres, forms K = X1 X2^T, takes a 3x3 SVD and fixes the
+// determinant; R = V Z U^T is the maximiser of tr(R K) over SO(3), i.e. so3_project(K^T) above.  Raw moments are accumulated in
+// double precision (one pass), the 3x3 problem is solved by one thread per pair of clouds.
+__global__ void __launch_bounds__(256) procrustes_moments_kernel(const float* __restrict__ S1, const float* __restrict__ S2, int N,
+                                                                 double* __restrict__ acc /*[B][16]*/) {
+  const int b = blockIdx.y;
+  const float* p1 = S1 + (size_t)b * N * 3;
+  const float* p2 = S2 + (size_t)b * N * 3;
+  double m[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) m[i] = 0.0;
+  for (int i = blockIdx.x * 256 + threadIdx.x; i < N; i += gridDim.x * 256) {
+    const double x[3] = {p1[i * 3], p1[i * 3 + 1], p1[i * 3 + 2]}, y[3] = {p2[i * 3], p2[i * 3 + 1], p2[i * 3 + 2]};
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { m[k] += x[k]; m[3 + k] += y[k]; m[6] += x[k] * x[k]; }
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) m[7 + r * 3 + c] += x[r] * y[c];
+  }
+  __shared__ double red[8][16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    double v = m[i];
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5][i] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < 16) {
+    double v = 0;
+    for (int w = 0; w < 8; ++w) v += red[w][threadIdx.x];
+    atomicAdd(acc + (size_t)b * 16 + threadIdx.x, v);
+  }
+}
+
+__global__ void procrustes_solve_kernel(const double* __restrict__ acc, int N, int B, float* __restrict__ Rout, float* __restrict__ tout,
+                                        float* __restrict__ sout) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const double* m = acc + (size_t)b * 16;
+  const double n = (double)N;
+  const double mu1[3] = {m[0] / n, m[1] / n, m[2] / n}, mu2[3] = {m[3] / n, m[4] / n, m[5] / n};
+  const double var1 = m[6] - n * (mu1[0] * mu1[0] + mu1[1] * mu1[1] + mu1[2] * mu1[2]);
+  double K[9];                                             // K = sum (x - mu1)(y - mu2)^T
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 3; ++c) K[r * 3 + c] = m[7 + r * 3 + c] - n * mu1[r] * mu2[c];
+  float Kt[9];
+  double nrm = 0;
+  for (int i = 0; i < 9; ++i) nrm = fmax(nrm, fabs(K[i]));
+  const double inv = nrm > 0 ? 1.0 / nrm : 1.0;            // so3_project takes floats: normalise first (the maximiser is scale-free)
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 3; ++c) Kt[r * 3 + c] = (float)(K[c * 3 + r] * inv);
+  double R[9];
+  so3_project(Kt, R);
+  double tr = 0;                                           // trace(R K)
+  for (int i = 0; i < 3; ++i)
+    for (int k = 0; k < 3; ++k) tr += R[i * 3 + k] * K[k * 3 + i];
+  const double scale = tr / var1;
+  for (int i = 0; i < 9; ++i) Rout[(size_t)b * 9 + i] = (float)R[i];
+  for (int i = 0; i < 3; ++i)
+    tout[(size_t)b * 3 + i] = (float)(mu2[i] - scale * (R[i * 3] * mu1[0] + R[i * 3 + 1] * mu1[1] + R[i * 3 + 2] * mu1[2]));
+  sout[b] = (float)scale;
+}
+
+// out = scale * R p + t for every point of cloud b (ProcrusteAlign.align_meshes, pose_utils.py:31; evalvideo_packed.py:131)
+__global__ void similarity_apply_kernel(const float* __restrict__ pts, int n, const float* __restrict__ R, const float* __restrict__ t,
+                                        const float* __restrict__ scale, float* __restrict__ out) {
+  const int b = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float* r = R + (size_t)b * 9;
+  const float s = scale[b];
+  const float* p = pts + ((size_t)b * n + i) * 3;
+  float* o = out + ((size_t)b * n + i) * 3;
+  const float x = p[0], y = p[1], z = p[2];
+  o[0] = s * (r[0] * x + r[1] * y + r[2] * z) + t[b * 3];
+  o[1] = s * (r[3] * x + r[4] * y + r[5] * z) + t[b * 3 + 1];
+  o[2] = s * (r[6] * x + r[7] * y + r[8] * z) + t[b * 3 + 2];
+}
+
 }  // namespace vt
 
 using namespace vt;
@@ -229,6 +312,28 @@ int vt_nn_dist(const float* x, int nx, const float* y, int ny, int B, float* dis
   dim3 grid(ceil_div(n, 256), B, 2);
   nn_dist_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, nx, y, ny, dist_x, dist_y);
   VT_CHECK_LAUNCH("vt_nn_dist");
+  return 0;
+}
+
+int vt_procrustes(const float* S1, const float* S2, int N, int B, double* workspace, float* R, float* t, float* scale, void* stream) {
+  VT_CHECK_ARG(N >= 3 && B > 0, "vt_procrustes: %d points, batch %d", N, B);
+  VT_CHECK_ARG(workspace != nullptr, "vt_procrustes: a workspace of 16 doubles per pair is required");
+  cudaStream_t s = (cudaStream_t)stream;
+  cudaError_t e = cudaMemsetAsync(workspace, 0, (size_t)B * 16 * sizeof(double), s);
+  if (e != cudaSuccess) return cuda_fail(e, "vt_procrustes memset");
+  int blocks = ceil_div(N, 256 * 8);
+  if (blocks > 148 * 4) blocks = 148 * 4;
+  procrustes_moments_kernel<<<dim3(blocks, B), 256, 0, s>>>(S1, S2, N, workspace);
+  VT_CHECK_LAUNCH("vt_procrustes(moments)");
+  procrustes_solve_kernel<<<ceil_div(B, 32), 32, 0, s>>>(workspace, N, B, R, t, scale);
+  VT_CHECK_LAUNCH("vt_procrustes(solve)");
+  return 0;
+}
+
+int vt_similarity_apply(const float* points, int n, int B, const float* R, const float* t, const float* scale, float* out, void* stream) {
+  if (n <= 0 || B <= 0) return 0;
+  similarity_apply_kernel<<<dim3(ceil_div(n, 256), B), 256, 0, (cudaStream_t)stream>>>(points, n, R, t, scale, out);
+  VT_CHECK_LAUNCH("vt_similarity_apply");
   return 0;
 }
 

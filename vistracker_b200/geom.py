@@ -104,3 +104,35 @@ def eval_chamfer_distance(x: torch.Tensor, y: torch.Tensor, direction: str = "bi
     out = {"x_to_y": dx.mean(1), "y_to_x": dy.mean(1)}
     res = out["x_to_y"] + out["y_to_x"] if direction == "bi" else out[direction]
     return res[0] if single else res
+
+
+def procrustes_transform(S1: torch.Tensor, S2: torch.Tensor):
+    """``compute_transform`` (recon/eval/pose_utils.py:153-198) for clouds S1, S2 [N, 3] or batches [B, N, 3]: returns (R [.., 3, 3],
+    t [.., 3], scale [..]) with ``scale * R @ p + t`` mapping S1 onto S2 -- what ``ProcrusteAlign.get_transform`` computes from the
+    combined SMPL + object vertices of an alignment window (pose_utils.py:49-69, evalvideo_packed.py:108-126)."""
+    from . import _lib
+    single = S1.dim() == 2
+    a, b = (S1[None] if single else S1).float().contiguous(), (S2[None] if single else S2).float().contiguous()
+    if not a.is_cuda:
+        raise RuntimeError("vistracker_b200 has no CPU path: procrustes_transform needs CUDA tensors")
+    if a.shape != b.shape:
+        raise ValueError(f"point sets must correspond: {tuple(S1.shape)} vs {tuple(S2.shape)}")
+    B, N = a.shape[0], a.shape[1]
+    ws = torch.empty(B, 16, dtype=torch.float64, device=a.device)
+    R, t, s = torch.empty(B, 3, 3, device=a.device), torch.empty(B, 3, device=a.device), torch.empty(B, device=a.device)
+    with torch.cuda.device(a.device):
+        _lib.call("vt_procrustes", _lib.ptr(a), _lib.ptr(b), N, B, _lib.ptr(ws), _lib.ptr(R), _lib.ptr(t), _lib.ptr(s), _lib.stream_ptr())
+    return (R[0], t[0], s[0]) if single else (R, t, s)
+
+
+def apply_similarity(points: torch.Tensor, R: torch.Tensor, t: torch.Tensor, scale: torch.Tensor) -> torch.Tensor:
+    """``scale * R @ p + t`` for points [n, 3] (single transform) or [B, n, 3] (one transform per cloud)."""
+    from . import _lib
+    single = points.dim() == 2
+    p = (points[None] if single else points).float().contiguous()
+    B, n = p.shape[0], p.shape[1]
+    R, t, scale = R.reshape(B, 9).float().contiguous(), t.reshape(B, 3).float().contiguous(), scale.reshape(B).float().contiguous()
+    out = torch.empty_like(p)
+    with torch.cuda.device(p.device):
+        _lib.call("vt_similarity_apply", _lib.ptr(p), n, B, _lib.ptr(R), _lib.ptr(t), _lib.ptr(scale), _lib.ptr(out), _lib.stream_ptr())
+    return out[0] if single else out
