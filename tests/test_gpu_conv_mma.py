@@ -26,21 +26,24 @@ CASES = [  # ks, cin, cout, n, H, W
 ]
 
 
-@pytest.fixture(params=["persist", "persist_nostrip", "plain", "strip", "pair"])
+@pytest.fixture(params=["persist", "persist_nostrip", "persist_e8", "plain", "strip", "pair"])
 def variant(request, monkeypatch):
     """persist (the default path) = one CTA per SM walking tiles with double-buffered TMEM accumulators and the merged N = 2 BN MMA,
     A strips for 3x3 on maps >= 128 wide (VT_CONV_PERSIST=4: for every BN; the default uses them for BN = 128 only) and a resident
-    weight panel for 1x1; persist_nostrip (VT_CONV_PERSIST=3) = the same without strips;
+    resident weight panel for 1x1; persist_nostrip (VT_CONV_PERSIST=3) = the same without strips; persist_e8 (=6) = 1x1 with a second
+    epilogue warp group instead of the resident panel;
     plain (VT_CONV_PERSIST=0) = one tile per CTA; VT_CONV_STRIP=1 = one A strip serves the three dx taps, =2 = strip + two images per
     CTA sharing the weight tiles.  The strip kernels serve 3x3 convolutions on maps at least 128 wide ('pair' needs an even image count)."""
-    monkeypatch.setenv("VT_CONV_STRIP", {"persist": "0", "persist_nostrip": "0", "plain": "0", "strip": "1", "pair": "2"}[request.param])
-    monkeypatch.setenv("VT_CONV_PERSIST", {"persist": "4", "persist_nostrip": "3"}.get(request.param, "0"))
+    monkeypatch.setenv("VT_CONV_STRIP", {"persist": "0", "persist_nostrip": "0", "persist_e8": "0", "plain": "0", "strip": "1", "pair": "2"}[request.param])
+    monkeypatch.setenv("VT_CONV_PERSIST", {"persist": "4", "persist_nostrip": "3", "persist_e8": "6"}.get(request.param, "0"))
     return request.param
 
 
 @pytest.mark.parametrize("ks,cin,cout,n,H,W", CASES)
 def test_conv_mma_matches_fp64(ks, cin, cout, n, H, W, variant):
     from vistracker_b200 import ops
+    if variant == "persist_e8" and ks != 1:
+        pytest.skip("the second epilogue warp group only serves 1x1 convolutions")
     if variant in ("strip", "pair") and not (ks == 3 and W >= 128):
         pytest.skip("the strip kernels only serve 3x3 convolutions on maps at least 128 wide")
     if variant == "pair":

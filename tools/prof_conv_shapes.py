@@ -27,6 +27,7 @@ B = int(arg("--batch", 8))
 modes = arg("--modes", "persist,plain").split(",")
 iters = int(arg("--iters", 7))
 MODE_ENV = {"persist": {"VT_CONV_PERSIST": "1", "VT_CONV_STRIP": "0", "VT_CONV_PREFETCH": "0"},
+            "e8": {"VT_CONV_PERSIST": "6", "VT_CONV_STRIP": "0", "VT_CONV_PREFETCH": "0"},
             "nostrip": {"VT_CONV_PERSIST": "3", "VT_CONV_STRIP": "0", "VT_CONV_PREFETCH": "0"},
             "pf2": {"VT_CONV_PERSIST": "1", "VT_CONV_STRIP": "0", "VT_CONV_PREFETCH": "2"},
             "pf4": {"VT_CONV_PERSIST": "1", "VT_CONV_STRIP": "0", "VT_CONV_PREFETCH": "4"},

@@ -32,6 +32,7 @@ constexpr int MM_THREADS = 192;
 struct ConvMmaParams {
   int H, W, pad, ks, kchunks;   // kchunks = Cin_pad / 64
   int prefetch;                 // persistent kernel: tiles of A-operand L2 prefetch distance (0 = off)
+  int dbg_nostore;              // debug (VT_CONV_DEBUG_NOSTORE=1): skip the global stores of the persistent epilogue (timing experiments only)
   long long* trace;             // debug (VT_CONV_TRACE=1): clock64 stamps of CTA 0: per tile [wait start, accumulator ready, tile drained]
   int bw, bh, tiles_x, bw_shift;   // bw is a power of two: pixel r of a tile sits at (y0 + (r >> bw_shift), x0 + (r & (bw-1)))
   int cout_total;               // rows per tap in the packed weight planes
@@ -350,13 +351,19 @@ conv_mma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
 // 128-pixel A tile for each of the 9 taps.  Here one 130-pixel strip per (K-chunk, dy) serves the three dx taps through UMMA
 // descriptor row offsets (as in conv_mma_strip_kernel below), with separate A-strip and weight rings: 1.5x (BN = 128) to 1.8x
 // (BN = 64) fewer bytes per MMA.
-template <int BN, bool RESB = false, bool STRIP = false>
+// E8 (1x1 convolutions, opt-in experiment): a SECOND group of four epilogue warps (warps 6-9, TMEM lane quadrant = warp % 4) that drains
+// the upper half of the tile's channel chunks, paid for with a 2-stage ring.  The trace says the 1x1 tiles wait on the epilogue, not on
+// the MMAs -- but neither removing the global stores (VT_CONV_DEBUG_NOSTORE) nor doubling the epilogue warps changes the time: the
+// shared-memory port is shared by the MMA operand reads, the TMA fills and the epilogue staging, and that sum is what paces the tile.
+template <int BN, bool RESB = false, bool STRIP = false, bool E8 = false>
 struct PersistCfg {
   static constexpr int A_BYTES = MM_M * MM_KC * 2;
   static constexpr int B_BYTES = BN * MM_KC * 2;
   static constexpr int PANEL_CHUNKS = 4;
   static constexpr int PANEL_BYTES = RESB ? PANEL_CHUNKS * 2 * B_BYTES : 0;
-  static constexpr int STAGES = RESB ? (BN == 128 ? 2 : (BN == 64 ? 4 : 5)) : (BN == 128 ? 3 : (BN == 64 ? 4 : 5));
+  static constexpr int STAGES = E8 ? (BN == 128 ? 2 : 3) : RESB ? (BN == 128 ? 2 : (BN == 64 ? 4 : 5)) : (BN == 128 ? 3 : (BN == 64 ? 4 : 5));
+  static constexpr int EPI_WARPS = E8 ? 8 : 4;
+  static constexpr int THREADS = E8 ? 320 : MM_THREADS;
   static constexpr int STAGE_BYTES = RESB ? 2 * A_BYTES : 2 * A_BYTES + 2 * B_BYTES;
   // strip mode: separate rings
   static constexpr int STRIP_BYTES = (MM_M + 2) * 128;               // one plane of a 130-pixel strip, what TMA writes
@@ -367,12 +374,12 @@ struct PersistCfg {
   static constexpr int NB = STRIP ? (BN == 128 ? 4 : (BN == 64 ? 6 : 9)) : 1;
   static constexpr int RING_BYTES = STRIP ? NA * STRIP_SLOT + NB * B_SLOT : STAGES * STAGE_BYTES + PANEL_BYTES;
   static constexpr int EPI_LD = 36;                                  // floats per staged row: 32 + 4 keeps float4 rows conflict-free
-  static constexpr int EPI_BYTES = 4 * 32 * EPI_LD * 4;
+  static constexpr int EPI_BYTES = EPI_WARPS * 32 * EPI_LD * 4;
   static constexpr int SMEM_BYTES = RING_BYTES + EPI_BYTES + 1024;
   static constexpr int TMEM_COLS = 4 * BN;
   static constexpr uint32_t IDESC_WIDE = (1u << 4) | ((uint32_t)(2 * BN >> 3) << 17) | ((uint32_t)(MM_M >> 4) << 24);
   static constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(MM_M >> 4) << 24);
-  static_assert(!(RESB && STRIP), "resident panel is for 1x1, strips for 3x3");
+  static_assert(!(RESB && STRIP) && !(E8 && (RESB || STRIP)) && !(E8 && BN < 64), "resident panel / second epilogue group are for 1x1, strips for 3x3");
   static_assert(SMEM_BYTES + 16 * BN * 4 + 1024 <= 227 * 1024 && TMEM_COLS <= 512, "persistent configuration (dynamic + static shared memory) exceeds the SM");
 };
 
@@ -407,12 +414,12 @@ __device__ __forceinline__ void tc_ld32_issue(uint32_t taddr, uint32_t (&r)[32])
       : "r"(taddr) : "memory");
 }
 
-template <int BN, bool RESB, bool STRIP>
-__global__ void __launch_bounds__(MM_THREADS, 1)
+template <int BN, bool RESB, bool STRIP, bool E8>
+__global__ void __launch_bounds__(E8 ? 320 : MM_THREADS, 1)
 conv_mma_persist_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                         const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo, const ConvMmaParams p,
                         int tiles_per_img, int n_tiles_n, int total_tiles) {
-  using Cfg = PersistCfg<BN, RESB, STRIP>;
+  using Cfg = PersistCfg<BN, RESB, STRIP, E8>;
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bar_full[Cfg::STAGES], bar_empty[Cfg::STAGES], acc_full[2], acc_empty[2], panel_full, panel_empty;
   __shared__ __align__(8) uint64_t a_full[Cfg::NA], a_empty[Cfg::NA], b_full[Cfg::NB], b_empty[Cfg::NB];      // strip mode rings
@@ -425,10 +432,10 @@ conv_mma_persist_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __gri
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_iter = p.ks * p.ks * p.kchunks;
 
-  for (int i = threadIdx.x; i < 4 * BN; i += MM_THREADS) { (&s_sum[0][0])[i] = 0.f; (&s_sq[0][0])[i] = 0.f; (&s_sum2[0][0])[i] = 0.f; (&s_sq2[0][0])[i] = 0.f; }
+  for (int i = threadIdx.x; i < 4 * BN; i += Cfg::THREADS) { (&s_sum[0][0])[i] = 0.f; (&s_sq[0][0])[i] = 0.f; (&s_sum2[0][0])[i] = 0.f; (&s_sq2[0][0])[i] = 0.f; }
   if (warp == 5 && lane == 0) {
     for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(smem_u32(&bar_full[s]), 1); mbar_init(smem_u32(&bar_empty[s]), 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(smem_u32(&acc_full[s]), 1); mbar_init(smem_u32(&acc_empty[s]), 4); }
+    for (int s = 0; s < 2; ++s) { mbar_init(smem_u32(&acc_full[s]), 1); mbar_init(smem_u32(&acc_empty[s]), Cfg::EPI_WARPS); }
     mbar_init(smem_u32(&panel_full), 1); mbar_init(smem_u32(&panel_empty), 1);
     for (int s = 0; s < Cfg::NA; ++s) { mbar_init(smem_u32(&a_full[s]), 1); mbar_init(smem_u32(&a_empty[s]), 1); }
     for (int s = 0; s < Cfg::NB; ++s) { mbar_init(smem_u32(&b_full[s]), 1); mbar_init(smem_u32(&b_empty[s]), 1); }
@@ -608,19 +615,22 @@ conv_mma_persist_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __gri
       }
     }
   } else {
-    // ------------------------------------------------------------------ epilogue warps 0-3 (TMEM lanes 32*warp .. +31)
-    float* wstage = reinterpret_cast<float*>(smem_raw + (smem_base - smem_u32(smem_raw)) + Cfg::RING_BYTES) + warp * 32 * Cfg::EPI_LD;
+    // ------------------------------------------------------------------ epilogue warps 0-3 (+ 6-9 with E8): TMEM lanes 32*(warp % 4) .. +31
+    const int team = warp >= 6 ? 1 : 0, q = warp & 3, ew = team * 4 + q;      // q: TMEM lane quadrant this warp may read
+    float* wstage = reinterpret_cast<float*>(smem_raw + (smem_base - smem_u32(smem_raw)) + Cfg::RING_BYTES) + ew * 32 * Cfg::EPI_LD;
     const int cl = lane & 7, rsub = lane >> 3;
     const bool st1 = p.stats != nullptr, st2 = p.out2 != nullptr && p.stats2 != nullptr;
     constexpr int NCH = BN / 32;
+    constexpr int CH_PER_TEAM = E8 ? NCH / 2 : NCH;                           // E8: team 0 drains the lower channel chunks, team 1 the upper
+    const int ch_first = team * CH_PER_TEAM;
     // pixel offsets of this lane's 8 rows inside a tile (tile-invariant)
     int roff[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { const int r = warp * 32 + rsub + 4 * j; roff[j] = (r >> p.bw_shift) * p.W + (r & (p.bw - 1)); }
+    for (int j = 0; j < 8; ++j) { const int r = q * 32 + rsub + 4 * j; roff[j] = (r >> p.bw_shift) * p.W + (r & (p.bw - 1)); }
     uint32_t i = 0;
     int stats_img = -1, stats_n0 = 0;
     auto flush_stats = [&]() {       // block partials (fp32, <= a few thousand values per channel) -> fp64 slots of image stats_img
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (E8) asm volatile("bar.sync 1, 256;" ::: "memory"); else asm volatile("bar.sync 1, 128;" ::: "memory");
       if (threadIdx.x < BN) {
         if (st1) {
           double* st = p.stats + ((size_t)stats_img * p.ld_stats + stats_n0 + threadIdx.x) * 2;
@@ -639,7 +649,7 @@ conv_mma_persist_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __gri
           for (int w = 0; w < 4; ++w) { s_sum2[w][c] = 0.f; s_sq2[w][c] = 0.f; }
         }
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (E8) asm volatile("bar.sync 1, 256;" ::: "memory"); else asm volatile("bar.sync 1, 128;" ::: "memory");
     };
     for (int t = t_first; t < t_last; ++t, ++i) {
       const TileCoord c = decode_tile(p, t, n_tiles_n, tiles_per_img, BN);
@@ -648,7 +658,7 @@ conv_mma_persist_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __gri
         stats_img = c.img; stats_n0 = c.n0;
       }
       const size_t pix0 = ((size_t)c.img * p.H + c.y0) * p.W + c.x0;
-      const int cbase = c.n0 + cl * 4;
+      const int cbase = c.n0 + ch_first * 32 + cl * 4;
       // residual operands are fetched one 32-channel chunk ahead (the first one before the accumulator is even ready): the loads
       // must not sit between dependent stores, or every row pays a full HBM round trip (out may alias res, so the compiler keeps
       // the program order)
@@ -668,7 +678,8 @@ conv_mma_persist_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __gri
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
 #pragma unroll
-          for (int ch = 0; ch < NCH; ++ch) {
+          for (int lc = 0; lc < CH_PER_TEAM; ++lc) {
+            const int ch = ch_first + lc;
             if (p.res) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.res + (pixn + roff[j]) * p.ldr + cn.n0 + ch * 32));
             if (p.out2) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.res2 + (pixn + roff[j]) * p.ldr2 + cn.n0 + ch * 32));
           }
@@ -680,9 +691,10 @@ conv_mma_persist_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __gri
       mbar_wait_relaxed(smem_u32(&acc_full[set]), (i >> 1) & 1u);
       tc_fence_after();
       if (tracing) p.trace[3 * i + 1] = clock64();
-      const uint32_t lane_base = tmem_base + set * 2 * BN + ((uint32_t)(warp * 32) << 16);
+      const uint32_t lane_base = tmem_base + set * 2 * BN + ((uint32_t)(q * 32) << 16);
 #pragma unroll
-      for (int ch = 0; ch < NCH; ++ch) {
+      for (int lc = 0; lc < CH_PER_TEAM; ++lc) {
+        const int ch = ch_first + lc;
         const bool micro = tracing && i == 2 && ch == 0;
         if (micro) p.trace[32] = clock64();
         {
@@ -691,7 +703,7 @@ conv_mma_persist_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __gri
           tc_ld32_issue(lane_base + BN + ch * 32, w);
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
           if (micro) p.trace[33] = clock64();
-          if (ch == NCH - 1) {                                           // this warp's last TMEM read of the tile: hand the set back
+          if (lc == CH_PER_TEAM - 1) {                                   // this warp's last TMEM read of the tile: hand the set back
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(smem_u32(&acc_empty[set]));
@@ -718,14 +730,14 @@ conv_mma_persist_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __gri
         __syncwarp();                                                    // wstage is rewritten by the next chunk
         if (micro) p.trace[35] = clock64();
         float4 nv[8], nw[8];
-        if (ch + 1 < NCH) {                                              // next chunk's residuals: in flight during this chunk's stores
+        if (lc + 1 < CH_PER_TEAM) {                                      // next chunk's residuals: in flight during this chunk's stores
           if (p.res) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) nv[j] = ld4(p.res + (pix0 + roff[j]) * p.ldr + cbase + (ch + 1) * 32);
+            for (int j = 0; j < 8; ++j) nv[j] = ld4(p.res + (pix0 + roff[j]) * p.ldr + cbase + (lc + 1) * 32);
           }
           if (p.out2) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) nw[j] = ld4(p.res2 + (pix0 + roff[j]) * p.ldr2 + cbase + (ch + 1) * 32);
+            for (int j = 0; j < 8; ++j) nw[j] = ld4(p.res2 + (pix0 + roff[j]) * p.ldr2 + cbase + (lc + 1) * 32);
           }
         }
         if (micro) p.trace[36] = clock64();
@@ -733,7 +745,7 @@ conv_mma_persist_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __gri
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           float4 v = val[j];
-          st4(p.out + (pix0 + roff[j]) * p.ldo + c.n0 + cc, v);
+          if (!p.dbg_nostore) st4(p.out + (pix0 + roff[j]) * p.ldo + c.n0 + cc, v);
           s4.x += v.x; s4.y += v.y; s4.z += v.z; s4.w += v.w;
           q4.x += v.x * v.x; q4.y += v.y * v.y; q4.z += v.z * v.z; q4.w += v.w * v.w;
           if (p.out2) {
@@ -743,7 +755,7 @@ conv_mma_persist_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __gri
             u4.x += v.x * v.x; u4.y += v.y * v.y; u4.z += v.z * v.z; u4.w += v.w * v.w;
           }
         }
-        if (ch + 1 < NCH) {
+        if (lc + 1 < CH_PER_TEAM) {
 #pragma unroll
           for (int j = 0; j < 8; ++j) { rv[j] = nv[j]; rw[j] = nw[j]; }
         }
@@ -757,10 +769,10 @@ conv_mma_persist_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __gri
             q4.z += __shfl_xor_sync(0xffffffffu, q4.z, o); q4.w += __shfl_xor_sync(0xffffffffu, q4.w, o);
           }
           if (rsub == 0) {
-            float4 a = *reinterpret_cast<float4*>(&s_sum[warp][cc]), bq = *reinterpret_cast<float4*>(&s_sq[warp][cc]);
+            float4 a = *reinterpret_cast<float4*>(&s_sum[q][cc]), bq = *reinterpret_cast<float4*>(&s_sq[q][cc]);
             a.x += s4.x; a.y += s4.y; a.z += s4.z; a.w += s4.w;
             bq.x += q4.x; bq.y += q4.y; bq.z += q4.z; bq.w += q4.w;
-            *reinterpret_cast<float4*>(&s_sum[warp][cc]) = a; *reinterpret_cast<float4*>(&s_sq[warp][cc]) = bq;
+            *reinterpret_cast<float4*>(&s_sum[q][cc]) = a; *reinterpret_cast<float4*>(&s_sq[q][cc]) = bq;
           }
         }
         if (st2) {
@@ -772,10 +784,10 @@ conv_mma_persist_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __gri
             u4.z += __shfl_xor_sync(0xffffffffu, u4.z, o); u4.w += __shfl_xor_sync(0xffffffffu, u4.w, o);
           }
           if (rsub == 0) {
-            float4 a = *reinterpret_cast<float4*>(&s_sum2[warp][cc]), bq = *reinterpret_cast<float4*>(&s_sq2[warp][cc]);
+            float4 a = *reinterpret_cast<float4*>(&s_sum2[q][cc]), bq = *reinterpret_cast<float4*>(&s_sq2[q][cc]);
             a.x += t4.x; a.y += t4.y; a.z += t4.z; a.w += t4.w;
             bq.x += u4.x; bq.y += u4.y; bq.z += u4.z; bq.w += u4.w;
-            *reinterpret_cast<float4*>(&s_sum2[warp][cc]) = a; *reinterpret_cast<float4*>(&s_sq2[warp][cc]) = bq;
+            *reinterpret_cast<float4*>(&s_sum2[q][cc]) = a; *reinterpret_cast<float4*>(&s_sq2[q][cc]) = bq;
           }
         }
         if (micro) p.trace[38] = clock64();
@@ -979,13 +991,13 @@ static int num_sms() {
   return n;
 }
 
-template <int BN, bool RESB, bool STRIP = false>
+template <int BN, bool RESB, bool STRIP = false, bool E8 = false>
 static int launch_conv_persist(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi, const CUtensorMap& b_lo,
                                const ConvMmaParams& p, dim3 grid, cudaStream_t stream) {
-  using Cfg = PersistCfg<BN, RESB, STRIP>;
+  using Cfg = PersistCfg<BN, RESB, STRIP, E8>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_mma_persist_kernel<BN, RESB, STRIP>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(conv_mma_persist_kernel<BN, RESB, STRIP, E8>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return cuda_fail(e, "conv_mma_persist smem attr");
     attr_set = true;
   }
@@ -999,14 +1011,14 @@ static int launch_conv_persist(const CUtensorMap& a_hi, const CUtensorMap& a_lo,
   ConvMmaParams p2 = p;
   const bool trace = getenv("VT_CONV_TRACE") != nullptr;         // debug only: synchronises and prints the epilogue stamps of CTA 0
   if (trace) { cudaMalloc(&p2.trace, 48 * sizeof(long long)); cudaMemset(p2.trace, 0, 48 * sizeof(long long)); }
-  conv_mma_persist_kernel<BN, RESB, STRIP><<<ctas, MM_THREADS, Cfg::SMEM_BYTES, stream>>>(a_hi, a_lo, b_hi, b_lo, p2, tiles_per_img, n_tiles_n, total);
+  conv_mma_persist_kernel<BN, RESB, STRIP, E8><<<ctas, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(a_hi, a_lo, b_hi, b_lo, p2, tiles_per_img, n_tiles_n, total);
   VT_CHECK_LAUNCH("vt_conv_mma(persistent)");
   if (trace) {
     long long h[48];
     cudaDeviceSynchronize();
     cudaMemcpy(h, p2.trace, sizeof(h), cudaMemcpyDeviceToHost);
     cudaFree(p2.trace);
-    fprintf(stderr, "[conv_mma_persist<%d,%d,%d> trace: per tile wait / drain cycles]", BN, (int)RESB, (int)STRIP);
+    fprintf(stderr, "[conv_mma_persist<%d,%d,%d,%d> trace: per tile wait / drain cycles]", BN, (int)RESB, (int)STRIP, (int)E8);
     for (int i = 0; i < 10 && h[3 * i + 2]; ++i) fprintf(stderr, " %lld/%lld", h[3 * i + 1] - h[3 * i], h[3 * i + 2] - h[3 * i + 1]);
     fprintf(stderr, " | chunk 0 of tile 2: tmem-ld %lld, combine+sts %lld, lds+bias+res %lld, prefetch-issue %lld, stg+stats-acc %lld, stats-reduce %lld",
             h[33] - h[32], h[34] - h[33], h[35] - h[34], h[36] - h[35], h[37] - h[36], h[38] - h[37]);
@@ -1091,6 +1103,7 @@ int vt_conv_mma_dual(const void* a_hi, const void* a_lo, int n_img, int H, int W
   p.bw = bw; p.bh = bh; p.tiles_x = W / bw; p.cout_total = Cout;
   p.bw_shift = 0; while ((1 << p.bw_shift) < bw) ++p.bw_shift;
   p.trace = nullptr;
+  p.dbg_nostore = getenv("VT_CONV_DEBUG_NOSTORE") != nullptr;
   {
     const char* pf = getenv("VT_CONV_PREFETCH");       // tiles of L2 prefetch distance for the HBM-streaming shapes; default off: measured 5-25 % SLOWER on B200 (profiles/r01k_*)
     p.prefetch = (ks == 1 || p.kchunks == 1) ? (pf ? atoi(pf) : 0) : 0;
@@ -1114,7 +1127,14 @@ int vt_conv_mma_dual(const void* a_hi, const void* a_lo, int n_img, int H, int W
     return launch_conv_persist<32, false, true>(ma_hi, ma_lo, mb_hi, mb_lo, p, grid, s);
   }
   if (persist_mode != 0) {
-    // 1x1 convolutions with Cin <= 256 keep the weight panel of a Cout tile resident in shared memory (VT_CONV_PERSIST=2 disables)
+    // 1x1 convolutions with Cout >= 64, two epilogue warp groups: opt-in (VT_CONV_PERSIST=6) -- measured no faster without a residual and
+    // 25-40 % slower with one (profiles/r01n_*): the 1x1 tiles are not bound by epilogue issue slots but, like the 3x3 ones, by the
+    // shared-memory port (per 128x128x256 tile: 320 KB of MMA operand reads + 128-256 KB of TMA fills + 128 KB of epilogue staging)
+    if (ks == 1 && BN >= 64 && persist_mode == 6) {
+      if (BN == 128) return launch_conv_persist<128, false, false, true>(ma_hi, ma_lo, mb_hi, mb_lo, p, grid, s);
+      return launch_conv_persist<64, false, false, true>(ma_hi, ma_lo, mb_hi, mb_lo, p, grid, s);
+    }
+    // 1x1 convolutions with Cin <= 256 can keep the weight panel of a Cout tile resident in shared memory
     if (ks == 1 && p.kchunks <= 4 && persist_mode != 2) {
       if (BN == 128) return launch_conv_persist<128, true>(ma_hi, ma_lo, mb_hi, mb_lo, p, grid, s);
       if (BN == 64) return launch_conv_persist<64, true>(ma_hi, ma_lo, mb_hi, mb_lo, p, grid, s);
