@@ -1,0 +1,51 @@
+"""The on-disk formats of vistracker_b200/io.py: keys, shapes and dtypes as the reference's writers produce them
+(preprocess/fit_SMPLH_kpts.py:250-261, recon/opt_utils.py:134-141, recon/recon_fit_base.py:278-313,830-844)."""
+import os
+import pickle as pkl
+
+import numpy as np
+import torch
+
+from vistracker_b200 import io as vio
+
+
+def test_output_folders_and_param_files(tmp_path):
+    paths = [f"/data/Date03_Sub03_chairwood_hand/t{i:04d}.000/k1.color.jpg" for i in range(3)]
+    folders = vio.output_folders(str(tmp_path), paths, "test-release")
+    assert folders[1] == os.path.join(str(tmp_path), "Date03_Sub03_chairwood_hand", "t0001.000", "test-release") and os.path.isdir(folders[2])
+    pose, betas, trans = torch.randn(3, 156), torch.randn(3, 10), torch.randn(3, 3)
+    files = vio.save_smpl_params(folders, 1, pose, betas, trans)
+    d = pkl.load(open(files[2], "rb"))
+    assert sorted(d) == ["betas", "pose", "score", "trans"] and d["pose"].shape == (156,) and d["pose"].dtype == np.float32
+    assert np.array_equal(d["trans"], trans[2].numpy()) and float(d["score"]) == 0.0
+    R = torch.linalg.qr(torch.randn(3, 3, 3))[0]
+    R = R * torch.sign(torch.linalg.det(R))[:, None, None]
+    ofiles = vio.save_object_params(folders, 1, R, torch.randn(3, 3), torch.ones(3))
+    o = pkl.load(open(ofiles[0], "rb"))
+    assert sorted(o) == ["rot", "scale", "trans"] and o["rot"].shape == (3, 3) and o["scale"].shape == ()
+
+
+def test_smplt_fit_files_round_trip_and_skip(tmp_path):
+    poses, betas, trans = np.random.rand(4, 156).astype(np.float32), np.random.rand(4, 10).astype(np.float32), np.random.rand(4, 3).astype(np.float32)
+    files = [str(tmp_path / f"f{i}.k1.smplfit_temporal.pkl") for i in range(4)]
+    n = vio.save_smplt_fits(files, torch.from_numpy(poses), betas, trans, skip=[False, True, False, False])
+    assert n == 3 and not os.path.exists(files[1])
+    d = pkl.load(open(files[0], "rb"))
+    assert sorted(d) == ["betas", "pose", "trans"]
+    P, B, T = vio.load_smplt_fits([files[0], files[2], files[3]])
+    assert np.array_equal(P, poses[[0, 2, 3]]) and np.array_equal(T, trans[[0, 2, 3]]) and B.shape == (3, 10)
+
+
+def test_neural_recon_npz(tmp_path):
+    folders = [str(tmp_path / f"fr{i}") for i in range(2)]
+    for f in folders:
+        os.makedirs(f)
+    batch = {t: {"points": torch.randn(2, 50, 3), "pca_axis": torch.randn(2, 3, 3), "parts": torch.randint(0, 14, (2, 50)),
+                 "centers": torch.randn(2, 6), "visibility": torch.rand(2, 1)} for t in ("human", "object")}
+    files = vio.save_neural_recon(folders, 1, batch)
+    assert os.path.basename(files[0]) == "k1_densepc.npz"
+    z = np.load(files[1], allow_pickle=True)
+    assert sorted(z.files) == ["human", "object"]
+    h = z["human"].item()
+    assert sorted(h) == ["centers", "parts", "pca_axis", "points", "visibility"] and h["points"].shape == (50, 3)
+    assert np.array_equal(h["parts"], batch["human"]["parts"][1].numpy())

@@ -1,0 +1,100 @@
+"""On-disk outputs of the hot-path stages, in the reference's formats (SURVEY.md section 8(b) "on-disk outputs that later steps read"), so
+that the reference's downstream scripts (pack_smplt.py, pack_recon.py, SmoothNet / HVOP-Net loaders, evaluation) read what this package
+writes.  Pure host code: one batched device->host copy per call, then the same per-frame files the reference writes.
+
+  save_smplt_fits     ``k{kid}.smplfit_temporal.pkl`` / ``.smplfit_smoothed.pkl`` = {'pose' (156,), 'betas' (10,), 'trans' (3,)}
+                      (preprocess/fit_SMPLH_kpts.py:250-261)
+  save_smpl_params    ``k{tid}.smpl.pkl`` = {'pose', 'betas', 'trans', 'score'}            (recon/opt_utils.py:134-141)
+  save_object_params  ``k{tid}.object.pkl`` = {'rot' (3,3) re-projected to SO(3) without noise, 'trans' (3,), 'scale' ()}
+                      (recon/recon_fit_base.py:296-313)
+  save_neural_recon   ``k{tid}_densepc.npz`` = {'human': {points, pca_axis, parts, centers, visibility}, 'object': {...}}
+                      (recon/recon_fit_base.py:830-844, recon/gen/generator_vis.py:54-55)
+  output_folders      ``<outpath>/<seq>/<frame>/<save_name>``                              (recon/recon_fit_base.py:278-294)
+"""
+from __future__ import annotations
+
+import os
+import pickle as pkl
+from typing import Dict, List, Sequence
+
+import numpy as np
+import torch
+
+
+def _np(t):
+    return t.detach().cpu().numpy() if torch.is_tensor(t) else np.asarray(t)
+
+
+def output_folders(outpath: str, image_paths: Sequence[str], save_name: str) -> List[str]:
+    """ROOT/SEQ/frame_time/kx.color.jpg -> <outpath>/SEQ/frame_time/<save_name> (created)."""
+    folders = []
+    for x in image_paths:
+        parts = str(x).split(os.sep)
+        folder = os.path.join(outpath, parts[-3], parts[-2], save_name)
+        os.makedirs(folder, exist_ok=True)
+        folders.append(folder)
+    return folders
+
+
+def save_smplt_fits(outfiles: Sequence[str], poses, betas, trans, skip=None) -> int:
+    """One ``{'pose', 'betas', 'trans'}`` pickle per frame (the SMPL-T pre-fit / smoothed-fit result); frames flagged in `skip` are not
+    written, as ``BaseFitter.save_results`` skips frames without confident keypoints.  Returns the number of files written."""
+    poses, betas, trans = _np(poses), _np(betas), _np(trans)
+    n = 0
+    for i, f in enumerate(outfiles):
+        if skip is not None and bool(skip[i]):
+            continue
+        with open(f, "wb") as fh:
+            pkl.dump({"pose": poses[i], "betas": betas[i], "trans": trans[i]}, fh)
+        n += 1
+    return n
+
+
+def save_smpl_params(folders: Sequence[str], tid: int, pose, betas, trans, scores=None) -> List[str]:
+    poses, betas, trans = _np(pose), _np(betas), _np(trans)
+    scores = np.zeros(len(folders)) if scores is None else _np(scores)
+    files = []
+    for i, folder in enumerate(folders):
+        f = os.path.join(folder, f"k{tid}.smpl.pkl")
+        with open(f, "wb") as fh:
+            pkl.dump({"pose": poses[i], "betas": betas[i], "trans": trans[i], "score": scores[i]}, fh)
+        files.append(f)
+    return files
+
+
+def save_object_params(folders: Sequence[str], tid: int, obj_R, obj_t, obj_s) -> List[str]:
+    """`obj_R` is the free 3x3 optimisation variable: it is projected to SO(3) WITHOUT the decopose_axis noise before saving
+    (recon/recon_fit_base.py:303, `no_rand=True`).  A host array / CPU tensor is taken to be projected already."""
+    from .geom import project_so3
+    R = _np(project_so3(obj_R.detach())) if torch.is_tensor(obj_R) and obj_R.is_cuda else _np(obj_R)
+    t, s = _np(obj_t), _np(obj_s)
+    files = []
+    for i, folder in enumerate(folders):
+        f = os.path.join(folder, f"k{tid}.object.pkl")
+        with open(f, "wb") as fh:
+            pkl.dump({"rot": R[i], "trans": t[i], "scale": s[i]}, fh)
+        files.append(f)
+    return files
+
+
+def save_neural_recon(folders: Sequence[str], tid: int, recon_batch: Dict[str, Dict[str, torch.Tensor]]) -> List[str]:
+    """recon_batch = {'human': {'points' [B, n, 3], 'pca_axis', 'parts', 'centers', 'visibility'}, 'object': {...}} as
+    ``GeneratorTriplaneVis.generate_pclouds_batch`` returns it; one npz per frame holding the two per-target dicts."""
+    host = {tar: {k: _np(v) for k, v in d.items()} for tar, d in recon_batch.items()}
+    files = []
+    for i, folder in enumerate(folders):
+        f = os.path.join(folder, f"k{tid}_densepc.npz")
+        np.savez(f, **{tar: {k: v[i] for k, v in d.items()} for tar, d in host.items()})
+        files.append(f)
+    return files
+
+
+def load_smplt_fits(files: Sequence[str]):
+    """Inverse of save_smplt_fits: stacked (poses [T, 156], betas [T, 10], trans [T, 3]) -- what SMPLTSmoother.load_inputs_raw collects
+    frame by frame (smoothnet/smooth_smplt.py:130-152)."""
+    P, B, T = [], [], []
+    for f in files:
+        with open(f, "rb") as fh:
+            d = pkl.load(fh)
+        P.append(d["pose"]); B.append(d["betas"]); T.append(d["trans"])
+    return np.stack(P, 0), np.stack(B, 0), np.stack(T, 0)
