@@ -309,6 +309,43 @@ int vt_smooth_unpack_smplt(const float* seq, int L, float* poses, float* betas, 
  * `obj_angles` (smooth_objrot.py:104-112). */
 int vt_smooth_rot6d_to_rotmat(const float* rot6d, int L, int transposed, float* out, void* stream);
 
+/* ---- HVOP-Net: model/infill/mfiller_cond.py:17-104 (ConditionalMInfiller), model/transformers/former_deci.py:31-175
+ * (pre-norm encoder layers, nn.MultiheadAttention with key_padding_mask), posi_embed.py:35-66, and the autoregressive clip loop of
+ * interp/test_infill_autoreg.py:34-174 / test_cinfill_autoreg.py:32-51.  All tensors fp32 on the device; tokens are rows [clip][t].
+ * A layer pack holds, k-major ([in][out]):  ln1.w ln1.b | Wqkv^T [D][3D] bqkv [3D] | Wo^T [D][D] bo [D] | ln2.w ln2.b | W1^T [D][F] b1 [F] |
+ * W2^T [F][D] b2 [D]. ---- */
+long long vt_infill_layer_pack_floats(int D, int F);
+
+/* Start of an encoder's first layer: optional feature projection x = in P + b (in[n_tok][in_ld], proj = P^T [in_dim][D] | b [D]; in == NULL:
+ * x already holds the stream), then forward_pre up to the attention (former_deci.py:83-84): h = LayerNorm1(x), q = (h + pos) Wq / sqrt(D /
+ * heads), k = (h + pos) Wk, v = h Wv -> qkv[n_tok][3D].  pos[T][D] is PositionEmbeddingSine_1D(B, T) (identical for every clip). */
+int vt_infill_head(const float* in, int in_ld, int in_dim, const float* proj, float* x, int x_ld, int n_tok, int T, int D, int F, int heads,
+                   const float* layer, const float* pos, float* qkv, void* stream);
+
+/* softmax(q k^T + key_padding_mask) v per head (former_deci.py:84-88); key_mask[n_clips][T] bytes, non-zero = key ignored, NULL = none.
+ * attn[n_tok][D] is the concatenation of the heads BEFORE the output projection. */
+int vt_infill_attn(const float* qkv, const unsigned char* key_mask, int n_clips, int T, int D, int heads, float* attn, void* stream);
+
+/* Rest of the layer (former_deci.py:89-93): x += attn Wo + bo; x += W2 act(W1 LayerNorm2(x)); activation 0 gelu / 1 relu / 2 leaky_relu.
+ * final_ln != NULL applies the encoder's closing LayerNorm (former_deci.py:126-127, only built when the pre_norm option is set).  The stream
+ * is written to y[n_tok][y_ld] (y may be x; a wider y_ld concatenates two encoders' features, mfiller_cond.py:95).  next_layer != NULL also
+ * starts the following layer exactly as vt_infill_head does. */
+int vt_infill_tail(float* x, int x_ld, const float* attn, int n_tok, int T, int D, int F, int heads, int activation, const float* layer,
+                   const float* final_ln, float* y, int y_ld, const float* next_layer, int next_F, const float* pos, float* qkv, void* stream);
+
+/* make_predictor (mfiller_cond.py:57-73): n_layers Linear layers with nn.LeakyReLU() between; dims[n_layers + 1] (host array);
+ * pack = per layer W^T [in][out] | b [out]. */
+int vt_infill_mlp(const float* x, int x_ld, int n_tok, int n_layers, const int* dims, const float* pack, float* out, int out_ld, void* stream);
+
+/* One clip of the autoregressive loop with obj_dim 6 (test_infill_autoreg.py:93-105 and 116-153, test_cinfill_autoreg.py:43-49): frames
+ * [start, start + T) of rot6d_smpl[L][144] | trans_smpl[L][3] -> data_smpl[T][147]; data_obj[T][6] takes rot6d_out (the running prediction)
+ * for the first n_ctx frames and rot6d_obj for the others, rows with mask[t] != 0 multiplied by zero. */
+int vt_infill_pack_clip(const float* rot6d_smpl, const float* trans_smpl, const float* rot6d_obj, const float* rot6d_out, const unsigned char* mask,
+                        int L, int start, int T, int n_ctx, float* data_smpl, float* data_obj, void* stream);
+
+/* rot6d_out[start + t] = pred[t] for t in [t0, T) (test_infill_autoreg.py:110 and 160). */
+int vt_infill_commit_clip(const float* pred, int L, int start, int t0, int T, float* rot6d_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -15,6 +15,8 @@ seeded synthetic checkpoint of ``vistracker_b200.synth`` and stores inputs-by-se
                                every 8th pixel of each feature map
 * ``smpl_small.npz``        -- SMPL_Layer.forward on the synthetic SMPL-H model, B=5, outputs + gradients
 * ``eval_chamfer.npz``      -- recon/eval/chamfer_distance.py (sklearn kd-tree) on three cloud pairs, all three directions
+* ``infill_small.npz``      -- (``--only infill``) ConditionalMInfiller forward on two batches and CondMotionInfillAutoreg.test (the
+  reference's own autoregressive clip loop, file IO redirected to a temporary folder) on a 400-frame synthetic sequence.
 * ``smooth_small.npz``      -- (``--only smooth``) SmoothNetSMPL / SmoothNet through SMPLTSmoother / ObjrotSmoother pre- and
                                post-processing on a 90-frame synthetic trajectory, window 64, + the rotation conversions
 """
@@ -423,6 +425,72 @@ def asset_fixtures(out_dir: str, ref_root: str):
     np.savez_compressed(os.path.join(out_dir, "assets.npz"), **out)
     print("assets:", {k: v.shape for k, v in out.items()})
 
+def infill_goldens(out_dir: str):
+    """HVOP-Net: the reference's ConditionalMInfiller (eval mode, config/cmf-k4-lrot.json, seeded synthetic checkpoint of
+    vistracker_b200/synth.py) on two batches, and the reference's own autoregressive loop -- CondMotionInfillAutoreg.test, file IO redirected
+    to a temporary folder -- on a 400-frame synthetic sequence (a full first clip, 8 strided clips, a short last clip) -> infill_small.npz."""
+    import tempfile
+    from argparse import Namespace
+    import joblib
+    b = _stub("behave"); b.utils = _stub("behave.utils", load_template=None); b.frame_data = _stub("behave.frame_data", FrameDataReader=object)
+    t = _stub("trainer"); t.__path__ = []; _stub("trainer.train_utils", load_checkpoint=None)     # trainer/ imports trimesh; only load_checkpoint is used
+    _stub("recon.pca_util", PCAUtil=object)
+    _stub("lib_smpl", get_smpl=None)
+    from config.config_loader import load_configs                                     # reference
+    from interp.test_cinfill_autoreg import CondMotionInfillAutoreg                   # reference
+    from model import ConditionalMInfiller                                            # reference
+    from vistracker_b200.synth import synthetic_infill_sequence, synthetic_infill_state_dict
+
+    with contextlib.redirect_stdout(io.StringIO()):
+        opt = load_configs("cmf-k4-lrot")
+    sd = synthetic_infill_state_dict(opt, seed=21)
+    net = ConditionalMInfiller(opt).eval()
+    missing = net.load_state_dict(sd, strict=True)
+    out = {"opt_json": json.dumps({k: v for k, v in vars(opt).items() if isinstance(v, (int, float, str, bool, list))})}
+
+    rng = np.random.default_rng(3)
+    for tag, B, T in (("a", 2, 180), ("b", 1, 47)):
+        ds = rng.standard_normal((B, T, opt.dim_smpl)).astype(np.float32)
+        do = rng.standard_normal((B, T, opt.dim_obj)).astype(np.float32)
+        mo = rng.random((B, T)) < 0.4
+        mo[:, :5] = False
+        ms = np.zeros((B, T), bool)
+        if tag == "b":
+            ms[:, 10:20] = True                                                        # the SMPL branch's mask is honoured too
+        do = do * (1 - mo[..., None].astype(np.float32))
+        with torch.no_grad():
+            pred = net(torch.from_numpy(ds), torch.from_numpy(ms), torch.from_numpy(do), torch.from_numpy(mo))
+        out.update({f"{tag}_data_smpl": ds, f"{tag}_mask_smpl": ms, f"{tag}_data_obj": do, f"{tag}_mask_obj": mo, f"{tag}_pred": pred.numpy()})
+
+    L = 400
+    rot6d_smpl, trans_smpl, rot6d_obj, trans_obj, occ = synthetic_infill_sequence(L, seed=5)
+    tmp = tempfile.mkdtemp(prefix="vt_infill_")
+    seq = "Date03_Sub03_chairwood_synthetic"
+
+    class Tester(CondMotionInfillAutoreg):
+        def __init__(self):
+            self.device, self.outdir, self.model, self.icap_kid, self.exp_name = "cpu", tmp, net, 2, "cmf-k4-lrot"
+
+        def get_test_files(self, args, recon_name):
+            return [os.path.join(tmp, "in.pkl")], [seq]
+
+        def prepare_rot6d(self, args, dat, file, recon_name, seq_name, gt_data):
+            return rot6d_obj.copy(), rot6d_smpl.copy()
+
+    joblib.dump({"frames": [f"t{i:04d}.000" for i in range(L)], "trans": trans_smpl.copy(), "obj_trans": trans_obj.copy(),
+                 "obj_angles": np.zeros((L, 3, 3), np.float32)}, os.path.join(tmp, "in.pkl"))
+    os.makedirs(os.path.join(tmp, "recon_objname"), exist_ok=True)
+    joblib.dump({"neural_visibility": np.stack([occ, occ], 1)}, os.path.join(tmp, f"recon_objname/{seq}_k1.pkl"))
+    args = Namespace(**vars(opt))
+    args.smpl_recon_name, args.obj_recon_name, args.save_name, args.occ_thres, args.occ_pred = "smplname", "objname", "out", 0.5, True
+    with contextlib.redirect_stdout(io.StringIO()), contextlib.redirect_stderr(io.StringIO()):
+        Tester().test(args)
+    res = joblib.load(os.path.join(tmp, f"recon_out/{seq}_k1.pkl"))
+    out.update({"seq_L": L, "seq_rot6d_smpl": rot6d_smpl, "seq_trans_smpl": trans_smpl, "seq_rot6d_obj": rot6d_obj, "seq_trans_obj": trans_obj,
+                "seq_occ": occ, "seq_obj_angles": res["obj_angles"], "seq_obj_trans": res["obj_trans"], "seq_obj_scales": res["obj_scales"]})
+    np.savez_compressed(os.path.join(out_dir, "infill_small.npz"), **out)
+    print("infill_small.npz:", {k: getattr(v, "shape", v) for k, v in out.items() if k != "opt_json"}, missing)
+
 
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
@@ -445,3 +513,5 @@ if __name__ == "__main__":
         eval_goldens(HERE)
     if a.only == "smooth":                  # stubs `behave` / `yacs`: run on its own
         smooth_goldens(HERE)
+    if a.only == "infill":                  # stubs `behave` / `trainer`: run on its own
+        infill_goldens(HERE)

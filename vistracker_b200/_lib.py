@@ -76,6 +76,13 @@ SIGNATURES.update({
     "vt_smooth_window_mean": (_i, [_p, _p, _i, _i, _i, _i, _i, _p, _p]),
     "vt_smooth_unpack_smplt": (_i, [_p, _i, _p, _p, _p, _p]),
     "vt_smooth_rot6d_to_rotmat": (_i, [_p, _i, _i, _p, _p]),
+    "vt_infill_layer_pack_floats": (_ll, [_i, _i]),
+    "vt_infill_head": (_i, [_p, _i, _i, _p, _p, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p]),
+    "vt_infill_attn": (_i, [_p, _p, _i, _i, _i, _i, _p, _p]),
+    "vt_infill_tail": (_i, [_p, _i, _p, _i, _i, _i, _i, _i, _i, _p, _p, _p, _i, _p, _i, _p, _p, _p]),
+    "vt_infill_mlp": (_i, [_p, _i, _i, _i, _p, _p, _p, _i, _p]),
+    "vt_infill_pack_clip": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _p, _p, _p]),
+    "vt_infill_commit_clip": (_i, [_p, _i, _i, _i, _i, _p, _p]),
     "vt_raster_fwd": (_i, [_p, _p, _i, _i, _i, _i, _p, _i, _p, _p, _p, _p, _p]),
     "vt_raster_bwd": (_i, [_p, _p, _i, _i, _i, _i, _p, _i, _p, _p, _p, _p, _p, _p, _p]),
 })

@@ -137,3 +137,62 @@ def synthetic_frames(batch: int, size: int = 512, seed: int = 0, n_points: int =
     pts = pts * np.array([2.0, 3.0, 1.2], np.float32) - np.array([1.0, 1.5, 0.6], np.float32) + body[:, None, :]
     return (torch.from_numpy(img), torch.from_numpy(pts.astype(np.float32)), torch.from_numpy(crop),
             torch.from_numpy(body))
+
+
+def infill_spec(opt) -> list:
+    """(key, shape, kind) of a ``ConditionalMInfiller`` checkpoint (model/infill/mfiller_cond.py:20-55; layers of
+    model/transformers/former_deci.py:31-51 around nn.MultiheadAttention), in state_dict order."""
+    g = (lambda k: opt[k]) if isinstance(opt, dict) else (lambda k: getattr(opt, k))
+    spec = [("feat_proj_smpl.weight", (g("d_model_smpl"), g("dim_smpl")), "w"), ("feat_proj_smpl.bias", (g("d_model_smpl"),), "b"),
+            ("feat_proj_obj.weight", (g("d_model_obj"), g("dim_obj")), "w"), ("feat_proj_obj.bias", (g("d_model_obj"),), "b")]
+    d_joint = g("d_model_smpl") + g("d_model_obj")
+    for name, D in (("smpl", g("d_model_smpl")), ("obj", g("d_model_obj")), ("joint", d_joint)):
+        F = g("dim_forward_" + name)
+        for i in range(g("num_layers_" + name)):
+            p = f"encoder_{name}.encoder.layers.{i}."
+            spec += [(p + "self_attn.in_proj_weight", (3 * D, D), "w"), (p + "self_attn.in_proj_bias", (3 * D,), "b"),
+                     (p + "self_attn.out_proj.weight", (D, D), "w"), (p + "self_attn.out_proj.bias", (D,), "b"),
+                     (p + "linear1.weight", (F, D), "w"), (p + "linear1.bias", (F,), "b"),
+                     (p + "linear2.weight", (D, F), "w"), (p + "linear2.bias", (D,), "b"),
+                     (p + "norm1.weight", (D,), "ln_w"), (p + "norm1.bias", (D,), "ln_b"),
+                     (p + "norm2.weight", (D,), "ln_w"), (p + "norm2.bias", (D,), "ln_b")]
+        if g("pre_norm_" + name):
+            spec += [(f"encoder_{name}.encoder.norm.weight", (D,), "ln_w"), (f"encoder_{name}.encoder.norm.bias", (D,), "ln_b")]
+    dims = [d_joint] + list(g("hidden_dims")) + [g("out_dim")]
+    for i in range(len(dims) - 1):
+        spec += [(f"predictor.{2 * i}.weight", (dims[i + 1], dims[i]), "w"), (f"predictor.{2 * i}.bias", (dims[i + 1],), "b")]
+    return spec
+
+
+def synthetic_infill_state_dict(opt, seed: int = 0) -> "OrderedDict[str, torch.Tensor]":
+    """Seeded random HVOP-Net checkpoint with the reference's key set: weights N(0, 1.5 / fan_in) (sharp enough that the attention is far
+    from uniform), biases N(0, 0.1), LayerNorm affines around (1, 0)."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    sd: "OrderedDict[str, torch.Tensor]" = OrderedDict()
+    for key, shape, kind in infill_spec(opt):
+        if kind == "w":
+            a = rng.standard_normal(shape, dtype=np.float32) * np.float32(np.sqrt(1.5 / shape[1]))
+        elif kind == "ln_w":
+            a = 1 + rng.standard_normal(shape, dtype=np.float32) * np.float32(0.1)
+        else:
+            a = rng.standard_normal(shape, dtype=np.float32) * np.float32(0.1)
+        sd[key] = torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32))
+    return sd
+
+
+def synthetic_infill_sequence(L: int, seed: int = 0, occluded=((70, 130), (215, 290))):
+    """A smooth synthetic trajectory in the in-filler's input format: rot6d_smpl [L,144], trans_smpl [L,3], rot6d_obj [L,6] (noisy inside the
+    occluded spans), trans_obj [L,3], occ_ratios [L] (visible fraction, low inside the spans).  float32 numpy."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    t = np.arange(L, dtype=np.float64)[:, None] / 30.0
+    rot6d_smpl = np.sin(t * rng.uniform(0.3, 2.0, (1, 144)) + rng.uniform(0, 6.28, (1, 144))) * 0.8
+    trans_smpl = np.array([[0.1, -0.2, 2.4]]) + 0.3 * np.sin(t * np.array([[0.7, 1.1, 0.4]]))
+    rot6d_obj = np.sin(t * rng.uniform(0.2, 1.0, (1, 6)) + rng.uniform(0, 6.28, (1, 6)))
+    trans_obj = np.array([[0.3, 0.1, 2.2]]) + 0.2 * np.sin(t * np.array([[0.5, 0.9, 0.3]]))
+    occ = 0.75 + 0.2 * rng.random(L)
+    for a, b in occluded:
+        a, b = min(a, L), min(b, L)
+        occ[a:b] = 0.05 + 0.3 * rng.random(b - a)
+        rot6d_obj[a:b] += 0.5 * rng.standard_normal((b - a, 6))
+    f = lambda x: np.ascontiguousarray(x, dtype=np.float32)
+    return f(rot6d_smpl), f(trans_smpl), f(rot6d_obj), f(trans_obj), f(occ)
