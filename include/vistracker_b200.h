@@ -246,6 +246,11 @@ int vt_fit_end_step(const double* acc, int B, int n_coords, float* ctrl, double*
 int vt_so3_project_fwd(const float* M, int B, float* R, void* stream);
 int vt_so3_project_bwd(const float* M, const float* gR, int B, float* gM, void* stream);
 
+/* init_object_orientation (recon/recon_fit_base.py:202-216; recon/pca_util.py:59-72): R[b] = project_so3((S^T S)^-1 S^T T[b] + 1e-4 noise[b])
+ * with T = tgt_axis[B][3][3] (the predicted PCA axes), S = src_axis (the template's; [B][3][3] when src_per_frame != 0, else one [3][3]
+ * shared by all frames), noise[B][3][3] the U(0,1) draws of decopose_axis or NULL (PCAUtil's variant adds none). */
+int vt_pca_orientation(const float* tgt_axis, const float* src_axis, int src_per_frame, const float* noise, int B, float* R, void* stream);
+
 /* pytorch3d.loss.chamfer_distance(Pointclouds(xs), Pointclouds(ys)) with default reductions, as called by compute_contact_loss
  * (recon/recon_fit_trivis_full.py:452-456): N ragged cloud pairs, x[sum_n][3] with x_off[N+1] row offsets (same for y).
  * loss[1] = mean_n ( mean_i min_j |x_i-y_j|^2 + mean_j min_i |y_j-x_i|^2 ); nn_x / nn_y receive the arg-min rows for backward.

@@ -96,3 +96,15 @@ def evaluate_sequence(sverts_recon, overts_recon, sverts_gt, overts_gt, window, 
         row = [eval_chamfer(g, r) * 100.0 for g, r in zip(gt, rec)] + [np.sqrt(((g - r) ** 2).sum(-1)).mean() * 100.0 for g, r in zip(gt, rec)]
         out.append(row)
     return np.asarray(out)
+
+
+def init_object_orientation(tgt_axis: torch.Tensor, src_axis: torch.Tensor, noise: torch.Tensor = None) -> torch.Tensor:
+    """recon/recon_fit_base.py:202-225 (inverse = (S^T S)^-1 S^T, then decopose_axis) and recon/pca_util.py:59-72 (noise None)."""
+    S, T = src_axis.double(), tgt_axis.double()
+    if S.dim() == 2:
+        S = S[None].expand(T.shape[0], 3, 3)
+    pseudo = torch.linalg.inv(S.transpose(1, 2) @ S) @ S.transpose(1, 2)
+    rot = pseudo @ T
+    if noise is not None:
+        rot = rot + 1e-4 * noise.double()
+    return project_so3(rot)

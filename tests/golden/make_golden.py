@@ -434,8 +434,8 @@ def infill_goldens(out_dir: str):
     import joblib
     b = _stub("behave"); b.utils = _stub("behave.utils", load_template=None); b.frame_data = _stub("behave.frame_data", FrameDataReader=object)
     t = _stub("trainer"); t.__path__ = []; _stub("trainer.train_utils", load_checkpoint=None)     # trainer/ imports trimesh; only load_checkpoint is used
-    _stub("recon.pca_util", PCAUtil=object)
     _stub("lib_smpl", get_smpl=None)
+    from recon.pca_util import PCAUtil                                                # reference
     from config.config_loader import load_configs                                     # reference
     from interp.test_cinfill_autoreg import CondMotionInfillAutoreg                   # reference
     from model import ConditionalMInfiller                                            # reference
@@ -461,6 +461,14 @@ def infill_goldens(out_dir: str):
         with torch.no_grad():
             pred = net(torch.from_numpy(ds), torch.from_numpy(ms), torch.from_numpy(do), torch.from_numpy(mo))
         out.update({f"{tag}_data_smpl": ds, f"{tag}_mask_smpl": ms, f"{tag}_data_obj": do, f"{tag}_mask_obj": mo, f"{tag}_pred": pred.numpy()})
+
+    # the glue between SIF-Net's PCA-axis prediction and the rotation inputs of this stage (test_infiller.py:172-183, smooth_objrot.py:46-57)
+    q, _ = np.linalg.qr(rng.standard_normal((3, 3)))
+    src = (q * np.array([[1.0], [0.6], [0.3]])).astype(np.float32)                    # rows = scaled, orthogonal template axes
+    tgt = np.stack([np.linalg.qr(rng.standard_normal((3, 3)))[0] @ src + 0.05 * rng.standard_normal((3, 3)) for _ in range(40)]).astype(np.float32)
+    tgt[3] *= -1                                                                      # a reflected prediction: the det fix of project_so3
+    out.update({"pca_src": src, "pca_tgt": tgt,
+                "pca_R": PCAUtil.init_object_orientation(torch.from_numpy(tgt), torch.stack([torch.from_numpy(src)] * 40, 0)).numpy()})
 
     L = 400
     rot6d_smpl, trans_smpl, rot6d_obj, trans_obj, occ = synthetic_infill_sequence(L, seed=5)

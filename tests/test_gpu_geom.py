@@ -116,3 +116,25 @@ def test_procrustes_matches_reference_golden():
     b = torch.stack([torch.from_numpy(gold["pa_dst0"]), torch.from_numpy(gold["pa_dst0"]).flip(0)]).to(dev)
     Rb, tb, sb = procrustes_transform(a, b)
     assert rel_err(Rb[0].cpu(), Rb[1].cpu()) < 1e-5 and rel_err(Rb[0].cpu(), gold["pa_R0"]) < 2e-5
+
+
+def test_pca_orientation_matches_reference_golden_and_oracle():
+    """vt_pca_orientation: PCAUtil.init_object_orientation's values (infill_small.npz), a per-frame template stack, and the decopose_axis
+    variant with injected noise against the float64 restatement."""
+    import os
+    import numpy as np
+    from oracle import geom_ref as GR
+    from vistracker_b200.geom import init_object_orientation
+    _need_gpu()
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "infill_small.npz"))
+    tgt, src = torch.from_numpy(g["pca_tgt"]).cuda(), torch.from_numpy(g["pca_src"]).cuda()
+    got = init_object_orientation(tgt, src, no_rand=True)
+    assert np.abs(got.cpu().numpy() - g["pca_R"]).max() < 2e-5
+    stack = src[None].repeat(tgt.shape[0], 1, 1)
+    assert torch.equal(init_object_orientation(tgt, stack, no_rand=True), got)
+    noise = torch.rand(tgt.shape[0], 3, 3, generator=torch.Generator().manual_seed(2))
+    ref = GR.init_object_orientation(tgt.cpu(), src.cpu(), noise=noise)
+    assert rel_err(init_object_orientation(tgt, src, noise=noise.cuda()).cpu(), ref) < 1e-5
+    assert init_object_orientation(tgt, src).shape == (tgt.shape[0], 3, 3)
+    with pytest.raises(ValueError, match="invalid shapes"):
+        init_object_orientation(tgt, stack[:3])

@@ -49,3 +49,11 @@ def test_position_embedding_shapes_and_spec():
     assert float(R.position_embedding(1, 8).abs().max()) <= 1.0
     g, opt, sd = _load()
     assert [k for k, _, _ in infill_spec(opt)] == list(sd.keys())
+
+
+def test_pca_orientation_matches_reference_pcautil():
+    from oracle import geom_ref as G
+    g = np.load(GOLD)
+    R_ref = G.init_object_orientation(torch.from_numpy(g["pca_tgt"]), torch.from_numpy(g["pca_src"]))
+    assert np.abs(R_ref.numpy() - g["pca_R"]).max() < 2e-5
+    assert np.abs(np.linalg.det(g["pca_R"]) - 1).max() < 1e-5

@@ -156,4 +156,18 @@ _xa, _ya = torch.randn(16, 10000, 3, device=dev), torch.randn(16, 10000, 3, devi
 ms = timeit(lambda: eval_chamfer_distance(_xa, _ya))
 row("evaluation Chamfer, 16 frames x (10 000 vs 10 000 points), both directions", ms, 16, "frames", 2 * 10000 * 12 + 2 * 10000 * 4, 2 * 1e8 * 8,
     "brute force, other cloud streamed through shared memory; 8 flop per pair")
+# ---------------------------------------------------------------- HVOP-Net (8(f) N2): autoregressive in-filling of a 1500-frame sequence
+from vistracker_b200.infill import CondMotionInfillAutoreg, ConditionalMInfiller, default_infill_options  # noqa: E402
+from vistracker_b200.synth import synthetic_infill_sequence, synthetic_infill_state_dict  # noqa: E402
+_opt = default_infill_options()
+_inf = ConditionalMInfiller(_opt, device=dev).load_state_dict(synthetic_infill_state_dict(_opt, 1))
+_seq = synthetic_infill_sequence(_T, seed=3)
+_occ = _seq[4]
+_seq_d = [torch.from_numpy(a).to(dev) for a in _seq[:4]]
+_drv = CondMotionInfillAutoreg(_inf)
+ms = timeit(lambda: _drv.infill(*_seq_d, _occ))
+_clips = len(_drv.clip_plan(_T))
+_mac_tok = sum(p.numel() for e in (_inf.enc_smpl, _inf.enc_obj, _inf.enc_joint) for p in e.layers) + 180 * (128 + 32 + 160) * 2 * 0 + 2 * 180 * (2 * 128 + 2 * 32 + 4 * 160)
+row(f"HVOP-Net autoregressive in-filling, 1500 frames ({_clips} serial clips x 21 launches, one CUDA graph)", ms, _T, "frames", None,
+    _clips * 180 * 2 * _mac_tok / _T, "latency-bound: clip i+1 is seeded by clip i; fp32 FFMA; ms includes the mask upload and output clones")
 print(json.dumps({"peaks": peaks, "rows": rows}, indent=1))

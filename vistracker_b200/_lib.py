@@ -63,6 +63,7 @@ SIGNATURES.update({
     "vt_fit_end_step": (_i, [_p, _i, _i, _p, _p, _i, _p]),
     "vt_so3_project_fwd": (_i, [_p, _i, _p, _p]),
     "vt_so3_project_bwd": (_i, [_p, _p, _i, _p, _p]),
+    "vt_pca_orientation": (_i, [_p, _p, _i, _p, _i, _p, _p]),
     "vt_chamfer_fwd": (_i, [_p, _p, _p, _p, _i, _p, _p, _p, _p]),
     "vt_chamfer_bwd": (_i, [_p, _p, _p, _p, _i, _p, _p, _p, _p, _p, _p]),
     "vt_query_bwd_heads": (_i, [_p, _p, _p, _i, _i, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _i, _p, _p]),

@@ -61,6 +61,44 @@ __global__ void so3_fwd_kernel(const float* __restrict__ M, int B, float* __rest
   for (int e = 0; e < 9; ++e) Rout[(size_t)b * 9 + e] = (float)R[e];
 }
 
+// init_object_orientation (recon/recon_fit_base.py:202-216, recon/pca_util.py:59-72): rot = (S^T S)^-1 S^T T, then the SO(3) projection of
+// rot (+ 1e-4 noise when given: decopose_axis).  src_stride 0 repeats one template axis set for every frame.
+__global__ void pca_orientation_kernel(const float* __restrict__ tgt, const float* __restrict__ src, int src_stride, const float* __restrict__ noise, int B,
+                                       float* __restrict__ Rout) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const float* S = src + (size_t)b * src_stride;
+  const float* T = tgt + (size_t)b * 9;
+  double G[9], Gi[9], P[9];
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) {
+      double g = 0;
+      for (int k = 0; k < 3; ++k) g += (double)S[k * 3 + i] * (double)S[k * 3 + j];
+      G[i * 3 + j] = g;
+    }
+  const double det = G[0] * (G[4] * G[8] - G[5] * G[7]) - G[1] * (G[3] * G[8] - G[5] * G[6]) + G[2] * (G[3] * G[7] - G[4] * G[6]);
+  const double id = 1.0 / det;                       // singular template axes: inf / NaN, as torch.inverse would raise
+  Gi[0] = (G[4] * G[8] - G[5] * G[7]) * id; Gi[1] = (G[2] * G[7] - G[1] * G[8]) * id; Gi[2] = (G[1] * G[5] - G[2] * G[4]) * id;
+  Gi[3] = (G[5] * G[6] - G[3] * G[8]) * id; Gi[4] = (G[0] * G[8] - G[2] * G[6]) * id; Gi[5] = (G[2] * G[3] - G[0] * G[5]) * id;
+  Gi[6] = (G[3] * G[7] - G[4] * G[6]) * id; Gi[7] = (G[1] * G[6] - G[0] * G[7]) * id; Gi[8] = (G[0] * G[4] - G[1] * G[3]) * id;
+  for (int i = 0; i < 3; ++i)                        // pseudo-inverse P = G^-1 S^T
+    for (int j = 0; j < 3; ++j) {
+      double v = 0;
+      for (int k = 0; k < 3; ++k) v += Gi[i * 3 + k] * (double)S[j * 3 + k];
+      P[i * 3 + j] = v;
+    }
+  float M[9];
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) {
+      double v = 0;
+      for (int k = 0; k < 3; ++k) v += P[i * 3 + k] * (double)T[k * 3 + j];
+      M[i * 3 + j] = (float)v + (noise ? 1e-4f * noise[(size_t)b * 9 + i * 3 + j] : 0.f);
+    }
+  double R[9];
+  so3_project(M, R);
+  for (int e = 0; e < 9; ++e) Rout[(size_t)b * 9 + e] = (float)R[e];
+}
+
 // dL/dM = R [c]x with c = (tr(P) I - P)^-1 b, P = sym(R^T M), b = axial(R^T G - G^T R)
 __global__ void so3_bwd_kernel(const float* __restrict__ M, const float* __restrict__ G, int B, float* __restrict__ gM) {
   const int bi = blockIdx.x * blockDim.x + threadIdx.x;
@@ -277,6 +315,14 @@ int vt_so3_project_fwd(const float* M, int B, float* R, void* stream) {
   if (B <= 0) return 0;
   so3_fwd_kernel<<<ceil_div(B, 64), 64, 0, (cudaStream_t)stream>>>(M, B, R);
   VT_CHECK_LAUNCH("vt_so3_project_fwd");
+  return 0;
+}
+
+int vt_pca_orientation(const float* tgt_axis, const float* src_axis, int src_per_frame, const float* noise, int B, float* R, void* stream) {
+  if (B <= 0) return 0;
+  VT_CHECK_ARG(tgt_axis && src_axis && R, "vt_pca_orientation: null pointer");
+  pca_orientation_kernel<<<ceil_div(B, 64), 64, 0, (cudaStream_t)stream>>>(tgt_axis, src_axis, src_per_frame ? 9 : 0, noise, B, R);
+  VT_CHECK_LAUNCH("vt_pca_orientation");
   return 0;
 }
 

@@ -37,6 +37,7 @@ constexpr float IF_LN_EPS = 1e-5f;  // nn.LayerNorm default
 struct IfLayer {                    // offsets (floats) into a layer pack
   int ln1, wqkv, bqkv, wo, bo, ln2, w1, b1, w2, b2, total;
 };
+__host__ __device__ inline int if_pad4(int n) { return (n + 3) & ~3; }
 __host__ __device__ inline IfLayer if_layer(int D, int F) {
   IfLayer l;
   int o = 0;
@@ -69,16 +70,24 @@ __device__ __forceinline__ void if_dense(const float* xs, int ldx, int K, const 
 #pragma unroll
     for (int t = 0; t < IF_TB; ++t) acc[t] = b;
     const float* w = Wt + o;
-    // the stage is latency-bound (a handful of CTAs, every one streaming the whole matrix out of L2): keep IF_KU loads in flight per thread
+    // the stage is latency-bound (a handful of CTAs, every one streaming the whole matrix out of L2): keep IF_KU loads in flight per thread;
+    // activations are read four k at a time (rows are 16-byte aligned and zero-padded to a multiple of 4)
     for (int k = 0; k < K; k += IF_KU) {
       float wv[IF_KU];
 #pragma unroll
       for (int u = 0; u < IF_KU; ++u) wv[u] = k + u < K ? __ldg(w + (size_t)(k + u) * ldw) : 0.f;
 #pragma unroll
-      for (int u = 0; u < IF_KU; ++u) {
-        const int ku = min(k + u, K - 1);            // wv is 0 past the end
+      for (int u = 0; u < IF_KU; u += 4) {
+        if (k + u < K) {
 #pragma unroll
-        for (int t = 0; t < IF_TB; ++t) acc[t] = fmaf(xs[t * ldx + ku], wv[u], acc[t]);
+          for (int t = 0; t < IF_TB; ++t) {
+            const float4 xv = *reinterpret_cast<const float4*>(xs + t * ldx + k + u);
+            acc[t] = fmaf(xv.x, wv[u], acc[t]);
+            acc[t] = fmaf(xv.y, wv[u + 1], acc[t]);
+            acc[t] = fmaf(xv.z, wv[u + 2], acc[t]);
+            acc[t] = fmaf(xv.w, wv[u + 3], acc[t]);
+          }
+        }
       }
     }
     epi(o, acc);
@@ -127,15 +136,17 @@ struct IfTokenArgs {
 };
 
 __global__ void __launch_bounds__(IF_THREADS) infill_token_kernel(IfTokenArgs a) {
-  extern __shared__ float sm[];
-  const int D = a.D, ld = a.D + 1;
+  extern __shared__ __align__(16) float sm[];
+  const int D = a.D, ld = if_pad4(a.D);
   float* xs = sm;                       // [TB][ld] residual stream
   float* hs = xs + IF_TB * ld;          // [TB][ld] LayerNorm output / attention rows
   float* hp = hs + IF_TB * ld;          // [TB][ld] LayerNorm output + positional embedding
   float* fs = hp + IF_TB * ld;          // [TB][max(F, in_dim) + 1]
-  const int ldf = max(a.F, a.in_dim) + 1;
+  const int ldf = if_pad4(max(max(a.F, a.in_dim), 1));
   const int tok0 = blockIdx.x * IF_TB;
   const int tid = threadIdx.x;
+  for (int i = tid; i < IF_TB * (3 * ld + ldf); i += IF_THREADS) sm[i] = 0.f;      // the pad columns must hold finite values
+  __syncthreads();
 
   if (a.in) {                            // feature projection (mfiller_cond.py:91, 93)
     for (int i = tid; i < IF_TB * a.in_dim; i += IF_THREADS) {
@@ -211,27 +222,40 @@ __global__ void __launch_bounds__(IF_THREADS) infill_token_kernel(IfTokenArgs a)
 }
 
 // grid (ceil(T / IF_QB), heads, clips); nn.MultiheadAttention core (former_deci.py:84-88) with key_padding_mask (True = ignored key)
+__device__ __forceinline__ void if_stage_head(float* dst, int ldk, const float* __restrict__ src, int T, int dh, int pitch) {
+  if ((dh & 3) == 0 && (pitch & 3) == 0 && (reinterpret_cast<size_t>(src) & 15) == 0) {
+    const int q4 = dh >> 2;
+    for (int i = threadIdx.x; i < T * q4; i += IF_THREADS) {
+      const int j = i / q4, c = (i - j * q4) * 4;
+      const float4 v = __ldg(reinterpret_cast<const float4*>(src + (size_t)j * pitch + c));
+      float* d = dst + j * ldk + c;
+      d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+    }
+  } else {
+    for (int i = threadIdx.x; i < T * dh; i += IF_THREADS) {
+      const int j = i / dh, c = i - j * dh;
+      dst[j * ldk + c] = __ldg(src + (size_t)j * pitch + c);
+    }
+  }
+}
+
 __global__ void __launch_bounds__(IF_THREADS) infill_attn_kernel(const float* __restrict__ qkv, const unsigned char* __restrict__ key_mask, int T, int D, int heads,
                                                                  float* __restrict__ attn) {
-  extern __shared__ float sm[];
+  extern __shared__ __align__(16) float sm[];
   const int dh = D / heads, ldk = dh | 1;                // odd pitch: lane j reads row j conflict-free
-  float* Ks = sm;                                        // [T][ldk]
+  float* Ks = sm;                                        // [T][ldk]: the head's keys, then its values
   float* qs = Ks + (size_t)T * ldk;                      // [QB][dh]
   float* ps = qs + IF_QB * dh;                           // [QB][T]
   const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * IF_QB;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const float* base = qkv + (size_t)b * T * 3 * D;
-  for (int i = threadIdx.x; i < T * dh; i += IF_THREADS) {
-    const int j = i / dh, c = i % dh;
-    Ks[j * ldk + c] = base[(size_t)j * 3 * D + D + h * dh + c];
-  }
+  if_stage_head(Ks, ldk, base + D + h * dh, T, dh, 3 * D);
   for (int i = threadIdx.x; i < IF_QB * dh; i += IF_THREADS) {
     const int qi = i / dh, c = i % dh;
     qs[i] = base[(size_t)min(q0 + qi, T - 1) * 3 * D + h * dh + c];
   }
   __syncthreads();
-  const int q = q0 + warp;
-  if (q >= T) return;
+  const int q = min(q0 + warp, T - 1);                   // warps past the end repeat the last query and do not store
   float s[IF_MAX_T / 32];
 #pragma unroll
   for (int i = 0; i < IF_MAX_T / 32; ++i) s[i] = 0.f;
@@ -267,28 +291,25 @@ __global__ void __launch_bounds__(IF_THREADS) infill_attn_kernel(const float* __
     const int j = lane + 32 * i;
     if (j < T) ps[warp * T + j] = s[i] * inv;
   }
-  __syncwarp();
-  const float* V = base + 2 * D + h * dh;
+  __syncthreads();                                       // every warp is done with the keys
+  if_stage_head(Ks, ldk, base + 2 * D + h * dh, T, dh, 3 * D);
+  __syncthreads();
   for (int c0 = 0; c0 < dh; c0 += 128) {
     float o4[4] = {0.f, 0.f, 0.f, 0.f};
-    const int ni = min(4, (dh - c0 - lane + 31) / 32);        // columns this lane owns in the pass
-    for (int j0 = 0; j0 < T; j0 += 8) {
-      float vv[8][4];
+    for (int j = 0; j < T; ++j) {
+      const float p = ps[warp * T + j];
 #pragma unroll
-      for (int u = 0; u < 8; ++u)
-#pragma unroll
-        for (int i = 0; i < 4; ++i) vv[u][i] = (j0 + u < T && i < ni) ? __ldg(V + (size_t)(j0 + u) * 3 * D + c0 + lane + 32 * i) : 0.f;
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const float p = ps[warp * T + min(j0 + u, T - 1)];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) o4[i] = fmaf(p, vv[u][i], o4[i]);
+      for (int i = 0; i < 4; ++i) {
+        const int c = c0 + lane + 32 * i;
+        if (c < dh) o4[i] = fmaf(p, Ks[j * ldk + c], o4[i]);
       }
     }
+    if (q0 + warp < T) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int c = c0 + lane + 32 * i;
-      if (c < dh) attn[((size_t)b * T + q) * D + h * dh + c] = o4[i];
+      for (int i = 0; i < 4; ++i) {
+        const int c = c0 + lane + 32 * i;
+        if (c < dh) attn[((size_t)b * T + q) * D + h * dh + c] = o4[i];
+      }
     }
   }
 }
@@ -297,13 +318,15 @@ __global__ void __launch_bounds__(IF_THREADS) infill_attn_kernel(const float* __
 struct IfMlpArgs { const float* x; int x_ld; int n_tok; int n_layers; int dims[6]; const float* pack; float* out; int out_ld; };
 
 __global__ void __launch_bounds__(IF_THREADS) infill_mlp_kernel(IfMlpArgs a) {
-  extern __shared__ float sm[];
+  extern __shared__ __align__(16) float sm[];
   int wmax = 0;
   for (int i = 0; i <= a.n_layers; ++i) wmax = max(wmax, a.dims[i]);
-  const int ld = wmax + 1;
+  const int ld = if_pad4(wmax);
   float* cur = sm;
   float* nxt = sm + IF_TB * ld;
   const int tok0 = blockIdx.x * IF_TB;
+  for (int i = threadIdx.x; i < 2 * IF_TB * ld; i += IF_THREADS) sm[i] = 0.f;
+  __syncthreads();
   for (int i = threadIdx.x; i < IF_TB * a.dims[0]; i += IF_THREADS) {
     const int t = i / a.dims[0], c = i % a.dims[0];
     cur[t * ld + c] = a.x[(size_t)min(tok0 + t, a.n_tok - 1) * a.x_ld + c];
@@ -360,7 +383,7 @@ static int if_check_dims(const char* who, int n_tok, int T, int D, int F, int he
 }
 
 static int if_launch_token(const IfTokenArgs& a, const char* who, cudaStream_t st) {
-  const size_t smem = (size_t)(3 * IF_TB * (a.D + 1) + IF_TB * (max(a.F, a.in_dim) + 1)) * sizeof(float);
+  const size_t smem = (size_t)(3 * IF_TB * if_pad4(a.D) + IF_TB * if_pad4(max(max(a.F, a.in_dim), 1))) * sizeof(float);
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(infill_token_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return cuda_fail(e, who);
@@ -428,7 +451,7 @@ int vt_infill_mlp(const float* x, int x_ld, int n_tok, int n_layers, const int* 
     a.dims[i] = dims[i];
     wmax = max(wmax, dims[i]);
   }
-  const size_t smem = (size_t)2 * IF_TB * (wmax + 1) * sizeof(float);
+  const size_t smem = (size_t)2 * IF_TB * if_pad4(wmax) * sizeof(float);
   infill_mlp_kernel<<<ceil_div(n_tok, IF_TB), IF_THREADS, smem, (cudaStream_t)stream>>>(a);
   VT_CHECK_LAUNCH("vt_infill_mlp");
   return 0;

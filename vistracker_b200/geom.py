@@ -49,6 +49,24 @@ def decopose_axis(rot: torch.Tensor, no_rand: bool = False, noise: torch.Tensor 
     return project_so3(rot + 1e-4 * noise)
 
 
+def init_object_orientation(tgt_axis: torch.Tensor, src_axis: torch.Tensor, no_rand: bool = False, noise: torch.Tensor = None) -> torch.Tensor:
+    """``ReconFitterBase.init_object_orientation`` (recon/recon_fit_base.py:202-216): the rotation from the template's PCA axes ``src_axis``
+    ([B,3,3] or one [3,3]) to the predicted ones ``tgt_axis`` [B,3,3]: ``decopose_axis(pinv(src) @ tgt)``.  ``no_rand=True`` is
+    ``PCAUtil.init_object_orientation`` (recon/pca_util.py:59-72, used by the object smoother and HVOP-Net inputs): no noise."""
+    t = tgt_axis.detach().float().contiguous()
+    s = src_axis.detach().to(t.device).float().contiguous()
+    B = t.shape[0]
+    if t.shape[1:] != (3, 3) or s.shape[-2:] != (3, 3) or (s.dim() == 3 and s.shape[0] != B):
+        raise ValueError(f"invalid shapes {tuple(tgt_axis.shape)} / {tuple(src_axis.shape)}")
+    if not no_rand and noise is None:
+        noise = torch.rand(B, 3, 3, device=t.device)
+    nz = None if no_rand else noise.to(t.device).float().contiguous()
+    out = torch.empty_like(t)
+    with torch.cuda.device(t.device):
+        _lib.call("vt_pca_orientation", P(t), P(s), int(s.dim() == 3), P(nz), B, P(out), S())
+    return out
+
+
 class _ChamferFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, y, x_off, y_off):
