@@ -4,6 +4,7 @@ import os
 import pickle as pkl
 
 import numpy as np
+import pytest
 import torch
 
 from vistracker_b200 import io as vio
@@ -49,3 +50,25 @@ def test_neural_recon_npz(tmp_path):
     h = z["human"].item()
     assert sorted(h) == ["centers", "parts", "pca_axis", "points", "visibility"] and h["points"].shape == (50, 3)
     assert np.array_equal(h["parts"], batch["human"]["parts"][1].numpy())
+
+
+def test_smplh_pose_padding_and_param_copy():
+    """a14: SMPLHGenerator.get_smplh's 72 -> 156 padding and ReconFitterBase.copy_smpl_params on host containers."""
+    import types
+    from vistracker_b200.recon_fit import SMPLParams, copy_smpl_params, smplh_pose
+    hm = np.arange(90, dtype=np.float32) * 0.01
+    p72 = np.random.default_rng(0).standard_normal((4, 72)).astype(np.float32)
+    out = smplh_pose(p72, hm)
+    assert out.shape == (4, 156) and np.array_equal(out[:, :66].numpy(), p72[:, :66]) and np.array_equal(out[:, 66:].numpy(), np.tile(hm, (4, 1)))
+    p156 = np.random.default_rng(1).standard_normal((4, 156)).astype(np.float32)
+    assert np.array_equal(smplh_pose(p156).numpy(), p156)
+    with pytest.raises(ValueError, match="mean hand pose"):
+        smplh_pose(p72)
+    layer = types.SimpleNamespace(device=torch.device("cpu"), th_faces=None)
+    a = SMPLParams(layer, None, torch.from_numpy(p156), torch.zeros(4, 10), torch.zeros(4, 3))
+    b = SMPLParams(layer, None, torch.from_numpy(p156) + 1, torch.ones(4, 10), torch.ones(4, 3))
+    copy_smpl_params(b, a)
+    assert torch.equal(a.pose, b.pose) and torch.equal(a.trans, b.trans) and torch.equal(a.betas[:, :2], b.betas[:, :2])
+    assert float(a.betas[:, 2:].abs().max()) == 0.0                               # the other betas are not copied
+    c = SMPLParams.from_smpl(b)
+    assert torch.equal(c.pose.detach(), b.pose.detach()) and c.global_pose.requires_grad and c.global_pose is not b.global_pose

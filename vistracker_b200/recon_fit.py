@@ -52,6 +52,50 @@ class SMPLParams:
         verts = self.verts if use_cache else self.forward()[0]
         return self.reg(verts), None, None          # only the body-25 set is consumed on this path
 
+    @classmethod
+    def from_smpl(cls, smpl: "SMPLParams") -> "SMPLParams":
+        """``SMPLPyTorchWrapperBatchSplitParams.from_smpl`` (lib_smpl/wrapper_pytorch.py:206-226): fresh leaf parameters holding the values of
+        another container (anything with ``pose [B,156]``, ``betas [B,10]``, ``trans [B,3]``, ``smpl``, ``reg``)."""
+        return cls(smpl.smpl, smpl.reg, smpl.pose.data, smpl.betas.data, smpl.trans.data)
+
+    @classmethod
+    def get_smplh(cls, layer: SMPL_Layer, body25: LandmarkRegressor, poses, betas, trans, hand_mean=None) -> "SMPLParams":
+        """``SMPLHGenerator.get_smplh`` (lib_smpl/smpl_generator.py:85-99): a container from a complete parameter set; 72-d SMPL poses are
+        padded to the 156 SMPL-H values with the GRAB mean hand pose (``Priors.hand_mean`` / ``mean_hand_pose``)."""
+        return cls(layer, body25, smplh_pose(poses, hand_mean), torch.as_tensor(np.asarray(betas), dtype=torch.float32), torch.as_tensor(np.asarray(trans), dtype=torch.float32))
+
+
+SMPLH_POSE_PRAMS_NUM, SMPLH_HANDPOSE_START = 156, 66     # lib_smpl/const.py
+
+
+def smplh_pose(poses, hand_mean=None) -> torch.Tensor:
+    """The pose handling of ``SMPLHGenerator.get_smplh`` (lib_smpl/smpl_generator.py:88-96): [B,156] passes through, [B,72] gets the 90 hand
+    values replaced by ``hand_mean`` (the body part keeps its first 66 values; SMPL's two hand joints are dropped)."""
+    poses = torch.as_tensor(np.asarray(poses.detach().cpu() if torch.is_tensor(poses) else poses), dtype=torch.float32)
+    if poses.shape[1] == SMPLH_POSE_PRAMS_NUM:
+        return poses
+    assert poses.shape[1] == SMPL_POSE_PRAMS_NUM, "using unknown source of smpl poses"
+    if hand_mean is None:
+        raise ValueError("72-d SMPL poses need the GRAB mean hand pose (Priors.hand_mean)")
+    out = torch.zeros(poses.shape[0], SMPLH_POSE_PRAMS_NUM)
+    out[:, :SMPL_POSE_PRAMS_NUM] = poses
+    out[:, SMPLH_HANDPOSE_START:] = torch.as_tensor(np.asarray(hand_mean.detach().cpu() if torch.is_tensor(hand_mean) else hand_mean), dtype=torch.float32).reshape(-1)
+    return out
+
+
+def copy_smpl_params(split_smpl: SMPLParams, smpl: SMPLParams) -> SMPLParams:
+    """``ReconFitterBase.copy_smpl_params`` (recon/recon_fit_base.py:808-816): the optimised global / body / hand pose, the two top betas and
+    the translation written back into ``smpl`` (the other betas are left as they were)."""
+    with torch.no_grad():
+        smpl.global_pose.copy_(split_smpl.global_pose)
+        smpl.body_pose.copy_(split_smpl.body_pose)
+        smpl.hand_pose.copy_(split_smpl.hand_pose)
+        smpl.top_betas.copy_(split_smpl.top_betas)
+        smpl.trans.copy_(split_smpl.trans)
+        smpl.pose = torch.cat([smpl.global_pose, smpl.body_pose, smpl.hand_pose], 1)
+        smpl.betas = torch.cat([smpl.top_betas, smpl.other_betas], 1)
+    return smpl
+
 
 class Priors:
     """get_prior() / HandPrior(type='grab') (lib_smpl/th_smpl_prior.py:25-48, th_hand_prior.py:46-72) loaded ONCE (the reference
