@@ -72,3 +72,27 @@ def test_smplh_pose_padding_and_param_copy():
     assert float(a.betas[:, 2:].abs().max()) == 0.0                               # the other betas are not copied
     c = SMPLParams.from_smpl(b)
     assert torch.equal(c.pose.detach(), b.pose.detach()) and c.global_pose.requires_grad and c.global_pose is not b.global_pose
+
+
+def test_sequence_packs_roundtrip(tmp_path):
+    T = 7
+    rng = np.random.default_rng(2)
+    frames = [f"t{i:04d}.000" for i in range(T)]
+    poses, betas, trans = rng.standard_normal((T, 156)).astype(np.float32), rng.standard_normal((T, 10)).astype(np.float32), rng.standard_normal((T, 3)).astype(np.float32)
+    f = vio.pack_smplt(str(tmp_path / "smplt" / "seq_k1.pkl"), frames, "male", torch.from_numpy(poses), betas, trans)
+    d = vio.load_packed(f)
+    assert list(d) == ["poses", "betas", "trans", "obj_angles", "obj_trans", "obj_scales", "gender", "frames"]          # pack_smplt.py:45-63
+    assert np.array_equal(d["poses"], poses) and d["obj_angles"].shape == (T, 3, 3) and d["gender"] == "male" and d["frames"] == frames
+    pca, nt, vis = rng.standard_normal((T, 3, 3)).astype(np.float32), rng.standard_normal((T, 3)).astype(np.float32), rng.random((T, 1)).astype(np.float32)
+    f = vio.pack_recon(str(tmp_path / "recon_x" / "seq_k1.pkl"), frames, "female", "x", pca, nt, vis)
+    import joblib
+    raw = joblib.load(f)
+    assert list(raw) == ["neural_pca", "neural_trans", "recon_exist", "neural_visibility", "recon_name", "frames", "gender"]
+    assert isinstance(raw["neural_pca"], list) and raw["neural_pca"][0].shape == (3, 3) and raw["neural_visibility"][0].shape == (1,)
+    assert np.array(raw["neural_visibility"])[:, 0].shape == (T,)                  # how test_infill_autoreg.py:80 reads it
+    d = vio.load_packed(f)
+    assert np.array_equal(d["neural_pca"], pca) and bool(d["recon_exist"].all())
+    ang = rng.standard_normal((T, 3, 3)).astype(np.float32)
+    f = vio.pack_recon(str(tmp_path / "recon_y" / "seq_k1.pkl"), frames, "male", "y", pca, nt, vis, poses, betas, trans, trans * 2, ang, trans + 1, np.ones(T))
+    d = vio.load_packed(f)
+    assert d["obj_angles"].shape == (T, 3, 3) and np.array_equal(d["root_joints"], trans * 2) and d["obj_scales"].shape == (T,) and "poses" in d

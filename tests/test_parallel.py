@@ -29,7 +29,14 @@ def _worker(rank, world, port, lens, q):
         start = sum(lens[:rank])
         t = torch.arange(start, start + lens[rank], dtype=torch.float32)[:, None] * torch.ones(1, PL.SMPLT_WIDTH) + 0.25 * rank
         full = PL.gather_trajectory(t)
-        q.put((rank, full.shape, float(full[:, 0].sum()), bool((full[1:, 3] >= full[:-1, 3]).all())))
+        # second collective of the path: the per-frame neural predictions [t, 13] that the object smoother / HVOP-Net consume
+        from vistracker_b200.pipeline import pack_neural
+        n = lens[rank]
+        frames = torch.arange(start, start + n, dtype=torch.float32)
+        neural = PL.gather_trajectory(pack_neural(frames[:, None, None] * torch.ones(n, 3, 3), torch.zeros(n, 3), frames / 100))
+        ok13 = tuple(neural.shape) == (sum(lens), 13) and bool(torch.equal(neural[:, 0], torch.arange(sum(lens), dtype=torch.float32))) and \
+            bool(torch.allclose(neural[:, 12], torch.arange(sum(lens), dtype=torch.float32) / 100))
+        q.put((rank, full.shape, float(full[:, 0].sum()), bool((full[1:, 3] >= full[:-1, 3]).all()) and ok13))
     finally:
         dist.destroy_process_group()
 

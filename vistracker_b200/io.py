@@ -10,6 +10,8 @@ writes.  Pure host code: one batched device->host copy per call, then the same p
   save_neural_recon   ``k{tid}_densepc.npz`` = {'human': {points, pca_axis, parts, centers, visibility}, 'object': {...}}
                       (recon/recon_fit_base.py:830-844, recon/gen/generator_vis.py:54-55)
   output_folders      ``<outpath>/<seq>/<frame>/<save_name>``                              (recon/recon_fit_base.py:278-294)
+  pack_smplt / pack_recon / load_packed   the per-sequence joblib packs (preprocess/pack_smplt.py:45-63, preprocess/pack_recon.py:118-157)
+                      written from in-memory trajectories instead of re-reading every per-frame file
 """
 from __future__ import annotations
 
@@ -98,3 +100,49 @@ def load_smplt_fits(files: Sequence[str]):
             d = pkl.load(fh)
         P.append(d["pose"]); B.append(d["betas"]); T.append(d["trans"])
     return np.stack(P, 0), np.stack(B, 0), np.stack(T, 0)
+
+
+def pack_smplt(outfile: str, frames: Sequence[str], gender: str, poses, betas, trans) -> str:
+    """The per-sequence pack ``preprocess/pack_smplt.py:45-63`` writes from the per-frame SMPL-T fits -- here straight from the (all-gathered)
+    trajectory: {'poses' (T,156), 'betas', 'trans', dummy 'obj_angles' eye / 'obj_trans' zeros / 'obj_scales' zeros, 'gender', 'frames'}."""
+    import joblib
+    poses, betas, trans = _np(poses), _np(betas), _np(trans)
+    L = poses.shape[0]
+    os.makedirs(os.path.dirname(outfile) or ".", exist_ok=True)
+    joblib.dump({"poses": poses, "betas": betas, "trans": trans, "obj_angles": np.eye(3)[None].repeat(L, 0), "obj_trans": np.zeros((L, 3)),
+                 "obj_scales": np.zeros((L,)), "gender": gender, "frames": list(frames)}, outfile)
+    return outfile
+
+
+def pack_recon(outfile: str, frames: Sequence[str], gender: str, recon_name: str, neural_pca, neural_trans, neural_visibility, poses=None, betas=None,
+               trans=None, root_joints=None, obj_angles=None, obj_trans=None, obj_scales=None) -> str:
+    """The per-sequence pack of ``preprocess/pack_recon.py:29-161`` from in-memory trajectories.  Without the SMPL / object arrays it is the
+    ``-neural_only`` pack (step 4.1 of demo.sh: 'neural_pca' / 'neural_trans' / 'neural_visibility' lists, 'recon_exist', meta); with them
+    the full one ('poses' Tx156|72, 'betas', 'trans', 'root_joints', 'obj_angles' as stored = R^T, 'obj_trans', 'obj_scales').
+    ``neural_trans`` is the object centre relative to the body (``centers[3:]``)."""
+    import joblib
+    T = len(frames)
+    d = {}
+    full = poses is not None
+    if full:
+        d.update({"poses": _np(poses), "betas": _np(betas), "trans": _np(trans), "root_joints": _np(root_joints), "obj_angles": _np(obj_angles),
+                  "obj_trans": _np(obj_trans), "obj_scales": np.asarray(_np(obj_scales)).reshape(T)})
+    d.update({"neural_pca": [a for a in _np(neural_pca).reshape(T, 3, 3)], "neural_trans": [a for a in _np(neural_trans).reshape(T, 3)],
+              "neural_visibility": [a for a in _np(neural_visibility).reshape(T, -1)], "recon_exist": np.ones(T, bool), "recon_name": recon_name,
+              "frames": list(frames), "gender": gender})
+    if not full:                                                                   # key order of the reference's neural-only dict
+        d = {k: d[k] for k in ("neural_pca", "neural_trans", "recon_exist", "neural_visibility", "recon_name", "frames", "gender")}
+    os.makedirs(os.path.dirname(outfile) or ".", exist_ok=True)
+    joblib.dump(d, outfile)
+    return outfile
+
+
+def load_packed(file: str) -> dict:
+    """``joblib.load`` of a pack written by the reference or by pack_smplt / pack_recon, list entries stacked: what ``ReconDataReader`` users,
+    ``ObjrotSmoother.load_inputs_raw`` (smooth_objrot.py:36-69) and ``MotionInfillAutoreg.test`` (test_infill_autoreg.py:60-82) start from."""
+    import joblib
+    d = dict(joblib.load(file))
+    for k in ("neural_pca", "neural_trans", "neural_visibility"):
+        if k in d and isinstance(d[k], list) and len(d[k]):
+            d[k] = np.stack([np.asarray(a) for a in d[k]], 0)
+    return d
