@@ -267,8 +267,11 @@ int vt_chamfer_bwd(const float* x, const int* x_off, const float* y, const int* 
 /* verts[B][V][3] camera-space, faces[F][3] (shared); mode 0: nr.projection with K4[B][4] = (fx, fy, cx, cy) normalised to the ROI
  * (orig_size 1), mode 1: orthographic (x, y in [-1, 1] rasterised directly).  Outputs: faces_ndc[B][2F][9] and face_index[B][S][S]
  * (kept for backward), alpha[B][S][S] and / or depth[B][S][S] (either may be NULL). */
+/* cull_ws: optional workspace of vt_raster_cull_floats(B, F) floats (16-byte aligned) for per-face / per-256-face-chunk bounding boxes; with it
+ * a pixel tile skips the chunks that miss it (same image, the face list is just scanned sparsely).  NULL scans every face per tile. */
+long long vt_raster_cull_floats(int B, int F);
 int vt_raster_fwd(const float* verts, const int* faces, int B, int V, int F, int mode, const float* K4, int image_size,
-                  float* faces_ndc, int* face_index, float* alpha, float* depth, void* stream);
+                  float* faces_ndc, int* face_index, float* alpha, float* depth, float* cull_ws, void* stream);
 /* NMR pseudo-gradient: g_alpha[B][S][S] -> g_verts[B][V][3] (overwritten); g_faces[B][2F][9] is scratch. */
 int vt_raster_bwd(const float* verts, const int* faces, int B, int V, int F, int mode, const float* K4, int image_size,
                   const float* faces_ndc, const int* face_index, const float* alpha, const float* g_alpha, float* g_faces,

@@ -128,10 +128,16 @@ gi = torch.randn_like(img)
 ms = timeit(lambda: torch.autograd.grad(img, vv, gi, retain_graph=True))
 row(f"raster bwd (NMR pseudo-gradient) B={Bm}", ms, Bm, "frames", 2 * F2 * 36 + 2 * 256 * 256 * 4, None, "")
 tri = TriplaneNrRenderer(512, dev)
-sm_faces = model["th_faces"].numpy()
-vs = torch.randn(8, 6890, 3) * torch.tensor([0.25, 0.45, 0.12])
-ms = timeit(lambda: tri.render_3views(sm_faces, vs), iters=5)
-row("triplane occupancy 3 views x 1024^2 (2x SSAA) B=8, 13776x2 faces", ms, 8, "frames", 3 * (27552 * 36 + 512 * 512), None, "")
+from vistracker_b200.synth_smpl import synthetic_body_mesh  # noqa: E402
+_bv, _bf = synthetic_body_mesh()
+vs = torch.from_numpy(_bv)[None].repeat(8, 1, 1) + 0.01 * torch.randn(8, 1, 3)
+ms = timeit(lambda: tri.render_3views(_bf, vs), iters=5)
+row("triplane occupancy 3 views x 1024^2 (2x SSAA) B=8, 13776x2 faces, body-like closed mesh", ms, 8, "frames", 3 * (27552 * 36 + 512 * 512), None,
+    "tiles skip 256-face chunks whose bounding box misses them; VT_RASTER_CULL=0 scans every face per tile")
+os.environ["VT_RASTER_CULL"] = "0"
+ms = timeit(lambda: tri.render_3views(_bf, vs), iters=5)
+os.environ.pop("VT_RASTER_CULL")
+row("triplane occupancy, same, exhaustive face scan per tile (VT_RASTER_CULL=0)", ms, 8, "frames", 3 * (27552 * 36 + 512 * 512), None, "")
 from vistracker_b200.geom import chamfer_distance_ragged, project_so3  # noqa: E402
 xs = [torch.randn(int(n), 3, device=dev) for n in rng.integers(20, 300, 400)]
 ys = [torch.randn(int(n), 3, device=dev) for n in rng.integers(20, 300, 400)]

@@ -50,10 +50,40 @@ __global__ void raster_setup_kernel(const float* __restrict__ verts, const int* 
   }
 }
 
+// Culling records for the tiled forward pass: face_bbox[b][f] = (min x, max x, min y, max y) of a counter-clockwise face (a clockwise one
+// gets an empty box), chunk_bbox[b][c] = the union over faces [256 c, 256 c + 256).  A tile skips every chunk whose box misses it -- mesh
+// faces are spatially coherent in index order, so a tile of a 1024^2 SMPL rendering scans a few chunks instead of all 27 552 faces.
+__global__ void __launch_bounds__(RCHUNK) raster_bbox_kernel(const float* __restrict__ faces_ndc, int nf, int nchunks, float4* __restrict__ face_bbox,
+                                                              float4* __restrict__ chunk_bbox) {
+  __shared__ float4 s_red[RCHUNK / 32];
+  const int b = blockIdx.y, f = blockIdx.x * RCHUNK + threadIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float4 bb = make_float4(INFINITY, -INFINITY, INFINITY, -INFINITY);
+  if (f < nf) {
+    const float* p = faces_ndc + ((size_t)b * nf + f) * 9;
+    const bool front = !((p[7] - p[1]) * (p[3] - p[0]) < (p[4] - p[1]) * (p[6] - p[0]));
+    if (front) bb = make_float4(fminf(p[0], fminf(p[3], p[6])), fmaxf(p[0], fmaxf(p[3], p[6])), fminf(p[1], fminf(p[4], p[7])), fmaxf(p[1], fmaxf(p[4], p[7])));
+    face_bbox[(size_t)b * nf + f] = bb;
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) {
+    bb.x = fminf(bb.x, __shfl_xor_sync(0xffffffffu, bb.x, o)); bb.y = fmaxf(bb.y, __shfl_xor_sync(0xffffffffu, bb.y, o));
+    bb.z = fminf(bb.z, __shfl_xor_sync(0xffffffffu, bb.z, o)); bb.w = fmaxf(bb.w, __shfl_xor_sync(0xffffffffu, bb.w, o));
+  }
+  if (lane == 0) s_red[warp] = bb;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < RCHUNK / 32; ++w) {
+      bb.x = fminf(bb.x, s_red[w].x); bb.y = fmaxf(bb.y, s_red[w].y); bb.z = fminf(bb.z, s_red[w].z); bb.w = fmaxf(bb.w, s_red[w].w);
+    }
+    chunk_bbox[(size_t)b * nchunks + blockIdx.x] = bb;
+  }
+}
+
 __global__ void __launch_bounds__(RT * RT) raster_fwd_kernel(const float* __restrict__ faces_ndc, int nf, int is,
                                                              int* __restrict__ face_index /*[B][is][is] internal (y up)*/,
                                                              float* __restrict__ alpha /*[B][is][is] image rows (flipped) or null*/,
-                                                             float* __restrict__ depth /*[B][is][is] image rows or null*/) {
+                                                             float* __restrict__ depth /*[B][is][is] image rows or null*/,
+                                                             const float4* __restrict__ face_bbox, const float4* __restrict__ chunk_bbox) {
   __shared__ float sf[RCHUNK][9];
   __shared__ int s_id[RCHUNK];
   __shared__ int s_warp_cnt[RT * RT / 32];
@@ -65,12 +95,24 @@ __global__ void __launch_bounds__(RT * RT) raster_fwd_kernel(const float* __rest
   const float ty0 = (2.f * (blockIdx.y * RT) + 1.f - is) / is, ty1 = (2.f * (blockIdx.y * RT + RT - 1) + 1.f - is) / is;
   float depth_min = R_FAR; int best = -1;
   const float* fb = faces_ndc + (size_t)b * nf * 9;
+  const int nchunks = (nf + RCHUNK - 1) / RCHUNK;
   for (int c0 = 0; c0 < nf; c0 += RCHUNK) {
+    if (chunk_bbox) {                                  // uniform over the CTA: no barrier has been entered in this iteration yet
+      const float4 cb = __ldg(chunk_bbox + (size_t)b * nchunks + c0 / RCHUNK);
+      if (!(cb.y >= tx0 && cb.x <= tx1 && cb.w >= ty0 && cb.z <= ty1)) continue;
+    }
     // ---- cull: keep counter-clockwise faces whose bounding box touches the tile, preserving face order
     const int f = c0 + tid;
     float p[9];
     bool keep = false;
-    if (f < nf) {
+    if (f < nf && face_bbox) {
+      const float4 bb = __ldg(face_bbox + (size_t)b * nf + f);
+      keep = bb.y >= tx0 && bb.x <= tx1 && bb.w >= ty0 && bb.z <= ty1;
+      if (keep) {
+#pragma unroll
+        for (int k = 0; k < 9; ++k) p[k] = fb[(size_t)f * 9 + k];
+      }
+    } else if (f < nf) {
 #pragma unroll
       for (int k = 0; k < 9; ++k) p[k] = fb[(size_t)f * 9 + k];
       const bool front = !((p[7] - p[1]) * (p[3] - p[0]) < (p[4] - p[1]) * (p[6] - p[0]));
@@ -255,8 +297,10 @@ using namespace vt;
 
 extern "C" {
 
+long long vt_raster_cull_floats(int B, int F) { return (B <= 0 || F <= 0) ? 0 : (long long)B * (2 * F + ceil_div(2 * F, RCHUNK)) * 4; }
+
 int vt_raster_fwd(const float* verts, const int* faces, int B, int V, int F, int mode, const float* K4, int image_size,
-                  float* faces_ndc, int* face_index, float* alpha, float* depth, void* stream) {
+                  float* faces_ndc, int* face_index, float* alpha, float* depth, float* cull_ws, void* stream) {
   VT_CHECK_ARG(mode == 0 || mode == 1, "vt_raster_fwd: camera mode %d (0 projection, 1 orthographic look)", mode);
   VT_CHECK_ARG(mode == 1 || K4 != nullptr, "vt_raster_fwd: projection mode needs per-frame intrinsics");
   VT_CHECK_ARG(image_size > 0 && image_size <= 4096, "vt_raster_fwd: image size %d", image_size);
@@ -264,8 +308,18 @@ int vt_raster_fwd(const float* verts, const int* faces, int B, int V, int F, int
   cudaStream_t s = (cudaStream_t)stream;
   raster_setup_kernel<<<ceil_div(B * 2 * F, 256), 256, 0, s>>>(verts, faces, B, V, F, mode, K4, faces_ndc);
   VT_CHECK_LAUNCH("vt_raster_fwd(setup)");
+  float4* face_bbox = nullptr;
+  float4* chunk_bbox = nullptr;
+  if (cull_ws) {
+    VT_CHECK_ARG((reinterpret_cast<size_t>(cull_ws) & 15) == 0, "vt_raster_fwd: cull workspace must be 16-byte aligned");
+    const int nchunks = ceil_div(2 * F, RCHUNK);
+    face_bbox = reinterpret_cast<float4*>(cull_ws);
+    chunk_bbox = face_bbox + (size_t)B * 2 * F;
+    raster_bbox_kernel<<<dim3(nchunks, B), RCHUNK, 0, s>>>(faces_ndc, 2 * F, nchunks, face_bbox, chunk_bbox);
+    VT_CHECK_LAUNCH("vt_raster_fwd(bbox)");
+  }
   dim3 grid(ceil_div(image_size, RT), ceil_div(image_size, RT), B);
-  raster_fwd_kernel<<<grid, RT * RT, 0, s>>>(faces_ndc, 2 * F, image_size, face_index, alpha, depth);
+  raster_fwd_kernel<<<grid, RT * RT, 0, s>>>(faces_ndc, 2 * F, image_size, face_index, alpha, depth, face_bbox, chunk_bbox);
   VT_CHECK_LAUNCH("vt_raster_fwd");
   return 0;
 }

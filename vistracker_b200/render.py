@@ -15,6 +15,14 @@ from . import _lib
 P, S = _lib.ptr, _lib.stream_ptr
 
 
+def _cull_ws(B: int, F: int, device):
+    """Workspace for the per-face / per-chunk bounding boxes of vt_raster_fwd (``VT_RASTER_CULL=0``: every tile scans every face)."""
+    import os
+    if os.environ.get("VT_RASTER_CULL", "1") == "0":
+        return None
+    return torch.empty(_lib.load().vt_raster_cull_floats(B, F), device=device, dtype=torch.float32)
+
+
 class _SilFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, r: "SilhouetteRenderer", verts):
@@ -24,8 +32,9 @@ class _SilFn(torch.autograd.Function):
         faces_ndc = torch.empty(B, 2 * F, 9, device=dev)
         fidx = torch.empty(B, isz, isz, dtype=torch.int32, device=dev)
         alpha = torch.empty(B, isz, isz, device=dev)
+        cull = _cull_ws(B, F, dev)
         with torch.cuda.device(dev):
-            _lib.call("vt_raster_fwd", P(v), P(r.faces), B, V, F, r.mode, P(r.K4), isz, P(faces_ndc), P(fidx), P(alpha), None, S())
+            _lib.call("vt_raster_fwd", P(v), P(r.faces), B, V, F, r.mode, P(r.K4), isz, P(faces_ndc), P(fidx), P(alpha), None, P(cull), S())
         ctx.r = r
         ctx.save_for_backward(v, faces_ndc, fidx, alpha)
         return alpha
@@ -66,9 +75,10 @@ class SilhouetteRenderer:
         faces_ndc = torch.empty(B, 2 * F, 9, device=v.device)
         fidx = torch.empty(B, self.image_size, self.image_size, dtype=torch.int32, device=v.device)
         depth = torch.empty(B, self.image_size, self.image_size, device=v.device)
+        cull = _cull_ws(B, F, v.device)
         with torch.cuda.device(v.device):
             _lib.call("vt_raster_fwd", P(v), P(self.faces), B, V, F, self.mode, P(self.K4), self.image_size, P(faces_ndc), P(fidx), None,
-                      P(depth), S())
+                      P(depth), P(cull), S())
         return depth
 
 

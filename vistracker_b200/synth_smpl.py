@@ -55,3 +55,28 @@ def synthetic_motion(frames: int, seed: int = 5, sigma: float = 0.02):
     betas = np.tile((rng.standard_normal(NUM_BETAS) * 0.5).astype(np.float32), (frames, 1))
     trans = np.array([0.0, 0.0, 2.2], np.float32) + np.cumsum(rng.standard_normal((frames, 3)) * 0.01, 0).astype(np.float32)
     return torch.from_numpy(pose), torch.from_numpy(betas), torch.from_numpy(trans.astype(np.float32))
+
+
+def synthetic_body_mesh(rings: int = 84, segments: int = 82, radii=(0.28, 0.85, 0.14)):
+    """A closed, consistently oriented genus-0 surface with SMPL's vertex and face counts (rings * segments + 2 = 6890 vertices,
+    2 * rings * segments = 13 776 faces): a latitude / longitude ellipsoid of body-like extent, vertices ordered ring by ring -- small,
+    spatially coherent triangles like the real template's (``synthetic_smplh`` draws its faces at random: fine for skinning parity,
+    meaningless for a rasteriser).  Returns (verts [V,3] float32, faces [F,3] int64)."""
+    th = np.pi * (np.arange(rings) + 1) / (rings + 1)                       # polar angle of each ring, poles excluded
+    ph = 2 * np.pi * np.arange(segments) / segments
+    ring = np.stack([np.sin(th)[:, None] * np.cos(ph)[None], np.cos(th)[:, None] * np.ones_like(ph)[None], np.sin(th)[:, None] * np.sin(ph)[None]], -1)
+    verts = np.concatenate([[[0.0, 1.0, 0.0]], ring.reshape(-1, 3), [[0.0, -1.0, 0.0]]], 0) * np.asarray(radii)
+    vid = lambda r, s: 1 + r * segments + (s % segments)
+    faces = []
+    south = 1 + rings * segments
+    for s in range(segments):
+        faces.append((0, vid(0, s + 1), vid(0, s)))
+        faces.append((south, vid(rings - 1, s), vid(rings - 1, s + 1)))
+    for r in range(rings - 1):
+        for s in range(segments):
+            a, b, c, d = vid(r, s), vid(r, s + 1), vid(r + 1, s), vid(r + 1, s + 1)
+            faces.append((a, b, c))
+            faces.append((b, d, c))
+    faces = np.asarray(faces, np.int64)
+    assert verts.shape[0] == rings * segments + 2 and faces.shape[0] == 2 * rings * segments
+    return verts.astype(np.float32), faces
