@@ -354,6 +354,22 @@ int vt_infill_pack_clip(const float* rot6d_smpl, const float* trans_smpl, const 
 /* rot6d_out[start + t] = pred[t] for t in [t0, T) (test_infill_autoreg.py:110 and 160). */
 int vt_infill_commit_clip(const float* pred, int L, int start, int t0, int T, float* rot6d_out, void* stream);
 
+/* ---- Test-time frame preparation: data/testdata_triplane.py:42-74, data/train_data.py:143-162,
+ * data/base_data.py:139-171, 204-265.  uint8 frames already decoded into device memory. ---- */
+
+/* BaseDataset.masks2bbox + center_from_masks: bbox[B][4] = (xmin, ymin, xmax, ymax) (max exclusive) of the pixels where the uint8 sum of
+ * person[B][H][W] and obj[B][H][W] (wrapping, as numpy's +=) exceeds thres (127); center[B][2] = (min + max) // 2 as floats (may be NULL).
+ * A frame without foreground keeps the reference's sentinels (50000, 50000, -100, -100). */
+int vt_mask_bbox(const unsigned char* person, const unsigned char* obj, int B, int H, int W, int thres, int* bbox, float* center, void* stream);
+
+/* prepare_image_crop + compose_images (+ the triplane channels of TestDataTriplane.get_item): rgb[B][H][W][3], person / obj[B][H][W],
+ * triplane[B][S][S][3] or NULL (uint8, already in (right, back, top) order) -> images[B][channels][S][S] float32 in [0, 1]: channels 0-2 RGB
+ * zeroed where neither mask exceeds 0.5, 3 person, 4 object, 5-7 triplane.  crop_size^2 pixels around crop_center[B][2] (zero padded,
+ * base_data.py:204-232) are resized to S = net_size with OpenCV's 8-bit INTER_LINEAR arithmetic; resize_tab[3][S] (host-built, see
+ * vistracker_b200/frameio.py) = source index, 11-bit weight of it, 11-bit weight of its right / lower neighbour. */
+int vt_prepare_image_crop(const unsigned char* rgb, const unsigned char* person, const unsigned char* obj, const unsigned char* triplane, int B, int H, int W,
+                          const float* crop_center, int crop_size, int net_size, const int* resize_tab, float* images, int channels, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -17,6 +17,8 @@ seeded synthetic checkpoint of ``vistracker_b200.synth`` and stores inputs-by-se
 * ``eval_chamfer.npz``      -- recon/eval/chamfer_distance.py (sklearn kd-tree) on three cloud pairs, all three directions
 * ``infill_small.npz``      -- (``--only infill``) ConditionalMInfiller forward on two batches and CondMotionInfillAutoreg.test (the
   reference's own autoregressive clip loop, file IO redirected to a temporary folder) on a 400-frame synthetic sequence.
+* ``frameio_small.npz``     -- (``--only frameio``) BehaveDataset.prepare_image_crop / BaseDataset.crop / compose_images on three synthetic
+  frames (centred, running past the right/bottom border, past the top/left one); cv2.resize / findContours injected (OpenCV absent).
 * ``smooth_small.npz``      -- (``--only smooth``) SmoothNetSMPL / SmoothNet through SMPLTSmoother / ObjrotSmoother pre- and
                                post-processing on a 90-frame synthetic trajectory, window 64, + the rotation conversions
 """
@@ -499,6 +501,35 @@ def infill_goldens(out_dir: str):
     np.savez_compressed(os.path.join(out_dir, "infill_small.npz"), **out)
     print("infill_small.npz:", {k: getattr(v, "shape", v) for k, v in out.items() if k != "opt_json"}, missing)
 
+def frameio_goldens(out_dir: str):
+    """Test-time frame preparation: the reference's BehaveDataset.prepare_image_crop / BaseDataset.crop /
+    compose_images (data/train_data.py:143-162, data/base_data.py:204-265), called unbound on a shim.  OpenCV is not installed: ``resize``
+    (cv2.resize) and ``center_from_masks`` (cv2.findContours) are injected from oracle/frameio_ref.py -- those two stay unpinned; the crop
+    arithmetic, the order of operations, the /255 in float64, the masking and the channel layout are the reference's -> frameio_small.npz."""
+    _stub("cv2", INTER_LINEAR=1, setNumThreads=lambda n: None)
+    pkg = _stub("data"); pkg.__path__ = [os.path.join(os.getcwd(), "data")]       # data/__init__.py pulls in trimesh / igl; load the two files only
+    from data.base_data import BaseDataset                                            # reference
+    from data.train_data import BehaveDataset                                         # reference
+    from oracle import frameio_ref as FR
+    from vistracker_b200.synth import synthetic_camera_frame
+
+    H, W, CROP, NET = 180, 240, 150, 64                                                # 150 / 64 = 1200 / 512
+    out = {"H": H, "W": W, "crop": CROP, "net": NET}
+    centers = {"mid": None, "right_bottom": (205.0, 150.0), "top_left": (30.0, 25.0)}
+    for i, (tag, ctr) in enumerate(centers.items()):
+        rgb, person, obj = synthetic_camera_frame(H, W, seed=30 + i, center=ctr)
+        shim = types.SimpleNamespace(CROP_SIZE=np.array([CROP, CROP]), img_size=(NET, NET), dtype=np.float32,
+                                     load_masks=lambda f, flip: (person, obj), load_rgb=lambda f, flip: rgb,
+                                     center_from_masks=lambda o, p, f: FR.center_from_masks(o, p),
+                                     resize=lambda img, size, mode=1: FR.resize_linear_u8(img, size))
+        shim.crop = types.MethodType(BaseDataset.crop, shim)
+        shim.compose_images = types.MethodType(BaseDataset.compose_images, shim)
+        images, center = BehaveDataset.prepare_image_crop(shim, "frame.color.jpg", False)
+        out[f"{tag}_images"], out[f"{tag}_center"] = images, np.asarray(center)
+        out[f"{tag}_crop_rgb"] = BaseDataset.crop(shim, rgb, center, shim.CROP_SIZE)
+    np.savez_compressed(os.path.join(out_dir, "frameio_small.npz"), **out)
+    print("frameio_small.npz:", {k: getattr(v, "shape", v) for k, v in out.items()})
+
 
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
@@ -521,5 +552,7 @@ if __name__ == "__main__":
         eval_goldens(HERE)
     if a.only == "smooth":                  # stubs `behave` / `yacs`: run on its own
         smooth_goldens(HERE)
+    if a.only == "frameio":                 # stubs `cv2` and the `data` package: run on its own
+        frameio_goldens(HERE)
     if a.only == "infill":                  # stubs `behave` / `trainer`: run on its own
         infill_goldens(HERE)

@@ -84,6 +84,8 @@ SIGNATURES.update({
     "vt_infill_mlp": (_i, [_p, _i, _i, _i, _p, _p, _p, _i, _p]),
     "vt_infill_pack_clip": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _p, _p, _p]),
     "vt_infill_commit_clip": (_i, [_p, _i, _i, _i, _i, _p, _p]),
+    "vt_mask_bbox": (_i, [_p, _p, _i, _i, _i, _i, _p, _p, _p]),
+    "vt_prepare_image_crop": (_i, [_p, _p, _p, _p, _i, _i, _i, _p, _i, _i, _p, _p, _i, _p]),
     "vt_raster_cull_floats": (_ll, [_i, _i]),
     "vt_raster_fwd": (_i, [_p, _p, _i, _i, _i, _i, _p, _i, _p, _p, _p, _p, _p, _p]),
     "vt_raster_bwd": (_i, [_p, _p, _i, _i, _i, _i, _p, _i, _p, _p, _p, _p, _p, _p, _p]),

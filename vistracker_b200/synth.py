@@ -196,3 +196,18 @@ def synthetic_infill_sequence(L: int, seed: int = 0, occluded=((70, 130), (215, 
         rot6d_obj[a:b] += 0.5 * rng.standard_normal((b - a, 6))
     f = lambda x: np.ascontiguousarray(x, dtype=np.float32)
     return f(rot6d_smpl), f(trans_smpl), f(rot6d_obj), f(trans_obj), f(occ)
+
+
+def synthetic_camera_frame(H: int = 1536, W: int = 2048, seed: int = 0, center=None, extent=(0.22, 0.42)):
+    """A seeded stand-in for one Kinect frame: rgb [H,W,3] uint8 noise + gradients, a person mask (ellipse) and an object mask (rotated box)
+    as uint8 0/255 with soft (anti-aliased, jpeg-like) borders, placed around ``center`` (x, y) -- default image centre."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    yy, xx = np.mgrid[0:H, 0:W].astype(np.float32)
+    cx, cy = (W / 2, H / 2) if center is None else center
+    rgb = (rng.integers(0, 256, (H, W, 3)).astype(np.float32) * 0.5 + np.stack([xx / W, yy / H, (xx + yy) / (W + H)], -1) * 127).astype(np.uint8)
+    a, b = extent[0] * H * 0.5, extent[1] * H * 0.5
+    d = ((xx - cx) / a) ** 2 + ((yy - cy) / b) ** 2
+    person = np.clip((1.05 - d) * 12, 0, 1)
+    u, v = (xx - cx - 0.9 * a) * 0.8 + (yy - cy) * 0.6, -(xx - cx - 0.9 * a) * 0.6 + (yy - cy) * 0.8
+    obj = np.clip((1.0 - np.maximum(np.abs(u) / (0.7 * a), np.abs(v) / (0.5 * a))) * 10, 0, 1)
+    return rgb, (person * 255).astype(np.uint8), (obj * 255).astype(np.uint8)
