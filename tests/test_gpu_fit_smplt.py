@@ -60,3 +60,17 @@ def test_other_batch_size_matches_oracle_and_early_stop_is_honoured(fitter):
     assert rel_err(out["pose"].cpu(), ref[0]) < TOL and rel_err(out["trans"].cpu(), ref[2]) < TOL
     with pytest.raises(ValueError):
         fitter.fit_batch(pose0[:2], betas0[:2], trans0[:2], kpts[:2])
+
+
+def test_smoothed_refit_schedule_matches_oracle(fitter):
+    """SMPLHFitterSmoothed (preprocess/fit_SMPLH_smoothed.py): no global-pose phase, 30 outer iterations at most, all-pose Adam from step 1."""
+    from vistracker_b200.fit_smplt import SMPLHFitterSmoothed
+    a, reg = load_assets()
+    model, kpts, pose0, betas0, trans0 = synthetic_fit_problem(24, seed=31)
+    sm = SMPLHFitterSmoothed(fitter.smpl, fitter.reg, a)
+    assert sm.get_globalopt_iters() == 0 and sm.get_max_iters() == 30
+    ref = F.fit(model, reg, a, pose0, betas0, trans0, kpts, n_outer=4, iter_for_global=0)
+    out = sm.fit_batch(pose0, betas0, trans0, kpts, max_iter=4, early_stop=False)
+    assert out["steps"] == 40 and rel_err(out["losses"], np.array(ref[3])) < TOL
+    assert rel_err(out["pose"].cpu(), ref[0]) < TOL and rel_err(out["betas"].cpu(), ref[1]) < TOL and rel_err(out["trans"].cpu(), ref[2]) < TOL
+    assert float((out["pose"][:, 3:66].cpu() - pose0[:, 3:66]).abs().max()) > 0          # the body pose moves from the first step

@@ -57,6 +57,8 @@ class SMPLHFitter30fps:
     def get_max_iters():
         return 100
 
+    LR_GLOBAL, LR_ALL = 0.01, 0.001          # init_globalpose_optimizer / init_allpose_optimizer (fit_SMPLH_kpts.py:182-190)
+
     # ---- buffers + the launch sequence ----------------------------------------------------------------------------------
     def _alloc(self, B: int, max_hist: int):
         m, dev = self.smpl, self.device
@@ -142,7 +144,7 @@ class SMPLHFitter30fps:
         with torch.cuda.device(self.device):
             self._load(pose0, betas0, trans0, kpts, n_max)
             b = self.buf
-            self._set_schedule(0, 0, 0.01)                      # init_globalpose_optimizer: Adam lr 0.01
+            self._set_schedule(0, 0, self.LR_GLOBAL)            # init_globalpose_optimizer
             if use_graph and self._graph is None:
                 # capture once per batch size; buffers are static so the graph stays valid across batches
                 keep = {k: b[k].clone() for k in ("pose", "betas", "trans", "m", "v", "ctrl", "hist")}
@@ -162,7 +164,7 @@ class SMPLHFitter30fps:
             for it in range(max_iter):
                 if it == iter_for_global:                       # init_allpose_optimizer: a NEW Adam, lr 0.001
                     b["m"].zero_(); b["v"].zero_(); b["ctrl"][10:11].zero_()
-                self._set_schedule(it // 3, 0 if it < iter_for_global else 1, 0.01 if it < iter_for_global else 0.001)
+                self._set_schedule(it // 3, 0 if it < iter_for_global else 1, self.LR_GLOBAL if it < iter_for_global else self.LR_ALL)
                 for _ in range(steps_per_iter):
                     run()
                     step += 1
@@ -180,3 +182,20 @@ class SMPLHFitter30fps:
             hist = b["hist"][:step].cpu()
         return {"pose": b["pose"].clone(), "betas": b["betas"].clone(), "trans": b["trans"].clone(), "losses": hist[:, 6].numpy(),
                 "terms": hist[:, :6].numpy(), "steps": step, "stopped_early": stopped, "snapshots": snaps}
+
+
+class SMPLHFitterSmoothed(SMPLHFitter30fps):
+    """``SMPLHFitterSmoothed`` (preprocess/fit_SMPLH_smoothed.py:25-118), the re-fit of demo.sh step 2 that starts from the SmoothNet output:
+    same objective, no global-pose phase (``get_globalopt_iters`` 0), at most 30 outer iterations, all-pose Adam lr 0.001 (the 0.005
+    global-pose optimiser is constructed by the reference but replaced before its first step).  ``init_smpl`` / ``load_kpts`` (joblib packs)
+    stay with the caller: pass the smoothed trajectory and the key points to ``fit_batch``."""
+
+    LR_GLOBAL, LR_ALL = 0.005, 0.001
+
+    @staticmethod
+    def get_globalopt_iters():
+        return 0
+
+    @staticmethod
+    def get_max_iters():
+        return 30
