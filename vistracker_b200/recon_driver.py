@@ -1,0 +1,129 @@
+"""The per-batch body of ``ReconFitterTriplane.fit_recon`` (recon/recon_fit_triplane.py:47-111) on in-memory tensors: neural reconstruction in
+mini-batches, filter of the whole batch, SMPL refinement, object initialisation, joint optimisation.  Everything file-shaped (data loader,
+``get_smpl_init`` / ``load_old_obj_recon`` pickles, key-point json, ``save_outputs``) is an argument or a return value, so the reference's
+``fit_recon`` loop -- or a rank of ``parallel.rank_frames`` -- calls one function per 96-frame batch and writes the results with
+``vistracker_b200.io``.
+"""
+from __future__ import annotations
+
+from typing import Callable, Dict, Optional
+
+import torch
+
+from .generator import GeneratorTriplaneVis
+from .geom import init_object_orientation
+from .recon_fit import SMPL_POSE_PRAMS_NUM, ReconFitterTriVisFull, SMPLParams
+
+MINI_BATCH = 16            # recon_fit_behave.py:124 (8 on the 'volta' partition)
+
+
+def combine_mini_batches(pcs, samples_count: int) -> Dict[str, Dict[str, torch.Tensor]]:
+    """recon_fit_behave.py:152-183: points / parts truncated to the smallest per-mini-batch sample count, everything else concatenated."""
+    out = {}
+    for target in ("human", "object"):
+        out[target] = {}
+        for key in pcs[0][target]:
+            parts = [(pc[target][key][:, :samples_count] if key in ("points", "parts") else pc[target][key]) for pc in pcs]
+            out[target][key] = torch.cat(parts, 0)
+    return out
+
+
+def generate_all(generator: GeneratorTriplaneVis, data: Dict[str, torch.Tensor], num_points: int = 4000, mini_batch_size: int = MINI_BATCH,
+                 on_mini_batch: Optional[Callable] = None):
+    """``ReconFitterBehave.generate_all`` (recon_fit_behave.py:121-150): ``generate_pclouds_batch`` per mini-batch of 16 frames with 10
+    projection steps, then ``combine_mini_batches``.  ``on_mini_batch(start, end, pc_generated)`` is where the reference writes
+    ``k{tid}_densepc.npz`` (``save_neural_recon``)."""
+    B = data["images"].shape[0]
+    pcs, samples = [], 100000
+    for s in range(0, B, mini_batch_size):
+        mini = {k: v[s:s + mini_batch_size] for k, v in data.items()}
+        pc = generator.generate_pclouds_batch(mini, num_points=num_points, num_steps=10, mute=True)
+        if on_mini_batch is not None:
+            on_mini_batch(s, min(s + mini_batch_size, B), pc)
+        samples = min(samples, pc["human"]["points"].shape[1], pc["object"]["points"].shape[1])
+        pcs.append(pc)
+    return combine_mini_batches(pcs, samples)
+
+
+def filter_batch(net, images: torch.Tensor, chunk: int = MINI_BATCH) -> None:
+    """``generator.filter(data)`` on the whole optimisation batch (recon_fit_triplane.py:58-60).  The encoders run in chunks to bound the
+    activation memory; the cached maps end up covering all B frames (image / tmpx maps concatenated along the batch, the three triplane
+    views kept view-major as ``filter`` lays them out)."""
+    B = images.shape[0]
+    if B <= chunk:
+        net.filter(images.to(net.device))
+        return
+    maps = []
+    for s in range(0, B, chunk):
+        net.filter(images[s:s + chunk].to(net.device))
+        maps.append((net._maps, min(chunk, B - s)))
+    cat_view = lambda i: torch.cat([torch.cat([m[i][v * n:(v + 1) * n] for m, n in maps]) for v in range(3)])
+    net._maps = (torch.cat([m[0] for m, _ in maps]), torch.cat([m[1] for m, _ in maps]), cat_view(2), cat_view(3))
+
+
+def scale_body_kpts(kpts: torch.Tensor, crop_center: torch.Tensor, crop_size: float = 1200.0, net_in_size: float = 512.0,
+                    resize_scale: Optional[torch.Tensor] = None, crop_scale: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """``scale_body_kpts`` (recon_fit_base.py:397-409): OpenPose key points [B,25,3] from original-image pixels to network-input pixels."""
+    B = kpts.shape[0]
+    one = torch.ones(B, device=kpts.device)
+    rs, cs = (one if resize_scale is None else resize_scale), (one if crop_scale is None else crop_scale)
+    pxy = kpts[:, :, :2] * rs[:, None, None]
+    size = cs * crop_size
+    pxy = pxy - crop_center[:, None, :] + size[:, None, None] / 2
+    pxy = pxy * net_in_size / size[:, None, None]
+    return torch.cat([pxy, kpts[:, :, 2:3]], -1)
+
+
+def fit_recon_batch(fitter: ReconFitterTriVisFull, generator: GeneratorTriplaneVis, data: Dict[str, torch.Tensor], smpl_init: Callable,
+                    body_kpts: torch.Tensor, obj_points: torch.Tensor, pca_init: Optional[torch.Tensor] = None,
+                    obj_rot_init: Optional[torch.Tensor] = None, silhouette=None, occ_ratios: Optional[torch.Tensor] = None,
+                    neural_only: bool = False, on_mini_batch: Optional[Callable] = None, noise_fn=None, mini_batch_size: int = MINI_BATCH, **loop_kw):
+    """One batch of ``fit_recon``.
+
+    data: {'images' [B,8,512,512], 'crop_center' [B,2], 'body_center' [B,3]} (device or host tensors).
+    smpl_init(human_t [B,3]) -> SMPLParams: ``get_smpl_init`` (recon_fit_trivis_full.py:62-77) -- the smoothed SMPL-T parameters of the frames
+    (the tri-vis fitter keeps their own translation and ignores ``human_t`` = the pre-fit body centre; it is passed for the variants that do not).
+    body_kpts [B,25,3]: OpenPose key points already in network-input pixels (``scale_body_kpts``).
+    obj_points [n,3]: surface samples of the object template (``compute_pca_init``); pca_init [3,3]: its PCA axes, used when the
+    rotation comes from the network (``-or neural``); obj_rot_init [B,3,3]: the rotation loaded from an earlier stage (HVOP-Net) instead.
+    silhouette: a ``render.SilLossROI`` for the batch, occ_ratios [B]: visibility used by the occlusion-aware terms (defaults to the
+    network's prediction, recon_fit_triplane.py:68).
+    Returns {'pc_generated', 'smpl', 'obj_R' (projected, no noise), 'obj_t', 'obj_s', 'hist_smpl', 'hist_obj'} -- or only 'pc_generated' for
+    ``neural_only`` (demo.sh step 4)."""
+    dev = fitter.model.device
+    pc = generate_all(generator, data, on_mini_batch=on_mini_batch, mini_batch_size=mini_batch_size)
+    if neural_only:
+        return {"pc_generated": pc}
+    if silhouette is None:
+        raise ValueError("the 'sil' phase needs a render.SilLossROI for the batch")
+    with torch.no_grad():
+        filter_batch(fitter.model, data["images"], chunk=mini_batch_size)
+    B = data["images"].shape[0]
+    human_t = data["body_center"].to(dev).float()                                   # ReconFitterTriplane.get_smpl_translation (recon_fit_triplane.py:210-220):
+                                                                                    # the pre-fit body centre, not the network's prediction
+    smpl = smpl_init(human_t)
+    query_dict = {"crop_center": data["crop_center"].to(dev), "body_center": data["body_center"].to(dev)}
+    dd = {"part_labels": fitter.part_labels.to(dev)[None].repeat(B, 1) if fitter.part_labels.dim() == 1 else fitter.part_labels.to(dev),
+          "query_dict": query_dict, "body_kpts": body_kpts.float().to(dev),
+          "pose_init": smpl.pose[:, 3:SMPL_POSE_PRAMS_NUM].detach().clone().to(dev)}
+    smpl, hist_smpl = _as_pair(fitter.optimize_smpl(smpl, dd, iter_for_kpts=1, iter_for_pose=1, iter_for_betas=1, **loop_kw))
+    # init_obj_fit_data (recon_fit_trivis_full.py:79-104): predicted centre relative to the optimised body centre, rotation from the PCA axes
+    obj_t = (pc["object"]["centers"][:, 3:].to(dev) + human_t.to(dev)).detach().clone().requires_grad_(True)
+    if obj_rot_init is None:
+        if pca_init is None:
+            raise ValueError("either obj_rot_init or pca_init (the template's PCA axes) is needed")
+        obj_R = init_object_orientation(pc["object"]["pca_axis"].to(dev), pca_init.to(dev), noise=None if noise_fn is None else noise_fn())
+    else:
+        obj_R = obj_rot_init.to(dev).float()
+    obj_R = obj_R.detach().clone().requires_grad_(True)
+    obj_s = torch.ones(B, device=dev)
+    vis = pc["object"]["visibility"].to(dev).reshape(B) if occ_ratios is None else occ_ratios.to(dev)
+    dd.update({"obj_R": obj_R, "obj_t": obj_t, "obj_s": obj_s, "objects": obj_points.to(dev)[None].repeat(B, 1, 1), "occ_ratios": vis,
+               "silhouette": silhouette, "trans_init": obj_t.detach().clone()})
+    smpl, obj_R, obj_t, hist_obj = fitter.optimize_smpl_object(smpl, dd, noise_fn=noise_fn, **loop_kw)
+    return {"pc_generated": pc, "smpl": smpl, "obj_R": fitter.final_rotation(obj_R), "obj_t": obj_t.detach(), "obj_s": obj_s, "hist_smpl": hist_smpl,
+            "hist_obj": hist_obj}
+
+
+def _as_pair(res):
+    return res if isinstance(res, tuple) and len(res) == 2 else (res, None)
