@@ -19,6 +19,7 @@ seeded synthetic checkpoint of ``vistracker_b200.synth`` and stores inputs-by-se
   reference's own autoregressive clip loop, file IO redirected to a temporary folder) on a 400-frame synthetic sequence.
 * ``frameio_small.npz``     -- (``--only frameio``) BehaveDataset.prepare_image_crop / BaseDataset.crop / compose_images on three synthetic
   frames (centred, running past the right/bottom border, past the top/left one); cv2.resize / findContours injected (OpenCV absent).
+* ``interp_small.npz``      -- (``--only interp``) BaseInterpolator.compute_missing_inds / interp_slerp / interp_lerp (SLERP baseline).
 * ``smooth_small.npz``      -- (``--only smooth``) SmoothNetSMPL / SmoothNet through SMPLTSmoother / ObjrotSmoother pre- and
                                post-processing on a 90-frame synthetic trajectory, window 64, + the rotation conversions
 """
@@ -530,6 +531,31 @@ def frameio_goldens(out_dir: str):
     np.savez_compressed(os.path.join(out_dir, "frameio_small.npz"), **out)
     print("frameio_small.npz:", {k: getattr(v, "shape", v) for k, v in out.items()})
 
+def interp_goldens(out_dir: str):
+    """SLERP / LERP baseline (interp/interpolate_recon.py): BaseInterpolator's static methods and the quaternion pipeline of interp_seq /
+    save_output on a synthetic sequence with three occluded spans (one of them crossing the antipodal hemisphere) -> interp_small.npz."""
+    from scipy.spatial.transform import Rotation
+    _stub("behave", SCRATCH_PATH="/tmp", GTPACK_PATH="/tmp")
+    from interp.interpolate_recon import BaseInterpolator                            # reference
+    from vistracker_b200.synth import synthetic_infill_sequence
+    L = 220
+    _, _, _, trans_obj, occ = synthetic_infill_sequence(L, seed=4, occluded=((20, 45), (90, 140), (170, 181)))
+    rng = np.random.default_rng(6)
+    t = np.arange(L)[:, None] / 25.0
+    rv = np.array([[0.5, 2.6, -0.4]]) + 0.9 * np.sin(t * np.array([[0.8, 0.5, 1.1]])) + 0.02 * rng.standard_normal((L, 3))     # angles near pi: sign flips of q
+    R = Rotation.from_rotvec(rv).as_matrix()
+    obj_angles = R.transpose(0, 2, 1).copy()
+    mask = (occ < 0.3).astype(float)
+    end_inds, start_inds = BaseInterpolator.compute_missing_inds(mask)
+    rot_q = Rotation.from_matrix(obj_angles.transpose(0, 2, 1)).as_quat()
+    frames = [f"t{i:04d}.000" for i in range(L)]
+    q = BaseInterpolator.interp_slerp(end_inds, frames, rot_q, start_inds, mute=True)
+    tr = BaseInterpolator.interp_lerp(end_inds, frames, trans_obj.astype(np.float64), start_inds, mute=True)
+    out = {"obj_angles_in": obj_angles, "occ": occ, "trans_in": trans_obj, "end_inds": end_inds, "start_inds": start_inds, "quat_out": q,
+           "obj_angles_out": Rotation.from_quat(q).as_matrix().transpose(0, 2, 1), "trans_out": tr}
+    np.savez_compressed(os.path.join(out_dir, "interp_small.npz"), **out)
+    print("interp_small.npz:", {k: getattr(v, "shape", v) for k, v in out.items()}, "spans", list(zip(start_inds, end_inds)))
+
 
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
@@ -554,5 +580,7 @@ if __name__ == "__main__":
         smooth_goldens(HERE)
     if a.only == "frameio":                 # stubs `cv2` and the `data` package: run on its own
         frameio_goldens(HERE)
+    if a.only == "interp":                  # stubs `behave`: run on its own
+        interp_goldens(HERE)
     if a.only == "infill":                  # stubs `behave` / `trainer`: run on its own
         infill_goldens(HERE)
