@@ -96,3 +96,15 @@ def test_sequence_packs_roundtrip(tmp_path):
     f = vio.pack_recon(str(tmp_path / "recon_y" / "seq_k1.pkl"), frames, "male", "y", pca, nt, vis, poses, betas, trans, trans * 2, ang, trans + 1, np.ones(T))
     d = vio.load_packed(f)
     assert d["obj_angles"].shape == (T, 3, 3) and np.array_equal(d["root_joints"], trans * 2) and d["obj_scales"].shape == (T,) and "poses" in d
+
+
+def test_triplane_png_roundtrip(tmp_path):
+    rng = np.random.default_rng(3)
+    masks = torch.from_numpy((rng.random((2, 3, 32, 32)) > 0.6).astype(np.uint8))
+    files = [str(tmp_path / f"t{i:04d}.000" / "k1.smooth_triplane.png") for i in range(2)]
+    assert vio.save_triplane_png(files, masks) == files
+    back = vio.load_triplane_png(files[1])
+    assert back.shape == (32, 32, 3) and back.dtype == np.uint8 and set(np.unique(back)) <= {0, 255}
+    assert np.array_equal(back.transpose(2, 0, 1) // 255, masks[1].numpy())           # channel 0 = right, 1 = back, 2 = top
+    with pytest.raises(ValueError, match="expected masks"):
+        vio.save_triplane_png(files, masks[:, :2])

@@ -146,3 +146,24 @@ def load_packed(file: str) -> dict:
         if k in d and isinstance(d[k], list) and len(d[k]):
             d[k] = np.stack([np.asarray(a) for a in d[k]], 0)
     return d
+
+
+def save_triplane_png(files: Sequence[str], masks) -> List[str]:
+    """``k{kid}.smooth_triplane.png`` and friends (render/render_triplane_nr.py:84-85): masks [B, 3, S, S] (right, back, top; 0/1 or bool, as
+    ``TriplaneNrRenderer.render_3views`` returns them) -> 8-bit RGB png with R = right, G = back, B = top scaled to 0/255 -- the bytes
+    ``cv2.imwrite(outfile, stack[:, :, ::-1])`` puts on disk."""
+    from PIL import Image
+    m = _np(masks)
+    if m.ndim != 4 or m.shape[1] != 3 or len(files) != m.shape[0]:
+        raise ValueError(f"expected masks [B, 3, S, S] and B file names, got {m.shape} and {len(files)}")
+    rgb = ((m > 0).astype(np.uint8) * 255).transpose(0, 2, 3, 1)
+    for f, img in zip(files, rgb):
+        os.makedirs(os.path.dirname(f) or ".", exist_ok=True)
+        Image.fromarray(np.ascontiguousarray(img), "RGB").save(f)
+    return list(files)
+
+
+def load_triplane_png(file: str) -> np.ndarray:
+    """[S, S, 3] uint8 in (right, back, top) order: ``cv2.imread(file)[:, :, ::-1]`` of data/testdata_triplane.py:79 (before the / 255)."""
+    from PIL import Image
+    return np.asarray(Image.open(file).convert("RGB"))
