@@ -108,3 +108,22 @@ def test_triplane_png_roundtrip(tmp_path):
     assert np.array_equal(back.transpose(2, 0, 1) // 255, masks[1].numpy())           # channel 0 = right, 1 = back, 2 = top
     with pytest.raises(ValueError, match="expected masks"):
         vio.save_triplane_png(files, masks[:, :2])
+
+
+def test_packed_batch_slices_by_frame_name(tmp_path):
+    T = 6
+    rng = np.random.default_rng(5)
+    frames = [f"t{i:04d}.{(i * 33) % 1000:03d}" for i in range(T)]
+    pca, nt, vis = rng.standard_normal((T, 3, 3)), rng.standard_normal((T, 3)), rng.random((T, 1))
+    poses, betas, trans, ang = rng.standard_normal((T, 156)), rng.standard_normal((T, 10)), rng.standard_normal((T, 3)), rng.standard_normal((T, 3, 3))
+    f = vio.pack_recon(str(tmp_path / "recon_z" / "seq_k1.pkl"), frames, "male", "z", pca, nt, vis, poses, betas, trans, trans, ang, trans, np.ones(T))
+    import joblib
+    raw = joblib.load(f)                                                          # lists, as the reference stores the neural entries
+    paths = [f"/data/Date03_Sub03_chairwood_hand/{frames[i]}/k1.color.jpg" for i in (4, 1, 2)]
+    b = vio.packed_batch(raw, paths)
+    assert b["frame_inds"].tolist() == [4, 1, 2] and np.array_equal(b["poses"], poses[[4, 1, 2]]) and np.array_equal(b["obj_angles"], ang[[4, 1, 2]])
+    assert np.array_equal(b["neural_pca"], pca[[4, 1, 2]]) and np.allclose(b["occ_ratios"], vis[[4, 1, 2], 0])
+    with pytest.raises(AssertionError, match="kinect id"):
+        vio.packed_batch(raw, [paths[0].replace("k1.", "k2.")])
+    with pytest.raises(ValueError):
+        vio.packed_batch(raw, ["/data/seq/t9999.000/k1.color.jpg"])

@@ -10,6 +10,8 @@ writes.  Pure host code: one batched device->host copy per call, then the same p
   save_neural_recon   ``k{tid}_densepc.npz`` = {'human': {points, pca_axis, parts, centers, visibility}, 'object': {...}}
                       (recon/recon_fit_base.py:830-844, recon/gen/generator_vis.py:54-55)
   output_folders      ``<outpath>/<seq>/<frame>/<save_name>``                              (recon/recon_fit_base.py:278-294)
+  save_triplane_png / load_triplane_png   ``k{kid}.smooth_triplane.png`` with R, G, B = right, back, top (render/render_triplane_nr.py:84-85)
+  packed_batch        the slices of a sequence pack for the frames of one batch (recon/recon_fit_base.py:346-370)
   pack_smplt / pack_recon / load_packed   the per-sequence joblib packs (preprocess/pack_smplt.py:45-63, preprocess/pack_recon.py:118-157)
                       written from in-memory trajectories instead of re-reading every per-frame file
 """
@@ -167,3 +169,25 @@ def load_triplane_png(file: str) -> np.ndarray:
     """[S, S, 3] uint8 in (right, back, top) order: ``cv2.imread(file)[:, :, ::-1]`` of data/testdata_triplane.py:79 (before the / 255)."""
     from PIL import Image
     return np.asarray(Image.open(file).convert("RGB"))
+
+
+def packed_batch(packed: dict, image_paths: Sequence[str], test_kid: int = 1) -> Dict[str, np.ndarray]:
+    """The slices of a sequence pack that belong to the frames of one batch -- ``extract_frame_inds`` + ``load_old_smpl_recon`` /
+    ``load_old_obj_recon`` / ``load_occ_ratios_recon`` (recon/recon_fit_base.py:346-370, recon/recon_fit_triplane.py:146-174): image paths
+    ``<root>/<seq>/<frame time>/k<kid>.color.jpg`` are matched against ``packed['frames']``; every file must come from ``test_kid``.
+    Returns the per-frame entries present in the pack ('poses', 'betas', 'trans', 'obj_angles', 'obj_trans', 'obj_scales', 'neural_pca',
+    'neural_trans', 'occ_ratios' = neural_visibility[:, 0]) stacked over the batch, plus 'frame_inds'."""
+    frames = list(packed["frames"])
+    inds = []
+    for f in image_paths:
+        name = os.path.basename(f)
+        kid = int(name.split(".")[0][1])
+        assert kid == test_kid, f"{f} kinect id={kid}!= test kid={test_kid}"
+        inds.append(frames.index(os.path.basename(os.path.dirname(f))))
+    out = {"frame_inds": np.asarray(inds)}
+    for k in ("poses", "betas", "trans", "obj_angles", "obj_trans", "obj_scales", "neural_pca", "neural_trans"):
+        if k in packed and len(packed[k]):
+            out[k] = np.stack([np.asarray(packed[k][i]) for i in inds], 0)
+    if "neural_visibility" in packed and len(packed["neural_visibility"]):
+        out["occ_ratios"] = np.array([np.asarray(packed["neural_visibility"][i]).reshape(-1)[0] for i in inds])
+    return out
