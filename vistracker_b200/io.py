@@ -48,6 +48,7 @@ def save_smplt_fits(outfiles: Sequence[str], poses, betas, trans, skip=None) -> 
     for i, f in enumerate(outfiles):
         if skip is not None and bool(skip[i]):
             continue
+        os.makedirs(os.path.dirname(f) or ".", exist_ok=True)
         with open(f, "wb") as fh:
             pkl.dump({"pose": poses[i], "betas": betas[i], "trans": trans[i]}, fh)
         n += 1
