@@ -127,3 +127,19 @@ def test_packed_batch_slices_by_frame_name(tmp_path):
         vio.packed_batch(raw, [paths[0].replace("k1.", "k2.")])
     with pytest.raises(ValueError):
         vio.packed_batch(raw, ["/data/seq/t9999.000/k1.color.jpg"])
+
+
+def test_ply_roundtrip_binary_and_ascii(tmp_path):
+    rng = np.random.default_rng(8)
+    v = rng.standard_normal((50, 3)).astype(np.float32)
+    f = rng.integers(0, 50, (80, 3))
+    p = vio.save_ply(str(tmp_path / "seq" / "t0001.000" / "k1.smplfit_smoothed.ply"), torch.from_numpy(v), f)
+    v2, f2 = vio.load_ply(p)
+    assert np.array_equal(v2.astype(np.float32), v) and np.array_equal(f2, f) and f2.dtype == np.int64
+    head = open(p, "rb").read(200).decode("ascii", "ignore")
+    assert head.startswith("ply\nformat binary_little_endian 1.0\nelement vertex 50\n") and "property list uchar int vertex_indices" in head
+    asc = tmp_path / "a.ply"
+    asc.write_text("ply\nformat ascii 1.0\ncomment made by hand\nelement vertex 3\nproperty float x\nproperty float y\nproperty float z\n"
+                   "property uchar red\nelement face 1\nproperty list uchar int vertex_indices\nend_header\n0 0 0 255\n1 0 0 255\n0 1.5 0 255\n3 0 1 2\n")
+    v3, f3 = vio.load_ply(str(asc))
+    assert v3.tolist() == [[0, 0, 0], [1, 0, 0], [0, 1.5, 0]] and f3.tolist() == [[0, 1, 2]]

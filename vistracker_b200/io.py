@@ -11,6 +11,7 @@ writes.  Pure host code: one batched device->host copy per call, then the same p
                       (recon/recon_fit_base.py:830-844, recon/gen/generator_vis.py:54-55)
   output_folders      ``<outpath>/<seq>/<frame>/<save_name>``                              (recon/recon_fit_base.py:278-294)
   save_triplane_png / load_triplane_png   ``k{kid}.smooth_triplane.png`` with R, G, B = right, back, top (render/render_triplane_nr.py:84-85)
+  save_ply / load_ply ``k{kid}.smplfit_*.ply`` meshes (psbody ``Mesh.write_ply``; read back by the triplane renderer and the test loader)
   packed_batch        the slices of a sequence pack for the frames of one batch (recon/recon_fit_base.py:346-370)
   pack_smplt / pack_recon / load_packed   the per-sequence joblib packs (preprocess/pack_smplt.py:45-63, preprocess/pack_recon.py:118-157)
                       written from in-memory trajectories instead of re-reading every per-frame file
@@ -192,3 +193,63 @@ def packed_batch(packed: dict, image_paths: Sequence[str], test_kid: int = 1) ->
     if "neural_visibility" in packed and len(packed["neural_visibility"]):
         out["occ_ratios"] = np.array([np.asarray(packed["neural_visibility"][i]).reshape(-1)[0] for i in inds])
     return out
+
+
+def save_ply(file: str, verts, faces) -> str:
+    """``Mesh(v, f).write_ply(file)`` (psbody.mesh; called at preprocess/fit_SMPLH_kpts.py:262-264, fit_SMPLH_smoothed.py:62-63): the
+    ``k{kid}.smplfit_temporal.ply`` / ``.smplfit_smoothed.ply`` meshes that the triplane renderer and ``TestDataTriplane.load_mesh`` read back.
+    Binary little-endian PLY, float32 x y z per vertex, ``list uchar int vertex_indices`` per face."""
+    v = np.ascontiguousarray(_np(verts), dtype="<f4").reshape(-1, 3)
+    f = np.ascontiguousarray(_np(faces), dtype="<i4").reshape(-1, 3)
+    os.makedirs(os.path.dirname(file) or ".", exist_ok=True)
+    header = ("ply\nformat binary_little_endian 1.0\n"
+              f"element vertex {v.shape[0]}\nproperty float x\nproperty float y\nproperty float z\n"
+              f"element face {f.shape[0]}\nproperty list uchar int vertex_indices\nend_header\n")
+    rec = np.empty(f.shape[0], dtype=[("n", "u1"), ("idx", "<i4", (3,))])
+    rec["n"], rec["idx"] = 3, f
+    with open(file, "wb") as fh:
+        fh.write(header.encode("ascii")); fh.write(v.tobytes()); fh.write(rec.tobytes())
+    return file
+
+
+def load_ply(file: str):
+    """(verts [V,3] float64, faces [F,3] int64) of an ascii or binary-little-endian triangle PLY whose vertex element starts with float x, y, z
+    (further float / uchar vertex properties are skipped) -- enough for the meshes the reference's fitters write."""
+    sizes = {"float": 4, "float32": 4, "double": 8, "float64": 8, "uchar": 1, "uint8": 1, "char": 1, "int": 4, "int32": 4, "uint": 4, "short": 2, "ushort": 2}
+    with open(file, "rb") as fh:
+        fmt, nv, nf, vprops, cur = None, 0, 0, [], None
+        while True:
+            line = fh.readline().decode("ascii").strip()
+            tok = line.split()
+            if not tok:
+                continue
+            if tok[0] == "format":
+                fmt = tok[1]
+            elif tok[0] == "element":
+                cur = tok[1]
+                if cur == "vertex":
+                    nv = int(tok[2])
+                elif cur == "face":
+                    nf = int(tok[2])
+            elif tok[0] == "property" and cur == "vertex":
+                vprops.append((tok[2], tok[1]))
+            elif tok[0] == "end_header":
+                break
+        if [p[0] for p in vprops[:3]] != ["x", "y", "z"]:
+            raise ValueError(f"{file}: vertex element does not start with x, y, z")
+        if fmt == "ascii":
+            rows = [fh.readline().split() for _ in range(nv)]
+            verts = np.array([[float(t) for t in r[:3]] for r in rows], np.float64)
+            faces = np.array([[int(t) for t in fh.readline().split()[1:4]] for _ in range(nf)], np.int64)
+        elif fmt == "binary_little_endian":
+            vdt = np.dtype([(n, {4: "<f4", 8: "<f8"}[sizes[t]] if t in ("float", "float32", "double", "float64") else f"<u{sizes[t]}") for n, t in vprops])
+            vraw = np.frombuffer(fh.read(vdt.itemsize * nv), dtype=vdt, count=nv)
+            verts = np.stack([vraw["x"], vraw["y"], vraw["z"]], 1).astype(np.float64)
+            fdt = np.dtype([("n", "u1"), ("idx", "<i4", (3,))])
+            fraw = np.frombuffer(fh.read(fdt.itemsize * nf), dtype=fdt, count=nf)
+            if nf and not bool((fraw["n"] == 3).all()):
+                raise ValueError(f"{file}: only triangle meshes are supported")
+            faces = fraw["idx"].astype(np.int64)
+        else:
+            raise ValueError(f"{file}: unsupported PLY format {fmt}")
+    return verts, faces.reshape(-1, 3)
