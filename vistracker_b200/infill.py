@@ -105,6 +105,7 @@ class ConditionalMInfiller:
         self._loaded = False
         self._pos: Dict[tuple, torch.Tensor] = {}
         self._ws: Dict[tuple, dict] = {}
+        self._pinned = set()            # workspaces a captured CUDA graph points into: never dropped
 
     def _g(self, k):
         return self.opt[k] if isinstance(self.opt, dict) else getattr(self.opt, k)
@@ -146,24 +147,28 @@ class ConditionalMInfiller:
             self._pos[(T, D)] = position_embedding(T, D).to(self.device)
         return self._pos[(T, D)]
 
-    def _workspace(self, B: int, T: int) -> dict:
+    def _workspace(self, B: int, T: int, pin: bool = False) -> dict:
         key = (B, T)
+        if pin:
+            self._pinned.add(key)
         if key not in self._ws:
             if len(self._ws) > 8:
-                self._ws.clear()
+                for k in [k for k in self._ws if k not in self._pinned]:
+                    del self._ws[k]
             n, dev = B * T, self.device
             e = lambda *s: torch.empty(*s, device=dev, dtype=torch.float32)
             self._ws[key] = dict(xs=e(n, self.Ds), xo=e(n, self.Do), xj=e(n, self.Dj), qkv=e(n, 3 * self.Dj), qkv2=e(n, 3 * self.Do), attn=e(n, self.Dj),
                                  attn2=e(n, self.Do), side=torch.cuda.Stream(device=dev))
         return self._ws[key]
 
-    def forward_into(self, data_smpl, mask_smpl, data_obj, mask_obj, pred):
-        """All arguments device tensors: data [B,T,*] float32 contiguous, masks [B,T] uint8/bool or None, pred [B,T,out_dim]."""
+    def forward_into(self, data_smpl, mask_smpl, data_obj, mask_obj, pred, pin: bool = False):
+        """All arguments device tensors: data [B,T,*] float32 contiguous, masks [B,T] uint8/bool or None, pred [B,T,out_dim].  ``pin`` keeps
+        the (B, T) workspace alive for the lifetime of the module (callers that capture the launches into a CUDA graph)."""
         if not self._loaded:
             raise RuntimeError("load_state_dict first")
         B, T = data_smpl.shape[:2]
         n = B * T
-        ws = self._workspace(B, T)
+        ws = self._workspace(B, T, pin)
         main = torch.cuda.current_stream(self.device)
         side = ws["side"]
         side.wait_stream(main)
@@ -238,7 +243,7 @@ class CondMotionInfillAutoreg:
         for i, (s, T, n_ctx) in enumerate(b["plan"]):
             ds, do, pred = b["ds"][:T], b["do"][:T], b["pred"][:T]
             _lib.call("vt_infill_pack_clip", P(b["rs"]), P(b["ts"]), P(b["ro"]), P(b["out"]), P(b["masks"][i]), L, s, T, n_ctx, P(ds), P(do), S())
-            m.forward_into(ds[None], b["zero"][None, :T], do[None], b["masks"][i][None, :T], pred[None])
+            m.forward_into(ds[None], b["zero"][None, :T], do[None], b["masks"][i][None, :T], pred[None], pin=self.use_graph)
             _lib.call("vt_infill_commit_clip", P(pred), L, s, n_ctx, T, P(b["out"]), S())
         _lib.call("vt_smooth_rot6d_to_rotmat", P(b["out"]), L, 1, P(b["angles"]), S())          # stored as R^T (interp/test_infiller.py:134)
 
