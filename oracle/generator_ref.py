@@ -2,9 +2,10 @@
 
 Follows recon/gen/generator.py:72-104 (approx_surface), :149-215 (gen_pc_batch), generator_triplane.py:32-55 and
 generator_vis.py:19-56 line by line, over the oracle's SIF-Net (oracle/sifnet_ref.py) instead of the reference nn.Module; the
-random draws come from torch's CPU generator in the reference's order.  The in-tree reference code cannot be constructed
-without a checkpoint directory and a CUDA device (generator.py:28,38,47-52), so this restatement is pinned only through the
-pinned SIF-Net oracle it calls -- the control flow is restated, not executed from the reference.
+random draws come from torch's CPU generator in the reference's order.  Pinned by tests/golden/generator_small.npz: the reference's
+own GeneratorTriplaneVis.get_grid_samples / approx_surface / gen_pc_batch executed on the CPU (the instance is created without
+``__init__``, which only wants a checkpoint directory and a CUDA device, generator.py:28-52) -- this restatement reproduces them
+bit for bit, including the sample counts and the resampling draws (tests/test_oracle_generator.py).
 """
 from __future__ import annotations
 

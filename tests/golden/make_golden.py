@@ -20,6 +20,8 @@ seeded synthetic checkpoint of ``vistracker_b200.synth`` and stores inputs-by-se
 * ``frameio_small.npz``     -- (``--only frameio``) BehaveDataset.prepare_image_crop / BaseDataset.crop / compose_images on three synthetic
   frames (centred, running past the right/bottom border, past the top/left one); cv2.resize / findContours injected (OpenCV absent).
 * ``interp_small.npz``      -- (``--only interp``) BaseInterpolator.compute_missing_inds / interp_slerp / interp_lerp (SLERP baseline).
+* ``generator_small.npz``   -- (``--only generator``) the reference's GeneratorTriplaneVis.get_grid_samples / approx_surface / gen_pc_batch
+  executed on the CPU (instance created without ``__init__``, which only loads a checkpoint and moves the model to CUDA).
 * ``smooth_small.npz``      -- (``--only smooth``) SmoothNetSMPL / SmoothNet through SMPLTSmoother / ObjrotSmoother pre- and
                                post-processing on a 90-frame synthetic trajectory, window 64, + the rotation conversions
 """
@@ -556,6 +558,47 @@ def interp_goldens(out_dir: str):
     np.savez_compressed(os.path.join(out_dir, "interp_small.npz"), **out)
     print("interp_small.npz:", {k: getattr(v, "shape", v) for k, v in out.items()}, "spans", list(zip(start_inds, end_inds)))
 
+def generator_goldens(out_dir: str):
+    """UDF -> point cloud generator: the reference's own GeneratorTriplaneVis methods -- get_grid_samples,
+    approx_surface, gen_pc_batch (with parse_preds / compose_outdict) -- executed on the CPU.  ``Generator.__init__`` wants a checkpoint
+    directory and a CUDA device (recon/gen/generator.py:28-52), none of which the methods need: the instance is created without it and
+    given device='cpu', the thresholds and the reference SIF-Net (seeded synthetic checkpoint).  -> generator_small.npz"""
+    t = _stub("trainer"); t.__path__ = []; _stub("trainer.train_utils", convertMillis=None, convertSecs=None, load_checkpoint=None)   # trainer/ imports trimesh
+    from config.config_loader import load_configs                                     # reference
+    from model import CHORETriplaneVisibility                                         # reference
+    from recon.gen.generator_vis import GeneratorTriplaneVis                          # reference
+    from vistracker_b200.config import resolve_dims
+    from vistracker_b200.synth import synthetic_frames, synthetic_state_dict
+
+    with contextlib.redirect_stdout(io.StringIO()):
+        opt = load_configs("tri-vis-l2")
+        net = CHORETriplaneVisibility(opt).eval()
+    net.load_state_dict(synthetic_state_dict(resolve_dims(opt), seed=0), strict=True)
+    for p in net.parameters():
+        p.requires_grad = False
+    gen = object.__new__(GeneratorTriplaneVis)
+    gen.device, gen.threshold, gen.filter_val, gen.sparse_thres, gen.model = torch.device("cpu"), 2.0, 10.0, 0.03, net
+    images, _, crop, body = synthetic_frames(2, size=64, seed=11, n_points=4, jitter=True)
+    batch = {"images": images, "crop_center": crop, "body_center": body, "path": ["a", "b"]}
+    gen.filter(batch)
+    torch.manual_seed(123)
+    init = gen.get_grid_samples(300, batch_size=2, body_center=body)
+    out = {"init": init.numpy().copy()}
+    # one call of approx_surface: 3 chained projection steps, both targets
+    for name in ("human", "object"):
+        s = init.clone().requires_grad_(True)
+        surf, preds = gen.approx_surface(net, s, 3, gen.prep_query_input(batch), df_type=name)
+        out[f"surf_{name}"] = surf.detach().numpy().copy()
+        out[f"surf_df_{name}"] = preds[0].detach().numpy().copy()
+    # the whole loop: resampling draws from torch's global CPU generator; filter_val 10 accepts every in-front point of the random-init UDF
+    torch.manual_seed(7)
+    with contextlib.redirect_stdout(io.StringIO()):
+        pc = gen.gen_pc_batch(net, "object", init, 250, batch, num_steps=1, mute=True)
+    for k, v in pc.items():
+        out[f"pc_{k}"] = v.numpy().copy()
+    np.savez_compressed(os.path.join(out_dir, "generator_small.npz"), **out)
+    print("generator_small.npz:", {k: v.shape for k, v in out.items()})
+
 
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
@@ -582,5 +625,7 @@ if __name__ == "__main__":
         frameio_goldens(HERE)
     if a.only == "interp":                  # stubs `behave`: run on its own
         interp_goldens(HERE)
+    if a.only == "generator":               # stubs `trainer`: run on its own
+        generator_goldens(HERE)
     if a.only == "infill":                  # stubs `behave` / `trainer`: run on its own
         infill_goldens(HERE)
