@@ -22,6 +22,8 @@ seeded synthetic checkpoint of ``vistracker_b200.synth`` and stores inputs-by-se
 * ``interp_small.npz``      -- (``--only interp``) BaseInterpolator.compute_missing_inds / interp_slerp / interp_lerp (SLERP baseline).
 * ``generator_small.npz``   -- (``--only generator``) the reference's GeneratorTriplaneVis.get_grid_samples / approx_surface / gen_pc_batch
   executed on the CPU (instance created without ``__init__``, which only loads a checkpoint and moves the model to CUDA).
+* ``render_views.npz``      -- (``--only render``) TriplaneNrRenderer.transform_view for the three views.
+* ``roi_small.npz``         -- (``--only roi``) make_bbox_square, SilLossROI.to_original_bbox / compute_K_roi / cvt_masks.
 * ``smooth_small.npz``      -- (``--only smooth``) SmoothNetSMPL / SmoothNet through SMPLTSmoother / ObjrotSmoother pre- and
                                post-processing on a 90-frame synthetic trajectory, window 64, + the rotation conversions
 """
@@ -599,6 +601,49 @@ def generator_goldens(out_dir: str):
     np.savez_compressed(os.path.join(out_dir, "generator_small.npz"), **out)
     print("generator_small.npz:", {k: v.shape for k, v in out.items()})
 
+def render_goldens(out_dir: str):
+    """TriplaneNrRenderer.transform_view (render/render_triplane_nr.py:110-139), the part of the triplane rendering that is the reference's
+    own code (the rasteriser behind it, neural_renderer, is not installable) -> render_views.npz."""
+    _stub("cv2", setNumThreads=lambda n: None)
+    b = _stub("behave"); b.frame_data = _stub("behave.frame_data", FrameDataReader=object); b.kinect_transform = _stub("behave.kinect_transform", KinectTransform=object)
+    _stub("lib_smpl.body_landmark", BodyLandmarks=object)
+    _stub("neural_renderer", Renderer=object)
+    from render.render_triplane_nr import TriplaneNrRenderer                          # reference
+    pts = np.random.default_rng(12).standard_normal((40, 3))
+    out = {"points": pts}
+    for view in ("right", "back", "top"):
+        out[view] = TriplaneNrRenderer.transform_view(pts, view)
+    out["top_z5"] = TriplaneNrRenderer.transform_view(pts, "top", z_offset=5.0)
+    np.savez_compressed(os.path.join(out_dir, "render_views.npz"), **out)
+    print("render_views.npz:", {k: v.shape for k, v in out.items()})
+
+def roi_goldens(out_dir: str):
+    """The set-up arithmetic of SilLossROI (recon/obj_pose_roi.py:21-75): make_bbox_square (recon/bbox.py:25-46), to_original_bbox (:110-120),
+    compute_K_roi (:123-155, torch.cuda.FloatTensor redirected to the CPU type), cvt_masks (:157-170).  The mask crop itself
+    (detectron2 BitMasks.crop_and_resize) and cv2's contour bbox are not installable -> not in this golden.  -> roi_small.npz"""
+    _stub("cv2", setNumThreads=lambda n: None)
+    _stub("neural_renderer", Renderer=object)
+    d = _stub("detectron2"); d.structures = _stub("detectron2.structures", BitMasks=object); _stub("detectron2.structures.boxes", BoxMode=object)
+    import scipy.ndimage
+    if not hasattr(scipy.ndimage, "morphology"):                                   # removed namespace in recent scipy; only an import in the reference
+        _stub("scipy.ndimage.morphology", distance_transform_edt=scipy.ndimage.distance_transform_edt)
+    _stub("recon.opt_utils", mask2bbox=None)                                         # imports cv2 / psbody at module level; one function is used
+    from recon.bbox import make_bbox_square                                           # reference
+    from recon.obj_pose_roi import SilLossROI                                         # reference
+    torch.cuda.FloatTensor = torch.FloatTensor
+    rng = np.random.default_rng(17)
+    boxes_xywh = np.stack([rng.uniform(50, 300, 6), rng.uniform(40, 280, 6), rng.uniform(30, 160, 6), rng.uniform(30, 160, 6)], 1)
+    squares = make_bbox_square(boxes_xywh.copy(), 0.3)
+    centers = rng.uniform(600, 1400, (6, 2))
+    orig = np.stack([SilLossROI.to_original_bbox(sq, 1200 / 512, c, 1200) for sq, c in zip(squares, centers)])
+    Ks = np.stack([SilLossROI.compute_K_roi(b)[0].numpy() for b in orig])
+    K_icap = SilLossROI.compute_K_roi(orig[0], image_width=1920, fx=918.457763671875, fy=918.4373779296875, cx=956.9661865234375, cy=555.944580078125)[0].numpy()
+    ps, ob = torch.from_numpy(rng.random((3, 32, 32)).astype(np.float32)), torch.from_numpy(rng.random((3, 32, 32)).astype(np.float32))
+    keep = torch.stack([SilLossROI.cvt_masks(None, p, o) for p, o in zip(ps, ob)]).numpy()
+    out = {"boxes_xywh": boxes_xywh, "squares": squares, "centers": centers, "orig": orig, "Ks": Ks, "K_icap": K_icap, "ps": ps.numpy(), "ob": ob.numpy(), "keep": keep}
+    np.savez_compressed(os.path.join(out_dir, "roi_small.npz"), **out)
+    print("roi_small.npz:", {k: v.shape for k, v in out.items()})
+
 
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
@@ -627,5 +672,9 @@ if __name__ == "__main__":
         interp_goldens(HERE)
     if a.only == "generator":               # stubs `trainer`: run on its own
         generator_goldens(HERE)
+    if a.only == "render":                  # stubs `cv2` / `behave` / `neural_renderer`: run on its own
+        render_goldens(HERE)
+    if a.only == "roi":                     # stubs `cv2` / `detectron2` / `neural_renderer`: run on its own
+        roi_goldens(HERE)
     if a.only == "infill":                  # stubs `behave` / `trainer`: run on its own
         infill_goldens(HERE)

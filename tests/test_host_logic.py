@@ -53,3 +53,46 @@ def test_position_embedding_host_table_equals_the_oracle():
     from vistracker_b200.infill import position_embedding
     for L, D in ((180, 128), (180, 32), (160, 160), (47, 33), (1, 8)):
         assert torch.equal(position_embedding(L, D), IR.position_embedding(L, D))
+
+
+def test_triplane_view_transforms_match_reference_static_method():
+    import os
+    from vistracker_b200.render import TriplaneNrRenderer
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "render_views.npz"))
+    pts = torch.from_numpy(g["points"])
+    for view in ("right", "back", "top"):
+        assert np.array_equal(TriplaneNrRenderer.transform_view(pts, view).numpy(), g[view]), view
+    assert np.array_equal(TriplaneNrRenderer.transform_view(pts, "top", 5.0).numpy(), g["top_z5"])
+    batched = TriplaneNrRenderer.transform_view(pts[None].repeat(2, 1, 1), "right")
+    assert np.array_equal(batched[1].numpy(), g["right"])
+
+
+def test_roi_setup_arithmetic_matches_reference_functions():
+    """make_bbox_square / to_original_bbox / compute_K_roi / cvt_masks against the reference's (roi_small.npz); the mask crop (detectron2,
+    restated on torchvision.ops.roi_align) is checked for its geometry."""
+    import os
+    from vistracker_b200.render import SilLossROI, cvt_masks, make_bbox_square, mask_bboxes_xyxy, roi_setup, to_original_bbox
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "roi_small.npz"))
+    sq = make_bbox_square(g["boxes_xywh"], 0.3)
+    assert np.allclose(sq, g["squares"], rtol=0, atol=1e-12)
+    for i in range(6):
+        o = to_original_bbox(sq[i], 1200 / 512, g["centers"][i], 1200)
+        assert np.allclose(o, g["orig"][i], rtol=0, atol=1e-9)
+        assert np.abs(SilLossROI.compute_K_roi(o).numpy() - g["Ks"][i]).max() < 1e-6
+    K = SilLossROI.compute_K_roi(g["orig"][0], image_width=1920, fx=918.457763671875, fy=918.4373779296875, cx=956.9661865234375, cy=555.944580078125)
+    assert np.abs(K.numpy() - g["K_icap"]).max() < 1e-6
+    keep = torch.stack([cvt_masks(torch.from_numpy(p), torch.from_numpy(o)) for p, o in zip(g["ps"], g["ob"])])
+    assert np.array_equal(keep.numpy(), g["keep"])
+    # geometry of the crop: a 40 x 20 object box centred at (100, 60) in a 128 x 192 network input, person to its left overlapping it
+    om = torch.zeros(2, 128, 192); om[:, 50:70, 80:120] = 1.0
+    pm = torch.zeros(2, 128, 192); pm[:, 40:90, 60:95] = 1.0
+    assert mask_bboxes_xyxy(om).tolist() == [[80, 50, 120, 70]] * 2
+    keep, ref, K = roi_setup(pm, om, torch.tensor([[1024.0, 768.0], [900.0, 700.0]]), rend_size=64, net_input_size=128, crop_size=1200)
+    assert keep.shape == (2, 64, 64) and ref.shape == (2, 64, 64) and K.shape == (2, 3, 3)
+    # the square is 52 px wide (40 * 1.3) around (100, 60): the object spans 40/52 of the width and 20/52 of the height of the crop
+    cols, rows = ref[0].any(0).nonzero().flatten(), ref[0].any(1).nonzero().flatten()
+    assert abs((int(cols[-1]) - int(cols[0]) + 1) - 64 * 40 / 52) <= 1.5 and abs((int(rows[-1]) - int(rows[0]) + 1) - 64 * 20 / 52) <= 1.5
+    assert abs((int(cols[0]) + int(cols[-1])) / 2 - 31.5) <= 1.0 and abs((int(rows[0]) + int(rows[-1])) / 2 - 31.5) <= 1.0
+    assert bool((keep[0][ref[0] > 0] == 1).all()) and float(keep[0].min()) == 0.0          # person-only pixels are ignored, object pixels kept
+    side = 52 * 1200 / 128
+    assert abs(float(K[0, 0, 0]) - 979.7844 / side) < 1e-6 and abs(float(K[1, 0, 2]) - (1018.952 - (900 - 600 + (100 - 26) * 1200 / 128)) / side) < 1e-5

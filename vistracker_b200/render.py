@@ -82,6 +82,66 @@ class SilhouetteRenderer:
         return depth
 
 
+def make_bbox_square(bbox_xywh: np.ndarray, bbox_expansion: float = 0.0) -> np.ndarray:
+    """recon/bbox.py:25-46: square boxes (xywh) around the centres, side = max(w, h) * (1 + expansion)."""
+    b = np.array(bbox_xywh, dtype=float).reshape(-1, 4)
+    center = np.stack((b[:, 0] + b[:, 2] / 2, b[:, 1] + b[:, 3] / 2), 1)
+    side = np.maximum(b[:, 2], b[:, 3])[:, None] * (1 + bbox_expansion)
+    return np.hstack((center - side / 2, side, side)).reshape(np.shape(bbox_xywh))
+
+
+def to_original_bbox(bbox_square: np.ndarray, scale: float, trans: np.ndarray, crop_size: float = 1200) -> np.ndarray:
+    """obj_pose_roi.py:110-120: an xywh box in network-input pixels -> original-image pixels (scale = crop_size / net_input_size, trans = the
+    crop centre)."""
+    out = np.array(bbox_square, dtype=float) * scale
+    out[:2] += np.asarray(trans, dtype=float) - crop_size / 2.0
+    return out
+
+
+def cvt_masks(person_mask: torch.Tensor, obj_mask: torch.Tensor) -> torch.Tensor:
+    """obj_pose_roi.py:157-170 (PHOSA's occlusion-aware convention): False only where the person covers the pixel and the object does not."""
+    fore, ps = obj_mask > 0.5, person_mask > 0.5
+    inv = -ps.float()
+    inv[fore] = 1.0
+    return inv >= 0
+
+
+def mask_bboxes_xyxy(masks: torch.Tensor) -> np.ndarray:
+    """``SilLossROI.masks2bboxes`` (obj_pose_roi.py:173-181 over recon/opt_utils.py:144-155): per mask the bounding box (x1, y1, x2, y2; max
+    exclusive) of ``uint8(mask * 255) > 127``; cv2's contour route reduces to the box of the thresholded pixels.  Empty masks keep the
+    reference's sentinels."""
+    out = []
+    for m in masks:
+        fg = (m.detach().float() * 255).to(torch.uint8) > 127
+        ys, xs = torch.nonzero(fg.any(1)).flatten(), torch.nonzero(fg.any(0)).flatten()
+        out.append([50000, 50000, -100, -100] if xs.numel() == 0 else [int(xs[0]), int(ys[0]), int(xs[-1]) + 1, int(ys[-1]) + 1])
+    return np.asarray(out)
+
+
+def roi_setup(person_masks, obj_masks, crop_centers, rend_size=256, bbox_expansion=0.3, camera_params=None, crop_size=1200, net_input_size=512):
+    """Everything ``SilLossROI.__init__`` derives from the batch (obj_pose_roi.py:41-70): object-mask boxes -> expanded squares -> both masks
+    cropped and resized to ``rend_size`` -> keep mask, reference silhouette, ROI intrinsics.  The crop is detectron2's
+    ``BitMasks.crop_and_resize`` = aligned RoIAlign (adaptive sampling) of the boolean mask thresholded at 0.5; detectron2 is not installable
+    here, so it is restated on ``torchvision.ops.roi_align`` -- the operator detectron2's ROIAlign wraps (set-up cost once per batch, not on
+    the loop).  Returns (keep_mask [B,S,S] float, image_ref [B,S,S] float, K_roi [B,3,3])."""
+    from torchvision.ops import roi_align
+    pm, om = torch.as_tensor(person_masks), torch.as_tensor(obj_masks)
+    B, dev = om.shape[0], om.device
+    xyxy = mask_bboxes_xyxy(om).astype(float)
+    xywh = np.concatenate([xyxy[:, :2], xyxy[:, 2:] - xyxy[:, :2]], 1)                  # BoxMode XYXY_ABS -> XYWH_ABS
+    squares = make_bbox_square(xywh, bbox_expansion)
+    sq_xyxy = np.concatenate([squares[:, :2], squares[:, :2] + squares[:, 2:]], 1)      # XYWH_ABS -> XYXY_ABS
+    rois = torch.cat([torch.arange(B, dtype=torch.float32)[:, None], torch.as_tensor(sq_xyxy, dtype=torch.float32)], 1).to(dev)
+    crop = lambda m: roi_align((m != 0).float()[:, None], rois, (rend_size, rend_size), 1.0, 0, True)[:, 0] >= 0.5
+    obj_c, ps_c = crop(om), crop(pm)
+    keep = torch.stack([cvt_masks(p, o) for p, o in zip(ps_c, obj_c)]).float()
+    ref = (obj_c > 0).float()
+    cc = torch.as_tensor(crop_centers).detach().cpu().numpy()
+    K = torch.stack([SilLossROI.compute_K_roi(to_original_bbox(sq, crop_size / net_input_size, c, crop_size), **(camera_params or {}))
+                     for sq, c in zip(squares, cc)])
+    return keep, ref, K
+
+
 class SilLossROI:
     """Occlusion-aware silhouette loss of recon/obj_pose_roi.py on already-cropped ROI masks.
 
@@ -93,6 +153,14 @@ class SilLossROI:
         self.keep_mask, self.image_ref = keep_mask.float().to(dev), image_ref.float().to(dev)
         self.vertices = torch.as_tensor(np.asarray(vertices), dtype=torch.float32).to(dev)
         self.renderer = SilhouetteRenderer(faces, rend_size, K_roi, dev)
+
+    @classmethod
+    def from_masks(cls, person_masks, obj_masks, vertices, faces, crop_centers, rend_size=256, bbox_expansion=0.3, device="cuda:0",
+                   camera_params=None, crop_size=1200, net_input_size=512):
+        """The reference constructor ``SilLossROI(person_masks, obj_masks, temp_mesh, crop_centers, ...)`` (obj_pose_roi.py:21-75): the masks
+        are channels 3 / 4 of the network input; see ``roi_setup`` for the steps."""
+        keep, ref, K = roi_setup(person_masks, obj_masks, crop_centers, rend_size, bbox_expansion, camera_params, crop_size, net_input_size)
+        return cls(keep, ref, K, vertices, faces, rend_size=rend_size, device=device)
 
     @staticmethod
     def compute_K_roi(bbox_square, image_width=2048, fx=979.7844, fy=979.840, cx=1018.952, cy=779.486):
