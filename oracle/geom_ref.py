@@ -66,14 +66,26 @@ def compute_transform(S1, S2):
     return R, t[:, 0], scale
 
 
-def evaluate_sequence(sverts_recon, overts_recon, sverts_gt, overts_gt, window, recon_exist=None, smpl_only=False):
-    """The alignment-window loop of VideoPackedEvaluator.eva_seq (recon/eval/evalvideo_packed.py:100-147) restated on plain arrays, with
+def evaluate_sequence(sverts_recon, overts_recon, sverts_gt, overts_gt, window, recon_exist=None, smpl_only=False, with_accel=False,
+                      return_transforms=False):
+    """The alignment-window loop of VideoPackedEvaluator.eva_seq (recon/eval/evalvideo_packed.py:100-163) restated on plain arrays, with
     the Chamfer distance evaluated on the vertices (the reference's trimesh surface samples are unseeded random draws): rows of
-    (Chamfer SMPL, Chamfer object, v2v SMPL, v2v object) in cm for every frame that has a reconstruction."""
+    (Chamfer SMPL, Chamfer object, v2v SMPL, v2v object) in cm for every frame that has a reconstruction; ``with_accel`` appends the two
+    acceleration-error columns (:148-160 over evaluate_video.py:138-157: one value per flushed group of frames, repeated).  Pinned by
+    tests/golden/eval_seq.npz -- the reference's own eva_seq run on in-memory arrays."""
     import numpy as np
     L = len(sverts_gt)
     exist = np.ones(L, bool) if recon_exist is None else np.asarray(recon_exist, bool)
-    count, arot, out = 0, None, []
+    count, arot, out, transforms = 0, None, [], []
+    col = [[], [], [], []]                           # aligned SMPL recon, SMPL gt, aligned object recon, object gt since the last flush
+    acc_s, acc_o = [], []
+
+    def accel(gt, rc):
+        gt, rc = np.stack(gt, 0), np.stack(rc, 0)
+        d = (gt[:-2] - 2 * gt[1:-1] + gt[2:]) - (rc[:-2] - 2 * rc[1:-1] + rc[2:])
+        n = np.linalg.norm(d, axis=2)
+        return float(n.mean() * 100) if n.size else float("nan")
+
     for i in range(L):
         count += 1
         rec = [np.asarray(sverts_recon[i], np.float64), np.asarray(overts_recon[i], np.float64)]
@@ -89,13 +101,24 @@ def evaluate_sequence(sverts_recon, overts_recon, sverts_gt, overts_gt, window, 
                     g = np.concatenate([np.concatenate(x[idx], 0) for x in (sverts_gt, overts_gt)], 0)
                     r = np.concatenate([np.concatenate(x[idx], 0) for x in (sverts_recon, overts_recon)], 0)
                 arot, atrans, ascale = compute_transform(r, g)
+                transforms.append((i, arot, atrans, ascale))
             rec = [(ascale * arot.dot(m.T) + atrans[:, None]).T for m in rec]
         if not exist[i]:
             continue
         gt = [np.asarray(sverts_gt[i], np.float64), np.asarray(overts_gt[i], np.float64)]
         row = [eval_chamfer(g, r) * 100.0 for g, r in zip(gt, rec)] + [np.sqrt(((g - r) ** 2).sum(-1)).mean() * 100.0 for g, r in zip(gt, rec)]
         out.append(row)
-    return np.asarray(out)
+        if with_accel:
+            col[0].append(rec[0]); col[1].append(gt[0]); col[2].append(rec[1]); col[3].append(gt[1])
+            if count % window == 0 or i == L - 1:
+                n = len(col[1])
+                acc_s += [accel(col[1], col[0])] * n
+                acc_o += [accel(col[3], col[2])] * n
+                col = [[], [], [], []]
+    out = np.asarray(out)
+    if with_accel:
+        out = np.concatenate([out, np.asarray(acc_s)[:, None], np.asarray(acc_o)[:, None]], 1)
+    return (out, transforms) if return_transforms else out
 
 
 def init_object_orientation(tgt_axis: torch.Tensor, src_axis: torch.Tensor, noise: torch.Tensor = None) -> torch.Tensor:

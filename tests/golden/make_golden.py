@@ -24,6 +24,8 @@ seeded synthetic checkpoint of ``vistracker_b200.synth`` and stores inputs-by-se
   executed on the CPU (instance created without ``__init__``, which only loads a checkpoint and moves the model to CUDA).
 * ``render_views.npz``      -- (``--only render``) TriplaneNrRenderer.transform_view for the three views.
 * ``roi_small.npz``         -- (``--only roi``) make_bbox_square, SilLossROI.to_original_bbox / compute_K_roi / cvt_masks.
+* ``eval_seq.npz``          -- (``--only evalseq``) VideoPackedEvaluator.eva_seq run on an in-memory synthetic sequence (alignment windows,
+  frames without a reconstruction, Chamfer on the vertices, v2v, acceleration errors).
 * ``smooth_small.npz``      -- (``--only smooth``) SmoothNetSMPL / SmoothNet through SMPLTSmoother / ObjrotSmoother pre- and
                                post-processing on a 90-frame synthetic trajectory, window 64, + the rotation conversions
 """
@@ -644,6 +646,58 @@ def roi_goldens(out_dir: str):
     np.savez_compressed(os.path.join(out_dir, "roi_small.npz"), **out)
     print("roi_small.npz:", {k: v.shape for k, v in out.items()})
 
+def evalseq_goldens(out_dir: str):
+    """The evaluation loop itself: the reference's VideoPackedEvaluator.eva_seq (recon/eval/evalvideo_packed.py:29-163)
+    executed on a synthetic sequence -- packed-file loading (prep_verts) replaced by in-memory arrays, psbody's Mesh by a two-field stand-in,
+    and surface_sampling by the vertices themselves (trimesh is not installed and its samples are unseeded draws anyway) -- so that the
+    alignment windows, the handling of frames without a reconstruction, Chamfer (sklearn kd-tree), v2v and the acceleration errors are the
+    reference's.  -> eval_seq.npz"""
+    from argparse import Namespace
+
+    class SimpleMesh:
+        def __init__(self, v=None, f=None):
+            self.v, self.f = v, f
+    ps = _stub("psbody"); ps.mesh = _stub("psbody.mesh", Mesh=SimpleMesh)
+    _stub("trimesh")
+    b = _stub("behave"); b.seq_utils = _stub("behave.seq_utils", SeqInfo=lambda seq: Namespace(get_obj_name=lambda: "chairwood"))
+    tmpl = SimpleMesh(np.zeros((1, 3)), np.zeros((1, 3), int))
+    b.utils = _stub("behave.utils", load_template=lambda name, **kw: tmpl)
+    _stub("lib_smpl", SMPL_Layer=lambda **kw: Namespace(th_faces=torch.zeros(1, 3, dtype=torch.long)))
+    _stub("recon.recon_data", ReconDataReader=object)
+    _stub("recon.opt_utils")
+    from recon.eval.evalvideo_packed import VideoPackedEvaluator                      # reference
+
+    rng = np.random.default_rng(33)
+    L, Vs, Vo, W = 23, 60, 25, 7
+    t = np.arange(L)[:, None, None] / 10.0
+    sv_gt = rng.standard_normal((1, Vs, 3)) * np.array([0.3, 0.8, 0.2]) + np.array([0.0, 0.0, 2.3]) + 0.1 * np.sin(t * np.array([1.0, 2.0, 0.5]))
+    ov_gt = rng.standard_normal((1, Vo, 3)) * 0.2 + np.array([0.5, 0.1, 2.1]) + 0.1 * np.cos(t * np.array([0.7, 1.3, 0.9]))
+    from scipy.spatial.transform import Rotation
+    Rm = Rotation.from_rotvec([0.2, -0.4, 0.1]).as_matrix()
+    sv_rc = 1.1 * sv_gt.dot(Rm.T) + np.array([0.3, -0.1, 0.2]) + 0.01 * rng.standard_normal((L, Vs, 3))
+    ov_rc = 1.1 * ov_gt.dot(Rm.T) + np.array([0.3, -0.1, 0.2]) + 0.03 * rng.standard_normal((L, Vo, 3))
+    exist = np.ones(L, bool); exist[[3, 7, 8, 9, 10, 11, 12, 13]] = False               # one whole window (7..13) has no reconstruction
+    out = {"sv_gt": sv_gt, "ov_gt": ov_gt, "sv_rc": sv_rc, "ov_rc": ov_rc, "exist": exist, "window": W}
+
+    class Ev(VideoPackedEvaluator):
+        def __init__(self):
+            self.errors_dict, self.sample_num, self.unit_cvt = {}, 10000, 100
+
+        def prep_verts(self, save_name, seq_name, smplh_layer, temp, tid):
+            return {"recon_exist": self._exist, "frames": [f"t{i:04d}.000" for i in range(L)]}, ov_gt, ov_rc, sv_gt, sv_rc
+
+        def surface_sampling(self, m):
+            return m.v
+
+    for tag, ex in (("all", np.ones(L, bool)), ("gaps", exist)):
+        ev = Ev(); ev._exist = ex
+        with contextlib.redirect_stdout(io.StringIO()):
+            ev.eva_seq("/data/Date03_Sub03_chairwood_synth", "name", 1, args=Namespace(window=W))
+        out[f"errors_{tag}"] = np.asarray(ev.errors_dict["Date03_Sub03_chairwood_synth"])
+    # (window <= 0, "no alignment", divides by zero in the packed evaluator's acceleration bookkeeping, :148 -- not a usable mode there)
+    np.savez_compressed(os.path.join(out_dir, "eval_seq.npz"), **out)
+    print("eval_seq.npz:", {k: getattr(v, "shape", v) for k, v in out.items()})
+
 
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
@@ -676,5 +730,7 @@ if __name__ == "__main__":
         render_goldens(HERE)
     if a.only == "roi":                     # stubs `cv2` / `detectron2` / `neural_renderer`: run on its own
         roi_goldens(HERE)
+    if a.only == "evalseq":                 # replaces psbody's Mesh and several loaders: run on its own
+        evalseq_goldens(HERE)
     if a.only == "infill":                  # stubs `behave` / `trainer`: run on its own
         infill_goldens(HERE)

@@ -21,3 +21,39 @@ def test_compute_transform_matches_reference():
         assert np.abs(R - GOLD[f"pa_R{i}"]).max() < 1e-10 and np.abs(t - GOLD[f"pa_t{i}"]).max() < 1e-10 and abs(s - float(GOLD[f"pa_s{i}"])) < 1e-10
         hat = s * GOLD[f"pa_src{i}"].astype(np.float64).dot(R.T) + t
         assert np.abs(hat - GOLD[f"pa_hat{i}"]).max() < 1e-9
+
+
+def test_evaluation_loop_matches_reference_eva_seq():
+    """oracle evaluate_sequence (alignment windows, missing reconstructions, Chamfer on vertices, v2v, acceleration errors) against the
+    reference's VideoPackedEvaluator.eva_seq run on in-memory arrays (tests/golden/eval_seq.npz)."""
+    import os
+    import numpy as np
+    from oracle import geom_ref as GR
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "eval_seq.npz"))
+    W = int(g["window"])
+    for tag, exist in (("all", None), ("gaps", g["exist"])):
+        got = GR.evaluate_sequence(g["sv_rc"], g["ov_rc"], g["sv_gt"], g["ov_gt"], W, recon_exist=exist, with_accel=True)
+        ref = g[f"errors_{tag}"]
+        assert got.shape == ref.shape, tag
+        assert np.allclose(got, ref, rtol=1e-7, atol=1e-8, equal_nan=True), (tag, np.nanmax(np.abs(got - ref)))
+    assert g["errors_gaps"].shape[0] == int(g["exist"].sum()) and g["errors_all"].shape == (23, 6)
+    four = GR.evaluate_sequence(g["sv_rc"], g["ov_rc"], g["sv_gt"], g["ov_gt"], W, recon_exist=g["exist"])
+    assert np.allclose(four, g["errors_gaps"][:, :4], rtol=1e-7, atol=1e-8)
+
+
+def test_acceleration_error_helper_matches_reference_columns():
+    """vistracker_b200.evaluate.acceleration_errors (plain tensor arithmetic, runs on any device) with the oracle's window alignments."""
+    import os
+    import numpy as np
+    import torch
+    from oracle import geom_ref as GR
+    from vistracker_b200.evaluate import acceleration_errors
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "eval_seq.npz"))
+    W = int(g["window"])
+    for tag, exist in (("all", None), ("gaps", g["exist"])):
+        _, tr = GR.evaluate_sequence(g["sv_rc"], g["ov_rc"], g["sv_gt"], g["ov_gt"], W, recon_exist=exist, return_transforms=True)
+        acc_s = acceleration_errors(torch.from_numpy(g["sv_rc"]), torch.from_numpy(g["sv_gt"]), tr, W, exist)
+        acc_o = acceleration_errors(torch.from_numpy(g["ov_rc"]), torch.from_numpy(g["ov_gt"]), tr, W, exist)
+        ref = g[f"errors_{tag}"]
+        assert np.allclose(acc_s.numpy(), ref[:, 4], rtol=1e-7, atol=1e-9, equal_nan=True), tag
+        assert np.allclose(acc_o.numpy(), ref[:, 5], rtol=1e-7, atol=1e-9, equal_nan=True), tag

@@ -78,3 +78,38 @@ def evaluate_sequence(sverts_recon, overts_recon, sverts_gt, overts_gt, smpl_fac
     errs = torch.stack([eval_chamfer_distance(ps_g, ps_r), eval_chamfer_distance(po_g, po_r),
                         (gs - rs).norm(dim=-1).mean(-1), (go - ro).norm(dim=-1).mean(-1)], 1) * UNIT_CVT
     return errs, keep, transforms
+
+
+def acceleration_errors(verts_recon: torch.Tensor, verts_gt: torch.Tensor, transforms, window: int, recon_exist=None) -> torch.Tensor:
+    """The 'smpl-acc' / 'obj-acc' column of ``VideoPackedEvaluator.eva_seq`` (recon/eval/evalvideo_packed.py:148-160 over
+    ``compute_accel_err``, recon/eval/evaluate_video.py:138-157) for one of the two meshes: per kept frame, the mean norm (cm) of the difference
+    of the second temporal differences of aligned reconstruction and ground truth, computed per flushed group -- a group ends when the
+    running frame count is a multiple of ``window`` or at the last frame, provided that frame has a reconstruction -- and repeated for the
+    frames of the group (NaN for groups of fewer than three frames).  ``transforms``: the (first frame, R, t, scale) list that
+    ``evaluate_sequence`` returns; frames use the latest alignment computed at or before them.  Plain tensor arithmetic on the device the
+    vertices live on."""
+    L = verts_gt.shape[0]
+    exist = torch.ones(L, dtype=torch.bool) if recon_exist is None else torch.as_tensor(recon_exist).bool().cpu()
+    starts = [int(t[0]) for t in transforms]
+    out, group_r, group_g, count, ti = [], [], [], 0, -1
+    for i in range(L):
+        count += 1
+        realign = (ti < 0 or count % window == 0)
+        if realign:
+            if i in starts:
+                ti = starts.index(i)
+            elif not bool(exist[i:min(L, i + window)].any()):
+                continue                                                           # no alignment possible: the reference skips the frame entirely
+        if not bool(exist[i]):
+            continue
+        _, R, t, s = transforms[ti]
+        R, t = torch.as_tensor(R, dtype=verts_recon.dtype, device=verts_recon.device), torch.as_tensor(t, dtype=verts_recon.dtype, device=verts_recon.device)
+        group_r.append(float(s) * verts_recon[i] @ R.T + t.reshape(1, 3))
+        group_g.append(verts_gt[i])
+        if count % window == 0 or i == L - 1:
+            g, r = torch.stack(group_g), torch.stack(group_r)
+            d = (g[:-2] - 2 * g[1:-1] + g[2:]) - (r[:-2] - 2 * r[1:-1] + r[2:])
+            val = d.norm(dim=2).mean() * UNIT_CVT if d.numel() else torch.tensor(float("nan"), device=verts_gt.device, dtype=verts_gt.dtype)
+            out += [val] * len(group_g)
+            group_r, group_g = [], []
+    return torch.stack(out) if out else torch.zeros(0, device=verts_gt.device, dtype=verts_gt.dtype)
