@@ -115,3 +115,23 @@ def test_chunk_culling_does_not_change_the_image(monkeypatch):
     assert 2000 < float(out["1"][0].sum()) < 3 * 200 * 200 / 2
     assert torch.equal(out["1"][0], out["0"][0]) and torch.equal(out["1"][2], out["0"][2])
     assert rel_err(out["1"][1].cpu(), out["0"][1].cpu()) < 1e-5                    # same face-index map; the vertex scatter uses atomics
+
+
+def test_silloss_roi_from_masks_constructor():
+    """The reference constructor signature (person masks, object masks, template, crop centres): ROI set-up on the device equals the CPU
+    run of the same function, and the loss renders into the ROI camera."""
+    _need_gpu()
+    from vistracker_b200.render import SilLossROI, roi_setup
+    verts0, faces = _mesh(3, n=40)
+    om = torch.zeros(2, 512, 512); om[:, 200:300, 260:340] = 1.0
+    pm = torch.zeros(2, 512, 512); pm[:, 150:400, 180:280] = 1.0
+    cc = torch.tensor([[1024.0, 768.0], [1000.0, 800.0]])
+    sil = SilLossROI.from_masks(pm.cuda(), om.cuda(), verts0 * 0.5, faces, cc.cuda(), device="cuda:0")
+    keep, ref, K = roi_setup(pm, om, cc)
+    assert torch.equal(sil.keep_mask.cpu(), keep) and torch.equal(sil.image_ref.cpu(), ref)
+    R = torch.eye(3, device="cuda")[None].repeat(2, 1, 1).requires_grad_(True)
+    t = torch.tensor([[0.05, 0.0, 2.3], [0.0, 0.05, 2.3]], device="cuda", requires_grad=True)
+    out = sil.forward(R, t, torch.ones(2, device="cuda"))
+    loss = out[0]["mask"] if isinstance(out, tuple) else out["mask"]
+    loss.sum().backward()
+    assert bool(torch.isfinite(loss).all()) and t.grad is not None and bool(torch.isfinite(t.grad).all())
