@@ -26,6 +26,7 @@ seeded synthetic checkpoint of ``vistracker_b200.synth`` and stores inputs-by-se
 * ``roi_small.npz``         -- (``--only roi``) make_bbox_square, SilLossROI.to_original_bbox / compute_K_roi / cvt_masks.
 * ``eval_seq.npz``          -- (``--only evalseq``) VideoPackedEvaluator.eva_seq run on an in-memory synthetic sequence (alignment windows,
   frames without a reconstruction, Chamfer on the vertices, v2v, acceleration errors).
+* ``io_formats.npz``        -- (``--only io``) what the reference's writers put on disk (save_neural_recon, save_outputs, save_results).
 * ``smooth_small.npz``      -- (``--only smooth``) SmoothNetSMPL / SmoothNet through SMPLTSmoother / ObjrotSmoother pre- and
                                post-processing on a 90-frame synthetic trajectory, window 64, + the rotation conversions
 """
@@ -698,6 +699,99 @@ def evalseq_goldens(out_dir: str):
     np.savez_compressed(os.path.join(out_dir, "eval_seq.npz"), **out)
     print("eval_seq.npz:", {k: getattr(v, "shape", v) for k, v in out.items()})
 
+def io_goldens(out_dir: str):
+    """On-disk formats: the reference's own writers executed into a temporary folder and read back --
+    ReconFitterBase.save_neural_recon / save_outputs / get_output_paths (recon/recon_fit_base.py:278-313, 830-845) with
+    opt_utils.save_smplfits (recon/opt_utils.py:113-141), BaseFitter.save_results (preprocess/fit_SMPLH_kpts.py:228-261) and the
+    neural-only joblib pack of preprocess/pack_recon.py:118-133 -> io_formats.npz (file names, key order, dtypes, shapes, values)."""
+    import pickle
+    import tempfile
+    from argparse import Namespace
+    for n in ("trimesh", "igl", "open3d", "zstd", "neural_renderer"):
+        _stub(n)
+
+    class Pointclouds:
+        def __init__(self, pts): self.pts = pts
+    _stub("pytorch3d"); _stub("pytorch3d.loss", chamfer_distance=None)
+    _stub("pytorch3d.structures", Pointclouds=Pointclouds, Meshes=None); _stub("pytorch3d.ops", knn_points=None, sample_points_from_meshes=None)
+    _stub("mesh_intersection"); _stub("mesh_intersection.bvh_search_tree", BVH=object); _stub("mesh_intersection.loss")
+    _stub("detectron2"); _stub("detectron2.structures", BitMasks=object, BoxMode=object, Boxes=object); _stub("detectron2.structures.boxes", BoxMode=object)
+    for m in list(sys.modules):
+        if m.startswith(("psbody", "pytorch3d", "detectron2", "mesh_intersection", "skimage", "chumpy")):
+            sys.modules[m].__path__ = []
+    written = []
+
+    class RecMesh:                                       # records what psbody's Mesh(...).write_ply would be asked to write
+        def __init__(self, v=None, f=None): self.v, self.f = v, f
+        def write_ply(self, path): written.append(path)
+    sys.modules["psbody.mesh"].Mesh = RecMesh
+    sys.modules["psbody.mesh"].MeshViewers = object
+    import recon.recon_fit_base as MB                                                  # reference
+    import preprocess.fit_SMPLH_kpts as FK                                             # reference
+    FK.Mesh = RecMesh
+    rng = np.random.default_rng(41)
+    B, n = 3, 50
+    tmp = tempfile.mkdtemp(prefix="vt_io_")
+    paths = [os.path.join("/data/behave", "Date03_Sub03_chairwood_hand", f"t{i:04d}.{(37 * i) % 1000:03d}", "k1.color.jpg") for i in range(B)]
+    tf = lambda *s: torch.from_numpy(rng.standard_normal(s).astype(np.float32))
+    recon_batch = {t: {"points": tf(B, n, 3), "pca_axis": tf(B, 3, 3), "parts": torch.from_numpy(rng.integers(0, 14, (B, n))),
+                       "centers": torch.cat([torch.full((B, 3), float("nan")), tf(B, 3)], 1), "visibility": torch.rand(B, 1)} for t in ("human", "object")}
+    shim = Namespace(outpath=os.path.join(tmp, "recon"))
+    MB.ReconFitterBase.save_neural_recon(shim, paths, recon_batch, "test-release", 1)
+    out = {"paths": np.array(paths)}
+    for i in range(B):
+        f = os.path.join(shim.outpath, "Date03_Sub03_chairwood_hand", os.path.basename(os.path.dirname(paths[i])), "test-release", "k1_densepc.npz")
+        d = np.load(f, allow_pickle=True)
+        assert sorted(d.files) == ["human", "object"]
+        for t in d.files:
+            for k, v in d[t].item().items():
+                out[f"densepc{i}.{t}.{k}"] = v
+        out[f"densepc{i}.order"] = np.array([f"{t}.{k}" for t in d.files for k in d[t].item()])
+    for t in ("human", "object"):
+        for k, v in recon_batch[t].items():
+            out[f"in.{t}.{k}"] = v.numpy()
+    # save_outputs: SMPL parameter pickle (+ score) and the object pickle with the rotation re-projected without noise
+    pose, betas, trans = tf(B, 156), tf(B, 10), tf(B, 3)
+    smpl = Namespace(pose=pose, betas=betas, trans=trans, faces=torch.zeros(1, 3, dtype=torch.long))
+    smpl_call = lambda: (torch.zeros(B, 4, 3), None, None, None)
+    class SmplShim:
+        def __init__(self): self.pose, self.betas, self.trans, self.faces = pose, betas, trans, torch.zeros(1, 3, dtype=torch.long)
+        def __call__(self): return smpl_call()
+    obj_R = tf(B, 3, 3) * 0.1 + torch.eye(3)
+    obj_t, obj_s = tf(B, 3), torch.ones(B)
+    fit = Namespace(outpath=shim.outpath, scan=Namespace(v=rng.standard_normal((20, 3)), f=np.zeros((1, 3), int)), device="cpu")
+    for name in ("get_output_paths", "transform_object", "transform_obj_verts"):
+        setattr(fit, name, types.MethodType(getattr(MB.ReconFitterBase, name), fit))
+    fit.decopose_axis = MB.ReconFitterBase.decopose_axis
+    MB.ReconFitterBase.save_outputs(fit, SmplShim(), obj_R, obj_t, paths, "test-releasev2", 1, obj_s)
+    for i in range(B):
+        folder = os.path.join(shim.outpath, "Date03_Sub03_chairwood_hand", os.path.basename(os.path.dirname(paths[i])), "test-releasev2")
+        sm, ob = pickle.load(open(os.path.join(folder, "k1.smpl.pkl"), "rb")), pickle.load(open(os.path.join(folder, "k1.object.pkl"), "rb"))
+        out[f"smpl{i}.order"], out[f"object{i}.order"] = np.array(list(sm)), np.array(list(ob))
+        for k, v in sm.items():
+            out[f"smpl{i}.{k}"] = np.asarray(v)
+        for k, v in ob.items():
+            out[f"object{i}.{k}"] = np.asarray(v)
+    out.update({"in.pose": pose.numpy(), "in.betas": betas.numpy(), "in.trans": trans.numpy(), "in.obj_R": obj_R.numpy(), "in.obj_t": obj_t.numpy(), "in.obj_s": obj_s.numpy()})
+    # BaseFitter.save_results: per-frame SMPL-T pickle, frames without confident key points are skipped
+    scores = torch.rand(B, 25); scores[1] = 0.0
+    files = [os.path.join(tmp, "seq", os.path.basename(os.path.dirname(p)), "k1.color.jpg") for p in paths]
+    for f in files:
+        os.makedirs(os.path.dirname(f), exist_ok=True)
+    fk = Namespace(get_outfile=lambda folder, kid: os.path.join(folder, f"k{kid}.smplfit_temporal.pkl"))
+    fk.skip_frame = types.MethodType(FK.BaseFitter.skip_frame, fk); fk.save_smpl_mesh = types.MethodType(FK.BaseFitter.save_smpl_mesh, fk)
+    with contextlib.redirect_stdout(io.StringIO()):
+        FK.BaseFitter.save_results(fk, SmplShim(), "seq", 1, 0, B, scores, files)
+    out["smplt.written"] = np.array([os.path.isfile(os.path.join(os.path.dirname(f), "k1.smplfit_temporal.pkl")) for f in files])
+    d0 = pickle.load(open(os.path.join(os.path.dirname(files[0]), "k1.smplfit_temporal.pkl"), "rb"))
+    out["smplt.order"] = np.array(list(d0))
+    for k, v in d0.items():
+        out[f"smplt0.{k}"] = np.asarray(v)
+    out["in.scores"] = scores.numpy()
+    out["ply_requests"] = np.array([os.path.basename(p) for p in written])
+    np.savez_compressed(os.path.join(out_dir, "io_formats.npz"), **out)
+    print("io_formats.npz:", len(out), "entries;", "ply requests:", sorted(set(out["ply_requests"].tolist())))
+
 
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
@@ -732,5 +826,7 @@ if __name__ == "__main__":
         roi_goldens(HERE)
     if a.only == "evalseq":                 # replaces psbody's Mesh and several loaders: run on its own
         evalseq_goldens(HERE)
+    if a.only == "io":                      # replaces psbody's Mesh: run on its own
+        io_goldens(HERE)
     if a.only == "infill":                  # stubs `behave` / `trainer`: run on its own
         infill_goldens(HERE)

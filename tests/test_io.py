@@ -143,3 +143,50 @@ def test_ply_roundtrip_binary_and_ascii(tmp_path):
                    "property uchar red\nelement face 1\nproperty list uchar int vertex_indices\nend_header\n0 0 0 255\n1 0 0 255\n0 1.5 0 255\n3 0 1 2\n")
     v3, f3 = vio.load_ply(str(asc))
     assert v3.tolist() == [[0, 0, 0], [1, 0, 0], [0, 1.5, 0]] and f3.tolist() == [[0, 1, 2]]
+
+
+def test_writers_match_what_the_reference_writes(tmp_path):
+    """tests/golden/io_formats.npz holds what the reference's own writers put on disk for these inputs (save_neural_recon, save_outputs with
+    save_smplfits, BaseFitter.save_results): same file names, key order, dtypes, shapes, values."""
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "io_formats.npz"), allow_pickle=False)
+    paths = [str(p) for p in g["paths"]]
+    B = len(paths)
+    # ---- k{tid}_densepc.npz
+    folders = vio.output_folders(str(tmp_path / "recon"), paths, "test-release")
+    recon_batch = {t: {k: torch.from_numpy(g[f"in.{t}.{k}"]) for k in ("points", "pca_axis", "parts", "centers", "visibility")} for t in ("human", "object")}
+    files = vio.save_neural_recon(folders, 1, recon_batch)
+    for i, f in enumerate(files):
+        assert f.endswith(os.path.join("Date03_Sub03_chairwood_hand", os.path.basename(os.path.dirname(paths[i])), "test-release", "k1_densepc.npz"))
+        d = np.load(f, allow_pickle=True)
+        order = [f"{t}.{k}" for t in d.files for k in d[t].item()]
+        assert order == [str(x) for x in g[f"densepc{i}.order"]]
+        for t in d.files:
+            for k, v in d[t].item().items():
+                ref = g[f"densepc{i}.{t}.{k}"]
+                assert v.dtype == ref.dtype and v.shape == ref.shape and np.array_equal(v, ref, equal_nan=True), (t, k)
+    # ---- k{tid}.smpl.pkl / k{tid}.object.pkl
+    folders = vio.output_folders(str(tmp_path / "recon"), paths, "test-releasev2")
+    vio.save_smpl_params(folders, 1, g["in.pose"], g["in.betas"], g["in.trans"])
+    from oracle.geom_ref import project_so3
+    R = project_so3(torch.from_numpy(g["in.obj_R"]))                                # a host array is taken as projected already (see io.py)
+    vio.save_object_params(folders, 1, R, g["in.obj_t"], g["in.obj_s"])
+    for i, folder in enumerate(folders):
+        sm = pkl.load(open(os.path.join(folder, "k1.smpl.pkl"), "rb"))
+        ob = pkl.load(open(os.path.join(folder, "k1.object.pkl"), "rb"))
+        assert list(sm) == [str(x) for x in g[f"smpl{i}.order"]] and list(ob) == [str(x) for x in g[f"object{i}.order"]]
+        for k, v in sm.items():
+            ref = g[f"smpl{i}.{k}"]
+            assert np.asarray(v).dtype == ref.dtype and np.array_equal(np.asarray(v), ref), k
+        for k, v in ob.items():
+            ref = g[f"object{i}.{k}"]
+            assert np.asarray(v).shape == ref.shape and np.asarray(v).dtype == ref.dtype, k
+            assert np.allclose(np.asarray(v), ref, atol=2e-6), k
+    # ---- k{kid}.smplfit_temporal.pkl, frames without confident key points skipped
+    outfiles = [str(tmp_path / "seq" / os.path.basename(os.path.dirname(p)) / "k1.smplfit_temporal.pkl") for p in paths]
+    skip = torch.from_numpy(g["in.scores"]).sum(1) < 0.1                            # BaseFitter.skip_frame
+    assert vio.save_smplt_fits(outfiles, g["in.pose"], g["in.betas"], g["in.trans"], skip=skip) == int(g["smplt.written"].sum())
+    assert [os.path.isfile(f) for f in outfiles] == g["smplt.written"].tolist()
+    d0 = pkl.load(open(outfiles[0], "rb"))
+    assert list(d0) == [str(x) for x in g["smplt.order"]]
+    for k, v in d0.items():
+        assert v.dtype == g[f"smplt0.{k}"].dtype and np.array_equal(v, g[f"smplt0.{k}"])
