@@ -27,6 +27,7 @@ seeded synthetic checkpoint of ``vistracker_b200.synth`` and stores inputs-by-se
 * ``eval_seq.npz``          -- (``--only evalseq``) VideoPackedEvaluator.eva_seq run on an in-memory synthetic sequence (alignment windows,
   frames without a reconstruction, Chamfer on the vertices, v2v, acceleration errors).
 * ``io_formats.npz``        -- (``--only io``) what the reference's writers put on disk (save_neural_recon, save_outputs, save_results).
+* ``pack_formats.npz``      -- (``--only pack``) the reference's pack_recon.py / pack_smplt.py run on per-frame files written by this package.
 * ``smooth_small.npz``      -- (``--only smooth``) SmoothNetSMPL / SmoothNet through SMPLTSmoother / ObjrotSmoother pre- and
                                post-processing on a 90-frame synthetic trajectory, window 64, + the rotation conversions
 """
@@ -792,6 +793,76 @@ def io_goldens(out_dir: str):
     np.savez_compressed(os.path.join(out_dir, "io_formats.npz"), **out)
     print("io_formats.npz:", len(out), "entries;", "ply requests:", sorted(set(out["ply_requests"].tolist())))
 
+def pack_goldens(out_dir: str):
+    """Interoperability of the per-frame files with the reference's packers: the files are written by THIS package's
+    vistracker_b200.io (k1_densepc.npz, k1.smpl.pkl, k1.object.pkl, k1.smplfit_smoothed.pkl) and then read by the reference's own
+    preprocess/pack_recon.py:main (neural-only and full) through its ReconDataReader, and preprocess/pack_smplt.py:main.  Only the frame
+    enumeration (behave.frame_data.FrameDataReader, un-vendored) and the SMPL model files behind get_root_joint are stand-ins.
+    The packs they write are stored -> pack_formats.npz, which vistracker_b200.io.pack_recon / pack_smplt must reproduce."""
+    import tempfile
+    from argparse import Namespace
+    import joblib
+    from vistracker_b200 import io as vio
+    tmp = tempfile.mkdtemp(prefix="vt_pack_")
+    T = 5
+    frames = [f"t{i:04d}.{(41 * i) % 1000:03d}" for i in range(T)]
+    seq = "Date03_Sub03_chairwood_hand"
+
+    class FrameDataReader:                                 # behave.frame_data (the BEHAVE toolkit is not vendored by the reference)
+        def __init__(self, seq_folder, check_image=False, ext="jpg"):
+            self.seq_path, self.seq_name, self.frames = seq_folder, os.path.basename(seq_folder), list(frames)
+            self.seq_info = Namespace(get_gender=lambda: "male")
+        def __len__(self): return len(self.frames)
+        def get_frame_folder(self, idx): return os.path.join(self.seq_path, self.frames[idx])
+        def frame_time(self, idx): return self.frames[idx]
+    b = _stub("behave"); b.frame_data = _stub("behave.frame_data", FrameDataReader=FrameDataReader)
+    _stub("cv2", setNumThreads=lambda n: None)
+    root_of = lambda pose, betas, trans: (trans + 0.125).reshape(-1, 1, 3)            # stand-in for SMPL_Layer.get_root_joint (licensed model files)
+    layer = Namespace(get_root_joint=root_of)
+    _stub("lib_smpl", SMPL_Layer=lambda **kw: layer, get_smpl=lambda *a, **k: layer)
+    import preprocess.pack_recon as PR                                                # reference
+    import preprocess.pack_smplt as PS                                                # reference
+
+    rng = np.random.default_rng(51)
+    f32 = lambda *s: rng.standard_normal(s).astype(np.float32)
+    recon_root = os.path.join(tmp, "recon")
+    paths = [os.path.join("/data", seq, f, "k1.color.jpg") for f in frames]
+    pcs = {t: {"points": torch.from_numpy(f32(T, 30, 3)), "pca_axis": torch.from_numpy(f32(T, 3, 3)), "parts": torch.from_numpy(rng.integers(0, 14, (T, 30))),
+               "centers": torch.cat([torch.full((T, 3), float("nan")), torch.from_numpy(f32(T, 3))], 1), "visibility": torch.rand(T, 1)} for t in ("human", "object")}
+    pose, betas, trans = f32(T, 156), f32(T, 10), f32(T, 3)
+    from scipy.spatial.transform import Rotation
+    rot = Rotation.from_rotvec(rng.standard_normal((T, 3))).as_matrix().astype(np.float32)
+    obj_t, obj_s = f32(T, 3), np.ones(T, np.float32)
+    for name in ("test-release", "test-releasev2"):
+        folders = vio.output_folders(recon_root, paths, name)
+        vio.save_neural_recon(folders, 1, pcs)
+    vio.save_smpl_params(folders, 1, pose, betas, trans)
+    vio.save_object_params(folders, 1, rot, obj_t, obj_s)
+    out = {"frames": np.array(frames), "in.pca": pcs["object"]["pca_axis"].numpy(), "in.centers": pcs["object"]["centers"].numpy(),
+           "in.vis": pcs["object"]["visibility"].numpy(), "in.pose": pose, "in.betas": betas, "in.trans": trans, "in.rot": rot, "in.obj_t": obj_t, "in.obj_s": obj_s}
+
+    def store(tag, d):
+        out[f"{tag}.order"] = np.array(list(d))
+        for k, v in d.items():
+            if isinstance(v, list) and len(v) and not isinstance(v[0], str):
+                out[f"{tag}.{k}"], out[f"{tag}.{k}.islist"] = np.stack([np.asarray(x) for x in v], 0), np.array(True)
+            else:
+                out[f"{tag}.{k}"] = np.asarray(v)
+
+    seq_folder = os.path.join(tmp, "data", seq)
+    with contextlib.redirect_stdout(io.StringIO()), contextlib.redirect_stderr(io.StringIO()):
+        PR.main(Namespace(seq_folder=seq_folder, out=os.path.join(tmp, "packed"), recon_path=recon_root, save_name="test-release", neural_only=True, test_ids=[1]))
+        PR.main(Namespace(seq_folder=seq_folder, out=os.path.join(tmp, "packed"), recon_path=recon_root, save_name="test-releasev2", neural_only=False, test_ids=[1]))
+    store("neural", joblib.load(os.path.join(tmp, "packed", "recon_test-release", f"{seq}_k1.pkl")))
+    store("full", joblib.load(os.path.join(tmp, "packed", "recon_test-releasev2", f"{seq}_k1.pkl")))
+    # pack_smplt reads k1.smplfit_smoothed.pkl from the SEQUENCE folders
+    vio.save_smplt_fits([os.path.join(seq_folder, f, "k1.smplfit_smoothed.pkl") for f in frames], pose, betas, trans)
+    with contextlib.redirect_stdout(io.StringIO()), contextlib.redirect_stderr(io.StringIO()):
+        PS.main(Namespace(seq_folder=seq_folder, mesh_type="smoothed", out=os.path.join(tmp, "packed_smplt"), test_id=1))
+    store("smplt", joblib.load(os.path.join(tmp, "packed_smplt", f"{seq}_k1.pkl")))
+    np.savez_compressed(os.path.join(out_dir, "pack_formats.npz"), **out)
+    print("pack_formats.npz:", {k: out[k].tolist() for k in out if k.endswith(".order")})
+
 
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
@@ -828,5 +899,7 @@ if __name__ == "__main__":
         evalseq_goldens(HERE)
     if a.only == "io":                      # replaces psbody's Mesh: run on its own
         io_goldens(HERE)
+    if a.only == "pack":                    # stubs `behave.frame_data` / `lib_smpl`: run on its own
+        pack_goldens(HERE)
     if a.only == "infill":                  # stubs `behave` / `trainer`: run on its own
         infill_goldens(HERE)

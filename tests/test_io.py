@@ -190,3 +190,35 @@ def test_writers_match_what_the_reference_writes(tmp_path):
     assert list(d0) == [str(x) for x in g["smplt.order"]]
     for k, v in d0.items():
         assert v.dtype == g[f"smplt0.{k}"].dtype and np.array_equal(v, g[f"smplt0.{k}"])
+
+
+def test_sequence_packs_match_the_reference_packers(tmp_path):
+    """pack_formats.npz: what the reference's preprocess/pack_recon.py (neural-only and full) and pack_smplt.py wrote after READING the
+    per-frame files this package's writers produced.  pack_recon / pack_smplt build the same packs straight from the arrays."""
+    import joblib
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "pack_formats.npz"))
+    frames = [str(f) for f in g["frames"]]
+    T = len(frames)
+
+    def check(tag, d):
+        assert list(d) == [str(k) for k in g[f"{tag}.order"]], tag
+        for k, v in d.items():
+            ref = g[f"{tag}.{k}"]
+            if f"{tag}.{k}.islist" in g.files:
+                assert isinstance(v, list) and len(v) == T, (tag, k)
+                v = np.stack([np.asarray(x) for x in v], 0)
+            if ref.dtype.kind in "US":
+                assert np.array_equal(np.asarray(v).astype(str), ref.astype(str)), (tag, k)
+            else:
+                assert np.asarray(v).shape == ref.shape, (tag, k, np.asarray(v).shape, ref.shape)
+                assert np.allclose(np.asarray(v, dtype=np.float64), ref.astype(np.float64), atol=2e-6, equal_nan=True), (tag, k)
+
+    pca, rel, vis = g["in.pca"], g["in.centers"][:, 3:], g["in.vis"]
+    f = vio.pack_recon(str(tmp_path / "a.pkl"), frames, "male", "test-release", pca, rel, vis)
+    check("neural", joblib.load(f))
+    root = g["in.trans"] + 0.125                                                   # the stand-in of get_root_joint used when the golden was made
+    f = vio.pack_recon(str(tmp_path / "b.pkl"), frames, "male", "test-releasev2", pca, rel, vis, g["in.pose"], g["in.betas"], g["in.trans"], root,
+                       g["in.rot"], g["in.obj_t"], g["in.obj_s"])
+    check("full", joblib.load(f))
+    f = vio.pack_smplt(str(tmp_path / "c.pkl"), frames, "male", g["in.pose"], g["in.betas"], g["in.trans"])
+    check("smplt", joblib.load(f))
