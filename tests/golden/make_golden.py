@@ -28,6 +28,7 @@ seeded synthetic checkpoint of ``vistracker_b200.synth`` and stores inputs-by-se
   frames without a reconstruction, Chamfer on the vertices, v2v, acceleration errors).
 * ``io_formats.npz``        -- (``--only io``) what the reference's writers put on disk (save_neural_recon, save_outputs, save_results).
 * ``pack_formats.npz``      -- (``--only pack``) the reference's pack_recon.py / pack_smplt.py run on per-frame files written by this package.
+* ``infill_io.npz``         -- (``--only infill_io``) MotionInfillTester.save_output on a small pack.
 * ``smooth_small.npz``      -- (``--only smooth``) SmoothNetSMPL / SmoothNet through SMPLTSmoother / ObjrotSmoother pre- and
                                post-processing on a 90-frame synthetic trajectory, window 64, + the rotation conversions
 """
@@ -863,6 +864,39 @@ def pack_goldens(out_dir: str):
     np.savez_compressed(os.path.join(out_dir, "pack_formats.npz"), **out)
     print("pack_formats.npz:", {k: out[k].tolist() for k in out if k.endswith(".order")})
 
+def infill_io_goldens(out_dir: str):
+    """MotionInfillTester.save_output (interp/test_infiller.py:129-143) run unbound on a small pack (both branches: in-filled rotations,
+    and save_orig when HVOP-Net skipped the sequence) -> infill_io.npz."""
+    import tempfile
+    from argparse import Namespace
+    import joblib
+    b = _stub("behave"); b.utils = _stub("behave.utils", load_template=None); b.frame_data = _stub("behave.frame_data", FrameDataReader=object)
+    t = _stub("trainer"); t.__path__ = []; _stub("trainer.train_utils", load_checkpoint=None)
+    _stub("lib_smpl", get_smpl=None)
+    from interp.test_infiller import MotionInfillTester                               # reference
+    tmp = tempfile.mkdtemp(prefix="vt_infio_")
+    rng = np.random.default_rng(61)
+    L = 6
+    dat = {"poses": rng.standard_normal((L, 156)), "betas": rng.standard_normal((L, 10)), "trans": rng.standard_normal((L, 3)),
+           "obj_angles": rng.standard_normal((L, 3, 3)), "obj_trans": rng.standard_normal((L, 3)), "obj_scales": np.zeros(L), "gender": "male",
+           "frames": [f"t{i:04d}.000" for i in range(L)]}
+    rot = torch.from_numpy(rng.standard_normal((L, 3, 3)).astype(np.float32))
+    tr = torch.from_numpy(rng.standard_normal((L, 3)).astype(np.float32))
+    out = {"rot_pred": rot.numpy(), "trans_pred": tr.numpy()}
+    for k, v in dat.items():
+        out[f"in.{k}"] = np.asarray(v)
+    shim = Namespace(exp_name="cmf-k4-lrot")
+    for tag, kw in (("filled", dict(rot_pred=rot, trans_pred=tr)), ("orig", dict(rot_pred=None, trans_pred=None, save_orig=True))):
+        f = os.path.join(tmp, tag, "seq_k1.pkl")
+        with contextlib.redirect_stdout(io.StringIO()):
+            MotionInfillTester.save_output(shim, {k: (v.copy() if hasattr(v, "copy") else v) for k, v in dat.items()}, f, **kw)
+        d = joblib.load(f)
+        out[f"{tag}.order"] = np.array(list(d))
+        for k, v in d.items():
+            out[f"{tag}.{k}"] = np.asarray(v)
+    np.savez_compressed(os.path.join(out_dir, "infill_io.npz"), **out)
+    print("infill_io.npz:", out["filled.order"].tolist())
+
 
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
@@ -901,5 +935,7 @@ if __name__ == "__main__":
         io_goldens(HERE)
     if a.only == "pack":                    # stubs `behave.frame_data` / `lib_smpl`: run on its own
         pack_goldens(HERE)
+    if a.only == "infill_io":
+        infill_io_goldens(HERE)
     if a.only == "infill":                  # stubs `behave` / `trainer`: run on its own
         infill_goldens(HERE)

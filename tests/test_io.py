@@ -222,3 +222,21 @@ def test_sequence_packs_match_the_reference_packers(tmp_path):
     check("full", joblib.load(f))
     f = vio.pack_smplt(str(tmp_path / "c.pkl"), frames, "male", g["in.pose"], g["in.betas"], g["in.trans"])
     check("smplt", joblib.load(f))
+
+
+def test_infill_output_pack_matches_reference_save_output(tmp_path):
+    import joblib
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "infill_io.npz"))
+    dat = {k[3:]: (g[k].tolist() if k == "in.frames" else (str(g[k]) if k == "in.gender" else g[k])) for k in g.files if k.startswith("in.")}
+    dat = {k: dat[k] for k in ("poses", "betas", "trans", "obj_angles", "obj_trans", "obj_scales", "gender", "frames")}
+    # the reference receives rot_pred (real rotations) and stores the transpose; the in-filler here already returns the stored layout
+    f = vio.save_infill_output(dat, str(tmp_path / "a" / "seq_k1.pkl"), torch.from_numpy(g["rot_pred"]).transpose(1, 2), torch.from_numpy(g["trans_pred"]))
+    for tag, path in (("filled", f), ("orig", vio.save_infill_output(dat, str(tmp_path / "b" / "seq_k1.pkl")))):
+        d = joblib.load(path)
+        assert list(d) == [str(k) for k in g[f"{tag}.order"]], tag
+        for k, v in d.items():
+            ref = g[f"{tag}.{k}"]
+            if ref.dtype.kind in "US":
+                assert np.array_equal(np.asarray(v).astype(str), ref.astype(str)), (tag, k)
+            else:
+                assert np.asarray(v).shape == ref.shape and np.allclose(np.asarray(v, dtype=np.float64), ref.astype(np.float64)), (tag, k)

@@ -12,6 +12,7 @@ writes.  Pure host code: one batched device->host copy per call, then the same p
   output_folders      ``<outpath>/<seq>/<frame>/<save_name>``                              (recon/recon_fit_base.py:278-294)
   save_triplane_png / load_triplane_png   ``k{kid}.smooth_triplane.png`` with R, G, B = right, back, top (render/render_triplane_nr.py:84-85)
   save_ply / load_ply ``k{kid}.smplfit_*.ply`` meshes (psbody ``Mesh.write_ply``; read back by the triplane renderer and the test loader)
+  save_infill_output  the pack HVOP-Net hands to the joint optimisation (interp/test_infiller.py:129-143)
   packed_batch        the slices of a sequence pack for the frames of one batch (recon/recon_fit_base.py:346-370)
   pack_smplt / pack_recon / load_packed   the per-sequence joblib packs (preprocess/pack_smplt.py:45-63, preprocess/pack_recon.py:118-157)
                       written from in-memory trajectories instead of re-reading every per-frame file
@@ -253,3 +254,22 @@ def load_ply(file: str):
         else:
             raise ValueError(f"{file}: unsupported PLY format {fmt}")
     return verts, faces.reshape(-1, 3)
+
+
+def save_infill_output(dat: dict, outfile: str, obj_angles=None, obj_trans=None, exp_name: str = "cmf-k4-lrot") -> str:
+    """``MotionInfillTester.save_output`` (interp/test_infiller.py:129-143): the pack the HVOP-Net stage hands to the joint optimisation
+    (``-or smooth-hvopnet``).  ``dat`` is the input pack (``load_packed``); ``obj_angles`` [T,3,3] as the in-filler returns them (= R^T, what
+    the reference stores after its transpose) and ``obj_trans`` replace the pack's entries -- ``None`` keeps the input (the reference's
+    ``save_orig`` branch when the first clip has no visible seed frames); 'obj_scales' becomes ones and 'exp_name' is added."""
+    import joblib
+    d = dict(dat)
+    L = len(d["frames"])
+    if obj_angles is not None:
+        d["obj_angles"] = _np(obj_angles).copy()
+        if obj_trans is not None:
+            d["obj_trans"] = _np(obj_trans)
+    d["obj_scales"] = np.ones(L)
+    d["exp_name"] = exp_name
+    os.makedirs(os.path.dirname(outfile) or ".", exist_ok=True)
+    joblib.dump(d, outfile)
+    return outfile
