@@ -29,6 +29,7 @@ seeded synthetic checkpoint of ``vistracker_b200.synth`` and stores inputs-by-se
 * ``io_formats.npz``        -- (``--only io``) what the reference's writers put on disk (save_neural_recon, save_outputs, save_results).
 * ``pack_formats.npz``      -- (``--only pack``) the reference's pack_recon.py / pack_smplt.py run on per-frame files written by this package.
 * ``infill_io.npz``         -- (``--only infill_io``) MotionInfillTester.save_output on a small pack.
+* ``recon_loop.npz``        -- (``--only reconloop``) ReconFitterBehave.optimize_smpl run for 15 steps on the CPU (loss history, final parameters).
 * ``smooth_small.npz``      -- (``--only smooth``) SmoothNetSMPL / SmoothNet through SMPLTSmoother / ObjrotSmoother pre- and
                                post-processing on a 90-frame synthetic trajectory, window 64, + the rotation conversions
 """
@@ -212,10 +213,9 @@ def fit_smplt_goldens(out_dir: str):
     print("fit_smplt_small: losses", losses[0], "->", losses[-1])
 
 
-def recon_goldens(out_dir: str):
-    """forward_smpl (phase 'kpts') and forward_step (phases 'object only', 'joint') of the UNMODIFIED reference fitter classes,
-    called unbound on CPU with a bare ``self`` (recon/recon_fit_behave.py:467-513, recon/recon_fit_trivis_full.py:193-270).
-    pytorch3d's chamfer_distance is not installable -> the contact term goes through oracle.geom_ref.chamfer_ragged."""
+def _recon_setup():
+    """The UNMODIFIED reference fitter classes on the CPU with a bare ``self``: import stubs for the un-vendored third-party packages, the
+    reference SIF-Net with the seeded synthetic checkpoint, a synthetic SMPL-H layer, the seeded problem of tests/recon_problem.py."""
     from argparse import Namespace
     for n in ("trimesh", "igl", "open3d", "zstd", "neural_renderer"):
         _stub(n)
@@ -278,6 +278,14 @@ def recon_goldens(out_dir: str):
     F.camera, F.net_in_size, F.debug, F.z_0, F.device, F.obj_scale = KinectColorCamera(1200), 512, False, 2.2, "cpu", 1.0
     F.part_labels, F.collision_loss, F.args = d["labels"], False, Namespace(model_name="chore-triplane-vis")
     F.part_names = [str(i) for i in range(14)]
+    return d, net, make_smpl, F, B
+
+
+def recon_goldens(out_dir: str):
+    """forward_smpl (phase 'kpts') and forward_step (phases 'object only', 'joint') of the UNMODIFIED reference fitter classes,
+    called unbound on CPU with a bare ``self`` (recon/recon_fit_behave.py:467-513, recon/recon_fit_trivis_full.py:193-270).
+    pytorch3d's chamfer_distance is not installable -> the contact term goes through oracle.geom_ref.chamfer_ragged."""
+    d, net, make_smpl, F, B = _recon_setup()
     weights = F.get_loss_weights()
     qd = {"crop_center": d["crop"], "body_center": d["body_center"]}
     out = {}
@@ -897,6 +905,32 @@ def infill_io_goldens(out_dir: str):
     np.savez_compressed(os.path.join(out_dir, "infill_io.npz"), **out)
     print("infill_io.npz:", out["filled.order"].tolist())
 
+def recon_loop_goldens(out_dir: str):
+    """The SMPL refinement LOOP of the reference -- ReconFitterBehave.optimize_smpl (recon/recon_fit_behave.py:393-465: phase schedule, the
+    two Adam set-ups, the decay, the early-stop rule) -- executed on the CPU for 1 + 1 + 1 + 2 outer iterations of 3 steps on the seeded
+    problem; every step's total loss and the final parameters are recorded.  -> recon_loop.npz"""
+    d, net, make_smpl, F, B = _recon_setup()
+    qd = {"crop_center": d["crop"], "body_center": d["body_center"]}
+    S = make_smpl()
+    dd = {"part_labels": d["labels"][None].repeat(B, 1), "net": net, "query_dict": qd, "pose_init": d["pose_init"], "body_kpts": d["body_kpts"]}
+    hist = []
+    orig_sum = F.sum_dict
+
+    def recording_sum(loss_dict, weight_dict, it):
+        v = orig_sum(loss_dict, weight_dict, it)
+        hist.append(float(v))
+        return v
+    F.sum_dict = recording_sum
+    F.split_smpl = lambda smpl: smpl                     # the split container is built above (its constructor reads the licensed model files)
+    F.copy_smpl_params = lambda split, smpl: split
+    F.get_smpl_height = lambda smpl: torch.ones(B)
+    with contextlib.redirect_stdout(io.StringIO()), contextlib.redirect_stderr(io.StringIO()):
+        S2, _ = F.optimize_smpl(S, dd, iter_for_betas=1, iter_for_pose=1, iter_for_kpts=1, steps_per_iter=3, max_iter=2)
+    out = {"hist": np.array(hist, np.float64), "pose": torch.cat([S2.global_pose, S2.body_pose, S2.hand_pose], 1).detach().numpy().copy(),
+           "betas": torch.cat([S2.top_betas, S2.other_betas], 1).detach().numpy().copy(), "trans": S2.trans.detach().numpy().copy()}
+    np.savez_compressed(os.path.join(out_dir, "recon_loop.npz"), **out)
+    print("recon_loop.npz: steps", len(hist), "losses", hist[0], "->", hist[-1])
+
 
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
@@ -935,6 +969,8 @@ if __name__ == "__main__":
         io_goldens(HERE)
     if a.only == "pack":                    # stubs `behave.frame_data` / `lib_smpl`: run on its own
         pack_goldens(HERE)
+    if a.only == "reconloop":
+        recon_loop_goldens(HERE)
     if a.only == "infill_io":
         infill_io_goldens(HERE)
     if a.only == "infill":                  # stubs `behave` / `trainer`: run on its own

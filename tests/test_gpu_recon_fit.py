@@ -100,3 +100,19 @@ def test_optimisation_loops_run_and_reduce_the_loss(ctx):
     assert "trans_init" in dd and "df_obj_h" in dd
     Rf = fitter.final_rotation(R_out)
     assert rel_err((Rf @ Rf.transpose(1, 2)).cpu(), torch.eye(3).expand(B, 3, 3)) < 1e-5
+
+
+@pytest.mark.xfail(strict=False, reason="added after the round's GPU budget was spent: first B200 run of this comparison happens at round end")
+def test_optimize_smpl_loop_follows_the_reference_loop(ctx, golden):
+    """The whole SMPL refinement loop (phase schedule, both Adam set-ups, decay, early stop) against the reference's own
+    ReconFitterBehave.optimize_smpl executed on the CPU (tests/golden/recon_loop.npz: 1 + 1 + 1 + 2 outer iterations of 3 steps)."""
+    d, fitter, make_smpl = ctx
+    g = golden("recon_loop.npz")
+    c = lambda t: t.cuda()
+    dd = {"part_labels": c(d["labels"])[None].repeat(B, 1), "query_dict": {"crop_center": c(d["crop"]), "body_center": c(d["body_center"])},
+          "pose_init": c(d["pose_init"]), "body_kpts": c(d["body_kpts"])}
+    smpl, hist = fitter.optimize_smpl(make_smpl(), dd, iter_for_betas=1, iter_for_pose=1, iter_for_kpts=1, steps_per_iter=3, max_iter=2)
+    assert len(hist) == len(g["hist"])                                            # same early stop
+    assert rel_err(np.asarray(hist), g["hist"]) < 1e-3
+    assert rel_err(smpl.pose.detach().cpu(), g["pose"]) < 1e-3 and rel_err(smpl.trans.detach().cpu(), g["trans"]) < 1e-3
+    assert rel_err(smpl.betas.detach().cpu(), g["betas"]) < 1e-3
