@@ -68,6 +68,14 @@ def test_product_never_touches_the_oracle():
                 assert "oracle/" not in text and "import_module(\"oracle" not in text, f
 
 
+def test_tools_do_not_touch_the_oracle_either():
+    """tools/ are timing / integration drivers of the product path: no oracle imports, no test-helper imports that pull it in."""
+    for f in os.listdir(os.path.join(ROOT, "tools")):
+        if f.endswith(".py"):
+            text = open(os.path.join(ROOT, "tools", f)).read()
+            assert not re.search(r"^\s*(from|import)\s+(oracle|fit_problem|recon_problem)\b", text, flags=re.M), f
+
+
 def test_missing_library_fails_loudly(monkeypatch, tmp_path):
     from vistracker_b200 import _lib
     monkeypatch.setattr(_lib, "_lib", None)

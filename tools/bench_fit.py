@@ -13,8 +13,8 @@ import numpy as np
 import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
-from fit_problem import load_assets  # noqa: E402
+sys.path.insert(0, ROOT)
+from _inputs import load_assets  # noqa: E402
 from vistracker_b200 import CHORETriplaneVisibility, default_options, resolve_dims  # noqa: E402
 from vistracker_b200.generator import GeneratorTriplaneVis  # noqa: E402
 from vistracker_b200.recon_fit import Priors, ReconFitterTriVisFull, SMPLParams  # noqa: E402

@@ -12,7 +12,7 @@ import numpy as np
 import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, ROOT)
 from vistracker_b200 import CHORETriplaneVisibility, default_options, resolve_dims  # noqa: E402
 from vistracker_b200.synth import synthetic_frames, synthetic_state_dict  # noqa: E402
 from vistracker_b200.synth_smpl import synthetic_motion, synthetic_smplh  # noqa: E402
@@ -80,7 +80,7 @@ row("filter (2 encoders, whole launch plan)", ms, 8, "frames", None, 613.46e9, "
 
 # ---------------------------------------------------------------- SMPL-H layer, landmarks, SMPL-T fit step
 from vistracker_b200.smpl import LandmarkRegressor, SMPL_Layer  # noqa: E402
-from fit_problem import load_assets, synthetic_fit_problem  # noqa: E402
+from _inputs import load_assets, synthetic_fit_problem  # noqa: E402
 a, reg = load_assets()
 model = synthetic_smplh(seed=3)
 layer = SMPL_Layer.from_buffers(model, model["parents"], dev)

@@ -22,8 +22,8 @@ import numpy as np
 import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
-from fit_problem import load_assets, synthetic_fit_problem  # noqa: E402
+sys.path.insert(0, ROOT)
+from _inputs import load_assets, synthetic_fit_problem  # noqa: E402
 from vistracker_b200 import CHORETriplaneVisibility, default_options, io as vio, parallel, resolve_dims  # noqa: E402
 from vistracker_b200.evaluate import evaluate_sequence  # noqa: E402
 from vistracker_b200.fit_smplt import SMPLHFitter30fps, SMPLHFitterSmoothed  # noqa: E402
