@@ -30,6 +30,7 @@ seeded synthetic checkpoint of ``vistracker_b200.synth`` and stores inputs-by-se
 * ``pack_formats.npz``      -- (``--only pack``) the reference's pack_recon.py / pack_smplt.py run on per-frame files written by this package.
 * ``infill_io.npz``         -- (``--only infill_io``) MotionInfillTester.save_output on a small pack.
 * ``recon_loop.npz``        -- (``--only reconloop``) ReconFitterBehave.optimize_smpl run for 15 steps on the CPU (loss history, final parameters).
+* ``driver_small.npz``      -- (``--only driver``) ReconFitterBase.scale_body_kpts, ReconFitterBehave.combine_mini_batches.
 * ``smooth_small.npz``      -- (``--only smooth``) SmoothNetSMPL / SmoothNet through SMPLTSmoother / ObjrotSmoother pre- and
                                post-processing on a 90-frame synthetic trajectory, window 64, + the rotation conversions
 """
@@ -931,6 +932,47 @@ def recon_loop_goldens(out_dir: str):
     np.savez_compressed(os.path.join(out_dir, "recon_loop.npz"), **out)
     print("recon_loop.npz: steps", len(hist), "losses", hist[0], "->", hist[-1])
 
+def driver_goldens(out_dir: str):
+    """Host arithmetic of the fit_recon driver, from the reference's own methods called unbound on the CPU: ReconFitterBase.scale_body_kpts
+    (recon/recon_fit_base.py:397-409) and ReconFitterBehave.combine_mini_batches (recon/recon_fit_behave.py:152-183).  -> driver_small.npz"""
+    from argparse import Namespace
+    for n in ("trimesh", "igl", "open3d", "zstd", "neural_renderer"):
+        _stub(n)
+    _stub("pytorch3d"); _stub("pytorch3d.loss", chamfer_distance=None)
+    _stub("pytorch3d.structures", Pointclouds=object, Meshes=None); _stub("pytorch3d.ops", knn_points=None, sample_points_from_meshes=None)
+    _stub("mesh_intersection"); _stub("mesh_intersection.bvh_search_tree", BVH=object); _stub("mesh_intersection.loss")
+    _stub("detectron2"); _stub("detectron2.structures", BitMasks=object, BoxMode=object, Boxes=object); _stub("detectron2.structures.boxes", BoxMode=object)
+    for m in list(sys.modules):
+        if m.startswith(("psbody", "pytorch3d", "detectron2", "mesh_intersection", "skimage", "chumpy")):
+            sys.modules[m].__path__ = []
+    sys.modules["psbody.mesh"].MeshViewers = object
+    import recon.recon_fit_base as MB                                                  # reference
+    import recon.recon_fit_behave as MBH                                               # reference
+    rng = np.random.default_rng(71)
+    B = 4
+    kpts = torch.from_numpy(np.concatenate([rng.uniform(0, 2048, (B, 25, 2)), rng.random((B, 25, 1))], -1).astype(np.float32))
+    rs, cs = torch.from_numpy(rng.uniform(0.8, 1.3, B).astype(np.float32)), torch.from_numpy(rng.uniform(0.7, 1.4, B).astype(np.float32))
+    cc = torch.from_numpy(rng.uniform(600, 1400, (B, 2)).astype(np.float32))
+    shim = Namespace(camera=Namespace(crop_size=1200), net_in_size=512)
+    out = {"kpts": kpts.numpy(), "resize_scale": rs.numpy(), "crop_scale": cs.numpy(), "crop_center": cc.numpy(),
+           "scaled": MB.ReconFitterBase.scale_body_kpts(shim, kpts, rs, cs, cc).numpy(),
+           "scaled_unit": MB.ReconFitterBase.scale_body_kpts(shim, kpts, torch.ones(B), torch.ones(B), cc).numpy()}
+    mk = lambda b, n: {t: {"points": torch.from_numpy(rng.standard_normal((b, n, 3)).astype(np.float32)), "parts": torch.from_numpy(rng.integers(0, 14, (b, n))).float(),
+                            "centers": torch.from_numpy(rng.standard_normal((b, 6)).astype(np.float32)), "pca_axis": torch.from_numpy(rng.standard_normal((b, 3, 3)).astype(np.float32)),
+                            "visibility": torch.from_numpy(rng.random((b,)).astype(np.float32))} for t in ("human", "object")}
+    pcs = [mk(2, 50), mk(1, 40), mk(2, 47)]
+    comb = MBH.ReconFitterBehave.combine_mini_batches(None, pcs, 40)
+    for i, pc in enumerate(pcs):
+        for t in pc:
+            for k, v in pc[t].items():
+                out[f"pc{i}.{t}.{k}"] = v.numpy()
+    for t in comb:
+        out[f"comb.{t}.order"] = np.array(list(comb[t]))
+        for k, v in comb[t].items():
+            out[f"comb.{t}.{k}"] = v.numpy()
+    np.savez_compressed(os.path.join(out_dir, "driver_small.npz"), **out)
+    print("driver_small.npz:", out["scaled"].shape, {k: out[k].shape for k in out if k.startswith("comb.human.") and not k.endswith("order")})
+
 
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
@@ -971,6 +1013,8 @@ if __name__ == "__main__":
         pack_goldens(HERE)
     if a.only == "reconloop":
         recon_loop_goldens(HERE)
+    if a.only == "driver":
+        driver_goldens(HERE)
     if a.only == "infill_io":
         infill_io_goldens(HERE)
     if a.only == "infill":                  # stubs `behave` / `trainer`: run on its own

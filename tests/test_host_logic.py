@@ -96,3 +96,19 @@ def test_roi_setup_arithmetic_matches_reference_functions():
     assert bool((keep[0][ref[0] > 0] == 1).all()) and float(keep[0].min()) == 0.0          # person-only pixels are ignored, object pixels kept
     side = 52 * 1200 / 128
     assert abs(float(K[0, 0, 0]) - 979.7844 / side) < 1e-6 and abs(float(K[1, 0, 2]) - (1018.952 - (900 - 600 + (100 - 26) * 1200 / 128)) / side) < 1e-5
+
+
+def test_driver_arithmetic_matches_reference_methods():
+    """scale_body_kpts and combine_mini_batches against the reference's own methods (tests/golden/driver_small.npz)."""
+    import os
+    from vistracker_b200.recon_driver import combine_mini_batches, scale_body_kpts
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "driver_small.npz"))
+    t = lambda k: torch.from_numpy(g[k])
+    got = scale_body_kpts(t("kpts"), t("crop_center"), resize_scale=t("resize_scale"), crop_scale=t("crop_scale"))
+    assert np.allclose(got.numpy(), g["scaled"], rtol=1e-6, atol=1e-4)
+    assert np.allclose(scale_body_kpts(t("kpts"), t("crop_center")).numpy(), g["scaled_unit"], rtol=1e-6, atol=1e-4)
+    pcs = [{tt: {k: t(f"pc{i}.{tt}.{k}") for k in ("points", "parts", "centers", "pca_axis", "visibility")} for tt in ("human", "object")} for i in range(3)]
+    comb = combine_mini_batches(pcs, 40)
+    for tt in ("human", "object"):
+        for k in ("points", "parts", "centers", "pca_axis", "visibility"):
+            assert tuple(comb[tt][k].shape) == g[f"comb.{tt}.{k}"].shape and np.array_equal(comb[tt][k].numpy(), g[f"comb.{tt}.{k}"]), (tt, k)
