@@ -488,6 +488,8 @@ def infill_goldens(out_dir: str):
     src = (q * np.array([[1.0], [0.6], [0.3]])).astype(np.float32)                    # rows = scaled, orthogonal template axes
     tgt = np.stack([np.linalg.qr(rng.standard_normal((3, 3)))[0] @ src + 0.05 * rng.standard_normal((3, 3)) for _ in range(40)]).astype(np.float32)
     tgt[3] *= -1                                                                      # a reflected prediction: the det fix of project_so3
+    tmpl = (rng.standard_normal((300, 3)) * np.array([0.5, 0.2, 0.35])) @ np.linalg.qr(rng.standard_normal((3, 3)))[0] + np.array([0.1, -0.2, 0.05])
+    out.update({"pca_template": tmpl, "pca_components_installed_sklearn": PCAUtil.compute_pca(tmpl)})
     out.update({"pca_src": src, "pca_tgt": tgt,
                 "pca_R": PCAUtil.init_object_orientation(torch.from_numpy(tgt), torch.stack([torch.from_numpy(src)] * 40, 0)).numpy()})
 

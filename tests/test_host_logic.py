@@ -112,3 +112,21 @@ def test_driver_arithmetic_matches_reference_methods():
     for tt in ("human", "object"):
         for k in ("points", "parts", "centers", "pca_axis", "visibility"):
             assert tuple(comb[tt][k].shape) == g[f"comb.{tt}.{k}"].shape and np.array_equal(comb[tt][k].numpy(), g[f"comb.{tt}.{k}"]), (tt, k)
+
+
+def test_compute_pca_matches_sklearn_conventions():
+    """geom.compute_pca: sign='v' reproduces PCAUtil.compute_pca as the reference computes it with the installed scikit-learn (golden),
+    sign='u' the pre-1.5 svd_flip rule; both span the same axes."""
+    import os
+    from sklearn.utils.extmath import svd_flip
+    from vistracker_b200.geom import compute_pca
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "infill_small.npz"))
+    X = g["pca_template"]
+    v = compute_pca(X, sign="v")
+    assert np.abs(v - g["pca_components_installed_sklearn"]).max() < 1e-10
+    U, S, Vt = np.linalg.svd(X - X.mean(0), full_matrices=False)
+    _, Vu = svd_flip(U, Vt, u_based_decision=True)
+    u = compute_pca(torch.from_numpy(X), sign="u")
+    assert np.abs(u - Vu).max() < 1e-10
+    assert np.abs(np.abs(u @ v.T) - np.eye(3)).max() < 1e-9 and np.abs(u @ u.T - np.eye(3)).max() < 1e-10
+    assert compute_pca(X).tolist() == u.tolist()                                   # default: the convention the checkpoints were trained with

@@ -154,3 +154,24 @@ def apply_similarity(points: torch.Tensor, R: torch.Tensor, t: torch.Tensor, sca
     with torch.cuda.device(p.device):
         _lib.call("vt_similarity_apply", _lib.ptr(p), n, B, _lib.ptr(R), _lib.ptr(t), _lib.ptr(scale), _lib.ptr(out), _lib.stream_ptr())
     return out[0] if single else out
+
+
+def compute_pca(points, sign: str = "u"):
+    """``PCAUtil.compute_pca`` / ``compute_pca_init`` (recon/pca_util.py:12-24, recon/recon_fit_base.py:130-144): the three principal axes of
+    the object template's vertices as rows (``sklearn.decomposition.PCA(3).fit(points).components_``) -- the ``src_axis`` of
+    ``init_object_orientation``.  Host arithmetic, once per object.  scikit-learn fixes the sign of every axis with ``svd_flip``; its rule
+    changed in scikit-learn 1.5: ``sign='u'`` (before: the sample with the largest absolute projection on the axis projects positively --
+    what the released checkpoints were trained against, requirements.txt does not pin the version) or ``sign='v'`` (since: the largest
+    absolute coordinate of the axis is positive)."""
+    import numpy as np
+    X = np.asarray(points.detach().cpu() if torch.is_tensor(points) else points, dtype=np.float64)
+    Xc = X - X.mean(0)
+    U, S, Vt = np.linalg.svd(Xc, full_matrices=False)
+    if sign == "u":
+        s = np.sign(U[np.argmax(np.abs(U), axis=0), np.arange(U.shape[1])])
+    elif sign == "v":
+        s = np.sign(Vt[np.arange(Vt.shape[0]), np.argmax(np.abs(Vt), axis=1)])
+    else:
+        raise ValueError("sign must be 'u' or 'v'")
+    s[s == 0] = 1
+    return Vt * s[:, None]
