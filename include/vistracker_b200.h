@@ -260,6 +260,69 @@ int vt_chamfer_fwd(const float* x, const int* x_off, const float* y, const int* 
 int vt_chamfer_bwd(const float* x, const int* x_off, const float* y, const int* y_off, int N, const int* nn_x, const int* nn_y,
                    const float* g_loss, float* gx, float* gy, void* stream);
 
+/* ---- joint optimisation steps as fixed kernel sequences: ReconFitterBehave.optimize_smpl / forward_smpl (recon/recon_fit_behave.py:393-513)
+ *      and ReconFitterTriVisFull.optimize_smpl_object / forward_step (recon/recon_fit_trivis_full.py:124-391).  State on the device:
+ *        ctrl  float[vt_recon_ctrl_words()]: [0..15] per-term weights ALREADY divided by (1 + decay) (0 = the term is not in this phase's
+ *              loss_dict); [16] lr of the first parameter group, [17] lr of the second, [18] phase, [19] early-stop tolerance, [20] early-stop
+ *              window open (0/1), [21] temporal multiplier (10 in the joint phase, recon_fit_trivis_full.py:386-388), [22] noise seed (bits);
+ *              [32] Adam step count, [33] next history row, [34] stopped (0/1), [35] previous total loss (fp32), [36] noise draw counter.
+ *              The host rewrites words [0..31] when the schedule changes and zeroes [32..] when a loop / a new optimiser starts.
+ *        acc   double[8]  per-step sums of the unweighted terms (zeroed by vt_recon_end_step)
+ *        hist  double[max_hist][vt_recon_hist_ld()]: term means (NaN where the weight is 0), [14] weighted total, [15] Adam step.
+ *      Term slots, SMPL refinement: 0 df_h, 1 pose, 2 hand, 3 part, 4 pinit, 5 j2d, 6 stemp; object phases: 0 otemp, 1 ovtemp, 2 mask,
+ *      3 scale, 4 trans, 5 object, 6 contact.  Once the early stop has fired (ctrl[34]) the Adam and end-step kernels leave all state
+ *      untouched, so replays the host had already queued are no-ops. ---- */
+int vt_recon_ctrl_words(void);
+int vt_recon_hist_ld(void);
+/* cudaMemsetAsync(p, 0, bytes) on the caller's stream. */
+int vt_zero(void* p, long long bytes, void* stream);
+/* x[B][n_points][3]: second / first difference smoothness over the batch axis (temporal_loss_smpl, recon_fit_trivis_full.py:170-177;
+ * temporal_loss_joint, :379-391; skipped when B < 4) with weights ctrl[iw2] / ctrl[iw1] (-1 = absent; use_k: times ctrl[21]) accumulated in
+ * acc[slot2] / acc[slot1], plus up to two per-point terms from vt_query_losses_tc: g[B][n][3] (overwritten) = temporal gradients +
+ * ctrl[iwA] frameA[b] gA / denA + ctrl[iwB] gB / denB, acc[slotA] += frameA[b] valsA[b][n] (frameA NULL = 1), acc[slotB] += valsB[b][n]. */
+int vt_recon_point_terms(const float* x, int B, int n_points, int iw2, int iw1, int slot2, int slot1, int use_k, const float* valsA,
+                         const float* gA, const float* frameA, int iwA, int slotA, float denA, const float* valsB, const float* gB, int iwB,
+                         int slotB, float denB, const float* ctrl, float* g, double* acc, void* stream);
+/* projection_loss (recon/recon_fit_base.py:787-802): J[B][25][3] into the network-input crop, kpts[B][25][3] = (x, y, confidence);
+ * cam6 (host) = {fx_px, fy_px, cx_px, cy_px, crop_size, net_input_size}; gJ = ctrl[5] * d j2d / dJ; acc[5] += sum. */
+int vt_recon_kpts(const float* J, const float* kpts, const float* crop_center, int B, int L, const float* cam6, const float* ctrl, float* gJ,
+                  double* acc, void* stream);
+/* compute_prior_loss (recon_fit_base.py:625-638) + the pinit term (recon_fit_behave.py:486-487): pose[B][156], pose_init[B][69];
+ * g_pose[B][156] overwritten with the gradient of ctrl[1] 'pose' + ctrl[4] 'pinit' (the hand prior is value-only). */
+int vt_recon_pose_terms(const float* pose, const float* pose_init, int B, const float* body_mean, const float* body_prec, const float* lh_mean,
+                        const float* lh_prec, const float* rh_mean, const float* rh_prec, const float* ctrl, float* g_pose, double* acc,
+                        void* stream);
+/* torch.optim.Adam (defaults) on the parameters of the current phase: 0 = [top_betas, trans], 1 = [trans, global_pose, body_pose, top_betas,
+ * other_betas] (recon_fit_behave.py:402,426-432); m, v: float[B][169]. */
+int vt_recon_adam_smpl(float* pose, float* betas, float* trans, const float* g_pose_a, const float* g_pose_b, const float* g_betas,
+                       const float* g_trans, float* m, float* v, int B, const float* ctrl, void* stream);
+/* Adam on obj_R[B][9] (lr ctrl[16]; skipped in phase 2 = 'joint') and obj_t[B][3] (lr ctrl[17]) (recon_fit_trivis_full.py:300-309,339,347);
+ * m, v: float[B][12]. */
+int vt_recon_adam_obj(float* obj_R, float* obj_t, const float* g_R, const float* g_t, float* m, float* v, int B, const float* ctrl, void* stream);
+/* Close a step: term k = acc[k] / div[k] (host array of n_terms doubles; the term in contact_slot is read from *contact_val instead, -1 = none),
+ * fp32 weighted total, history row, the early-stop predicate `abs(prev - loss) / prev < prev * tol` on fp32 values (recon_fit_behave.py:452,
+ * recon_fit_trivis_full.py:371), counters, acc zeroed. */
+int vt_recon_end_step(double* acc, int n_terms, const double* div, int contact_slot, const float* contact_val, float* ctrl, double* hist,
+                      int max_hist, void* stream);
+/* decopose_axis (recon_fit_base.py:461-469) input: M = obj_R + 1e-4 * U(0,1); noise[B][9] replays given draws, NULL draws them on the device
+ * (Philox4x32-10 keyed on ctrl[22], counter ctrl[36]); noise_out (optional) receives the draws used. */
+int vt_recon_obj_noise(const float* obj_R, const float* noise, int B, const float* ctrl, float* M, float* noise_out, void* stream);
+/* transform_obj_verts (recon_fit_base.py:455-459), row vectors: out[b][n] = (P[n] R[b] + t[b]) * s[b]; P is [N][3] (per_frame 0) or [B][N][3];
+ * and its backward: gR[B][9] (+)= s P^T g, gt[B][3] (+)= s sum_n g. */
+int vt_recon_obj_transform(const float* P, int per_frame, const float* R, const float* t, const float* s, int B, int N, float* out, void* stream);
+int vt_recon_obj_transform_bwd(const float* P, int per_frame, const float* g, const float* s, int B, int N, int accumulate, float* gR, float* gt,
+                               void* stream);
+/* SilLossROI.forward + compute_mask_loss (recon/obj_pose_roi.py:183-202, recon_fit_trivis_full.py:179-184) on a rendered alpha[B][S][S]:
+ * acc[2] += occ[b] sum_px (keep alpha - ref)^2, g_alpha = ctrl[2] occ[b] / B * 2 (keep alpha - ref) keep. */
+int vt_recon_sil_loss(const float* alpha, const float* keep, const float* ref, const float* occ, int B, int image_size, const float* ctrl,
+                      float* g_alpha, double* acc, void* stream);
+/* 'scale' = mean (obj_s - s0)^2 (value only) and, with_trans, 'trans' = mean (obj_t - t_init)^2 whose gradient is ADDED to gt[B][3]. */
+int vt_recon_obj_small_terms(const float* obj_t, const float* t_init, const float* obj_s, float s0, int B, int with_trans, const float* ctrl,
+                             float* gt, double* acc, void* stream);
+/* dst[n][3] = src[idx[n]][3]; dst[idx[n]][3] += src[n][3] (the contact sets of compute_contact_loss, recon_fit_trivis_full.py:405-449). */
+int vt_recon_gather_rows(const float* src, const long long* idx, int n, float* dst, void* stream);
+int vt_recon_scatter_add_rows(const float* src, const long long* idx, int n, float* dst, void* stream);
+
 /* ---- rasteriser with neural_renderer semantics (third-party, un-vendored: restated from the upstream algorithm, PARITY
  *      UNPINNED): silhouettes for SilLossROI (recon/obj_pose_roi.py:87-94,183-202) and orthographic depth / occupancy for the
  *      triplane renderings (render/render_triplane_nr.py:25-30,88-110).  fill_back = True, near 0.1, far 100, no anti-aliasing. ---- */

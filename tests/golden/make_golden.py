@@ -29,7 +29,8 @@ seeded synthetic checkpoint of ``vistracker_b200.synth`` and stores inputs-by-se
 * ``io_formats.npz``        -- (``--only io``) what the reference's writers put on disk (save_neural_recon, save_outputs, save_results).
 * ``pack_formats.npz``      -- (``--only pack``) the reference's pack_recon.py / pack_smplt.py run on per-frame files written by this package.
 * ``infill_io.npz``         -- (``--only infill_io``) MotionInfillTester.save_output on a small pack.
-* ``recon_loop.npz``        -- (``--only reconloop``) ReconFitterBehave.optimize_smpl run for 15 steps on the CPU (loss history, final parameters).
+* ``recon_loop.npz``        -- (``--only reconloop``) ReconFitterBehave.optimize_smpl run unpatched on the CPU, two schedules (per-step terms, totals, final parameters, scale).
+* ``recon_obj_loop.npz``    -- (``--only reconobjloop``) ReconFitterTriVisFull.optimize_smpl_object run on the CPU through all three phases.
 * ``driver_small.npz``      -- (``--only driver``) ReconFitterBase.scale_body_kpts, ReconFitterBehave.combine_mini_batches.
 * ``smooth_small.npz``      -- (``--only smooth``) SmoothNetSMPL / SmoothNet through SMPLTSmoother / ObjrotSmoother pre- and
                                post-processing on a 90-frame synthetic trajectory, window 64, + the rotation conversions
@@ -908,31 +909,219 @@ def infill_io_goldens(out_dir: str):
     np.savez_compressed(os.path.join(out_dir, "infill_io.npz"), **out)
     print("infill_io.npz:", out["filled.order"].tolist())
 
+def _unsplit_container(d, L, B):
+    """A ``SMPLPyTorchWrapperBatch`` (lib_smpl/wrapper_pytorch.py:23-70) as ``SMPLHGenerator.get_smplh`` hands it to the fitters, without its
+    constructor (which reads the licensed model file): pose / betas / trans / offsets Parameters + the synthetic SMPL-H layer."""
+    from lib_smpl.wrapper_pytorch import SMPLPyTorchWrapperBatch
+    from lib_smpl.body_landmark import load_regressors
+    S = SMPLPyTorchWrapperBatch.__new__(SMPLPyTorchWrapperBatch); torch.nn.Module.__init__(S)
+    P = torch.nn.Parameter
+    S.model_root, S.hands, S.device, S.gender = "synthetic", True, "cpu", "male"
+    S.betas, S.pose, S.trans = P(d["betas"].clone()), P(d["pose"].clone()), P(d["trans"].clone())
+    S.offsets = P(torch.zeros(B, 6890, 3)); S.smpl = L; S.faces = torch.zeros(1, 3, dtype=torch.long)
+    S.body25_reg_torch, S.face_reg_torch, S.hand_reg_torch = load_regressors("assets", batch_size=B)
+    return S
+
+
+def _real_split(L):
+    """Let the reference's own ``split_smpl`` -> ``SMPLPyTorchWrapperBatchSplitParams.from_smpl`` run (lib_smpl/wrapper_pytorch.py:206-226):
+    only the two things its constructor fetches from licensed / configured paths are redirected (the SMPL layer, the regressor folder)."""
+    import lib_smpl.wrapper_pytorch as W
+    from lib_smpl.body_landmark import load_regressors
+    W.SMPL_Layer = lambda **kw: L
+    W.load_regressors = lambda root, batch_size=5: load_regressors("assets", batch_size=batch_size)
+
+
 def recon_loop_goldens(out_dir: str):
-    """The SMPL refinement LOOP of the reference -- ReconFitterBehave.optimize_smpl (recon/recon_fit_behave.py:393-465: phase schedule, the
-    two Adam set-ups, the decay, the early-stop rule) -- executed on the CPU for 1 + 1 + 1 + 2 outer iterations of 3 steps on the seeded
-    problem; every step's total loss and the final parameters are recorded.  -> recon_loop.npz"""
+    """The SMPL refinement LOOP of the reference -- ReconFitterBehave.optimize_smpl (recon/recon_fit_behave.py:393-465: split_smpl, phase
+    schedule, the two Adam set-ups, the decay, the early-stop rule on fp32 tensors, get_smpl_height, copy_smpl_params) -- executed UNPATCHED on
+    the CPU on the seeded problem, starting from the un-split container the driver passes.  Two runs: 'a' = 1 + 1 + 1 + 2 outer iterations of 3
+    steps (stops at step 11), 'b' = 1 + 1 + 1 + 12 outer iterations of 2 steps.  Per step: every loss term and the total; at the end the
+    parameters of the RETURNED container, the height ratio, and whether the split parameters aliased the caller's storage (they do: from_smpl
+    wraps views of smpl.pose.data / betas.data, so the other-betas updates survive copy_smpl_params).  -> recon_loop.npz"""
     d, net, make_smpl, F, B = _recon_setup()
+    L = make_smpl().smpl
+    _real_split(L)
     qd = {"crop_center": d["crop"], "body_center": d["body_center"]}
-    S = make_smpl()
-    dd = {"part_labels": d["labels"][None].repeat(B, 1), "net": net, "query_dict": qd, "pose_init": d["pose_init"], "body_kpts": d["body_kpts"]}
-    hist = []
-    orig_sum = F.sum_dict
+    names = ["df_h", "pose", "hand", "part", "pinit", "j2d", "stemp"]
+    out = {"term_names": np.array(names)}
+    for tag, kw in (("a", dict(steps_per_iter=3, max_iter=2)), ("b", dict(steps_per_iter=2, max_iter=12))):
+        S = _unsplit_container(d, L, B)
+        dd = {"part_labels": d["labels"][None].repeat(B, 1), "net": net, "query_dict": qd, "pose_init": d["pose_init"], "body_kpts": d["body_kpts"]}
+        hist, terms, splits = [], [], []
+        orig_sum, orig_fwd, orig_split = F.sum_dict, F.forward_smpl, F.split_smpl
+
+        def recording_sum(loss_dict, weight_dict, it):
+            v = orig_sum(loss_dict, weight_dict, it)
+            hist.append(float(v))
+            return v
+
+        def recording_fwd(smpl, data_dict, phase):
+            ld = orig_fwd(smpl, data_dict, phase)
+            terms.append([float(ld[k]) if k in ld else np.nan for k in names])
+            return ld
+
+        def recording_split(smpl):
+            sp = orig_split(smpl)
+            splits.append(sp)
+            return sp
+        F.sum_dict, F.forward_smpl, F.split_smpl = recording_sum, recording_fwd, recording_split
+        try:
+            with contextlib.redirect_stdout(io.StringIO()), contextlib.redirect_stderr(io.StringIO()):
+                S2, scale = F.optimize_smpl(S, dd, iter_for_betas=1, iter_for_pose=1, iter_for_kpts=1, **kw)
+        finally:
+            del F.sum_dict, F.forward_smpl, F.split_smpl
+        sp = splits[0]
+        alias = bool(sp.other_betas.data_ptr() == S.betas.data[:, 2:].data_ptr() and sp.body_pose.data_ptr() == S.pose.data[:, 3:].data_ptr())
+        h = np.array(hist, np.float64)
+        # distance of every eligible early-stop test from its threshold (a knife-edge golden would be a useless golden)
+        first_ok = (0.25 * kw["max_iter"] + 2)
+        margin = []
+        for i in range(1, len(h)):
+            it = i // kw["steps_per_iter"]
+            if it > first_ok:
+                margin.append((abs(h[i - 1] - h[i]) / h[i - 1]) / (h[i - 1] * 1e-3))
+        out.update({f"{tag}_hist": h, f"{tag}_terms": np.array(terms, np.float64), f"{tag}_pose": S2.pose.detach().numpy().copy(),
+                    f"{tag}_betas": S2.betas.detach().numpy().copy(), f"{tag}_trans": S2.trans.detach().numpy().copy(),
+                    f"{tag}_scale": scale.detach().numpy().copy(), f"{tag}_alias": np.array(alias), f"{tag}_stop_ratio": np.array(margin),
+                    f"{tag}_betas_changed": np.array(float((S2.betas.detach() - d["betas"]).abs()[:, 2:].max()))})
+        print(f"recon_loop[{tag}]: steps", len(hist), "of", (3 + kw["max_iter"]) * kw["steps_per_iter"], "losses", hist[0], "->", hist[-1], "alias", alias,
+              "other-betas moved by", float(out[f"{tag}_betas_changed"]), "stop ratios (x threshold)", np.round(margin, 3))
+    np.savez_compressed(os.path.join(out_dir, "recon_loop.npz"), **out)
+
+
+def _install_sil_stubs():
+    """Third-party operators of SilLossROI that cannot be installed, restated so that the reference's OWN class runs: detectron2's
+    BitMasks.crop_and_resize (aligned RoIAlign of the boolean mask, >= 0.5) and BoxMode.convert on torchvision / numpy, neural_renderer's
+    Renderer(mode='silhouettes') + its pseudo-gradient on oracle/raster_ref.py (parity unpinned, see its header).  cv2 and scipy are real."""
+    from oracle import raster_ref as RR
+    from torchvision.ops import roi_align
+
+    class BitMasks:
+        def __init__(self, t): self.tensor = t
+        def crop_and_resize(self, boxes, size):
+            n = self.tensor.shape[0]
+            rois = torch.cat([torch.arange(n, dtype=torch.float32)[:, None], boxes.float()], 1)
+            return roi_align((self.tensor != 0).float()[:, None], rois, (size, size), 1.0, 0, True)[:, 0] >= 0.5
+
+    class BoxMode:
+        XYXY_ABS, XYWH_ABS = 0, 1
+        @staticmethod
+        def convert(box, from_mode, to_mode):
+            b = np.array(box, dtype=float).copy()
+            if from_mode == to_mode:
+                return b
+            if from_mode == BoxMode.XYXY_ABS:
+                b[:, 2:] -= b[:, :2]
+            else:
+                b[:, 2:] += b[:, :2]
+            return b
+
+    class _SilFn(torch.autograd.Function):
+        @staticmethod
+        def forward(ctx, verts, faces, K, size):
+            v, f = verts.detach().double().numpy(), faces.numpy()
+            imgs, saved = [], []
+            for b in range(v.shape[0]):
+                K4 = (float(K[b, 0, 0]), float(K[b, 1, 1]), float(K[b, 0, 2]), float(K[b, 1, 2]))
+                fv = RR.faces_of(RR.project(v[b], K4), f)
+                idx, alpha, _ = RR.rasterize_fast(fv, size)
+                imgs.append(alpha); saved.append((fv, idx, alpha, K4))
+            ctx.saved, ctx.v, ctx.f, ctx.size = saved, v, f, size
+            return torch.from_numpy(np.stack(imgs)).float()
+
+        @staticmethod
+        def backward(ctx, g):
+            g = g.double().numpy()
+            out = []
+            for b, (fv, idx, alpha, K4) in enumerate(ctx.saved):
+                gf = RR.backward_faces(fv, idx, alpha, g[b], ctx.size)
+                out.append(RR.backward_verts(gf, ctx.v[b], ctx.f, K4))
+            return torch.from_numpy(np.stack(out)).float(), None, None, None
+
+    class Renderer:
+        def __init__(self, image_size=256, K=None, R=None, t=None, orig_size=1, anti_aliasing=False, **kw):
+            assert orig_size == 1 and not anti_aliasing
+            self.image_size, self.K = image_size, K
+        def __call__(self, verts, faces, mode="silhouettes"):
+            assert mode == "silhouettes"
+            return _SilFn.apply(verts, faces[0], self.K, self.image_size)
+
+    nr = _stub("neural_renderer", Renderer=Renderer)
+    nr.renderer = _stub("neural_renderer.renderer", Renderer=Renderer)
+    return BitMasks, BoxMode
+
+
+def recon_obj_loop_goldens(out_dir: str):
+    """The object / joint optimisation LOOP of the reference -- ReconFitterTriVisFull.optimize_smpl_object (recon/recon_fit_trivis_full.py:283-377)
+    with its own SilLossROI construction (recon/obj_pose_roi.py:21-107), split_smpl, the three optimisers, phase switches ('object only' 2 outer
+    iterations -> 'sil' 2 -> 'joint' up to 101, max_iter is hard-wired to 100), the per-phase decay, decopose_axis noise (torch.rand replaced by a
+    seeded sequence that the GPU test replays), the contact sets computed once on the first joint step, and the joint-phase early stop -- run on the
+    CPU, one step per outer iteration.  Third-party pieces restated: see _install_sil_stubs.  -> recon_obj_loop.npz"""
+    d, net, make_smpl, F, B = _recon_setup()
+    BitMasks, BoxMode = _install_sil_stubs()
+    import recon.bbox as BB
+    import recon.obj_pose_roi as OPR
+    OPR.BitMasks, BB.BoxMode = BitMasks, BoxMode
+    OPR.nr = sys.modules["neural_renderer"]
+    import recon.recon_fit_trivis_full as M
+    M.SilLossROI = OPR.SilLossROI
+    OPR.SilLossROI.__init__.__defaults__ = tuple("cpu" if x == "cuda:0" else x for x in OPR.SilLossROI.__init__.__defaults__)
+    torch.cuda.FloatTensor = torch.FloatTensor
+    from recon_problem import make_loop_extras
+    from argparse import Namespace
+    e = make_loop_extras(d)
+    L = make_smpl().smpl
+    _real_split(L)
+    F.scan = Namespace(v=e["temp_v"].astype(np.float64), f=e["temp_f"])
+    F.get_opt_iters = lambda: {"sil": 2, "object": 2}
+    qd = {"crop_center": d["crop"], "body_center": d["body_center"]}
+    names = ["otemp", "ovtemp", "mask", "scale", "trans", "object", "ocent", "contact"]
+    S = _unsplit_container(d, L, B)
+    R_, t_ = d["obj_R"].clone().requires_grad_(True), d["obj_t"].clone().requires_grad_(True)
+    dd = {"images": e["images_sil"], "query_dict": qd, "camera_params": {}, "crop_size": 1200, "net_input_size": d["images"].shape[-1],
+          "smpl": S, "obj_R": R_, "obj_t": t_, "obj_s": d["obj_s"].clone(), "objects": d["objects"], "occ_ratios": d["occ"]}
+    hist, terms, phases, draws = [], [], [], [0]
+    orig_sum, orig_fwd = F.sum_dict, F.forward_step
 
     def recording_sum(loss_dict, weight_dict, it):
         v = orig_sum(loss_dict, weight_dict, it)
         hist.append(float(v))
         return v
-    F.sum_dict = recording_sum
-    F.split_smpl = lambda smpl: smpl                     # the split container is built above (its constructor reads the licensed model files)
-    F.copy_smpl_params = lambda split, smpl: split
-    F.get_smpl_height = lambda smpl: torch.ones(B)
-    with contextlib.redirect_stdout(io.StringIO()), contextlib.redirect_stderr(io.StringIO()):
-        S2, _ = F.optimize_smpl(S, dd, iter_for_betas=1, iter_for_pose=1, iter_for_kpts=1, steps_per_iter=3, max_iter=2)
-    out = {"hist": np.array(hist, np.float64), "pose": torch.cat([S2.global_pose, S2.body_pose, S2.hand_pose], 1).detach().numpy().copy(),
-           "betas": torch.cat([S2.top_betas, S2.other_betas], 1).detach().numpy().copy(), "trans": S2.trans.detach().numpy().copy()}
-    np.savez_compressed(os.path.join(out_dir, "recon_loop.npz"), **out)
-    print("recon_loop.npz: steps", len(hist), "losses", hist[0], "->", hist[-1])
+
+    def recording_fwd(model, smpl, data_dict, obj_R, obj_t, obj_s, phase):
+        ld = orig_fwd(model, smpl, data_dict, obj_R, obj_t, obj_s, phase)
+        terms.append([float(ld[k]) if k in ld else np.nan for k in names])
+        phases.append(phase)
+        return ld
+    F.sum_dict, F.forward_step = recording_sum, recording_fwd
+    real_rand = torch.rand
+
+    def seeded_rand(*a, **k):
+        assert tuple(a) == (B, 3, 3)
+        draws[0] += 1
+        return e["noise_seq"][draws[0] - 1].clone()
+    torch.rand = seeded_rand
+    try:
+        with contextlib.redirect_stdout(io.StringIO()), contextlib.redirect_stderr(io.StringIO()):
+            S2, R2, t2 = F.optimize_smpl_object(net, dd, joint_iter=1, steps_per_iter=1)
+    finally:
+        torch.rand = real_rand
+        del F.sum_dict, F.forward_step
+    sil = dd["silhouette"]
+    h = np.array(hist, np.float64)
+    ratios = [(abs(h[i - 1] - h[i]) / h[i - 1]) / (h[i - 1] * 1e-4) for i in range(26, len(h))]
+    out = {"term_names": np.array(names), "hist": h, "terms": np.array(terms, np.float64), "phases": np.array(phases), "n_draws": np.array(draws[0]),
+           "obj_R": R2.detach().numpy().copy(), "obj_t": t2.detach().numpy().copy(), "rot_final": M.ReconFitterTriVisFull.decopose_axis(R2.detach(), no_rand=True).numpy(),
+           "rot_init": dd["rot_init"].numpy().copy(), "trans_init": dd["trans_init"].numpy().copy(), "smpl_center": dd["smpl_center"].numpy().copy(),
+           "df_obj_h": dd["df_obj_h"].numpy().copy(), "df_hum_o": dd["df_hum_o"].numpy().copy(), "parts_obj": dd["parts_obj"].numpy().copy(),
+           "keep_mask": sil.keep_mask.numpy().copy(), "image_ref": sil.image_ref.numpy().copy(), "K_roi": sil.renderer.K.numpy().copy(),
+           "stop_ratio": np.array(ratios)}
+    np.savez_compressed(os.path.join(out_dir, "recon_obj_loop.npz"), **out)
+    n_h, n_o = int((dd["df_hum_o"] < 0.08).sum()), int((dd["df_obj_h"] < 0.08).sum())
+    print("recon_obj_loop.npz: steps", len(hist), "losses", hist[0], "->", hist[-1], "draws", draws[0], "contact verts (human, object)", n_h, n_o,
+          "contact term present in", int(np.isfinite(out["terms"][:, names.index("contact")]).sum()), "steps; stop ratios (x threshold)", np.round(ratios[-5:], 3))
+
 
 def driver_goldens(out_dir: str):
     """Host arithmetic of the fit_recon driver, from the reference's own methods called unbound on the CPU: ReconFitterBase.scale_body_kpts
@@ -1015,6 +1204,8 @@ if __name__ == "__main__":
         pack_goldens(HERE)
     if a.only == "reconloop":
         recon_loop_goldens(HERE)
+    if a.only == "reconobjloop":            # replaces SilLossROI's third-party operators: run on its own
+        recon_obj_loop_goldens(HERE)
     if a.only == "driver":
         driver_goldens(HERE)
     if a.only == "infill_io":

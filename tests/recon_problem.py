@@ -42,3 +42,33 @@ def make_problem(seed=31):
              parts_obj=torch.from_numpy(rng.integers(0, 14, (B, N_OBJ)).astype(np.int64)), assets=a, reg=reg)
     d["df_hum_o"][2] = 1.0           # a frame without human contacts is skipped (recon_fit_trivis_full.py:419-432)
     return d
+
+
+def make_loop_extras(d, seed=57):
+    """Extra inputs of the optimize_smpl_object loop golden (tests/golden/recon_obj_loop.npz): a low-poly closed template mesh (the
+    reference's ``self.scan``), person / object masks whose object blob sits where the template projects, and the seeded U(0,1) draws that
+    replace ``torch.rand`` inside ``decopose_axis`` in both runs."""
+    from scipy.spatial import ConvexHull
+    rng = np.random.Generator(np.random.PCG64(seed))
+    t = lambda x: torch.from_numpy(np.asarray(x, np.float32))
+    p = rng.standard_normal((28, 3)); p /= np.linalg.norm(p, axis=1, keepdims=True)
+    tv = (p * np.array([0.3, 0.25, 0.2])).astype(np.float32)
+    hull = ConvexHull(tv.astype(np.float64))
+    tf = hull.simplices.astype(np.int64)
+    # orient the faces outwards (ConvexHull does not promise a winding)
+    c = tv.mean(0)
+    for i, f in enumerate(tf):
+        n = np.cross(tv[f[1]] - tv[f[0]], tv[f[2]] - tv[f[0]])
+        if np.dot(n, tv[f[0]] - c) < 0:
+            tf[i] = f[::-1]
+    S = d["images"].shape[-1]
+    crop, ot = d["crop"].numpy(), d["obj_t"].numpy()
+    px = (600 + 979.7844 * ot[:, 0] / ot[:, 2] + 1018.952 - crop[:, 0]) * S / 1200
+    py = (600 + 979.840 * ot[:, 1] / ot[:, 2] + 779.486 - crop[:, 1]) * S / 1200
+    yy, xx = np.mgrid[0:S, 0:S]
+    obj = np.stack([((xx - (x + 1.5)) ** 2 / 7.0 ** 2 + (yy - (y - 1.0)) ** 2 / 5.5 ** 2) < 1 for x, y in zip(px, py)]).astype(np.float32)
+    person = np.zeros_like(obj); person[:, S // 4: 3 * S // 4, S // 2 - 6: S // 2 + 4] = 1.0
+    images_sil = d["images"].clone()
+    images_sil[:, 3], images_sil[:, 4] = t(person), t(obj)
+    noise = t(rng.random((400, d["obj_R"].shape[0], 3, 3)))
+    return dict(temp_v=tv, temp_f=tf, images_sil=images_sil, noise_seq=noise)

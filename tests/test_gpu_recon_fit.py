@@ -72,47 +72,124 @@ def test_forward_step_matches_reference(ctx, golden, phase, tag, decay):
     assert rel_err(t_.grad.cpu(), g[f"{tag}_g_t"]) < TOL
 
 
-def test_optimisation_loops_run_and_reduce_the_loss(ctx):
-    """Short runs of both loops (phase switches included through tiny iteration counts)."""
-    from vistracker_b200.render import SilLossROI
-    d, fitter, make_smpl = ctx
+def _smpl_dd(d):
     c = lambda t: t.cuda()
-    qd = {"crop_center": c(d["crop"]), "body_center": c(d["body_center"])}
+    return {"part_labels": c(d["labels"])[None].repeat(B, 1), "query_dict": {"crop_center": c(d["crop"]), "body_center": c(d["body_center"])},
+            "pose_init": c(d["pose_init"]), "body_kpts": c(d["body_kpts"])}
+
+
+def _obj_dd(d, e, smpl):
+    c = lambda t: t.cuda()
+    return {"images": c(e["images_sil"]), "query_dict": {"crop_center": c(d["crop"]), "body_center": c(d["body_center"])}, "camera_params": {},
+            "crop_size": 1200, "net_input_size": d["images"].shape[-1], "smpl": smpl, "obj_R": c(d["obj_R"]).requires_grad_(True),
+            "obj_t": c(d["obj_t"]).requires_grad_(True), "obj_s": c(d["obj_s"]), "objects": c(d["objects"]), "occ_ratios": c(d["occ"])}
+
+
+def _nan_equal_close(a, b, tol):
+    """Same NaN pattern (a term that is not part of a phase's loss_dict) and every present value within tol of the reference."""
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    assert a.shape == b.shape, (a.shape, b.shape)
+    assert np.array_equal(np.isnan(a), np.isnan(b)), "different terms present"
+    m = ~np.isnan(b)
+    err = np.abs(a[m] - b[m]) / np.maximum(np.abs(b[m]), 1e-6)
+    return float(err.max()) if err.size else 0.0
+
+
+@pytest.mark.parametrize("mode", ["graph", "eager"])
+def test_optimisation_loops_run_and_reduce_the_loss(ctx, mode):
+    """Short runs of both loops (phase switches included through tiny iteration counts), CUDA-graph steps and PyTorch-glue steps."""
+    from recon_problem import make_loop_extras
+    d, fitter, make_smpl = ctx
+    e = make_loop_extras(d)
     smpl = make_smpl()
-    dd = {"part_labels": c(d["labels"])[None].repeat(B, 1), "query_dict": qd, "pose_init": c(d["pose_init"]), "body_kpts": c(d["body_kpts"])}
-    smpl, hist = fitter.optimize_smpl(smpl, dd, 1, 1, 1, steps_per_iter=3, max_iter=2)
+    smpl, scale = fitter.optimize_smpl(smpl, _smpl_dd(d), 1, 1, 1, steps_per_iter=3, max_iter=2, loop_mode=mode)
+    hist = fitter.last_hist
     # the reference's early-stop rule |prev - loss| / prev < prev * 1e-3 scales with the loss value, so it may fire once
     # it > 0.25 * max_iter + 2; the run is 15 steps at most
     assert 10 <= len(hist) <= 15 and np.isfinite(hist).all() and min(hist[5:]) < hist[1]
-    # object: template = the ellipsoid points' convex hull, ROI = whole crop
-    from scipy.spatial import ConvexHull
-    tmpl = d["objects"][0].numpy()
-    faces = ConvexHull(tmpl).simplices
-    K = SilLossROI.compute_K_roi((424.0, 168.0, 1200.0, 1200.0))[None].repeat(B, 1, 1)
-    ref = torch.zeros(B, 64, 64); ref[:, 20:44, 24:40] = 1
-    sil = SilLossROI(torch.ones(B, 64, 64), ref, K, tmpl, faces, rend_size=64)
-    R_, t_ = c(d["obj_R"]).requires_grad_(True), c(d["obj_t"]).requires_grad_(True)
-    dd = {"objects": c(d["objects"]), "query_dict": qd, "occ_ratios": c(d["occ"]), "obj_R": R_, "obj_t": t_, "obj_s": c(d["obj_s"]),
-          "silhouette": sil}
+    assert scale.shape == (B,) and float((scale - 1).abs().max()) < 0.2
+    fitter.scan = (e["temp_v"], e["temp_f"])
+    dd = _obj_dd(d, e, smpl)
+    old = fitter.get_opt_iters
     fitter.get_opt_iters = staticmethod(lambda: {"sil": 2, "object": 2})
-    _, R_out, t_out, hist = fitter.optimize_smpl_object(smpl, dd, joint_iter=1, steps_per_iter=2, max_iter=1)
+    try:
+        _, R_out, t_out = fitter.optimize_smpl_object(fitter.model, dd, joint_iter=1, steps_per_iter=2, max_iter=1, loop_mode=mode)
+    finally:
+        fitter.get_opt_iters = old
+    hist = fitter.last_hist
     assert 8 <= len(hist) <= 12 and np.isfinite(hist).all()          # 6 outer x 2 steps unless the joint-phase early stop fires
-    assert "trans_init" in dd and "df_obj_h" in dd
+    assert "trans_init" in dd and "df_obj_h" in dd and R_out is dd["obj_R"] and t_out is dd["obj_t"]
     Rf = fitter.final_rotation(R_out)
     assert rel_err((Rf @ Rf.transpose(1, 2)).cpu(), torch.eye(3).expand(B, 3, 3)) < 1e-5
 
 
-@pytest.mark.xfail(strict=False, reason="added after the round's GPU budget was spent: first B200 run of this comparison happens at round end")
-def test_optimize_smpl_loop_follows_the_reference_loop(ctx, golden):
-    """The whole SMPL refinement loop (phase schedule, both Adam set-ups, decay, early stop) against the reference's own
-    ReconFitterBehave.optimize_smpl executed on the CPU (tests/golden/recon_loop.npz: 1 + 1 + 1 + 2 outer iterations of 3 steps)."""
+LOOP_TOL = 1e-4          # north_star tolerance; observed on B200: <= 2.3e-5 on every per-step term, <= 2e-5 on the final parameters (tests/diag_loops.py)
+
+
+@pytest.mark.parametrize("mode", ["graph", "eager"])
+@pytest.mark.parametrize("tag,kw", [("a", dict(steps_per_iter=3, max_iter=2)), ("b", dict(steps_per_iter=2, max_iter=12))])
+def test_optimize_smpl_loop_follows_the_reference_loop(ctx, golden, tag, kw, mode):
+    """The whole SMPL refinement loop (split parameters aliasing the caller's container, phase schedule, both Adam set-ups, decay, early stop,
+    height ratio) against the reference's own ReconFitterBehave.optimize_smpl executed unpatched on the CPU (tests/golden/recon_loop.npz)."""
     d, fitter, make_smpl = ctx
     g = golden("recon_loop.npz")
-    c = lambda t: t.cuda()
-    dd = {"part_labels": c(d["labels"])[None].repeat(B, 1), "query_dict": {"crop_center": c(d["crop"]), "body_center": c(d["body_center"])},
-          "pose_init": c(d["pose_init"]), "body_kpts": c(d["body_kpts"])}
-    smpl, hist = fitter.optimize_smpl(make_smpl(), dd, iter_for_betas=1, iter_for_pose=1, iter_for_kpts=1, steps_per_iter=3, max_iter=2)
-    assert len(hist) == len(g["hist"])                                            # same early stop
-    assert rel_err(np.asarray(hist), g["hist"]) < 1e-3
-    assert rel_err(smpl.pose.detach().cpu(), g["pose"]) < 1e-3 and rel_err(smpl.trans.detach().cpu(), g["trans"]) < 1e-3
-    assert rel_err(smpl.betas.detach().cpu(), g["betas"]) < 1e-3
+    assert bool(g[f"{tag}_alias"]) and float(g[f"{tag}_betas_changed"]) > 1e-3      # the reference itself updates the caller's 'other' betas
+    smpl0 = make_smpl()
+    smpl, scale = fitter.optimize_smpl(smpl0, _smpl_dd(d), iter_for_betas=1, iter_for_pose=1, iter_for_kpts=1, loop_mode=mode, **kw)
+    assert smpl is smpl0
+    hist, ref = np.asarray(fitter.last_hist), g[f"{tag}_hist"]
+    assert len(hist) == len(ref), f"early stop at step {len(hist)}, the reference stops at {len(ref)}"
+    assert fitter.last_stopped == (len(ref) < (3 + kw["max_iter"]) * kw["steps_per_iter"])
+    worst = np.abs(hist - ref) / np.abs(ref)
+    assert worst.max() < LOOP_TOL, f"per-step relative deviation of the total loss: {np.round(worst, 6)}"
+    assert list(g["term_names"]) == ["df_h", "pose", "hand", "part", "pinit", "j2d", "stemp"]
+    assert _nan_equal_close(fitter.last_terms, g[f"{tag}_terms"], LOOP_TOL) < LOOP_TOL
+    pose = torch.cat([smpl.global_pose, smpl.body_pose, smpl.hand_pose], 1).detach().cpu()
+    betas = torch.cat([smpl.top_betas, smpl.other_betas], 1).detach().cpu()
+    assert rel_err(pose, g[f"{tag}_pose"]) < LOOP_TOL and rel_err(smpl.trans.detach().cpu(), g[f"{tag}_trans"]) < LOOP_TOL
+    assert rel_err(betas, g[f"{tag}_betas"]) < LOOP_TOL and rel_err(scale.cpu(), g[f"{tag}_scale"]) < LOOP_TOL
+    assert float((betas[:, 2:] - d["betas"][:, 2:]).abs().max()) > 1e-3             # ... and so does this implementation
+
+
+@pytest.mark.parametrize("mode", ["graph", "eager"])
+def test_optimize_smpl_object_loop_follows_the_reference_loop(ctx, golden, mode):
+    """optimize_smpl_object through all three phases against the reference's own loop run on the CPU (tests/golden/recon_obj_loop.npz): the
+    reference's SilLossROI construction, 2 'object only' + 2 'sil' + 101 'joint' steps with the decopose_axis draws replayed, the contact sets
+    of the first joint step, the three optimisers, the per-phase decay.  The rasteriser inside the 'sil' phase is the restated one on both
+    sides (parity unpinned, oracle/raster_ref.py)."""
+    from recon_problem import make_loop_extras
+    d, fitter, make_smpl = ctx
+    g = golden("recon_obj_loop.npz")
+    e = make_loop_extras(d)
+    fitter.scan = (e["temp_v"], e["temp_f"])
+    dd = _obj_dd(d, e, make_smpl())
+    draws = [0]
+
+    def noise_fn():
+        draws[0] += 1
+        return e["noise_seq"][draws[0] - 1].cuda()
+    old = fitter.get_opt_iters
+    fitter.get_opt_iters = staticmethod(lambda: {"sil": 2, "object": 2})
+    try:
+        _, R_out, t_out = fitter.optimize_smpl_object(fitter.model, dd, joint_iter=1, steps_per_iter=1, noise_fn=noise_fn, loop_mode=mode)
+    finally:
+        fitter.get_opt_iters = old
+    sil = dd["silhouette"]
+    assert np.array_equal(sil.keep_mask.cpu().numpy(), g["keep_mask"]) and np.array_equal(sil.image_ref.cpu().numpy(), g["image_ref"])
+    K = torch.zeros(B, 3, 3); K[:, 0, 0], K[:, 1, 1], K[:, 0, 2], K[:, 1, 2], K[:, 2, 2] = *sil.renderer.K4.cpu().T, 1.0
+    assert rel_err(K, g["K_roi"]) < 1e-6
+    hist, ref = np.asarray(fitter.last_hist), g["hist"]
+    assert len(hist) == len(ref) and draws[0] == int(g["n_draws"])
+    worst = np.abs(hist - ref) / np.abs(ref)
+    assert worst.max() < LOOP_TOL, f"per-step relative deviation of the total loss: {np.round(worst, 6)}"
+    names = list(g["term_names"])
+    ours = np.full_like(g["terms"], np.nan)
+    for k, name in enumerate(("otemp", "ovtemp", "mask", "scale", "trans", "object", "contact")):
+        ours[:, names.index(name)] = fitter.last_terms[:, k]
+    ref_terms = g["terms"].copy()
+    ref_terms[:, names.index("ocent")] = np.nan            # weight 0 ("no loss anymore"): reported by the eager path only, never part of the total
+    assert _nan_equal_close(ours, ref_terms, LOOP_TOL) < LOOP_TOL
+    assert rel_err(dd["df_obj_h"].cpu(), g["df_obj_h"]) < 1e-4 and rel_err(dd["df_hum_o"].cpu(), g["df_hum_o"]) < 1e-4
+    assert rel_err(dd["trans_init"].cpu(), g["trans_init"]) < LOOP_TOL
+    assert rel_err(R_out.detach().cpu(), g["obj_R"]) < LOOP_TOL and rel_err(t_out.detach().cpu(), g["obj_t"]) < LOOP_TOL
+    assert rel_err(fitter.final_rotation(R_out).cpu(), g["rot_final"]) < LOOP_TOL

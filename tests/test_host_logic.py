@@ -130,3 +130,56 @@ def test_compute_pca_matches_sklearn_conventions():
     assert np.abs(u - Vu).max() < 1e-10
     assert np.abs(np.abs(u @ v.T) - np.eye(3)).max() < 1e-9 and np.abs(u @ u.T - np.eye(3)).max() < 1e-10
     assert compute_pca(X).tolist() == u.tolist()                                   # default: the convention the checkpoints were trained with
+
+
+def test_contact_pairs_equal_the_reference_double_loop():
+    """ReconFitterTriVisFull.contact_pairs (vectorised sorts / counts) against the literal frame x part loop of compute_contact_loss
+    (recon/recon_fit_trivis_full.py:405-449) written out in Python: same clouds, same order, incl. a frame without human contacts, a frame
+    without object contacts and parts present on one side only."""
+    from types import SimpleNamespace
+    from vistracker_b200.recon_fit import ReconFitterTriVisFull
+    rng = np.random.default_rng(5)
+    B, Nh, No = 5, 300, 90
+    labels = torch.from_numpy(rng.integers(0, 14, Nh))
+    df_hum_o = torch.from_numpy(rng.uniform(0, 0.3, (B, Nh)).astype(np.float32))
+    df_obj_h = torch.from_numpy(rng.uniform(0, 0.3, (B, No)).astype(np.float32))
+    part_o = torch.from_numpy(rng.standard_normal((B, 14, No)).astype(np.float32))
+    part_o[:, 5] = -10.0                                 # part 5 never predicted on the object
+    df_hum_o[1] = 1.0                                    # no human contact in frame 1
+    df_obj_h[3] = 1.0                                    # no object contact in frame 3
+    shim = SimpleNamespace(part_labels=labels)
+    h_idx, o_idx, h_off, o_off = ReconFitterTriVisFull.contact_pairs(shim, df_hum_o, df_obj_h, part_o)
+    # literal restatement of the reference loop, as lists of flat indices
+    hs, os_ = [], []
+    po = part_o.argmax(1)
+    for b in range(B):
+        mh, mo = df_hum_o[b] < 0.08, df_obj_h[b] < 0.08
+        if int(mh.sum()) + int(mo.sum()) == 0 or int(mo.sum()) == 0 or int(mh.sum()) == 0:
+            continue
+        hv, ov = torch.where(mh)[0], torch.where(mo)[0]
+        lh, lo = labels[hv], po[b][ov]
+        for i in range(14):
+            if i not in lh or i not in lo:
+                continue
+            hs.append(hv[lh == i] + b * Nh); os_.append(ov[lo == i] + b * No)
+    assert len(hs) == h_off.numel() - 1 == o_off.numel() - 1 and len(hs) > 10
+    for n, (a, c) in enumerate(zip(hs, os_)):
+        assert torch.equal(h_idx[h_off[n]:h_off[n + 1]], a) and torch.equal(o_idx[o_off[n]:o_off[n + 1]], c)
+    assert h_off.dtype == torch.int32 and int(h_off[-1]) == h_idx.numel() and int(o_off[-1]) == o_idx.numel()
+    # nothing in contact anywhere
+    assert ReconFitterTriVisFull.contact_pairs(shim, df_hum_o + 1, df_obj_h, part_o) is None
+
+
+def test_phase_schedules_follow_the_reference_chains():
+    from vistracker_b200.recon_fit import ReconFitterTriVisFull as F
+    s = F.smpl_phase_schedule(1, 1, 1, 100)              # the tri-vis driver's call (recon_fit_triplane.py:66)
+    assert len(s) == 103 and s[0] == ("global", False) and s[1] == ("smpl all pose", True) and s[2] == ("kpts", False) and s[-1] == ("kpts", False)
+    s = F.smpl_phase_schedule(10, 10, 5, 100)            # the defaults of recon_fit_behave.py:393-395
+    assert [p for p, _ in s[:10]] == ["global"] * 10 and s[10] == ("smpl all pose", True) and s[19][0] == "smpl all pose" and s[20][0] == "kpts"
+    s = F.smpl_phase_schedule(1, 0, 1, 3)                # iter_for_pose = 0: the `elif` chain never reaches 'kpts'
+    assert [p for p, _ in s] == ["global"] + ["smpl all pose"] * 4
+    o = F.object_phase_schedule(15, 30, 10, 100)
+    assert len(o) == 155 and o[14] == ("object only", False, 1) and o[15] == ("sil", True, 1) and o[44] == ("sil", False, 30)
+    assert o[45][:2] == ("joint", True) and abs(o[45][2] - 31 / 3) < 1e-12 and o[46][:2] == ("joint", False)
+    o = F.object_phase_schedule(2, 0, 1, 3)              # no silhouette phase: `it == it_obj and it != it_obj + it_sil` is False, joint starts at it_obj
+    assert [p for p, _, _ in o] == ["object only"] * 2 + ["joint"] * 4 and o[2][1]

@@ -10,7 +10,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libvistracker_sm100a.so")
 
-_p, _i, _f, _ll = C.c_void_p, C.c_int, C.c_float, C.c_longlong
+_p, _i, _f, _ll, _d = C.c_void_p, C.c_int, C.c_float, C.c_longlong, C.c_double
 
 # name -> (restype, argtypes); must list every symbol of include/vistracker_b200.h (tests/test_cabi.py checks both ways)
 SIGNATURES = {
@@ -89,6 +89,22 @@ SIGNATURES.update({
     "vt_raster_cull_floats": (_ll, [_i, _i]),
     "vt_raster_fwd": (_i, [_p, _p, _i, _i, _i, _i, _p, _i, _p, _p, _p, _p, _p, _p]),
     "vt_raster_bwd": (_i, [_p, _p, _i, _i, _i, _i, _p, _i, _p, _p, _p, _p, _p, _p, _p]),
+    "vt_recon_ctrl_words": (_i, []),
+    "vt_recon_hist_ld": (_i, []),
+    "vt_zero": (_i, [_p, _ll, _p]),
+    "vt_recon_point_terms": (_i, [_p, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _i, _i, _f, _p, _p, _i, _i, _f, _p, _p, _p, _p]),
+    "vt_recon_kpts": (_i, [_p, _p, _p, _i, _i, _p, _p, _p, _p, _p]),
+    "vt_recon_pose_terms": (_i, [_p, _p, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "vt_recon_adam_smpl": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _p, _p]),
+    "vt_recon_adam_obj": (_i, [_p, _p, _p, _p, _p, _p, _i, _p, _p]),
+    "vt_recon_end_step": (_i, [_p, _i, _p, _i, _p, _p, _p, _i, _p]),
+    "vt_recon_obj_noise": (_i, [_p, _p, _i, _p, _p, _p, _p]),
+    "vt_recon_obj_transform": (_i, [_p, _i, _p, _p, _p, _i, _i, _p, _p]),
+    "vt_recon_obj_transform_bwd": (_i, [_p, _i, _p, _p, _i, _i, _i, _p, _p, _p]),
+    "vt_recon_sil_loss": (_i, [_p, _p, _p, _p, _i, _i, _p, _p, _p, _p]),
+    "vt_recon_obj_small_terms": (_i, [_p, _p, _p, _f, _i, _i, _p, _p, _p, _p]),
+    "vt_recon_gather_rows": (_i, [_p, _p, _i, _p, _p]),
+    "vt_recon_scatter_add_rows": (_i, [_p, _p, _i, _p, _p]),
 })
 
 _lib = None

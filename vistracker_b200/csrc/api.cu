@@ -25,6 +25,12 @@ extern "C" {
 
 const char* vt_last_error(void) { return vt::g_err; }
 int vt_version(void) { return 1; }
+/* cudaMemsetAsync on the caller's stream (a memset node when captured into a CUDA graph) */
+int vt_zero(void* p, long long bytes, void* stream) {
+  if (bytes <= 0) return 0;
+  cudaError_t e = cudaMemsetAsync(p, 0, (size_t)bytes, (cudaStream_t)stream);
+  return e == cudaSuccess ? 0 : vt::cuda_fail(e, "vt_zero");
+}
 int vt_compiled_arch(void) {
 #ifdef VT_ARCH
   return VT_ARCH;

@@ -88,14 +88,14 @@ def fit_recon_batch(fitter: ReconFitterTriVisFull, generator: GeneratorTriplaneV
     rotation comes from the network (``-or neural``); obj_rot_init [B,3,3]: the rotation loaded from an earlier stage (HVOP-Net) instead.
     silhouette: a ``render.SilLossROI`` for the batch, occ_ratios [B]: visibility used by the occlusion-aware terms (defaults to the
     network's prediction, recon_fit_triplane.py:68).
-    Returns {'pc_generated', 'smpl', 'obj_R' (projected, no noise), 'obj_t', 'obj_s', 'hist_smpl', 'hist_obj'} -- or only 'pc_generated' for
+    Returns {'pc_generated', 'smpl', 'obj_R' (projected, no noise), 'obj_t', 'obj_s', 'hist_smpl', 'hist_obj', 'stopped_*', 'smpl_scale'} -- or only 'pc_generated' for
     ``neural_only`` (demo.sh step 4)."""
     dev = fitter.model.device
     pc = generate_all(generator, data, on_mini_batch=on_mini_batch, mini_batch_size=mini_batch_size)
     if neural_only:
         return {"pc_generated": pc}
-    if silhouette is None:
-        raise ValueError("the 'sil' phase needs a render.SilLossROI for the batch")
+    if silhouette is None and fitter.scan is None:
+        raise ValueError("the 'sil' phase needs a render.SilLossROI for the batch, or fitter.scan = (template vertices, faces) to build one")
     with torch.no_grad():
         filter_batch(fitter.model, data["images"], chunk=mini_batch_size)
     B = data["images"].shape[0]
@@ -106,7 +106,8 @@ def fit_recon_batch(fitter: ReconFitterTriVisFull, generator: GeneratorTriplaneV
     dd = {"part_labels": fitter.part_labels.to(dev)[None].repeat(B, 1) if fitter.part_labels.dim() == 1 else fitter.part_labels.to(dev),
           "query_dict": query_dict, "body_kpts": body_kpts.float().to(dev),
           "pose_init": smpl.pose[:, 3:SMPL_POSE_PRAMS_NUM].detach().clone().to(dev)}
-    smpl, hist_smpl = _as_pair(fitter.optimize_smpl(smpl, dd, iter_for_kpts=1, iter_for_pose=1, iter_for_betas=1, **loop_kw))
+    smpl, scale = fitter.optimize_smpl(smpl, dd, iter_for_kpts=1, iter_for_pose=1, iter_for_betas=1, **loop_kw)       # recon_fit_triplane.py:66
+    hist_smpl, stopped_smpl = fitter.last_hist, fitter.last_stopped
     # init_obj_fit_data (recon_fit_trivis_full.py:79-104): predicted centre relative to the optimised body centre, rotation from the PCA axes
     obj_t = (pc["object"]["centers"][:, 3:].to(dev) + human_t.to(dev)).detach().clone().requires_grad_(True)
     if obj_rot_init is None:
@@ -119,11 +120,7 @@ def fit_recon_batch(fitter: ReconFitterTriVisFull, generator: GeneratorTriplaneV
     obj_s = torch.ones(B, device=dev)
     vis = pc["object"]["visibility"].to(dev).reshape(B) if occ_ratios is None else occ_ratios.to(dev)
     dd.update({"obj_R": obj_R, "obj_t": obj_t, "obj_s": obj_s, "objects": obj_points.to(dev)[None].repeat(B, 1, 1), "occ_ratios": vis,
-               "silhouette": silhouette, "trans_init": obj_t.detach().clone()})
-    smpl, obj_R, obj_t, hist_obj = fitter.optimize_smpl_object(smpl, dd, noise_fn=noise_fn, **loop_kw)
+               "silhouette": silhouette, "trans_init": obj_t.detach().clone(), "smpl": smpl, "images": data["images"]})
+    smpl, obj_R, obj_t = fitter.optimize_smpl_object(fitter.model, dd, noise_fn=noise_fn, **loop_kw)                     # recon_fit_triplane.py:106
     return {"pc_generated": pc, "smpl": smpl, "obj_R": fitter.final_rotation(obj_R), "obj_t": obj_t.detach(), "obj_s": obj_s, "hist_smpl": hist_smpl,
-            "hist_obj": hist_obj}
-
-
-def _as_pair(res):
-    return res if isinstance(res, tuple) and len(res) == 2 else (res, None)
+            "hist_obj": fitter.last_hist, "stopped_smpl": stopped_smpl, "stopped_obj": fitter.last_stopped, "smpl_scale": scale}

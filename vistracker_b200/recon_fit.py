@@ -5,12 +5,20 @@
     SMPL-H layer fwd/bwd (csrc/smpl.cu) · landmark regressors · SIF-Net fused query losses / query fwd (csrc/query_bwd_tc.cu, query_tc.cu) ·
     SO(3) projection, ragged Chamfer (csrc/geom.cu) · silhouette rasteriser fwd/bwd (csrc/raster.cu)
 
-Each of those is a ``torch.autograd.Function`` around one or two kernel launches; the scalar glue between them (clamps, means,
-the 14-way cross-entropy, the 63x63 prior products) and Adam are ordinary PyTorch device ops in this round -- see DESIGN.md
-"what is not fused yet".  File IO, data loading and mesh templates of the reference stay outside: everything is tensors.
+Two executions of the same loops:
+
+* the default: every optimisation step is ONE CUDA-graph replay of a fixed kernel sequence (``recon_steps.SmplRefineStep`` /
+  ``ObjectFitStep`` over csrc/recon.cu): loss terms, analytic gradients, masked Adam, loss history and the early-stop predicate all on the
+  device, the host only walks the schedule;
+* ``loop_mode = "eager"``: ``forward_smpl`` / ``forward_step`` below -- each operator a ``torch.autograd.Function`` around its kernels, the
+  scalar glue and ``torch.optim.Adam`` in PyTorch -- written like the reference's methods; it is what the per-term goldens are checked
+  against and the cross-check of the graph path (tests/test_gpu_recon_fit.py compares both with the reference's own loops).
+
+File IO, data loading and mesh templates of the reference stay outside: everything is tensors.
 """
 from __future__ import annotations
 
+import struct
 from typing import Dict, Optional
 
 import numpy as np
@@ -18,6 +26,7 @@ import torch
 import torch.nn.functional as F
 
 from .geom import chamfer_distance_packed, chamfer_distance_ragged, decopose_axis, project_so3
+from .recon_steps import OBJ_TERMS, RC_ESTOP, RC_LR0, RC_LR1, RC_PHASE, RC_SEED, RC_TEMP_K, RC_TOL, SMPL_TERMS, ObjectFitStep, SmplRefineStep
 from .sifnet import CHORETriplaneVisibility
 from .smpl import LandmarkRegressor, SMPL_Layer
 
@@ -120,20 +129,25 @@ class Priors:
 
 class ReconFitterTriVisFull:
     def __init__(self, model: CHORETriplaneVisibility, priors: Priors, part_labels: torch.Tensor, obj_scale: float = 1.0,
-                 z_0: float = 2.2, net_in_size: int = 512):
+                 z_0: float = 2.2, net_in_size: int = 512, scan=None, loop_mode: str = "graph"):
+        """scan: (vertices [V,3], faces [F,3]) of the centred object template (the reference's ``self.scan``), used to build the silhouette loss
+        when the caller does not pass one.  loop_mode: 'graph' (one CUDA-graph replay per step) or 'eager' (PyTorch glue, the cross-check)."""
         self.model, self.priors, self.device = model, priors, model.device
+        self.scan, self.loop_mode = scan, loop_mode
+        self.last_hist, self.last_terms, self.last_stopped = None, None, False
         self.part_labels = part_labels.to(self.device).long()            # [6890]
         self.obj_scale, self.z_0, self.net_in_size = obj_scale, z_0, net_in_size
         self.collision_loss = False       # off unless the hostname matches two cluster nodes (recon_fit_base.py:106-108)
 
     # ------------------------------------------------------------------ schedules
-    @staticmethod
-    def get_loss_weights():
-        """recon_fit_trivis_full.py:124-153."""
-        w = {"beta": 1.0, "pose": 1e-5, "hand": 1e-5, "j2d": 0.3 ** 2, "object": 30.0 ** 2, "part": 0.05 ** 2, "contact": 30.0 ** 2,
-             "scale": 10.0 ** 2, "df_h": 10.0 ** 2, "smplz": 30 ** 2, "mask": 0.03 ** 2, "ocent": 0.0, "collide": 3 ** 2, "pinit": 5 ** 2,
-             "rot": 10.0 ** 2, "trans": 10.0 ** 2, "stemp": 100.0 ** 2, "otemp": 15.0 ** 2, "ovtemp": 50.0 ** 2}
-        return {k: (lambda cst, it, c=v: c * cst / (1 + it)) for k, v in w.items()}
+    # recon_fit_trivis_full.py:124-153
+    LOSS_WEIGHTS = {"beta": 1.0, "pose": 1e-5, "hand": 1e-5, "j2d": 0.3 ** 2, "object": 30.0 ** 2, "part": 0.05 ** 2, "contact": 30.0 ** 2,
+                    "scale": 10.0 ** 2, "df_h": 10.0 ** 2, "smplz": 30 ** 2, "mask": 0.03 ** 2, "ocent": 0.0, "collide": 3 ** 2, "pinit": 5 ** 2,
+                    "rot": 10.0 ** 2, "trans": 10.0 ** 2, "stemp": 100.0 ** 2, "otemp": 15.0 ** 2, "ovtemp": 50.0 ** 2}
+
+    @classmethod
+    def get_loss_weights(cls):
+        return {k: (lambda cst, it, c=v: c * cst / (1 + it)) for k, v in cls.LOSS_WEIGHTS.items()}
 
     @staticmethod
     def sum_dict(loss_dict, weight_dict, it):
@@ -142,6 +156,43 @@ class ReconFitterTriVisFull:
     @staticmethod
     def get_opt_iters():
         return {"sil": 30, "object": 15}
+
+    @staticmethod
+    def smpl_phase_schedule(iter_for_betas, iter_for_pose, iter_for_kpts, max_iter):
+        """The if / elif chain of recon_fit_behave.py:414-435 as a list of (phase, starts_new_optimizer) per outer iteration."""
+        out, phase = [], None
+        for it in range(iter_for_betas + iter_for_kpts + iter_for_pose + max_iter):
+            new_opt = False
+            if it < iter_for_betas:
+                phase = "global"
+            elif it == iter_for_betas:
+                phase, new_opt = "smpl all pose", True
+            elif it < iter_for_betas + iter_for_pose:
+                pass
+            elif it == iter_for_betas + iter_for_pose:
+                phase = "kpts"
+            out.append((phase, new_opt))
+        return out
+
+    @staticmethod
+    def object_phase_schedule(it_obj, it_sil, joint_iter, max_iter):
+        """The if / elif chain of recon_fit_trivis_full.py:329-348: (phase, starts_new_optimizer, decay) per outer iteration."""
+        out, phase = [], None
+        for it in range(joint_iter + it_obj + max_iter + it_sil):
+            new_opt = False
+            if it < it_obj:
+                phase = "object only"
+            elif it == it_obj and it != it_obj + it_sil:
+                phase, new_opt = "sil", True
+            elif it == it_obj + it_sil:
+                phase, new_opt = "joint", True
+            decay = 1 if phase == "object only" else it
+            if phase == "sil":
+                decay = it - it_obj + 1
+            elif phase == "joint":
+                decay = (it - it_obj + 1) / 3
+            out.append((phase, new_opt, decay))
+        return out
 
     # ------------------------------------------------------------------ SMPL refinement against the neural UDF
     def project_points(self, joints3d, crop_center):
@@ -180,20 +231,52 @@ class ReconFitterTriVisFull:
             loss_dict["stemp"] = F.mse_loss(v1, v2)
         return loss_dict
 
-    def optimize_smpl(self, smpl: SMPLParams, data_dict, iter_for_betas=1, iter_for_pose=1, iter_for_kpts=1, steps_per_iter=10,
-                      max_iter=100):
-        """recon_fit_behave.py:393-465 (the tri-vis driver calls it with 1, 1, 1 -- recon_fit_triplane.py:66)."""
+    def get_smpl_height(self, smpl: SMPLParams):
+        """recon_fit_base.py:818-828."""
+        with torch.no_grad():
+            verts = smpl()[0]
+        return verts[:, :, 1].amax(1) - verts[:, :, 1].amin(1)
+
+    def optimize_smpl(self, smpl: SMPLParams, data_dict, iter_for_betas=10, iter_for_pose=10, iter_for_kpts=5, steps_per_iter=10,
+                      max_iter=100, loop_mode: Optional[str] = None):
+        """recon_fit_behave.py:393-465 (the tri-vis driver calls it with 1, 1, 1 -- recon_fit_triplane.py:66).  Returns ``(smpl, scale)`` like
+        the reference: the container it was given, updated in place, and the body-height ratio after / before.
+
+        In place is what the reference does, too: ``split_smpl`` -> ``SMPLPyTorchWrapperBatchSplitParams.from_smpl`` wraps VIEWS of
+        ``smpl.pose.data / betas.data / trans.data`` in new Parameters (lib_smpl/wrapper_pytorch.py:206-226; ``.to()`` on the same device is a
+        no-op), so Adam's in-place updates of the split parameters -- the eight 'other' betas included -- land in the caller's container, and
+        ``copy_smpl_params`` re-copies a subset of the same storage (tests/golden/recon_loop.npz records ``alias = True`` from the reference's
+        own run).  The per-step totals / terms are kept in ``self.last_hist`` / ``self.last_terms``, ``self.last_stopped``."""
+        mode = self.loop_mode if loop_mode is None else loop_mode
+        if mode == "eager":
+            return self._optimize_smpl_eager(smpl, data_dict, iter_for_betas, iter_for_pose, iter_for_kpts, steps_per_iter, max_iter)
+        n_it = iter_for_betas + iter_for_kpts + iter_for_pose + max_iter
+        with torch.cuda.device(self.device):
+            st = SmplRefineStep(self, smpl, data_dict, n_it * steps_per_iter)
+            height_init = st.heights()
+            self.last_stopped = st.run(self.LOSS_WEIGHTS, iter_for_betas, iter_for_pose, iter_for_kpts, steps_per_iter, max_iter)
+            scale = st.heights() / height_init
+            st.write_back(smpl)
+            self.last_hist, self.last_terms = st._history()
+            self.last_launches = st.steps_launched * st.LAUNCHES_PER_STEP
+        return smpl, scale
+
+    def _optimize_smpl_eager(self, smpl: SMPLParams, data_dict, iter_for_betas, iter_for_pose, iter_for_kpts, steps_per_iter, max_iter):
+        """The same loop with PyTorch glue, autograd and torch.optim.Adam around the operator kernels (one host synchronisation per step for
+        the early-stop test, which is evaluated on fp32 tensors exactly as recon_fit_behave.py:452 does)."""
+        height_init = self.get_smpl_height(smpl)
         opt = torch.optim.Adam([smpl.top_betas, smpl.trans], lr=0.02)
         weight_dict = self.get_loss_weights()
-        prev_loss, phase, hist = 300.0, "global", []
-        for it in range(iter_for_betas + iter_for_kpts + iter_for_pose + max_iter):
-            if it < iter_for_betas:
-                phase = "global"
-            elif it == iter_for_betas:
-                phase = "smpl all pose"
+        prev_loss, hist, terms = 300.0, [], []
+        self.last_stopped = False
+
+        def done():
+            self.last_hist = np.asarray(hist, np.float64)
+            self.last_terms = np.asarray([[float(ld[k]) if k in ld else np.nan for k in SMPL_TERMS] for ld in terms], np.float64)
+            return smpl, self.get_smpl_height(smpl) / height_init
+        for it, (phase, new_opt) in enumerate(self.smpl_phase_schedule(iter_for_betas, iter_for_pose, iter_for_kpts, max_iter)):
+            if new_opt:
                 opt = torch.optim.Adam([smpl.trans, smpl.global_pose, smpl.body_pose, smpl.top_betas, smpl.other_betas], 0.006, betas=(0.9, 0.999))
-            if it == iter_for_betas + iter_for_pose:
-                phase = "kpts"
             for _ in range(steps_per_iter):
                 opt.zero_grad()
                 loss_dict = self.forward_smpl(smpl, data_dict, phase)
@@ -201,12 +284,12 @@ class ReconFitterTriVisFull:
                 loss = self.sum_dict(loss_dict, weight_dict, decay)
                 loss.backward()
                 opt.step()
-                lv = float(loss)
-                hist.append(lv)
-                if (abs(prev_loss - lv) / prev_loss < prev_loss * 0.001) and (it > 0.25 * max_iter + iter_for_betas + iter_for_pose):
-                    return smpl, hist
-                prev_loss = lv
-        return smpl, hist
+                hist.append(float(loss)); terms.append({k: v.detach() for k, v in loss_dict.items()})
+                if bool(abs(prev_loss - loss) / prev_loss < prev_loss * 0.001) and (it > 0.25 * max_iter + iter_for_betas + iter_for_pose):
+                    self.last_stopped = True
+                    return done()
+                prev_loss = loss.detach()
+        return done()
 
     # ------------------------------------------------------------------ object / joint optimisation
     @staticmethod
@@ -222,32 +305,33 @@ class ReconFitterTriVisFull:
         loss_dict["ovtemp"] = F.mse_loss(obj_verts[1:], obj_verts[:-1]) * weight
 
     def contact_pairs(self, df_hum_o, df_obj_h, part_o, cont_thres=0.08):
-        """The (frame, body part) pairing of recon_fit_trivis_full.py:405-449 as index lists.  The contact masks are frozen after
-        the first joint step (:242-253), so the pairing is computed ONCE per batch and every later step is two gathers + one
-        Chamfer launch (the reference re-runs the Python double loop with GPU->CPU syncs on each of its ~1100 joint steps)."""
+        """The (frame, body part) pairing of recon_fit_trivis_full.py:405-449 as packed index lists ``(h_idx, o_idx, h_off, o_off)``: rows of
+        the flattened [B*Nh, 3] vertices / [B*No, 3] object points, grouped by (frame, part) in the reference's loop order (frame outer, part
+        inner, point order kept), with int32 group offsets.  The contact masks are frozen after the first joint step (:242-253), so this runs
+        ONCE per batch -- a handful of device-wide sorts / counts, no Python loop over frames and parts -- and every later step is one gather +
+        one Chamfer launch (the reference re-runs its double loop, with a GPU->CPU sync per `in` test, on each of its ~1100 joint steps)."""
         mask_o, mask_h = df_obj_h < cont_thres, df_hum_o < cont_thres
         if part_o.dim() == 3:
             part_o = torch.argmax(part_o, 1)
         B, Nh, No = mask_h.shape[0], mask_h.shape[1], mask_o.shape[1]
-        dev = mask_h.device
-        hi, oi, hoff, ooff = [], [], [0], [0]
-        mask_h_c, mask_o_c, part_o_c, labels_c = mask_h.cpu(), mask_o.cpu(), part_o.cpu(), self.part_labels.cpu()
-        for b in range(B):
-            mh, mo = mask_h_c[b], mask_o_c[b]
-            if int(mh.sum()) == 0 or int(mo.sum()) == 0:
-                continue
-            hv, ov = torch.nonzero(mh)[:, 0], torch.nonzero(mo)[:, 0]
-            lh, lo = labels_c[hv], part_o_c[b][ov]
-            for i in range(SMPL_PARTS_NUM):
-                sh, so = hv[lh == i], ov[lo == i]
-                if sh.numel() == 0 or so.numel() == 0:
-                    continue
-                hi.append(sh + b * Nh); oi.append(so + b * No)
-                hoff.append(hoff[-1] + sh.numel()); ooff.append(ooff[-1] + so.numel())
-        if not hi:
+        both = mask_h.any(1) & mask_o.any(1)                             # frames lacking either side are skipped (:419-432)
+        labels_h = self.part_labels.to(mask_h.device)[None].expand(B, Nh)
+
+        def side(mask, labels, n):
+            idx = torch.nonzero((mask & both[:, None]).reshape(-1))[:, 0]               # ascending = frame-major, point order
+            key = torch.div(idx, n, rounding_mode="floor") * SMPL_PARTS_NUM + labels.reshape(-1)[idx].long()
+            srt = torch.sort(key, stable=True)
+            return idx[srt.indices], srt.values
+        hi, hk = side(mask_h, labels_h, Nh)
+        oi, ok = side(mask_o, part_o, No)
+        ch, co = torch.bincount(hk, minlength=B * SMPL_PARTS_NUM), torch.bincount(ok, minlength=B * SMPL_PARTS_NUM)
+        valid = (ch > 0) & (co > 0)                                      # `if i not in label_h or i not in label_o: continue`
+        if not bool(valid.any()):
             return None
-        return (torch.cat(hi).to(dev), torch.cat(oi).to(dev), torch.tensor(hoff, dtype=torch.int32, device=dev),
-                torch.tensor(ooff, dtype=torch.int32, device=dev))
+        z = torch.zeros(1, dtype=torch.int64, device=hi.device)
+        h_off = torch.cat([z, torch.cumsum(ch[valid], 0)]).to(torch.int32)
+        o_off = torch.cat([z, torch.cumsum(co[valid], 0)]).to(torch.int32)
+        return hi[valid[hk]], oi[valid[ok]], h_off, o_off
 
     def compute_contact_loss(self, df_hum_o, df_obj_h, object, smpl_verts, loss_dict, part_o, cont_thres=0.08, pairs="build"):
         """recon_fit_trivis_full.py:393-457: per frame and body part, pull human contact vertices and object contact points
@@ -322,48 +406,141 @@ class ReconFitterTriVisFull:
             J, _, _ = smpl.get_landmarks()
             return J[:, 8]
 
-    def optimize_smpl_object(self, smpl: SMPLParams, data_dict, obj_iter=20, joint_iter=10, steps_per_iter=10, max_iter=100,
-                             noise_fn=None):
-        """recon_fit_trivis_full.py:283-377: 'object only' (Adam R lr .002, t lr .006) -> 'sil' (new Adam [R, t] .006) ->
-        'joint' (new Adam [t] .002) with the per-phase decay schedule and the joint-phase early stop."""
+    def _silhouette(self, data_dict):
+        """``SilLossROI(images[:, 3], images[:, 4], self.scan, crop_center, camera_params=..., crop_size=..., net_input_size=...)`` of
+        recon_fit_trivis_full.py:289-294, unless the caller already put one into data_dict['silhouette']."""
+        if data_dict.get("silhouette") is not None:
+            return data_dict["silhouette"]
+        if self.scan is None or "images" not in data_dict:
+            raise ValueError("the 'sil' phase needs data_dict['silhouette'] or (fitter.scan, data_dict['images'])")
+        from .render import SilLossROI
+        images = data_dict["images"]
+        sil = SilLossROI.from_masks(images[:, 3], images[:, 4], self.scan[0], self.scan[1], data_dict["query_dict"]["crop_center"],
+                                    device=self.device, camera_params=data_dict.get("camera_params"), crop_size=data_dict.get("crop_size", 1200),
+                                    net_input_size=data_dict.get("net_input_size", self.net_in_size))
+        data_dict["silhouette"] = sil
+        return sil
+
+    def _first_joint_contacts(self, data_dict, object, smpl_verts):
+        """recon_fit_trivis_full.py:242-253: the distance / part predictions that define the contact sets, evaluated once."""
+        if "df_obj_h" not in data_dict:
+            with torch.no_grad():
+                self.model.query(object.detach(), **data_dict["query_dict"])
+                preds = self.model.get_preds()
+                df_obj_h, part_o = preds[0][:, 0, :].clone(), preds[2].clone()
+                self.model.query(smpl_verts.detach(), **data_dict["query_dict"])
+                data_dict["df_obj_h"], data_dict["df_hum_o"] = df_obj_h, self.model.get_preds()[0][:, 1, :].clone()
+                data_dict["parts_obj"] = part_o
+        if "contact_pairs" not in data_dict:
+            data_dict["contact_pairs"] = self.contact_pairs(data_dict["df_hum_o"], data_dict["df_obj_h"], data_dict["parts_obj"])
+        return data_dict["contact_pairs"]
+
+    def optimize_smpl_object(self, model, data_dict, obj_iter=20, joint_iter=10, sil_iter=50, steps_per_iter=10, max_iter=100, noise_fn=None,
+                             loop_mode: Optional[str] = None, seed: int = 1):
+        """recon_fit_trivis_full.py:283-377, same signature (``model`` is the network the fitter already holds; ``data_dict['smpl']`` the body,
+        ``obj_R / obj_t / obj_s``, ``objects``, ``occ_ratios``, ``query_dict`` and -- for the silhouette phase -- ``images`` or a ready
+        ``silhouette``): 'object only' (Adam R lr .002, t lr .006) -> 'sil' (new Adam [R, t] .006) -> 'joint' (new Adam [t] .002) with the
+        per-phase decay, the contact sets fixed on the first joint step and the joint-phase early stop.  ``max_iter`` is the reference's
+        hard-wired 100.  ``noise_fn()`` -> [B,3,3] replays the U(0,1) draws of decopose_axis (parity runs); otherwise they are drawn on the
+        device (Philox, ``seed``).  Returns ``(smpl, obj_R, obj_t)``; obj_R / obj_t are updated in place."""
+        mode = self.loop_mode if loop_mode is None else loop_mode
+        smpl = data_dict["smpl"]
+        if model is not None and model is not self.model:
+            raise ValueError("the fitter is bound to its own network (ReconFitterTriVisFull(model, ...))")
+        sil = self._silhouette(data_dict)
+        if mode == "eager":
+            return self._optimize_smpl_object_eager(smpl, data_dict, joint_iter, steps_per_iter, max_iter, noise_fn)
+        obj_R, obj_t = data_dict["obj_R"], data_dict["obj_t"]
+        it_sil, it_obj = self.get_opt_iters()["sil"], self.get_opt_iters()["object"]
+        sched = self.object_phase_schedule(it_obj, it_sil, joint_iter, max_iter)
+        W = self.LOSS_WEIGHTS
+        seed_word = struct.unpack("f", struct.pack("I", (int(seed) & 0x7FFFFF) | 1))[0]
+        rows = []
+        for it, (phase, _, decay) in enumerate(sched):
+            row = [0.0] * 32
+            on = {"otemp": True, "ovtemp": True, "mask": phase == "sil", "scale": True, "trans": phase == "sil", "object": phase != "sil",
+                  "contact": phase == "joint"}
+            for k, name in enumerate(OBJ_TERMS):
+                row[k] = W[name] / (1 + decay) if on[name] else 0.0
+            row[RC_LR0], row[RC_LR1] = (0.002, 0.006) if phase == "object only" else ((0.006, 0.006) if phase == "sil" else (0.0, 0.002))
+            row[RC_PHASE] = float(ObjectFitStep.PHASES.index(phase))
+            row[RC_TOL] = 0.0001
+            row[RC_ESTOP] = 1.0 if (it > 0.25 * max_iter and phase == "joint") else 0.0
+            row[RC_TEMP_K] = 10.0 if phase == "joint" else 1.0
+            row[RC_SEED] = seed_word
+            rows.append(row)
+        with torch.cuda.device(self.device):
+            with torch.no_grad():
+                smpl_verts = smpl()[0].detach()
+                data_dict["smpl_center"] = smpl.reg(smpl_verts)[:, 8]                  # compute_smpl_center_pred: body-25 joint 8
+            st = ObjectFitStep(self, smpl_verts, data_dict, len(sched) * steps_per_iter, inject_noise=noise_fn is not None, seed=seed)
+            st._upload_schedule(rows)
+            st._start()
+            stopped, contacts_ready = False, False
+            for it, (phase, new_opt, _) in enumerate(sched):
+                if new_opt:
+                    st._new_optimizer()
+                    if phase == "sil":
+                        data_dict["rot_init"] = decopose_axis(obj_R.detach(), noise=None if noise_fn is None else noise_fn()).clone()
+                        data_dict["trans_init"] = obj_t.detach().clone()
+                        st.buf["t_init"].copy_(data_dict["trans_init"])
+                st._set_row(it)
+                pidx = ObjectFitStep.PHASES.index(phase)
+                for _ in range(steps_per_iter):
+                    if noise_fn is not None:
+                        st.buf["noise"].copy_(noise_fn().reshape(-1, 9).to(self.device))
+                    if phase == "joint" and not contacts_ready:
+                        st.enqueue_pose()                                               # this step's R / object points: same draw as the replay below
+                        st.set_contact_pairs(self._first_joint_contacts(data_dict, st.buf["object"], smpl_verts))
+                        contacts_ready = True
+                    st.step(pidx)
+                    if rows[it][RC_ESTOP] != 0.0 and st._poll_stop():
+                        stopped = True
+                        break
+                if stopped:
+                    break
+            torch.cuda.current_stream().synchronize()
+            self.last_stopped = bool(st.ctrl[34].item() != 0.0)
+            self.last_hist, self.last_terms = st._history()
+            self.last_launches = st.steps_launched
+        return smpl, obj_R, obj_t
+
+    def _optimize_smpl_object_eager(self, smpl: SMPLParams, data_dict, joint_iter, steps_per_iter, max_iter, noise_fn):
+        """The same loop with PyTorch glue, autograd and torch.optim.Adam around the operator kernels."""
         obj_R, obj_t, obj_s = data_dict["obj_R"], data_dict["obj_t"], data_dict["obj_s"]
         opt = torch.optim.Adam([{"params": obj_R, "lr": 0.002}, {"params": obj_t, "lr": 0.006}])
         weight_dict = self.get_loss_weights()
         it_sil, it_obj = self.get_opt_iters()["sil"], self.get_opt_iters()["object"]
-        prev_loss, phase, hist = 300.0, "object only", []
+        prev_loss, hist, terms = 300.0, [], []
+        self.last_stopped = False
         data_dict["smpl_center"] = self.compute_smpl_center_pred(smpl)
         with torch.no_grad():
             data_dict["_smpl_verts_frozen"] = smpl()[0].detach()
-        for it in range(joint_iter + it_obj + max_iter + it_sil):
-            if it < it_obj:
-                phase = "object only"
-            elif it == it_obj and it != it_obj + it_sil:
-                phase = "sil"
+
+        def done():
+            data_dict.pop("_smpl_verts_frozen", None)
+            self.last_hist = np.asarray(hist, np.float64)
+            self.last_terms = np.asarray([[float(ld[k]) if k in ld else np.nan for k in OBJ_TERMS] for ld in terms], np.float64)
+            return smpl, obj_R, obj_t
+        for it, (phase, new_opt, decay) in enumerate(self.object_phase_schedule(it_obj, it_sil, joint_iter, max_iter)):
+            if new_opt and phase == "sil":
                 opt = torch.optim.Adam([obj_R, obj_t], lr=0.006)
                 data_dict["rot_init"] = decopose_axis(obj_R, noise=None if noise_fn is None else noise_fn()).detach().clone()
                 data_dict["trans_init"] = obj_t.detach().clone()
-            elif it == it_obj + it_sil:
-                phase = "joint"
+            elif new_opt:
                 opt = torch.optim.Adam([obj_t], lr=0.002)
             for _ in range(steps_per_iter):
                 opt.zero_grad()
                 loss_dict = self.forward_step(smpl, data_dict, obj_R, obj_t, obj_s, phase, None if noise_fn is None else noise_fn())
-                decay = 1 if phase == "object only" else it
-                if phase == "sil":
-                    decay = it - it_obj + 1
-                elif phase == "joint":
-                    decay = (it - it_obj + 1) / 3
                 loss = self.sum_dict(loss_dict, weight_dict, decay)
                 loss.backward()
                 opt.step()
-                lv = float(loss)
-                hist.append(lv)
-                if (abs(prev_loss - lv) / prev_loss < prev_loss * 0.0001) and (it > 0.25 * max_iter) and phase == "joint":
-                    data_dict.pop("_smpl_verts_frozen", None)
-                    return smpl, obj_R, obj_t, hist
-                prev_loss = lv
-        data_dict.pop("_smpl_verts_frozen", None)
-        return smpl, obj_R, obj_t, hist
+                hist.append(float(loss)); terms.append({k: v.detach() for k, v in loss_dict.items()})
+                if bool(abs(prev_loss - loss) / prev_loss < prev_loss * 0.0001) and (it > 0.25 * max_iter) and phase == "joint":
+                    self.last_stopped = True
+                    return done()
+                prev_loss = loss.detach()
+        return done()
 
     def final_rotation(self, obj_R):
         """save_outputs stores the projection WITHOUT noise (recon_fit_base.py:303)."""

@@ -357,13 +357,23 @@ class CHORETriplaneVisibility:
                 raise ValueError(f"part_labels must be [B, N] = {(B, N)}, got {tuple(labels.shape)}")
             vals_ce, g_ce = torch.empty_like(vals_df), torch.empty_like(g_df)
         out_fwd = torch.empty(B, N_OUT, N, dtype=torch.float32, device=self.device) if fwd_mask else None
+        self.enqueue_query_losses(pts, cc, bc, df_channel, clamp_max, labels, vals_df, g_df, vals_ce, g_ce, fwd_mask, out_fwd)
+        return vals_df, g_df, vals_ce, g_ce, out_fwd
+
+    def enqueue_query_losses(self, pts, cc, bc, df_channel, clamp_max, labels, vals_df, g_df, vals_ce, g_ce, fwd_mask=0, out_fwd=None, maps=None):
+        """The bare ``vt_query_losses_tc`` launch on caller-owned, contiguous fp32 device buffers (pts [B,N,3], cc [B,2], bc [B,3], labels int64
+        [B,N] or None, outputs as in ``_query_losses_raw``): no allocation, no host synchronisation -- the form the CUDA-graph optimisation
+        steps (recon_steps.py) capture.  ``maps`` defaults to the maps of the last ``filter()`` call."""
+        im_feat, tmpx, tri_tmpx, tri_feat = self._maps if maps is None else maps
+        B, N = pts.shape[0], pts.shape[1]
+        if B != im_feat.shape[0]:
+            raise ValueError(f"points batch {B} != filtered batch {im_feat.shape[0]}")
         with torch.cuda.device(self.device):
             _lib.call("vt_query_losses_tc", _lib.ptr(pts), _lib.ptr(cc), _lib.ptr(bc), B, N, _lib.ptr(im_feat), _lib.ptr(tmpx),
                       _lib.ptr(tri_tmpx), _lib.ptr(tri_feat), im_feat.shape[1], im_feat.shape[2], tmpx.shape[1], tmpx.shape[2],
                       self._cam7, _lib.ptr(self._wpack), *(_lib.ptr(t) for t in self._wtc), *(_lib.ptr(t) for t in self._wtc_bwd),
                       int(df_channel), float(clamp_max), _lib.ptr(labels), _lib.ptr(vals_df), _lib.ptr(g_df), _lib.ptr(vals_ce),
                       _lib.ptr(g_ce), int(fwd_mask), _lib.ptr(out_fwd), _lib.ptr(self._q_overflow), _lib.stream_ptr())
-        return vals_df, g_df, vals_ce, g_ce, out_fwd
 
     def query_losses(self, points, crop_center=None, df_channel=0, clamp_max=0.1, part_labels=None, also=(), **kwargs):
         """The query-dependent loss terms of the fitters as per-point tensors, differentiable w.r.t. ``points``:
