@@ -100,8 +100,9 @@ class HGEncoder:
             if v.dim() == 4 and name == "conv1.weight":
                 self.stem_w = pack_stem(v).to(device)
             elif v.dim() == 4:
-                pk = pack_conv(v.to(device))
-                self.conv[name[:-len(".weight")]] = pk
+                # packed on the host (the checkpoint arrives there), uploaded as three plain copies: no device launches at load time
+                pk = pack_conv(v.detach().cpu())
+                self.conv[name[:-len(".weight")]] = {k: (t.to(device) if torch.is_tensor(t) else t) for k, t in pk.items()}
             else:
                 self.vec[name] = v.float().contiguous().to(device)
         self.overflow = torch.zeros(1, dtype=torch.int32, device=device)

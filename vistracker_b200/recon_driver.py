@@ -53,12 +53,27 @@ def filter_batch(net, images: torch.Tensor, chunk: int = MINI_BATCH) -> None:
     if B <= chunk:
         net.filter(images.to(net.device))
         return
-    maps = []
+    direct = net.use_graph and net.filter_streams == 1          # graph replay: each chunk's maps are copied straight into their rows
+    full, parts = None, []
     for s in range(0, B, chunk):
-        net.filter(images[s:s + chunk].to(net.device))
-        maps.append((net._maps, min(chunk, B - s)))
-    cat_view = lambda i: torch.cat([torch.cat([m[i][v * n:(v + 1) * n] for m, n in maps]) for v in range(3)])
-    net._maps = (torch.cat([m[0] for m, _ in maps]), torch.cat([m[1] for m, _ in maps]), cat_view(2), cat_view(3))
+        part = images[s:s + chunk].to(net.device)
+        n = part.shape[0]
+        if direct and full is not None:
+            net.filter(part, into=(full, s, B))
+            continue
+        net.filter(part)
+        if not direct:
+            parts.append((net._maps, n))
+            continue
+        m = net._maps                                            # first chunk: learn the map shapes, allocate the whole-batch tensors once
+        full = tuple(torch.empty((B if i < 2 else 3 * B,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device) for i, t in enumerate(m))
+        full[0][:n].copy_(m[0]); full[1][:n].copy_(m[1])
+        for v in range(3):
+            full[2][v * B:v * B + n].copy_(m[2][v * n:(v + 1) * n]); full[3][v * B:v * B + n].copy_(m[3][v * n:(v + 1) * n])
+    if not direct:                                               # eager filter (VT_FILTER_GRAPH=0 / multi-stream experiments): concatenate
+        cat_view = lambda i: torch.cat([torch.cat([m[i][v * n:(v + 1) * n] for m, n in parts]) for v in range(3)])
+        full = (torch.cat([m[0] for m, _ in parts]), torch.cat([m[1] for m, _ in parts]), cat_view(2), cat_view(3))
+    net._maps = full
 
 
 def scale_body_kpts(kpts: torch.Tensor, crop_center: torch.Tensor, crop_size: float = 1200.0, net_in_size: float = 512.0,

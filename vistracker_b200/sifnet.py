@@ -165,7 +165,7 @@ class CHORETriplaneVisibility:
         return self
 
     # ------------------------------------------------------------------ filter
-    def filter(self, images: torch.Tensor):
+    def filter(self, images: torch.Tensor, into=None):
         """CHORETriplane.filter (model/chore_triplane.py:60-95): images [B, 8, H, W] = RGB, person mask, object mask,
         3 triplane renderings.  The three triplane views go through the shared encoder as one batch of 3B.
 
@@ -183,22 +183,39 @@ class CHORETriplaneVisibility:
                 if entry is None:
                     static_in = torch.empty_like(images)
                     static_in.copy_(images)
+                    # every captured graph owns its GroupNorm-statistics arenas: a later, larger input shape must not replace (and free) a buffer
+                    # whose address an earlier graph still memsets and accumulates into on replay
+                    for e in (self._rgb, self._tri):
+                        e.arena = None
                     self._filter_eager(static_in)                       # warm-up: lazy one-time initialisation stays outside the capture
                     torch.cuda.current_stream().synchronize()
                     graph = torch.cuda.CUDAGraph()
                     with torch.cuda.graph(graph):
                         maps = self._filter_eager(static_in)
-                    entry = (graph, static_in, maps, self._rgb.launches + self._tri.launches)
+                    entry = (graph, static_in, maps, self._rgb.launches + self._tri.launches, (self._rgb.arena, self._tri.arena))
+                    for e in (self._rgb, self._tri):
+                        e.arena = None                                  # eager calls after this allocate their own
                     if len(self._graphs) >= 4:                          # bound the memory held by graph-private pools
                         self._graphs.pop(next(iter(self._graphs)))
                     self._graphs[key] = entry
-                graph, static_in, static_maps, launches = entry
+                graph, static_in, static_maps, launches, _arenas = entry
                 static_in.copy_(images)
                 graph.replay()
                 # the graph writes into its private buffers; hand out copies so that maps kept from an earlier filter() call stay valid,
                 # as with the reference's freshly allocated tensors (0.57 GB at B = 8: ~0.2 ms, < 1 % of the step)
-                maps = tuple(t.clone() for t in static_maps)
-                self.launches_filter = launches + len(maps)
+                if into is None:
+                    maps = tuple(t.clone() for t in static_maps)
+                else:
+                    # chunked filter of a larger batch (recon_driver.filter_batch): this chunk's maps go straight into their rows of the
+                    # whole-batch tensors -- one copy instead of clone + torch.cat
+                    full, s0, Bt = into
+                    n = images.shape[0]
+                    full[0][s0:s0 + n].copy_(static_maps[0]); full[1][s0:s0 + n].copy_(static_maps[1])
+                    for v in range(3):
+                        full[2][v * Bt + s0:v * Bt + s0 + n].copy_(static_maps[2][v * n:(v + 1) * n])
+                        full[3][v * Bt + s0:v * Bt + s0 + n].copy_(static_maps[3][v * n:(v + 1) * n])
+                    maps = static_maps
+                self.launches_filter = launches + 4
             else:
                 maps = self._filter_eager(images)
                 self.launches_filter = self._rgb.launches + self._tri.launches

@@ -211,3 +211,54 @@ def synthetic_camera_frame(H: int = 1536, W: int = 2048, seed: int = 0, center=N
     u, v = (xx - cx - 0.9 * a) * 0.8 + (yy - cy) * 0.6, -(xx - cx - 0.9 * a) * 0.6 + (yy - cy) * 0.8
     obj = np.clip((1.0 - np.maximum(np.abs(u) / (0.7 * a), np.abs(v) / (0.5 * a))) * 10, 0, 1)
     return rgb, (person * 255).astype(np.uint8), (obj * 255).astype(np.uint8)
+
+
+def synthetic_recon_batch(frames: int = 96, size: int = 512, seed: int = 4, n_obj_points: int = 3000, obj_rings: int = 20, obj_segments: int = 20):
+    """One batch of BASELINE config 4 (joint optimisation): everything ``recon_driver.fit_recon_batch`` reads, as host
+    tensors.  Frames are temporally coherent where it matters for the optimiser (SMPL-T initialisation = a smooth random walk, object
+    rotation = a slow drift, object and person masks = blobs that follow the projected object / body), the RGB content is noise (the
+    network weights are random-init as well).
+
+    Returns dict: images [T,8,S,S] fp32, crop_center [T,2], body_center [T,3], pose [T,156], betas [T,10], trans [T,3], body_kpts [T,25,3]
+    (network-input pixels, confidence), obj_verts [V,3] / obj_faces [F,3] (closed template, ~800 faces as the BEHAVE templates),
+    obj_points [n,3] (surface samples), obj_rot_init [T,3,3], occ_ratios [T]."""
+    from .synth_smpl import synthetic_body_mesh, synthetic_motion
+    rng = np.random.Generator(np.random.PCG64(seed))
+    T, S = frames, size
+    pose, betas, trans = synthetic_motion(T, seed=seed + 11)
+    img = rng.random((T, 8, S, S), dtype=np.float32)
+    img[:, 5:] = (img[:, 5:] > 0.5).astype(np.float32)
+    crop = (np.array([[1024.0, 768.0]]) + np.cumsum(rng.standard_normal((T, 2)) * 3.0, 0)).astype(np.float32)
+    body = (trans.numpy() + np.array([0.0, -0.25, 0.0])).astype(np.float32)             # body-25 joint 8 sits near the pelvis
+    # object: an ellipsoid template 0.35 m beside the body, drifting slowly
+    ov, of = synthetic_body_mesh(rings=obj_rings, segments=obj_segments, radii=(0.3, 0.25, 0.2))
+    p = rng.standard_normal((n_obj_points, 3)); p /= np.linalg.norm(p, axis=1, keepdims=True)
+    obj_points = (p * np.array([0.3, 0.25, 0.2])).astype(np.float32)
+    obj_center = body + np.array([0.35, 0.0, 0.1], np.float32) + np.cumsum(rng.standard_normal((T, 3)) * 0.004, 0).astype(np.float32)
+    ang = np.cumsum(rng.standard_normal((T, 3)) * 0.02, 0) + rng.standard_normal(3) * 0.3
+    cx, sx, cy, sy, cz, sz = np.cos(ang[:, 0]), np.sin(ang[:, 0]), np.cos(ang[:, 1]), np.sin(ang[:, 1]), np.cos(ang[:, 2]), np.sin(ang[:, 2])
+    Rm = np.zeros((T, 3, 3), np.float32)
+    Rm[:, 0, 0], Rm[:, 0, 1], Rm[:, 0, 2] = cy * cz, -cy * sz, sy
+    Rm[:, 1, 0], Rm[:, 1, 1], Rm[:, 1, 2] = sx * sy * cz + cx * sz, -sx * sy * sz + cx * cz, -sx * cy
+    Rm[:, 2, 0], Rm[:, 2, 1], Rm[:, 2, 2] = -cx * sy * cz + sx * sz, cx * sy * sz + sx * cz, cx * cy
+    # masks in network-input pixels: an ellipse where the object projects, a box around the body
+    to_px = lambda c: ((600 + 979.7844 * c[:, 0] / c[:, 2] + 1018.952 - crop[:, 0]) * S / 1200, (600 + 979.840 * c[:, 1] / c[:, 2] + 779.486 - crop[:, 1]) * S / 1200)
+    ox, oy = to_px(obj_center)
+    bx, by = to_px(body)
+    yy, xx = np.mgrid[0:S, 0:S].astype(np.float32)
+    r_obj = 0.27 * 979.8 / obj_center[:, 2] * S / 1200
+    obj_mask = (((xx[None] - ox[:, None, None]) / (1.15 * r_obj[:, None, None])) ** 2 + ((yy[None] - oy[:, None, None]) / (0.9 * r_obj[:, None, None])) ** 2) < 1
+    hw, hh = 0.22 * 979.8 / body[:, 2] * S / 1200, 0.85 * 979.8 / body[:, 2] * S / 1200
+    person_mask = (np.abs(xx[None] - bx[:, None, None]) < hw[:, None, None]) & (np.abs(yy[None] - by[:, None, None]) < hh[:, None, None])
+    img[:, 3], img[:, 4] = person_mask.astype(np.float32), obj_mask.astype(np.float32)
+    img[:, :3] *= np.maximum(img[:, 3:4], img[:, 4:5])
+    # 2-D key points: a rigid joint cloud riding on the body centre, projected into the crop, + 2 px noise
+    off = rng.standard_normal((1, 25, 3)) * np.array([0.25, 0.45, 0.12])
+    J = body[:, None, :] + off
+    kx = (600 + 979.7844 * J[..., 0] / J[..., 2] + 1018.952 - crop[:, 0:1]) * S / 1200 + rng.standard_normal((T, 25)) * 2
+    ky = (600 + 979.840 * J[..., 1] / J[..., 2] + 779.486 - crop[:, 1:2]) * S / 1200 + rng.standard_normal((T, 25)) * 2
+    kpts = np.stack([kx, ky, rng.uniform(0.3, 1.0, (T, 25))], -1).astype(np.float32)
+    t = torch.from_numpy
+    return {"images": t(img), "crop_center": t(crop), "body_center": t(body), "pose": pose, "betas": betas, "trans": trans, "body_kpts": t(kpts),
+            "obj_verts": t(ov), "obj_faces": t(np.asarray(of, np.int64)), "obj_points": t(obj_points), "obj_rot_init": t(Rm),
+            "occ_ratios": t(rng.uniform(0.4, 1.0, T).astype(np.float32))}
