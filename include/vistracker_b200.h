@@ -173,6 +173,18 @@ int vt_query_losses_tc(const float* points, const float* crop_center, const floa
                        const void* w23t_lo, const void* w1t_hi, const void* w1t_lo, int df_idx, float clamp_max, const long long* part_labels,
                        float* vals_df, float* g_df, float* vals_ce, float* g_ce, int fwd_mask, float* out_fwd, int* overflow, void* stream);
 
+/* vt_query_losses_tc with the two heads MERGED (the SMPL refinement step, recon/recon_fit_behave.py:471-476): the caller's loss weights
+ * w_df = *w_df * w_df_mul and w_ce = *w_ce * w_ce_mul (device scalars times host factors, e.g. the schedule word and 1 / (B N)) are folded into
+ * the cotangents, both heads' hidden-layer gradients stay in tensor memory and accumulate into one feature-gradient tile, and the second
+ * gather (the contraction with d feature / d point) runs once: g_points[B][N][3] = w_df d clamp(df) / d point + w_ce d CE / d point.
+ * vals_df / vals_ce as in vt_query_losses_tc. */
+int vt_query_losses_merged_tc(const float* points, const float* crop_center, const float* body_center, int B, int N, const float* im_feat,
+                              const float* tmpx, const float* tri_tmpx, const float* tri_feat, int Hf, int Wf, int Ht, int Wt, const float* cam7,
+                              const float* wpack, const void* w1_hi, const void* w1_lo, const void* w23_hi, const void* w23_lo, const void* w23t_hi,
+                              const void* w23t_lo, const void* w1t_hi, const void* w1t_lo, int df_idx, float clamp_max, const long long* part_labels,
+                              const float* w_df, float w_df_mul, const float* w_ce, float w_ce_mul, float* vals_df, float* vals_ce, float* g_points,
+                              int* overflow, void* stream);
+
 /* ---- SMPL-H layer: SMPL_Layer.forward (lib_smpl/smplpytorch/smplpytorch/pytorch/smpl_layer.py:73-176) and its gradient
  *      w.r.t. pose / betas / trans; landmark regressors (lib_smpl/torch_functions.py:52-76, wrapper_pytorch.py:187-203) ---- */
 

@@ -53,6 +53,21 @@ def test_chunked_filter_equals_one_call():
         assert a.shape == b.shape and float((a - b).abs().max()) <= 1e-5 * float(a.abs().max())
 
 
+def test_maps_kept_from_the_generator_equal_a_second_filter():
+    """fit_recon_batch keeps the feature maps of the generator's per-mini-batch filter calls instead of filtering the whole batch again
+    (recon_fit_triplane.py:57-60): both give the same maps (GroupNorm statistics are summed with atomics: equal to rounding)."""
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    from vistracker_b200.recon_driver import filter_batch, generate_all
+    dev, net, fitter, gen, data, *_rest = _setup(5)
+    torch.manual_seed(0)
+    generate_all(gen, data, mini_batch_size=2, keep_maps=True)
+    kept = [m.clone() for m in net._maps]
+    filter_batch(net, data["images"], chunk=2)
+    for a, b in zip(kept, net._maps):
+        assert a.shape == b.shape and float((a - b).abs().max()) <= 1e-5 * float(b.abs().max())
+
+
 def test_fit_recon_batch_runs_end_to_end():
     if not torch.cuda.is_available():
         pytest.skip("needs a CUDA device")

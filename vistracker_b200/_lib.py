@@ -35,6 +35,7 @@ SIGNATURES = {
     "vt_query_project_step_tc": (_i, [_p, _p, _p, _i, _i, _p, _p, _p, _p, _i, _i, _i, _i, _p, _p] + [_p] * 8 + [_i, _f, _p, _p, _p, _p]),
     "vt_query_fwd_tc_heads": (_i, [_p, _p, _p, _i, _i, _p, _p, _p, _p, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _i, _p, _p, _p, _p]),
     "vt_query_losses_tc": (_i, [_p, _p, _p, _i, _i, _p, _p, _p, _p, _i, _i, _i, _i, _p, _p] + [_p] * 8 + [_i, _f, _p, _p, _p, _p, _p, _i, _p, _p, _p]),
+    "vt_query_losses_merged_tc": (_i, [_p, _p, _p, _i, _i, _p, _p, _p, _p, _i, _i, _i, _i, _p, _p] + [_p] * 8 + [_i, _f, _p, _p, _f, _p, _f, _p, _p, _p, _p, _p]),
     "vt_query_wpack_bwd_floats": (_ll, []),
     "vt_query_bwd": (_i, [_p, _p, _p, _i, _i, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p]),
 }

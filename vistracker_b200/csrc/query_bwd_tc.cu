@@ -41,7 +41,29 @@ struct TbParams {
   int fwd_mask;            // mode 2: heads evaluated forward-only (they share the gather; no backward) ...
   float* out_fwd;          // ... into the packed [B][29][N] prediction buffer
   long long* trace;        // debug (VT_QUERY_TRACE=1): clock64 stamps of CTA (0,0): [0..15] epilogue thread 0, [16..31] gather warp 0
+  // mode 2, merged heads (both pointers set, labels given): the caller's loss weights w_df = *w_df_ptr * w_df_mul, w_ce = *w_ce_ptr * w_ce_mul are
+  // folded into the cotangents at the head outputs, both heads' g1 stay in tensor memory and accumulate into ONE feature-gradient tile, so the
+  // backward gather-dot runs once per tile: g_points = w_df d clamp(df) / d point + w_ce d CE / d point (g_points2 is not written)
+  const float* w_df_ptr; const float* w_ce_ptr; float w_df_mul, w_ce_mul;
 };
+
+// tcgen05.mma with the A operand in tensor memory (fp16 pairs packed K-contiguous: element k of row m at lane m, column k / 2, half k & 1)
+__device__ __forceinline__ void tb_mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t accumulate) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+               ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(TQ_IDESC), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tb_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+               ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+                 "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]) : "memory");
+}
+__device__ __forceinline__ void tb_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+                 "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+               : "r"(taddr) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
 
 // power-of-two normalisation of a non-negative maximum: returns e with 2^-e * m in [0.5, 1) (0 for m == 0 / non-finite)
 __device__ __forceinline__ int tb_norm_exp(float m) {
@@ -82,6 +104,7 @@ query_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_c
   const int b = blockIdx.y, n0 = blockIdx.x * TQ_M;
   const int heads = prm.mode == 1 ? 1 : prm.mode == 2 ? ((prm.labels ? 5 : 1) | prm.fwd_mask) : prm.head_mask;
   auto fwd_only = [&](int h) { return prm.mode == 2 && ((prm.fwd_mask >> h) & 1) != 0; };
+  const bool merge = prm.mode == 2 && prm.labels != nullptr && prm.w_df_ptr != nullptr && prm.w_ce_ptr != nullptr;   // heads 0 and 2 as ONE pair
   // heads are processed in pairs that share ONE forward gather: both first layers accumulate from the same feature chunks (TMEM
   // columns 0-127 and 128-255), then each head runs its own forward / backward chain and backward gather; gf slots start at column 256
   const int n_heads = __popc((unsigned)heads), n_pairs = (n_heads + 1) >> 1;
@@ -144,7 +167,7 @@ query_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_c
     const int sub = lane >> 4, k = (lane & 15) * 4;
     constexpr int PB = 4;                                   // point PAIRS in flight per warp
     constexpr int PW = TQ_M / TQ_GATHER_WARPS;              // 16 points per warp
-    constexpr int PBB = 2;                                  // ... and in the backward contraction (more live registers per point);
+    constexpr int PBB = 2, NGRP = 2;                        // ... and in the backward contraction: NGRP groups of PBB point pairs;
     static_assert(PBB == 2, "the butterfly reduction below handles exactly two points per half-warp");
     for (int i = lane; i < PW * 3; i += 32) (&s_gacc[gw * PW][0])[i] = 0.f;      // each warp owns the rows of its 16 points
     __syncwarp();
@@ -205,6 +228,7 @@ query_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_c
       const int h = pair_head(pi, pj);
       if (h < 0) break;
       if (fwd_only(h)) continue;
+      if (merge && pj == 0) continue;                       // merged heads: one staged feature-gradient tile, after the second head's chain
       // ---- backward: contract the staged feature gradients with d(feature)/d(u, v) (second gather of the same taps)
       for (int c = 0; c < TQ_NCHUNK; ++c, ++sc) {
         const int slot = sc & 1;
@@ -215,39 +239,41 @@ query_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_c
         const bool full_res = (c < 4) || (c >= 5 && c < 8);                // im_feat / tri_feat maps (Hf x Wf); else tmpx-sized maps
         const float su = 0.5f * (float)((full_res ? m.Wf : m.Wt) - 1), sv = 0.5f * (float)((full_res ? m.Hf : m.Ht) - 1);
 #pragma unroll 1
-        for (int i0 = 0; i0 < PW; i0 += 2 * PBB) {
-          TqTap tap[PBB];
-          float4 g[PBB];
+        for (int i0 = 0; i0 < PW; i0 += 2 * PBB * NGRP) {
+          // d(feature)/d(u, v) of a bilinear sample is linear in the four taps, so the contraction with the staged feature gradient reduces to
+          // four dot products per point -- D_ab = sum_k gf_k * tap_ab_k, 16 FMAs per lane -- and the (1 - t, t) blend is applied to the four
+          // scalars afterwards (the previous form blended every feature: ~44 operations per lane).  The taps of NGRP groups of two point
+          // pairs are requested before the first group is reduced: twice the loads in flight per warp (the loop is L2-latency-bound).
+          TqTap tap[NGRP][PBB];
+          float4 t00[NGRP][PBB], t01[NGRP][PBB], t10[NGRP][PBB], t11[NGRP][PBB];
 #pragma unroll
-          for (int j = 0; j < PBB; ++j) {
-            const int pp = gw * PW + i0 + 2 * j + sub;
-            tap[j] = tq_tap_get(s_tap, src, pp);
-            g[j] = *reinterpret_cast<const float4*>(stg + pp * 256 + (((lane & 15) ^ (pp & 15)) << 4));
-          }
-          float4 t00[PBB], t01[PBB], t10[PBB], t11[PBB];
+          for (int gq = 0; gq < NGRP; ++gq)
 #pragma unroll
-          for (int j = 0; j < PBB; ++j) {
-            const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-            t00[j] = (tap[j].valid & 1u) ? ld4(tap[j].p) : z;
-            t01[j] = (tap[j].valid & 2u) ? ld4(tap[j].p + tap[j].C) : z;
-            t10[j] = (tap[j].valid & 4u) ? ld4(tap[j].p + tap[j].rowstride) : z;
-            t11[j] = (tap[j].valid & 8u) ? ld4(tap[j].p + tap[j].rowstride + tap[j].C) : z;
-          }
+            for (int j = 0; j < PBB; ++j) {
+              tap[gq][j] = tq_tap_get(s_tap, src, gw * PW + i0 + gq * 2 * PBB + 2 * j + sub);
+              const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+              t00[gq][j] = (tap[gq][j].valid & 1u) ? ld4(tap[gq][j].p) : z;
+              t01[gq][j] = (tap[gq][j].valid & 2u) ? ld4(tap[gq][j].p + tap[gq][j].C) : z;
+              t10[gq][j] = (tap[gq][j].valid & 4u) ? ld4(tap[gq][j].p + tap[gq][j].rowstride) : z;
+              t11[gq][j] = (tap[gq][j].valid & 8u) ? ld4(tap[gq][j].p + tap[gq][j].rowstride + tap[gq][j].C) : z;
+            }
+#pragma unroll
+          for (int gq = 0; gq < NGRP; ++gq) {
+          const int ib = i0 + gq * 2 * PBB;
           float red[8];                                              // (gx, gy, gz) of the two points of this half-warp + 2 pads
           red[6] = 0.f; red[7] = 0.f;
 #pragma unroll
           for (int j = 0; j < PBB; ++j) {
-            const int pp = gw * PW + i0 + 2 * j + sub;
+            const int pp = gw * PW + ib + 2 * j + sub;
+            const float4 g = *reinterpret_cast<const float4*>(stg + pp * 256 + (((lane & 15) ^ (pp & 15)) << 4));
             const float scale = ldexpf(1.f, s_scale_e[pp]);
-            const float tx = tap[j].tx, ty = tap[j].ty;
-            float dix = g[j].x * ((t01[j].x - t00[j].x) * (1.f - ty) + (t11[j].x - t10[j].x) * ty) +
-                        g[j].y * ((t01[j].y - t00[j].y) * (1.f - ty) + (t11[j].y - t10[j].y) * ty) +
-                        g[j].z * ((t01[j].z - t00[j].z) * (1.f - ty) + (t11[j].z - t10[j].z) * ty) +
-                        g[j].w * ((t01[j].w - t00[j].w) * (1.f - ty) + (t11[j].w - t10[j].w) * ty);
-            float diy = g[j].x * ((t10[j].x - t00[j].x) * (1.f - tx) + (t11[j].x - t01[j].x) * tx) +
-                        g[j].y * ((t10[j].y - t00[j].y) * (1.f - tx) + (t11[j].y - t01[j].y) * tx) +
-                        g[j].z * ((t10[j].z - t00[j].z) * (1.f - tx) + (t11[j].z - t01[j].z) * tx) +
-                        g[j].w * ((t10[j].w - t00[j].w) * (1.f - tx) + (t11[j].w - t01[j].w) * tx);
+            const float tx = tap[gq][j].tx, ty = tap[gq][j].ty;
+            const float d00 = fmaf(g.w, t00[gq][j].w, fmaf(g.z, t00[gq][j].z, fmaf(g.y, t00[gq][j].y, g.x * t00[gq][j].x)));
+            const float d01 = fmaf(g.w, t01[gq][j].w, fmaf(g.z, t01[gq][j].z, fmaf(g.y, t01[gq][j].y, g.x * t01[gq][j].x)));
+            const float d10 = fmaf(g.w, t10[gq][j].w, fmaf(g.z, t10[gq][j].z, fmaf(g.y, t10[gq][j].y, g.x * t10[gq][j].x)));
+            const float d11 = fmaf(g.w, t11[gq][j].w, fmaf(g.z, t11[gq][j].z, fmaf(g.y, t11[gq][j].y, g.x * t11[gq][j].x)));
+            const float dix = (d01 - d00) * (1.f - ty) + (d11 - d10) * ty;
+            const float diy = (d10 - d00) * (1.f - tx) + (d11 - d01) * tx;
             const float gu = dix * su * scale, gv = diy * sv * scale;
             float gx = 0.f, gy = 0.f, gz = 0.f;
             if (src.view < 0) {           // perspective: nx = 2 (crop/2 + fx x / z + cx - ccx) / crop - 1
@@ -262,7 +288,7 @@ query_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_c
             } else if (src.view == 2) {   // top: (x, -z)
               gx = gu; gz = -gv;
             } else if (src.direct) {      // the (x, y, z - z0) inputs themselves
-              gx = g[j].x * scale; gy = g[j].y * scale; gz = g[j].z * scale;
+              gx = g.x * scale; gy = g.y * scale; gz = g.z * scale;
             }
             red[3 * j] = gx; red[3 * j + 1] = gy; red[3 * j + 2] = gz;
           }
@@ -286,8 +312,9 @@ query_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_c
             }
             red[0] += __shfl_xor_sync(0xffffffffu, red[0], 1);
             const int idx = (u8 ? 4 : 0) + (u4 ? 2 : 0) + (u2 ? 1 : 0);
-            if ((lane & 1) == 0 && idx < 6) s_gacc[gw * PW + i0 + 2 * (idx / 3) + sub][idx % 3] += red[0];
+            if ((lane & 1) == 0 && idx < 6) s_gacc[gw * PW + ib + 2 * (idx / 3) + sub][idx % 3] += red[0];
           }
+          }   // groups
         }
         __syncwarp();
         if (lane == 0) tq_mbar_arrive(tq_smem_u32(&stg_empty[slot]));
@@ -298,7 +325,7 @@ query_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_c
         if (lane < PW) {
           const int pp = gw * PW + lane, n = n0 + pp;
           if (n < N) {
-            float* gp = (h == 0 ? prm.g_points : prm.g_points2) + ((size_t)b * N + n) * 3;
+            float* gp = ((h == 0 || merge) ? prm.g_points : prm.g_points2) + ((size_t)b * N + n) * 3;
             gp[0] = s_gacc[pp][0]; gp[1] = s_gacc[pp][1]; gp[2] = s_gacc[pp][2];
           }
           s_gacc[pp][0] = 0.f; s_gacc[pp][1] = 0.f; s_gacc[pp][2] = 0.f;
@@ -349,6 +376,13 @@ query_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_c
           if (fwd_only(h)) continue;
           for (int layer = 1; layer >= 0; --layer)
             for (int kc = 0; kc < 2; ++kc) load(&tm_w23t_hi, &tm_w23t_lo, kc * TQ_KC, (layer * 5 + h) * TQ_H);
+          if (merge) {
+            if (pj == 0) continue;
+            for (int u = 0; u < TQ_NCHUNK / 2; ++u)                      // merged B1: per column group the W1^T tiles of both heads
+              for (int q = 0; q < 4; ++q)
+                load(&tm_w1t_hi, &tm_w1t_lo, (q & 1) * TQ_KC, (q < 2 ? hA : hB) * TQ_NCHUNK * TQ_KC + u * TQ_H);
+            continue;
+          }
           for (int u = 0; u < TQ_NCHUNK / 2; ++u)
             for (int kc = 0; kc < 2; ++kc) load(&tm_w1t_hi, &tm_w1t_lo, kc * TQ_KC, h * TQ_NCHUNK * TQ_KC + u * TQ_H);
         }
@@ -397,6 +431,35 @@ query_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_c
           tq_mbar_wait(tq_smem_u32(&act_full), (uint32_t)iact & 1u); ++iact;   // g1 is in the act buffer (forward-only head: its
           tq_fence_after();                                                    // accumulator has been read out and may be reused)
           if (fo) continue;
+          if (merge) {
+            if (pj == 0) continue;                                      // g1 of the first head waits in tensor memory (its accumulator columns)
+            for (int u = 0; u < TQ_NCHUNK / 2; ++u, ++gfi) {            // merged B1: gf = g1_A W1_A + g1_B W1_B, A operands from tensor memory
+              const int gs = gfi % TB_NGF;
+              tq_mbar_wait(tq_smem_u32(&gf_empty[gs]), ((uint32_t)(gfi / TB_NGF) & 1u) ^ 1u);
+              tq_fence_after();
+              for (int q = 0; q < 4; ++q) {
+                const int s = iw % TQ_NW;
+                tq_mbar_wait(tq_smem_u32(&w_full[s]), (uint32_t)(iw / TQ_NW) & 1u);
+                tq_fence_after();
+                const uint64_t b_hi = tq_desc(w_base + s * TQ_SLOT), b_lo = tq_desc(w_base + s * TQ_SLOT + TQ_PLANE);
+                const uint32_t a_base = tmem_base + (q < 2 ? 0 : TQ_H), d = tmem_base + 2 * TQ_H + gs * TQ_H;
+#pragma unroll
+                for (int kk = 0; kk < TQ_KC / 16; ++kk) {
+                  // K step of 16 elements = 8 columns; per 32-element chunk the layout is [hi: 16 columns | lo: 16 columns]
+                  const int kg = (q & 1) * TQ_KC + kk * 16;
+                  const uint32_t a_hi = a_base + (kg >> 5) * 32 + ((kg >> 4) & 1) * 8, a_lo = a_hi + 16;
+                  const uint64_t adv = (uint64_t)(kk * 32 >> 4);
+                  tb_mma_ts(d, a_hi, b_hi + adv, (q == 0 && kk == 0) ? 0u : 1u);
+                  tb_mma_ts(d, a_hi, b_lo + adv, 1u);
+                  tb_mma_ts(d, a_lo, b_hi + adv, 1u);
+                }
+                tq_commit(tq_smem_u32(&w_empty[s]));
+                ++iw;
+              }
+              tq_commit(tq_smem_u32(&gf_full[gs]));
+            }
+            continue;
+          }
           for (int u = 0; u < TQ_NCHUNK / 2; ++u, ++gfi) {              // B1: five groups of 128 feature-gradient columns
             const int gs = gfi % TB_NGF;
             tq_mbar_wait(tq_smem_u32(&gf_empty[gs]), ((uint32_t)(gfi / TB_NGF) & 1u) ^ 1u);
@@ -537,6 +600,7 @@ query_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_c
             g = val;                                       // mode 2: keep the logit, turned into softmax - onehot below
           }
           if (h == 0 && !s_in_img[r]) g = 0.f;
+          if (merge && h == 0) g *= __ldg(prm.w_df_ptr) * prm.w_df_mul;
         }
         g4[c] = g;
         gmax = fmaxf(gmax, fabsf(g));
@@ -553,8 +617,9 @@ query_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_c
           for (int c = 0; c < 14; ++c) { if (c == lab) l_lab = g4[c]; g4[c] = expf(g4[c] - mx); sum += g4[c]; }
           prm.vals_ce[(size_t)b * N + n] = logf(sum) - (l_lab - mx);
           const float inv_sum = 1.f / sum;
+          const float wce = merge ? __ldg(prm.w_ce_ptr) * prm.w_ce_mul : 1.f;
 #pragma unroll
-          for (int c = 0; c < 14; ++c) { g4[c] = g4[c] * inv_sum - (c == lab ? 1.f : 0.f); gmax = fmaxf(gmax, fabsf(g4[c])); }
+          for (int c = 0; c < 14; ++c) { g4[c] = (g4[c] * inv_sum - (c == lab ? 1.f : 0.f)) * wce; gmax = fmaxf(gmax, fabsf(g4[c])); }
         } else {
 #pragma unroll
           for (int c = 0; c < 14; ++c) g4[c] = 0.f;
@@ -612,6 +677,48 @@ query_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_c
         }
         const int e = tb_norm_exp(vmax);
         e_total += e;
+        if (merge && bl == 0) {
+          // g1 of this head stays in TENSOR MEMORY, written over its own accumulator columns (per 32-column chunk: 16 columns of packed hi
+          // pairs, 16 of lo pairs), as the A operand of the merged B1 product.  Both heads must share one per-point exponent E = max(e_A, e_B):
+          // the second head scales its own values on the way in and, if it raised E, rescales the first head's columns (powers of two: exact).
+          int E = e_total;
+          if (pj == 1) E = max(E, s_scale_e[r]);
+          const float inv = ldexpf(1.f, -e + (e_total - E));
+#pragma unroll 1
+          for (int ch = 0; ch < 4; ++ch) {
+            float v[32];
+            tq_ld32(acc_base + ch * 32, v);
+            const uint32_t mk = s_mask[bl][ch][r];
+            uint32_t hi[16], lo[16];
+#pragma unroll
+            for (int i = 0; i < 32; i += 2) {
+              const float a = ((mk >> i) & 1u) ? v[i] * inv : 0.f, c2 = ((mk >> (i + 1)) & 1u) ? v[i + 1] * inv : 0.f;
+              tq_split2(a, c2, hi[i >> 1], lo[i >> 1], amax);
+            }
+            tb_st16(acc_base + ch * 32, hi);
+            tb_st16(acc_base + ch * 32 + 16, lo);
+          }
+          if (pj == 1 && s_scale_e[r] < E) {
+            const __half2 sc2 = __float2half2_rn(ldexpf(1.f, s_scale_e[r] - E));
+            const uint32_t other = lane_base;               // the first head's accumulator columns
+#pragma unroll 1
+            for (int q = 0; q < 8; ++q) {
+              uint32_t w[16];
+              tb_ld16(other + q * 16, w);
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                const __half2 t = __hmul2(*reinterpret_cast<const __half2*>(&w[i]), sc2);
+                w[i] = *reinterpret_cast<const uint32_t*>(&t);
+              }
+              tb_st16(other + q * 16, w);
+            }
+          }
+          asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+          s_scale_e[r] = E;
+          publish_act();
+          TB_STAMP();
+          continue;
+        }
         const float inv = ldexpf(1.f, -e);
 #pragma unroll 1
         for (int ch = 0; ch < 4; ++ch) {
@@ -626,6 +733,7 @@ query_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_c
         publish_act();
         TB_STAMP();
       }
+      if (merge && pj == 0) continue;                      // the feature gradients of both heads are drained together, after the second head
       // ---- drain gf (five 128-column groups) into the fp32 staging ring for the gather warps
       for (int u = 0; u < TQ_NCHUNK / 2; ++u, ++gfi) {
         const int gs = gfi % TB_NGF;
@@ -749,6 +857,23 @@ int vt_query_losses_tc(const float* points, const float* crop_center, const floa
   TbParams prm{nullptr, g_df, nullptr, 2, df_idx, 0, clamp_max, part_labels, vals_df, vals_ce, g_ce, fwd_mask, out_fwd, nullptr};
   return launch_bwd_tc(points, crop_center, body_center, B, N, im_feat, tmpx, tri_tmpx, tri_feat, Hf, Wf, Ht, Wt, cam7, wpack, planes, prm,
                        overflow, (cudaStream_t)stream, "vt_query_losses_tc");
+}
+
+int vt_query_losses_merged_tc(const float* points, const float* crop_center, const float* body_center, int B, int N, const float* im_feat,
+                              const float* tmpx, const float* tri_tmpx, const float* tri_feat, int Hf, int Wf, int Ht, int Wt, const float* cam7,
+                              const float* wpack, const void* w1_hi, const void* w1_lo, const void* w23_hi, const void* w23_lo, const void* w23t_hi,
+                              const void* w23t_lo, const void* w1t_hi, const void* w1t_lo, int df_idx, float clamp_max, const long long* part_labels,
+                              const float* w_df, float w_df_mul, const float* w_ce, float w_ce_mul, float* vals_df, float* vals_ce, float* g_points,
+                              int* overflow, void* stream) {
+  VT_CHECK_ARG(df_idx == 0 || df_idx == 1, "vt_query_losses_merged_tc: df_idx %d (0 human, 1 object)", df_idx);
+  VT_CHECK_ARG(part_labels != nullptr && w_df != nullptr && w_ce != nullptr, "vt_query_losses_merged_tc: part_labels and both weight pointers are required");
+  VT_CHECK_ARG(vals_df != nullptr && vals_ce != nullptr && g_points != nullptr && overflow != nullptr,
+               "vt_query_losses_merged_tc: vals_df, vals_ce, g_points and overflow are required");
+  if (B <= 0 || N <= 0) return 0;
+  const void* planes[8] = {w1_hi, w1_lo, w23_hi, w23_lo, w23t_hi, w23t_lo, w1t_hi, w1t_lo};
+  TbParams prm{nullptr, g_points, nullptr, 2, df_idx, 0, clamp_max, part_labels, vals_df, vals_ce, nullptr, 0, nullptr, nullptr, w_df, w_ce, w_df_mul, w_ce_mul};
+  return launch_bwd_tc(points, crop_center, body_center, B, N, im_feat, tmpx, tri_tmpx, tri_feat, Hf, Wf, Ht, Wt, cam7, wpack, planes, prm,
+                       overflow, (cudaStream_t)stream, "vt_query_losses_merged_tc");
 }
 
 }  // extern "C"

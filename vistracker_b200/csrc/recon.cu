@@ -49,7 +49,9 @@ __global__ void recon_point_terms_kernel(PointTerms p, const float* __restrict__
   const bool temporal = B >= 4;                                        // `if verts.shape[0] < 4: return`
   const float kmul = p.use_k ? ctrl[RC_TEMP_K] : 1.f;
   const float w2 = (p.iw2 >= 0 && temporal) ? ctrl[p.iw2] * kmul : 0.f, w1 = (p.iw1 >= 0 && temporal) ? ctrl[p.iw1] * kmul : 0.f;
-  const float wA = p.iwA >= 0 ? ctrl[p.iwA] / p.denA : 0.f, wB = p.iwB >= 0 ? ctrl[p.iwB] / p.denB : 0.f;
+  // weight index -2: the gradient tensor already carries its loss weight (merged query-loss launch) -> coefficient 1 / den
+  const float wA = p.iwA >= 0 ? ctrl[p.iwA] / p.denA : (p.iwA == -2 ? 1.f / p.denA : 0.f);
+  const float wB = p.iwB >= 0 ? ctrl[p.iwB] / p.denB : (p.iwB == -2 ? 1.f / p.denB : 0.f);
   float l2 = 0.f, l1 = 0.f, lA = 0.f, lB = 0.f;
   if (i < n) {
     const float k2 = temporal ? w2 * 2.f / ((float)(B - 2) * (float)n) : 0.f, k1 = temporal ? w1 * 2.f / ((float)(B - 1) * (float)n) : 0.f;
@@ -67,15 +69,13 @@ __global__ void recon_point_terms_kernel(PointTerms p, const float* __restrict__
         l1 += dm * dm;
       }
       const size_t e = (size_t)s * n + i;
-      if (p.gA) {
+      if (p.gA || p.valsA) {
         const float f = p.frameA ? p.frameA[s] : 1.f;
-        g += wA * f * p.gA[e];
-        if (i % 3 == 0) lA += f * p.valsA[(size_t)s * (n / 3) + i / 3];
+        if (p.gA) g += wA * f * p.gA[e];
+        if (p.valsA && i % 3 == 0) lA += f * p.valsA[(size_t)s * (n / 3) + i / 3];
       }
-      if (p.gB) {
-        g += wB * p.gB[e];
-        if (i % 3 == 0) lB += p.valsB[(size_t)s * (n / 3) + i / 3];
-      }
+      if (p.gB) g += wB * p.gB[e];
+      if (p.valsB && i % 3 == 0) lB += p.valsB[(size_t)s * (n / 3) + i / 3];
       p.g[e] = g;
       v0 = v1; v1 = v2; v2 = v3; v3 = v4;
     }
@@ -84,8 +84,8 @@ __global__ void recon_point_terms_kernel(PointTerms p, const float* __restrict__
   if ((threadIdx.x & 31) == 0) {
     if (p.iw2 >= 0 && temporal) atomicAdd(acc + p.slot2, (double)l2 * kmul);
     if (p.iw1 >= 0 && temporal) atomicAdd(acc + p.slot1, (double)l1 * kmul);
-    if (p.gA) atomicAdd(acc + p.slotA, (double)lA);
-    if (p.gB) atomicAdd(acc + p.slotB, (double)lB);
+    if (p.valsA) atomicAdd(acc + p.slotA, (double)lA);
+    if (p.valsB) atomicAdd(acc + p.slotB, (double)lB);
   }
 }
 

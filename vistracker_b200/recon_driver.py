@@ -29,19 +29,34 @@ def combine_mini_batches(pcs, samples_count: int) -> Dict[str, Dict[str, torch.T
 
 
 def generate_all(generator: GeneratorTriplaneVis, data: Dict[str, torch.Tensor], num_points: int = 4000, mini_batch_size: int = MINI_BATCH,
-                 on_mini_batch: Optional[Callable] = None):
+                 on_mini_batch: Optional[Callable] = None, keep_maps: bool = False):
     """``ReconFitterBehave.generate_all`` (recon_fit_behave.py:121-150): ``generate_pclouds_batch`` per mini-batch of 16 frames with 10
     projection steps, then ``combine_mini_batches``.  ``on_mini_batch(start, end, pc_generated)`` is where the reference writes
-    ``k{tid}_densepc.npz`` (``save_neural_recon``)."""
+    ``k{tid}_densepc.npz`` (``save_neural_recon``).
+
+    ``keep_maps``: every mini-batch's feature maps are copied into whole-batch tensors as they are produced and left in ``net._maps`` at
+    the end, i.e. exactly what ``filter_batch`` would recompute.  The reference filters the whole batch a second time after the generator
+    (recon_fit_triplane.py:57-60: the generator's per-mini-batch filter calls overwrite the network's cached maps and the whole batch does
+    not fit its GPU otherwise); the maps are a pure function of the frames, so keeping them gives the same values for half the encoder work."""
     B = data["images"].shape[0]
-    pcs, samples = [], 100000
+    net = generator.model
+    pcs, samples, full = [], 100000, None
     for s in range(0, B, mini_batch_size):
         mini = {k: v[s:s + mini_batch_size] for k, v in data.items()}
         pc = generator.generate_pclouds_batch(mini, num_points=num_points, num_steps=10, mute=True)
+        if keep_maps and B > mini_batch_size:
+            m, n = net._maps, mini["images"].shape[0]
+            if full is None:
+                full = tuple(torch.empty((B if i < 2 else 3 * B,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device) for i, t in enumerate(m))
+            full[0][s:s + n].copy_(m[0]); full[1][s:s + n].copy_(m[1])
+            for v in range(3):
+                full[2][v * B + s:v * B + s + n].copy_(m[2][v * n:(v + 1) * n]); full[3][v * B + s:v * B + s + n].copy_(m[3][v * n:(v + 1) * n])
         if on_mini_batch is not None:
             on_mini_batch(s, min(s + mini_batch_size, B), pc)
         samples = min(samples, pc["human"]["points"].shape[1], pc["object"]["points"].shape[1])
         pcs.append(pc)
+    if full is not None:
+        net._maps = full
     return combine_mini_batches(pcs, samples)
 
 
@@ -92,7 +107,8 @@ def scale_body_kpts(kpts: torch.Tensor, crop_center: torch.Tensor, crop_size: fl
 def fit_recon_batch(fitter: ReconFitterTriVisFull, generator: GeneratorTriplaneVis, data: Dict[str, torch.Tensor], smpl_init: Callable,
                     body_kpts: torch.Tensor, obj_points: torch.Tensor, pca_init: Optional[torch.Tensor] = None,
                     obj_rot_init: Optional[torch.Tensor] = None, silhouette=None, occ_ratios: Optional[torch.Tensor] = None,
-                    neural_only: bool = False, on_mini_batch: Optional[Callable] = None, noise_fn=None, mini_batch_size: int = MINI_BATCH, **loop_kw):
+                    neural_only: bool = False, on_mini_batch: Optional[Callable] = None, noise_fn=None, mini_batch_size: int = MINI_BATCH,
+                    reuse_generator_maps: bool = True, **loop_kw):
     """One batch of ``fit_recon``.
 
     data: {'images' [B,8,512,512], 'crop_center' [B,2], 'body_center' [B,3]} (device or host tensors).
@@ -101,19 +117,23 @@ def fit_recon_batch(fitter: ReconFitterTriVisFull, generator: GeneratorTriplaneV
     body_kpts [B,25,3]: OpenPose key points already in network-input pixels (``scale_body_kpts``).
     obj_points [n,3]: surface samples of the object template (``compute_pca_init``); pca_init [3,3]: its PCA axes, used when the
     rotation comes from the network (``-or neural``); obj_rot_init [B,3,3]: the rotation loaded from an earlier stage (HVOP-Net) instead.
+    reuse_generator_maps: keep the maps the generator's per-mini-batch filter calls produced instead of filtering the whole batch again (same
+    values, see ``generate_all``).
     silhouette: a ``render.SilLossROI`` for the batch, occ_ratios [B]: visibility used by the occlusion-aware terms (defaults to the
     network's prediction, recon_fit_triplane.py:68).
     Returns {'pc_generated', 'smpl', 'obj_R' (projected, no noise), 'obj_t', 'obj_s', 'hist_smpl', 'hist_obj', 'stopped_*', 'smpl_scale'} -- or only 'pc_generated' for
     ``neural_only`` (demo.sh step 4)."""
     dev = fitter.model.device
-    pc = generate_all(generator, data, on_mini_batch=on_mini_batch, mini_batch_size=mini_batch_size)
+    B = data["images"].shape[0]
+    reuse = reuse_generator_maps and not neural_only and generator.model is fitter.model
+    pc = generate_all(generator, data, on_mini_batch=on_mini_batch, mini_batch_size=mini_batch_size, keep_maps=reuse)
     if neural_only:
         return {"pc_generated": pc}
     if silhouette is None and fitter.scan is None:
         raise ValueError("the 'sil' phase needs a render.SilLossROI for the batch, or fitter.scan = (template vertices, faces) to build one")
-    with torch.no_grad():
-        filter_batch(fitter.model, data["images"], chunk=mini_batch_size)
-    B = data["images"].shape[0]
+    if not reuse:                                    # "need to run image filter again" (recon_fit_triplane.py:57-60)
+        with torch.no_grad():
+            filter_batch(fitter.model, data["images"], chunk=mini_batch_size)
     human_t = data["body_center"].to(dev).float()                                   # ReconFitterTriplane.get_smpl_translation (recon_fit_triplane.py:210-220):
                                                                                     # the pre-fit body centre, not the network's prediction
     smpl = smpl_init(human_t)

@@ -15,6 +15,7 @@ from __future__ import annotations
 
 import collections
 import ctypes
+import os
 from typing import Dict, Optional
 
 import numpy as np
@@ -160,6 +161,7 @@ class SmplRefineStep(_GraphLoop):
         V = m.V
         self._div = (ctypes.c_double * 8)(B * V, B, 45.0, B, B, B * reg.L, max(B - 2, 1) * 3.0 * V, 1.0)
         self._maps = net._maps                      # the graph holds these pointers: keep the tensors alive as long as the graph
+        self.merge_heads = os.environ.get("VT_QUERY_MERGE", "1") != "0"
         with torch.no_grad():
             b["pose"].copy_(torch.cat([smpl.global_pose, smpl.body_pose, smpl.hand_pose], 1))
             b["betas"].copy_(torch.cat([smpl.top_betas, smpl.other_betas], 1))
@@ -180,11 +182,20 @@ class SmplRefineStep(_GraphLoop):
         ms = ctypes.byref(m.struct)
         ctrl, acc = P(self.ctrl), P(self.acc)
         self.enqueue_forward()
-        self.net.enqueue_query_losses(b["verts"], self.cc, self.bc, 0, 0.1, self.labels, b["vals_df"], b["g_df"], b["vals_ce"], b["g_ce"],
-                                      maps=self._maps)
-        # stemp + df_h + part -> g_verts
-        _lib.call("vt_recon_point_terms", P(b["verts"]), B, m.V, 6, -1, 6, 0, 0, P(b["vals_df"]), P(b["g_df"]), None, 0, 0, float(B * m.V),
-                  P(b["vals_ce"]), P(b["g_ce"]), 3, 3, float(B), ctrl, P(b["g_verts"]), acc, S())
+        if self.merge_heads:
+            # df_h and part heads merged in the kernel: the schedule's weights (ctrl words 0 and 3) times 1 / (B V) and 1 / B are folded into the
+            # cotangents, one backward gather serves both terms, g_df holds w_dfh d df_h + w_part d part
+            c0 = self.ctrl.data_ptr()
+            self.net.enqueue_query_losses_merged(b["verts"], self.cc, self.bc, 0, 0.1, self.labels, c0, 1.0 / (B * m.V), c0 + 4 * 3, 1.0 / B,
+                                                 b["vals_df"], b["vals_ce"], b["g_df"], maps=self._maps)
+            _lib.call("vt_recon_point_terms", P(b["verts"]), B, m.V, 6, -1, 6, 0, 0, P(b["vals_df"]), P(b["g_df"]), None, -2, 0, 1.0,
+                      P(b["vals_ce"]), None, -1, 3, 1.0, ctrl, P(b["g_verts"]), acc, S())
+        else:
+            self.net.enqueue_query_losses(b["verts"], self.cc, self.bc, 0, 0.1, self.labels, b["vals_df"], b["g_df"], b["vals_ce"], b["g_ce"],
+                                          maps=self._maps)
+            # stemp + df_h + part -> g_verts
+            _lib.call("vt_recon_point_terms", P(b["verts"]), B, m.V, 6, -1, 6, 0, 0, P(b["vals_df"]), P(b["g_df"]), None, 0, 0, float(B * m.V),
+                      P(b["vals_ce"]), P(b["g_ce"]), 3, 3, float(B), ctrl, P(b["g_verts"]), acc, S())
         _lib.call("vt_landmarks_fwd", P(b["verts"]), B, m.V, P(reg.rowptr), P(reg.col), P(reg.val), reg.L, P(b["J25"]), S())
         _lib.call("vt_recon_kpts", P(b["J25"]), P(self.kpts), P(self.cc), B, reg.L, self._cam6, ctrl, P(b["gJ25"]), acc, S())
         _lib.call("vt_landmarks_bwd", P(b["gJ25"]), B, m.V, P(reg.rowptr), P(reg.col), P(reg.val), reg.L, P(b["g_verts"]), S())

@@ -392,6 +392,21 @@ class CHORETriplaneVisibility:
                       int(df_channel), float(clamp_max), _lib.ptr(labels), _lib.ptr(vals_df), _lib.ptr(g_df), _lib.ptr(vals_ce),
                       _lib.ptr(g_ce), int(fwd_mask), _lib.ptr(out_fwd), _lib.ptr(self._q_overflow), _lib.stream_ptr())
 
+    def enqueue_query_losses_merged(self, pts, cc, bc, df_channel, clamp_max, labels, w_df_ptr, w_df_mul, w_ce_ptr, w_ce_mul, vals_df, vals_ce, g_points,
+                                    maps=None):
+        """``vt_query_losses_merged_tc``: both loss heads in one pass with ONE backward gather; ``w_*_ptr`` are raw device addresses of fp32
+        scalars (e.g. words of the optimisation step's control block), ``w_*_mul`` host factors; g_points = w_df d clamp(df) + w_ce d CE."""
+        im_feat, tmpx, tri_tmpx, tri_feat = self._maps if maps is None else maps
+        B, N = pts.shape[0], pts.shape[1]
+        if B != im_feat.shape[0]:
+            raise ValueError(f"points batch {B} != filtered batch {im_feat.shape[0]}")
+        with torch.cuda.device(self.device):
+            _lib.call("vt_query_losses_merged_tc", _lib.ptr(pts), _lib.ptr(cc), _lib.ptr(bc), B, N, _lib.ptr(im_feat), _lib.ptr(tmpx),
+                      _lib.ptr(tri_tmpx), _lib.ptr(tri_feat), im_feat.shape[1], im_feat.shape[2], tmpx.shape[1], tmpx.shape[2],
+                      self._cam7, _lib.ptr(self._wpack), *(_lib.ptr(t) for t in self._wtc), *(_lib.ptr(t) for t in self._wtc_bwd),
+                      int(df_channel), float(clamp_max), _lib.ptr(labels), ctypes.c_void_p(w_df_ptr), float(w_df_mul), ctypes.c_void_p(w_ce_ptr),
+                      float(w_ce_mul), _lib.ptr(vals_df), _lib.ptr(vals_ce), _lib.ptr(g_points), _lib.ptr(self._q_overflow), _lib.stream_ptr())
+
     def query_losses(self, points, crop_center=None, df_channel=0, clamp_max=0.1, part_labels=None, also=(), **kwargs):
         """The query-dependent loss terms of the fitters as per-point tensors, differentiable w.r.t. ``points``:
         ``clamp(df[:, df_channel], max=clamp_max)`` [B, N] and (with ``part_labels`` [B, N]) ``F.cross_entropy(parts, labels,
