@@ -303,3 +303,27 @@ def test_fused_losses_with_forward_only_heads(net, with_parts, also):
     full = dict(zip(("df", "pca", "parts", "centers", "visibility"), net.get_preds()))
     for h in also:
         assert torch.equal(extra[h], full[h]), h
+
+
+@pytest.mark.parametrize("w_df,w_ce,clamp_max", [(1.0, 1.0, 0.1), (30.0, 0.0005, 0.1), (7.5, 3.0e3, 2.0), (0.0, 1.0, 0.1)])
+def test_merged_heads_launch_equals_the_weighted_sum_of_the_two_head_gradients(net, w_df, w_ce, clamp_max):
+    """vt_query_losses_merged_tc (both heads' hidden gradients accumulated in tensor memory, ONE backward gather) against
+    w_df * g_df + w_ce * g_ce of vt_query_losses_tc, with weights spanning the ratios the schedule of optimize_smpl reaches
+    (recon_fit_behave.py:393-420: df_h 30^2 / (B V), part 0.05^2 / B and back)."""
+    B, N = 2, 419
+    images, points, crop, body = synthetic_frames(B, size=64, seed=121, n_points=N, jitter=True)
+    net.filter(images.cuda())
+    pts, cc, bc = points.cuda().contiguous(), crop.cuda(), body.cuda()
+    labels = torch.randint(0, 14, (B, N), generator=torch.Generator().manual_seed(11)).cuda()
+    f = lambda *s: torch.full(s, float("nan"), device="cuda")
+    vd, gd, vc, gc = f(B, N), f(B, N, 3), f(B, N), f(B, N, 3)
+    net.enqueue_query_losses(pts, cc, bc, 0, clamp_max, labels, vd, gd, vc, gc)
+    w = torch.tensor([w_df, w_ce], device="cuda")
+    vd2, vc2, gm = f(B, N), f(B, N), f(B, N, 3)
+    net.enqueue_query_losses_merged(pts, cc, bc, 0, clamp_max, labels, w.data_ptr(), 0.5, w.data_ptr() + 4, 2.0, vd2, vc2, gm)
+    torch.cuda.synchronize()
+    net.check()
+    assert torch.equal(vd, vd2) and torch.equal(vc, vc2)
+    ref = (0.5 * w_df) * gd + (2.0 * w_ce) * gc
+    assert float(ref.abs().max()) > 0
+    assert rel_err(gm.cpu(), ref.cpu()) < 2e-5

@@ -54,4 +54,29 @@ def run(pts, labels, tag):
 
 labels = torch.randint(0, 14, (B, 6890), device=dev)
 run(verts, labels, "df + parts heads on the SMPL vertices")
+
+
+def run_merged():
+    Bn, N = verts.shape[:2]
+    w = torch.tensor([30.0 ** 2, 0.05 ** 2], device=dev)
+    vd, vc, g = f(Bn, N), f(Bn, N), f(Bn, N, 3)
+    go = lambda: net.enqueue_query_losses_merged(verts, cc, bc, 0, 0.1, labels, w.data_ptr(), 1.0 / (Bn * N), w.data_ptr() + 4, 1.0 / Bn, vd, vc, g)
+    for _ in range(3):
+        go()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(10):
+        go()
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 10
+    tiles = Bn * ((N + 127) // 128)
+    print(f"df + parts heads MERGED on the SMPL vertices: {ms:.3f} ms, {ms * 1e3 / (tiles / 148):.1f} us per tile-slot", flush=True)
+    if trace:
+        os.environ["VT_QUERY_TRACE"] = "1"
+        go(); torch.cuda.synchronize()
+        os.environ.pop("VT_QUERY_TRACE")
+
+
+run_merged()
 run(obj, None, "df head on the object points")

@@ -698,8 +698,10 @@ query_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_c
             tb_st16(acc_base + ch * 32, hi);
             tb_st16(acc_base + ch * 32 + 16, lo);
           }
-          if (pj == 1 && s_scale_e[r] < E) {
-            const __half2 sc2 = __float2half2_rn(ldexpf(1.f, s_scale_e[r] - E));
+          // (tcgen05.ld / st are warp-collective: the branch must be warp-uniform, rows that need no rescale multiply by one)
+          const bool rescale = pj == 1 && s_scale_e[r] < E;
+          if (__any_sync(0xffffffffu, rescale)) {
+            const __half2 sc2 = __float2half2_rn(rescale ? ldexpf(1.f, max(s_scale_e[r] - E, -30)) : 1.f);
             const uint32_t other = lane_base;               // the first head's accumulator columns
 #pragma unroll 1
             for (int q = 0; q < 8; ++q) {
