@@ -39,8 +39,8 @@ C4_WORKLOAD = ("recon_fit_trivis_full joint optimisation (C4): fit_recon_batch o
 SMPL_CAPS = dict(iter_for_betas=1, iter_for_pose=1, iter_for_kpts=1, steps_per_iter=10, max_iter=100)          # recon_fit_triplane.py:66
 OBJ_CAPS = dict(it_obj=15, it_sil=30, joint_iter=10, steps_per_iter=10, max_iter=100)                          # recon_fit_trivis_full.py:283-327
 # bytes a point moves through the fused query-loss launch (forward gather 9 728 + second gather of the backward 9 728 +
-# point 12 + label 8 + two values 8 + two point gradients 24)
-QUERY_LOSS_BYTES_PER_POINT = 2 * 9728 + 12 + 8 + 8 + 24
+# point 12 + label 8 + two values 8 + the merged point gradient 12)
+QUERY_LOSS_BYTES_PER_POINT = 2 * 9728 + 12 + 8 + 8 + 12
 QUERY_LOSS_FLOP_PER_POINT = 2 * (1.117e6 / 5) * 3           # two heads, forward + the two backward products (1.117 MFLOP / 5 heads)
 # ---- C2 (extra)
 BATCH, NPTS = 8, 10000
@@ -388,9 +388,11 @@ def query_roofline(c4: C4, share_launches, step_ms):
         verts = c4.last["smpl"]()[0].detach().contiguous()
     f = lambda *s: torch.empty(*s, dtype=torch.float32, device=dev)
     labels = c4.fitter.part_labels.to(dev)[None].repeat(B, 1).contiguous()
-    vals_df, g_df, vals_ce, g_ce = f(B, V), f(B, V, 3), f(B, V), f(B, V, 3)
+    vals_df, g_df, vals_ce = f(B, V), f(B, V, 3), f(B, V)
     cc, bc = c4.devd["crop_center"].contiguous(), c4.devd["body_center"].contiguous()
-    run = lambda: net.enqueue_query_losses(verts, cc, bc, 0, 0.1, labels, vals_df, g_df, vals_ce, g_ce)
+    w = torch.tensor([30.0 ** 2, 0.05 ** 2], device=dev)   # the launch the optimize_smpl step replays: both heads merged, weights from device words
+    run = lambda: net.enqueue_query_losses_merged(verts, cc, bc, 0, 0.1, labels, w.data_ptr(), 1.0 / (B * V), w.data_ptr() + 4, 1.0 / B,
+                                                  vals_df, vals_ce, g_df)
     for _ in range(3):
         run()
     n = 20
@@ -405,7 +407,7 @@ def query_roofline(c4: C4, share_launches, step_ms):
     pk, src = peaks()
     nbytes = QUERY_LOSS_BYTES_PER_POINT * B * V
     achieved = nbytes / (ms * 1e-3) / 1e9
-    return {"bound": "hbm", "kernel": "query_bwd_tc_kernel, fused-loss mode (vt_query_losses_tc) on 96 x 6890 vertices: 1 launch per optimize_smpl step",
+    return {"bound": "hbm", "kernel": "query_bwd_tc_kernel, fused-loss mode with merged heads (vt_query_losses_merged_tc) on 96 x 6890 vertices: 1 launch per optimize_smpl step",
             "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": achieved / pk["hbm_gbs"],
             "traffic": None, "traffic_note": "ncu dram bytes per launch: see profiles/ (the gathers are L2-served: the 8 maps of a frame are 71 MB, the vertices of one body touch a small part)",
             "algorithmic_bytes_per_launch": nbytes, "bytes_per_point": QUERY_LOSS_BYTES_PER_POINT, "ms_per_launch": ms,

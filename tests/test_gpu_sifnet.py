@@ -301,8 +301,8 @@ def test_fused_losses_with_forward_only_heads(net, with_parts, also):
     assert torch.equal(v0, v1) and torch.equal(p0.grad, p1.grad)
     net.query(points.cuda(), crop_center=crop.cuda(), body_center=body.cuda())
     full = dict(zip(("df", "pca", "parts", "centers", "visibility"), net.get_preds()))
-    for h in also:
-        assert torch.equal(extra[h], full[h]), h
+    for h in also:        # the two column halves of the last hidden layer are summed by two threads: equal to the last rounding, not bitwise
+        assert rel_err(extra[h].cpu(), full[h].cpu()) < 1e-6, h
 
 
 @pytest.mark.parametrize("w_df,w_ce,clamp_max", [(1.0, 1.0, 0.1), (30.0, 0.0005, 0.1), (7.5, 3.0e3, 2.0), (0.0, 1.0, 0.1)])

@@ -40,7 +40,7 @@ struct TbParams {
   float* g_points2;        // [B][N][3] d CE / d point
   int fwd_mask;            // mode 2: heads evaluated forward-only (they share the gather; no backward) ...
   float* out_fwd;          // ... into the packed [B][29][N] prediction buffer
-  long long* trace;        // debug (VT_QUERY_TRACE=1): clock64 stamps of CTA (0,0): [0..15] epilogue thread 0, [16..31] gather warp 0
+  long long* trace;        // debug (VT_QUERY_TRACE=1): clock64 stamps of CTA (0,0): [0..63] epilogue thread 0, [64..127] gather warp 0
   // mode 2, merged heads (both pointers set, labels given): the caller's loss weights w_df = *w_df_ptr * w_df_mul, w_ce = *w_ce_ptr * w_ce_mul are
   // folded into the cotangents at the head outputs, both heads' g1 stay in tensor memory and accumulate into ONE feature-gradient tile, so the
   // backward gather-dot runs once per tile: g_points = w_df d clamp(df) / d point + w_ce d CE / d point (g_points2 is not written)
@@ -65,6 +65,20 @@ __device__ __forceinline__ void tb_ld16(uint32_t taddr, uint32_t (&r)[16]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ void tq_ld8(uint32_t taddr, float (&v)[8]) {
+  uint32_t r[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "r"(taddr) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tb_st4(uint32_t taddr, const uint32_t (&r)[4]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]) : "memory");
+}
+// 2^e for |e| <= 126 (the renormalisation exponents are clamped to [-100, 128]; 127 / 128 only for non-finite input, where any factor does)
+__device__ __forceinline__ float tb_pow2(int e) { return __int_as_float((min(max(e, -126), 127) + 127) << 23); }
+
 // power-of-two normalisation of a non-negative maximum: returns e with 2^-e * m in [0.5, 1) (0 for m == 0 / non-finite)
 __device__ __forceinline__ int tb_norm_exp(float m) {
   if (!(m > 0.f) || !(m < 3.0e38f)) return 0;
@@ -73,6 +87,7 @@ __device__ __forceinline__ int tb_norm_exp(float m) {
   return max(e, -100);
 }
 
+// 14 warps are allocated registers as 16 (groups of four): 65536 / 512 = 128 per thread
 __global__ void __launch_bounds__(TB_THREADS, 1)
 query_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_constant__ CUtensorMap tm_w1_lo,
                     const __grid_constant__ CUtensorMap tm_w23_hi, const __grid_constant__ CUtensorMap tm_w23_lo,
@@ -82,16 +97,19 @@ query_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_c
                     int B, int N, TqMaps m, TqCam cam, const float* __restrict__ wpack, int wpack_head_stride, TbParams prm,
                     int* __restrict__ overflow) {
   extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t feat_full[2], feat_empty[2], w_full[TQ_NW], w_empty[TQ_NW], acc_full, act_full, gf_full[TB_NGF],
+  __shared__ __align__(8) uint64_t feat_full[2], feat_empty[2], w_full[4], w_empty[4], f1_done, acc_full, act_full, gf_full[TB_NGF],
       gf_empty[TB_NGF], stg_full[2], stg_empty[2];
   __shared__ uint32_t s_tmem_base;
   __shared__ TqTapTable s_tap;
   __shared__ float s_xyz[TQ_M][4];                          // x, y, z - z0, z
-  __shared__ int s_in_img[TQ_M];
+  __shared__ unsigned char s_in_img[TQ_M];
   __shared__ int s_scale_e[TQ_M];                           // exponent of the per-point renormalisation of the current head
+  __shared__ float s_wloss[2];                              // merged heads: the two loss weights (device scalar x host factor)
+  __shared__ unsigned char s_label[TQ_M];                   // mode 2: part label of every point (14 classes)
   __shared__ float s_dfc[TQ_M];                             // clamp(df, max=threshold) (projection step)
   __shared__ uint32_t s_mask[3][4][TQ_M];                   // ReLU masks of the three hidden layers of the current head (128 bits per point)
-  __shared__ float s_gacc[TQ_M][3];                         // d/d(x, y, z) of every point, summed over chunks and heads
+  __shared__ float s_gp[TQ_M][2];                           // current head, before the per-point scale: d/d(u, v) of the perspective samples ...
+  __shared__ float s_g3[TQ_M][3];                           // ... and d/d(x, y, z) through the three orthographic views and the direct inputs
   __shared__ __align__(16) float s_w4[TQ_H * 16 + 16];
   __shared__ __align__(16) float s_bias[3][TQ_H];           // b1, b2, b3 of the current head
 
@@ -100,27 +118,24 @@ query_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_c
   const uint32_t feat_base = smem_base, w_base = smem_base + 2 * TQ_SLOT, act_base = w_base + TQ_NW * TQ_SLOT;
   uint8_t* feat_ptr = smem_al;                              // also the gf staging ring: slot = fp32 [128 points][64 features]
   uint8_t* act_ptr = smem_al + 2 * TQ_SLOT + TQ_NW * TQ_SLOT;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int b = blockIdx.y, n0 = blockIdx.x * TQ_M;
+  // the warp index through a shuffle: the compiler then knows the role branches are warp-uniform (needed for straight-line UTCHMMA issue below)
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const int heads = prm.mode == 1 ? 1 : prm.mode == 2 ? ((prm.labels ? 5 : 1) | prm.fwd_mask) : prm.head_mask;
   auto fwd_only = [&](int h) { return prm.mode == 2 && ((prm.fwd_mask >> h) & 1) != 0; };
   const bool merge = prm.mode == 2 && prm.labels != nullptr && prm.w_df_ptr != nullptr && prm.w_ce_ptr != nullptr;   // heads 0 and 2 as ONE pair
   // heads are processed in pairs that share ONE forward gather: both first layers accumulate from the same feature chunks (TMEM
   // columns 0-127 and 128-255), then each head runs its own forward / backward chain and backward gather; gf slots start at column 256
   const int n_heads = __popc((unsigned)heads), n_pairs = (n_heads + 1) >> 1;
+  // a head's chain stages may borrow the idle feature ring for their weight tiles when no backward gather (which stages through that
+  // ring) runs between the pair's forward gather and this chain: always for the first head of a pair, for the second when the heads are
+  // merged or the first was forward-only
+  auto chain_wide = [&](int pi, int pj) {
+    if (pj == 0 || merge) return true;
+    const int hA = 2 * pi < n_heads ? (int)__fns((unsigned)heads, 0, 2 * pi + 1) : -1;
+    return hA >= 0 && prm.mode == 2 && ((prm.fwd_mask >> hA) & 1) != 0;
+  };
   auto pair_head = [&](int pi, int j) { return 2 * pi + j < n_heads ? (int)__fns((unsigned)heads, 0, 2 * pi + j + 1) : -1; };
 
-  if (warp == 5 && lane == 0) {
-    for (int s = 0; s < 2; ++s) {
-      tq_mbar_init(tq_smem_u32(&feat_full[s]), TQ_GATHER_WARPS); tq_mbar_init(tq_smem_u32(&feat_empty[s]), 1);
-      tq_mbar_init(tq_smem_u32(&stg_full[s]), 4); tq_mbar_init(tq_smem_u32(&stg_empty[s]), TQ_GATHER_WARPS);
-    }
-    for (int s = 0; s < TQ_NW; ++s) { tq_mbar_init(tq_smem_u32(&w_full[s]), 1); tq_mbar_init(tq_smem_u32(&w_empty[s]), 1); }
-    for (int s = 0; s < TB_NGF; ++s) { tq_mbar_init(tq_smem_u32(&gf_full[s]), 1); tq_mbar_init(tq_smem_u32(&gf_empty[s]), 4); }
-    tq_mbar_init(tq_smem_u32(&acc_full), 1);
-    tq_mbar_init(tq_smem_u32(&act_full), 4);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
   if (warp == 4 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_w1_hi) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_w1_lo) : "memory");
@@ -134,6 +149,21 @@ query_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_c
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tq_smem_u32(&s_tmem_base)), "r"(512u) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  // one tile of 128 points per CTA (a persistent loop over tiles with a static round-robin assignment was measured 8 % SLOWER: tiles differ in
+  // cost -- points outside the image skip their taps -- and the hardware CTA scheduler balances them dynamically)
+  const int b = blockIdx.y, n0 = blockIdx.x * TQ_M;
+  if (warp == 5 && lane == 0) {
+    for (int s = 0; s < 2; ++s) {
+      tq_mbar_init(tq_smem_u32(&feat_full[s]), TQ_GATHER_WARPS); tq_mbar_init(tq_smem_u32(&feat_empty[s]), 1);
+      tq_mbar_init(tq_smem_u32(&stg_full[s]), 4); tq_mbar_init(tq_smem_u32(&stg_empty[s]), TQ_GATHER_WARPS);
+    }
+    for (int s = 0; s < 4; ++s) { tq_mbar_init(tq_smem_u32(&w_full[s]), 1); tq_mbar_init(tq_smem_u32(&w_empty[s]), 1); }
+    tq_mbar_init(tq_smem_u32(&f1_done), 1);
+    for (int s = 0; s < TB_NGF; ++s) { tq_mbar_init(tq_smem_u32(&gf_full[s]), 1); tq_mbar_init(tq_smem_u32(&gf_empty[s]), 4); }
+    tq_mbar_init(tq_smem_u32(&acc_full), 1);
+    tq_mbar_init(tq_smem_u32(&act_full), 8);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   // projections of the tile's points (gather warps, one thread per point) -- same arithmetic as query_fwd_tc_kernel
   if (warp >= 6 && (threadIdx.x - 6 * 32) < TQ_M) {
@@ -154,12 +184,328 @@ query_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_c
     } else {
       q.nx = q.ny = q.tu0 = q.tv0 = q.tu1 = q.tv1 = q.tu2 = q.tv2 = 1e30f;       // every tap out of range -> zero features
     }
+    if (prm.mode == 2 && prm.labels != nullptr) s_label[pp] = n < N ? (unsigned char)prm.labels[(size_t)b * N + n] : 0;
+    if (merge && pp < 2) s_wloss[pp] = pp == 0 ? __ldg(prm.w_df_ptr) * prm.w_df_mul : __ldg(prm.w_ce_ptr) * prm.w_ce_mul;
     tq_tap_fill(s_tap, pp, q, m); s_xyz[pp][0] = x; s_xyz[pp][1] = y; s_xyz[pp][2] = __fadd_rn(z, -cam.z0); s_xyz[pp][3] = z; s_in_img[pp] = in_img;
   }
   tq_fence_before();
   __syncthreads();
   tq_fence_after();
   const uint32_t tmem_base = s_tmem_base;
+
+  // ================================================================== the decoder chain of one head (epilogue side), thread = point row =
+  // TMEM lane, split by COLUMN HALVES between two warps per lane quadrant: the epilogue warp q (hf = 0: hidden units 0-63) and gather
+  // warp 6 + ((q + 2) & 3), which has nothing to gather while the chain runs and whose warp id gives it the same TMEM lane quadrant
+  // (hf = 1: hidden units 64-127).  What the two threads of a row must share -- the partial head outputs, the cotangent, the row maximum of
+  // each backward stage -- goes through a 128-byte mailbox in the activation buffer: each thread owns the row's line of the K chunk it
+  // writes itself (slot hf), the partner posts into that line and the owner reads it before its own store overwrites it; a 64-thread named
+  // barrier per quadrant orders post and read.
+  // Every stage walks its 64 columns in ROLLED loops over groups of 8 (tcgen05.ld.x8): each stage runs once per tile and head, so fully
+  // unrolled 32-column bodies (the previous form) executed ~6 k instructions of cold straight-line code per head -- the second pass over
+  // the same code ran twice as fast as the first (instruction fetch, not arithmetic, set the stage time).
+  int tr = 0;
+  const bool tracing = prm.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0;
+#define TB_STAMP() do { if (tracing && tr < 64) prm.trace[tr++] = clock64(); } while (0)
+  auto chain_head = [&](const int hi, const int hf, int& iacc, float& amax) {
+    const int q = warp & 3, r = q * 32 + lane, n = n0 + r;
+    const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
+    const int h = (int)__fns((unsigned)heads, 0, hi + 1), pj = hi & 1;          // pj: which accumulator of the pair
+    const uint32_t acc_base = lane_base + pj * TQ_H;
+    uint8_t* act_mine = act_ptr + hf * TQ_SLOT;            // K chunk hf of the A operand = columns 64 hf .. 64 hf + 63
+    float* mail_in = reinterpret_cast<float*>(act_mine + (r >> 3) * 1024 + (r & 7) * 128);
+    float* mail_out = reinterpret_cast<float*>(act_ptr + (hf ^ 1) * TQ_SLOT + (r >> 3) * 1024 + (r & 7) * 128);
+    auto pair_sync = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(4 + q) : "memory"); };
+    // 8 values (columns 64 hf + 8 g .. + 7 of a 128-wide layer) of this point into the next MMA's A operand: one 16-byte unit per plane
+    auto store_act8 = [&](const float (&v)[8], int g) {
+      uint4 hh, ll;
+      tq_split2(v[0], v[1], hh.x, ll.x, amax); tq_split2(v[2], v[3], hh.y, ll.y, amax);
+      tq_split2(v[4], v[5], hh.z, ll.z, amax); tq_split2(v[6], v[7], hh.w, ll.w, amax);
+      const uint32_t off = tq_sw_off(r, g * 8);
+      *reinterpret_cast<uint4*>(act_mine + off) = hh;
+      *reinterpret_cast<uint4*>(act_mine + TQ_PLANE + off) = ll;
+    };
+    auto publish_act = [&]() {
+      tq_fence_before();                                   // TMEM reads of the accumulator are done before the MMA overwrites it
+      tq_fence_async();
+      __syncwarp();
+      if (lane == 0) tq_mbar_arrive(tq_smem_u32(&act_full));
+    };
+    const float* hw = wpack + (size_t)h * wpack_head_stride;
+    const float* b1 = hw + 616 * 128;
+    const float* b2 = b1 + 128 + 128 * 128;
+    const float* b3 = b2 + 128 + 128 * 128;
+    const float* W4 = b3 + 128;
+    asm volatile("bar.sync 2, 256;" ::: "memory");        // the previous head has finished reading s_w4
+    if (hf == 0) {
+      for (int i = threadIdx.x; i < (TQ_H * 16 + 16) / 4; i += 128)
+        reinterpret_cast<float4*>(s_w4)[i] = __ldg(reinterpret_cast<const float4*>(W4) + i);
+      if (threadIdx.x < 96) {
+        const int l = threadIdx.x >> 5, qq = threadIdx.x & 31;
+        reinterpret_cast<float4*>(s_bias[l])[qq] = __ldg(reinterpret_cast<const float4*>(l == 0 ? b1 : l == 1 ? b2 : b3) + qq);
+      }
+    }
+    asm volatile("bar.sync 2, 256;" ::: "memory");
+    float o[16];                                            // this thread's share of the head outputs (14 used)
+#pragma unroll
+    for (int c = 0; c < 16; ++c) o[c] = 0.f;
+    const bool narrow = h == 0 || h == 3 || h == 4;         // <= 4 outputs: W4 columns 4..15 are zero padding
+    const int col0 = 64 * hf;
+    // ---- forward epilogues E1, E2, E3 (ReLU masks -> s_mask)
+#pragma unroll 1
+    for (int layer = 0; layer < 3; ++layer) {
+      if (!(layer == 0 && pj == 1)) {            // the second head's first layer was completed together with the first head's
+        tq_mbar_wait(tq_smem_u32(&acc_full), (uint32_t)iacc & 1u); ++iacc;
+      }
+      tq_fence_after();
+      TB_STAMP();
+      const float* bias = s_bias[layer] + col0;
+      uint32_t mword = 0;
+#pragma unroll 1
+      for (int g = 0; g < 8; ++g) {
+        float v[8];
+        tq_ld8(acc_base + col0 + g * 8, v);
+        const float4 ba = *reinterpret_cast<const float4*>(bias + g * 8), bb = *reinterpret_cast<const float4*>(bias + g * 8 + 4);
+        v[0] += ba.x; v[1] += ba.y; v[2] += ba.z; v[3] += ba.w; v[4] += bb.x; v[5] += bb.y; v[6] += bb.z; v[7] += bb.w;
+        uint32_t mk = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { mk |= (v[i] > 0.f ? 1u : 0u) << i; v[i] = fmaxf(v[i], 0.f); }
+        mword |= mk << ((g & 3) * 8);
+        if ((g & 3) == 3) { s_mask[layer][2 * hf + (g >> 2)][r] = mword; mword = 0; }
+        if (layer < 2) {
+          store_act8(v, g);
+        } else if (narrow) {                   // heads with <= 4 outputs (df, centers, visibility): one 16-byte weight load per unit
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float4 w0 = *reinterpret_cast<const float4*>(s_w4 + (col0 + g * 8 + i) * 16);
+            o[0] = fmaf(v[i], w0.x, o[0]); o[1] = fmaf(v[i], w0.y, o[1]); o[2] = fmaf(v[i], w0.z, o[2]); o[3] = fmaf(v[i], w0.w, o[3]);
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float4* wr = reinterpret_cast<const float4*>(s_w4 + (col0 + g * 8 + i) * 16);
+            const float4 w0 = wr[0], w1 = wr[1], w2 = wr[2], w3 = wr[3];
+            o[0] = fmaf(v[i], w0.x, o[0]); o[1] = fmaf(v[i], w0.y, o[1]); o[2] = fmaf(v[i], w0.z, o[2]); o[3] = fmaf(v[i], w0.w, o[3]);
+            o[4] = fmaf(v[i], w1.x, o[4]); o[5] = fmaf(v[i], w1.y, o[5]); o[6] = fmaf(v[i], w1.z, o[6]); o[7] = fmaf(v[i], w1.w, o[7]);
+            o[8] = fmaf(v[i], w2.x, o[8]); o[9] = fmaf(v[i], w2.y, o[9]); o[10] = fmaf(v[i], w2.z, o[10]); o[11] = fmaf(v[i], w2.w, o[11]);
+            o[12] = fmaf(v[i], w3.x, o[12]); o[13] = fmaf(v[i], w3.y, o[13]);
+          }
+        }
+      }
+      if (layer < 2) publish_act();
+      TB_STAMP();
+    }
+    // ---- the head outputs: the upper half posts its partial sums, the lower half owns the result
+    if (hf) {
+#pragma unroll
+      for (int c = 0; c < 16; c += 4) *reinterpret_cast<float4*>(mail_out + c) = make_float4(o[c], o[c + 1], o[c + 2], o[c + 3]);
+    }
+    pair_sync();
+    if (!hf) {
+#pragma unroll
+      for (int c = 0; c < 16; c += 4) {
+        const float4 t = *reinterpret_cast<const float4*>(mail_in + c);
+        o[c] += t.x; o[c + 1] += t.y; o[c + 2] += t.z; o[c + 3] += t.w;
+      }
+    }
+    const int nout = h == 0 ? 2 : h == 1 ? 9 : h == 2 ? 14 : h == 3 ? 3 : 1;
+    const int hoff = h == 0 ? 0 : h == 1 ? 2 : h == 2 ? 11 : h == 3 ? 25 : 28;
+    if (fwd_only(h)) {                         // predictions only: write them, hand the accumulator back, next head
+      if (!hf && n < N) {
+#pragma unroll
+        for (int c = 0; c < 14; ++c) {
+          if (c >= nout) break;
+          float val = o[c] + s_w4[TQ_H * 16 + c];
+          if (h == 4) val = 1.f / (1.f + expf(-val));
+          if (h == 0 && !s_in_img[r]) val = cam.out_dist;
+          prm.out_fwd[((size_t)b * 29 + hoff + c) * N + n] = val;
+        }
+      }
+      publish_act();
+      return;
+    }
+    // ---- cotangent at the head outputs, normalised per point (lower half; posted to the upper half)
+    float g4[16];
+    int e_total = 0;
+    if (!hf) {
+      float gmax = 0.f;
+#pragma unroll
+      for (int c = 0; c < 14; ++c) {
+        float g = 0.f;
+        if (c < nout && n < N) {
+          float val = o[c] + s_w4[TQ_H * 16 + c];
+          if (h == 4) val = 1.f / (1.f + expf(-val));
+          if (h == 0 && !s_in_img[r]) val = cam.out_dist;
+          if (prm.mode == 0) {
+            g = prm.g_out[((size_t)b * 29 + hoff + c) * N + n];
+            if (h == 4) g *= val * (1.f - val);
+          } else if (h == 0 && c == prm.df_idx) {
+            g = val <= prm.threshold ? 1.f : 0.f;
+            s_dfc[r] = fminf(val, prm.threshold);
+            if (prm.mode == 2) prm.vals_df[(size_t)b * N + n] = fminf(val, prm.threshold);
+          } else if (h == 2) {
+            g = val;                                       // mode 2: keep the logit, turned into softmax - onehot below
+          }
+          if (h == 0 && !s_in_img[r]) g = 0.f;
+        }
+        g4[c] = g;
+        gmax = fmaxf(gmax, fabsf(g));
+      }
+      g4[14] = 0.f; g4[15] = 0.f;
+      if (merge && h == 0) {
+        const float wdf = s_wloss[0];
+#pragma unroll
+        for (int c = 0; c < 2; ++c) g4[c] *= wdf;
+        gmax *= fabsf(wdf);
+      }
+      if (prm.mode == 2 && h == 2) {                       // F.cross_entropy(parts, labels, reduction='none') and its logit gradient
+        gmax = 0.f;
+        if (n < N) {
+          const int lab = s_label[r];
+          float mx = g4[0];
+#pragma unroll
+          for (int c = 1; c < 14; ++c) mx = fmaxf(mx, g4[c]);
+          float sum = 0.f, l_lab = 0.f;
+#pragma unroll
+          for (int c = 0; c < 14; ++c) { if (c == lab) l_lab = g4[c]; g4[c] = __expf(g4[c] - mx); sum += g4[c]; }
+          prm.vals_ce[(size_t)b * N + n] = logf(sum) - (l_lab - mx);
+          const float inv_sum = 1.f / sum;
+          const float wce = merge ? s_wloss[1] : 1.f;
+#pragma unroll
+          for (int c = 0; c < 14; ++c) { g4[c] = (g4[c] * inv_sum - (c == lab ? 1.f : 0.f)) * wce; gmax = fmaxf(gmax, fabsf(g4[c])); }
+        } else {
+#pragma unroll
+          for (int c = 0; c < 14; ++c) g4[c] = 0.f;
+        }
+      }
+      e_total = tb_norm_exp(gmax);
+      const float inv = tb_pow2(-e_total);
+#pragma unroll
+      for (int c = 0; c < 14; ++c) g4[c] *= inv;
+      g4[15] = __int_as_float(e_total);
+#pragma unroll
+      for (int c = 0; c < 16; c += 4) *reinterpret_cast<float4*>(mail_out + c) = make_float4(g4[c], g4[c + 1], g4[c + 2], g4[c + 3]);
+    }
+    pair_sync();
+    if (hf) {
+#pragma unroll
+      for (int c = 0; c < 16; c += 4) {
+        const float4 t = *reinterpret_cast<const float4*>(mail_in + c);
+        g4[c] = t.x; g4[c + 1] = t.y; g4[c + 2] = t.z; g4[c + 3] = t.w;
+      }
+      e_total = __float_as_int(g4[15]);
+    }
+    // g3 = relu'(h3) . (W4^T g4): 128 x <=14 on the CUDA cores, straight into the A operand of B3
+#pragma unroll 1
+    for (int g = 0; g < 8; ++g) {
+      float v[8];
+      const uint32_t mk = s_mask[2][2 * hf + (g >> 2)][r] >> ((g & 3) * 8);
+      if (narrow) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float4 w0 = *reinterpret_cast<const float4*>(s_w4 + (col0 + g * 8 + i) * 16);
+          float a = g4[0] * w0.x;
+          a = fmaf(g4[1], w0.y, a); a = fmaf(g4[2], w0.z, a); a = fmaf(g4[3], w0.w, a);
+          v[i] = ((mk >> i) & 1u) ? a : 0.f;
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float4* wr = reinterpret_cast<const float4*>(s_w4 + (col0 + g * 8 + i) * 16);
+          const float4 w0 = wr[0], w1 = wr[1], w2 = wr[2], w3 = wr[3];
+          float a = g4[0] * w0.x;
+          a = fmaf(g4[1], w0.y, a); a = fmaf(g4[2], w0.z, a); a = fmaf(g4[3], w0.w, a);
+          a = fmaf(g4[4], w1.x, a); a = fmaf(g4[5], w1.y, a); a = fmaf(g4[6], w1.z, a); a = fmaf(g4[7], w1.w, a);
+          a = fmaf(g4[8], w2.x, a); a = fmaf(g4[9], w2.y, a); a = fmaf(g4[10], w2.z, a); a = fmaf(g4[11], w2.w, a);
+          a = fmaf(g4[12], w3.x, a); a = fmaf(g4[13], w3.y, a);
+          v[i] = ((mk >> i) & 1u) ? a : 0.f;
+        }
+      }
+      store_act8(v, g);
+    }
+    publish_act();
+    TB_STAMP();
+    // ---- backward epilogues EB3 (mask of layer 2), EB2 (mask of layer 1): renormalise by the ROW maximum (both halves), mask, split
+#pragma unroll 1
+    for (int bl = 1; bl >= 0; --bl) {
+      tq_mbar_wait(tq_smem_u32(&acc_full), (uint32_t)iacc & 1u); ++iacc;
+      tq_fence_after();
+      float vmax = 0.f;
+#pragma unroll 1
+      for (int g = 0; g < 8; ++g) {
+        float v[8];
+        tq_ld8(acc_base + col0 + g * 8, v);
+        const uint32_t mk = s_mask[bl][2 * hf + (g >> 2)][r] >> ((g & 3) * 8);
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          if ((mk >> i) & 1u) vmax = fmaxf(vmax, fabsf(v[i]));
+      }
+      const int e_first = s_scale_e[r];                    // merged heads, second head: the first head's exponent (read before the lower half replaces it)
+      mail_out[0] = vmax;
+      pair_sync();
+      vmax = fmaxf(vmax, mail_in[0]);
+      const int e = tb_norm_exp(vmax);
+      e_total += e;
+      if (merge && bl == 0) {
+        // g1 of this head stays in TENSOR MEMORY, written over its own accumulator columns (per 32-column chunk: 16 columns of packed hi
+        // pairs, 16 of lo pairs), as the A operand of the merged B1 product.  Both heads must share one per-point exponent E = max(e_A, e_B):
+        // the second head scales its own values on the way in and, if it raised E, rescales the first head's columns (powers of two: exact).
+        int E = e_total;
+        if (pj == 1) E = max(E, e_first);
+        const float inv = tb_pow2(-e + (e_total - E));
+        // (a chunk of 32 fp32 columns is replaced by its own packed form: read the whole chunk before the first store)
+#pragma unroll 1
+        for (int ch = 2 * hf; ch < 2 * hf + 2; ++ch) {
+          float v[32];
+          tq_ld32(acc_base + ch * 32, v);
+          const uint32_t mk = s_mask[bl][ch][r];
+          uint32_t hi16[16], lo16[16];
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            const float a = ((mk >> i) & 1u) ? v[i] * inv : 0.f, c2 = ((mk >> (i + 1)) & 1u) ? v[i + 1] * inv : 0.f;
+            tq_split2(a, c2, hi16[i >> 1], lo16[i >> 1], amax);
+          }
+          tb_st16(acc_base + ch * 32, hi16);
+          tb_st16(acc_base + ch * 32 + 16, lo16);
+        }
+        // (tcgen05.ld / st are warp-collective: the branch must be warp-uniform, rows that need no rescale multiply by one)
+        const bool rescale = pj == 1 && e_first < E;
+        if (__any_sync(0xffffffffu, rescale)) {
+          const __half2 sc2 = __float2half2_rn(rescale ? tb_pow2(max(e_first - E, -30)) : 1.f);
+          const uint32_t other = lane_base + col0;        // the first head's accumulator columns, this thread's half
+#pragma unroll 1
+          for (int qq = 0; qq < 4; ++qq) {
+            uint32_t w[16];
+            tb_ld16(other + qq * 16, w);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const __half2 t = __hmul2(*reinterpret_cast<const __half2*>(&w[i]), sc2);
+              w[i] = *reinterpret_cast<const uint32_t*>(&t);
+            }
+            tb_st16(other + qq * 16, w);
+          }
+        }
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        pair_sync();                                       // the upper half has read the first head's exponent
+        if (!hf) s_scale_e[r] = E;
+        publish_act();
+        TB_STAMP();
+        continue;
+      }
+      const float inv = tb_pow2(-e);
+#pragma unroll 1
+      for (int g = 0; g < 8; ++g) {
+        float v[8];
+        tq_ld8(acc_base + col0 + g * 8, v);
+        const uint32_t mk = s_mask[bl][2 * hf + (g >> 2)][r] >> ((g & 3) * 8);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = ((mk >> i) & 1u) ? v[i] * inv : 0.f;
+        store_act8(v, g);
+      }
+      if (bl == 0 && !hf) s_scale_e[r] = e_total;          // read by the gather warps after the first staging chunk is published
+      publish_act();
+      TB_STAMP();
+    }
+  };
 
   if (warp >= 6) {
     // ================================================================== gather warps
@@ -169,13 +515,15 @@ query_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_c
     constexpr int PW = TQ_M / TQ_GATHER_WARPS;              // 16 points per warp
     constexpr int PBB = 2, NGRP = 2;                        // ... and in the backward contraction: NGRP groups of PBB point pairs;
     static_assert(PBB == 2, "the butterfly reduction below handles exactly two points per half-warp");
-    for (int i = lane; i < PW * 3; i += 32) (&s_gacc[gw * PW][0])[i] = 0.f;      // each warp owns the rows of its 16 points
+    for (int i = lane; i < PW * 3; i += 32) (&s_g3[gw * PW][0])[i] = 0.f;       // each warp owns the rows of its 16 points
+    (&s_gp[gw * PW][0])[lane] = 0.f;
+    float acc_x = 0.f, acc_y = 0.f, acc_z = 0.f;           // lanes 0-15: point gw * PW + lane, summed over heads (modes 0 and 1)
     __syncwarp();
-    int it = 0, sc = 0;
+    int it = 0, sc = 0, iacc_h = 0;
     float amax = 0.f;
-    int trg = 16;
+    int trg = 64;
     const bool tracing_g = prm.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && gw == 0 && lane == 0;
-#define TB_STAMP_G() do { if (tracing_g && trg < 32) prm.trace[trg++] = clock64(); } while (0)
+#define TB_STAMP_G() do { if (tracing_g && trg < 128) prm.trace[trg++] = clock64(); } while (0)
     TB_STAMP_G();
     for (int pi = 0; pi < n_pairs; ++pi) {
       asm volatile("bar.sync 3, 256;" ::: "memory");       // every gather warp is done reading the previous head's staging slots
@@ -227,13 +575,14 @@ query_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_c
       for (int pj = 0; pj < 2; ++pj) {
       const int h = pair_head(pi, pj);
       if (h < 0) break;
+      if (gw < 4) chain_head(2 * pi + pj, 1, iacc_h, amax);  // gather warps 0-3: the upper column half of this head's chain stages
       if (fwd_only(h)) continue;
       if (merge && pj == 0) continue;                       // merged heads: one staged feature-gradient tile, after the second head's chain
       // ---- backward: contract the staged feature gradients with d(feature)/d(u, v) (second gather of the same taps)
       for (int c = 0; c < TQ_NCHUNK; ++c, ++sc) {
         const int slot = sc & 1;
         tq_mbar_wait(tq_smem_u32(&stg_full[slot]), (uint32_t)(sc >> 1) & 1u);
-        if (c == 0) TB_STAMP_G();
+        TB_STAMP_G();
         const uint8_t* stg = feat_ptr + slot * TQ_SLOT;
         const TqChunkSrc src = tq_chunk_src(c, k, m, b, B);
         const bool full_res = (c < 4) || (c >= 5 && c < 8);                // im_feat / tri_feat maps (Hf x Wf); else tmpx-sized maps
@@ -260,78 +609,95 @@ query_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_c
 #pragma unroll
           for (int gq = 0; gq < NGRP; ++gq) {
           const int ib = i0 + gq * 2 * PBB;
-          float red[8];                                              // (gx, gy, gz) of the two points of this half-warp + 2 pads
-          red[6] = 0.f; red[7] = 0.f;
+          // per point only (d/du, d/dv) in map pixels are reduced over the lanes -- 4 values per half-warp through a halving butterfly (5
+          // shuffles; 4 in the chunks whose 8-lane halves sample different views) -- and summed per projection in shared memory; the
+          // projection Jacobians and the per-point scale are applied once per point and head in finish_head below
+          float red[4];
 #pragma unroll
           for (int j = 0; j < PBB; ++j) {
             const int pp = gw * PW + ib + 2 * j + sub;
             const float4 g = *reinterpret_cast<const float4*>(stg + pp * 256 + (((lane & 15) ^ (pp & 15)) << 4));
-            const float scale = ldexpf(1.f, s_scale_e[pp]);
             const float tx = tap[gq][j].tx, ty = tap[gq][j].ty;
             const float d00 = fmaf(g.w, t00[gq][j].w, fmaf(g.z, t00[gq][j].z, fmaf(g.y, t00[gq][j].y, g.x * t00[gq][j].x)));
             const float d01 = fmaf(g.w, t01[gq][j].w, fmaf(g.z, t01[gq][j].z, fmaf(g.y, t01[gq][j].y, g.x * t01[gq][j].x)));
             const float d10 = fmaf(g.w, t10[gq][j].w, fmaf(g.z, t10[gq][j].z, fmaf(g.y, t10[gq][j].y, g.x * t10[gq][j].x)));
             const float d11 = fmaf(g.w, t11[gq][j].w, fmaf(g.z, t11[gq][j].z, fmaf(g.y, t11[gq][j].y, g.x * t11[gq][j].x)));
-            const float dix = (d01 - d00) * (1.f - ty) + (d11 - d10) * ty;
-            const float diy = (d10 - d00) * (1.f - tx) + (d11 - d01) * tx;
-            const float gu = dix * su * scale, gv = diy * sv * scale;
-            float gx = 0.f, gy = 0.f, gz = 0.f;
-            if (src.view < 0) {           // perspective: nx = 2 (crop/2 + fx x / z + cx - ccx) / crop - 1
-              const float kk = 2.f / cam.crop, x = s_xyz[pp][0], y = s_xyz[pp][1], iz = 1.f / s_xyz[pp][3];
-              gx = gu * kk * cam.fx * iz;
-              gy = gv * kk * cam.fy * iz;
-              gz = -gu * kk * cam.fx * x * iz * iz - gv * kk * cam.fy * y * iz * iz;
-            } else if (src.view == 0) {   // right: (z, y)
-              gz = gu; gy = gv;
-            } else if (src.view == 1) {   // back: (-x, y)
-              gx = -gu; gy = gv;
-            } else if (src.view == 2) {   // top: (x, -z)
-              gx = gu; gz = -gv;
-            } else if (src.direct) {      // the (x, y, z - z0) inputs themselves
-              gx = g.x * scale; gy = g.y * scale; gz = g.z * scale;
-            }
-            red[3 * j] = gx; red[3 * j + 1] = gy; red[3 * j + 2] = gz;
+            red[2 * j] = ((d01 - d00) * (1.f - ty) + (d11 - d10) * ty) * su;
+            red[2 * j + 1] = ((d10 - d00) * (1.f - tx) + (d11 - d01) * tx) * sv;
+            if (src.direct) { s_g3[pp][0] += g.x; s_g3[pp][1] += g.y; s_g3[pp][2] += g.z; }     // one lane of chunk 9: the (x, y, z - z0) inputs
           }
-          // sum the 6 values over the 16 lanes (features) of the half-warp with a halving butterfly: 8 shuffles instead of 24; lane l ends
-          // up owning value index 4*bit3 + 2*bit2 + bit1
+          if (c == 9) __syncwarp();                                        // ... before the top-view sums of the same points below
           {
             const bool u8 = (lane & 8) != 0, u4 = (lane & 4) != 0, u2 = (lane & 2) != 0;
+            int idx, cls;
+            if (c < 8) {                                                   // one projection for the 16 lanes
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const float send = u8 ? red[i] : red[i + 4], keep = u8 ? red[i + 4] : red[i];
-              red[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-            }
+              for (int i = 0; i < 2; ++i) {
+                const float send = u8 ? red[i] : red[i + 2], keep = u8 ? red[i + 2] : red[i];
+                red[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+              }
+              {
+                const float send = u4 ? red[0] : red[1], keep = u4 ? red[1] : red[0];
+                red[0] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+              }
+              red[0] += __shfl_xor_sync(0xffffffffu, red[0], 2);
+              red[0] += __shfl_xor_sync(0xffffffffu, red[0], 1);
+              idx = (u8 ? 2 : 0) + (u4 ? 1 : 0);
+              cls = (lane & 3) == 0 ? src.view + 1 : -1;
+            } else {                                                       // chunks 8 / 9: lanes 0-7 and 8-15 sample different views
 #pragma unroll
-            for (int i = 0; i < 2; ++i) {
-              const float send = u4 ? red[i] : red[i + 2], keep = u4 ? red[i + 2] : red[i];
-              red[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+              for (int i = 0; i < 2; ++i) {
+                const float send = u4 ? red[i] : red[i + 2], keep = u4 ? red[i + 2] : red[i];
+                red[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+              }
+              {
+                const float send = u2 ? red[0] : red[1], keep = u2 ? red[1] : red[0];
+                red[0] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+              }
+              red[0] += __shfl_xor_sync(0xffffffffu, red[0], 1);
+              idx = (u4 ? 2 : 0) + (u2 ? 1 : 0);
+              cls = ((lane & 1) == 0 && src.sampled) ? src.view + 1 : -1;
             }
-            {
-              const float send = u2 ? red[0] : red[1], keep = u2 ? red[1] : red[0];
-              red[0] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+            // right view samples (z, y), back (-x, y), top (x, -z); in chunk 8 the two 8-lane halves (right | back) both add to y: in turn
+            const int pp = gw * PW + ib + 2 * (idx >> 1) + sub, uv = idx & 1;
+#pragma unroll
+            for (int turn = 0; turn < 2; ++turn) {
+              if (cls >= 0 && (c != 8 || (int)u8 == turn)) {
+                if (cls == 0) s_gp[pp][uv] += red[0];
+                else if (cls == 1) s_g3[pp][uv ? 1 : 2] += red[0];
+                else if (cls == 2) { if (uv) s_g3[pp][1] += red[0]; else s_g3[pp][0] -= red[0]; }
+                else { if (uv) s_g3[pp][2] -= red[0]; else s_g3[pp][0] += red[0]; }
+              }
+              if (c != 8) break;
+              __syncwarp();
             }
-            red[0] += __shfl_xor_sync(0xffffffffu, red[0], 1);
-            const int idx = (u8 ? 4 : 0) + (u4 ? 2 : 0) + (u2 ? 1 : 0);
-            if ((lane & 1) == 0 && idx < 6) s_gacc[gw * PW + ib + 2 * (idx / 3) + sub][idx % 3] += red[0];
           }
           }   // groups
         }
         __syncwarp();
+        TB_STAMP_G();
         if (lane == 0) tq_mbar_arrive(tq_smem_u32(&stg_empty[slot]));
       }
       TB_STAMP_G();
-      if (prm.mode == 2) {        // one gradient tensor per loss term: write this head's and start the next from zero
-        __syncwarp();
-        if (lane < PW) {
-          const int pp = gw * PW + lane, n = n0 + pp;
+      // ---- finish_head: projection Jacobians and the per-point scale, once per point (one lane per point)
+      __syncwarp();
+      if (lane < PW) {
+        const int pp = gw * PW + lane, n = n0 + pp;
+        const float scale = ldexpf(1.f, s_scale_e[pp]);
+        const float kk = 2.f / cam.crop, x = s_xyz[pp][0], y = s_xyz[pp][1], iz = 1.f / s_xyz[pp][3];
+        const float pu = s_gp[pp][0] * (kk * cam.fx * iz), pv = s_gp[pp][1] * (kk * cam.fy * iz);   // nx = 2 (crop/2 + fx x / z + cx - ccx) / crop - 1
+        const float gx = (pu + s_g3[pp][0]) * scale, gy = (pv + s_g3[pp][1]) * scale, gz = (s_g3[pp][2] - (pu * x + pv * y) * iz) * scale;
+        if (prm.mode == 2) {      // one gradient tensor per loss term
           if (n < N) {
             float* gp = ((h == 0 || merge) ? prm.g_points : prm.g_points2) + ((size_t)b * N + n) * 3;
-            gp[0] = s_gacc[pp][0]; gp[1] = s_gacc[pp][1]; gp[2] = s_gacc[pp][2];
+            gp[0] = gx; gp[1] = gy; gp[2] = gz;
           }
-          s_gacc[pp][0] = 0.f; s_gacc[pp][1] = 0.f; s_gacc[pp][2] = 0.f;
+        } else {
+          acc_x += gx; acc_y += gy; acc_z += gz;
         }
-        __syncwarp();
+        s_gp[pp][0] = 0.f; s_gp[pp][1] = 0.f; s_g3[pp][0] = 0.f; s_g3[pp][1] = 0.f; s_g3[pp][2] = 0.f;
       }
+      __syncwarp();
       }   // heads of the pair
     }
     // ---- write the point gradients / the projected points (one lane per point)
@@ -339,7 +705,7 @@ query_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_c
     if (prm.mode != 2 && lane < PW) {
       const int pp = gw * PW + lane, n = n0 + pp;
       if (n < N) {
-        const float gx = s_gacc[pp][0], gy = s_gacc[pp][1], gz = s_gacc[pp][2];
+        const float gx = acc_x, gy = acc_y, gz = acc_z;
         if (prm.g_points) { float* gp = prm.g_points + ((size_t)b * N + n) * 3; gp[0] = gx; gp[1] = gy; gp[2] = gz; }
         if (prm.mode == 1) {     // samples - F.normalize(gradient, dim=2) * df_target   (eps 1e-12, generator.py:96)
           const float inv = 1.f / fmaxf(sqrtf(gx * gx + gy * gy + gz * gz), 1e-12f), dd = s_dfc[pp];
@@ -352,81 +718,110 @@ query_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_c
   } else if (warp == 4) {
     // ================================================================== TMA producer (weights), same order as the MMA issuer
     if (lane == 0) {
-      int iw = 0;
-      auto load = [&](const CUtensorMap* hi, const CUtensorMap* lo, int col, int row) {
-        const int s = iw % TQ_NW;
-        tq_mbar_wait(tq_smem_u32(&w_empty[s]), ((uint32_t)(iw / TQ_NW) & 1u) ^ 1u);
-        const uint32_t full = tq_smem_u32(&w_full[s]);
+      // Weight tiles go through a ring of two 32 KB slots -- or of FOUR while a head's chain stages run: the feature ring is idle between
+      // the last first-layer MMA (f1_done) and the first staging write of the backward gather, and with only two slots the tiles of stage
+      // s + 1 could not be requested before the MMAs of stage s had drained, which put an L2 round trip of 64 KB on every one of the
+      // (latency-chained) stages.  Producer and MMA issuer walk the same tile sequence and pick slots with the same rule.
+      uint32_t par = 0;                                     // bit s: uses of slot s so far, mod 2
+      int nsel = 0, wsel = 0;
+      bool f1_ok = false;
+      int pair_idx = 0;
+      auto load = [&](const CUtensorMap* hi, const CUtensorMap* lo, int col, int row, bool wide) {
+        const int s = wide ? (wsel++ & 3) : (nsel++ & 1);
+        if (s >= 2 && !f1_ok) { tq_mbar_wait(tq_smem_u32(&f1_done), (uint32_t)pair_idx & 1u); f1_ok = true; }
+        tq_mbar_wait(tq_smem_u32(&w_empty[s]), ((par >> s) & 1u) ^ 1u);
+        par ^= 1u << s;
+        const uint32_t full = tq_smem_u32(&w_full[s]), dst = s < 2 ? w_base + s * TQ_SLOT : feat_base + (s - 2) * TQ_SLOT;
         tq_mbar_expect_tx(full, TQ_SLOT);
-        tq_tma_2d(w_base + s * TQ_SLOT, hi, full, col, row);
-        tq_tma_2d(w_base + s * TQ_SLOT + TQ_PLANE, lo, full, col, row);
-        ++iw;
+        tq_tma_2d(dst, hi, full, col, row);
+        tq_tma_2d(dst + TQ_PLANE, lo, full, col, row);
       };
       for (int pi = 0; pi < n_pairs; ++pi) {
         const int hA = pair_head(pi, 0), hB = pair_head(pi, 1);
+        pair_idx = pi; f1_ok = false;
         for (int c = 0; c < TQ_NCHUNK; ++c) {
-          load(&tm_w1_hi, &tm_w1_lo, c * TQ_KC, hA * TQ_H);
-          if (hB >= 0) load(&tm_w1_hi, &tm_w1_lo, c * TQ_KC, hB * TQ_H);
+          load(&tm_w1_hi, &tm_w1_lo, c * TQ_KC, hA * TQ_H, false);
+          if (hB >= 0) load(&tm_w1_hi, &tm_w1_lo, c * TQ_KC, hB * TQ_H, false);
         }
         for (int pj = 0; pj < 2; ++pj) {
           const int h = pj == 0 ? hA : hB;
           if (h < 0) break;
+          const bool wide = chain_wide(pi, pj);
           for (int layer = 0; layer < 2; ++layer)
-            for (int kc = 0; kc < 2; ++kc) load(&tm_w23_hi, &tm_w23_lo, kc * TQ_KC, (layer * 5 + h) * TQ_H);
+            for (int kc = 0; kc < 2; ++kc) load(&tm_w23_hi, &tm_w23_lo, kc * TQ_KC, (layer * 5 + h) * TQ_H, wide);
           if (fwd_only(h)) continue;
           for (int layer = 1; layer >= 0; --layer)
-            for (int kc = 0; kc < 2; ++kc) load(&tm_w23t_hi, &tm_w23t_lo, kc * TQ_KC, (layer * 5 + h) * TQ_H);
+            for (int kc = 0; kc < 2; ++kc) load(&tm_w23t_hi, &tm_w23t_lo, kc * TQ_KC, (layer * 5 + h) * TQ_H, wide);
           if (merge) {
             if (pj == 0) continue;
             for (int u = 0; u < TQ_NCHUNK / 2; ++u)                      // merged B1: per column group the W1^T tiles of both heads
               for (int q = 0; q < 4; ++q)
-                load(&tm_w1t_hi, &tm_w1t_lo, (q & 1) * TQ_KC, (q < 2 ? hA : hB) * TQ_NCHUNK * TQ_KC + u * TQ_H);
+                load(&tm_w1t_hi, &tm_w1t_lo, (q & 1) * TQ_KC, (q < 2 ? hA : hB) * TQ_NCHUNK * TQ_KC + u * TQ_H, false);
             continue;
           }
           for (int u = 0; u < TQ_NCHUNK / 2; ++u)
-            for (int kc = 0; kc < 2; ++kc) load(&tm_w1t_hi, &tm_w1t_lo, kc * TQ_KC, h * TQ_NCHUNK * TQ_KC + u * TQ_H);
+            for (int kc = 0; kc < 2; ++kc) load(&tm_w1t_hi, &tm_w1t_lo, kc * TQ_KC, h * TQ_NCHUNK * TQ_KC + u * TQ_H, false);
         }
       }
     }
   } else if (warp == 5) {
-    // ================================================================== MMA issuer
-    if (lane == 0) {
-      int it = 0, iw = 0, iact = 0, gfi = 0;
-      auto mma_tile = [&](uint32_t a_addr, uint32_t acc, bool first) {
-        const int s = iw % TQ_NW;
-        tq_mbar_wait(tq_smem_u32(&w_full[s]), (uint32_t)(iw / TQ_NW) & 1u);
+    // ================================================================== MMA issuer: the whole warp walks the (uniform) control flow and polls the
+    // barriers, ONE elected lane issues -- under `if (lane == 0)` the compiler wraps every tcgen05.mma in an ELECT / BRA.U.ANY loop over
+    // the active lanes (~10 instructions and ~80 cycles per 32-cycle MMA: the issue thread, not the tensor pipe, set the stage times)
+    {
+      int it = 0, iact = 0, gfi = 0, nsel = 0, wsel = 0;
+      uint32_t par = 0;
+      int trm = 128;
+      const bool tracing_m = prm.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && lane == 0;
+#define TB_STAMP_M() do { if (tracing_m && trm < 256) prm.trace[trm++] = clock64(); } while (0)
+      auto next_w = [&](bool wide, uint32_t& addr) {         // wait for the next weight tile of the sequence; returns its slot
+        const int s = wide ? (wsel++ & 3) : (nsel++ & 1);
+        tq_mbar_wait(tq_smem_u32(&w_full[s]), (par >> s) & 1u);
+        par ^= 1u << s;
         tq_fence_after();
-        const uint64_t a_hi = tq_desc(a_addr), a_lo = tq_desc(a_addr + TQ_PLANE);
-        const uint64_t b_hi = tq_desc(w_base + s * TQ_SLOT), b_lo = tq_desc(w_base + s * TQ_SLOT + TQ_PLANE);
-#pragma unroll
-        for (int kk = 0; kk < TQ_KC / 16; ++kk) {
-          const uint64_t adv = (uint64_t)(kk * 32 >> 4);
-          tq_mma(acc, a_hi + adv, b_hi + adv, (first && kk == 0) ? 0u : 1u);
-          tq_mma(acc, a_hi + adv, b_lo + adv, 1u);
-          tq_mma(acc, a_lo + adv, b_hi + adv, 1u);
-        }
-        tq_commit(tq_smem_u32(&w_empty[s]));
-        ++iw;
+        addr = s < 2 ? w_base + s * TQ_SLOT : feat_base + (s - 2) * TQ_SLOT;
+        return s;
       };
+      auto mma_tile = [&](uint32_t a_addr, uint32_t acc, bool first, bool wide) {
+        uint32_t waddr;
+        const int s = next_w(wide, waddr);
+        const uint64_t a_hi = tq_desc(a_addr), a_lo = tq_desc(a_addr + TQ_PLANE);
+        const uint64_t b_hi = tq_desc(waddr), b_lo = tq_desc(waddr + TQ_PLANE);
+        if (tq_elect_one()) {
+#pragma unroll
+          for (int kk = 0; kk < TQ_KC / 16; ++kk) {
+            const uint64_t adv = (uint64_t)(kk * 32 >> 4);
+            tq_mma(acc, a_hi + adv, b_hi + adv, (first && kk == 0) ? 0u : 1u);
+            tq_mma(acc, a_hi + adv, b_lo + adv, 1u);
+            tq_mma(acc, a_lo + adv, b_hi + adv, 1u);
+          }
+          tq_commit(tq_smem_u32(&w_empty[s]));
+        }
+        __syncwarp();
+      };
+      auto commit = [&](uint64_t* bar) { if (tq_elect_one()) tq_commit(tq_smem_u32(bar)); __syncwarp(); };
       for (int pi = 0; pi < n_pairs; ++pi) {
         const bool two = pair_head(pi, 1) >= 0;
         for (int c = 0; c < TQ_NCHUNK; ++c, ++it) {                     // F1 of both heads of the pair from the same feature chunk
           const int slot = it & 1;
           tq_mbar_wait(tq_smem_u32(&feat_full[slot]), (uint32_t)(it >> 1) & 1u);
           tq_fence_after();
-          mma_tile(feat_base + slot * TQ_SLOT, tmem_base, c == 0);
-          if (two) mma_tile(feat_base + slot * TQ_SLOT, tmem_base + TQ_H, c == 0);
-          tq_commit(tq_smem_u32(&feat_empty[slot]));
+          mma_tile(feat_base + slot * TQ_SLOT, tmem_base, c == 0, false);
+          if (two) mma_tile(feat_base + slot * TQ_SLOT, tmem_base + TQ_H, c == 0, false);
+          commit(&feat_empty[slot]);
         }
-        tq_commit(tq_smem_u32(&acc_full));
+        commit(&acc_full);
+        commit(&f1_done);                               // the feature ring is free: the weight producer may borrow it
         for (int pj = 0; pj < (two ? 2 : 1); ++pj) {
           const uint32_t acc = tmem_base + pj * TQ_H;
+          const bool wide = chain_wide(pi, pj);
           const bool fo = fwd_only(pair_head(pi, pj));
           for (int stage = 0; stage < (fo ? 2 : 4); ++stage) {          // F2, F3, B3, B2: act buffer -> this head's accumulator
             tq_mbar_wait(tq_smem_u32(&act_full), (uint32_t)iact & 1u); ++iact;
             tq_fence_after();
-            for (int kc = 0; kc < 2; ++kc) mma_tile(act_base + kc * TQ_SLOT, acc, kc == 0);
-            tq_commit(tq_smem_u32(&acc_full));
+            TB_STAMP_M();
+            for (int kc = 0; kc < 2; ++kc) { mma_tile(act_base + kc * TQ_SLOT, acc, kc == 0, wide); TB_STAMP_M(); }
+            commit(&acc_full);
           }
           tq_mbar_wait(tq_smem_u32(&act_full), (uint32_t)iact & 1u); ++iact;   // g1 is in the act buffer (forward-only head: its
           tq_fence_after();                                                    // accumulator has been read out and may be reused)
@@ -438,25 +833,26 @@ query_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_c
               tq_mbar_wait(tq_smem_u32(&gf_empty[gs]), ((uint32_t)(gfi / TB_NGF) & 1u) ^ 1u);
               tq_fence_after();
               for (int q = 0; q < 4; ++q) {
-                const int s = iw % TQ_NW;
-                tq_mbar_wait(tq_smem_u32(&w_full[s]), (uint32_t)(iw / TQ_NW) & 1u);
-                tq_fence_after();
-                const uint64_t b_hi = tq_desc(w_base + s * TQ_SLOT), b_lo = tq_desc(w_base + s * TQ_SLOT + TQ_PLANE);
+                uint32_t waddr;
+                const int s = next_w(false, waddr);
+                const uint64_t b_hi = tq_desc(waddr), b_lo = tq_desc(waddr + TQ_PLANE);
                 const uint32_t a_base = tmem_base + (q < 2 ? 0 : TQ_H), d = tmem_base + 2 * TQ_H + gs * TQ_H;
+                if (tq_elect_one()) {
 #pragma unroll
-                for (int kk = 0; kk < TQ_KC / 16; ++kk) {
-                  // K step of 16 elements = 8 columns; per 32-element chunk the layout is [hi: 16 columns | lo: 16 columns]
-                  const int kg = (q & 1) * TQ_KC + kk * 16;
-                  const uint32_t a_hi = a_base + (kg >> 5) * 32 + ((kg >> 4) & 1) * 8, a_lo = a_hi + 16;
-                  const uint64_t adv = (uint64_t)(kk * 32 >> 4);
-                  tb_mma_ts(d, a_hi, b_hi + adv, (q == 0 && kk == 0) ? 0u : 1u);
-                  tb_mma_ts(d, a_hi, b_lo + adv, 1u);
-                  tb_mma_ts(d, a_lo, b_hi + adv, 1u);
+                  for (int kk = 0; kk < TQ_KC / 16; ++kk) {
+                    // K step of 16 elements = 8 columns; per 32-element chunk the layout is [hi: 16 columns | lo: 16 columns]
+                    const int kg = (q & 1) * TQ_KC + kk * 16;
+                    const uint32_t a_hi = a_base + (kg >> 5) * 32 + ((kg >> 4) & 1) * 8, a_lo = a_hi + 16;
+                    const uint64_t adv = (uint64_t)(kk * 32 >> 4);
+                    tb_mma_ts(d, a_hi, b_hi + adv, (q == 0 && kk == 0) ? 0u : 1u);
+                    tb_mma_ts(d, a_hi, b_lo + adv, 1u);
+                    tb_mma_ts(d, a_lo, b_hi + adv, 1u);
+                  }
+                  tq_commit(tq_smem_u32(&w_empty[s]));
                 }
-                tq_commit(tq_smem_u32(&w_empty[s]));
-                ++iw;
+                __syncwarp();
               }
-              tq_commit(tq_smem_u32(&gf_full[gs]));
+              commit(&gf_full[gs]);
             }
             continue;
           }
@@ -464,283 +860,30 @@ query_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_c
             const int gs = gfi % TB_NGF;
             tq_mbar_wait(tq_smem_u32(&gf_empty[gs]), ((uint32_t)(gfi / TB_NGF) & 1u) ^ 1u);
             tq_fence_after();
-            for (int kc = 0; kc < 2; ++kc) mma_tile(act_base + kc * TQ_SLOT, tmem_base + 2 * TQ_H + gs * TQ_H, kc == 0);
-            tq_commit(tq_smem_u32(&gf_full[gs]));
+            for (int kc = 0; kc < 2; ++kc) mma_tile(act_base + kc * TQ_SLOT, tmem_base + 2 * TQ_H + gs * TQ_H, kc == 0, false);
+            commit(&gf_full[gs]);
           }
         }
       }
     }
   } else {
-    // ================================================================== epilogue warps: thread = point row = TMEM lane
-    const int r = warp * 32 + lane, n = n0 + r;
+    // ================================================================== epilogue warps: lower column half of every chain stage, then the drain
+    const int r = warp * 32 + lane;
     const uint32_t lane_base = tmem_base + ((uint32_t)(warp * 32) << 16);
     int iacc = 0, gfi = 0, sc = 0;
     float amax = 0.f;
-    int tr = 0;
-    const bool tracing = prm.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0;
-#define TB_STAMP() do { if (tracing && tr < 16) prm.trace[tr++] = clock64(); } while (0)
     TB_STAMP();
-    // write 32 values (K index ch*32 + i of a 128-wide layer) of this point as the next MMA's A operand
-    auto store_act = [&](const float (&v)[32], int ch) {
-      uint8_t* dst = act_ptr + (ch >> 1) * TQ_SLOT;
-#pragma unroll
-      for (int i = 0; i < 32; i += 8) {
-        uint4 hh, ll;
-        tq_split2(v[i], v[i + 1], hh.x, ll.x, amax); tq_split2(v[i + 2], v[i + 3], hh.y, ll.y, amax);
-        tq_split2(v[i + 4], v[i + 5], hh.z, ll.z, amax); tq_split2(v[i + 6], v[i + 7], hh.w, ll.w, amax);
-        const uint32_t off = tq_sw_off(r, (ch & 1) * 32 + i);
-        *reinterpret_cast<uint4*>(dst + off) = hh;
-        *reinterpret_cast<uint4*>(dst + TQ_PLANE + off) = ll;
-      }
-    };
-    auto publish_act = [&]() {
-      tq_fence_before();                                   // TMEM reads of the accumulator are done before the MMA overwrites it
-      tq_fence_async();
-      __syncwarp();
-      if (lane == 0) tq_mbar_arrive(tq_smem_u32(&act_full));
-    };
     for (int hi = 0; hi < n_heads; ++hi) {
-      const int h = (int)__fns((unsigned)heads, 0, hi + 1), pj = hi & 1;        // pj: which accumulator of the pair
-      const uint32_t acc_base = lane_base + pj * TQ_H;
-      const float* hw = wpack + (size_t)h * wpack_head_stride;
-      const float* b1 = hw + 616 * 128;
-      const float* b2 = b1 + 128 + 128 * 128;
-      const float* b3 = b2 + 128 + 128 * 128;
-      const float* W4 = b3 + 128;
-      asm volatile("bar.sync 2, 128;" ::: "memory");      // the previous head has finished reading s_w4
-      for (int i = threadIdx.x; i < (TQ_H * 16 + 16) / 4; i += 128)
-        reinterpret_cast<float4*>(s_w4)[i] = __ldg(reinterpret_cast<const float4*>(W4) + i);
-      if (threadIdx.x < 96) {
-        const int l = threadIdx.x >> 5, q = threadIdx.x & 31;
-        reinterpret_cast<float4*>(s_bias[l])[q] = __ldg(reinterpret_cast<const float4*>(l == 0 ? b1 : l == 1 ? b2 : b3) + q);
-      }
-      asm volatile("bar.sync 2, 128;" ::: "memory");
-      float o[14];
-#pragma unroll
-      for (int c = 0; c < 14; ++c) o[c] = 0.f;
-      const bool narrow = h == 0 || h == 3 || h == 4;       // <= 4 outputs: W4 columns 4..15 are zero padding
-      // ---- forward epilogues E1, E2, E3 (ReLU masks -> s_mask; the loops stay rolled, every v[] index is a compile-time constant)
-#pragma unroll 1
-      for (int layer = 0; layer < 3; ++layer) {
-        if (!(layer == 0 && pj == 1)) {          // the second head's first layer was completed together with the first head's
-          tq_mbar_wait(tq_smem_u32(&acc_full), (uint32_t)iacc & 1u); ++iacc;
-        }
-        tq_fence_after();
-        const float* bias = s_bias[layer];
-#pragma unroll 1
-        for (int ch = 0; ch < 4; ++ch) {
-          float v[32];
-          tq_ld32(acc_base + ch * 32, v);
-          uint32_t mk = 0;
-#pragma unroll
-          for (int i = 0; i < 32; i += 4) {
-            const float4 bb = *reinterpret_cast<const float4*>(bias + ch * 32 + i);
-            const float t0 = v[i] + bb.x, t1 = v[i + 1] + bb.y, t2 = v[i + 2] + bb.z, t3 = v[i + 3] + bb.w;
-            mk |= ((t0 > 0.f ? 1u : 0u) | (t1 > 0.f ? 2u : 0u) | (t2 > 0.f ? 4u : 0u) | (t3 > 0.f ? 8u : 0u)) << i;
-            v[i] = fmaxf(t0, 0.f); v[i + 1] = fmaxf(t1, 0.f); v[i + 2] = fmaxf(t2, 0.f); v[i + 3] = fmaxf(t3, 0.f);
-          }
-          s_mask[layer][ch][r] = mk;
-          if (layer < 2) {
-            store_act(v, ch);
-          } else if (narrow) {                   // heads with <= 4 outputs (df, centers, visibility): one 16-byte weight load per unit
-#pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              const float4 w0 = *reinterpret_cast<const float4*>(s_w4 + (ch * 32 + i) * 16);
-              o[0] = fmaf(v[i], w0.x, o[0]); o[1] = fmaf(v[i], w0.y, o[1]); o[2] = fmaf(v[i], w0.z, o[2]); o[3] = fmaf(v[i], w0.w, o[3]);
-            }
-          } else {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              const float4* wr = reinterpret_cast<const float4*>(s_w4 + (ch * 32 + i) * 16);
-              const float4 w0 = wr[0], w1 = wr[1], w2 = wr[2], w3 = wr[3];
-              o[0] = fmaf(v[i], w0.x, o[0]); o[1] = fmaf(v[i], w0.y, o[1]); o[2] = fmaf(v[i], w0.z, o[2]); o[3] = fmaf(v[i], w0.w, o[3]);
-              o[4] = fmaf(v[i], w1.x, o[4]); o[5] = fmaf(v[i], w1.y, o[5]); o[6] = fmaf(v[i], w1.z, o[6]); o[7] = fmaf(v[i], w1.w, o[7]);
-              o[8] = fmaf(v[i], w2.x, o[8]); o[9] = fmaf(v[i], w2.y, o[9]); o[10] = fmaf(v[i], w2.z, o[10]); o[11] = fmaf(v[i], w2.w, o[11]);
-              o[12] = fmaf(v[i], w3.x, o[12]); o[13] = fmaf(v[i], w3.y, o[13]);
-            }
-          }
-        }
-        if (layer < 2) publish_act();
-        TB_STAMP();
-      }
-      const int nout = h == 0 ? 2 : h == 1 ? 9 : h == 2 ? 14 : h == 3 ? 3 : 1;
-      const int hoff = h == 0 ? 0 : h == 1 ? 2 : h == 2 ? 11 : h == 3 ? 25 : 28;
-      if (fwd_only(h)) {                         // predictions only: write them, hand the accumulator back, next head
-        if (n < N) {
-#pragma unroll
-          for (int c = 0; c < 14; ++c) {
-            if (c >= nout) break;
-            float val = o[c] + s_w4[TQ_H * 16 + c];
-            if (h == 4) val = 1.f / (1.f + expf(-val));
-            if (h == 0 && !s_in_img[r]) val = cam.out_dist;
-            prm.out_fwd[((size_t)b * 29 + hoff + c) * N + n] = val;
-          }
-        }
-        publish_act();
-        continue;
-      }
-      // ---- cotangent at the head outputs, normalised per point
-      float g4[14];
-      float gmax = 0.f;
-#pragma unroll
-      for (int c = 0; c < 14; ++c) {
-        float g = 0.f;
-        if (c < nout && n < N) {
-          float val = o[c] + s_w4[TQ_H * 16 + c];
-          if (h == 4) val = 1.f / (1.f + expf(-val));
-          if (h == 0 && !s_in_img[r]) val = cam.out_dist;
-          if (prm.mode == 0) {
-            g = prm.g_out[((size_t)b * 29 + hoff + c) * N + n];
-            if (h == 4) g *= val * (1.f - val);
-          } else if (h == 0 && c == prm.df_idx) {
-            g = val <= prm.threshold ? 1.f : 0.f;
-            s_dfc[r] = fminf(val, prm.threshold);
-            if (prm.mode == 2) prm.vals_df[(size_t)b * N + n] = fminf(val, prm.threshold);
-          } else if (h == 2) {
-            g = val;                                       // mode 2: keep the logit, turned into softmax - onehot below
-          }
-          if (h == 0 && !s_in_img[r]) g = 0.f;
-          if (merge && h == 0) g *= __ldg(prm.w_df_ptr) * prm.w_df_mul;
-        }
-        g4[c] = g;
-        gmax = fmaxf(gmax, fabsf(g));
-      }
-      if (prm.mode == 2 && h == 2) {                       // F.cross_entropy(parts, labels, reduction='none') and its logit gradient
-        gmax = 0.f;
-        if (n < N) {
-          const int lab = (int)prm.labels[(size_t)b * N + n];
-          float mx = g4[0];
-#pragma unroll
-          for (int c = 1; c < 14; ++c) mx = fmaxf(mx, g4[c]);
-          float sum = 0.f, l_lab = 0.f;
-#pragma unroll
-          for (int c = 0; c < 14; ++c) { if (c == lab) l_lab = g4[c]; g4[c] = expf(g4[c] - mx); sum += g4[c]; }
-          prm.vals_ce[(size_t)b * N + n] = logf(sum) - (l_lab - mx);
-          const float inv_sum = 1.f / sum;
-          const float wce = merge ? __ldg(prm.w_ce_ptr) * prm.w_ce_mul : 1.f;
-#pragma unroll
-          for (int c = 0; c < 14; ++c) { g4[c] = (g4[c] * inv_sum - (c == lab ? 1.f : 0.f)) * wce; gmax = fmaxf(gmax, fabsf(g4[c])); }
-        } else {
-#pragma unroll
-          for (int c = 0; c < 14; ++c) g4[c] = 0.f;
-        }
-      }
-      int e_total = tb_norm_exp(gmax);
-      {
-        const float inv = ldexpf(1.f, -e_total);
-#pragma unroll
-        for (int c = 0; c < 14; ++c) g4[c] *= inv;
-      }
-      // g3 = relu'(h3) . (W4^T g4): 128 x <=14 on the CUDA cores, straight into the A operand of B3
-#pragma unroll 1
-      for (int ch = 0; ch < 4; ++ch) {
-        float v[32];
-        const uint32_t mk = s_mask[2][ch][r];
-        if (narrow) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const float4 w0 = *reinterpret_cast<const float4*>(s_w4 + (ch * 32 + i) * 16);
-            float a = g4[0] * w0.x;
-            a = fmaf(g4[1], w0.y, a); a = fmaf(g4[2], w0.z, a); a = fmaf(g4[3], w0.w, a);
-            v[i] = ((mk >> i) & 1u) ? a : 0.f;
-          }
-        } else
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const float4* wr = reinterpret_cast<const float4*>(s_w4 + (ch * 32 + i) * 16);
-          const float4 w0 = wr[0], w1 = wr[1], w2 = wr[2], w3 = wr[3];
-          float a = g4[0] * w0.x;
-          a = fmaf(g4[1], w0.y, a); a = fmaf(g4[2], w0.z, a); a = fmaf(g4[3], w0.w, a);
-          a = fmaf(g4[4], w1.x, a); a = fmaf(g4[5], w1.y, a); a = fmaf(g4[6], w1.z, a); a = fmaf(g4[7], w1.w, a);
-          a = fmaf(g4[8], w2.x, a); a = fmaf(g4[9], w2.y, a); a = fmaf(g4[10], w2.z, a); a = fmaf(g4[11], w2.w, a);
-          a = fmaf(g4[12], w3.x, a); a = fmaf(g4[13], w3.y, a);
-          v[i] = ((mk >> i) & 1u) ? a : 0.f;
-        }
-        store_act(v, ch);
-      }
-      publish_act();
-      TB_STAMP();
-      // ---- backward epilogues EB3 (mask of layer 2), EB2 (mask of layer 1): renormalise, mask, split
-#pragma unroll 1
-      for (int bl = 1; bl >= 0; --bl) {
-        tq_mbar_wait(tq_smem_u32(&acc_full), (uint32_t)iacc & 1u); ++iacc;
-        tq_fence_after();
-        float vmax = 0.f;
-#pragma unroll 1
-        for (int ch = 0; ch < 4; ++ch) {
-          float v[32];
-          tq_ld32(acc_base + ch * 32, v);
-          const uint32_t mk = s_mask[bl][ch][r];
-#pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if ((mk >> i) & 1u) vmax = fmaxf(vmax, fabsf(v[i]));
-        }
-        const int e = tb_norm_exp(vmax);
-        e_total += e;
-        if (merge && bl == 0) {
-          // g1 of this head stays in TENSOR MEMORY, written over its own accumulator columns (per 32-column chunk: 16 columns of packed hi
-          // pairs, 16 of lo pairs), as the A operand of the merged B1 product.  Both heads must share one per-point exponent E = max(e_A, e_B):
-          // the second head scales its own values on the way in and, if it raised E, rescales the first head's columns (powers of two: exact).
-          int E = e_total;
-          if (pj == 1) E = max(E, s_scale_e[r]);
-          const float inv = ldexpf(1.f, -e + (e_total - E));
-#pragma unroll 1
-          for (int ch = 0; ch < 4; ++ch) {
-            float v[32];
-            tq_ld32(acc_base + ch * 32, v);
-            const uint32_t mk = s_mask[bl][ch][r];
-            uint32_t hi[16], lo[16];
-#pragma unroll
-            for (int i = 0; i < 32; i += 2) {
-              const float a = ((mk >> i) & 1u) ? v[i] * inv : 0.f, c2 = ((mk >> (i + 1)) & 1u) ? v[i + 1] * inv : 0.f;
-              tq_split2(a, c2, hi[i >> 1], lo[i >> 1], amax);
-            }
-            tb_st16(acc_base + ch * 32, hi);
-            tb_st16(acc_base + ch * 32 + 16, lo);
-          }
-          // (tcgen05.ld / st are warp-collective: the branch must be warp-uniform, rows that need no rescale multiply by one)
-          const bool rescale = pj == 1 && s_scale_e[r] < E;
-          if (__any_sync(0xffffffffu, rescale)) {
-            const __half2 sc2 = __float2half2_rn(rescale ? ldexpf(1.f, max(s_scale_e[r] - E, -30)) : 1.f);
-            const uint32_t other = lane_base;               // the first head's accumulator columns
-#pragma unroll 1
-            for (int q = 0; q < 8; ++q) {
-              uint32_t w[16];
-              tb_ld16(other + q * 16, w);
-#pragma unroll
-              for (int i = 0; i < 16; ++i) {
-                const __half2 t = __hmul2(*reinterpret_cast<const __half2*>(&w[i]), sc2);
-                w[i] = *reinterpret_cast<const uint32_t*>(&t);
-              }
-              tb_st16(other + q * 16, w);
-            }
-          }
-          asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-          s_scale_e[r] = E;
-          publish_act();
-          TB_STAMP();
-          continue;
-        }
-        const float inv = ldexpf(1.f, -e);
-#pragma unroll 1
-        for (int ch = 0; ch < 4; ++ch) {
-          float v[32];
-          tq_ld32(acc_base + ch * 32, v);
-          const uint32_t mk = s_mask[bl][ch][r];
-#pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = ((mk >> i) & 1u) ? v[i] * inv : 0.f;
-          store_act(v, ch);
-        }
-        if (bl == 0) s_scale_e[r] = e_total;               // read by the gather warps after the first staging chunk is published
-        publish_act();
-        TB_STAMP();
-      }
+      const int h = (int)__fns((unsigned)heads, 0, hi + 1), pj = hi & 1;
+      chain_head(hi, 0, iacc, amax);
+      if (fwd_only(h)) continue;
       if (merge && pj == 0) continue;                      // the feature gradients of both heads are drained together, after the second head
       // ---- drain gf (five 128-column groups) into the fp32 staging ring for the gather warps
       for (int u = 0; u < TQ_NCHUNK / 2; ++u, ++gfi) {
         const int gs = gfi % TB_NGF;
         tq_mbar_wait(tq_smem_u32(&gf_full[gs]), (uint32_t)(gfi / TB_NGF) & 1u);
         tq_fence_after();
+        TB_STAMP();
 #pragma unroll 1
         for (int ch = 0; ch < 4; ++ch) {
           if ((ch & 1) == 0) {
@@ -761,15 +904,15 @@ query_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_c
         tq_fence_before();
         __syncwarp();
         if (lane == 0) tq_mbar_arrive(tq_smem_u32(&gf_empty[gs]));
+        TB_STAMP();
       }
-      TB_STAMP();
     }
     if (amax > 65504.f) atomicAdd(overflow, 1);
   }
   tq_fence_before();
   __syncthreads();
   if (warp == 0) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(s_tmem_base), "r"(512u) : "memory");
   }
 }
 
@@ -791,19 +934,21 @@ static int launch_bwd_tc(const float* points, const float* crop_center, const fl
   const int head_stride = 616 * 128 + 128 + 2 * (128 * 128 + 128) + 128 * 16 + 16;
   TbParams prm2 = prm;
   const bool trace = getenv("VT_QUERY_TRACE") != nullptr;       // debug only: synchronises and prints the phase stamps of CTA (0,0)
-  if (trace) { cudaMalloc(&prm2.trace, 32 * sizeof(long long)); cudaMemset(prm2.trace, 0, 32 * sizeof(long long)); }
+  if (trace) { cudaMalloc(&prm2.trace, 256 * sizeof(long long)); cudaMemset(prm2.trace, 0, 256 * sizeof(long long)); }
   query_bwd_tc_kernel<<<grid, TB_THREADS, TB_SMEM, stream>>>(mp[0], mp[1], mp[2], mp[3], mp[4], mp[5], mp[6], mp[7], points, crop_center,
                                                              body_center, B, N, m, cam, wpack, head_stride, prm2, overflow);
   VT_CHECK_LAUNCH(who);
   if (trace) {
-    long long h[32];
+    long long h[256];
     cudaDeviceSynchronize();
     cudaMemcpy(h, prm2.trace, sizeof(h), cudaMemcpyDeviceToHost);
     cudaFree(prm2.trace);
     fprintf(stderr, "[%s trace, cycles since CTA start] epilogue:", who);
-    for (int i = 1; i < 16 && h[i]; ++i) fprintf(stderr, " %lld", h[i] - h[0]);
+    for (int i = 1; i < 64 && h[i]; ++i) fprintf(stderr, " %lld", h[i] - h[0]);
     fprintf(stderr, " | gather:");
-    for (int i = 17; i < 32 && h[i]; ++i) fprintf(stderr, " %lld", h[i] - h[0]);
+    for (int i = 65; i < 128 && h[i]; ++i) fprintf(stderr, " %lld", h[i] - h[0]);
+    fprintf(stderr, " | mma:");
+    for (int i = 128; i < 256 && h[i]; ++i) fprintf(stderr, " %lld", h[i] - h[0]);
     fprintf(stderr, "\n");
   }
   return 0;

@@ -35,15 +35,24 @@ __device__ __forceinline__ bool tq_mbar_try_wait(uint32_t bar, uint32_t parity) 
                : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
   return ok != 0;
 }
+// spin on try_wait (which itself suspends the thread for a hardware-bounded time); the deadlock guard counts polls instead of reading the
+// clock: the waiting warps share their scheduler's issue slots with the working ones, so the loop is kept to try_wait + add + branch
 __device__ __forceinline__ void tq_mbar_wait(uint32_t bar, uint32_t parity) {
-  long long t0 = clock64();
+  unsigned polls = 0;
   while (!tq_mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000LL) { printf("vt query_tc: mbarrier timeout (block %d,%d thread %d)\n", blockIdx.x, blockIdx.y, threadIdx.x); __trap(); }
+    if (++polls > (1u << 27)) { printf("vt query_tc: mbarrier timeout (block %d,%d thread %d)\n", blockIdx.x, blockIdx.y, threadIdx.x); __trap(); }
   }
 }
 __device__ __forceinline__ void tq_tma_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
                ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+// one lane of a converged warp; tcgen05.mma / commit issued under this predicate in warp-uniform control flow compile to straight-line
+// UTCHMMA (under a plain `lane == 0` test every one sits in an ELECT / BRA.U.ANY loop over the active lanes)
+__device__ __forceinline__ bool tq_elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+  return pred != 0;
 }
 __device__ __forceinline__ void tq_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tq_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
