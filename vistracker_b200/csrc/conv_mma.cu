@@ -97,16 +97,25 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+// The MMA-issuer WARP walks its (warp-uniform) control flow as a whole and polls the barriers; tcgen05.mma / commit are issued by one lane
+// elected here.  Under a plain `lane == 0` branch the compiler wraps every tcgen05.mma in an ELECT / BRA.U.ANY loop over the active lanes
+// (~10 instructions per MMA); with elect.sync in converged code it emits straight-line UTCHMMA.
+__device__ __forceinline__ bool tc_elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+  if (tc_elect_one()) asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 // D[tmem] (+)= A[smem] * B[smem], kind::f16, M=128, single CTA
 __device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+  if (tc_elect_one())
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
 }
 __device__ __forceinline__ void tc_ld32(uint32_t taddr, float (&v)[32]) {
   uint32_t r[32];
@@ -142,7 +151,7 @@ __device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t saddr) {
 template <int BN>
 __device__ __forceinline__ void conv_epilogue(const ConvMmaParams& p, uint32_t bar_accum_addr, uint32_t tmem_base, float* stile,
                                               float* s_sum, float* s_sq, float* s_sum2, float* s_sq2, int img, int n0, int y0, int x0) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // warp-uniform for the compiler
   mbar_wait(bar_accum_addr, 0);
   tc_fence_after();
   constexpr int LDT = BN + 4;
@@ -249,7 +258,7 @@ conv_mma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
   __shared__ float s_sum[BN], s_sq[BN], s_sum2[BN], s_sq2[BN];
 
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // warp-uniform for the compiler
   const int img = blockIdx.y, n0 = blockIdx.z * BN;
   const int tile_y = blockIdx.x / p.tiles_x, tile_x = blockIdx.x % p.tiles_x;
   const int y0 = tile_y * p.bh, x0 = tile_x * p.bw;
@@ -296,8 +305,8 @@ conv_mma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
       }
     }
   } else if (warp == 5) {
-    // ------------------------------------------------------------------ MMA issuer (one thread)
-    if (lane == 0) {
+    // ------------------------------------------------------------------ MMA issuer (whole warp; one elected lane issues, see tc_elect_one)
+    {
       const uint32_t acc0 = tmem_base, acc1 = tmem_base + BN;
       for (int it = 0; it < n_iter; ++it) {
         const int s = it % Cfg::STAGES;
@@ -429,7 +438,7 @@ conv_mma_persist_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __gri
   __shared__ __align__(16) float s_sum[4][BN], s_sq[4][BN], s_sum2[4][BN], s_sq2[4][BN];
 
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // warp-uniform for the compiler
   const int n_iter = p.ks * p.ks * p.kchunks;
 
   for (int i = threadIdx.x; i < 4 * BN; i += Cfg::THREADS) { (&s_sum[0][0])[i] = 0.f; (&s_sq[0][0])[i] = 0.f; (&s_sum2[0][0])[i] = 0.f; (&s_sq2[0][0])[i] = 0.f; }
@@ -541,8 +550,8 @@ conv_mma_persist_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __gri
       }
     }
   } else if (warp == 5) {
-    // ------------------------------------------------------------------ MMA issuer (one thread)
-    if (lane == 0) {
+    // ------------------------------------------------------------------ MMA issuer (whole warp; one elected lane issues, see tc_elect_one)
+    {
       if constexpr (STRIP) {
         uint32_t ga = 0, gb = 0, i = 0;
         const uint32_t b_base = smem_base + Cfg::NA * Cfg::STRIP_SLOT;
@@ -839,7 +848,7 @@ conv_mma_strip_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_
   __shared__ float s_sum[T][BN], s_sq[T][BN], s_sum2[T][BN], s_sq2[T][BN];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t b_base = smem_base + Cfg::NA * Cfg::A_SLOT;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // warp-uniform for the compiler
   const int img0 = blockIdx.y * T, n0 = blockIdx.z * BN;
   const int y0 = blockIdx.x / p.tiles_x, x0 = (blockIdx.x % p.tiles_x) * MM_M;     // bh == 1: one image row per tile
   const int n_strips = 3 * p.kchunks;
@@ -895,7 +904,8 @@ conv_mma_strip_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_
       }
     }
   } else if (warp == 5) {
-    if (lane == 0) {     // ---------------- MMA issuer
+    // ------------------------------------------------------------------ MMA issuer (whole warp; one elected lane issues, see tc_elect_one)
+    {
       int ib = 0;
       for (int is = 0; is < n_strips; ++is) {
         const int sa = is % Cfg::NA;

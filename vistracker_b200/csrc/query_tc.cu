@@ -42,7 +42,7 @@ query_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_c
   const uint32_t feat_base = smem_base, w_base = smem_base + TQ_NF * TQ_SLOT, act_base = w_base + TQ_NW * TQ_SLOT;
   uint8_t* feat_ptr = smem_al;
   uint8_t* act_ptr = smem_al + TQ_NF * TQ_SLOT + TQ_NW * TQ_SLOT;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // warp-uniform for the compiler
   const int b = blockIdx.y, n0 = blockIdx.x * TQ_M;
   // active heads (bit h of head_mask), four per pass: the g-th head of pass p is the (4p+g+1)-th set bit
   const int n_heads = __popc((unsigned)head_mask), n_pass = (n_heads + 3) >> 2;
@@ -174,23 +174,28 @@ query_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_c
       }
     }
   } else if (warp == 5) {
-    // ================================================================== MMA issuer
-    if (lane == 0) {
+    // ================================================================== MMA issuer (whole warp walks the control flow; one elected lane issues:
+    // straight-line UTCHMMA instead of an ELECT / BRA.U.ANY loop per instruction, see tq_elect_one)
+    {
       int it = 0, iw = 0, iact = 0;
+      auto commit = [&](uint64_t* bar) { if (tq_elect_one()) tq_commit(tq_smem_u32(bar)); __syncwarp(); };
       auto mma_tile = [&](uint32_t a_addr, uint32_t acc, bool first) {
         const int s = iw % TQ_NW;
         tq_mbar_wait(tq_smem_u32(&w_full[s]), (uint32_t)(iw / TQ_NW) & 1u);
         tq_fence_after();
         const uint64_t a_hi = tq_desc(a_addr), a_lo = tq_desc(a_addr + TQ_PLANE);
         const uint64_t b_hi = tq_desc(w_base + s * TQ_SLOT), b_lo = tq_desc(w_base + s * TQ_SLOT + TQ_PLANE);
+        if (tq_elect_one()) {
 #pragma unroll
-        for (int k = 0; k < TQ_KC / 16; ++k) {
-          const uint64_t adv = (uint64_t)(k * 32 >> 4);
-          tq_mma(acc, a_hi + adv, b_hi + adv, (first && k == 0) ? 0u : 1u);
-          tq_mma(acc, a_hi + adv, b_lo + adv, 1u);
-          tq_mma(acc, a_lo + adv, b_hi + adv, 1u);
+          for (int k = 0; k < TQ_KC / 16; ++k) {
+            const uint64_t adv = (uint64_t)(k * 32 >> 4);
+            tq_mma(acc, a_hi + adv, b_hi + adv, (first && k == 0) ? 0u : 1u);
+            tq_mma(acc, a_hi + adv, b_lo + adv, 1u);
+            tq_mma(acc, a_lo + adv, b_hi + adv, 1u);
+          }
+          tq_commit(tq_smem_u32(&w_empty[s]));
         }
-        tq_commit(tq_smem_u32(&w_empty[s]));
+        __syncwarp();
         ++iw;
       };
       for (int pass = 0; pass < n_pass; ++pass) {
@@ -200,15 +205,15 @@ query_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_c
           tq_mbar_wait(tq_smem_u32(&feat_full[slot]), (uint32_t)(it / TQ_NF) & 1u);
           tq_fence_after();
           for (int g = 0; g < nh; ++g) mma_tile(feat_base + slot * TQ_SLOT, tmem_base + g * TQ_H, c == 0);
-          tq_commit(tq_smem_u32(&feat_empty[slot]));
+          commit(&feat_empty[slot]);
         }
-        tq_commit(tq_smem_u32(&acc_full));                 // layer 1 of the whole group is complete
+        commit(&acc_full);                                 // layer 1 of the whole group is complete
         for (int g = 0; g < nh; ++g)
           for (int layer = 0; layer < 2; ++layer) {
             tq_mbar_wait(tq_smem_u32(&act_full), (uint32_t)iact & 1u); ++iact;     // epilogue wrote this layer's input
             tq_fence_after();
             for (int kc = 0; kc < 2; ++kc) mma_tile(act_base + kc * TQ_SLOT, tmem_base + g * TQ_H, kc == 0);
-            tq_commit(tq_smem_u32(&acc_full));
+            commit(&acc_full);
           }
       }
     }
