@@ -18,7 +18,7 @@ seeded synthetic checkpoint of ``vistracker_b200.synth`` and stores inputs-by-se
 * ``infill_small.npz``      -- (``--only infill``) ConditionalMInfiller forward on two batches and CondMotionInfillAutoreg.test (the
   reference's own autoregressive clip loop, file IO redirected to a temporary folder) on a 400-frame synthetic sequence.
 * ``frameio_small.npz``     -- (``--only frameio``) BehaveDataset.prepare_image_crop / BaseDataset.crop / compose_images on three synthetic
-  frames (centred, running past the right/bottom border, past the top/left one); cv2.resize / findContours injected (OpenCV absent).
+  frames (centred, running past the right/bottom border, past the top/left one) with the real cv2 4.13; direct cv2.resize / bbox vectors.
 * ``interp_small.npz``      -- (``--only interp``) BaseInterpolator.compute_missing_inds / interp_slerp / interp_lerp (SLERP baseline).
 * ``generator_small.npz``   -- (``--only generator``) the reference's GeneratorTriplaneVis.get_grid_samples / approx_surface / gen_pc_batch
   executed on the CPU (instance created without ``__init__``, which only loads a checkpoint and moves the model to CUDA).
@@ -524,31 +524,63 @@ def infill_goldens(out_dir: str):
     print("infill_small.npz:", {k: getattr(v, "shape", v) for k, v in out.items() if k != "opt_json"}, missing)
 
 def frameio_goldens(out_dir: str):
-    """Test-time frame preparation: the reference's BehaveDataset.prepare_image_crop / BaseDataset.crop /
-    compose_images (data/train_data.py:143-162, data/base_data.py:204-265), called unbound on a shim.  OpenCV is not installed: ``resize``
-    (cv2.resize) and ``center_from_masks`` (cv2.findContours) are injected from oracle/frameio_ref.py -- those two stay unpinned; the crop
-    arithmetic, the order of operations, the /255 in float64, the masking and the channel layout are the reference's -> frameio_small.npz."""
-    _stub("cv2", INTER_LINEAR=1, setNumThreads=lambda n: None)
+    """Test-time frame preparation: the reference's BehaveDataset.prepare_image_crop and BaseDataset.crop /
+    compose_images / resize / masks2bbox / center_from_masks (data/train_data.py:143-162, data/base_data.py:139-171,204-265), called unbound on a
+    shim, WITH THE REAL OpenCV (cv2 4.13, opencv-python-headless): cv2.resize(INTER_LINEAR) on uint8 and cv2.threshold / findContours /
+    boundingRect run as the reference runs them.  Also direct cv2 vectors for the two restated operators: resizes at the production ratio
+    (1200 -> 512 = 2.34375, 3 and 1 channels; the full-size result as a SHA-256), a non-square and an identity resize, and the bounding box of
+    masks with isolated speckle, a uint8 wrap-around (128 + 128) and soft borders -> frameio_small.npz."""
+    import hashlib
+    import cv2                                                                         # real
     pkg = _stub("data"); pkg.__path__ = [os.path.join(os.getcwd(), "data")]       # data/__init__.py pulls in trimesh / igl; load the two files only
+    ps = _stub("psbody"); ps.mesh = _stub("psbody.mesh", Mesh=object)
     from data.base_data import BaseDataset                                            # reference
     from data.train_data import BehaveDataset                                         # reference
-    from oracle import frameio_ref as FR
     from vistracker_b200.synth import synthetic_camera_frame
 
     H, W, CROP, NET = 180, 240, 150, 64                                                # 150 / 64 = 1200 / 512
-    out = {"H": H, "W": W, "crop": CROP, "net": NET}
+    out = {"H": H, "W": W, "crop": CROP, "net": NET, "cv2_version": cv2.__version__}
     centers = {"mid": None, "right_bottom": (205.0, 150.0), "top_left": (30.0, 25.0)}
     for i, (tag, ctr) in enumerate(centers.items()):
         rgb, person, obj = synthetic_camera_frame(H, W, seed=30 + i, center=ctr)
         shim = types.SimpleNamespace(CROP_SIZE=np.array([CROP, CROP]), img_size=(NET, NET), dtype=np.float32,
-                                     load_masks=lambda f, flip: (person, obj), load_rgb=lambda f, flip: rgb,
-                                     center_from_masks=lambda o, p, f: FR.center_from_masks(o, p),
-                                     resize=lambda img, size, mode=1: FR.resize_linear_u8(img, size))
-        shim.crop = types.MethodType(BaseDataset.crop, shim)
-        shim.compose_images = types.MethodType(BaseDataset.compose_images, shim)
+                                     load_masks=lambda f, flip: (person, obj), load_rgb=lambda f, flip: rgb)
+        for name in ("crop", "compose_images", "resize", "masks2bbox", "center_from_masks"):
+            setattr(shim, name, types.MethodType(getattr(BaseDataset, name), shim))
         images, center = BehaveDataset.prepare_image_crop(shim, "frame.color.jpg", False)
         out[f"{tag}_images"], out[f"{tag}_center"] = images, np.asarray(center)
         out[f"{tag}_crop_rgb"] = BaseDataset.crop(shim, rgb, center, shim.CROP_SIZE)
+        bmin, bmax = BaseDataset.masks2bbox(shim, [person, obj])
+        out[f"{tag}_bbox"] = np.concatenate([bmin, bmax])
+    # ---- cv2.resize vectors (seeded noise + gradients: every interpolation weight pair occurs)
+    rng = np.random.Generator(np.random.PCG64(77))
+    def noise(h, w, c=None):
+        return rng.integers(0, 256, (h, w) if c is None else (h, w, c)).astype(np.uint8)
+    for tag, (src, dsize) in {"r300_128_rgb": (noise(300, 300, 3), (128, 128)), "r300_128_mask": (noise(300, 300), (128, 128)),
+                              "r300x200_128x96": (noise(200, 300, 3), (128, 96)), "r75_32": (noise(75, 75, 3), (32, 32)),
+                              "r64_64": (noise(64, 64, 3), (64, 64)), "r37_100": (noise(37, 37), (100, 100))}.items():
+        out[f"{tag}_src"], out[f"{tag}_dst"] = src, cv2.resize(src, dsize, interpolation=cv2.INTER_LINEAR)
+    big_rgb, big_person, _ = synthetic_camera_frame(1200, 1200, seed=41)
+    out["r1200_512_rgb_sha256"] = hashlib.sha256(cv2.resize(big_rgb, (512, 512), interpolation=cv2.INTER_LINEAR).tobytes()).hexdigest()
+    out["r1200_512_mask_sha256"] = hashlib.sha256(cv2.resize(big_person, (512, 512), interpolation=cv2.INTER_LINEAR).tobytes()).hexdigest()
+    # ---- masks2bbox vectors
+    shim = types.SimpleNamespace()
+    boxes = []
+    for k in range(4):
+        a, b = np.zeros((120, 160), np.uint8), np.zeros((120, 160), np.uint8)
+        r = np.random.Generator(np.random.PCG64(90 + k))
+        x0, y0 = int(r.integers(5, 60)), int(r.integers(5, 40))
+        a[y0:y0 + int(r.integers(8, 50)), x0:x0 + int(r.integers(8, 60))] = 255
+        b[y0 + 10:y0 + 10 + int(r.integers(8, 50)), x0 + 20:x0 + 20 + int(r.integers(8, 60))] = int(r.integers(128, 256))
+        for _ in range(6):                                                            # isolated speckle, some below the threshold
+            yy, xx = int(r.integers(0, 120)), int(r.integers(0, 160))
+            a[yy, xx] = int(r.choice([60, 127, 128, 200, 255]))
+        if k == 1:                                                                    # 128 + 128 wraps to 0 in uint8 before the clip
+            a[100, 150] = 128; b[100, 150] = 128
+        out[f"bbox{k}_a"], out[f"bbox{k}_b"] = a, b
+        bmin, bmax = BaseDataset.masks2bbox(shim, [a, b])
+        boxes.append(np.concatenate([bmin, bmax]))
+    out["bbox_ref"] = np.stack(boxes)
     np.savez_compressed(os.path.join(out_dir, "frameio_small.npz"), **out)
     print("frameio_small.npz:", {k: getattr(v, "shape", v) for k, v in out.items()})
 
@@ -1186,7 +1218,7 @@ if __name__ == "__main__":
         eval_goldens(HERE)
     if a.only == "smooth":                  # stubs `behave` / `yacs`: run on its own
         smooth_goldens(HERE)
-    if a.only == "frameio":                 # stubs `cv2` and the `data` package: run on its own
+    if a.only == "frameio":                 # stubs the `data` package (real cv2): run on its own
         frameio_goldens(HERE)
     if a.only == "interp":                  # stubs `behave`: run on its own
         interp_goldens(HERE)

@@ -57,3 +57,29 @@ def test_acceleration_error_helper_matches_reference_columns():
         ref = g[f"errors_{tag}"]
         assert np.allclose(acc_s.numpy(), ref[:, 4], rtol=1e-7, atol=1e-9, equal_nan=True), tag
         assert np.allclose(acc_o.numpy(), ref[:, 5], rtol=1e-7, atol=1e-9, equal_nan=True), tag
+
+
+def test_chamfer_ragged_agrees_with_an_independent_kd_tree_computation():
+    """pytorch3d.loss.chamfer_distance(Pointclouds(x), Pointclouds(y)) -- the operator behind compute_contact_loss
+    (recon/recon_fit_trivis_full.py:393-457) -- is un-vendored, so oracle/geom_ref.chamfer_ragged restates its published
+    definition: per cloud pair the mean SQUARED nearest-neighbour distance in both directions (point_reduction='mean'), averaged over the
+    batch (batch_reduction='mean').  Cross-check against a computation that shares no code with it: exact nearest neighbours from
+    scikit-learn's KDTree (the structure the reference's own evaluation uses, recon/eval/chamfer_distance.py:28-33) in float64, on ragged
+    clouds including a single-point cloud and duplicated points."""
+    import torch
+    from sklearn.neighbors import KDTree
+    rng = np.random.default_rng(5)
+    sizes = [(37, 210), (1, 64), (150, 3), (96, 96)]
+    xs = [rng.standard_normal((a, 3)) * 0.3 for a, _ in sizes]
+    ys = [rng.standard_normal((b, 3)) * 0.3 + 0.1 for _, b in sizes]
+    xs[3][10:20] = xs[3][0]                                                        # duplicates: ties between neighbours
+    ref = 0.0
+    for x, y in zip(xs, ys):
+        dxy = KDTree(y).query(x, k=1)[0][:, 0]
+        dyx = KDTree(x).query(y, k=1)[0][:, 0]
+        ref += (dxy ** 2).mean() + (dyx ** 2).mean()
+    ref /= len(xs)
+    got = G.chamfer_ragged([torch.from_numpy(x) for x in xs], [torch.from_numpy(y) for y in ys])
+    assert abs(float(got) - ref) <= 1e-12 * max(1.0, abs(ref))
+    got32 = G.chamfer_ragged([torch.from_numpy(x).float() for x in xs], [torch.from_numpy(y).float() for y in ys])
+    assert abs(float(got32) - ref) <= 2e-6 * abs(ref)

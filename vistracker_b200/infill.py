@@ -20,6 +20,18 @@ import torch
 from . import _lib
 
 P, S = _lib.ptr, _lib.stream_ptr
+
+
+def _on_own_device(fn):
+    """Run a method with the module's device current: ``_lib.stream_ptr()``, the kernel launches and CUDA-graph capture all act on the
+    CURRENT device (a multi-GPU process may not have called ``torch.cuda.set_device``)."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapped(self, *a, **kw):
+        with torch.cuda.device(self.device):
+            return fn(self, *a, **kw)
+    return wrapped
 _ACT = {"gelu": 0, "relu": 1, "leaky_relu": 2}
 
 
@@ -161,6 +173,7 @@ class ConditionalMInfiller:
                                  attn2=e(n, self.Do), side=torch.cuda.Stream(device=dev))
         return self._ws[key]
 
+    @_on_own_device
     def forward_into(self, data_smpl, mask_smpl, data_obj, mask_obj, pred, pin: bool = False):
         """All arguments device tensors: data [B,T,*] float32 contiguous, masks [B,T] uint8/bool or None, pred [B,T,out_dim].  ``pin`` keeps
         the (B, T) workspace alive for the lifetime of the module (callers that capture the launches into a CUDA graph)."""
@@ -247,6 +260,7 @@ class CondMotionInfillAutoreg:
             _lib.call("vt_infill_commit_clip", P(pred), L, s, n_ctx, T, P(b["out"]), S())
         _lib.call("vt_smooth_rot6d_to_rotmat", P(b["out"]), L, 1, P(b["angles"]), S())          # stored as R^T (interp/test_infiller.py:134)
 
+    @_on_own_device
     def infill(self, rot6d_smpl, trans_smpl, rot6d_obj, trans_obj, occ_ratios, occ_thres: float = 0.5):
         """rot6d_smpl [L,144], trans_smpl [L,3], rot6d_obj [L,6], trans_obj [L,3] (tensors or arrays), occ_ratios [L] (visible fraction, the
         first column of ``neural_visibility``).  Returns what ``save_output`` stores: ``obj_angles`` [L,3,3] (= R^T), ``obj_trans`` (a copy of the

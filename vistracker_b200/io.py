@@ -71,9 +71,17 @@ def save_smpl_params(folders: Sequence[str], tid: int, pose, betas, trans, score
 
 def save_object_params(folders: Sequence[str], tid: int, obj_R, obj_t, obj_s) -> List[str]:
     """`obj_R` is the free 3x3 optimisation variable: it is projected to SO(3) WITHOUT the decopose_axis noise before saving
-    (recon/recon_fit_base.py:303, `no_rand=True`).  A host array / CPU tensor is taken to be projected already."""
+    (recon/recon_fit_base.py:303, `no_rand=True`) -- always, as the reference does: a host array / CPU tensor goes through the same SVD
+    projection on the host (U diag(1, 1, det(U V^T)) V^T, what ``decopose_axis`` computes)."""
     from .geom import project_so3
-    R = _np(project_so3(obj_R.detach())) if torch.is_tensor(obj_R) and obj_R.is_cuda else _np(obj_R)
+    if torch.is_tensor(obj_R) and obj_R.is_cuda:
+        R = _np(project_so3(obj_R.detach()))
+    else:
+        A = np.asarray(_np(obj_R), np.float64).reshape(-1, 3, 3)
+        U, _, Vt = np.linalg.svd(A)
+        d = np.linalg.det(U @ Vt)
+        D = np.tile(np.eye(3), (A.shape[0], 1, 1)); D[:, 2, 2] = d
+        R = (U @ D @ Vt).astype(np.float32)
     t, s = _np(obj_t), _np(obj_s)
     files = []
     for i, folder in enumerate(folders):

@@ -36,6 +36,7 @@ class _QueryFn(torch.autograd.Function):
     def forward(ctx, net: "CHORETriplaneVisibility", points, crop_center, body_center):
         out, xy = net._query_raw(points, crop_center, body_center, want_xy=True)
         ctx.net = net
+        ctx.maps = net._maps                       # the backward differentiates against the maps of THIS forward, not of a later filter()
         ctx.save_for_backward(points, crop_center, body_center)
         ctx.set_materialize_grads(False)
         ctx.mark_non_differentiable(xy)
@@ -52,7 +53,7 @@ class _QueryFn(torch.autograd.Function):
         for h, (lo, hi) in enumerate(HEAD_SLICES):
             if grads[h] is not None:
                 g_out[:, lo:hi] = grads[h]
-        g_pts = ctx.net._query_backward(points, crop_center, body_center, g_out, head_mask=mask)
+        g_pts = ctx.net._query_backward(points, crop_center, body_center, g_out, head_mask=mask, maps=ctx.maps)
         return None, g_pts, None, None
 
 
@@ -335,10 +336,11 @@ class CHORETriplaneVisibility:
             return feat, xy
         return out, xy
 
-    def _query_backward(self, points, crop_center, body_center, g_out, head_mask: int = 31):
+    def _query_backward(self, points, crop_center, body_center, g_out, head_mask: int = 31, maps=None):
         """d(sum g_out * out)/d(points) with the maps of the last filter() call (csrc/query.cu: query_bwd_kernel), restricted to
-        the heads in ``head_mask`` (bit h set = head h has a non-zero cotangent)."""
-        im_feat, tmpx, tri_tmpx, tri_feat = self._maps
+        the heads in ``head_mask`` (bit h set = head h has a non-zero cotangent).  ``maps``: the feature maps of the forward pass (autograd
+        keeps them; default = the current ones)."""
+        im_feat, tmpx, tri_tmpx, tri_feat = self._maps if maps is None else maps
         B, N = points.shape[0], points.shape[1]
         pts = points.detach().to(self.device, torch.float32).contiguous()
         cc = crop_center.to(self.device, torch.float32).contiguous()
