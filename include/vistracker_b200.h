@@ -26,6 +26,39 @@ const char* vt_last_error(void);          /* host string, valid until the next f
 int vt_version(void);                     /* ABI version, currently 1 */
 int vt_compiled_arch(void);               /* 100 -> built with -gencode arch=compute_100a,code=sm_100a */
 
+/* ---- one-time re-packing of a reference checkpoint (HOST pointers in and out; csrc/pack.cu) -- SURVEY.md 8(b) `vt_pack_weights_<op>` ----
+ * The reference keeps `CHORETriplaneVisibility.state_dict()` tensors in torch layouts (model/HGFilters.py: Conv2d [Cout][Cin][k][k];
+ * model/chore.py:113-126: Conv1d(k=1) decoders [out][in][1]) and the SMPL-H buffers of lib_smpl/smplpytorch/smplpytorch/pytorch/smpl_layer.py:30-71;
+ * these functions write the layouts the kernels below read.  The caller allocates the outputs and uploads them. */
+
+/* input channels of the fp16 planes, padded to the K chunk of the tensor-core convolution (64) */
+int vt_conv_cin_pad(int cin);
+/* Conv2d weight w[Cout][Cin][ks][ks] -> ffma fp32 [ks*ks][Cin][Cout] (vt_conv_ffma) and fp16 planes hi / lo [ks*ks][Cout][cin_pad] with
+ * w ~= hi + lo / 2048 (vt_conv_mma).  ffma or the plane pair may be NULL.  -4: a weight exceeds the fp16 range. */
+int vt_pack_weights_conv(const float* w, int cout, int cin, int ks, float* ffma, void* hi, void* lo);
+/* Conv2d(cin, cout, 7, stride 2) weight w[Cout][Cin][7][7] -> fp32 [49*cin][cout] (vt_stem_conv7x7s2) */
+int vt_pack_weights_stem(const float* w, int cout, int cin, float* out);
+/* The five decoders: w[h*4 + l] / b[h*4 + l] = Conv1d(k=1) weight [out][in] / bias [out] of head h (df, pca_predictor, part_predictor,
+ * center_predictor, visib_predictor) layer l (in = 611, 128, 128, 128).  wpack: vt_query_wpack_floats() floats (vt_query_fwd and the fp32
+ * part of the tensor-core kernels), wpack_bwd: vt_query_wpack_bwd_floats() floats (vt_query_bwd); either may be NULL. */
+int vt_pack_weights_decoders(const float* const* w, const float* const* b, float* wpack, float* wpack_bwd);
+/* fp16 hi / lo planes of the tcgen05 decoder kernels (x ~= hi + lo): w1 [5*128][640], w23 [2*5*128][128] (vt_query_fwd_tc) and the
+ * transposes w23t [2*5*128][128], w1t [5*640][128] (vt_query_bwd_tc, vt_query_project_step_tc, vt_query_losses_*_tc; may be NULL together). */
+int vt_pack_weights_decoders_tc(const float* const* w, void* w1_hi, void* w1_lo, void* w23_hi, void* w23_lo, void* w23t_hi, void* w23t_lo,
+                                void* w1t_hi, void* w1t_lo);
+/* SMPL-H model buffers -> the arrays of SmplModel below.  Sizes: kd = 9 (J - 1) + n_betas, kdp / nv3p = kd / 3 V rounded up to 4,
+ * nnz = most non-zero skinning weights of a vertex.  v_template [V][3], shapedirs [V][3][n_betas], posedirs [V][3][9 (J - 1)],
+ * J_regressor [J][V] in float64 (as the model pickles hold them), weights [V][J] fp32, parents [J] (root: any value <= 0).
+ * Outputs: templ [3 V], dirs [kdp][nv3p], dirsT [nv3p][kdp], j_templ [J][3], j_dirs [J][3][n_betas], parents_out [J], skin_idx / skin_w [V][nnz]. */
+int vt_smpl_pack_dims(int V, int J, int n_betas, const float* weights, int* kd, int* kdp, int* nv3p, int* nnz);
+int vt_pack_weights_smpl(const double* v_template, const double* shapedirs, const double* posedirs, const double* J_regressor,
+                         const float* weights, const int* parents, int V, int J, int n_betas, float* templ, float* dirs, float* dirsT,
+                         float* j_templ, float* j_dirs, int* parents_out, int* skin_idx, float* skin_w);
+/* Caller-owned workspaces (SURVEY.md 8(b) `vt_workspace_bytes_<op>`): only vt_raster_* (optional culling boxes) and vt_procrustes take
+ * one; every other entry point works in the buffers named in its signature and needs no scratch memory. */
+long long vt_workspace_bytes_raster_cull(int B, int F);
+long long vt_workspace_bytes_procrustes(int B);
+
 /* ---- stacked-hourglass encoder pieces: model/HGFilters.py:162-203 (HGFilter.forward), :26-50 (HourGlass._forward),
  *      model/net_util.py:374-396 (ConvBlock.forward) ------------------------------------------------------------------ */
 

@@ -17,6 +17,15 @@ SIGNATURES = {
     "vt_last_error": (C.c_char_p, []),
     "vt_version": (_i, []),
     "vt_compiled_arch": (_i, []),
+    "vt_conv_cin_pad": (_i, [_i]),
+    "vt_pack_weights_conv": (_i, [_p, _i, _i, _i, _p, _p, _p]),
+    "vt_pack_weights_stem": (_i, [_p, _i, _i, _p]),
+    "vt_pack_weights_decoders": (_i, [_p, _p, _p, _p]),
+    "vt_pack_weights_decoders_tc": (_i, [_p] * 9),
+    "vt_smpl_pack_dims": (_i, [_i, _i, _i, _p, _p, _p, _p, _p]),
+    "vt_pack_weights_smpl": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "vt_workspace_bytes_raster_cull": (_ll, [_i, _i]),
+    "vt_workspace_bytes_procrustes": (_ll, [_i]),
     "vt_stem_conv7x7s2": (_i, [_p, _i, _i, _i, _i, _i, _i, _i, _p, _p, _i, _p, _p, _i, _p]),
     "vt_gn_finalize": (_i, [_p, _i, _p, _p, _i, _i, _i, _ll, _f, _p, _p, _p]),
     "vt_affine_act": (_i, [_p, _i, _p, _p, _i, _i, _i, _i, _p, _i, _p, _i, _p]),

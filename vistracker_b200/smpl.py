@@ -16,10 +16,6 @@ import torch
 from . import _lib
 
 
-def _pad4(n: int) -> int:
-    return (n + 3) // 4 * 4
-
-
 class _SmplFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, layer: "SMPL_Layer", pose, betas, trans, offsets, scale):
@@ -84,28 +80,24 @@ class SMPL_Layer:
         self.device, self.hands, self.center_idx, self.gender = dev, hands, center_idx, gender
         self.kintree_parents = list(kintree_parents)
         self.num_joints = len(self.kintree_parents)
-        vt = buffers["th_v_template"].detach().double().cpu().reshape(-1, 3)
-        sd = buffers["th_shapedirs"].detach().double().cpu()
-        pd = buffers["th_posedirs"].detach().double().cpu()
-        jr = buffers["th_J_regressor"].detach().double().cpu()
-        w = buffers["th_weights"].detach().float().cpu()
+        # the model buffers as the reference holds them (float64 pickles) -> kernel layouts: host C behind the ABI (vt_pack_weights_smpl)
+        h64 = lambda t: t.detach().to("cpu", torch.float64).contiguous()
+        vt, sd, pd, jr = h64(buffers["th_v_template"]).reshape(-1, 3), h64(buffers["th_shapedirs"]), h64(buffers["th_posedirs"]), h64(buffers["th_J_regressor"])
+        w = buffers["th_weights"].detach().to("cpu", torch.float32).contiguous()
         V, J, nb = vt.shape[0], self.num_joints, sd.shape[2]
         assert pd.shape == (V, 3, 9 * (J - 1)) and jr.shape == (J, V) and w.shape == (V, J)
+        hp = lambda t: ctypes.c_void_p(t.data_ptr())
+        dims = [ctypes.c_int() for _ in range(4)]
+        _lib.call("vt_smpl_pack_dims", V, J, nb, hp(w), *(ctypes.byref(d) for d in dims))
         self.V, self.J, self.n_betas = V, J, nb
-        self.kd = 9 * (J - 1) + nb
-        self.kdp, self.nv3p = _pad4(self.kd), _pad4(3 * V)
-        dirs = torch.zeros(self.kdp, self.nv3p, dtype=torch.float32)
-        dirs[:9 * (J - 1), :3 * V] = pd.reshape(3 * V, -1).t().float()
-        dirs[9 * (J - 1):self.kd, :3 * V] = sd.reshape(3 * V, -1).t().float()
-        nnz = int((w != 0).sum(1).max())
-        order = torch.argsort((w != 0).to(torch.int8), dim=1, descending=True, stable=True)[:, :nnz]
-        skin_w = torch.gather(w, 1, order).contiguous()
-        f = lambda t: t.contiguous().to(dev)
-        self._keep = dict(
-            templ=f(vt.reshape(-1).float()), dirs=f(dirs), dirsT=f(dirs.t()), j_templ=f((jr @ vt).float()),
-            j_dirs=f(torch.einsum("jv,vck->jck", jr, sd).float()),
-            parents=f(torch.tensor([max(p, 0) for p in self.kintree_parents], dtype=torch.int32)),
-            skin_idx=f(order.to(torch.int32)), skin_w=f(skin_w))
+        self.kd, self.kdp, self.nv3p, nnz = (d.value for d in dims)
+        parents = torch.tensor(self.kintree_parents, dtype=torch.int32)
+        e = lambda *sh, dt=torch.float32: torch.empty(*sh, dtype=dt)
+        host = dict(templ=e(3 * V), dirs=e(self.kdp, self.nv3p), dirsT=e(self.nv3p, self.kdp), j_templ=e(J, 3), j_dirs=e(J, 3, nb),
+                    parents=e(J, dt=torch.int32), skin_idx=e(V, nnz, dt=torch.int32), skin_w=e(V, nnz))
+        _lib.call("vt_pack_weights_smpl", hp(vt), hp(sd), hp(pd), hp(jr), hp(w), hp(parents), V, J, nb,
+                  *(hp(host[k]) for k in ("templ", "dirs", "dirsT", "j_templ", "j_dirs", "parents", "skin_idx", "skin_w")))
+        self._keep = {k: t.to(dev) for k, t in host.items()}
         self.struct = _lib.SmplModelStruct(V, J, nb, self.kd, self.kdp, self.nv3p, nnz,
                                            *(ctypes.c_void_p(self._keep[k].data_ptr()) for k in
                                              ("templ", "dirs", "dirsT", "j_templ", "j_dirs", "parents", "skin_idx", "skin_w")))
