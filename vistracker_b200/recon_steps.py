@@ -36,6 +36,24 @@ def _zero(t: torch.Tensor):
     _lib.call("vt_zero", P(t), t.numel() * t.element_size(), S())
 
 
+def capture_graph(enqueue) -> torch.cuda.CUDAGraph:
+    """Capture ``enqueue()`` on a side stream with ``CUDAGraph.capture_begin / capture_end`` directly.  The ``torch.cuda.graph`` context
+    manager also runs ``gc.collect()`` and ``torch.cuda.empty_cache()`` on entry, which hands every cached block back to the driver:
+    measured 0.11 s per capture on a B200 holding the feature maps of a 96-frame batch (four captures per batch: 12 % of the batch time),
+    plus the re-allocation cost afterwards."""
+    g = torch.cuda.CUDAGraph()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        g.capture_begin()
+        try:
+            enqueue()
+        finally:
+            g.capture_end()
+    torch.cuda.current_stream().wait_stream(side)
+    return g
+
+
 class _GraphLoop:
     """Shared plumbing: control block, history, schedule table, graph capture with state save / restore, asynchronous early-stop polling."""
 
@@ -80,9 +98,7 @@ class _GraphLoop:
         keep = [t.clone() for t in self._mutable_state()]
         enqueue()
         torch.cuda.current_stream().synchronize()
-        g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
-            enqueue()
+        g = capture_graph(enqueue)
         with torch.no_grad():
             for t, k in zip(self._mutable_state(), keep):
                 t.copy_(k)
