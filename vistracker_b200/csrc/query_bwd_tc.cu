@@ -47,6 +47,14 @@ struct TbParams {
   const float* w_df_ptr; const float* w_ce_ptr; float w_df_mul, w_ce_mul;
 };
 
+// per head slot of a pair: last-layer weights, the three biases and the ReLU masks of the three hidden layers (128 bits per point)
+struct TbHeadTab {
+  float w4[TQ_H * 16 + 16];
+  float bias[3][TQ_H];
+  uint32_t mask[3][4][TQ_M];
+};
+static_assert(sizeof(TbHeadTab) % 16 == 0 && 2 * sizeof(TbHeadTab) <= TQ_SLOT, "two head tables share one 32 KB slot");
+
 // tcgen05.mma with the A operand in tensor memory (fp16 pairs packed K-contiguous: element k of row m at lane m, column k / 2, half k & 1)
 __device__ __forceinline__ void tb_mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t accumulate) {
   asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
@@ -97,7 +105,7 @@ query_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_c
                     int B, int N, TqMaps m, TqCam cam, const float* __restrict__ wpack, int wpack_head_stride, TbParams prm,
                     int* __restrict__ overflow) {
   extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t feat_full[2], feat_empty[2], w_full[4], w_empty[4], f1_done, acc_full, act_full, gf_full[TB_NGF],
+  __shared__ __align__(8) uint64_t feat_full[2], feat_empty[2], w_full[4], w_empty[4], f1_done, acc_full[2], act_full[2], gf_full[TB_NGF],
       gf_empty[TB_NGF], stg_full[2], stg_empty[2];
   __shared__ uint32_t s_tmem_base;
   __shared__ TqTapTable s_tap;
@@ -107,17 +115,16 @@ query_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_c
   __shared__ float s_wloss[2];                              // merged heads: the two loss weights (device scalar x host factor)
   __shared__ unsigned char s_label[TQ_M];                   // mode 2: part label of every point (14 classes)
   __shared__ float s_dfc[TQ_M];                             // clamp(df, max=threshold) (projection step)
-  __shared__ uint32_t s_mask[3][4][TQ_M];                   // ReLU masks of the three hidden layers of the current head (128 bits per point)
   __shared__ float s_gp[TQ_M][2];                           // current head, before the per-point scale: d/d(u, v) of the perspective samples ...
   __shared__ float s_g3[TQ_M][3];                           // ... and d/d(x, y, z) through the three orthographic views and the direct inputs
-  __shared__ __align__(16) float s_w4[TQ_H * 16 + 16];
-  __shared__ __align__(16) float s_bias[3][TQ_H];           // b1, b2, b3 of the current head
 
   const uint32_t smem_base = (tq_smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_al = smem_raw + (smem_base - tq_smem_u32(smem_raw));
-  const uint32_t feat_base = smem_base, w_base = smem_base + 2 * TQ_SLOT, act_base = w_base + TQ_NW * TQ_SLOT;
+  const uint32_t feat_base = smem_base, w_base = smem_base + 2 * TQ_SLOT;
   uint8_t* feat_ptr = smem_al;                              // also the gf staging ring: slot = fp32 [128 points][64 features]
-  uint8_t* act_ptr = smem_al + 2 * TQ_SLOT + TQ_NW * TQ_SLOT;
+  // the former activation buffer (the A operands live in tensor memory now): 32 KB of mailboxes, then the tables of the two head slots
+  uint8_t* mail_ptr = smem_al + 2 * TQ_SLOT + TQ_NW * TQ_SLOT;
+  TbHeadTab* tab[2] = {reinterpret_cast<TbHeadTab*>(mail_ptr + TQ_SLOT), reinterpret_cast<TbHeadTab*>(mail_ptr + TQ_SLOT) + 1};
   // the warp index through a shuffle: the compiler then knows the role branches are warp-uniform (needed for straight-line UTCHMMA issue below)
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const int heads = prm.mode == 1 ? 1 : prm.mode == 2 ? ((prm.labels ? 5 : 1) | prm.fwd_mask) : prm.head_mask;
@@ -129,11 +136,17 @@ query_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_c
   // a head's chain stages may borrow the idle feature ring for their weight tiles when no backward gather (which stages through that
   // ring) runs between the pair's forward gather and this chain: always for the first head of a pair, for the second when the heads are
   // merged or the first was forward-only
+  // tensor-memory regions (128 columns each): head slot pj accumulates in region pj, its activations live in region 2 + pj.  The feature
+  // gradients gf of a head go through a ring of the two regions that are dead by then: merged pair: both accumulators; otherwise the
+  // head's own accumulator and the OTHER slot's activation region
+  auto gf_region = [&](int pj, int gs) { return merge ? gs : (gs == 0 ? pj : 2 + (pj ^ 1)); };
   auto chain_wide = [&](int pi, int pj) {
     if (pj == 0 || merge) return true;
     const int hA = 2 * pi < n_heads ? (int)__fns((unsigned)heads, 0, 2 * pi + 1) : -1;
     return hA >= 0 && prm.mode == 2 && ((prm.fwd_mask >> hA) & 1) != 0;
   };
+  // merged pair: the chains of the two heads run interleaved, stage by stage (each head has its own accumulator and activation regions)
+  const bool interleave = merge;
   auto pair_head = [&](int pi, int j) { return 2 * pi + j < n_heads ? (int)__fns((unsigned)heads, 0, 2 * pi + j + 1) : -1; };
 
   if (warp == 4 && lane == 0) {
@@ -161,8 +174,7 @@ query_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_c
     for (int s = 0; s < 4; ++s) { tq_mbar_init(tq_smem_u32(&w_full[s]), 1); tq_mbar_init(tq_smem_u32(&w_empty[s]), 1); }
     tq_mbar_init(tq_smem_u32(&f1_done), 1);
     for (int s = 0; s < TB_NGF; ++s) { tq_mbar_init(tq_smem_u32(&gf_full[s]), 1); tq_mbar_init(tq_smem_u32(&gf_empty[s]), 4); }
-    tq_mbar_init(tq_smem_u32(&acc_full), 1);
-    tq_mbar_init(tq_smem_u32(&act_full), 8);
+    for (int s = 0; s < 2; ++s) { tq_mbar_init(tq_smem_u32(&acc_full[s]), 1); tq_mbar_init(tq_smem_u32(&act_full[s]), 8); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   // projections of the tile's points (gather warps, one thread per point) -- same arithmetic as query_fwd_tc_kernel
@@ -193,72 +205,79 @@ query_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_c
   tq_fence_after();
   const uint32_t tmem_base = s_tmem_base;
 
-  // ================================================================== the decoder chain of one head (epilogue side), thread = point row =
-  // TMEM lane, split by COLUMN HALVES between two warps per lane quadrant: the epilogue warp q (hf = 0: hidden units 0-63) and gather
-  // warp 6 + ((q + 2) & 3), which has nothing to gather while the chain runs and whose warp id gives it the same TMEM lane quadrant
-  // (hf = 1: hidden units 64-127).  What the two threads of a row must share -- the partial head outputs, the cotangent, the row maximum of
-  // each backward stage -- goes through a 128-byte mailbox in the activation buffer: each thread owns the row's line of the K chunk it
-  // writes itself (slot hf), the partner posts into that line and the owner reads it before its own store overwrites it; a 64-thread named
-  // barrier per quadrant orders post and read.
-  // Every stage walks its 64 columns in ROLLED loops over groups of 8 (tcgen05.ld.x8): each stage runs once per tile and head, so fully
-  // unrolled 32-column bodies (the previous form) executed ~6 k instructions of cold straight-line code per head -- the second pass over
-  // the same code ran twice as fast as the first (instruction fetch, not arithmetic, set the stage time).
+  // ================================================================== the decoder chain of a head, ONE STAGE per call (epilogue side):
+  // thread = point row = TMEM lane, split by COLUMN HALVES between two warps per lane quadrant -- the epilogue warp q (hf = 0: hidden units
+  // 0-63) and gather warp 6 + ((q + 2) & 3), idle while the chain runs and in the same TMEM lane quadrant (hf = 1: units 64-127).
+  //
+  // Tensor memory (four regions of 128 columns): head slot pj of a pair accumulates in region pj and keeps its ACTIVATIONS in region 2 + pj as
+  // the A operand of the next tcgen05.mma (packed fp16 pairs, per 32-element K chunk 16 columns of hi | 16 of lo).  An MMA with A in tensor
+  // memory reads only the weight tile through the shared-memory port -- with A in shared memory the 128x128x16 MMAs of these stages ran at
+  // 75 cycles each against 32 of tensor-pipe time (4 KB of A + 4 KB of B per MMA at 128 B/clk) -- and, with one A region per head, the chains
+  // of the two heads of a merged pair are INTERLEAVED stage by stage: while the tensor pipe works on head A's stage the epilogue warps run
+  // head B's, so the MMA + barrier round trip (~40 % of a stage) is hidden instead of waited for twelve times per tile.
+  //   stage 0 / 1: layers 1 / 2: bias + ReLU (mask kept), activation -> X          stage 2: layer 3 + head outputs + cotangent, g3 -> X
+  //   stage 3 / 4: backward through layers 3 / 2: row renormalisation, mask, -> X (stage 4 leaves g1, the A operand of the B1 product)
+  // What the two threads of a row share (partial head outputs, cotangent, row maxima) goes through 64-byte mailboxes, double-buffered by
+  // exchange parity (a writer may be one exchange ahead of its reader), ordered by a 64-thread named barrier per quadrant.
   int tr = 0;
   const bool tracing = prm.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0;
 #define TB_STAMP() do { if (tracing && tr < 64) prm.trace[tr++] = clock64(); } while (0)
-  auto chain_head = [&](const int hi, const int hf, int& iacc, float& amax) {
-    const int q = warp & 3, r = q * 32 + lane, n = n0 + r;
-    const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
-    const int h = (int)__fns((unsigned)heads, 0, hi + 1), pj = hi & 1;          // pj: which accumulator of the pair
-    const uint32_t acc_base = lane_base + pj * TQ_H;
-    uint8_t* act_mine = act_ptr + hf * TQ_SLOT;            // K chunk hf of the A operand = columns 64 hf .. 64 hf + 63
-    float* mail_in = reinterpret_cast<float*>(act_mine + (r >> 3) * 1024 + (r & 7) * 128);
-    float* mail_out = reinterpret_cast<float*>(act_ptr + (hf ^ 1) * TQ_SLOT + (r >> 3) * 1024 + (r & 7) * 128);
-    auto pair_sync = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(4 + q) : "memory"); };
-    // 8 values (columns 64 hf + 8 g .. + 7 of a 128-wide layer) of this point into the next MMA's A operand: one 16-byte unit per plane
-    auto store_act8 = [&](const float (&v)[8], int g) {
-      uint4 hh, ll;
-      tq_split2(v[0], v[1], hh.x, ll.x, amax); tq_split2(v[2], v[3], hh.y, ll.y, amax);
-      tq_split2(v[4], v[5], hh.z, ll.z, amax); tq_split2(v[6], v[7], hh.w, ll.w, amax);
-      const uint32_t off = tq_sw_off(r, g * 8);
-      *reinterpret_cast<uint4*>(act_mine + off) = hh;
-      *reinterpret_cast<uint4*>(act_mine + TQ_PLANE + off) = ll;
-    };
-    auto publish_act = [&]() {
-      tq_fence_before();                                   // TMEM reads of the accumulator are done before the MMA overwrites it
-      tq_fence_async();
-      __syncwarp();
-      if (lane == 0) tq_mbar_arrive(tq_smem_u32(&act_full));
-    };
-    const float* hw = wpack + (size_t)h * wpack_head_stride;
-    const float* b1 = hw + 616 * 128;
-    const float* b2 = b1 + 128 + 128 * 128;
-    const float* b3 = b2 + 128 + 128 * 128;
-    const float* W4 = b3 + 128;
-    asm volatile("bar.sync 2, 256;" ::: "memory");        // the previous head has finished reading s_w4
-    if (hf == 0) {
-      for (int i = threadIdx.x; i < (TQ_H * 16 + 16) / 4; i += 128)
-        reinterpret_cast<float4*>(s_w4)[i] = __ldg(reinterpret_cast<const float4*>(W4) + i);
-      if (threadIdx.x < 96) {
-        const int l = threadIdx.x >> 5, qq = threadIdx.x & 31;
-        reinterpret_cast<float4*>(s_bias[l])[qq] = __ldg(reinterpret_cast<const float4*>(l == 0 ? b1 : l == 1 ? b2 : b3) + qq);
+  struct HeadState { int iacc; int e_total; };
+  // stage tables of the two head slots of a pair, filled by the epilogue warps before stage 0 (load_tables)
+  auto load_tables = [&](int pi) {
+    asm volatile("bar.sync 2, 256;" ::: "memory");        // the previous pair has finished reading the tables
+    if (warp < 4) {
+      for (int pj = 0; pj < 2; ++pj) {
+        const int h = pair_head(pi, pj);
+        if (h < 0) break;
+        const float* hw = wpack + (size_t)h * wpack_head_stride;
+        const float* b1 = hw + 616 * 128;
+        const float* b2 = b1 + 128 + 128 * 128;
+        const float* b3 = b2 + 128 + 128 * 128;
+        const float* W4 = b3 + 128;
+        for (int i = threadIdx.x; i < (TQ_H * 16 + 16) / 4; i += 128)
+          reinterpret_cast<float4*>(tab[pj]->w4)[i] = __ldg(reinterpret_cast<const float4*>(W4) + i);
+        if (threadIdx.x < 96) {
+          const int l = threadIdx.x >> 5, qq = threadIdx.x & 31;
+          reinterpret_cast<float4*>(tab[pj]->bias[l])[qq] = __ldg(reinterpret_cast<const float4*>(l == 0 ? b1 : l == 1 ? b2 : b3) + qq);
+        }
       }
     }
     asm volatile("bar.sync 2, 256;" ::: "memory");
-    float o[16];                                            // this thread's share of the head outputs (14 used)
-#pragma unroll
-    for (int c = 0; c < 16; ++c) o[c] = 0.f;
-    const bool narrow = h == 0 || h == 3 || h == 4;         // <= 4 outputs: W4 columns 4..15 are zero padding
+  };
+  int xchg = 0;                                           // exchanges done by this thread (mailbox parity); same sequence in both halves
+  auto stage = [&](const int h, const int pj, const int hf, const int st, HeadState& hs, float& amax) -> bool {
+    const int q = warp & 3, r = q * 32 + lane, n = n0 + r;
+    const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
+    const uint32_t acc_base = lane_base + pj * TQ_H, x_base = lane_base + (2 + pj) * TQ_H;
+    TbHeadTab& T = *tab[pj];
     const int col0 = 64 * hf;
-    // ---- forward epilogues E1, E2, E3 (ReLU masks -> s_mask)
-#pragma unroll 1
-    for (int layer = 0; layer < 3; ++layer) {
-      if (!(layer == 0 && pj == 1)) {            // the second head's first layer was completed together with the first head's
-        tq_mbar_wait(tq_smem_u32(&acc_full), (uint32_t)iacc & 1u); ++iacc;
-      }
+    const bool narrow = h == 0 || h == 3 || h == 4;         // <= 4 outputs: W4 columns 4..15 are zero padding
+    auto mail = [&](int side) { return reinterpret_cast<float*>(mail_ptr + (((xchg & 1) * TQ_M + r) * 2 + side) * 64); };
+    auto pair_sync = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(4 + q) : "memory"); ++xchg; };
+    // 8 values (hidden units 64 hf + 8 g .. + 7 of this point) into the A-operand region: 4 columns of hi pairs, 4 of lo pairs
+    auto store_x8 = [&](const float (&v)[8], int g) {
+      uint32_t hi4[4], lo4[4];
+      tq_split2(v[0], v[1], hi4[0], lo4[0], amax); tq_split2(v[2], v[3], hi4[1], lo4[1], amax);
+      tq_split2(v[4], v[5], hi4[2], lo4[2], amax); tq_split2(v[6], v[7], hi4[3], lo4[3], amax);
+      const uint32_t at = x_base + col0 + (g >> 2) * 32 + (g & 3) * 4;
+      tb_st4(at, hi4);
+      tb_st4(at + 16, lo4);
+    };
+    auto publish = [&]() {
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      tq_fence_before();                                   // this warp's TMEM reads / writes are done before the MMA it releases
+      __syncwarp();
+      if (lane == 0) tq_mbar_arrive(tq_smem_u32(&act_full[pj]));
+    };
+    auto wait_acc = [&]() {
+      tq_mbar_wait(tq_smem_u32(&acc_full[pj]), (uint32_t)hs.iacc & 1u); ++hs.iacc;
       tq_fence_after();
-      TB_STAMP();
-      const float* bias = s_bias[layer] + col0;
+    };
+    if (st < 2) {
+      // ---- forward epilogues E1, E2: bias, ReLU (mask kept), activation -> X
+      wait_acc();
+      const float* bias = T.bias[st] + col0;
       uint32_t mword = 0;
 #pragma unroll 1
       for (int g = 0; g < 8; ++g) {
@@ -270,19 +289,42 @@ query_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_c
 #pragma unroll
         for (int i = 0; i < 8; ++i) { mk |= (v[i] > 0.f ? 1u : 0u) << i; v[i] = fmaxf(v[i], 0.f); }
         mword |= mk << ((g & 3) * 8);
-        if ((g & 3) == 3) { s_mask[layer][2 * hf + (g >> 2)][r] = mword; mword = 0; }
-        if (layer < 2) {
-          store_act8(v, g);
-        } else if (narrow) {                   // heads with <= 4 outputs (df, centers, visibility): one 16-byte weight load per unit
+        if ((g & 3) == 3) { T.mask[st][2 * hf + (g >> 2)][r] = mword; mword = 0; }
+        store_x8(v, g);
+      }
+      publish();
+      TB_STAMP();
+      return true;
+    }
+    if (st == 2) {
+      // ---- E3: layer 3 -> head outputs on the CUDA cores (this half's share), cotangent, g3 -> X
+      wait_acc();
+      float o[16];
+#pragma unroll
+      for (int c = 0; c < 16; ++c) o[c] = 0.f;
+      const float* bias = T.bias[2] + col0;
+      uint32_t mword = 0;
+#pragma unroll 1
+      for (int g = 0; g < 8; ++g) {
+        float v[8];
+        tq_ld8(acc_base + col0 + g * 8, v);
+        const float4 ba = *reinterpret_cast<const float4*>(bias + g * 8), bb = *reinterpret_cast<const float4*>(bias + g * 8 + 4);
+        v[0] += ba.x; v[1] += ba.y; v[2] += ba.z; v[3] += ba.w; v[4] += bb.x; v[5] += bb.y; v[6] += bb.z; v[7] += bb.w;
+        uint32_t mk = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { mk |= (v[i] > 0.f ? 1u : 0u) << i; v[i] = fmaxf(v[i], 0.f); }
+        mword |= mk << ((g & 3) * 8);
+        if ((g & 3) == 3) { T.mask[2][2 * hf + (g >> 2)][r] = mword; mword = 0; }
+        if (narrow) {                          // heads with <= 4 outputs (df, centers, visibility): one 16-byte weight load per unit
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            const float4 w0 = *reinterpret_cast<const float4*>(s_w4 + (col0 + g * 8 + i) * 16);
+            const float4 w0 = *reinterpret_cast<const float4*>(T.w4 + (col0 + g * 8 + i) * 16);
             o[0] = fmaf(v[i], w0.x, o[0]); o[1] = fmaf(v[i], w0.y, o[1]); o[2] = fmaf(v[i], w0.z, o[2]); o[3] = fmaf(v[i], w0.w, o[3]);
           }
         } else {
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            const float4* wr = reinterpret_cast<const float4*>(s_w4 + (col0 + g * 8 + i) * 16);
+            const float4* wr = reinterpret_cast<const float4*>(T.w4 + (col0 + g * 8 + i) * 16);
             const float4 w0 = wr[0], w1 = wr[1], w2 = wr[2], w3 = wr[3];
             o[0] = fmaf(v[i], w0.x, o[0]); o[1] = fmaf(v[i], w0.y, o[1]); o[2] = fmaf(v[i], w0.z, o[2]); o[3] = fmaf(v[i], w0.w, o[3]);
             o[4] = fmaf(v[i], w1.x, o[4]); o[5] = fmaf(v[i], w1.y, o[5]); o[6] = fmaf(v[i], w1.z, o[6]); o[7] = fmaf(v[i], w1.w, o[7]);
@@ -291,220 +333,212 @@ query_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_c
           }
         }
       }
-      if (layer < 2) publish_act();
-      TB_STAMP();
-    }
-    // ---- the head outputs: the upper half posts its partial sums, the lower half owns the result
-    if (hf) {
+      // the upper half posts its partial sums, the lower half owns the head outputs
+      if (hf) {
+        float* mo = mail(0);
 #pragma unroll
-      for (int c = 0; c < 16; c += 4) *reinterpret_cast<float4*>(mail_out + c) = make_float4(o[c], o[c + 1], o[c + 2], o[c + 3]);
-    }
-    pair_sync();
-    if (!hf) {
-#pragma unroll
-      for (int c = 0; c < 16; c += 4) {
-        const float4 t = *reinterpret_cast<const float4*>(mail_in + c);
-        o[c] += t.x; o[c + 1] += t.y; o[c + 2] += t.z; o[c + 3] += t.w;
+        for (int c = 0; c < 16; c += 4) *reinterpret_cast<float4*>(mo + c) = make_float4(o[c], o[c + 1], o[c + 2], o[c + 3]);
       }
-    }
-    const int nout = h == 0 ? 2 : h == 1 ? 9 : h == 2 ? 14 : h == 3 ? 3 : 1;
-    const int hoff = h == 0 ? 0 : h == 1 ? 2 : h == 2 ? 11 : h == 3 ? 25 : 28;
-    if (fwd_only(h)) {                         // predictions only: write them, hand the accumulator back, next head
-      if (!hf && n < N) {
+      {
+        float* mi = mail(0);
+        pair_sync();
+        if (!hf) {
+#pragma unroll
+          for (int c = 0; c < 16; c += 4) {
+            const float4 t = *reinterpret_cast<const float4*>(mi + c);
+            o[c] += t.x; o[c + 1] += t.y; o[c + 2] += t.z; o[c + 3] += t.w;
+          }
+        }
+      }
+      const int nout = h == 0 ? 2 : h == 1 ? 9 : h == 2 ? 14 : h == 3 ? 3 : 1;
+      const int hoff = h == 0 ? 0 : h == 1 ? 2 : h == 2 ? 11 : h == 3 ? 25 : 28;
+      if (fwd_only(h)) {                       // predictions only: write them, hand the accumulator back
+        if (!hf && n < N) {
+#pragma unroll
+          for (int c = 0; c < 14; ++c) {
+            if (c >= nout) break;
+            float val = o[c] + T.w4[TQ_H * 16 + c];
+            if (h == 4) val = 1.f / (1.f + expf(-val));
+            if (h == 0 && !s_in_img[r]) val = cam.out_dist;
+            prm.out_fwd[((size_t)b * 29 + hoff + c) * N + n] = val;
+          }
+        }
+        publish();
+        return false;
+      }
+      // cotangent at the head outputs, normalised per point (lower half; posted to the upper half)
+      float g4[16];
+      if (!hf) {
+        float gmax = 0.f;
 #pragma unroll
         for (int c = 0; c < 14; ++c) {
-          if (c >= nout) break;
-          float val = o[c] + s_w4[TQ_H * 16 + c];
-          if (h == 4) val = 1.f / (1.f + expf(-val));
-          if (h == 0 && !s_in_img[r]) val = cam.out_dist;
-          prm.out_fwd[((size_t)b * 29 + hoff + c) * N + n] = val;
-        }
-      }
-      publish_act();
-      return;
-    }
-    // ---- cotangent at the head outputs, normalised per point (lower half; posted to the upper half)
-    float g4[16];
-    int e_total = 0;
-    if (!hf) {
-      float gmax = 0.f;
-#pragma unroll
-      for (int c = 0; c < 14; ++c) {
-        float g = 0.f;
-        if (c < nout && n < N) {
-          float val = o[c] + s_w4[TQ_H * 16 + c];
-          if (h == 4) val = 1.f / (1.f + expf(-val));
-          if (h == 0 && !s_in_img[r]) val = cam.out_dist;
-          if (prm.mode == 0) {
-            g = prm.g_out[((size_t)b * 29 + hoff + c) * N + n];
-            if (h == 4) g *= val * (1.f - val);
-          } else if (h == 0 && c == prm.df_idx) {
-            g = val <= prm.threshold ? 1.f : 0.f;
-            s_dfc[r] = fminf(val, prm.threshold);
-            if (prm.mode == 2) prm.vals_df[(size_t)b * N + n] = fminf(val, prm.threshold);
-          } else if (h == 2) {
-            g = val;                                       // mode 2: keep the logit, turned into softmax - onehot below
+          float g = 0.f;
+          if (c < nout && n < N) {
+            float val = o[c] + T.w4[TQ_H * 16 + c];
+            if (h == 4) val = 1.f / (1.f + expf(-val));
+            if (h == 0 && !s_in_img[r]) val = cam.out_dist;
+            if (prm.mode == 0) {
+              g = prm.g_out[((size_t)b * 29 + hoff + c) * N + n];
+              if (h == 4) g *= val * (1.f - val);
+            } else if (h == 0 && c == prm.df_idx) {
+              g = val <= prm.threshold ? 1.f : 0.f;
+              s_dfc[r] = fminf(val, prm.threshold);
+              if (prm.mode == 2) prm.vals_df[(size_t)b * N + n] = fminf(val, prm.threshold);
+            } else if (h == 2) {
+              g = val;                                     // mode 2: keep the logit, turned into softmax - onehot below
+            }
+            if (h == 0 && !s_in_img[r]) g = 0.f;
           }
-          if (h == 0 && !s_in_img[r]) g = 0.f;
+          g4[c] = g;
+          gmax = fmaxf(gmax, fabsf(g));
         }
-        g4[c] = g;
-        gmax = fmaxf(gmax, fabsf(g));
+        g4[14] = 0.f; g4[15] = 0.f;
+        if (merge && h == 0) {
+          const float wdf = s_wloss[0];
+#pragma unroll
+          for (int c = 0; c < 2; ++c) g4[c] *= wdf;
+          gmax *= fabsf(wdf);
+        }
+        if (prm.mode == 2 && h == 2) {                     // F.cross_entropy(parts, labels, reduction='none') and its logit gradient
+          gmax = 0.f;
+          if (n < N) {
+            const int lab = s_label[r];
+            float mx = g4[0];
+#pragma unroll
+            for (int c = 1; c < 14; ++c) mx = fmaxf(mx, g4[c]);
+            float sum = 0.f, l_lab = 0.f;
+#pragma unroll
+            for (int c = 0; c < 14; ++c) { if (c == lab) l_lab = g4[c]; g4[c] = __expf(g4[c] - mx); sum += g4[c]; }
+            prm.vals_ce[(size_t)b * N + n] = logf(sum) - (l_lab - mx);
+            const float inv_sum = 1.f / sum;
+            const float wce = merge ? s_wloss[1] : 1.f;
+#pragma unroll
+            for (int c = 0; c < 14; ++c) { g4[c] = (g4[c] * inv_sum - (c == lab ? 1.f : 0.f)) * wce; gmax = fmaxf(gmax, fabsf(g4[c])); }
+          } else {
+#pragma unroll
+            for (int c = 0; c < 14; ++c) g4[c] = 0.f;
+          }
+        }
+        hs.e_total = tb_norm_exp(gmax);
+        const float inv = tb_pow2(-hs.e_total);
+#pragma unroll
+        for (int c = 0; c < 14; ++c) g4[c] *= inv;
+        g4[15] = __int_as_float(hs.e_total);
+        float* mo = mail(1);
+#pragma unroll
+        for (int c = 0; c < 16; c += 4) *reinterpret_cast<float4*>(mo + c) = make_float4(g4[c], g4[c + 1], g4[c + 2], g4[c + 3]);
       }
-      g4[14] = 0.f; g4[15] = 0.f;
-      if (merge && h == 0) {
-        const float wdf = s_wloss[0];
+      {
+        float* mi = mail(1);
+        pair_sync();
+        if (hf) {
 #pragma unroll
-        for (int c = 0; c < 2; ++c) g4[c] *= wdf;
-        gmax *= fabsf(wdf);
+          for (int c = 0; c < 16; c += 4) {
+            const float4 t = *reinterpret_cast<const float4*>(mi + c);
+            g4[c] = t.x; g4[c + 1] = t.y; g4[c + 2] = t.z; g4[c + 3] = t.w;
+          }
+          hs.e_total = __float_as_int(g4[15]);
+        }
       }
-      if (prm.mode == 2 && h == 2) {                       // F.cross_entropy(parts, labels, reduction='none') and its logit gradient
-        gmax = 0.f;
-        if (n < N) {
-          const int lab = s_label[r];
-          float mx = g4[0];
+      // g3 = relu'(h3) . (W4^T g4): 128 x <= 14 on the CUDA cores, straight into the A operand of B3
+#pragma unroll 1
+      for (int g = 0; g < 8; ++g) {
+        float v[8];
+        const uint32_t mk = T.mask[2][2 * hf + (g >> 2)][r] >> ((g & 3) * 8);
+        if (narrow) {
 #pragma unroll
-          for (int c = 1; c < 14; ++c) mx = fmaxf(mx, g4[c]);
-          float sum = 0.f, l_lab = 0.f;
-#pragma unroll
-          for (int c = 0; c < 14; ++c) { if (c == lab) l_lab = g4[c]; g4[c] = __expf(g4[c] - mx); sum += g4[c]; }
-          prm.vals_ce[(size_t)b * N + n] = logf(sum) - (l_lab - mx);
-          const float inv_sum = 1.f / sum;
-          const float wce = merge ? s_wloss[1] : 1.f;
-#pragma unroll
-          for (int c = 0; c < 14; ++c) { g4[c] = (g4[c] * inv_sum - (c == lab ? 1.f : 0.f)) * wce; gmax = fmaxf(gmax, fabsf(g4[c])); }
+          for (int i = 0; i < 8; ++i) {
+            const float4 w0 = *reinterpret_cast<const float4*>(T.w4 + (col0 + g * 8 + i) * 16);
+            float a = g4[0] * w0.x;
+            a = fmaf(g4[1], w0.y, a); a = fmaf(g4[2], w0.z, a); a = fmaf(g4[3], w0.w, a);
+            v[i] = ((mk >> i) & 1u) ? a : 0.f;
+          }
         } else {
 #pragma unroll
-          for (int c = 0; c < 14; ++c) g4[c] = 0.f;
+          for (int i = 0; i < 8; ++i) {
+            const float4* wr = reinterpret_cast<const float4*>(T.w4 + (col0 + g * 8 + i) * 16);
+            const float4 w0 = wr[0], w1 = wr[1], w2 = wr[2], w3 = wr[3];
+            float a = g4[0] * w0.x;
+            a = fmaf(g4[1], w0.y, a); a = fmaf(g4[2], w0.z, a); a = fmaf(g4[3], w0.w, a);
+            a = fmaf(g4[4], w1.x, a); a = fmaf(g4[5], w1.y, a); a = fmaf(g4[6], w1.z, a); a = fmaf(g4[7], w1.w, a);
+            a = fmaf(g4[8], w2.x, a); a = fmaf(g4[9], w2.y, a); a = fmaf(g4[10], w2.z, a); a = fmaf(g4[11], w2.w, a);
+            a = fmaf(g4[12], w3.x, a); a = fmaf(g4[13], w3.y, a);
+            v[i] = ((mk >> i) & 1u) ? a : 0.f;
+          }
         }
+        store_x8(v, g);
       }
-      e_total = tb_norm_exp(gmax);
-      const float inv = tb_pow2(-e_total);
-#pragma unroll
-      for (int c = 0; c < 14; ++c) g4[c] *= inv;
-      g4[15] = __int_as_float(e_total);
-#pragma unroll
-      for (int c = 0; c < 16; c += 4) *reinterpret_cast<float4*>(mail_out + c) = make_float4(g4[c], g4[c + 1], g4[c + 2], g4[c + 3]);
+      publish();
+      TB_STAMP();
+      return true;
     }
-    pair_sync();
-    if (hf) {
-#pragma unroll
-      for (int c = 0; c < 16; c += 4) {
-        const float4 t = *reinterpret_cast<const float4*>(mail_in + c);
-        g4[c] = t.x; g4[c + 1] = t.y; g4[c + 2] = t.z; g4[c + 3] = t.w;
-      }
-      e_total = __float_as_int(g4[15]);
-    }
-    // g3 = relu'(h3) . (W4^T g4): 128 x <=14 on the CUDA cores, straight into the A operand of B3
+    // ---- backward epilogues EB3 (st 3: mask of layer 2), EB2 (st 4: mask of layer 1): renormalise by the ROW maximum (both halves), mask, split
+    const int bl = 4 - st;
+    wait_acc();
+    float vmax = 0.f;
 #pragma unroll 1
     for (int g = 0; g < 8; ++g) {
       float v[8];
-      const uint32_t mk = s_mask[2][2 * hf + (g >> 2)][r] >> ((g & 3) * 8);
-      if (narrow) {
+      tq_ld8(acc_base + col0 + g * 8, v);
+      const uint32_t mk = T.mask[bl][2 * hf + (g >> 2)][r] >> ((g & 3) * 8);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float4 w0 = *reinterpret_cast<const float4*>(s_w4 + (col0 + g * 8 + i) * 16);
-          float a = g4[0] * w0.x;
-          a = fmaf(g4[1], w0.y, a); a = fmaf(g4[2], w0.z, a); a = fmaf(g4[3], w0.w, a);
-          v[i] = ((mk >> i) & 1u) ? a : 0.f;
-        }
-      } else {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float4* wr = reinterpret_cast<const float4*>(s_w4 + (col0 + g * 8 + i) * 16);
-          const float4 w0 = wr[0], w1 = wr[1], w2 = wr[2], w3 = wr[3];
-          float a = g4[0] * w0.x;
-          a = fmaf(g4[1], w0.y, a); a = fmaf(g4[2], w0.z, a); a = fmaf(g4[3], w0.w, a);
-          a = fmaf(g4[4], w1.x, a); a = fmaf(g4[5], w1.y, a); a = fmaf(g4[6], w1.z, a); a = fmaf(g4[7], w1.w, a);
-          a = fmaf(g4[8], w2.x, a); a = fmaf(g4[9], w2.y, a); a = fmaf(g4[10], w2.z, a); a = fmaf(g4[11], w2.w, a);
-          a = fmaf(g4[12], w3.x, a); a = fmaf(g4[13], w3.y, a);
-          v[i] = ((mk >> i) & 1u) ? a : 0.f;
-        }
-      }
-      store_act8(v, g);
+      for (int i = 0; i < 8; ++i)
+        if ((mk >> i) & 1u) vmax = fmaxf(vmax, fabsf(v[i]));
     }
-    publish_act();
-    TB_STAMP();
-    // ---- backward epilogues EB3 (mask of layer 2), EB2 (mask of layer 1): renormalise by the ROW maximum (both halves), mask, split
-#pragma unroll 1
-    for (int bl = 1; bl >= 0; --bl) {
-      tq_mbar_wait(tq_smem_u32(&acc_full), (uint32_t)iacc & 1u); ++iacc;
-      tq_fence_after();
-      float vmax = 0.f;
-#pragma unroll 1
-      for (int g = 0; g < 8; ++g) {
-        float v[8];
-        tq_ld8(acc_base + col0 + g * 8, v);
-        const uint32_t mk = s_mask[bl][2 * hf + (g >> 2)][r] >> ((g & 3) * 8);
-#pragma unroll
-        for (int i = 0; i < 8; ++i)
-          if ((mk >> i) & 1u) vmax = fmaxf(vmax, fabsf(v[i]));
-      }
-      const int e_first = s_scale_e[r];                    // merged heads, second head: the first head's exponent (read before the lower half replaces it)
-      mail_out[0] = vmax;
+    // merged pair, second head: the first head's exponent.  The lower half wrote it (same thread, earlier stage) and hands it to the upper
+    // half with the row maximum, so that no read of s_scale_e crosses threads without a barrier
+    int e_first = hf ? 0 : s_scale_e[r];
+    {
+      float* mo = mail(hf ^ 1);
+      float* mi = mail(hf);
+      mo[0] = vmax;
+      if (!hf) mo[1] = __int_as_float(e_first);
       pair_sync();
-      vmax = fmaxf(vmax, mail_in[0]);
-      const int e = tb_norm_exp(vmax);
-      e_total += e;
-      if (merge && bl == 0) {
-        // g1 of this head stays in TENSOR MEMORY, written over its own accumulator columns (per 32-column chunk: 16 columns of packed hi
-        // pairs, 16 of lo pairs), as the A operand of the merged B1 product.  Both heads must share one per-point exponent E = max(e_A, e_B):
-        // the second head scales its own values on the way in and, if it raised E, rescales the first head's columns (powers of two: exact).
-        int E = e_total;
-        if (pj == 1) E = max(E, e_first);
-        const float inv = tb_pow2(-e + (e_total - E));
-        // (a chunk of 32 fp32 columns is replaced by its own packed form: read the whole chunk before the first store)
-#pragma unroll 1
-        for (int ch = 2 * hf; ch < 2 * hf + 2; ++ch) {
-          float v[32];
-          tq_ld32(acc_base + ch * 32, v);
-          const uint32_t mk = s_mask[bl][ch][r];
-          uint32_t hi16[16], lo16[16];
-#pragma unroll
-          for (int i = 0; i < 32; i += 2) {
-            const float a = ((mk >> i) & 1u) ? v[i] * inv : 0.f, c2 = ((mk >> (i + 1)) & 1u) ? v[i + 1] * inv : 0.f;
-            tq_split2(a, c2, hi16[i >> 1], lo16[i >> 1], amax);
-          }
-          tb_st16(acc_base + ch * 32, hi16);
-          tb_st16(acc_base + ch * 32 + 16, lo16);
-        }
-        // (tcgen05.ld / st are warp-collective: the branch must be warp-uniform, rows that need no rescale multiply by one)
-        const bool rescale = pj == 1 && e_first < E;
-        if (__any_sync(0xffffffffu, rescale)) {
-          const __half2 sc2 = __float2half2_rn(rescale ? tb_pow2(max(e_first - E, -30)) : 1.f);
-          const uint32_t other = lane_base + col0;        // the first head's accumulator columns, this thread's half
-#pragma unroll 1
-          for (int qq = 0; qq < 4; ++qq) {
-            uint32_t w[16];
-            tb_ld16(other + qq * 16, w);
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              const __half2 t = __hmul2(*reinterpret_cast<const __half2*>(&w[i]), sc2);
-              w[i] = *reinterpret_cast<const uint32_t*>(&t);
-            }
-            tb_st16(other + qq * 16, w);
-          }
-        }
-        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-        pair_sync();                                       // the upper half has read the first head's exponent
-        if (!hf) s_scale_e[r] = E;
-        publish_act();
-        TB_STAMP();
-        continue;
-      }
-      const float inv = tb_pow2(-e);
-#pragma unroll 1
-      for (int g = 0; g < 8; ++g) {
-        float v[8];
-        tq_ld8(acc_base + col0 + g * 8, v);
-        const uint32_t mk = s_mask[bl][2 * hf + (g >> 2)][r] >> ((g & 3) * 8);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) v[i] = ((mk >> i) & 1u) ? v[i] * inv : 0.f;
-        store_act8(v, g);
-      }
-      if (bl == 0 && !hf) s_scale_e[r] = e_total;          // read by the gather warps after the first staging chunk is published
-      publish_act();
-      TB_STAMP();
+      vmax = fmaxf(vmax, mi[0]);
+      if (hf) e_first = __float_as_int(mi[1]);
     }
+    const int e = tb_norm_exp(vmax);
+    hs.e_total += e;
+    // merged pair: both heads' g1 enter ONE product and need a common per-point exponent E = max(e_A, e_B): the second head scales its own
+    // values on the way in and, if it raised E, rescales the first head's g1 (powers of two on fp16 pairs: exact up to underflow)
+    int E = hs.e_total;
+    const bool last_merged = merge && bl == 0;
+    if (last_merged && pj == 1) E = max(E, e_first);
+    // the lower half publishes the exponent right after the row-maximum exchange: both halves have read the first head's value (e_first)
+    // before that barrier, and with interleaved chains the upper half may reach the second head's read with no further barrier in between
+    if (bl == 0 && !hf) s_scale_e[r] = E;                  // also read by the gather warps after the first staging chunk is published
+    const float inv = tb_pow2(-e + (hs.e_total - E));
+#pragma unroll 1
+    for (int g = 0; g < 8; ++g) {
+      float v[8];
+      tq_ld8(acc_base + col0 + g * 8, v);
+      const uint32_t mk = T.mask[bl][2 * hf + (g >> 2)][r] >> ((g & 3) * 8);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = ((mk >> i) & 1u) ? v[i] * inv : 0.f;
+      store_x8(v, g);
+    }
+    if (last_merged) {
+      // (tcgen05.ld / st are warp-collective: the branch must be warp-uniform, rows that need no rescale multiply by one)
+      const bool rescale = pj == 1 && e_first < E;
+      if (__any_sync(0xffffffffu, rescale)) {
+        const __half2 sc2 = __float2half2_rn(rescale ? tb_pow2(max(e_first - E, -30)) : 1.f);
+        const uint32_t other = lane_base + 2 * TQ_H + col0;       // the first head's g1, this thread's half
+#pragma unroll 1
+        for (int qq = 0; qq < 4; ++qq) {
+          uint32_t w[16];
+          tb_ld16(other + qq * 16, w);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const __half2 t = __hmul2(*reinterpret_cast<const __half2*>(&w[i]), sc2);
+            w[i] = *reinterpret_cast<const uint32_t*>(&t);
+          }
+          tb_st16(other + qq * 16, w);
+        }
+      }
+    }
+    publish();
+    TB_STAMP();
+    return true;
   };
 
   if (warp >= 6) {
@@ -519,7 +553,8 @@ query_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_c
     (&s_gp[gw * PW][0])[lane] = 0.f;
     float acc_x = 0.f, acc_y = 0.f, acc_z = 0.f;           // lanes 0-15: point gw * PW + lane, summed over heads (modes 0 and 1)
     __syncwarp();
-    int it = 0, sc = 0, iacc_h = 0;
+    int it = 0, sc = 0;
+    HeadState hs_h[2] = {{0, 0}, {0, 0}};                  // gather warps 0-3: upper column half of the chain stages
     float amax = 0.f;
     int trg = 64;
     const bool tracing_g = prm.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && gw == 0 && lane == 0;
@@ -572,10 +607,23 @@ query_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_c
         if (lane == 0) tq_mbar_arrive(tq_smem_u32(&feat_full[slot]));
       }
       TB_STAMP_G();
+      if (gw < 4) {
+        load_tables(pi);
+        if (interleave) {
+#pragma unroll 1
+          for (int st = 0; st < 5; ++st)
+#pragma unroll
+            for (int pj = 0; pj < 2; ++pj) stage(pair_head(pi, pj), pj, 1, st, hs_h[pj], amax);
+        }
+      }
       for (int pj = 0; pj < 2; ++pj) {
       const int h = pair_head(pi, pj);
       if (h < 0) break;
-      if (gw < 4) chain_head(2 * pi + pj, 1, iacc_h, amax);  // gather warps 0-3: the upper column half of this head's chain stages
+      if (gw < 4 && !interleave) {
+#pragma unroll 1
+        for (int st = 0; st < 5; ++st)
+          if (!stage(h, pj, 1, st, hs_h[pj], amax)) break;
+      }
       if (fwd_only(h)) continue;
       if (merge && pj == 0) continue;                       // merged heads: one staged feature-gradient tile, after the second head's chain
       // ---- backward: contract the staged feature gradients with d(feature)/d(u, v) (second gather of the same taps)
@@ -743,6 +791,20 @@ query_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_c
           load(&tm_w1_hi, &tm_w1_lo, c * TQ_KC, hA * TQ_H, false);
           if (hB >= 0) load(&tm_w1_hi, &tm_w1_lo, c * TQ_KC, hB * TQ_H, false);
         }
+        if (interleave) {                                   // merged pair: stage by stage, head A then head B (the issuer's order)
+          for (int st = 0; st < 4; ++st)
+            for (int pj = 0; pj < 2; ++pj) {
+              const int h = pj == 0 ? hA : hB, layer = st < 2 ? st : 3 - st;
+              for (int kc = 0; kc < 2; ++kc) {
+                if (st < 2) load(&tm_w23_hi, &tm_w23_lo, kc * TQ_KC, (layer * 5 + h) * TQ_H, true);
+                else load(&tm_w23t_hi, &tm_w23t_lo, kc * TQ_KC, (layer * 5 + h) * TQ_H, true);
+              }
+            }
+          for (int u = 0; u < TQ_NCHUNK / 2; ++u)                        // merged B1: per column group the W1^T tiles of both heads
+            for (int q = 0; q < 4; ++q)
+              load(&tm_w1t_hi, &tm_w1t_lo, (q & 1) * TQ_KC, (q < 2 ? hA : hB) * TQ_NCHUNK * TQ_KC + u * TQ_H, false);
+          continue;
+        }
         for (int pj = 0; pj < 2; ++pj) {
           const int h = pj == 0 ? hA : hB;
           if (h < 0) break;
@@ -752,13 +814,6 @@ query_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_c
           if (fwd_only(h)) continue;
           for (int layer = 1; layer >= 0; --layer)
             for (int kc = 0; kc < 2; ++kc) load(&tm_w23t_hi, &tm_w23t_lo, kc * TQ_KC, (layer * 5 + h) * TQ_H, wide);
-          if (merge) {
-            if (pj == 0) continue;
-            for (int u = 0; u < TQ_NCHUNK / 2; ++u)                      // merged B1: per column group the W1^T tiles of both heads
-              for (int q = 0; q < 4; ++q)
-                load(&tm_w1t_hi, &tm_w1t_lo, (q & 1) * TQ_KC, (q < 2 ? hA : hB) * TQ_NCHUNK * TQ_KC + u * TQ_H, false);
-            continue;
-          }
           for (int u = 0; u < TQ_NCHUNK / 2; ++u)
             for (int kc = 0; kc < 2; ++kc) load(&tm_w1t_hi, &tm_w1t_lo, kc * TQ_KC, h * TQ_NCHUNK * TQ_KC + u * TQ_H, false);
         }
@@ -769,7 +824,7 @@ query_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_c
     // barriers, ONE elected lane issues -- under `if (lane == 0)` the compiler wraps every tcgen05.mma in an ELECT / BRA.U.ANY loop over
     // the active lanes (~10 instructions and ~80 cycles per 32-cycle MMA: the issue thread, not the tensor pipe, set the stage times)
     {
-      int it = 0, iact = 0, gfi = 0, nsel = 0, wsel = 0;
+      int it = 0, iact[2] = {0, 0}, gfi = 0, nsel = 0, wsel = 0;
       uint32_t par = 0;
       int trm = 128;
       const bool tracing_m = prm.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && lane == 0;
@@ -799,6 +854,25 @@ query_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_c
         }
         __syncwarp();
       };
+      // K chunk kc (64 elements) of an A operand held in tensor memory (per 32-element chunk: 16 columns of hi pairs | 16 of lo pairs)
+      auto mma_tile_ts = [&](uint32_t x_region, int kc, uint32_t acc, bool first, bool wide) {
+        uint32_t waddr;
+        const int s = next_w(wide, waddr);
+        const uint64_t b_hi = tq_desc(waddr), b_lo = tq_desc(waddr + TQ_PLANE);
+        if (tq_elect_one()) {
+#pragma unroll
+          for (int kk = 0; kk < TQ_KC / 16; ++kk) {
+            const int kg = kc * TQ_KC + kk * 16;                       // K step of 16 elements = 8 columns
+            const uint32_t a_hi = x_region + (kg >> 5) * 32 + ((kg >> 4) & 1) * 8, a_lo = a_hi + 16;
+            const uint64_t adv = (uint64_t)(kk * 32 >> 4);
+            tb_mma_ts(acc, a_hi, b_hi + adv, (first && kk == 0) ? 0u : 1u);
+            tb_mma_ts(acc, a_hi, b_lo + adv, 1u);
+            tb_mma_ts(acc, a_lo, b_hi + adv, 1u);
+          }
+          tq_commit(tq_smem_u32(&w_empty[s]));
+        }
+        __syncwarp();
+      };
       auto commit = [&](uint64_t* bar) { if (tq_elect_one()) tq_commit(tq_smem_u32(bar)); __syncwarp(); };
       for (int pi = 0; pi < n_pairs; ++pi) {
         const bool two = pair_head(pi, 1) >= 0;
@@ -810,57 +884,45 @@ query_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_c
           if (two) mma_tile(feat_base + slot * TQ_SLOT, tmem_base + TQ_H, c == 0, false);
           commit(&feat_empty[slot]);
         }
-        commit(&acc_full);
+        commit(&acc_full[0]);
+        if (two) commit(&acc_full[1]);
         commit(&f1_done);                               // the feature ring is free: the weight producer may borrow it
+        // one chain stage of head slot pj (F2, F3, B3, B2): A = the head's activation region in tensor memory, D = its accumulator
+        auto stage_mma = [&](int pj, bool wide) {
+          tq_mbar_wait(tq_smem_u32(&act_full[pj]), (uint32_t)iact[pj] & 1u); ++iact[pj];
+          tq_fence_after();
+          TB_STAMP_M();
+          for (int kc = 0; kc < 2; ++kc) { mma_tile_ts(tmem_base + (2 + pj) * TQ_H, kc, tmem_base + pj * TQ_H, kc == 0, wide); TB_STAMP_M(); }
+          commit(&acc_full[pj]);
+        };
+        if (interleave) {
+          for (int st = 0; st < 4; ++st)
+            for (int pj = 0; pj < 2; ++pj) stage_mma(pj, true);
+          for (int pj = 0; pj < 2; ++pj) {                                // both heads' g1 are in their activation regions
+            tq_mbar_wait(tq_smem_u32(&act_full[pj]), (uint32_t)iact[pj] & 1u); ++iact[pj];
+          }
+          tq_fence_after();
+          for (int u = 0; u < TQ_NCHUNK / 2; ++u, ++gfi) {              // merged B1: gf = g1_A W1_A + g1_B W1_B into the (dead) accumulator regions
+            const int gs = gfi % TB_NGF;
+            tq_mbar_wait(tq_smem_u32(&gf_empty[gs]), ((uint32_t)(gfi / TB_NGF) & 1u) ^ 1u);
+            tq_fence_after();
+            for (int q = 0; q < 4; ++q) mma_tile_ts(tmem_base + (2 + (q >> 1)) * TQ_H, q & 1, tmem_base + gf_region(0, gs) * TQ_H, q == 0, false);
+            commit(&gf_full[gs]);
+          }
+          continue;
+        }
         for (int pj = 0; pj < (two ? 2 : 1); ++pj) {
-          const uint32_t acc = tmem_base + pj * TQ_H;
           const bool wide = chain_wide(pi, pj);
           const bool fo = fwd_only(pair_head(pi, pj));
-          for (int stage = 0; stage < (fo ? 2 : 4); ++stage) {          // F2, F3, B3, B2: act buffer -> this head's accumulator
-            tq_mbar_wait(tq_smem_u32(&act_full), (uint32_t)iact & 1u); ++iact;
-            tq_fence_after();
-            TB_STAMP_M();
-            for (int kc = 0; kc < 2; ++kc) { mma_tile(act_base + kc * TQ_SLOT, acc, kc == 0, wide); TB_STAMP_M(); }
-            commit(&acc_full);
-          }
-          tq_mbar_wait(tq_smem_u32(&act_full), (uint32_t)iact & 1u); ++iact;   // g1 is in the act buffer (forward-only head: its
-          tq_fence_after();                                                    // accumulator has been read out and may be reused)
+          for (int st = 0; st < (fo ? 2 : 4); ++st) stage_mma(pj, wide);
+          tq_mbar_wait(tq_smem_u32(&act_full[pj]), (uint32_t)iact[pj] & 1u); ++iact[pj];   // g1 is in the activation region (forward-only head:
+          tq_fence_after();                                                              // its accumulator has been read out and may be reused)
           if (fo) continue;
-          if (merge) {
-            if (pj == 0) continue;                                      // g1 of the first head waits in tensor memory (its accumulator columns)
-            for (int u = 0; u < TQ_NCHUNK / 2; ++u, ++gfi) {            // merged B1: gf = g1_A W1_A + g1_B W1_B, A operands from tensor memory
-              const int gs = gfi % TB_NGF;
-              tq_mbar_wait(tq_smem_u32(&gf_empty[gs]), ((uint32_t)(gfi / TB_NGF) & 1u) ^ 1u);
-              tq_fence_after();
-              for (int q = 0; q < 4; ++q) {
-                uint32_t waddr;
-                const int s = next_w(false, waddr);
-                const uint64_t b_hi = tq_desc(waddr), b_lo = tq_desc(waddr + TQ_PLANE);
-                const uint32_t a_base = tmem_base + (q < 2 ? 0 : TQ_H), d = tmem_base + 2 * TQ_H + gs * TQ_H;
-                if (tq_elect_one()) {
-#pragma unroll
-                  for (int kk = 0; kk < TQ_KC / 16; ++kk) {
-                    // K step of 16 elements = 8 columns; per 32-element chunk the layout is [hi: 16 columns | lo: 16 columns]
-                    const int kg = (q & 1) * TQ_KC + kk * 16;
-                    const uint32_t a_hi = a_base + (kg >> 5) * 32 + ((kg >> 4) & 1) * 8, a_lo = a_hi + 16;
-                    const uint64_t adv = (uint64_t)(kk * 32 >> 4);
-                    tb_mma_ts(d, a_hi, b_hi + adv, (q == 0 && kk == 0) ? 0u : 1u);
-                    tb_mma_ts(d, a_hi, b_lo + adv, 1u);
-                    tb_mma_ts(d, a_lo, b_hi + adv, 1u);
-                  }
-                  tq_commit(tq_smem_u32(&w_empty[s]));
-                }
-                __syncwarp();
-              }
-              commit(&gf_full[gs]);
-            }
-            continue;
-          }
           for (int u = 0; u < TQ_NCHUNK / 2; ++u, ++gfi) {              // B1: five groups of 128 feature-gradient columns
             const int gs = gfi % TB_NGF;
             tq_mbar_wait(tq_smem_u32(&gf_empty[gs]), ((uint32_t)(gfi / TB_NGF) & 1u) ^ 1u);
             tq_fence_after();
-            for (int kc = 0; kc < 2; ++kc) mma_tile(act_base + kc * TQ_SLOT, tmem_base + 2 * TQ_H + gs * TQ_H, kc == 0, false);
+            for (int kc = 0; kc < 2; ++kc) mma_tile_ts(tmem_base + (2 + pj) * TQ_H, kc, tmem_base + gf_region(pj, gs) * TQ_H, kc == 0, false);
             commit(&gf_full[gs]);
           }
         }
@@ -870,14 +932,29 @@ query_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_c
     // ================================================================== epilogue warps: lower column half of every chain stage, then the drain
     const int r = warp * 32 + lane;
     const uint32_t lane_base = tmem_base + ((uint32_t)(warp * 32) << 16);
-    int iacc = 0, gfi = 0, sc = 0;
+    int gfi = 0, sc = 0;
     float amax = 0.f;
+    HeadState hs[2] = {{0, 0}, {0, 0}};
     TB_STAMP();
-    for (int hi = 0; hi < n_heads; ++hi) {
-      const int h = (int)__fns((unsigned)heads, 0, hi + 1), pj = hi & 1;
-      chain_head(hi, 0, iacc, amax);
-      if (fwd_only(h)) continue;
-      if (merge && pj == 0) continue;                      // the feature gradients of both heads are drained together, after the second head
+    for (int pi = 0; pi < n_pairs; ++pi) {
+    load_tables(pi);
+    if (interleave) {
+#pragma unroll 1
+      for (int st = 0; st < 5; ++st)
+#pragma unroll
+        for (int pj = 0; pj < 2; ++pj) stage(pair_head(pi, pj), pj, 0, st, hs[pj], amax);
+    }
+    for (int pj = 0; pj < 2; ++pj) {
+      const int h = pair_head(pi, pj);
+      if (h < 0) break;
+      if (!interleave) {
+        bool backward = true;
+#pragma unroll 1
+        for (int st = 0; st < 5 && backward; ++st) backward = stage(h, pj, 0, st, hs[pj], amax);
+        if (!backward) continue;
+      } else if (pj == 0) {
+        continue;                                          // the feature gradients of both heads are drained together
+      }
       // ---- drain gf (five 128-column groups) into the fp32 staging ring for the gather warps
       for (int u = 0; u < TQ_NCHUNK / 2; ++u, ++gfi) {
         const int gs = gfi % TB_NGF;
@@ -890,7 +967,7 @@ query_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_c
             tq_mbar_wait(tq_smem_u32(&stg_empty[sc & 1]), ((uint32_t)(sc >> 1) & 1u) ^ 1u);
           }
           float v[32];
-          tq_ld32(lane_base + 2 * TQ_H + gs * TQ_H + ch * 32, v);
+          tq_ld32(lane_base + gf_region(pj, gs) * TQ_H + ch * 32, v);
           uint8_t* stg = feat_ptr + (sc & 1) * TQ_SLOT + r * 256;
 #pragma unroll
           for (int q4 = 0; q4 < 8; ++q4)
@@ -906,7 +983,8 @@ query_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_c
         if (lane == 0) tq_mbar_arrive(tq_smem_u32(&gf_empty[gs]));
         TB_STAMP();
       }
-    }
+    }   // head slots
+    }   // pairs
     if (amax > 65504.f) atomicAdd(overflow, 1);
   }
   tq_fence_before();
