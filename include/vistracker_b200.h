@@ -384,6 +384,13 @@ int vt_raster_fwd(const float* verts, const int* faces, int B, int V, int F, int
 int vt_raster_bwd(const float* verts, const int* faces, int B, int V, int F, int mode, const float* K4, int image_size,
                   const float* faces_ndc, const int* face_index, const float* alpha, const float* g_alpha, float* g_faces,
                   float* g_verts, void* stream);
+/* vt_raster_bwd with a caller-owned workspace of vt_workspace_bytes_raster_bwd(B, image_size) bytes (2-byte aligned): prefix counts of the
+ * background pixels that can contribute (alpha == 0 and g_alpha < 0) along every row and column, so that the walks from a visible edge to the
+ * image border -- the bulk of the work -- are skipped where they cannot contribute.  Same result bit for bit; skip_ws == NULL = vt_raster_bwd. */
+long long vt_workspace_bytes_raster_bwd(int B, int image_size);
+int vt_raster_bwd_ws(const float* verts, const int* faces, int B, int V, int F, int mode, const float* K4, int image_size,
+                     const float* faces_ndc, const int* face_index, const float* alpha, const float* g_alpha, float* g_faces,
+                     float* g_verts, void* skip_ws, void* stream);
 
 /* Evaluation Chamfer (the "Chamfer vs ref" half of the metric): per-point Euclidean nearest-neighbour distances between
  * dense clouds, both directions -- recon/eval/chamfer_distance.py:10-52 is mean(dist_x) + mean(dist_y) per frame (sklearn kd-tree there).

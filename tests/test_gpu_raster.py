@@ -135,3 +135,34 @@ def test_silloss_roi_from_masks_constructor():
     loss = out[0]["mask"] if isinstance(out, tuple) else out["mask"]
     loss.sum().backward()
     assert bool(torch.isfinite(loss).all()) and t.grad is not None and bool(torch.isfinite(t.grad).all())
+
+
+def test_backward_walk_skipping_does_not_change_the_gradient():
+    """vt_raster_bwd_ws (prefix counts of the contributing background pixels: walks that cannot contribute are skipped) against the plain
+    vt_raster_bwd walk: the same gradient (to the rounding of the atomic vertex scatter), on a target that is offset from the render (a band of contributing pixels), with an
+    occluder strip, and on a target equal to the render (nothing contributes)."""
+    _need_gpu()
+    from vistracker_b200.render import SilhouetteRenderer
+    size = 96
+    verts0, faces = _mesh(4, n=40)
+    K4 = np.array([1.9, 1.9, 0.5, 0.5])
+    K = torch.tensor([[K4[0], 0, K4[2]], [0, K4[1], K4[3]], [0, 0, 1]], dtype=torch.float32)
+    batch = np.stack([_pose(verts0, s) for s in (1, 2, 3)])
+    rend = SilhouetteRenderer(faces, size, K[None].repeat(3, 1, 1), "cuda:0")
+    with torch.no_grad():
+        shifted = rend(torch.from_numpy(np.stack([_pose(verts0, s + 10) for s in (1, 2, 3)])).cuda())
+        same = rend(torch.from_numpy(batch).cuda())
+    keep = torch.ones(3, size, size, device="cuda"); keep[:, :, :9] = 0
+    for ti, target in enumerate((shifted, same)):
+        grads = []
+        for skip in (False, True):
+            rend.skip_walks = skip
+            v = torch.from_numpy(batch).cuda().requires_grad_(True)
+            ((keep * rend(v) - target) ** 2).sum().backward()
+            grads.append(v.grad.clone())
+        # the per-face gradients are identical; the scatter to the vertices adds them with float atomics (order varies run to run)
+        if ti == 0:
+            assert float(grads[0].abs().max()) > 0 and rel_err(grads[1].cpu(), grads[0].cpu()) < 1e-6
+        else:
+            assert float((grads[1] - grads[0]).abs().max()) <= 1e-6 * max(float(grads[0].abs().max()), 1e-30)
+    rend.skip_walks = True

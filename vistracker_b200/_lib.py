@@ -99,6 +99,8 @@ SIGNATURES.update({
     "vt_raster_cull_floats": (_ll, [_i, _i]),
     "vt_raster_fwd": (_i, [_p, _p, _i, _i, _i, _i, _p, _i, _p, _p, _p, _p, _p, _p]),
     "vt_raster_bwd": (_i, [_p, _p, _i, _i, _i, _i, _p, _i, _p, _p, _p, _p, _p, _p, _p]),
+    "vt_workspace_bytes_raster_bwd": (_ll, [_i, _i]),
+    "vt_raster_bwd_ws": (_i, [_p, _p, _i, _i, _i, _i, _p, _i, _p, _p, _p, _p, _p, _p, _p, _p]),
     "vt_recon_ctrl_words": (_i, []),
     "vt_recon_hist_ld": (_i, []),
     "vt_zero": (_i, [_p, _ll, _p]),

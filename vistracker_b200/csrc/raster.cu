@@ -164,12 +164,38 @@ __global__ void __launch_bounds__(RT * RT) raster_fwd_kernel(const float* __rest
   }
 }
 
+// Inclusive prefix counts of the "active" background pixels -- alpha == 0 and g_alpha < 0, the only ones the OUT walk of raster_bwd_kernel
+// can take a contribution from ((a - alpha_in) g_alpha > 0 with alpha_in = 1) -- along every column (z = 0: P[b][col][row + 1]) and every row
+// (z = 1: P[b][row][col + 1]) of the y-up internal maps.  One warp scans one line.  The backward kernel skips a walk whose range holds none:
+// in the silhouette loss of the fitters the active pixels are the part of the target mask the render does not cover yet, a thin band,
+// while every visible edge pixel column used to walk to the image border.
+__global__ void __launch_bounds__(32) raster_active_prefix_kernel(const float* __restrict__ alpha, const float* __restrict__ g_alpha, int is,
+                                                                  unsigned short* __restrict__ pcol, unsigned short* __restrict__ prow) {
+  const int line = blockIdx.x, bn = blockIdx.y, by_row = blockIdx.z, lane = threadIdx.x;
+  unsigned short* P = (by_row ? prow : pcol) + ((size_t)bn * is + line) * (is + 1);
+  if (lane == 0) P[0] = 0;
+  unsigned carry = 0;
+  for (int i0 = 0; i0 < is; i0 += 32) {
+    const int i = i0 + lane;
+    unsigned act = 0;
+    if (i < is) {
+      const int row = by_row ? line : i, col = by_row ? i : line;
+      const size_t o = ((size_t)bn * is + (is - 1 - row)) * is + col;
+      act = (alpha[o] == 0.f && g_alpha[o] < 0.f) ? 1u : 0u;
+    }
+    const unsigned bal = __ballot_sync(0xffffffffu, act);
+    if (i < is) P[i + 1] = (unsigned short)(carry + __popc(bal & (0xffffffffu >> (31 - lane))));
+    carry += __popc(bal);
+  }
+}
+
 // NMR pseudo-gradient of the silhouette w.r.t. the (x, y) of every face vertex.  One WARP per (frame, face): the lanes split the
 // pixel columns / rows an edge crosses (the upstream kernel walks them in one thread: up to `is` iterations, each with an inner walk of
 // up to `is` pixels -- latency-bound), partial sums are combined with shuffles at the end.
 __global__ void __launch_bounds__(128) raster_bwd_kernel(const float* __restrict__ faces_ndc, const int* __restrict__ face_index,
                                   const float* __restrict__ alpha /*image rows*/, const float* __restrict__ g_alpha /*image rows*/,
-                                  int B, int nf, int is, float* __restrict__ g_faces /*[B][nf][9]*/) {
+                                  int B, int nf, int is, float* __restrict__ g_faces /*[B][nf][9]*/,
+                                  const unsigned short* __restrict__ pcol, const unsigned short* __restrict__ prow /*optional: see above*/) {
   const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (i >= B * nf) return;
   const int bn = i / nf, fn = i % nf;
@@ -211,7 +237,12 @@ __global__ void __launch_bounds__(128) raster_bwd_kernel(const float* __restrict
         const bool is_in_fn = (axis == 0 ? FI(d1_in, d0) : FI(d0, d1_in)) == fn;
         if (is_in_fn) {     // "out": pixels beyond the edge that would become covered
           const int d1_limit = direction > 0 ? is - 1 : 0;
-          const int d1_from = max(min(d1_out, d1_limit), 0), d1_to = min(max(d1_out, d1_limit), is - 1);
+          const int d1_from = max(min(d1_out, d1_limit), 0);
+          int d1_to = min(max(d1_out, d1_limit), is - 1);
+          if (pcol) {                  // no active pixel in the range: every iteration below would `continue`
+            const unsigned short* P = (axis == 0 ? pcol : prow) + ((size_t)bn * is + d0) * (is + 1);
+            if (P[d1_to + 1] == P[d1_from]) d1_to = d1_from - 1;
+          }
           for (int d1 = d1_from; d1 <= d1_to; ++d1) {
             const float a = axis == 0 ? A(d1, d0) : A(d0, d1);
             const float ga = axis == 0 ? GA(d1, d0) : GA(d0, d1);
@@ -324,15 +355,34 @@ int vt_raster_fwd(const float* verts, const int* faces, int B, int V, int F, int
   return 0;
 }
 
+long long vt_workspace_bytes_raster_bwd(int B, int image_size) {
+  return (B <= 0 || image_size <= 0) ? 0 : (long long)B * 2 * image_size * (image_size + 1) * 2;
+}
+
 int vt_raster_bwd(const float* verts, const int* faces, int B, int V, int F, int mode, const float* K4, int image_size,
                   const float* faces_ndc, const int* face_index, const float* alpha, const float* g_alpha, float* g_faces,
                   float* g_verts, void* stream) {
+  return vt_raster_bwd_ws(verts, faces, B, V, F, mode, K4, image_size, faces_ndc, face_index, alpha, g_alpha, g_faces, g_verts, nullptr, stream);
+}
+
+int vt_raster_bwd_ws(const float* verts, const int* faces, int B, int V, int F, int mode, const float* K4, int image_size,
+                     const float* faces_ndc, const int* face_index, const float* alpha, const float* g_alpha, float* g_faces,
+                     float* g_verts, void* skip_ws, void* stream) {
   VT_CHECK_ARG(mode == 0 || mode == 1, "vt_raster_bwd: camera mode %d", mode);
+  VT_CHECK_ARG(image_size > 0 && image_size <= 4096, "vt_raster_bwd: image size %d", image_size);
   if (B <= 0 || F <= 0) return 0;
   cudaStream_t s = (cudaStream_t)stream;
+  unsigned short* pcol = nullptr;
+  unsigned short* prow = nullptr;
+  if (skip_ws) {
+    pcol = reinterpret_cast<unsigned short*>(skip_ws);
+    prow = pcol + (size_t)B * image_size * (image_size + 1);
+    raster_active_prefix_kernel<<<dim3(image_size, B, 2), 32, 0, s>>>(alpha, g_alpha, image_size, pcol, prow);
+    VT_CHECK_LAUNCH("vt_raster_bwd(prefix)");
+  }
   cudaError_t e = cudaMemsetAsync(g_verts, 0, (size_t)B * V * 3 * sizeof(float), s);
   if (e != cudaSuccess) return cuda_fail(e, "vt_raster_bwd memset");
-  raster_bwd_kernel<<<ceil_div(B * 2 * F, 4), 128, 0, s>>>(faces_ndc, face_index, alpha, g_alpha, B, 2 * F, image_size, g_faces);   // one warp per face
+  raster_bwd_kernel<<<ceil_div(B * 2 * F, 4), 128, 0, s>>>(faces_ndc, face_index, alpha, g_alpha, B, 2 * F, image_size, g_faces, pcol, prow);   // one warp per face
   VT_CHECK_LAUNCH("vt_raster_bwd");
   raster_bwd_verts_kernel<<<ceil_div(B * 2 * F, 256), 256, 0, s>>>(g_faces, verts, faces, B, V, F, mode, K4, g_verts);
   VT_CHECK_LAUNCH("vt_raster_bwd(verts)");

@@ -324,6 +324,7 @@ class ObjectFitStep(_GraphLoop):
             b["fidx"] = torch.empty(B, isz, isz, dtype=torch.int32, device=dev)
             b["alpha"], b["g_alpha"] = f(B, isz, isz), f(B, isz, isz)
             b["cull"] = torch.empty(_lib.load().vt_raster_cull_floats(B, F), **to)
+            b["skip"] = torch.empty(_lib.load().vt_workspace_bytes_raster_bwd(B, isz), dtype=torch.uint8, device=dev)
 
     def _mutable_state(self):
         return [self.obj_R, self.obj_t, self.m, self.v, self.ctrl, self.acc, self.hist]
@@ -382,8 +383,8 @@ class ObjectFitStep(_GraphLoop):
             _lib.call("vt_raster_fwd", P(b["vsil"]), P(r.faces), B, Vs, F, r.mode, P(r.K4), isz, P(b["faces_ndc"]), P(b["fidx"]), P(b["alpha"]), None,
                       P(b["cull"]), S())
             _lib.call("vt_recon_sil_loss", P(b["alpha"]), P(sil.keep_mask), P(sil.image_ref), P(self.occ), B, isz, ctrl, P(b["g_alpha"]), acc, S())
-            _lib.call("vt_raster_bwd", P(b["vsil"]), P(r.faces), B, Vs, F, r.mode, P(r.K4), isz, P(b["faces_ndc"]), P(b["fidx"]), P(b["alpha"]),
-                      P(b["g_alpha"]), P(b["g_faces"]), P(b["g_vsil"]), S())
+            _lib.call("vt_raster_bwd_ws", P(b["vsil"]), P(r.faces), B, Vs, F, r.mode, P(r.K4), isz, P(b["faces_ndc"]), P(b["fidx"]), P(b["alpha"]),
+                      P(b["g_alpha"]), P(b["g_faces"]), P(b["g_vsil"]), P(b["skip"]), S())
             _lib.call("vt_recon_obj_transform_bwd", P(sil.vertices), 0, P(b["g_vsil"]), P(self.obj_s), B, Vs, 1, P(b["gR"]), P(b["gt"]), S())
         _lib.call("vt_recon_obj_small_terms", P(self.obj_t), P(b["t_init"]), P(self.obj_s), float(self.fitter.obj_scale), B, 1 if phase == 1 else 0,
                   ctrl, P(b["gt"]), acc, S())

@@ -48,8 +48,9 @@ class _SilFn(torch.autograd.Function):
         g_faces = torch.empty(B, 2 * F, 9, device=v.device)
         g_verts = torch.empty_like(v)
         with torch.cuda.device(v.device):
-            _lib.call("vt_raster_bwd", P(v), P(r.faces), B, V, F, r.mode, P(r.K4), r.image_size, P(faces_ndc), P(fidx), P(alpha), P(g),
-                      P(g_faces), P(g_verts), S())
+            ws = torch.empty(_lib.load().vt_workspace_bytes_raster_bwd(B, r.image_size), dtype=torch.uint8, device=v.device) if r.skip_walks else None
+            _lib.call("vt_raster_bwd_ws", P(v), P(r.faces), B, V, F, r.mode, P(r.K4), r.image_size, P(faces_ndc), P(fidx), P(alpha), P(g),
+                      P(g_faces), P(g_verts), P(ws), S())
         return None, g_verts
 
 
@@ -59,6 +60,7 @@ class SilhouetteRenderer:
     def __init__(self, faces, image_size=256, K=None, device="cuda:0"):
         dev = torch.device(device)
         self.faces = torch.as_tensor(np.asarray(faces)).to(torch.int32).contiguous().to(dev)
+        self.skip_walks = True            # backward: skip border walks that hold no contributing pixel (prefix counts; same result bit for bit)
         self.image_size, self.mode = int(image_size), 0 if K is not None else 1
         self.K4 = None
         if K is not None:
