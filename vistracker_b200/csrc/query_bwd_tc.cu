@@ -18,6 +18,7 @@
 // MMA issuer, warps 6-13 gather (half a warp per point, 16-byte tap loads, four point pairs in flight).
 #include "query_tc_common.cuh"
 #include <stdlib.h>
+#include <type_traits>
 #include "vt_internal.h"
 
 namespace vt {
@@ -93,6 +94,34 @@ __device__ __forceinline__ int tb_norm_exp(float m) {
   int e;
   frexpf(m, &e);
   return max(e, -100);
+}
+
+__device__ __forceinline__ float4 tb_ld4_stream(const float* p) {
+  float4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
+}
+
+// the four bilinear taps (4 channels each) of one point in one chunk.  ALLV: the caller knows that every tap is inside the map (warp-uniform
+// fast path): plain loads at 32-bit element offsets; otherwise the predicated, zero-filled form.  Same addresses, same values.
+template <bool ALLV>
+__device__ __forceinline__ void tb_load_taps(const TqTapTable& T, const TqChunkSrc& s, int pp, float4& t00, float4& t01, float4& t10, float4& t11,
+                                             float& tx, float& ty) {
+  const uint32_t offv = T.offv[s.combo][pp];
+  tx = T.tx[s.combo][pp]; ty = T.ty[s.combo][pp];
+  const int rs = s.W * s.C;
+  if (ALLV) {
+    const int e = ((int)(offv & 0x0FFFFFFFu) - (s.W + 1)) * s.C + s.ch;       // inside one frame's map: < 2^31 elements
+    t00 = ld4(s.base + e); t01 = ld4(s.base + (e + s.C)); t10 = ld4(s.base + (e + rs)); t11 = ld4(s.base + (e + rs + s.C));
+  } else {
+    const unsigned valid = s.sampled ? (offv >> 28) : 0u;
+    const float* p = s.base + ((long long)((int)(offv & 0x0FFFFFFFu) - (s.W + 1)) * s.C + s.ch);
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    t00 = (valid & 1u) ? ld4(p) : z;
+    t01 = (valid & 2u) ? ld4(p + s.C) : z;
+    t10 = (valid & 4u) ? ld4(p + rs) : z;
+    t11 = (valid & 8u) ? ld4(p + rs + s.C) : z;
+  }
 }
 
 // 14 warps are allocated registers as 16 (groups of four): 65536 / 512 = 128 per thread
@@ -554,6 +583,16 @@ query_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_c
     float acc_x = 0.f, acc_y = 0.f, acc_z = 0.f;           // lanes 0-15: point gw * PW + lane, summed over heads (modes 0 and 1)
     __syncwarp();
     int it = 0, sc = 0;
+    // bit c: all four taps of all 16 points of this warp are inside the maps chunk c samples (warp-uniform; tap table of the prologue)
+    uint32_t fastc = 0;
+    {
+      uint32_t fm = 0;
+#pragma unroll
+      for (int cb = 0; cb < TQ_NCOMBO; ++cb)
+        if (__all_sync(0xffffffffu, (s_tap.offv[cb][gw * PW + (lane & 15)] >> 28) == 0xFu)) fm |= 1u << cb;
+      const uint32_t b = fm;
+      fastc = ((b & 1u) ? 0xFu : 0u) | (((b >> 1) & 1u) << 4) | (((b >> 2) & 7u) << 5) | ((((b >> 5) & 3u) == 3u ? 1u : 0u) << 8) | (((b >> 7) & 1u) << 9);
+    }
     HeadState hs_h[2] = {{0, 0}, {0, 0}};                  // gather warps 0-3: upper column half of the chain stages
     float amax = 0.f;
     int trg = 64;
@@ -568,40 +607,40 @@ query_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_c
         tq_mbar_wait(tq_smem_u32(&feat_empty[slot]), ((uint32_t)(it >> 1) & 1u) ^ 1u);
         uint8_t* dst = feat_ptr + slot * TQ_SLOT;
         const TqChunkSrc src = tq_chunk_src(c, k, m, b, B);
+        // ALLV: every tap of the warp's 16 points lies inside the maps of this chunk (fastc, set up once per tile): unconditional loads --
+        // no zero-filled destination registers, no per-tap predicates (the predicated form spends ~10 instructions of set-up per load, and
+        // the gather loops are instruction-issue-bound at two gather warps per scheduler)
+        auto rounds = [&](auto allv) {
 #pragma unroll
-        for (int i0 = 0; i0 < PW; i0 += 2 * PB) {
-          TqTap tap[PB];
+          for (int i0 = 0; i0 < PW; i0 += 2 * PB) {
+            float4 t00[PB], t01[PB], t10[PB], t11[PB];
+            float tx[PB], ty[PB];
 #pragma unroll
-          for (int j = 0; j < PB; ++j) tap[j] = tq_tap_get(s_tap, src, gw * PW + i0 + 2 * j + sub);
-          float4 t00[PB], t01[PB], t10[PB], t11[PB];
+            for (int j = 0; j < PB; ++j)
+              tb_load_taps<decltype(allv)::value>(s_tap, src, gw * PW + i0 + 2 * j + sub, t00[j], t01[j], t10[j], t11[j], tx[j], ty[j]);
 #pragma unroll
-          for (int j = 0; j < PB; ++j) {
-            const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-            t00[j] = (tap[j].valid & 1u) ? ld4(tap[j].p) : z;
-            t01[j] = (tap[j].valid & 2u) ? ld4(tap[j].p + tap[j].C) : z;
-            t10[j] = (tap[j].valid & 4u) ? ld4(tap[j].p + tap[j].rowstride) : z;
-            t11[j] = (tap[j].valid & 8u) ? ld4(tap[j].p + tap[j].rowstride + tap[j].C) : z;
-          }
-#pragma unroll
-          for (int j = 0; j < PB; ++j) {
-            const int pp = gw * PW + i0 + 2 * j + sub;
-            float v[4];
-            v[0] = t00[j].x * tap[j].w00; v[1] = t00[j].y * tap[j].w00; v[2] = t00[j].z * tap[j].w00; v[3] = t00[j].w * tap[j].w00;
-            v[0] += t01[j].x * tap[j].w01; v[1] += t01[j].y * tap[j].w01; v[2] += t01[j].z * tap[j].w01; v[3] += t01[j].w * tap[j].w01;
-            v[0] += t10[j].x * tap[j].w10; v[1] += t10[j].y * tap[j].w10; v[2] += t10[j].z * tap[j].w10; v[3] += t10[j].w * tap[j].w10;
-            v[0] += t11[j].x * tap[j].w11; v[1] += t11[j].y * tap[j].w11; v[2] += t11[j].z * tap[j].w11; v[3] += t11[j].w * tap[j].w11;
-            if (!src.sampled) {
-              v[0] = v[1] = v[2] = v[3] = 0.f;
-              if (src.direct) { v[0] = s_xyz[pp][0]; v[1] = s_xyz[pp][1]; v[2] = s_xyz[pp][2]; }
+            for (int j = 0; j < PB; ++j) {
+              const int pp = gw * PW + i0 + 2 * j + sub;
+              const float w00 = (1.f - tx[j]) * (1.f - ty[j]), w01 = tx[j] * (1.f - ty[j]), w10 = (1.f - tx[j]) * ty[j], w11 = tx[j] * ty[j];
+              float v[4];
+              v[0] = t00[j].x * w00; v[1] = t00[j].y * w00; v[2] = t00[j].z * w00; v[3] = t00[j].w * w00;
+              v[0] += t01[j].x * w01; v[1] += t01[j].y * w01; v[2] += t01[j].z * w01; v[3] += t01[j].w * w01;
+              v[0] += t10[j].x * w10; v[1] += t10[j].y * w10; v[2] += t10[j].z * w10; v[3] += t10[j].w * w10;
+              v[0] += t11[j].x * w11; v[1] += t11[j].y * w11; v[2] += t11[j].z * w11; v[3] += t11[j].w * w11;
+              if (!src.sampled) {
+                v[0] = v[1] = v[2] = v[3] = 0.f;
+                if (src.direct) { v[0] = s_xyz[pp][0]; v[1] = s_xyz[pp][1]; v[2] = s_xyz[pp][2]; }
+              }
+              uint2 hh, ll;
+              tq_split2(v[0], v[1], hh.x, ll.x, amax);
+              tq_split2(v[2], v[3], hh.y, ll.y, amax);
+              const uint32_t off = tq_sw_off(pp, k);
+              *reinterpret_cast<uint2*>(dst + off) = hh;
+              *reinterpret_cast<uint2*>(dst + TQ_PLANE + off) = ll;
             }
-            uint2 hh, ll;
-            tq_split2(v[0], v[1], hh.x, ll.x, amax);
-            tq_split2(v[2], v[3], hh.y, ll.y, amax);
-            const uint32_t off = tq_sw_off(pp, k);
-            *reinterpret_cast<uint2*>(dst + off) = hh;
-            *reinterpret_cast<uint2*>(dst + TQ_PLANE + off) = ll;
           }
-        }
+        };
+        if ((fastc >> c) & 1u) rounds(std::true_type{}); else rounds(std::false_type{});
         tq_fence_async();
         __syncwarp();
         if (lane == 0) tq_mbar_arrive(tq_smem_u32(&feat_full[slot]));
@@ -635,25 +674,21 @@ query_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_c
         const TqChunkSrc src = tq_chunk_src(c, k, m, b, B);
         const bool full_res = (c < 4) || (c >= 5 && c < 8);                // im_feat / tri_feat maps (Hf x Wf); else tmpx-sized maps
         const float su = 0.5f * (float)((full_res ? m.Wf : m.Wt) - 1), sv = 0.5f * (float)((full_res ? m.Hf : m.Ht) - 1);
+        auto rounds = [&](auto allv) {
 #pragma unroll 1
         for (int i0 = 0; i0 < PW; i0 += 2 * PBB * NGRP) {
           // d(feature)/d(u, v) of a bilinear sample is linear in the four taps, so the contraction with the staged feature gradient reduces to
           // four dot products per point -- D_ab = sum_k gf_k * tap_ab_k, 16 FMAs per lane -- and the (1 - t, t) blend is applied to the four
           // scalars afterwards (the previous form blended every feature: ~44 operations per lane).  The taps of NGRP groups of two point
-          // pairs are requested before the first group is reduced: twice the loads in flight per warp (the loop is L2-latency-bound).
-          TqTap tap[NGRP][PBB];
+          // pairs are requested before the first group is reduced: twice the loads in flight per warp.
           float4 t00[NGRP][PBB], t01[NGRP][PBB], t10[NGRP][PBB], t11[NGRP][PBB];
+          float txs[NGRP][PBB], tys[NGRP][PBB];
 #pragma unroll
           for (int gq = 0; gq < NGRP; ++gq)
 #pragma unroll
-            for (int j = 0; j < PBB; ++j) {
-              tap[gq][j] = tq_tap_get(s_tap, src, gw * PW + i0 + gq * 2 * PBB + 2 * j + sub);
-              const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-              t00[gq][j] = (tap[gq][j].valid & 1u) ? ld4(tap[gq][j].p) : z;
-              t01[gq][j] = (tap[gq][j].valid & 2u) ? ld4(tap[gq][j].p + tap[gq][j].C) : z;
-              t10[gq][j] = (tap[gq][j].valid & 4u) ? ld4(tap[gq][j].p + tap[gq][j].rowstride) : z;
-              t11[gq][j] = (tap[gq][j].valid & 8u) ? ld4(tap[gq][j].p + tap[gq][j].rowstride + tap[gq][j].C) : z;
-            }
+            for (int j = 0; j < PBB; ++j)
+              tb_load_taps<decltype(allv)::value>(s_tap, src, gw * PW + i0 + gq * 2 * PBB + 2 * j + sub, t00[gq][j], t01[gq][j], t10[gq][j], t11[gq][j],
+                                                  txs[gq][j], tys[gq][j]);
 #pragma unroll
           for (int gq = 0; gq < NGRP; ++gq) {
           const int ib = i0 + gq * 2 * PBB;
@@ -665,7 +700,7 @@ query_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_c
           for (int j = 0; j < PBB; ++j) {
             const int pp = gw * PW + ib + 2 * j + sub;
             const float4 g = *reinterpret_cast<const float4*>(stg + pp * 256 + (((lane & 15) ^ (pp & 15)) << 4));
-            const float tx = tap[gq][j].tx, ty = tap[gq][j].ty;
+            const float tx = txs[gq][j], ty = tys[gq][j];
             const float d00 = fmaf(g.w, t00[gq][j].w, fmaf(g.z, t00[gq][j].z, fmaf(g.y, t00[gq][j].y, g.x * t00[gq][j].x)));
             const float d01 = fmaf(g.w, t01[gq][j].w, fmaf(g.z, t01[gq][j].z, fmaf(g.y, t01[gq][j].y, g.x * t01[gq][j].x)));
             const float d10 = fmaf(g.w, t10[gq][j].w, fmaf(g.z, t10[gq][j].z, fmaf(g.y, t10[gq][j].y, g.x * t10[gq][j].x)));
@@ -722,6 +757,8 @@ query_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_c
           }
           }   // groups
         }
+        };
+        if ((fastc >> c) & 1u) rounds(std::true_type{}); else rounds(std::false_type{});
         __syncwarp();
         TB_STAMP_G();
         if (lane == 0) tq_mbar_arrive(tq_smem_u32(&stg_empty[slot]));
