@@ -48,18 +48,27 @@ struct TbParams {
   const float* w_df_ptr; const float* w_ce_ptr; float w_df_mul, w_ce_mul;
 };
 
-// per head slot of a pair: last-layer weights, the three biases and the ReLU masks of the three hidden layers (128 bits per point)
+// per head slot of a pair: the last layer's bias, the three hidden biases and the ReLU masks of the three hidden layers (128 bits per point).
+// The last layer's weights live next to the tables as tcgen05 B operands (fp16 hi / lo): see load_tables.
 struct TbHeadTab {
-  float w4[TQ_H * 16 + 16];
+  float b4[16];
   float bias[3][TQ_H];
   uint32_t mask[3][4][TQ_M];
 };
-static_assert(sizeof(TbHeadTab) % 16 == 0 && 2 * sizeof(TbHeadTab) <= TQ_SLOT, "two head tables share one 32 KB slot");
+constexpr int TB_W4F_PLANE = 2 * 16 * TQ_KC * 2;          // W4 as B of the forward product: [16 outputs x 128 units], two 64-unit K chunks, 128-byte swizzle
+constexpr int TB_W4B_PLANE = TQ_H * 16 * 2;               // W4 as B of the backward product: [128 units x 16 outputs], 32-byte rows, 32-byte swizzle
+static_assert(sizeof(TbHeadTab) % 16 == 0 && 2 * sizeof(TbHeadTab) + 2 * TQ_M * 2 * 16 <= TQ_SLOT, "two head tables and the mailboxes share one 32 KB slot");
+static_assert(4 * TB_W4F_PLANE + 4 * TB_W4B_PLANE == TQ_SLOT, "the last-layer operands of two head slots fill one 32 KB slot");
 
 // tcgen05.mma with the A operand in tensor memory (fp16 pairs packed K-contiguous: element k of row m at lane m, column k / 2, half k & 1)
-__device__ __forceinline__ void tb_mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t accumulate) {
+__device__ __forceinline__ void tb_mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t accumulate, uint32_t idesc = TQ_IDESC) {
   asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
-               ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(TQ_IDESC), "r"(accumulate) : "memory");
+               ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+constexpr uint32_t TB_IDESC_N16 = (1u << 4) | ((uint32_t)(16 >> 3) << 17) | ((uint32_t)(TQ_M >> 4) << 24);     // M = 128, N = 16 (the head outputs)
+// K-major operand with 32-byte rows (K = 16 fp16), SWIZZLE_32B: groups of 8 rows are 256 bytes apart
+__device__ __forceinline__ uint64_t tb_desc_sw32(uint32_t saddr) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)1 << 16) | ((uint64_t)(256 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)6 << 61);
 }
 __device__ __forceinline__ void tb_st16(uint32_t taddr, const uint32_t (&r)[16]) {
   asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
@@ -151,9 +160,13 @@ query_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_c
   uint8_t* smem_al = smem_raw + (smem_base - tq_smem_u32(smem_raw));
   const uint32_t feat_base = smem_base, w_base = smem_base + 2 * TQ_SLOT;
   uint8_t* feat_ptr = smem_al;                              // also the gf staging ring: slot = fp32 [128 points][64 features]
-  // the former activation buffer (the A operands live in tensor memory now): 32 KB of mailboxes, then the tables of the two head slots
-  uint8_t* mail_ptr = smem_al + 2 * TQ_SLOT + TQ_NW * TQ_SLOT;
-  TbHeadTab* tab[2] = {reinterpret_cast<TbHeadTab*>(mail_ptr + TQ_SLOT), reinterpret_cast<TbHeadTab*>(mail_ptr + TQ_SLOT) + 1};
+  // the former activation buffer (the A operands live in tensor memory now), two 32 KB slots: [0] the last layer's weights of the two head slots as
+  // tcgen05 B operands -- per slot pj: forward hi | lo planes at pj * 8 KB, backward hi | lo planes at 16 KB + pj * 8 KB --, [1] the two head
+  // tables, then the 16-byte mailboxes of the column-half pairs
+  uint8_t* w4_ptr = smem_al + 2 * TQ_SLOT + TQ_NW * TQ_SLOT;
+  const uint32_t w4_base = smem_base + 2 * TQ_SLOT + TQ_NW * TQ_SLOT;
+  TbHeadTab* tab[2] = {reinterpret_cast<TbHeadTab*>(w4_ptr + TQ_SLOT), reinterpret_cast<TbHeadTab*>(w4_ptr + TQ_SLOT) + 1};
+  uint8_t* mail_ptr = w4_ptr + TQ_SLOT + 2 * sizeof(TbHeadTab);
   // the warp index through a shuffle: the compiler then knows the role branches are warp-uniform (needed for straight-line UTCHMMA issue below)
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const int heads = prm.mode == 1 ? 1 : prm.mode == 2 ? ((prm.labels ? 5 : 1) | prm.fwd_mask) : prm.head_mask;
@@ -263,14 +276,45 @@ query_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_c
         const float* b1 = hw + 616 * 128;
         const float* b2 = b1 + 128 + 128 * 128;
         const float* b3 = b2 + 128 + 128 * 128;
-        const float* W4 = b3 + 128;
-        for (int i = threadIdx.x; i < (TQ_H * 16 + 16) / 4; i += 128)
-          reinterpret_cast<float4*>(tab[pj]->w4)[i] = __ldg(reinterpret_cast<const float4*>(W4) + i);
+        const float* W4 = b3 + 128;                       // [128 units][16 outputs (zero padded)], then the 16 output biases
         if (threadIdx.x < 96) {
           const int l = threadIdx.x >> 5, qq = threadIdx.x & 31;
           reinterpret_cast<float4*>(tab[pj]->bias[l])[qq] = __ldg(reinterpret_cast<const float4*>(l == 0 ? b1 : l == 1 ? b2 : b3) + qq);
+        } else if (threadIdx.x < 100) {
+          reinterpret_cast<float4*>(tab[pj]->b4)[threadIdx.x - 96] = __ldg(reinterpret_cast<const float4*>(W4 + TQ_H * 16) + (threadIdx.x - 96));
+        }
+        // the last layer as tcgen05 operands: thread = hidden unit u, its 16 weights split into fp16 hi / lo
+        //   forward  B[n = output][k = unit]: two [16 x 64] K chunks, rows of 128 bytes, 128-byte swizzle (the layout of every other weight tile)
+        //   backward B[n = unit][k = output]: [128 x 16], rows of 32 bytes, 32-byte swizzle (16-byte chunk j of row n at j ^ ((n >> 2) & 1))
+        const int u = threadIdx.x;
+        float w[16];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float4 t = __ldg(reinterpret_cast<const float4*>(W4 + u * 16) + i);
+          w[4 * i] = t.x; w[4 * i + 1] = t.y; w[4 * i + 2] = t.z; w[4 * i + 3] = t.w;
+        }
+        uint32_t hi[8], lo[8];
+        float wmax = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) tq_split2(w[2 * i], w[2 * i + 1], hi[i], lo[i], wmax);
+        uint8_t* fb = w4_ptr + pj * 2 * TB_W4F_PLANE;                        // hi plane (both K chunks), then the lo plane
+        uint8_t* bb = w4_ptr + 4 * TB_W4F_PLANE + pj * 2 * TB_W4B_PLANE;
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const uint32_t o = (uint32_t)((u >> 3) * 256 + (u & 7) * 32 + ((j ^ ((u >> 2) & 1)) << 4));
+          *reinterpret_cast<uint4*>(bb + o) = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
+          *reinterpret_cast<uint4*>(bb + TB_W4B_PLANE + o) = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+        }
+        const int kc = u >> 6, kk = u & 63;
+#pragma unroll
+        for (int c = 0; c < 16; ++c) {
+          const uint32_t o = (uint32_t)(kc * (16 * TQ_KC * 2) + (c >> 3) * 1024 + (c & 7) * 128 + ((((kk >> 3) ^ (c & 7)) & 7) << 4) + (kk & 7) * 2);
+          const uint32_t hv = (c & 1) ? (hi[c >> 1] >> 16) : (hi[c >> 1] & 0xFFFFu), lv = (c & 1) ? (lo[c >> 1] >> 16) : (lo[c >> 1] & 0xFFFFu);
+          *reinterpret_cast<unsigned short*>(fb + o) = (unsigned short)hv;
+          *reinterpret_cast<unsigned short*>(fb + TB_W4F_PLANE + o) = (unsigned short)lv;
         }
       }
+      tq_fence_async();                                   // generic-proxy writes above -> the tensor core's (async proxy) reads
     }
     asm volatile("bar.sync 2, 256;" ::: "memory");
   };
@@ -281,15 +325,14 @@ query_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_c
     const uint32_t acc_base = lane_base + pj * TQ_H, x_base = lane_base + (2 + pj) * TQ_H;
     TbHeadTab& T = *tab[pj];
     const int col0 = 64 * hf;
-    const bool narrow = h == 0 || h == 3 || h == 4;         // <= 4 outputs: W4 columns 4..15 are zero padding
-    auto mail = [&](int side) { return reinterpret_cast<float*>(mail_ptr + (((xchg & 1) * TQ_M + r) * 2 + side) * 64); };
+    auto mail = [&](int side) { return reinterpret_cast<float*>(mail_ptr + (((xchg & 1) * TQ_M + r) * 2 + side) * 16); };
     auto pair_sync = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(4 + q) : "memory"); ++xchg; };
-    // 8 values (hidden units 64 hf + 8 g .. + 7 of this point) into the A-operand region: 4 columns of hi pairs, 4 of lo pairs
-    auto store_x8 = [&](const float (&v)[8], int g) {
+    // 8 values (K elements c0 + 8 g .. + 7 of this point) into the A-operand region: 4 columns of hi pairs, 4 of lo pairs
+    auto store_x8 = [&](const float (&v)[8], int g, int c0) {
       uint32_t hi4[4], lo4[4];
       tq_split2(v[0], v[1], hi4[0], lo4[0], amax); tq_split2(v[2], v[3], hi4[1], lo4[1], amax);
       tq_split2(v[4], v[5], hi4[2], lo4[2], amax); tq_split2(v[6], v[7], hi4[3], lo4[3], amax);
-      const uint32_t at = x_base + col0 + (g >> 2) * 32 + (g & 3) * 4;
+      const uint32_t at = x_base + c0 + (g >> 2) * 32 + (g & 3) * 4;
       tb_st4(at, hi4);
       tb_st4(at + 16, lo4);
     };
@@ -303,8 +346,10 @@ query_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_c
       tq_mbar_wait(tq_smem_u32(&acc_full[pj]), (uint32_t)hs.iacc & 1u); ++hs.iacc;
       tq_fence_after();
     };
-    if (st < 2) {
-      // ---- forward epilogues E1, E2: bias, ReLU (mask kept), activation -> X
+    if (st < 3) {
+      // ---- forward epilogues E1, E2, E3: bias, ReLU (mask kept), activation -> X.  (E3's activation is the A operand of the last layer:
+      //      [128 x 128] x W4^T [128 x 16] on the tensor core; as FFMA loops over W4 in shared memory -- 32 broadcast LDS.128 per 8 hidden units and
+      //      point for the part head -- the last layer and its transpose took 39 k of a merged tile's 173 k cycles.)
       wait_acc();
       const float* bias = T.bias[st] + col0;
       uint32_t mword = 0;
@@ -319,65 +364,22 @@ query_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_c
         for (int i = 0; i < 8; ++i) { mk |= (v[i] > 0.f ? 1u : 0u) << i; v[i] = fmaxf(v[i], 0.f); }
         mword |= mk << ((g & 3) * 8);
         if ((g & 3) == 3) { T.mask[st][2 * hf + (g >> 2)][r] = mword; mword = 0; }
-        store_x8(v, g);
+        store_x8(v, g, col0);
       }
       publish();
       TB_STAMP();
       return true;
     }
-    if (st == 2) {
-      // ---- E3: layer 3 -> head outputs on the CUDA cores (this half's share), cotangent, g3 -> X
+    if (st == 3) {
+      // ---- head outputs (16 accumulator columns; BOTH column halves read them and derive the same cotangent: nothing to exchange), cotangent at
+      //      the outputs, normalised per point -> the K = 16 A operand of g3 = g4 W4 (written by the lower half)
       wait_acc();
       float o[16];
-#pragma unroll
-      for (int c = 0; c < 16; ++c) o[c] = 0.f;
-      const float* bias = T.bias[2] + col0;
-      uint32_t mword = 0;
-#pragma unroll 1
-      for (int g = 0; g < 8; ++g) {
-        float v[8];
-        tq_ld8(acc_base + col0 + g * 8, v);
-        const float4 ba = *reinterpret_cast<const float4*>(bias + g * 8), bb = *reinterpret_cast<const float4*>(bias + g * 8 + 4);
-        v[0] += ba.x; v[1] += ba.y; v[2] += ba.z; v[3] += ba.w; v[4] += bb.x; v[5] += bb.y; v[6] += bb.z; v[7] += bb.w;
-        uint32_t mk = 0;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) { mk |= (v[i] > 0.f ? 1u : 0u) << i; v[i] = fmaxf(v[i], 0.f); }
-        mword |= mk << ((g & 3) * 8);
-        if ((g & 3) == 3) { T.mask[2][2 * hf + (g >> 2)][r] = mword; mword = 0; }
-        if (narrow) {                          // heads with <= 4 outputs (df, centers, visibility): one 16-byte weight load per unit
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float4 w0 = *reinterpret_cast<const float4*>(T.w4 + (col0 + g * 8 + i) * 16);
-            o[0] = fmaf(v[i], w0.x, o[0]); o[1] = fmaf(v[i], w0.y, o[1]); o[2] = fmaf(v[i], w0.z, o[2]); o[3] = fmaf(v[i], w0.w, o[3]);
-          }
-        } else {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float4* wr = reinterpret_cast<const float4*>(T.w4 + (col0 + g * 8 + i) * 16);
-            const float4 w0 = wr[0], w1 = wr[1], w2 = wr[2], w3 = wr[3];
-            o[0] = fmaf(v[i], w0.x, o[0]); o[1] = fmaf(v[i], w0.y, o[1]); o[2] = fmaf(v[i], w0.z, o[2]); o[3] = fmaf(v[i], w0.w, o[3]);
-            o[4] = fmaf(v[i], w1.x, o[4]); o[5] = fmaf(v[i], w1.y, o[5]); o[6] = fmaf(v[i], w1.z, o[6]); o[7] = fmaf(v[i], w1.w, o[7]);
-            o[8] = fmaf(v[i], w2.x, o[8]); o[9] = fmaf(v[i], w2.y, o[9]); o[10] = fmaf(v[i], w2.z, o[10]); o[11] = fmaf(v[i], w2.w, o[11]);
-            o[12] = fmaf(v[i], w3.x, o[12]); o[13] = fmaf(v[i], w3.y, o[13]);
-          }
-        }
-      }
-      // the upper half posts its partial sums, the lower half owns the head outputs
-      if (hf) {
-        float* mo = mail(0);
-#pragma unroll
-        for (int c = 0; c < 16; c += 4) *reinterpret_cast<float4*>(mo + c) = make_float4(o[c], o[c + 1], o[c + 2], o[c + 3]);
-      }
       {
-        float* mi = mail(0);
-        pair_sync();
-        if (!hf) {
+        float t0[8], t1[8];
+        tq_ld8(acc_base, t0); tq_ld8(acc_base + 8, t1);
 #pragma unroll
-          for (int c = 0; c < 16; c += 4) {
-            const float4 t = *reinterpret_cast<const float4*>(mi + c);
-            o[c] += t.x; o[c + 1] += t.y; o[c + 2] += t.z; o[c + 3] += t.w;
-          }
-        }
+        for (int c = 0; c < 8; ++c) { o[c] = t0[c]; o[8 + c] = t1[c]; }
       }
       const int nout = h == 0 ? 2 : h == 1 ? 9 : h == 2 ? 14 : h == 3 ? 3 : 1;
       const int hoff = h == 0 ? 0 : h == 1 ? 2 : h == 2 ? 11 : h == 3 ? 25 : 28;
@@ -386,7 +388,7 @@ query_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_c
 #pragma unroll
           for (int c = 0; c < 14; ++c) {
             if (c >= nout) break;
-            float val = o[c] + T.w4[TQ_H * 16 + c];
+            float val = o[c] + T.b4[c];
             if (h == 4) val = 1.f / (1.f + expf(-val));
             if (h == 0 && !s_in_img[r]) val = cam.out_dist;
             prm.out_fwd[((size_t)b * 29 + hoff + c) * N + n] = val;
@@ -395,114 +397,90 @@ query_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_c
         publish();
         return false;
       }
-      // cotangent at the head outputs, normalised per point (lower half; posted to the upper half)
       float g4[16];
-      if (!hf) {
-        float gmax = 0.f;
+      float gmax = 0.f;
 #pragma unroll
-        for (int c = 0; c < 14; ++c) {
-          float g = 0.f;
-          if (c < nout && n < N) {
-            float val = o[c] + T.w4[TQ_H * 16 + c];
-            if (h == 4) val = 1.f / (1.f + expf(-val));
-            if (h == 0 && !s_in_img[r]) val = cam.out_dist;
-            if (prm.mode == 0) {
-              g = prm.g_out[((size_t)b * 29 + hoff + c) * N + n];
-              if (h == 4) g *= val * (1.f - val);
-            } else if (h == 0 && c == prm.df_idx) {
-              g = val <= prm.threshold ? 1.f : 0.f;
+      for (int c = 0; c < 14; ++c) {
+        float g = 0.f;
+        if (c < nout && n < N) {
+          float val = o[c] + T.b4[c];
+          if (h == 4) val = 1.f / (1.f + expf(-val));
+          if (h == 0 && !s_in_img[r]) val = cam.out_dist;
+          if (prm.mode == 0) {
+            g = prm.g_out[((size_t)b * 29 + hoff + c) * N + n];
+            if (h == 4) g *= val * (1.f - val);
+          } else if (h == 0 && c == prm.df_idx) {
+            g = val <= prm.threshold ? 1.f : 0.f;
+            if (!hf) {
               s_dfc[r] = fminf(val, prm.threshold);
               if (prm.mode == 2) prm.vals_df[(size_t)b * N + n] = fminf(val, prm.threshold);
-            } else if (h == 2) {
-              g = val;                                     // mode 2: keep the logit, turned into softmax - onehot below
             }
-            if (h == 0 && !s_in_img[r]) g = 0.f;
+          } else if (h == 2) {
+            g = val;                                     // mode 2: keep the logit, turned into softmax - onehot below
           }
-          g4[c] = g;
-          gmax = fmaxf(gmax, fabsf(g));
+          if (h == 0 && !s_in_img[r]) g = 0.f;
         }
-        g4[14] = 0.f; g4[15] = 0.f;
-        if (merge && h == 0) {
-          const float wdf = s_wloss[0];
-#pragma unroll
-          for (int c = 0; c < 2; ++c) g4[c] *= wdf;
-          gmax *= fabsf(wdf);
-        }
-        if (prm.mode == 2 && h == 2) {                     // F.cross_entropy(parts, labels, reduction='none') and its logit gradient
-          gmax = 0.f;
-          if (n < N) {
-            const int lab = s_label[r];
-            float mx = g4[0];
-#pragma unroll
-            for (int c = 1; c < 14; ++c) mx = fmaxf(mx, g4[c]);
-            float sum = 0.f, l_lab = 0.f;
-#pragma unroll
-            for (int c = 0; c < 14; ++c) { if (c == lab) l_lab = g4[c]; g4[c] = __expf(g4[c] - mx); sum += g4[c]; }
-            prm.vals_ce[(size_t)b * N + n] = logf(sum) - (l_lab - mx);
-            const float inv_sum = 1.f / sum;
-            const float wce = merge ? s_wloss[1] : 1.f;
-#pragma unroll
-            for (int c = 0; c < 14; ++c) { g4[c] = (g4[c] * inv_sum - (c == lab ? 1.f : 0.f)) * wce; gmax = fmaxf(gmax, fabsf(g4[c])); }
-          } else {
-#pragma unroll
-            for (int c = 0; c < 14; ++c) g4[c] = 0.f;
-          }
-        }
-        hs.e_total = tb_norm_exp(gmax);
-        const float inv = tb_pow2(-hs.e_total);
-#pragma unroll
-        for (int c = 0; c < 14; ++c) g4[c] *= inv;
-        g4[15] = __int_as_float(hs.e_total);
-        float* mo = mail(1);
-#pragma unroll
-        for (int c = 0; c < 16; c += 4) *reinterpret_cast<float4*>(mo + c) = make_float4(g4[c], g4[c + 1], g4[c + 2], g4[c + 3]);
+        g4[c] = g;
+        gmax = fmaxf(gmax, fabsf(g));
       }
-      {
-        float* mi = mail(1);
-        pair_sync();
-        if (hf) {
+      g4[14] = 0.f; g4[15] = 0.f;
+      if (merge && h == 0) {
+        const float wdf = s_wloss[0];
 #pragma unroll
-          for (int c = 0; c < 16; c += 4) {
-            const float4 t = *reinterpret_cast<const float4*>(mi + c);
-            g4[c] = t.x; g4[c + 1] = t.y; g4[c + 2] = t.z; g4[c + 3] = t.w;
-          }
-          hs.e_total = __float_as_int(g4[15]);
-        }
+        for (int c = 0; c < 2; ++c) g4[c] *= wdf;
+        gmax *= fabsf(wdf);
       }
-      // g3 = relu'(h3) . (W4^T g4): 128 x <= 14 on the CUDA cores, straight into the A operand of B3
-#pragma unroll 1
-      for (int g = 0; g < 8; ++g) {
-        float v[8];
-        const uint32_t mk = T.mask[2][2 * hf + (g >> 2)][r] >> ((g & 3) * 8);
-        if (narrow) {
+      if (prm.mode == 2 && h == 2) {                     // F.cross_entropy(parts, labels, reduction='none') and its logit gradient
+        gmax = 0.f;
+        if (n < N) {
+          const int lab = s_label[r];
+          float mx = g4[0];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float4 w0 = *reinterpret_cast<const float4*>(T.w4 + (col0 + g * 8 + i) * 16);
-            float a = g4[0] * w0.x;
-            a = fmaf(g4[1], w0.y, a); a = fmaf(g4[2], w0.z, a); a = fmaf(g4[3], w0.w, a);
-            v[i] = ((mk >> i) & 1u) ? a : 0.f;
-          }
+          for (int c = 1; c < 14; ++c) mx = fmaxf(mx, g4[c]);
+          float sum = 0.f, l_lab = 0.f;
+#pragma unroll
+          for (int c = 0; c < 14; ++c) { if (c == lab) l_lab = g4[c]; g4[c] = __expf(g4[c] - mx); sum += g4[c]; }
+          if (!hf) prm.vals_ce[(size_t)b * N + n] = logf(sum) - (l_lab - mx);
+          const float inv_sum = 1.f / sum;
+          const float wce = merge ? s_wloss[1] : 1.f;
+#pragma unroll
+          for (int c = 0; c < 14; ++c) { g4[c] = (g4[c] * inv_sum - (c == lab ? 1.f : 0.f)) * wce; gmax = fmaxf(gmax, fabsf(g4[c])); }
         } else {
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float4* wr = reinterpret_cast<const float4*>(T.w4 + (col0 + g * 8 + i) * 16);
-            const float4 w0 = wr[0], w1 = wr[1], w2 = wr[2], w3 = wr[3];
-            float a = g4[0] * w0.x;
-            a = fmaf(g4[1], w0.y, a); a = fmaf(g4[2], w0.z, a); a = fmaf(g4[3], w0.w, a);
-            a = fmaf(g4[4], w1.x, a); a = fmaf(g4[5], w1.y, a); a = fmaf(g4[6], w1.z, a); a = fmaf(g4[7], w1.w, a);
-            a = fmaf(g4[8], w2.x, a); a = fmaf(g4[9], w2.y, a); a = fmaf(g4[10], w2.z, a); a = fmaf(g4[11], w2.w, a);
-            a = fmaf(g4[12], w3.x, a); a = fmaf(g4[13], w3.y, a);
-            v[i] = ((mk >> i) & 1u) ? a : 0.f;
-          }
+          for (int c = 0; c < 14; ++c) g4[c] = 0.f;
         }
-        store_x8(v, g);
+      }
+      hs.e_total = tb_norm_exp(gmax);
+      if (!hf) {                                           // (warp-uniform: tcgen05.st is warp-collective)
+        const float inv = tb_pow2(-hs.e_total);
+        float v0[8], v1[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) { v0[c] = g4[c] * inv; v1[c] = g4[8 + c] * inv; }
+        store_x8(v0, 0, 0);
+        store_x8(v1, 1, 0);
       }
       publish();
       TB_STAMP();
       return true;
     }
-    // ---- backward epilogues EB3 (st 3: mask of layer 2), EB2 (st 4: mask of layer 1): renormalise by the ROW maximum (both halves), mask, split
-    const int bl = 4 - st;
+    if (st == 4) {
+      // ---- g3 = relu'(h3) . (g4 W4): mask the tensor core's product, -> X (the A operand of B3)
+      wait_acc();
+#pragma unroll 1
+      for (int g = 0; g < 8; ++g) {
+        float v[8];
+        tq_ld8(acc_base + col0 + g * 8, v);
+        const uint32_t mk = T.mask[2][2 * hf + (g >> 2)][r] >> ((g & 3) * 8);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = ((mk >> i) & 1u) ? v[i] : 0.f;
+        store_x8(v, g, col0);
+      }
+      publish();
+      TB_STAMP();
+      return true;
+    }
+    // ---- backward epilogues EB3 (st 5: mask of layer 2), EB2 (st 6: mask of layer 1): renormalise by the ROW maximum (both halves), mask, split
+    const int bl = 6 - st;
     wait_acc();
     float vmax = 0.f;
 #pragma unroll 1
@@ -544,7 +522,7 @@ query_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_c
       const uint32_t mk = T.mask[bl][2 * hf + (g >> 2)][r] >> ((g & 3) * 8);
 #pragma unroll
       for (int i = 0; i < 8; ++i) v[i] = ((mk >> i) & 1u) ? v[i] * inv : 0.f;
-      store_x8(v, g);
+      store_x8(v, g, col0);
     }
     if (last_merged) {
       // (tcgen05.ld / st are warp-collective: the branch must be warp-uniform, rows that need no rescale multiply by one)
@@ -569,6 +547,7 @@ query_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_c
     TB_STAMP();
     return true;
   };
+  constexpr int TB_NSTAGE = 7;
 
   if (warp >= 6) {
     // ================================================================== gather warps
@@ -650,7 +629,7 @@ query_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_c
         load_tables(pi);
         if (interleave) {
 #pragma unroll 1
-          for (int st = 0; st < 5; ++st)
+          for (int st = 0; st < TB_NSTAGE; ++st)
 #pragma unroll
             for (int pj = 0; pj < 2; ++pj) stage(pair_head(pi, pj), pj, 1, st, hs_h[pj], amax);
         }
@@ -660,7 +639,7 @@ query_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_c
       if (h < 0) break;
       if (gw < 4 && !interleave) {
 #pragma unroll 1
-        for (int st = 0; st < 5; ++st)
+        for (int st = 0; st < TB_NSTAGE; ++st)
           if (!stage(h, pj, 1, st, hs_h[pj], amax)) break;
       }
       if (fwd_only(h)) continue;
@@ -932,8 +911,48 @@ query_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_c
           for (int kc = 0; kc < 2; ++kc) { mma_tile_ts(tmem_base + (2 + pj) * TQ_H, kc, tmem_base + pj * TQ_H, kc == 0, wide); TB_STAMP_M(); }
           commit(&acc_full[pj]);
         };
+        // the last layer and its transpose: operands resident in shared memory (load_tables), A in the head's activation region
+        //   forward   out[128 x 16]  = h3[128 x 128] W4^T   (8 K steps x 3 MMAs, N = 16) -> accumulator columns 0-15
+        //   backward  g3[128 x 128]  = g4[128 x 16]  W4     (1 K step  x 3 MMAs)        -> the whole accumulator region
+        auto stage_w4f = [&](int pj) {
+          tq_mbar_wait(tq_smem_u32(&act_full[pj]), (uint32_t)iact[pj] & 1u); ++iact[pj];
+          tq_fence_after();
+          const uint32_t fb = w4_base + pj * 2 * TB_W4F_PLANE, x_region = tmem_base + (2 + pj) * TQ_H, acc = tmem_base + pj * TQ_H;
+          if (tq_elect_one()) {
+#pragma unroll
+            for (int ks = 0; ks < TQ_H / 16; ++ks) {
+              const int kg = ks * 16;
+              const uint32_t a_hi = x_region + (kg >> 5) * 32 + ((kg >> 4) & 1) * 8, a_lo = a_hi + 16;
+              const uint32_t boff = (uint32_t)((kg >> 6) * (16 * TQ_KC * 2));
+              const uint64_t adv = (uint64_t)((kg & 63) >> 3);
+              const uint64_t b_hi = tq_desc(fb + boff) + adv, b_lo = tq_desc(fb + TB_W4F_PLANE + boff) + adv;
+              tb_mma_ts(acc, a_hi, b_hi, ks == 0 ? 0u : 1u, TB_IDESC_N16);
+              tb_mma_ts(acc, a_hi, b_lo, 1u, TB_IDESC_N16);
+              tb_mma_ts(acc, a_lo, b_hi, 1u, TB_IDESC_N16);
+            }
+          }
+          __syncwarp();
+          commit(&acc_full[pj]);
+        };
+        auto stage_w4b = [&](int pj) {
+          tq_mbar_wait(tq_smem_u32(&act_full[pj]), (uint32_t)iact[pj] & 1u); ++iact[pj];
+          tq_fence_after();
+          const uint32_t bb = w4_base + 4 * TB_W4F_PLANE + pj * 2 * TB_W4B_PLANE, x_region = tmem_base + (2 + pj) * TQ_H, acc = tmem_base + pj * TQ_H;
+          if (tq_elect_one()) {
+            const uint64_t b_hi = tb_desc_sw32(bb), b_lo = tb_desc_sw32(bb + TB_W4B_PLANE);
+            tb_mma_ts(acc, x_region, b_hi, 0u);
+            tb_mma_ts(acc, x_region, b_lo, 1u);
+            tb_mma_ts(acc, x_region + 16, b_hi, 1u);
+          }
+          __syncwarp();
+          commit(&acc_full[pj]);
+        };
         if (interleave) {
-          for (int st = 0; st < 4; ++st)
+          for (int st = 0; st < 2; ++st)
+            for (int pj = 0; pj < 2; ++pj) stage_mma(pj, true);
+          for (int pj = 0; pj < 2; ++pj) stage_w4f(pj);
+          for (int pj = 0; pj < 2; ++pj) stage_w4b(pj);
+          for (int st = 2; st < 4; ++st)
             for (int pj = 0; pj < 2; ++pj) stage_mma(pj, true);
           for (int pj = 0; pj < 2; ++pj) {                                // both heads' g1 are in their activation regions
             tq_mbar_wait(tq_smem_u32(&act_full[pj]), (uint32_t)iact[pj] & 1u); ++iact[pj];
@@ -951,7 +970,12 @@ query_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_c
         for (int pj = 0; pj < (two ? 2 : 1); ++pj) {
           const bool wide = chain_wide(pi, pj);
           const bool fo = fwd_only(pair_head(pi, pj));
-          for (int st = 0; st < (fo ? 2 : 4); ++st) stage_mma(pj, wide);
+          for (int st = 0; st < 2; ++st) stage_mma(pj, wide);
+          stage_w4f(pj);
+          if (!fo) {
+            stage_w4b(pj);
+            for (int st = 2; st < 4; ++st) stage_mma(pj, wide);
+          }
           tq_mbar_wait(tq_smem_u32(&act_full[pj]), (uint32_t)iact[pj] & 1u); ++iact[pj];   // g1 is in the activation region (forward-only head:
           tq_fence_after();                                                              // its accumulator has been read out and may be reused)
           if (fo) continue;
@@ -977,7 +1001,7 @@ query_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_c
     load_tables(pi);
     if (interleave) {
 #pragma unroll 1
-      for (int st = 0; st < 5; ++st)
+      for (int st = 0; st < TB_NSTAGE; ++st)
 #pragma unroll
         for (int pj = 0; pj < 2; ++pj) stage(pair_head(pi, pj), pj, 0, st, hs[pj], amax);
     }
@@ -987,7 +1011,7 @@ query_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_c
       if (!interleave) {
         bool backward = true;
 #pragma unroll 1
-        for (int st = 0; st < 5 && backward; ++st) backward = stage(h, pj, 0, st, hs[pj], amax);
+        for (int st = 0; st < TB_NSTAGE && backward; ++st) backward = stage(h, pj, 0, st, hs[pj], amax);
         if (!backward) continue;
       } else if (pj == 0) {
         continue;                                          // the feature gradients of both heads are drained together
