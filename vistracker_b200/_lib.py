@@ -152,3 +152,22 @@ def ptr(t):
 def stream_ptr():
     import torch
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+# ---- NVTX ranges around the stages of a batch (VT_NVTX=1; nsys / ncu --nvtx pick them up).  A no-op context manager otherwise.
+import contextlib as _contextlib
+
+_NVTX = os.environ.get("VT_NVTX", "0") not in ("", "0")
+
+
+@_contextlib.contextmanager
+def nvtx_range(name: str):
+    if not _NVTX:
+        yield
+        return
+    import torch
+    torch.cuda.nvtx.range_push(name)
+    try:
+        yield
+    finally:
+        torch.cuda.nvtx.range_pop()

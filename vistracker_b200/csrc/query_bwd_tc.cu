@@ -23,7 +23,8 @@
 
 namespace vt {
 
-constexpr int TB_THREADS = 448;
+constexpr int TB_GATHER_WARPS = 16;                          // gather warps (8 points each); the forward kernel keeps TQ_GATHER_WARPS = 8
+constexpr int TB_THREADS = (6 + TB_GATHER_WARPS) * 32;
 constexpr int TB_NGF = 2;                                  // TMEM slots of 128 columns for gf, after the two 128-column head accumulators
 constexpr int TB_SMEM = 2 * TQ_SLOT /*features | gf staging*/ + TQ_NW * TQ_SLOT /*weights*/ + 2 * TQ_SLOT /*activations*/ + 1024;
 
@@ -83,6 +84,12 @@ __device__ __forceinline__ void tb_ld16(uint32_t taddr, uint32_t (&r)[16]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ void tb_ld16f(uint32_t taddr, float (&v)[16]) {
+  uint32_t r[16];
+  tb_ld16(taddr, r);
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
 __device__ __forceinline__ void tq_ld8(uint32_t taddr, float (&v)[8]) {
   uint32_t r[8];
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
@@ -210,13 +217,13 @@ query_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_c
   const int b = blockIdx.y, n0 = blockIdx.x * TQ_M;
   if (warp == 5 && lane == 0) {
     for (int s = 0; s < 2; ++s) {
-      tq_mbar_init(tq_smem_u32(&feat_full[s]), TQ_GATHER_WARPS); tq_mbar_init(tq_smem_u32(&feat_empty[s]), 1);
-      tq_mbar_init(tq_smem_u32(&stg_full[s]), 4); tq_mbar_init(tq_smem_u32(&stg_empty[s]), TQ_GATHER_WARPS);
+      tq_mbar_init(tq_smem_u32(&feat_full[s]), TB_GATHER_WARPS); tq_mbar_init(tq_smem_u32(&feat_empty[s]), 1);
+      tq_mbar_init(tq_smem_u32(&stg_full[s]), 4); tq_mbar_init(tq_smem_u32(&stg_empty[s]), TB_GATHER_WARPS);
     }
     for (int s = 0; s < 4; ++s) { tq_mbar_init(tq_smem_u32(&w_full[s]), 1); tq_mbar_init(tq_smem_u32(&w_empty[s]), 1); }
     tq_mbar_init(tq_smem_u32(&f1_done), 1);
     for (int s = 0; s < TB_NGF; ++s) { tq_mbar_init(tq_smem_u32(&gf_full[s]), 1); tq_mbar_init(tq_smem_u32(&gf_empty[s]), 4); }
-    for (int s = 0; s < 2; ++s) { tq_mbar_init(tq_smem_u32(&acc_full[s]), 1); tq_mbar_init(tq_smem_u32(&act_full[s]), 8); }
+    for (int s = 0; s < 2; ++s) { tq_mbar_init(tq_smem_u32(&acc_full[s]), 1); tq_mbar_init(tq_smem_u32(&act_full[s]), 16); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   // projections of the tile's points (gather warps, one thread per point) -- same arithmetic as query_fwd_tc_kernel
@@ -267,7 +274,7 @@ query_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_c
   struct HeadState { int iacc; int e_total; };
   // stage tables of the two head slots of a pair, filled by the epilogue warps before stage 0 (load_tables)
   auto load_tables = [&](int pi) {
-    asm volatile("bar.sync 2, 256;" ::: "memory");        // the previous pair has finished reading the tables
+    asm volatile("bar.sync 2, 512;" ::: "memory");        // the previous pair has finished reading the tables
     if (warp < 4) {
       for (int pj = 0; pj < 2; ++pj) {
         const int h = pair_head(pi, pj);
@@ -316,17 +323,17 @@ query_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_c
       }
       tq_fence_async();                                   // generic-proxy writes above -> the tensor core's (async proxy) reads
     }
-    asm volatile("bar.sync 2, 256;" ::: "memory");
+    asm volatile("bar.sync 2, 512;" ::: "memory");
   };
   int xchg = 0;                                           // exchanges done by this thread (mailbox parity); same sequence in both halves
-  auto stage = [&](const int h, const int pj, const int hf, const int st, HeadState& hs, float& amax) -> bool {
+  auto stage = [&](const int h, const int pj, const int hq, const int st, HeadState& hs, float& amax) -> bool {
     const int q = warp & 3, r = q * 32 + lane, n = n0 + r;
     const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
     const uint32_t acc_base = lane_base + pj * TQ_H, x_base = lane_base + (2 + pj) * TQ_H;
     TbHeadTab& T = *tab[pj];
-    const int col0 = 64 * hf;
-    auto mail = [&](int side) { return reinterpret_cast<float*>(mail_ptr + (((xchg & 1) * TQ_M + r) * 2 + side) * 16); };
-    auto pair_sync = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(4 + q) : "memory"); ++xchg; };
+    const int col0 = 32 * hq;                              // this thread's quarter of the 128 hidden units
+    auto mail = [&]() { return reinterpret_cast<float*>(mail_ptr + ((xchg & 1) * TQ_M + r) * 32); };       // 4 row maxima + the first head's exponent
+    auto quad_sync = [&]() { asm volatile("bar.sync %0, 128;" ::"r"(4 + q) : "memory"); ++xchg; };
     // 8 values (K elements c0 + 8 g .. + 7 of this point) into the A-operand region: 4 columns of hi pairs, 4 of lo pairs
     auto store_x8 = [&](const float (&v)[8], int g, int c0) {
       uint32_t hi4[4], lo4[4];
@@ -354,18 +361,24 @@ query_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_c
       const float* bias = T.bias[st] + col0;
       uint32_t mword = 0;
 #pragma unroll 1
-      for (int g = 0; g < 8; ++g) {
-        float v[8];
-        tq_ld8(acc_base + col0 + g * 8, v);
-        const float4 ba = *reinterpret_cast<const float4*>(bias + g * 8), bb = *reinterpret_cast<const float4*>(bias + g * 8 + 4);
-        v[0] += ba.x; v[1] += ba.y; v[2] += ba.z; v[3] += ba.w; v[4] += bb.x; v[5] += bb.y; v[6] += bb.z; v[7] += bb.w;
-        uint32_t mk = 0;
+      for (int g2 = 0; g2 < 2; ++g2) {                     // 16 accumulator columns per tensor-memory round trip
+        float w16[16];
+        tb_ld16f(acc_base + col0 + g2 * 16, w16);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) { mk |= (v[i] > 0.f ? 1u : 0u) << i; v[i] = fmaxf(v[i], 0.f); }
-        mword |= mk << ((g & 3) * 8);
-        if ((g & 3) == 3) { T.mask[st][2 * hf + (g >> 2)][r] = mword; mword = 0; }
-        store_x8(v, g, col0);
+        for (int gg = 0; gg < 2; ++gg) {
+          const int g = 2 * g2 + gg;
+          float v[8];
+          const float4 ba = *reinterpret_cast<const float4*>(bias + g * 8), bb = *reinterpret_cast<const float4*>(bias + g * 8 + 4);
+          v[0] = w16[8 * gg] + ba.x; v[1] = w16[8 * gg + 1] + ba.y; v[2] = w16[8 * gg + 2] + ba.z; v[3] = w16[8 * gg + 3] + ba.w;
+          v[4] = w16[8 * gg + 4] + bb.x; v[5] = w16[8 * gg + 5] + bb.y; v[6] = w16[8 * gg + 6] + bb.z; v[7] = w16[8 * gg + 7] + bb.w;
+          uint32_t mk = 0;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) { mk |= (v[i] > 0.f ? 1u : 0u) << i; v[i] = fmaxf(v[i], 0.f); }
+          mword |= mk << ((g & 3) * 8);
+          store_x8(v, g, col0);
+        }
       }
+      T.mask[st][hq][r] = mword;
       publish();
       TB_STAMP();
       return true;
@@ -380,11 +393,17 @@ query_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_c
         tq_ld8(acc_base, t0); tq_ld8(acc_base + 8, t1);
 #pragma unroll
         for (int c = 0; c < 8; ++c) { o[c] = t0[c]; o[8 + c] = t1[c]; }
+#pragma unroll 1
+        for (int ks = 1; ks < TQ_H / 16; ++ks) {             // the partial sums of the other K steps (see stage_w4f)
+          tq_ld8(acc_base + 16 * ks, t0); tq_ld8(acc_base + 16 * ks + 8, t1);
+#pragma unroll
+          for (int c = 0; c < 8; ++c) { o[c] += t0[c]; o[8 + c] += t1[c]; }
+        }
       }
       const int nout = h == 0 ? 2 : h == 1 ? 9 : h == 2 ? 14 : h == 3 ? 3 : 1;
       const int hoff = h == 0 ? 0 : h == 1 ? 2 : h == 2 ? 11 : h == 3 ? 25 : 28;
       if (fwd_only(h)) {                       // predictions only: write them, hand the accumulator back
-        if (!hf && n < N) {
+        if (!hq && n < N) {
 #pragma unroll
           for (int c = 0; c < 14; ++c) {
             if (c >= nout) break;
@@ -397,61 +416,56 @@ query_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_c
         publish();
         return false;
       }
+      // (one compact path per use: this block runs once per head and tile, and the generic form -- 14 unrolled outputs with the head tests inside --
+      //  was 1.4 k instructions per inlined copy: the stage spent most of its 8 k cycles fetching them)
       float g4[16];
+#pragma unroll
+      for (int c = 0; c < 16; ++c) g4[c] = 0.f;
       float gmax = 0.f;
+      if (prm.mode == 0) {                                 // generic cotangent (autograd backward of query())
 #pragma unroll
-      for (int c = 0; c < 14; ++c) {
-        float g = 0.f;
-        if (c < nout && n < N) {
-          float val = o[c] + T.b4[c];
-          if (h == 4) val = 1.f / (1.f + expf(-val));
-          if (h == 0 && !s_in_img[r]) val = cam.out_dist;
-          if (prm.mode == 0) {
+        for (int c = 0; c < 14; ++c) {
+          float g = 0.f;
+          if (c < nout && n < N) {
             g = prm.g_out[((size_t)b * 29 + hoff + c) * N + n];
-            if (h == 4) g *= val * (1.f - val);
-          } else if (h == 0 && c == prm.df_idx) {
-            g = val <= prm.threshold ? 1.f : 0.f;
-            if (!hf) {
-              s_dfc[r] = fminf(val, prm.threshold);
-              if (prm.mode == 2) prm.vals_df[(size_t)b * N + n] = fminf(val, prm.threshold);
-            }
-          } else if (h == 2) {
-            g = val;                                     // mode 2: keep the logit, turned into softmax - onehot below
+            if (h == 4) { const float val = 1.f / (1.f + expf(-(o[c] + T.b4[c]))); g *= val * (1.f - val); }
+            if (h == 0 && !s_in_img[r]) g = 0.f;
           }
-          if (h == 0 && !s_in_img[r]) g = 0.f;
+          g4[c] = g;
+          gmax = fmaxf(gmax, fabsf(g));
         }
-        g4[c] = g;
-        gmax = fmaxf(gmax, fabsf(g));
-      }
-      g4[14] = 0.f; g4[15] = 0.f;
-      if (merge && h == 0) {
-        const float wdf = s_wloss[0];
-#pragma unroll
-        for (int c = 0; c < 2; ++c) g4[c] *= wdf;
-        gmax *= fabsf(wdf);
-      }
-      if (prm.mode == 2 && h == 2) {                     // F.cross_entropy(parts, labels, reduction='none') and its logit gradient
-        gmax = 0.f;
+      } else if (h == 0) {                                 // d clamp(df[df_idx], max = threshold): one output
+        if (n < N) {
+          float val = (prm.df_idx ? o[1] : o[0]) + T.b4[prm.df_idx];
+          const bool inside = s_in_img[r] != 0;
+          if (!inside) val = cam.out_dist;
+          float g = (val <= prm.threshold && inside) ? 1.f : 0.f;
+          if (!hq) {
+            s_dfc[r] = fminf(val, prm.threshold);
+            if (prm.mode == 2) prm.vals_df[(size_t)b * N + n] = fminf(val, prm.threshold);
+          }
+          if (merge) g *= s_wloss[0];
+          if (prm.df_idx) g4[1] = g; else g4[0] = g;
+          gmax = fabsf(g);
+        }
+      } else if (prm.mode == 2 && h == 2) {                // F.cross_entropy(parts, labels, reduction='none') and its logit gradient
         if (n < N) {
           const int lab = s_label[r];
-          float mx = g4[0];
+          float mx = -3.0e38f;
 #pragma unroll
-          for (int c = 1; c < 14; ++c) mx = fmaxf(mx, g4[c]);
+          for (int c = 0; c < 14; ++c) { g4[c] = o[c] + T.b4[c]; mx = fmaxf(mx, g4[c]); }
           float sum = 0.f, l_lab = 0.f;
 #pragma unroll
           for (int c = 0; c < 14; ++c) { if (c == lab) l_lab = g4[c]; g4[c] = __expf(g4[c] - mx); sum += g4[c]; }
-          if (!hf) prm.vals_ce[(size_t)b * N + n] = logf(sum) - (l_lab - mx);
+          if (!hq) prm.vals_ce[(size_t)b * N + n] = logf(sum) - (l_lab - mx);
           const float inv_sum = 1.f / sum;
           const float wce = merge ? s_wloss[1] : 1.f;
 #pragma unroll
           for (int c = 0; c < 14; ++c) { g4[c] = (g4[c] * inv_sum - (c == lab ? 1.f : 0.f)) * wce; gmax = fmaxf(gmax, fabsf(g4[c])); }
-        } else {
-#pragma unroll
-          for (int c = 0; c < 14; ++c) g4[c] = 0.f;
         }
       }
       hs.e_total = tb_norm_exp(gmax);
-      if (!hf) {                                           // (warp-uniform: tcgen05.st is warp-collective)
+      if (!hq) {                                           // (warp-uniform: tcgen05.st is warp-collective)
         const float inv = tb_pow2(-hs.e_total);
         float v0[8], v1[8];
 #pragma unroll
@@ -467,13 +481,17 @@ query_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_c
       // ---- g3 = relu'(h3) . (g4 W4): mask the tensor core's product, -> X (the A operand of B3)
       wait_acc();
 #pragma unroll 1
-      for (int g = 0; g < 8; ++g) {
-        float v[8];
-        tq_ld8(acc_base + col0 + g * 8, v);
-        const uint32_t mk = T.mask[2][2 * hf + (g >> 2)][r] >> ((g & 3) * 8);
+      for (int g2 = 0; g2 < 2; ++g2) {
+        float w16[16];
+        tb_ld16f(acc_base + col0 + g2 * 16, w16);
+        const uint32_t mk16 = T.mask[2][hq][r] >> (g2 * 16);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) v[i] = ((mk >> i) & 1u) ? v[i] : 0.f;
-        store_x8(v, g, col0);
+        for (int gg = 0; gg < 2; ++gg) {
+          float v[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) v[i] = ((mk16 >> (8 * gg + i)) & 1u) ? w16[8 * gg + i] : 0.f;
+          store_x8(v, 2 * g2 + gg, col0);
+        }
       }
       publish();
       TB_STAMP();
@@ -484,25 +502,25 @@ query_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_c
     wait_acc();
     float vmax = 0.f;
 #pragma unroll 1
-    for (int g = 0; g < 8; ++g) {
-      float v[8];
-      tq_ld8(acc_base + col0 + g * 8, v);
-      const uint32_t mk = T.mask[bl][2 * hf + (g >> 2)][r] >> ((g & 3) * 8);
+    for (int g2 = 0; g2 < 2; ++g2) {
+      float w16[16];
+      tb_ld16f(acc_base + col0 + g2 * 16, w16);
+      const uint32_t mk16 = T.mask[bl][hq][r] >> (g2 * 16);
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
-        if ((mk >> i) & 1u) vmax = fmaxf(vmax, fabsf(v[i]));
+      for (int i = 0; i < 16; ++i)
+        if ((mk16 >> i) & 1u) vmax = fmaxf(vmax, fabsf(w16[i]));
     }
     // merged pair, second head: the first head's exponent.  The lower half wrote it (same thread, earlier stage) and hands it to the upper
     // half with the row maximum, so that no read of s_scale_e crosses threads without a barrier
-    int e_first = hf ? 0 : s_scale_e[r];
+    int e_first = hq ? 0 : s_scale_e[r];
     {
-      float* mo = mail(hf ^ 1);
-      float* mi = mail(hf);
-      mo[0] = vmax;
-      if (!hf) mo[1] = __int_as_float(e_first);
-      pair_sync();
-      vmax = fmaxf(vmax, mi[0]);
-      if (hf) e_first = __float_as_int(mi[1]);
+      float* mb = mail();
+      mb[hq] = vmax;
+      if (!hq) mb[4] = __int_as_float(e_first);
+      quad_sync();
+      const float4 t = *reinterpret_cast<const float4*>(mb);
+      vmax = fmaxf(fmaxf(t.x, t.y), fmaxf(t.z, t.w));
+      if (hq) e_first = __float_as_int(mb[4]);
     }
     const int e = tb_norm_exp(vmax);
     hs.e_total += e;
@@ -513,25 +531,29 @@ query_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_c
     if (last_merged && pj == 1) E = max(E, e_first);
     // the lower half publishes the exponent right after the row-maximum exchange: both halves have read the first head's value (e_first)
     // before that barrier, and with interleaved chains the upper half may reach the second head's read with no further barrier in between
-    if (bl == 0 && !hf) s_scale_e[r] = E;                  // also read by the gather warps after the first staging chunk is published
+    if (bl == 0 && !hq) s_scale_e[r] = E;                  // also read by the gather warps after the first staging chunk is published
     const float inv = tb_pow2(-e + (hs.e_total - E));
 #pragma unroll 1
-    for (int g = 0; g < 8; ++g) {
-      float v[8];
-      tq_ld8(acc_base + col0 + g * 8, v);
-      const uint32_t mk = T.mask[bl][2 * hf + (g >> 2)][r] >> ((g & 3) * 8);
+    for (int g2 = 0; g2 < 2; ++g2) {
+      float w16[16];
+      tb_ld16f(acc_base + col0 + g2 * 16, w16);
+      const uint32_t mk16 = T.mask[bl][hq][r] >> (g2 * 16);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) v[i] = ((mk >> i) & 1u) ? v[i] * inv : 0.f;
-      store_x8(v, g, col0);
+      for (int gg = 0; gg < 2; ++gg) {
+        float v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = ((mk16 >> (8 * gg + i)) & 1u) ? w16[8 * gg + i] * inv : 0.f;
+        store_x8(v, 2 * g2 + gg, col0);
+      }
     }
     if (last_merged) {
       // (tcgen05.ld / st are warp-collective: the branch must be warp-uniform, rows that need no rescale multiply by one)
       const bool rescale = pj == 1 && e_first < E;
       if (__any_sync(0xffffffffu, rescale)) {
         const __half2 sc2 = __float2half2_rn(rescale ? tb_pow2(max(e_first - E, -30)) : 1.f);
-        const uint32_t other = lane_base + 2 * TQ_H + col0;       // the first head's g1, this thread's half
+        const uint32_t other = lane_base + 2 * TQ_H + col0;       // the first head's g1, this thread's quarter
 #pragma unroll 1
-        for (int qq = 0; qq < 4; ++qq) {
+        for (int qq = 0; qq < 2; ++qq) {
           uint32_t w[16];
           tb_ld16(other + qq * 16, w);
 #pragma unroll
@@ -553,12 +575,12 @@ query_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_c
     // ================================================================== gather warps
     const int gw = warp - 6;
     const int sub = lane >> 4, k = (lane & 15) * 4;
-    constexpr int PB = 4;                                   // point PAIRS in flight per warp
-    constexpr int PW = TQ_M / TQ_GATHER_WARPS;              // 16 points per warp
-    constexpr int PBB = 2, NGRP = 2;                        // ... and in the backward contraction: NGRP groups of PBB point pairs;
+    constexpr int PB = 2;                                   // point PAIRS in flight per warp
+    constexpr int PW = TQ_M / TB_GATHER_WARPS;              // points per warp
+    constexpr int PBB = 2, NGRP = 1;                        // ... and in the backward contraction: NGRP groups of PBB point pairs;
     static_assert(PBB == 2, "the butterfly reduction below handles exactly two points per half-warp");
     for (int i = lane; i < PW * 3; i += 32) (&s_g3[gw * PW][0])[i] = 0.f;       // each warp owns the rows of its 16 points
-    (&s_gp[gw * PW][0])[lane] = 0.f;
+    if (lane < PW * 2) (&s_gp[gw * PW][0])[lane] = 0.f;
     float acc_x = 0.f, acc_y = 0.f, acc_z = 0.f;           // lanes 0-15: point gw * PW + lane, summed over heads (modes 0 and 1)
     __syncwarp();
     int it = 0, sc = 0;
@@ -568,7 +590,7 @@ query_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_c
       uint32_t fm = 0;
 #pragma unroll
       for (int cb = 0; cb < TQ_NCOMBO; ++cb)
-        if (__all_sync(0xffffffffu, (s_tap.offv[cb][gw * PW + (lane & 15)] >> 28) == 0xFu)) fm |= 1u << cb;
+        if (__all_sync(0xffffffffu, (s_tap.offv[cb][gw * PW + (lane & (PW - 1))] >> 28) == 0xFu)) fm |= 1u << cb;
       const uint32_t b = fm;
       fastc = ((b & 1u) ? 0xFu : 0u) | (((b >> 1) & 1u) << 4) | (((b >> 2) & 7u) << 5) | ((((b >> 5) & 3u) == 3u ? 1u : 0u) << 8) | (((b >> 7) & 1u) << 9);
     }
@@ -579,7 +601,7 @@ query_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_c
 #define TB_STAMP_G() do { if (tracing_g && trg < 128) prm.trace[trg++] = clock64(); } while (0)
     TB_STAMP_G();
     for (int pi = 0; pi < n_pairs; ++pi) {
-      asm volatile("bar.sync 3, 256;" ::: "memory");       // every gather warp is done reading the previous head's staging slots
+      asm volatile("bar.sync 3, %0;" ::"n"(TB_GATHER_WARPS * 32) : "memory");       // every gather warp is done reading the previous head's staging slots
       // ---- forward: 10 feature chunks into the A-operand ring (once per pair of heads)
       for (int c = 0; c < TQ_NCHUNK; ++c, ++it) {
         const int slot = it & 1;
@@ -625,22 +647,24 @@ query_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_c
         if (lane == 0) tq_mbar_arrive(tq_smem_u32(&feat_full[slot]));
       }
       TB_STAMP_G();
-      if (gw < 4) {
-        load_tables(pi);
-        if (interleave) {
+      if (gw < 12) load_tables(pi);
 #pragma unroll 1
-          for (int st = 0; st < TB_NSTAGE; ++st)
-#pragma unroll
-            for (int pj = 0; pj < 2; ++pj) stage(pair_head(pi, pj), pj, 1, st, hs_h[pj], amax);
-        }
-      }
       for (int pj = 0; pj < 2; ++pj) {
       const int h = pair_head(pi, pj);
       if (h < 0) break;
-      if (gw < 4 && !interleave) {
+      // the chain: a merged pair runs both head slots stage by stage (once, at slot 0's turn), otherwise slot pj alone.  ONE call site of the
+      // stage code per warp role, head slot and stage as run-time values: inlined at six sites the stages were a third of the kernel's 25 k
+      // instructions, each copy executed once per tile -- the chain was instruction-fetch-bound
+      if (gw < 12 && (!interleave || pj == 0)) {
+        const int nsj = interleave ? 2 * TB_NSTAGE : TB_NSTAGE;
 #pragma unroll 1
-        for (int st = 0; st < TB_NSTAGE; ++st)
-          if (!stage(h, pj, 1, st, hs_h[pj], amax)) break;
+        for (int sj = 0; sj < nsj; ++sj) {
+          const int st = interleave ? (sj >> 1) : sj, pq = interleave ? (sj & 1) : pj;
+          HeadState cur = pq ? hs_h[1] : hs_h[0];
+          const bool live = stage(pair_head(pi, pq), pq, 1 + (gw >> 2), st, cur, amax);
+          if (pq) hs_h[1] = cur; else hs_h[0] = cur;
+          if (!live) break;
+        }
       }
       if (fwd_only(h)) continue;
       if (merge && pj == 0) continue;                       // merged heads: one staged feature-gradient tile, after the second head's chain
@@ -912,24 +936,27 @@ query_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_c
           commit(&acc_full[pj]);
         };
         // the last layer and its transpose: operands resident in shared memory (load_tables), A in the head's activation region
-        //   forward   out[128 x 16]  = h3[128 x 128] W4^T   (8 K steps x 3 MMAs, N = 16) -> accumulator columns 0-15
+        //   forward   out[128 x 16]  = h3[128 x 128] W4^T   (8 K steps x 3 MMAs, N = 16) -> eight partial sums in accumulator columns 16 ks .. 16 ks + 15
         //   backward  g3[128 x 128]  = g4[128 x 16]  W4     (1 K step  x 3 MMAs)        -> the whole accumulator region
         auto stage_w4f = [&](int pj) {
           tq_mbar_wait(tq_smem_u32(&act_full[pj]), (uint32_t)iact[pj] & 1u); ++iact[pj];
           tq_fence_after();
           const uint32_t fb = w4_base + pj * 2 * TB_W4F_PLANE, x_region = tmem_base + (2 + pj) * TQ_H, acc = tmem_base + pj * TQ_H;
+          // every K step accumulates into its OWN 16 columns (8 x 16 = the accumulator region; the epilogue adds the eight partial sums): 24
+          // N = 16 MMAs chained on one accumulator ran at ~250 cycles each -- a 16-column update is shorter than the tensor pipe's depth, so
+          // each waited for the previous one -- while here consecutive MMAs are independent (dependency distance 8)
           if (tq_elect_one()) {
 #pragma unroll
-            for (int ks = 0; ks < TQ_H / 16; ++ks) {
-              const int kg = ks * 16;
-              const uint32_t a_hi = x_region + (kg >> 5) * 32 + ((kg >> 4) & 1) * 8, a_lo = a_hi + 16;
-              const uint32_t boff = (uint32_t)((kg >> 6) * (16 * TQ_KC * 2));
-              const uint64_t adv = (uint64_t)((kg & 63) >> 3);
-              const uint64_t b_hi = tq_desc(fb + boff) + adv, b_lo = tq_desc(fb + TB_W4F_PLANE + boff) + adv;
-              tb_mma_ts(acc, a_hi, b_hi, ks == 0 ? 0u : 1u, TB_IDESC_N16);
-              tb_mma_ts(acc, a_hi, b_lo, 1u, TB_IDESC_N16);
-              tb_mma_ts(acc, a_lo, b_hi, 1u, TB_IDESC_N16);
-            }
+            for (int term = 0; term < 3; ++term)
+#pragma unroll
+              for (int ks = 0; ks < TQ_H / 16; ++ks) {
+                const int kg = ks * 16;
+                const uint32_t a_hi = x_region + (kg >> 5) * 32 + ((kg >> 4) & 1) * 8, a_lo = a_hi + 16;
+                const uint32_t boff = (uint32_t)((kg >> 6) * (16 * TQ_KC * 2));
+                const uint64_t adv = (uint64_t)((kg & 63) >> 3);
+                const uint64_t b_hi = tq_desc(fb + boff) + adv, b_lo = tq_desc(fb + TB_W4F_PLANE + boff) + adv;
+                tb_mma_ts(acc + 16 * ks, term == 2 ? a_lo : a_hi, term == 1 ? b_lo : b_hi, term == 0 ? 0u : 1u, TB_IDESC_N16);
+              }
           }
           __syncwarp();
           commit(&acc_full[pj]);
@@ -999,23 +1026,23 @@ query_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_c
     TB_STAMP();
     for (int pi = 0; pi < n_pairs; ++pi) {
     load_tables(pi);
-    if (interleave) {
 #pragma unroll 1
-      for (int st = 0; st < TB_NSTAGE; ++st)
-#pragma unroll
-        for (int pj = 0; pj < 2; ++pj) stage(pair_head(pi, pj), pj, 0, st, hs[pj], amax);
-    }
     for (int pj = 0; pj < 2; ++pj) {
       const int h = pair_head(pi, pj);
       if (h < 0) break;
-      if (!interleave) {
-        bool backward = true;
+      bool backward = true;
+      if (!interleave || pj == 0) {                        // (one call site: see the gather warps' copy of this loop)
+        const int nsj = interleave ? 2 * TB_NSTAGE : TB_NSTAGE;
 #pragma unroll 1
-        for (int st = 0; st < TB_NSTAGE && backward; ++st) backward = stage(h, pj, 0, st, hs[pj], amax);
-        if (!backward) continue;
-      } else if (pj == 0) {
-        continue;                                          // the feature gradients of both heads are drained together
+        for (int sj = 0; sj < nsj && backward; ++sj) {
+          const int st = interleave ? (sj >> 1) : sj, pq = interleave ? (sj & 1) : pj;
+          HeadState cur = pq ? hs[1] : hs[0];
+          backward = stage(pair_head(pi, pq), pq, 0, st, cur, amax);
+          if (pq) hs[1] = cur; else hs[0] = cur;
+        }
       }
+      if (interleave && pj == 0) continue;                 // the feature gradients of both heads are drained together
+      if (!backward) continue;
       // ---- drain gf (five 128-column groups) into the fp32 staging ring for the gather warps
       for (int u = 0; u < TQ_NCHUNK / 2; ++u, ++gfi) {
         const int gs = gfi % TB_NGF;

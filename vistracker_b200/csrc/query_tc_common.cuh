@@ -37,10 +37,15 @@ __device__ __forceinline__ bool tq_mbar_try_wait(uint32_t bar, uint32_t parity) 
 }
 // spin on try_wait (which itself suspends the thread for a hardware-bounded time); the deadlock guard counts polls instead of reading the
 // clock: the waiting warps share their scheduler's issue slots with the working ones, so the loop is kept to try_wait + add + branch
+// (out of line: inlined, the printf set-up of ~150 wait sites was a fifth of the backward kernel's code)
+static __device__ __noinline__ void tq_mbar_timeout() {
+  printf("vt query_tc: mbarrier timeout (block %d,%d thread %d)\n", blockIdx.x, blockIdx.y, threadIdx.x);
+  __trap();
+}
 __device__ __forceinline__ void tq_mbar_wait(uint32_t bar, uint32_t parity) {
   unsigned polls = 0;
   while (!tq_mbar_try_wait(bar, parity)) {
-    if (++polls > (1u << 27)) { printf("vt query_tc: mbarrier timeout (block %d,%d thread %d)\n", blockIdx.x, blockIdx.y, threadIdx.x); __trap(); }
+    if (++polls > (1u << 27)) tq_mbar_timeout();
   }
 }
 __device__ __forceinline__ void tq_tma_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {

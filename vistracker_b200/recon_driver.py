@@ -10,6 +10,7 @@ from typing import Callable, Dict, Optional
 
 import torch
 
+from ._lib import nvtx_range
 from .generator import GeneratorTriplaneVis
 from .geom import init_object_orientation
 from .recon_fit import SMPL_POSE_PRAMS_NUM, ReconFitterTriVisFull, SMPLParams
@@ -126,13 +127,14 @@ def fit_recon_batch(fitter: ReconFitterTriVisFull, generator: GeneratorTriplaneV
     dev = fitter.model.device
     B = data["images"].shape[0]
     reuse = reuse_generator_maps and not neural_only and generator.model is fitter.model
-    pc = generate_all(generator, data, on_mini_batch=on_mini_batch, mini_batch_size=mini_batch_size, keep_maps=reuse)
+    with nvtx_range("fit_recon_batch/generate_all"):
+        pc = generate_all(generator, data, on_mini_batch=on_mini_batch, mini_batch_size=mini_batch_size, keep_maps=reuse)
     if neural_only:
         return {"pc_generated": pc}
     if silhouette is None and fitter.scan is None:
         raise ValueError("the 'sil' phase needs a render.SilLossROI for the batch, or fitter.scan = (template vertices, faces) to build one")
     if not reuse:                                    # "need to run image filter again" (recon_fit_triplane.py:57-60)
-        with torch.no_grad():
+        with torch.no_grad(), nvtx_range("fit_recon_batch/filter"):
             filter_batch(fitter.model, data["images"], chunk=mini_batch_size)
     human_t = data["body_center"].to(dev).float()                                   # ReconFitterTriplane.get_smpl_translation (recon_fit_triplane.py:210-220):
                                                                                     # the pre-fit body centre, not the network's prediction
@@ -141,7 +143,8 @@ def fit_recon_batch(fitter: ReconFitterTriVisFull, generator: GeneratorTriplaneV
     dd = {"part_labels": fitter.part_labels.to(dev)[None].repeat(B, 1) if fitter.part_labels.dim() == 1 else fitter.part_labels.to(dev),
           "query_dict": query_dict, "body_kpts": body_kpts.float().to(dev),
           "pose_init": smpl.pose[:, 3:SMPL_POSE_PRAMS_NUM].detach().clone().to(dev)}
-    smpl, scale = fitter.optimize_smpl(smpl, dd, iter_for_kpts=1, iter_for_pose=1, iter_for_betas=1, **loop_kw)       # recon_fit_triplane.py:66
+    with nvtx_range("fit_recon_batch/optimize_smpl"):
+        smpl, scale = fitter.optimize_smpl(smpl, dd, iter_for_kpts=1, iter_for_pose=1, iter_for_betas=1, **loop_kw)   # recon_fit_triplane.py:66
     hist_smpl, stopped_smpl = fitter.last_hist, fitter.last_stopped
     # init_obj_fit_data (recon_fit_trivis_full.py:79-104): predicted centre relative to the optimised body centre, rotation from the PCA axes
     obj_t = (pc["object"]["centers"][:, 3:].to(dev) + human_t.to(dev)).detach().clone().requires_grad_(True)
@@ -156,6 +159,7 @@ def fit_recon_batch(fitter: ReconFitterTriVisFull, generator: GeneratorTriplaneV
     vis = pc["object"]["visibility"].to(dev).reshape(B) if occ_ratios is None else occ_ratios.to(dev)
     dd.update({"obj_R": obj_R, "obj_t": obj_t, "obj_s": obj_s, "objects": obj_points.to(dev)[None].repeat(B, 1, 1), "occ_ratios": vis,
                "silhouette": silhouette, "trans_init": obj_t.detach().clone(), "smpl": smpl, "images": data["images"]})
-    smpl, obj_R, obj_t = fitter.optimize_smpl_object(fitter.model, dd, noise_fn=noise_fn, **loop_kw)                     # recon_fit_triplane.py:106
+    with nvtx_range("fit_recon_batch/optimize_smpl_object"):
+        smpl, obj_R, obj_t = fitter.optimize_smpl_object(fitter.model, dd, noise_fn=noise_fn, **loop_kw)                 # recon_fit_triplane.py:106
     return {"pc_generated": pc, "smpl": smpl, "obj_R": fitter.final_rotation(obj_R), "obj_t": obj_t.detach(), "obj_s": obj_s, "hist_smpl": hist_smpl,
             "hist_obj": fitter.last_hist, "stopped_smpl": stopped_smpl, "stopped_obj": fitter.last_stopped, "smpl_scale": scale}
