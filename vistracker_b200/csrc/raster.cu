@@ -260,7 +260,10 @@ __global__ void __launch_bounds__(128) raster_bwd_kernel(const float* __restrict
             }
           }
         }
-        {                   // "in": pixels of this face that would become uncovered
+        // "in": pixels of this face that would become uncovered.  They are covered (alpha = 1: the index map names this face), so with a covered
+        // pixel beyond the edge (alpha_out = 1, every interior edge of the mesh) (a - alpha_out) is zero and the walk cannot contribute: skipped
+        // in the workspace mode (only silhouette edges walk); same result bit for bit
+        if (!(pcol && alpha_out >= 1.f)) {
           float d0_cross2;
           if ((d0 - p[0][0]) * (d0 - p[2][0]) < 0) d0_cross2 = (p[2][1] - p[0][1]) / (p[2][0] - p[0][0]) * (d0 - p[0][0]) + p[0][1];
           else d0_cross2 = (p[1][1] - p[2][1]) / (p[1][0] - p[2][0]) * (d0 - p[2][0]) + p[2][1];
