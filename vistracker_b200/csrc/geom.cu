@@ -137,27 +137,48 @@ __global__ void so3_bwd_kernel(const float* __restrict__ M, const float* __restr
 }
 
 // ------------------------------------------------------------------------------------------------ ragged Chamfer
-// One CTA per cloud pair n; x points of pair n are rows [xo[n], xo[n+1]) of the packed [sum, 3] array.
+// x points of pair n are rows [xo[n], xo[n+1]) of the packed [sum, 3] array.
 // loss += (1/N) * ( mean_i min_j |x_i - y_j|^2 + mean_j min_i |y_j - x_i|^2 )
+// Grid (N, CH_SPLIT): the query points of a pair -- both directions, chunks of 128 -- are dealt round-robin to the CH_SPLIT CTAs of the pair (one CTA per
+// pair left 52 SMs idle and 4 warps on the others: 0.48 ms for 96 pairs of 296 x 3000 points).  The other cloud is staged through shared memory in
+// tiles of CH_TILE points (one broadcast LDS.128 per candidate); every thread scans the candidates in increasing order with a strict `<`, i.e. the
+// first nearest neighbour, as before.
+constexpr int CH_SPLIT = 8, CH_TILE = 1024;
 __global__ void __launch_bounds__(128) chamfer_fwd_kernel(const float* __restrict__ x, const int* __restrict__ xo, const float* __restrict__ y,
                                                           const int* __restrict__ yo, int N, int* __restrict__ nn_x, int* __restrict__ nn_y,
                                                           float* __restrict__ loss) {
+  __shared__ float4 tile[CH_TILE];
   const int n = blockIdx.x;
   const int x0 = xo[n], x1 = xo[n + 1], y0 = yo[n], y1 = yo[n + 1];
+  const int cx = (x1 - x0 + 127) >> 7, cy = (y1 - y0 + 127) >> 7;       // chunks of 128 query points per direction
   float part = 0.f;
-  for (int dir = 0; dir < 2; ++dir) {
+  for (int ch = blockIdx.y; ch < cx + cy; ch += gridDim.y) {
+    const int dir = ch < cx ? 0 : 1;
     const float* a = dir == 0 ? x : y;  const float* b = dir == 0 ? y : x;
     const int a0 = dir == 0 ? x0 : y0, a1 = dir == 0 ? x1 : y1, b0 = dir == 0 ? y0 : x0, b1 = dir == 0 ? y1 : x1;
     int* nn = dir == 0 ? nn_x : nn_y;
     const float scale = (a1 > a0) ? 1.f / (float)(a1 - a0) : 0.f;
-    for (int i = a0 + threadIdx.x; i < a1; i += blockDim.x) {
-      const float px = a[i * 3], py = a[i * 3 + 1], pz = a[i * 3 + 2];
-      float best = 3.4e38f; int bj = -1;
-      for (int j = b0; j < b1; ++j) {
-        const float dx = px - b[j * 3], dy = py - b[j * 3 + 1], dz = pz - b[j * 3 + 2];
-        const float d = dx * dx + dy * dy + dz * dz;
-        if (d < best) { best = d; bj = j; }
+    const int i = a0 + (dir == 0 ? ch : ch - cx) * 128 + threadIdx.x;
+    const bool live = i < a1;
+    float px = 0.f, py = 0.f, pz = 0.f;
+    if (live) { px = a[i * 3]; py = a[i * 3 + 1]; pz = a[i * 3 + 2]; }
+    float best = 3.4e38f; int bj = -1;
+    for (int t0 = b0; t0 < b1; t0 += CH_TILE) {
+      const int nt = min(CH_TILE, b1 - t0);
+      __syncthreads();                                     // the previous tile (or chunk) has been read by every thread
+      for (int j = threadIdx.x; j < nt; j += 128) tile[j] = make_float4(b[(t0 + j) * 3], b[(t0 + j) * 3 + 1], b[(t0 + j) * 3 + 2], 0.f);
+      __syncthreads();
+      if (live) {
+#pragma unroll 4
+        for (int j = 0; j < nt; ++j) {
+          const float4 q = tile[j];
+          const float dx = px - q.x, dy = py - q.y, dz = pz - q.z;
+          const float d = dx * dx + dy * dy + dz * dz;
+          if (d < best) { best = d; bj = t0 + j; }
+        }
       }
+    }
+    if (live) {
       nn[i] = bj;
       if (bj >= 0) part += best * scale;
     }
@@ -338,7 +359,7 @@ int vt_chamfer_fwd(const float* x, const int* x_off, const float* y, const int* 
   if (N <= 0) return 0;
   cudaError_t e = cudaMemsetAsync(loss, 0, sizeof(float), (cudaStream_t)stream);
   if (e != cudaSuccess) return cuda_fail(e, "vt_chamfer_fwd memset");
-  chamfer_fwd_kernel<<<N, 128, 0, (cudaStream_t)stream>>>(x, x_off, y, y_off, N, nn_x, nn_y, loss);
+  chamfer_fwd_kernel<<<dim3(N, CH_SPLIT), 128, 0, (cudaStream_t)stream>>>(x, x_off, y, y_off, N, nn_x, nn_y, loss);
   VT_CHECK_LAUNCH("vt_chamfer_fwd");
   return 0;
 }
