@@ -22,6 +22,14 @@ def rel_err(a, b):
     return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
 
 
+def elementwise_err(a, b):
+    """max over the elements of |a - b| / max(|b|, 1e-3 * max|b|) -- the per-element form SURVEY.md 7 proposes
+    (|a - b| <= tol * max(|b|, 1e-3 * ||b||_inf)); reported next to ``rel_err`` by the parity tests that state both."""
+    a = np.asarray(a, dtype=np.float64); b = np.asarray(b, dtype=np.float64)
+    den = np.maximum(np.abs(b), 1e-3 * max(np.abs(b).max(), 1e-30))
+    return float((np.abs(a - b) / den).max())
+
+
 @pytest.fixture(scope="session")
 def golden():
     def load(name):

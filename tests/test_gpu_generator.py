@@ -77,3 +77,37 @@ def test_gen_pc_batch_control_flow_matches_restatement(setup):
     assert close(ours["pca_axis"], ref["pca_axis"]) and close(ours["visibility"], ref["visibility"])
     assert torch.isnan(ours["centers"][:, :3]).all() and close(ours["centers"][:, 3:], ref["centers"][:, 3:])
     assert (ours["parts"] == ref["parts"]).float().mean() > 0.99
+
+
+def test_gen_pc_batch_resampling_with_a_selective_threshold(setup):
+    """The resampling control flow of gen_pc_batch (generator.py:149-215) at a threshold that about half of the points pass -- per-frame
+    survivor counts, the stable survivor order, randint / randn draws in the reference's order, several rounds, compose_outdict.  With a
+    random-init UDF a point within rounding of the threshold would flip its mask bit and, through the next randint range, everything after
+    it, so the network is taken out of the comparison: BOTH sides see the oracle's predictions (our approx_surface is replaced by the CPU
+    restatement's), and then every output must be identical.  (The numerics of approx_surface have their own tests above.)"""
+    from vistracker_b200.generator import GeneratorTriplaneVis
+    net, sd, maps, points, crop, body = setup
+    torch.manual_seed(123)
+    init = torch.rand(2, 300, 3).float() * torch.tensor([2.0, 3.0, 1.2]) - torch.tensor([1.0, 1.5, 0.6]) + body.unsqueeze(1)
+    _, preds0 = G.approx_surface(sd, maps, init, 1, crop, body, CAM, 1, 2.0)
+    fv = float(torch.clamp(preds0[0][:, 1], max=2.0).median())            # about half of the first round's points survive
+    gen = GeneratorTriplaneVis(net, threshold=2.0, filter_val=fv)
+    calls = []
+
+    def oracle_surface(samples, num_steps, query_input, df_type):
+        pts, preds = G.approx_surface(sd, maps, samples.detach().cpu(), num_steps, crop, body, CAM, 0 if df_type == "human" else 1, 2.0)
+        calls.append(samples.shape[1])
+        return pts.cuda(), tuple(p.cuda() for p in preds)
+
+    gen.approx_surface = oracle_surface
+    torch.manual_seed(7)
+    ours = gen.gen_pc_batch("object", init.cuda(), 25000, {"crop_center": crop, "body_center": body}, num_steps=1)
+    torch.manual_seed(7)
+    ref = G.gen_pc_batch(sd, maps, "object", init, 25000, crop, body, CAM, num_steps=1, filter_val=fv)
+    assert len(calls) >= 3 and calls[0] == 300 and calls[1] == 20000      # several rounds: the first on the grid samples, then 20 000 resampled
+    assert ours["points"].shape == ref["points"].shape and ours["points"].shape[1] >= 25000
+    for k in ("points", "parts"):                                          # selections and copies: bit for bit
+        assert torch.equal(torch.as_tensor(ours[k]).cpu(), torch.as_tensor(ref[k])), k
+    for k in ("pca_axis", "visibility"):                                   # means over the kept samples (device vs host summation order)
+        assert rel_err(torch.as_tensor(ours[k]).cpu(), ref[k]) < 1e-6, k
+    assert torch.isnan(ours["centers"][:, :3]).all() and rel_err(ours["centers"][:, 3:].cpu(), ref["centers"][:, 3:]) < 1e-6

@@ -84,6 +84,30 @@ def test_batch_matches_oracle(net):
         assert rel_err(o.cpu(), r) < TOL
 
 
+def test_config2_shape_matches_oracle(net):
+    """BASELINE config 2 -- the shape bench.py's C2 numbers are quoted on: 8 frames of 512 x 512, 10 000 query points per frame.  Frames 0 and 5
+    of the batch are compared with the CPU oracle head by head, in both tolerance forms: max|a - b| / max|b| (north_star's 1e-4) and the
+    per-element form of SURVEY.md 7 (denominator max(|b|, 1e-3 max|b|))."""
+    from conftest import elementwise_err
+    sd = synthetic_state_dict(DIMS, seed=0)
+    images, points, crop, body = synthetic_frames(8, size=512, seed=33, n_points=10000, jitter=True)
+    net.filter(images.cuda())
+    net.query(points.cuda(), crop_center=crop.cuda(), body_center=body.cuda())
+    ours = [o.cpu() for o in net.get_preds()]
+    worst = {}
+    for f in (0, 5):
+        with torch.no_grad():
+            maps = R.sif_filter(sd, images[f:f + 1])
+            ref = R.sif_query(sd, maps, points[f:f + 1], crop[f:f + 1], body[f:f + 1], CAM)
+        for name, o, r in zip(("df", "pca", "parts", "centers", "vis"), ours, ref):
+            e1, e2 = rel_err(o[f:f + 1], r), elementwise_err(o[f:f + 1], r)
+            worst[name] = (max(worst.get(name, (0, 0))[0], e1), max(worst.get(name, (0, 0))[1], e2))
+    print("C2 shape, worst (max-rel, element-wise) per head:", {k: (f"{a:.2e}", f"{b:.2e}") for k, (a, b) in worst.items()})
+    for name, (e1, e2) in worst.items():
+        assert e1 < TOL, (name, e1)
+        assert e2 < 1e-4, (name, e2)                       # north_star's 1e-4, per element
+
+
 def test_query_edge_cases(net):
     images, points, crop, body = synthetic_frames(1, size=64, seed=3, n_points=33)
     net.filter(images.cuda())
