@@ -96,14 +96,29 @@ class GeneratorTriplaneVis:
         sample_num = 20000
         it, samples_count = 0, 0
         samples = samples_init.clone().to(self.device)
+        n_init = samples_init.shape[1]
+        samples_init_dev = samples_init.to(self.device)
         while samples_count < num_points:
             samples_surface, preds = self.approx_surface(samples, num_steps, query_input, df_type)
             df_target = torch.clamp(preds[0][:, df_idx, :], max=self.threshold)
             mask = (df_target < self.filter_val) & (samples_surface[:, :, 2] > 1.0)
+            counts_dev = mask.sum(1)
+            order = torch.argsort((~mask).to(torch.uint8), dim=1, stable=True)
+            # While the device works on the launches above: the noise of the resampling below, drawn from torch's CPU generator in the
+            # reference's order (per frame: randint(high, (1, sample_num)), then randn(1, sample_num, 3)).  The noise does not depend on the
+            # survivor counts, the randint range does -- but randint consumes the same generator outputs whatever its range (one 32-bit draw
+            # per element below 2^32), so a dummy randint advances the generator here and the real one is drawn after the counts are known,
+            # from the state saved in front of it.  Identical samples for equal seeds, and the 0.22 ms per frame of randn no longer sit
+            # between the round's host sync and the next round's first launch.
+            states, noise = [], torch.empty(batch_size, sample_num, 3, pin_memory=True)
+            for i in range(batch_size):
+                states.append(torch.get_rng_state())
+                torch.randint(2, (1, sample_num))
+                noise[i] = torch.randn(1, sample_num, 3)[0]
+            final_state = torch.get_rng_state()
             # ONE host sync per round: the per-frame counts.  `order` lists the surviving sample positions of every frame first (stable),
             # so frame i's survivors are order[i, :counts[i]] -- the boolean-mask indexing of the reference without a sync per frame
-            counts = mask.sum(1).cpu().tolist()
-            order = torch.argsort((~mask).to(torch.uint8), dim=1, stable=True)
+            counts = counts_dev.cpu().tolist()
             if it > 0:
                 for i in range(batch_size):
                     keep = order[i, :counts[i]]
@@ -113,19 +128,20 @@ class GeneratorTriplaneVis:
                 samples_count += int(np.min(counts))
                 if not mute:
                     print("{} points".format(samples_count))
+            indices = torch.empty(batch_size, sample_num, dtype=torch.int64, pin_memory=True)
+            for i in range(batch_size):
+                torch.set_rng_state(states[i])
+                indices[i] = torch.randint(counts[i] if counts[i] > 1 else n_init, (1, sample_num))[0]
+            torch.set_rng_state(final_state)
+            indices_dev, noise_dev = indices.to(self.device, non_blocking=True), noise.to(self.device, non_blocking=True)
             samples_new = []
             for i in range(batch_size):
-                # the random draws come from torch's CPU generator in the reference's order and shapes (identical samples for equal seeds)
-                if counts[i] > 1:
-                    indices = torch.randint(counts[i], (1, sample_num))
-                    noise = (self.threshold / 3) * torch.randn(1, sample_num, 3)
-                    src = samples[i].index_select(0, order[i, :counts[i]].index_select(0, indices[0].to(self.device, non_blocking=True)))
-                    samples_i = src.unsqueeze(0) + noise.to(self.device, non_blocking=True)
-                else:
-                    indices = torch.randint(samples_init.shape[1], (1, sample_num))
-                    noise = 0.5 * torch.randn(1, sample_num, 3)
-                    src = samples_init[i].to(self.device).index_select(0, indices[0].to(self.device, non_blocking=True))
-                    samples_i = src.unsqueeze(0) + noise.to(self.device, non_blocking=True)
+                if counts[i] > 1:       # around the survivors: sigma = threshold / 3 (the product is formed in fp32 as on the host)
+                    src = samples[i].index_select(0, order[i, :counts[i]].index_select(0, indices_dev[i]))
+                    samples_i = src.unsqueeze(0) + ((self.threshold / 3) * noise_dev[i]).unsqueeze(0)
+                else:                   # no survivor: around the initial grid samples, sigma = 0.5
+                    src = samples_init_dev[i].index_select(0, indices_dev[i])
+                    samples_i = src.unsqueeze(0) + (0.5 * noise_dev[i]).unsqueeze(0)
                 samples_new.append(samples_i)
             samples = torch.cat(samples_new, 0).detach()
             it += 1
