@@ -239,11 +239,26 @@ __global__ void __launch_bounds__(128) raster_bwd_kernel(const float* __restrict
           const int d1_limit = direction > 0 ? is - 1 : 0;
           const int d1_from = max(min(d1_out, d1_limit), 0);
           int d1_to = min(max(d1_out, d1_limit), is - 1);
-          if (pcol) {                  // no active pixel in the range: every iteration below would `continue`
+          int d1_first = d1_from;
+          if (pcol) {
+            // Only ACTIVE pixels (alpha == 0, g_alpha < 0) pass the `diff_grad > 0` test below.  None in the range: nothing to walk.  Otherwise the
+            // walk is clipped to [first active, last active] by two binary searches on the (monotone) prefix counts: in the fitters the active
+            // pixels are the band of the target mask the render does not cover yet, while the range runs to the image border (a pixel-by-pixel
+            // walk of up to `is` dependent loads was 60 % of this kernel).  Skipped pixels contribute nothing: same sums, same order.
             const unsigned short* P = (axis == 0 ? pcol : prow) + ((size_t)bn * is + d0) * (is + 1);
-            if (P[d1_to + 1] == P[d1_from]) d1_to = d1_from - 1;
+            const unsigned base = P[d1_from], top = P[d1_to + 1];
+            if (top == base) {
+              d1_to = d1_from - 1;
+            } else {
+              int lo = d1_from, hi = d1_to;
+              while (lo < hi) { const int mid = (lo + hi) >> 1; if (P[mid + 1] > base) hi = mid; else lo = mid + 1; }
+              d1_first = lo;
+              hi = d1_to;
+              while (lo < hi) { const int mid = (lo + hi) >> 1; if (P[mid + 1] >= top) hi = mid; else lo = mid + 1; }
+              d1_to = lo;
+            }
           }
-          for (int d1 = d1_from; d1 <= d1_to; ++d1) {
+          for (int d1 = d1_first; d1 <= d1_to; ++d1) {
             const float a = axis == 0 ? A(d1, d0) : A(d0, d1);
             const float ga = axis == 0 ? GA(d1, d0) : GA(d0, d1);
             const float diff_grad = (a - alpha_in) * ga;
