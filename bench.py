@@ -265,6 +265,8 @@ class Dist:
         self.dev = torch.device("cuda", self.local)
         self.dist = dist
         if self.world > 1:
+            # NCCL writes its version banner (NCCL_DEBUG=VERSION in this image) to stdout: keep stdout for the ONE JSON line
+            os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
             dist.init_process_group("nccl", device_id=self.dev)
 
     def barrier(self):
