@@ -184,3 +184,37 @@ def test_phase_schedules_follow_the_reference_chains():
     assert o[45][:2] == ("joint", True) and abs(o[45][2] - 31 / 3) < 1e-12 and o[46][:2] == ("joint", False)
     o = F.object_phase_schedule(2, 0, 1, 3)              # no silhouette phase: `it == it_obj and it != it_obj + it_sil` is False, joint starts at it_obj
     assert [p for p, _, _ in o] == ["object only"] * 2 + ["joint"] * 4 and o[2][1]
+
+
+def test_generator_random_stream_trick_reproduces_the_reference_draw_order():
+    """gen_pc_batch draws the resampling noise BEFORE the survivor counts are known (generator.py of this package): a dummy randint advances
+    torch's CPU generator exactly like the reference's ``randint(high, (1, n))`` whatever ``high`` is (one 32-bit draw per element below 2^32),
+    the real index draw is made later from the generator state saved in front of it, and the state after the round is restored.  The tensors
+    and the generator state afterwards must equal the reference's sequential order (recon/gen/generator.py:185-205: per frame randint, randn)."""
+    import torch
+    n, highs = 4000, [17, 19999, 30000, 2, 123456, 1 << 20]
+
+    def reference_order():
+        torch.manual_seed(11)
+        out = [(torch.randint(h, (1, n)), torch.randn(1, n, 3)) for h in highs]
+        return out, torch.rand(5)
+
+    def early_noise_order():
+        torch.manual_seed(11)
+        states, noise = [], []
+        for _ in highs:                                   # before the counts are known
+            states.append(torch.get_rng_state())
+            torch.randint(2, (1, n))
+            noise.append(torch.randn(1, n, 3))
+        final = torch.get_rng_state()
+        idx = []
+        for s, h in zip(states, highs):                   # after: the real ranges
+            torch.set_rng_state(s)
+            idx.append(torch.randint(h, (1, n)))
+        torch.set_rng_state(final)
+        return list(zip(idx, noise)), torch.rand(5)
+
+    a, ta = reference_order()
+    b, tb = early_noise_order()
+    assert all(torch.equal(x[0], y[0]) and torch.equal(x[1], y[1]) for x, y in zip(a, b))
+    assert torch.equal(ta, tb)                            # the generator continues as in the reference
