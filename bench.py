@@ -100,6 +100,18 @@ class ClockSampler:
 # =====================================================================================================================================
 # CPU side (oracle/): cpu_baseline leg and --impl reference only
 # =====================================================================================================================================
+BODY = os.environ.get("VT_BENCH_BODY", "surface")             # "surface" (default) | "cloud" (the Gaussian point cloud of the earlier bench lines)
+BODY_NOTE = {"surface": "human-shaped synthetic SMPL-H (synth_smpl.synthetic_smplh_surface: closed 1.7 m surface, vertices in surface order, proximity "
+                        "skinning) -- SMPLH_male.pkl itself is licensed and absent",
+             "cloud": "synth_smpl.synthetic_smplh: Gaussian point cloud in random vertex order (the body of the bench lines up to profiles/r02k)"}
+
+
+def body_model(kind=None):
+    """The SMPL-H stand-in of the C4 workload (same V = 6890, J = 52, buffers and work per vertex either way; only where the vertices lie differs)."""
+    from vistracker_b200.synth_smpl import synthetic_smplh, synthetic_smplh_surface
+    return synthetic_smplh_surface(seed=3) if (kind or BODY) == "surface" else synthetic_smplh(seed=3)
+
+
 def c4_expected_steps():
     """Step counts of the seeded C4 batch as measured on the B200 (profiles/r02_c4_steps.json, written by a bench run) -- the CPU arm cannot
     know where the early stops fire without running hours of CPU optimisation; without the file the iteration caps are used."""
@@ -124,12 +136,11 @@ def cpu_c4_sample(seed=4):
     from tools_inputs import load_assets
     from vistracker_b200 import default_options, resolve_dims
     from vistracker_b200.synth import synthetic_recon_batch, synthetic_state_dict
-    from vistracker_b200.synth_smpl import synthetic_smplh
     n = 4                                                     # frames of the sample batch (the temporal terms need >= 4)
     a, reg = load_assets()
     d = synthetic_recon_batch(n, size=SIZE, seed=seed)
     sd = synthetic_state_dict(resolve_dims(default_options()), seed=0)
-    model = synthetic_smplh(seed=3)
+    model = body_model()
     t = {}
     t0 = time.perf_counter()
     with torch.no_grad():
@@ -312,7 +323,6 @@ class C4:
         from vistracker_b200.recon_fit import Priors, ReconFitterTriVisFull
         from vistracker_b200.smpl import LandmarkRegressor, SMPL_Layer
         from vistracker_b200.synth import synthetic_recon_batch, synthetic_state_dict
-        from vistracker_b200.synth_smpl import synthetic_smplh
         dev = D.dev
         self.D, self.dev, self.frames = D, dev, frames
         a, reg = load_assets()
@@ -321,7 +331,7 @@ class C4:
         self.net = CHORETriplaneVisibility(default_options(), device=dev).eval()
         self.net.load_state_dict(self.sd)
         self.net.defer_checks = True
-        model = synthetic_smplh(seed=3)
+        model = body_model()
         self.layer = SMPL_Layer.from_buffers(model, model["parents"], dev)
         self.reg = LandmarkRegressor(np.stack([reg[0], reg[1]]), reg[2], reg[3], dev)
         h = synthetic_recon_batch(frames, size=SIZE, seed=seed + 100 * D.rank)
@@ -396,26 +406,43 @@ def query_roofline(c4: C4, share_launches, step_ms):
     w = torch.tensor([30.0 ** 2, 0.05 ** 2], device=dev)   # the launch the optimize_smpl step replays: both heads merged, weights from device words
     run = lambda: net.enqueue_query_losses_merged(verts, cc, bc, 0, 0.1, labels, w.data_ptr(), 1.0 / (B * V), w.data_ptr() + 4, 1.0 / B,
                                                   vals_df, vals_ce, g_df)
-    for _ in range(3):
-        run()
     n = 20
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    torch.cuda.synchronize()
-    e0.record()
-    for _ in range(n):
-        run()
-    e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / n
+
+    def timed_launches():
+        for _ in range(3):
+            run()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(n):
+            run()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n
+    ms = timed_launches()
     pk, src = peaks()
     nbytes = QUERY_LOSS_BYTES_PER_POINT * B * V
     achieved = nbytes / (ms * 1e-3) / 1e9
+    # the same launch on the OTHER synthetic body at the batch's initial parameters (continuity with the earlier bench lines: where the vertices
+    # lie decides how well the taps of a 128-point tile share cache lines, nothing else differs)
+    other = "cloud" if BODY == "surface" else "surface"
+    try:
+        from vistracker_b200.smpl import SMPL_Layer
+        mo = body_model(other)
+        lo = SMPL_Layer.from_buffers(mo, mo["parents"], dev)
+        with torch.no_grad():
+            vo = lo(c4.devd["pose"], c4.devd["betas"], c4.devd["trans"])[0].detach().contiguous()
+        verts.copy_(vo)
+        ms_o = timed_launches()
+        other_body = {"body": BODY_NOTE[other], "ms_per_launch": ms_o, "frac": nbytes / (ms_o * 1e-3) / 1e9 / pk["hbm_gbs"]}
+    except Exception as ex:              # noqa: BLE001
+        other_body = {"error": f"{type(ex).__name__}: {ex}"}
     return {"bound": "hbm", "kernel": "query_bwd_tc_kernel, fused-loss mode with merged heads (vt_query_losses_merged_tc) on 96 x 6890 vertices: 1 launch per optimize_smpl step",
             "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": achieved / pk["hbm_gbs"],
             "traffic": NCU_QUERY_LOSS_DRAM_BYTES_PER_POINT * B * V,
             "traffic_note": "dram__bytes_read + write of one ncu --set full capture of this launch (profiles/r02h_query_loss_merged_final_ncu_summary.txt: 559.3 MB at 96 x 6890 points), scaled per point; "
                             "far BELOW the algorithmic bytes: the bilinear taps are L1- (71 %) and L2-served (88 %), the 8 maps of a frame are 71 MB and the vertices of one body touch a small part",
-            "algorithmic_bytes_per_launch": nbytes, "bytes_per_point": QUERY_LOSS_BYTES_PER_POINT, "ms_per_launch": ms,
+            "algorithmic_bytes_per_launch": nbytes, "bytes_per_point": QUERY_LOSS_BYTES_PER_POINT, "ms_per_launch": ms, "body": BODY_NOTE[BODY], "other_body": other_body,
             "tensor_tflops": QUERY_LOSS_FLOP_PER_POINT * B * V / (ms * 1e-3) / 1e12, "launches_per_step": share_launches,
             "share_of_step": share_launches * ms / step_ms, "peak_source": f"{src} HBM copy bandwidth",
             "timing": "CUDA events around 20 back-to-back launches on the launching stream after the timed region"}
@@ -552,12 +579,11 @@ def c4_accuracy(D: Dist):
     from vistracker_b200.render import SilLossROI
     from vistracker_b200.smpl import LandmarkRegressor, SMPL_Layer
     from vistracker_b200.synth import synthetic_recon_batch, synthetic_state_dict
-    from vistracker_b200.synth_smpl import synthetic_smplh
     dev, n, S = D.dev, 4, 64
     a, reg = load_assets()
     dims = resolve_dims(default_options())
     sd = synthetic_state_dict(dims, seed=0)
-    model = synthetic_smplh(seed=3)
+    model = body_model()
     d = synthetic_recon_batch(n, size=S, seed=9, n_obj_points=600, obj_rings=6, obj_segments=8)
     net = CHORETriplaneVisibility(default_options(), device=dev).eval()
     net.load_state_dict(sd)
@@ -707,7 +733,7 @@ def run_ours(args):
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": D.world, "steps": args.steps, "warmup": warmup, "ms_per_step": step_ms,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": C4_WORKLOAD, "frames_per_step_per_gpu": c4.frames, "global_frames_per_step": D.world * c4.frames,
+            "config": {"workload": C4_WORKLOAD, "body_model": BODY_NOTE[BODY], "frames_per_step_per_gpu": c4.frames, "global_frames_per_step": D.world * c4.frames,
                        "sequence_1500_frames": "16 such batches; whole reference batches per rank (SURVEY.md 8(e))",
                        "parallelism": f"frame-batch-parallel x{D.world}, one NCCL all-gather of the [96,169] + [96,13] trajectories per step" if D.world > 1 else "1 GPU",
                        "l2": "working set per step: 0.8 GB of images + 6.8 GB of feature maps for 96 frames, far larger than L2",

@@ -7,7 +7,7 @@ import torch
 
 from conftest import ROOT, rel_err
 from oracle.smpl_ref import landmarks, smpl_forward
-from vistracker_b200.synth_smpl import synthetic_motion, synthetic_smplh
+from vistracker_b200.synth_smpl import synthetic_motion, synthetic_smplh, synthetic_smplh_surface
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-4
@@ -65,6 +65,31 @@ def test_matches_oracle_fp64(layer, B, scale, with_offsets):
     smpl_forward(model, *ref2, None, scale)[1].sum().backward()
     for a, b in zip(ins2, ref2):
         assert rel_err(a.grad.cpu(), b.grad) < TOL
+
+
+def test_surface_skinned_body_matches_oracle_fp64():
+    """The human-shaped model (skinning follows the surface: the lanes of a warp share their joints, so smpl_skin_bwd_kernel sums whole groups with
+    a butterfly before ONE lane touches the shared accumulators -- the random model above only takes the direct-atomics path) against the fp64
+    restatement, forward and backward, B = 40 with a gradient on the vertices only and on vertices + joints."""
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    from vistracker_b200.smpl import SMPL_Layer
+    model = synthetic_smplh_surface(seed=3)
+    L = SMPL_Layer.from_buffers(model, model["parents"], "cuda:0")
+    B = 40
+    pose, betas, trans = synthetic_motion(B, seed=321)
+    for with_joints in (False, True):
+        ref_in = [t.double().requires_grad_(True) for t in (pose, betas, trans)]
+        rv, rj, _, _ = smpl_forward(model, *ref_in, None, 1.0)
+        ins = [t.cuda().requires_grad_(True) for t in (pose, betas, trans)]
+        verts, jtr, _, _ = L(*ins)
+        assert rel_err(verts.detach().cpu(), rv.detach()) < 1e-5 and rel_err(jtr.detach().cpu(), rj.detach()) < 1e-5
+        gen = torch.Generator().manual_seed(11)
+        gv, gj = torch.randn(B, 6890, 3, generator=gen), torch.randn(B, 52, 3, generator=gen) * float(with_joints)
+        ((rv * gv.double()).sum() + (rj * gj.double()).sum()).backward()
+        ((verts * gv.cuda()).sum() + (jtr * gj.cuda()).sum()).backward()
+        for a, b in zip(ins, ref_in):
+            assert rel_err(a.grad.cpu(), b.grad) < TOL
 
 
 def test_body25_landmarks_with_the_reference_asset(layer):

@@ -218,3 +218,29 @@ def test_generator_random_stream_trick_reproduces_the_reference_draw_order():
     b, tb = early_noise_order()
     assert all(torch.equal(x[0], y[0]) and torch.equal(x[1], y[1]) for x, y in zip(a, b))
     assert torch.equal(ta, tb)                            # the generator continues as in the reference
+
+
+def test_human_shaped_synthetic_body_model_has_the_structure_of_smplh():
+    """synth_smpl.synthetic_smplh_surface (the body of the bench's C4 batch): SMPL-H buffer shapes, a regressor and skinning weights with rows
+    summing to one and 4 joints per vertex, vertices that are neighbours in index order, and -- posed by the bench's own motion through the
+    CPU restatement of SMPL_Layer.forward -- a body that stays inside the triplane around the batch's body centre."""
+    from oracle.smpl_ref import smpl_forward
+    from vistracker_b200.synth import synthetic_recon_batch
+    from vistracker_b200.synth_smpl import NUM_JOINTS, NUM_VERTS, synthetic_smplh, synthetic_smplh_surface
+    m, ref = synthetic_smplh_surface(seed=3), synthetic_smplh(seed=3)
+    assert set(m) == set(ref)
+    for k in ref:
+        if torch.is_tensor(ref[k]):
+            assert m[k].shape == ref[k].shape and m[k].dtype == ref[k].dtype, k
+    assert m["parents"] == ref["parents"]
+    assert torch.allclose(m["th_J_regressor"].sum(1), torch.ones(NUM_JOINTS), atol=1e-5)
+    assert torch.allclose(m["th_weights"].sum(1), torch.ones(NUM_VERTS), atol=1e-5) and int((m["th_weights"] > 0).sum(1).max()) == 4
+    assert int(m["th_faces"].max()) == NUM_VERTS - 1 and int(m["th_faces"].min()) == 0
+    h = synthetic_recon_batch(8, size=16, seed=4)
+    verts, jtr = smpl_forward(m, h["pose"], h["betas"], h["trans"])[:2]
+    assert torch.isfinite(verts).all()
+    c = verts - h["body_center"][:, None]
+    assert float(c.abs().max()) < 1.0                                             # every tap of every vertex inside the three triplane views
+    assert float((jtr[:, 0] - h["body_center"]).abs().max()) < 0.1               # the root joint rides on the body centre
+    step = (verts[:, 1:] - verts[:, :-1]).norm(dim=-1).median()
+    assert float(step) < 0.05                                                    # consecutive vertices are surface neighbours (0.5 m for the cloud)

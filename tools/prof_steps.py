@@ -21,7 +21,7 @@ from vistracker_b200.recon_steps import ObjectFitStep, SmplRefineStep  # noqa: E
 from vistracker_b200.render import SilLossROI  # noqa: E402
 from vistracker_b200.smpl import LandmarkRegressor, SMPL_Layer  # noqa: E402
 from vistracker_b200.synth import synthetic_recon_batch, synthetic_state_dict  # noqa: E402
-from vistracker_b200.synth_smpl import synthetic_smplh  # noqa: E402
+from vistracker_b200.synth_smpl import synthetic_smplh, synthetic_smplh_surface  # noqa: E402
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 96
 N = 10
@@ -30,7 +30,7 @@ a, reg = load_assets()
 net = CHORETriplaneVisibility(default_options(), device=dev).eval()
 net.load_state_dict(synthetic_state_dict(resolve_dims(default_options()), seed=0))
 net.defer_checks = True
-model = synthetic_smplh(seed=3)
+model = synthetic_smplh(seed=3) if os.environ.get("VT_BENCH_BODY", "surface") == "cloud" else synthetic_smplh_surface(seed=3)   # as bench.py
 layer = SMPL_Layer.from_buffers(model, model["parents"], dev)
 body25 = LandmarkRegressor(np.stack([reg[0], reg[1]]), reg[2], reg[3], dev)
 h = synthetic_recon_batch(B, seed=4)

@@ -13,6 +13,9 @@
 //
 // Forward is tiled: a CTA owns a 16x16 pixel tile, culls the face list against the tile in order-preserving chunks (ballot
 // compaction into shared memory) and only then runs the per-pixel tests -- upstream loops every pixel over every face.
+// (Measured, profiles/r02l_raster_fwd_ncu.txt: 0.33 ms for the 96 silhouettes of a batch is NOT the culling -- a 64x64 super-tile variant that
+// culled once per 16 tiles took the same 0.33 ms -- but the depth of the covered pixels: ten IEEE divisions per covered (pixel, face) pair,
+// executed by warps in which a small face leaves most lanes idle.  The arithmetic is upstream's and stays as it is.)
 #include "common.cuh"
 #include "vt_internal.h"
 
@@ -79,6 +82,25 @@ __global__ void __launch_bounds__(RCHUNK) raster_bbox_kernel(const float* __rest
   }
 }
 
+// One pixel centre against one counter-clockwise face q = (x, y, z) x 3 in NDC: the three edge tests, then the depth 1 / sum(w_k / z_k) with the
+// clamped, renormalised barycentric weights; false when the pixel is not covered or the depth is outside (near, far).  ONE statement of the
+// arithmetic for both forward kernels (the nearest-face decision compares these depths between faces).
+__device__ __forceinline__ bool raster_cover(const float* q, float xp, float yp, float& zp) {
+  if (((yp - q[1]) * (q[3] - q[0]) < (xp - q[0]) * (q[4] - q[1])) ||
+      ((yp - q[4]) * (q[6] - q[3]) < (xp - q[3]) * (q[7] - q[4])) ||
+      ((yp - q[7]) * (q[0] - q[6]) < (xp - q[6]) * (q[1] - q[7])))
+    return false;
+  const float den = q[6] * (q[1] - q[4]) + q[0] * (q[4] - q[7]) + q[3] * (q[7] - q[1]);
+  float w0 = ((q[4] - q[7]) * xp + (q[6] - q[3]) * yp + (q[3] * q[7] - q[6] * q[4])) / den;
+  float w1 = ((q[7] - q[1]) * xp + (q[0] - q[6]) * yp + (q[6] * q[1] - q[0] * q[7])) / den;
+  float w2 = ((q[1] - q[4]) * xp + (q[3] - q[0]) * yp + (q[0] * q[4] - q[3] * q[1])) / den;
+  w0 = fminf(fmaxf(w0, 0.f), 1.f); w1 = fminf(fmaxf(w1, 0.f), 1.f); w2 = fminf(fmaxf(w2, 0.f), 1.f);
+  const float ws = fmaxf(w0 + w1 + w2, 1e-10f);
+  w0 /= ws; w1 /= ws; w2 /= ws;
+  zp = 1.f / (w0 / q[2] + w1 / q[5] + w2 / q[8]);
+  return !(zp <= R_NEAR || zp >= R_FAR);
+}
+
 __global__ void __launch_bounds__(RT * RT) raster_fwd_kernel(const float* __restrict__ faces_ndc, int nf, int is,
                                                              int* __restrict__ face_index /*[B][is][is] internal (y up)*/,
                                                              float* __restrict__ alpha /*[B][is][is] image rows (flipped) or null*/,
@@ -137,20 +159,8 @@ __global__ void __launch_bounds__(RT * RT) raster_fwd_kernel(const float* __rest
     // ---- per-pixel tests over the compacted faces
     if (xi < is && yi < is) {
       for (int j = 0; j < cnt; ++j) {
-        const float* q = sf[j];
-        if (((yp - q[1]) * (q[3] - q[0]) < (xp - q[0]) * (q[4] - q[1])) ||
-            ((yp - q[4]) * (q[6] - q[3]) < (xp - q[3]) * (q[7] - q[4])) ||
-            ((yp - q[7]) * (q[0] - q[6]) < (xp - q[6]) * (q[1] - q[7])))
-          continue;
-        const float den = q[6] * (q[1] - q[4]) + q[0] * (q[4] - q[7]) + q[3] * (q[7] - q[1]);
-        float w0 = ((q[4] - q[7]) * xp + (q[6] - q[3]) * yp + (q[3] * q[7] - q[6] * q[4])) / den;
-        float w1 = ((q[7] - q[1]) * xp + (q[0] - q[6]) * yp + (q[6] * q[1] - q[0] * q[7])) / den;
-        float w2 = ((q[1] - q[4]) * xp + (q[3] - q[0]) * yp + (q[0] * q[4] - q[3] * q[1])) / den;
-        w0 = fminf(fmaxf(w0, 0.f), 1.f); w1 = fminf(fmaxf(w1, 0.f), 1.f); w2 = fminf(fmaxf(w2, 0.f), 1.f);
-        const float ws = fmaxf(w0 + w1 + w2, 1e-10f);
-        w0 /= ws; w1 /= ws; w2 /= ws;
-        const float zp = 1.f / (w0 / q[2] + w1 / q[5] + w2 / q[8]);
-        if (zp <= R_NEAR || zp >= R_FAR) continue;
+        float zp;
+        if (!raster_cover(sf[j], xp, yp, zp)) continue;
         if (zp < depth_min) { depth_min = zp; best = s_id[j]; }
       }
     }
@@ -169,9 +179,10 @@ __global__ void __launch_bounds__(RT * RT) raster_fwd_kernel(const float* __rest
 // (z = 1: P[b][row][col + 1]) of the y-up internal maps.  One warp scans one line.  The backward kernel skips a walk whose range holds none:
 // in the silhouette loss of the fitters the active pixels are the part of the target mask the render does not cover yet, a thin band,
 // while every visible edge pixel column used to walk to the image border.
-__global__ void __launch_bounds__(32) raster_active_prefix_kernel(const float* __restrict__ alpha, const float* __restrict__ g_alpha, int is,
-                                                                  unsigned short* __restrict__ pcol, unsigned short* __restrict__ prow) {
-  const int line = blockIdx.x, bn = blockIdx.y, by_row = blockIdx.z, lane = threadIdx.x;
+__global__ void __launch_bounds__(256) raster_active_prefix_kernel(const float* __restrict__ alpha, const float* __restrict__ g_alpha, int is,
+                                                                   unsigned short* __restrict__ pcol, unsigned short* __restrict__ prow) {
+  const int line = blockIdx.x * 8 + (threadIdx.x >> 5), bn = blockIdx.y, by_row = blockIdx.z, lane = threadIdx.x & 31;
+  if (line >= is) return;                                  // (whole warps: no barrier below)
   unsigned short* P = (by_row ? prow : pcol) + ((size_t)bn * is + line) * (is + 1);
   if (lane == 0) P[0] = 0;
   unsigned carry = 0;
@@ -395,7 +406,7 @@ int vt_raster_bwd_ws(const float* verts, const int* faces, int B, int V, int F, 
   if (skip_ws) {
     pcol = reinterpret_cast<unsigned short*>(skip_ws);
     prow = pcol + (size_t)B * image_size * (image_size + 1);
-    raster_active_prefix_kernel<<<dim3(image_size, B, 2), 32, 0, s>>>(alpha, g_alpha, image_size, pcol, prow);
+    raster_active_prefix_kernel<<<dim3(ceil_div(image_size, 8), B, 2), 256, 0, s>>>(alpha, g_alpha, image_size, pcol, prow);
     VT_CHECK_LAUNCH("vt_raster_bwd(prefix)");
   }
   cudaError_t e = cudaMemsetAsync(g_verts, 0, (size_t)B * V * 3 * sizeof(float), s);

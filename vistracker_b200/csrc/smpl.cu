@@ -312,29 +312,64 @@ __global__ void __launch_bounds__(256) smpl_skin_bwd_kernel(SmplModel m, const f
   if (threadIdx.x < 3) sgt[threadIdx.x] = 0.f;
   __syncthreads();
   float gx = 0.f, gy = 0.f, gz = 0.f;
+  float sx = 0.f, sy = 0.f, sz = 0.f, ph[4] = {0.f, 0.f, 0.f, 1.f};
+  float T[9];
+#pragma unroll
+  for (int e = 0; e < 9; ++e) T[e] = 0.f;
   if (v < m.V) {
     const float* g = g_verts + ((size_t)b * m.V + v) * 3;
     gx = g[0]; gy = g[1]; gz = g[2];
-    const float sx = gx * scale, sy = gy * scale, sz = gz * scale;
+    sx = gx * scale; sy = gy * scale; sz = gz * scale;
     const float* p = v_posed + ((size_t)b * m.V + v) * 3;
-    const float ph[4] = {p[0], p[1], p[2], 1.f};
-    float T[9];
-#pragma unroll
-    for (int e = 0; e < 9; ++e) T[e] = 0.f;
-    for (int k = 0; k < m.nnz; ++k) {
-      const float w = m.skin_w[(size_t)v * m.nnz + k];
-      const int j = m.skin_idx[(size_t)v * m.nnz + k];
-      const float* a = sA + j * 12;
+    ph[0] = p[0]; ph[1] = p[1]; ph[2] = p[2];
+  }
+  // d/dA[j] += w (s (x) ph): neighbouring vertices of a real mesh are skinned to the same joints, so the lanes of a warp mostly hit the
+  // same 12 shared-memory words -- fp32 shared atomics are compare-and-swap loops, 32 lanes on one address take 32 rounds each (this kernel
+  // took 0.14 ms for 96 frames with random skinning and 0.47 ms with a body whose skinning follows the surface).  Lanes are grouped by joint
+  // (match.any); a group of 8 or more is summed with a butterfly over the whole warp (the other lanes add zeros) and ONE lane does the 12
+  // atomics, smaller groups keep their direct atomics.
+  const int lane = threadIdx.x & 31;
+  for (int k = 0; k < m.nnz; ++k) {
+    float w = 0.f;
+    int j = -1 - lane;                                     // inactive lanes: a private key, no group
+    if (v < m.V) {
+      w = m.skin_w[(size_t)v * m.nnz + k];
+      const int jj = m.skin_idx[(size_t)v * m.nnz + k];
+      const float* a = sA + jj * 12;
 #pragma unroll
       for (int r = 0; r < 3; ++r)
 #pragma unroll
         for (int c = 0; c < 3; ++c) T[r * 3 + c] = fmaf(w, a[r * 4 + c], T[r * 3 + c]);
-      if (w != 0.f) {
-        float* ga = sgA + j * 12;
+      if (w != 0.f) j = jj;
+    }
+    const unsigned grp = __match_any_sync(0xffffffffu, j);
+    const bool big = j >= 0 && __popc(grp) >= 8;
+    unsigned todo = __ballot_sync(0xffffffffu, big && lane == __ffs(grp) - 1);
+    while (todo) {                                         // (warp-uniform)
+      const int leader = __ffs(todo) - 1;
+      todo &= todo - 1;
+      const int jl = __shfl_sync(0xffffffffu, j, leader);
+      const float wl = (j == jl) ? w : 0.f;
+      float* ga = sgA + jl * 12;
 #pragma unroll
-        for (int c = 0; c < 4; ++c) { atomicAdd(ga + c, w * sx * ph[c]); atomicAdd(ga + 4 + c, w * sy * ph[c]); atomicAdd(ga + 8 + c, w * sz * ph[c]); }
+      for (int r = 0; r < 3; ++r) {
+        const float ws = wl * (r == 0 ? sx : r == 1 ? sy : sz);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          float t = ws * ph[c];
+#pragma unroll
+          for (int o = 16; o >= 1; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+          if (lane == 0) atomicAdd(ga + r * 4 + c, t);
+        }
       }
     }
+    if (j >= 0 && !big) {
+      float* ga = sgA + j * 12;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) { atomicAdd(ga + c, w * sx * ph[c]); atomicAdd(ga + 4 + c, w * sy * ph[c]); atomicAdd(ga + 8 + c, w * sz * ph[c]); }
+    }
+  }
+  if (v < m.V) {
     float* o = g_vposed + (size_t)b * ld_gvp + (size_t)v * 3;
     o[0] = T[0] * sx + T[3] * sy + T[6] * sz;
     o[1] = T[1] * sx + T[4] * sy + T[7] * sz;

@@ -43,6 +43,55 @@ def synthetic_smplh(seed: int = 3, num_verts: int = NUM_VERTS):
             "th_faces": torch.from_numpy(faces), "parents": list(SMPLH_PARENTS)}
 
 
+# rest joints of the human-shaped model below, metres, y up, origin at the middle of the trunk: the 22 SMPL body joints in kintree order
+_BODY_JOINTS = [(0, -0.05, 0), (0.07, -0.14, 0), (-0.07, -0.14, 0), (0, 0.07, 0), (0.10, -0.50, 0), (-0.10, -0.50, 0), (0, 0.20, 0),
+                (0.09, -0.78, 0), (-0.09, -0.78, 0), (0, 0.27, 0), (0.10, -0.83, 0.08), (-0.10, -0.83, 0.08), (0, 0.48, 0),
+                (0.06, 0.40, 0), (-0.06, 0.40, 0), (0, 0.60, 0), (0.17, 0.42, 0), (-0.17, 0.42, 0), (0.24, 0.18, 0), (-0.24, 0.18, 0),
+                (0.26, -0.05, 0), (-0.26, -0.05, 0)]
+
+
+def synthetic_smplh_surface(seed: int = 3, pelvis=(0.0, -0.25, 0.0)):
+    """A HUMAN-SHAPED stand-in for ``SMPLH_male.pkl`` with the same buffers as ``synthetic_smplh``: the template is the closed 1.7 m surface of
+    ``synthetic_body_mesh`` (6890 vertices ordered ring by ring, 13 776 coherent faces), the 52 rest joints sit where a person's do (22 body
+    joints + 15 finger joints hanging off each wrist), each joint is regressed from the 24 template vertices nearest to it, every vertex is
+    skinned to its four nearest joints (inverse-square-distance weights), the shape directions are smooth fields (one random 3 x 3 shear of
+    the template per beta) and the pose directions a millimetre of noise.  What matters for throughput is what the real model has and
+    ``synthetic_smplh`` (a Gaussian point cloud in random vertex order, right for skinning parity) has not: consecutive vertices are
+    neighbours on a surface, so the 128 points of a query tile sample a patch of the feature maps instead of the whole body volume.
+    ``pelvis``: where the root joint lies relative to the translation -- the offset the synthetic batches use for the body centre
+    (vistracker_b200/synth.py: ``body = trans + (0, -0.25, 0)``), so the triplane is centred on the hips as in BEHAVE."""
+    rng = np.random.Generator(np.random.PCG64(seed + 7000))
+    f32 = np.float32
+    J = NUM_JOINTS
+    shift = np.asarray(pelvis, np.float64) - np.asarray(_BODY_JOINTS[0], np.float64)
+    verts, faces = synthetic_body_mesh()
+    v = verts.astype(np.float64) + shift
+    V = v.shape[0]
+    joints = np.zeros((J, 3))
+    joints[:22] = np.asarray(_BODY_JOINTS, np.float64) + shift
+    for side, wrist in ((0, 20), (1, 21)):                   # five fingers x three joints below each wrist
+        for fgr in range(5):
+            for k in range(3):
+                joints[22 + side * 15 + fgr * 3 + k] = joints[wrist] + np.array([(0.012 if side == 0 else -0.012) * (fgr - 2), -0.03 * (k + 1) - 0.04, 0.01])
+    jreg = np.zeros((J, V), f32)
+    for j in range(J):
+        idx = np.argsort(((v - joints[j]) ** 2).sum(1))[:24]
+        w = rng.random(24).astype(f32) + 0.1
+        jreg[j, idx] = w / w.sum()
+    jpos = jreg.astype(np.float64) @ v                       # where the regressor puts the joints: the skinning neighbourhoods follow these
+    d2 = ((v[:, None, :] - jpos[None]) ** 2).sum(-1)
+    near = np.argsort(d2, 1)[:, :4]
+    weights = np.zeros((V, J), f32)
+    w = 1.0 / (np.take_along_axis(d2, near, 1) + 0.02 ** 2)
+    np.put_along_axis(weights, near, (w / w.sum(1, keepdims=True)).astype(f32), 1)
+    shear = rng.standard_normal((NUM_BETAS, 3, 3)) * 0.03
+    shapedirs = (np.einsum("kab,vb->vak", shear, v - shift) + rng.standard_normal((V, 3, NUM_BETAS)) * 0.001).astype(f32)
+    posedirs = (rng.standard_normal((V, 3, (J - 1) * 9)) * 0.001).astype(f32)
+    return {"th_betas": torch.zeros(1, NUM_BETAS), "th_shapedirs": torch.from_numpy(shapedirs), "th_posedirs": torch.from_numpy(posedirs),
+            "th_v_template": torch.from_numpy(v.astype(f32)[None]), "th_J_regressor": torch.from_numpy(jreg),
+            "th_weights": torch.from_numpy(weights), "th_faces": torch.from_numpy(faces.astype(np.int64)), "parents": list(SMPLH_PARENTS)}
+
+
 def synthetic_motion(frames: int, seed: int = 5, sigma: float = 0.02):
     """Smooth random walk in body pose: pose [T,156], betas [T,10] = (2.2, 0, ...)-like, trans [T,3]."""
     rng = np.random.Generator(np.random.PCG64(seed))
