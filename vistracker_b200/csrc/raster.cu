@@ -13,9 +13,10 @@
 //
 // Forward is tiled: a CTA owns a 16x16 pixel tile, culls the face list against the tile in order-preserving chunks (ballot
 // compaction into shared memory) and only then runs the per-pixel tests -- upstream loops every pixel over every face.
-// (Measured, profiles/r02l_raster_fwd_ncu.txt: 0.33 ms for the 96 silhouettes of a batch is NOT the culling -- a 64x64 super-tile variant that
-// culled once per 16 tiles took the same 0.33 ms -- but the depth of the covered pixels: ten IEEE divisions per covered (pixel, face) pair,
-// executed by warps in which a small face leaves most lanes idle.  The arithmetic is upstream's and stays as it is.)
+// (Measured, profiles/r02l_raster_fwd_ncu.txt: the 0.33 ms for the 96 silhouettes of a batch were NOT the culling -- a 64x64 super-tile variant
+// that culled once per 16 tiles took the same 0.33 ms -- but the depth of the covered pixels: ten IEEE divisions per covered (pixel, face) pair,
+// executed by warps in which a small face leaves most lanes idle.  The arithmetic is upstream's and stays; the depths are now evaluated
+// lane-parallel over different faces, see the per-pixel loop.)
 #include "common.cuh"
 #include "vt_internal.h"
 
@@ -23,6 +24,7 @@ namespace vt {
 
 constexpr int RT = 16;                 // tile edge
 constexpr int RCHUNK = 256;            // faces examined per compaction round
+static_assert(RCHUNK <= 256, "the forward kernel packs slot numbers of a chunk into bytes");
 constexpr float R_NEAR = 0.1f, R_FAR = 100.f, R_EPS = 1e-3f;
 
 // camera: mode 0 = nr.projection with per-frame (fx, fy, cx, cy), orig_size 1, eps 1e-9, no distortion; mode 1 = (x, y, z) as given
@@ -82,14 +84,14 @@ __global__ void __launch_bounds__(RCHUNK) raster_bbox_kernel(const float* __rest
   }
 }
 
-// One pixel centre against one counter-clockwise face q = (x, y, z) x 3 in NDC: the three edge tests, then the depth 1 / sum(w_k / z_k) with the
-// clamped, renormalised barycentric weights; false when the pixel is not covered or the depth is outside (near, far).  ONE statement of the
-// arithmetic for both forward kernels (the nearest-face decision compares these depths between faces).
-__device__ __forceinline__ bool raster_cover(const float* q, float xp, float yp, float& zp) {
-  if (((yp - q[1]) * (q[3] - q[0]) < (xp - q[0]) * (q[4] - q[1])) ||
-      ((yp - q[4]) * (q[6] - q[3]) < (xp - q[3]) * (q[7] - q[4])) ||
-      ((yp - q[7]) * (q[0] - q[6]) < (xp - q[6]) * (q[1] - q[7])))
-    return false;
+// One pixel centre against one counter-clockwise face q = (x, y, z) x 3 in NDC, in two parts: the three edge tests (covered or not), and the
+// depth 1 / sum(w_k / z_k) of a covered pixel with the clamped, renormalised barycentric weights (false when it is outside (near, far)).
+__device__ __forceinline__ bool raster_edges(const float* q, float xp, float yp) {
+  return !(((yp - q[1]) * (q[3] - q[0]) < (xp - q[0]) * (q[4] - q[1])) ||
+           ((yp - q[4]) * (q[6] - q[3]) < (xp - q[3]) * (q[7] - q[4])) ||
+           ((yp - q[7]) * (q[0] - q[6]) < (xp - q[6]) * (q[1] - q[7])));
+}
+__device__ __forceinline__ bool raster_depth(const float* q, float xp, float yp, float& zp) {
   const float den = q[6] * (q[1] - q[4]) + q[0] * (q[4] - q[7]) + q[3] * (q[7] - q[1]);
   float w0 = ((q[4] - q[7]) * xp + (q[6] - q[3]) * yp + (q[3] * q[7] - q[6] * q[4])) / den;
   float w1 = ((q[7] - q[1]) * xp + (q[0] - q[6]) * yp + (q[6] * q[1] - q[0] * q[7])) / den;
@@ -157,12 +159,30 @@ __global__ void __launch_bounds__(RT * RT) raster_fwd_kernel(const float* __rest
     __syncthreads();
     const int cnt = s_total;
     // ---- per-pixel tests over the compacted faces
-    if (xi < is && yi < is) {
+    // Edge tests first, depths later: a face covers a few of a warp's 32 pixels, so evaluating the depth (ten IEEE divisions) inside the face loop ran
+    // it with most lanes idle -- it was the bulk of this kernel (profiles/r02l_raster_fwd_ncu.txt).  Every lane queues the slots of the faces
+    // that cover ITS pixel (up to four, packed into one word) and the warp evaluates the queued depths together, each lane on its own face, when
+    // a queue is full and at the end of the chunk: a pixel still sees its faces in face order with the same arithmetic -> same image.
+    {
+      const bool inside = xi < is && yi < is;
+      uint32_t pend = 0;
+      int np = 0;
+      auto flush = [&]() {
+#pragma unroll 1
+        for (int t = 0; __any_sync(0xffffffffu, t < np); ++t) {
+          if (t < np) {
+            const int j = (pend >> (8 * t)) & 0xFF;
+            float zp;
+            if (raster_depth(sf[j], xp, yp, zp) && zp < depth_min) { depth_min = zp; best = s_id[j]; }
+          }
+        }
+        pend = 0; np = 0;
+      };
       for (int j = 0; j < cnt; ++j) {
-        float zp;
-        if (!raster_cover(sf[j], xp, yp, zp)) continue;
-        if (zp < depth_min) { depth_min = zp; best = s_id[j]; }
+        if (inside && raster_edges(sf[j], xp, yp)) { pend |= (uint32_t)j << (8 * np); ++np; }
+        if (__any_sync(0xffffffffu, np == 4)) flush();
       }
+      if (__any_sync(0xffffffffu, np > 0)) flush();
     }
     __syncthreads();
   }
