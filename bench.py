@@ -563,6 +563,81 @@ def torch_eager_gpu(D: Dist, sd, dims, steps=3):
     return out
 
 
+def torch_eager_gpu_c4(dev, counts, frames=C4_FRAMES, size=SIZE, gen_points=30000, gen_frames=16, n_steps=3, seed=4):
+    """R-GPU context number for the metric's own workload: the reference's algorithm of every C4 stage
+    as PLAIN PyTorch on the same B200 -- the restatements under oracle/ (pinned to the reference's own loops) run under ``torch.device(cuda)``:
+    cuDNN / ATen eager kernels, autograd, torch.optim.Adam, fp32 with TF32 off (torch 1.6 behaviour), none of this repo's kernels.  Per-unit times
+    (filter per frame on a 16-frame mini-batch; one generator projection step on 16 x 30 000 points; optimize_smpl / 'object only' / 'joint'
+    steps on the 96-frame batch), extrapolated to the step counts of the batch exactly like the CPU baseline (cpu_c4_fps); the silhouette
+    rasteriser is left out of the value on both sides of that formula (the restatement has no GPU rasteriser, the reference's is neural_renderer)."""
+    import numpy as np
+    import torch
+    from oracle import recon_fit_ref as RF
+    from oracle import sifnet_ref as SR
+    from tools_inputs import load_assets
+    from vistracker_b200 import default_options, resolve_dims
+    from vistracker_b200.synth import synthetic_recon_batch, synthetic_state_dict
+    dev = torch.device(dev)
+    on_gpu = dev.type == "cuda"
+    sync = (lambda: torch.cuda.synchronize(dev)) if on_gpu else (lambda: None)
+    keep = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    torch.backends.cuda.matmul.allow_tf32 = torch.backends.cudnn.allow_tf32 = False
+    a, reg = load_assets()
+    d = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in synthetic_recon_batch(frames, size=size, seed=seed).items()}
+    sd = {k: v.to(dev) for k, v in synthetic_state_dict(resolve_dims(default_options()), seed=0).items()}
+    model = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in body_model().items()}
+    labels = a["part_labels"].astype(np.int64)
+    t = {}
+
+    def timed(fn, n=1):
+        fn(); sync()                                            # warm-up (cuDNN algorithm selection, allocator)
+        t0 = time.perf_counter()
+        for _ in range(n):
+            fn()
+        sync()
+        return (time.perf_counter() - t0) / n
+    try:
+        with torch.device(dev):
+            gf = min(gen_frames, frames)
+            with torch.no_grad():
+                t["filter_per_frame"] = timed(lambda: SR.sif_filter(sd, d["images"][:gf])) / gf
+                chunks = [SR.sif_filter(sd, d["images"][i:i + gf]) for i in range(0, frames, gf)]
+            maps = {k: ([torch.cat([c[k][j] for c in chunks]) for j in range(len(chunks[0][k]))] if isinstance(chunks[0][k], (list, tuple))
+                        else torch.cat([c[k] for c in chunks])) for k in chunks[0]}
+            del chunks
+            P = RF.Problem(sd, maps, model, reg, a, labels, d["crop_center"], d["body_center"], net_in_size=size)
+            # generator: one projection step = query + backward to the points (recon/gen/generator.py:72-104) on a mini-batch
+            P1 = RF.Problem(sd, {k: ([x[:gf] for x in v] if isinstance(v, (list, tuple)) else v[:gf]) for k, v in maps.items()}, model, reg, a, labels,
+                            d["crop_center"][:gf], d["body_center"][:gf], net_in_size=size)
+            g = torch.Generator(device="cpu").manual_seed(seed)
+            pts0 = d["body_center"][:gf, None] + ((torch.rand(gf, gen_points, 3, generator=g, device="cpu") - 0.5) * torch.tensor([2.0, 3.0, 1.2], device="cpu")).to(dev)
+
+            def gen_step():
+                pts = pts0.clone().requires_grad_(True)
+                torch.clamp(P1.query(pts)[0][:, 0], max=2.0).sum().backward()
+            t["generator_step_per_frame"] = timed(gen_step, 2) / gf
+            kp, pose_init = d["body_kpts"], d["pose"][:, 3:72].clone()
+            t["smpl_step_per_frame"] = timed(lambda: RF.optimize_smpl(P, d["pose"], d["betas"], d["trans"], pose_init, kp, 1, 1, 1, steps_per_iter=1, max_iter=0,
+                                                                     step_budget=n_steps)) / (n_steps * frames)
+            rng = torch.Generator(device="cpu").manual_seed(seed)
+            noise = lambda: torch.rand(frames, 3, 3, generator=rng, device="cpu").to(dev)
+            obj_t = d["body_center"] + torch.tensor([0.35, 0.0, 0.1])
+            common = dict(objects=d["obj_points"][None].repeat(frames, 1, 1), occ=d["occ_ratios"], noise_fn=noise, it_obj=1, it_sil=0, joint_iter=0,
+                          steps_per_iter=n_steps, max_iter=1)
+            for key, budget in (("object_step_per_frame", {"object only": n_steps, "joint": 0}), ("joint_step_per_frame", {"object only": 0, "joint": n_steps})):
+                t[key] = timed(lambda: RF.optimize_smpl_object(P, d["pose"], d["betas"], d["trans"], d["obj_rot_init"], obj_t, torch.ones(frames), sil=None,
+                                                               step_budget=budget, **common)) / (n_steps * frames)
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = keep
+    t["sil_step_per_frame"] = float("nan")
+    fps, per_frame, _ = cpu_c4_fps(t, counts)
+    return {"frames_per_s": fps, "seconds_per_frame": per_frame, "unit_seconds_per_frame": {k: v for k, v in t.items() if v == v},
+            "ms_per_step_on_the_batch": {"optimize_smpl": t["smpl_step_per_frame"] * frames * 1e3, "object only": t["object_step_per_frame"] * frames * 1e3,
+                                         "joint": t["joint_step_per_frame"] * frames * 1e3, "generator projection (16 frames x 30000 points)": t["generator_step_per_frame"] * gf * 1e3},
+            "what": "oracle/ restatements of the reference's C4 stages as plain PyTorch on cuda (cuDNN / ATen eager + autograd + torch.optim.Adam, fp32, TF32 off), per-unit times "
+                    "EXTRAPOLATED to this batch's step counts with the CPU baseline's formula (silhouette rasteriser excluded); a baseline, none of this repo's kernels"}
+
+
 def c4_accuracy(D: Dist):
     """The accuracy half of the metric on a problem the CPU can finish: the same 4-frame batch (64 x 64 network input) through both loops on
     the GPU and through the CPU oracle (oracle/recon_fit_ref.py, pinned to the reference's own loops) with the same decopose_axis draws;
@@ -717,6 +792,12 @@ def run_ours(args):
                 extra["torch_eager_gpu"] = torch_eager_gpu(D, c4.sd, c4.dims)
             except Exception as ex:      # noqa: BLE001
                 extra["torch_eager_gpu"] = {"error": f"{type(ex).__name__}: {ex}"}
+        if D.world == 1:
+            try:
+                extra["torch_eager_gpu_c4"] = torch_eager_gpu_c4(D.dev, counts)
+            except Exception as ex:      # noqa: BLE001
+                extra["torch_eager_gpu_c4"] = {"error": f"{type(ex).__name__}: {ex}"}
+            torch.cuda.empty_cache()
         accuracy = c4_accuracy(D) if D.world == 1 else None
         cores = os.cpu_count() or 1
         torch.set_num_threads(cores)
