@@ -41,7 +41,7 @@ OBJ_CAPS = dict(it_obj=15, it_sil=30, joint_iter=10, steps_per_iter=10, max_iter
 # bytes a point moves through the fused query-loss launch (forward gather 9 728 + second gather of the backward 9 728 +
 # point 12 + label 8 + two values 8 + the merged point gradient 12)
 QUERY_LOSS_BYTES_PER_POINT = 2 * 9728 + 12 + 8 + 8 + 12
-NCU_QUERY_LOSS_DRAM_BYTES_PER_POINT = (543.237120e6 + 16.036864e6) / (96 * 6890)     # profiles/r02h_query_loss_merged_final_ncu_summary.txt
+NCU_QUERY_LOSS_DRAM_BYTES_PER_POINT = (543.143936e6 + 15.972608e6) / (96 * 6890)     # profiles/r02m_query_loss_merged_ncu_summary.txt
 QUERY_LOSS_FLOP_PER_POINT = 2 * (1.117e6 / 5) * 3           # two heads, forward + the two backward products (1.117 MFLOP / 5 heads)
 # ---- C2 (extra)
 BATCH, NPTS = 8, 10000
@@ -440,8 +440,8 @@ def query_roofline(c4: C4, share_launches, step_ms):
     return {"bound": "hbm", "kernel": "query_bwd_tc_kernel, fused-loss mode with merged heads (vt_query_losses_merged_tc) on 96 x 6890 vertices: 1 launch per optimize_smpl step",
             "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": achieved / pk["hbm_gbs"],
             "traffic": NCU_QUERY_LOSS_DRAM_BYTES_PER_POINT * B * V,
-            "traffic_note": "dram__bytes_read + write of one ncu --set full capture of this launch (profiles/r02h_query_loss_merged_final_ncu_summary.txt: 559.3 MB at 96 x 6890 points), scaled per point; "
-                            "far BELOW the algorithmic bytes: the bilinear taps are L1- (71 %) and L2-served (88 %), the 8 maps of a frame are 71 MB and the vertices of one body touch a small part",
+            "traffic_note": "dram__bytes_read + write of one ncu --set full capture of this launch (profiles/r02m_query_loss_merged_ncu_summary.txt: 559.1 MB at 96 x 6890 points of a surface body), scaled per point; "
+                            "far BELOW the algorithmic bytes: the bilinear taps are L1- (67 %) and L2-served (91 %), the 8 maps of a frame are 71 MB and the vertices of one body touch a small part",
             "algorithmic_bytes_per_launch": nbytes, "bytes_per_point": QUERY_LOSS_BYTES_PER_POINT, "ms_per_launch": ms, "body": BODY_NOTE[BODY], "other_body": other_body,
             "tensor_tflops": QUERY_LOSS_FLOP_PER_POINT * B * V / (ms * 1e-3) / 1e12, "launches_per_step": share_launches,
             "share_of_step": share_launches * ms / step_ms, "peak_source": f"{src} HBM copy bandwidth",
