@@ -100,6 +100,10 @@ class ClockSampler:
 # =====================================================================================================================================
 # CPU side (oracle/): cpu_baseline leg and --impl reference only
 # =====================================================================================================================================
+# Weak scaling: every rank fits ITS OWN COPY of the same seeded batch.  The early stops of the optimisation are data dependent: with a different
+# synthetic batch per rank (VT_BENCH_RANK_SEEDS=1: seed + 100 * rank) the max-over-ranks time measures which rank drew the batch with the longest
+# joint phase (2.34 s at seed 4, 3.74 s at seed 104), not how the system scales.  extra.steps_taken_per_rank shows the balance either way.
+RANK_SEEDS = os.environ.get("VT_BENCH_RANK_SEEDS", "0") == "1"
 BODY = os.environ.get("VT_BENCH_BODY", "surface")             # "surface" (default) | "cloud" (the Gaussian point cloud of the earlier bench lines)
 BODY_NOTE = {"surface": "human-shaped synthetic SMPL-H (synth_smpl.synthetic_smplh_surface: closed 1.7 m surface, vertices in surface order, proximity "
                         "skinning) -- SMPLH_male.pkl itself is licensed and absent",
@@ -277,8 +281,20 @@ class Dist:
         self.dist = dist
         if self.world > 1:
             # NCCL writes its version banner (NCCL_DEBUG=VERSION in this image) to stdout: keep stdout for the ONE JSON line
+            # (NCCL_DEBUG_FILE does not move the banner): drop the banner level, and point fd 1 at stderr while the communicator comes up
+            if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+                os.environ["NCCL_DEBUG"] = "WARN"
             os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
-            dist.init_process_group("nccl", device_id=self.dev)
+            sys.stdout.flush()
+            saved = os.dup(1)
+            os.dup2(2, 1)
+            try:
+                dist.init_process_group("nccl", device_id=self.dev)
+                dist.barrier()
+                torch.cuda.synchronize()
+            finally:
+                os.dup2(saved, 1)
+                os.close(saved)
 
     def barrier(self):
         import torch
@@ -334,7 +350,7 @@ class C4:
         model = body_model()
         self.layer = SMPL_Layer.from_buffers(model, model["parents"], dev)
         self.reg = LandmarkRegressor(np.stack([reg[0], reg[1]]), reg[2], reg[3], dev)
-        h = synthetic_recon_batch(frames, size=SIZE, seed=seed + 100 * D.rank)
+        h = synthetic_recon_batch(frames, size=SIZE, seed=seed + (100 * D.rank if RANK_SEEDS else 0))
         self.fitter = ReconFitterTriVisFull(self.net, Priors(a, dev), torch.from_numpy(a["part_labels"].astype(np.int64)),
                                             scan=(h["obj_verts"].numpy(), h["obj_faces"].numpy()))
         # random-init UDF: every in-front point counts as "on the surface" -> the minimum of 2 rounds per target a trained network needs
@@ -771,10 +787,15 @@ def run_ours(args):
     step_ms = ms / args.steps
     # launches of this repo's kernels per batch: 16 per optimize_smpl step, ~12-19 per object step, ~440 per filter call (12 calls: 6 generator
     # mini-batches + 6 chunks of the whole-batch filter), 1 per generator projection step (2 targets x 2 rounds x 10 x 6 mini-batches) + forward queries
+    counts_all = [counts]
+    if D.world > 1:
+        counts_all = [None] * D.world
+        D.dist.all_gather_object(counts_all, counts)
     launches = (counts["smpl"] * 16 + counts["object only"] * 11 + counts["sil"] * 16 + counts["joint"] * 17 + 12 * c4.net.launches_filter + 6 * 2 * 2 * 11)
     if D.rank == 0:
         roof = query_roofline(c4, counts["smpl"], step_ms)
-        extra = {"per_rank_ms": [x / args.steps for x in per_rank], "steps_taken": counts}
+        extra = {"per_rank_ms": [x / args.steps for x in per_rank], "steps_taken": counts, "steps_taken_per_rank": counts_all,
+                 "rank_batches": "a different seeded batch per rank" if RANK_SEEDS else "every rank fits its own copy of the same seeded batch"}
         stage = {}
         # where the time of a batch goes (device-synchronised wall time of one more batch, stage by stage)
         try:
