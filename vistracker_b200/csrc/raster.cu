@@ -220,28 +220,28 @@ __global__ void __launch_bounds__(256) raster_active_prefix_kernel(const float* 
   }
 }
 
-// NMR pseudo-gradient of the silhouette w.r.t. the (x, y) of every face vertex.  One WARP per (frame, face): the lanes split the
+// NMR pseudo-gradient of the silhouette w.r.t. the (x, y) of every face vertex.  One HALF-WARP per (frame, face): its 16 lanes split the
 // pixel columns / rows an edge crosses (the upstream kernel walks them in one thread: up to `is` iterations, each with an inner walk of
-// up to `is` pixels -- latency-bound), partial sums are combined with shuffles at the end.
+// up to `is` pixels -- latency-bound), partial sums are combined with shuffles at the end.  (With a whole warp per face the kernel ran at 12
+// active lanes per instruction and 63 % of its issue slots -- the faces of a fitted template are ~16 pixels wide, profiles/r02l_raster_fwd_ncu.txt;
+// consecutive faces are mesh neighbours, so the two halves of a warp walk edges of similar length.)
 __global__ void __launch_bounds__(128) raster_bwd_kernel(const float* __restrict__ faces_ndc, const int* __restrict__ face_index,
                                   const float* __restrict__ alpha /*image rows*/, const float* __restrict__ g_alpha /*image rows*/,
                                   int B, int nf, int is, float* __restrict__ g_faces /*[B][nf][9]*/,
                                   const unsigned short* __restrict__ pcol, const unsigned short* __restrict__ prow /*optional: see above*/) {
-  const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-  if (i >= B * nf) return;
-  const int bn = i / nf, fn = i % nf;
-  const float* face = faces_ndc + (size_t)i * 9;
+  const int i = 2 * (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) + ((threadIdx.x >> 4) & 1), lane = threadIdx.x & 15;
+  const bool live = i < B * nf;
+  const int bn = live ? i / nf : 0, fn = live ? i % nf : 0;
+  const float* face = faces_ndc + (size_t)(live ? i : 0) * 9;
   float grad_face[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-  float* out = g_faces + (size_t)i * 9;
-  if ((face[7] - face[1]) * (face[3] - face[0]) < (face[4] - face[1]) * (face[6] - face[0])) {   // back side
-    if (lane < 9) out[lane] = 0.f;
-    return;
-  }
+  float* out = g_faces + (size_t)(live ? i : 0) * 9;
+  // back side: a zero gradient (the sums below stay zero); both halves of the warp reach the shuffles at the end
+  const bool front = live && !((face[7] - face[1]) * (face[3] - face[0]) < (face[4] - face[1]) * (face[6] - face[0]));
   // internal maps are y-up: internal (row = y index, col = x index) lives at image row is-1-row
   auto A = [&](int row, int col) { return alpha[((size_t)bn * is + (is - 1 - row)) * is + col]; };
   auto GA = [&](int row, int col) { return g_alpha[((size_t)bn * is + (is - 1 - row)) * is + col]; };
   auto FI = [&](int row, int col) { return face_index[((size_t)bn * is + row) * is + col]; };
-  for (int edge = 0; edge < 3; ++edge) {
+  for (int edge = 0; front && edge < 3; ++edge) {
     int pi[3];
     float pp[3][2];
     for (int n = 0; n < 3; ++n) pi[n] = (edge + n) % 3;
@@ -256,7 +256,7 @@ __global__ void __launch_bounds__(128) raster_bwd_kernel(const float* __restrict
       else direction = (p[0][0] < p[1][0]) ? 1 : -1;
       const int d0_from = (int)fmaxf(ceilf(fminf(p[0][0], p[1][0])), 0.f);
       const int d0_to = (int)fminf(fmaxf(p[0][0], p[1][0]), (float)(is - 1));
-      for (int d0 = d0_from + lane; d0 <= d0_to; d0 += 32) {
+      for (int d0 = d0_from + lane; d0 <= d0_to; d0 += 16) {
         const float d1_cross = (p[1][1] - p[0][1]) / (p[1][0] - p[0][0]) * (d0 - p[0][0]) + p[0][1];
         const int d1_in = direction > 0 ? (int)floorf(d1_cross) : (int)ceilf(d1_cross);
         const int d1_out = d1_in + direction;
@@ -340,8 +340,8 @@ __global__ void __launch_bounds__(128) raster_bwd_kernel(const float* __restrict
   for (int k = 0; k < 9; ++k) {
     float v = grad_face[k];
 #pragma unroll
-    for (int o = 16; o >= 1; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    if (lane == 0) out[k] = v;
+    for (int o = 8; o >= 1; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);      // within the half-warp
+    if (lane == 0 && live) out[k] = v;
   }
 }
 
@@ -431,7 +431,7 @@ int vt_raster_bwd_ws(const float* verts, const int* faces, int B, int V, int F, 
   }
   cudaError_t e = cudaMemsetAsync(g_verts, 0, (size_t)B * V * 3 * sizeof(float), s);
   if (e != cudaSuccess) return cuda_fail(e, "vt_raster_bwd memset");
-  raster_bwd_kernel<<<ceil_div(B * 2 * F, 4), 128, 0, s>>>(faces_ndc, face_index, alpha, g_alpha, B, 2 * F, image_size, g_faces, pcol, prow);   // one warp per face
+  raster_bwd_kernel<<<ceil_div(B * 2 * F, 8), 128, 0, s>>>(faces_ndc, face_index, alpha, g_alpha, B, 2 * F, image_size, g_faces, pcol, prow);   // one half-warp per face
   VT_CHECK_LAUNCH("vt_raster_bwd");
   raster_bwd_verts_kernel<<<ceil_div(B * 2 * F, 256), 256, 0, s>>>(g_faces, verts, faces, B, V, F, mode, K4, g_verts);
   VT_CHECK_LAUNCH("vt_raster_bwd(verts)");
