@@ -225,11 +225,12 @@ __global__ void __launch_bounds__(256) raster_active_prefix_kernel(const float* 
 // up to `is` pixels -- latency-bound), partial sums are combined with shuffles at the end.  (With a whole warp per face the kernel ran at 12
 // active lanes per instruction and 63 % of its issue slots -- the faces of a fitted template are ~16 pixels wide, profiles/r02l_raster_fwd_ncu.txt;
 // consecutive faces are mesh neighbours, so the two halves of a warp walk edges of similar length.)
+constexpr int RB_LANES = 16;           // lanes per face in raster_bwd_kernel (measured per step at 96 frames: 32 lanes 0.29 ms, 16: 0.24, 8: 0.25)
 __global__ void __launch_bounds__(128) raster_bwd_kernel(const float* __restrict__ faces_ndc, const int* __restrict__ face_index,
                                   const float* __restrict__ alpha /*image rows*/, const float* __restrict__ g_alpha /*image rows*/,
                                   int B, int nf, int is, float* __restrict__ g_faces /*[B][nf][9]*/,
                                   const unsigned short* __restrict__ pcol, const unsigned short* __restrict__ prow /*optional: see above*/) {
-  const int i = 2 * (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) + ((threadIdx.x >> 4) & 1), lane = threadIdx.x & 15;
+  const int i = (blockIdx.x * blockDim.x + threadIdx.x) / RB_LANES, lane = threadIdx.x & (RB_LANES - 1);
   const bool live = i < B * nf;
   const int bn = live ? i / nf : 0, fn = live ? i % nf : 0;
   const float* face = faces_ndc + (size_t)(live ? i : 0) * 9;
@@ -256,7 +257,7 @@ __global__ void __launch_bounds__(128) raster_bwd_kernel(const float* __restrict
       else direction = (p[0][0] < p[1][0]) ? 1 : -1;
       const int d0_from = (int)fmaxf(ceilf(fminf(p[0][0], p[1][0])), 0.f);
       const int d0_to = (int)fminf(fmaxf(p[0][0], p[1][0]), (float)(is - 1));
-      for (int d0 = d0_from + lane; d0 <= d0_to; d0 += 16) {
+      for (int d0 = d0_from + lane; d0 <= d0_to; d0 += RB_LANES) {
         const float d1_cross = (p[1][1] - p[0][1]) / (p[1][0] - p[0][0]) * (d0 - p[0][0]) + p[0][1];
         const int d1_in = direction > 0 ? (int)floorf(d1_cross) : (int)ceilf(d1_cross);
         const int d1_out = d1_in + direction;
@@ -340,7 +341,7 @@ __global__ void __launch_bounds__(128) raster_bwd_kernel(const float* __restrict
   for (int k = 0; k < 9; ++k) {
     float v = grad_face[k];
 #pragma unroll
-    for (int o = 8; o >= 1; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);      // within the half-warp
+    for (int o = RB_LANES / 2; o >= 1; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);      // within the face's lanes
     if (lane == 0 && live) out[k] = v;
   }
 }
@@ -431,7 +432,7 @@ int vt_raster_bwd_ws(const float* verts, const int* faces, int B, int V, int F, 
   }
   cudaError_t e = cudaMemsetAsync(g_verts, 0, (size_t)B * V * 3 * sizeof(float), s);
   if (e != cudaSuccess) return cuda_fail(e, "vt_raster_bwd memset");
-  raster_bwd_kernel<<<ceil_div(B * 2 * F, 8), 128, 0, s>>>(faces_ndc, face_index, alpha, g_alpha, B, 2 * F, image_size, g_faces, pcol, prow);   // one half-warp per face
+  raster_bwd_kernel<<<ceil_div(B * 2 * F, 128 / RB_LANES), 128, 0, s>>>(faces_ndc, face_index, alpha, g_alpha, B, 2 * F, image_size, g_faces, pcol, prow);   // RB_LANES lanes per face
   VT_CHECK_LAUNCH("vt_raster_bwd");
   raster_bwd_verts_kernel<<<ceil_div(B * 2 * F, 256), 256, 0, s>>>(g_faces, verts, faces, B, V, F, mode, K4, g_verts);
   VT_CHECK_LAUNCH("vt_raster_bwd(verts)");
