@@ -166,3 +166,52 @@ def test_backward_walk_skipping_does_not_change_the_gradient():
         else:
             assert float((grads[1] - grads[0]).abs().max()) <= 1e-6 * max(float(grads[0].abs().max()), 1e-30)
     rend.skip_walks = True
+
+
+def test_many_layers_over_one_pixel_keep_the_nearest_face_in_face_order():
+    """Up to 13 faces stacked over the same pixels, nearest one in the middle of the face list and two faces at EXACTLY the same depth: the forward
+    kernel queues the faces that cover a pixel (four per queue) and evaluates their depths later -- the queue must flush in the middle of the
+    face loop without losing the order ('nearest wins, first one on ties').  Depth image and face-index map against the restatement."""
+    _need_gpu()
+    from vistracker_b200 import _lib
+    from vistracker_b200.render import SilhouetteRenderer, _cull_ws
+    rng = np.random.Generator(np.random.PCG64(5))
+    S, L = 48, 13
+    depth_of = [9.0, 7.5, 8.0, 6.0, 6.5, 3.0, 5.0, 3.0, 4.0, 2.5, 2.5, 7.0, 2.75]          # nearest: faces 9 and 10 (a tie: 9 wins), 5 and 7 tie behind them
+    verts, faces = [], []
+    for l in range(L):
+        c = rng.uniform(-0.25, 0.25, 2)
+        r = rng.uniform(0.45, 0.8)
+        a0 = rng.uniform(0, 2 * np.pi)
+        for k in range(3):
+            verts.append([c[0] + r * np.cos(a0 + 2.1 * k), c[1] + r * np.sin(a0 + 2.1 * k), depth_of[l]])
+        faces.append([3 * l, 3 * l + 1, 3 * l + 2])
+    verts, faces = np.asarray(verts, np.float32), np.asarray(faces, np.int64)
+    rend = SilhouetteRenderer(faces, S, None, "cuda:0")                           # orthographic: (x, y, z) are NDC
+    v = torch.from_numpy(verts)[None].cuda().contiguous()
+    F_ = faces.shape[0]
+    faces_ndc = torch.empty(1, 2 * F_, 9, device="cuda")
+    fidx = torch.empty(1, S, S, dtype=torch.int32, device="cuda")
+    depth = torch.empty(1, S, S, device="cuda")
+    cull = _cull_ws(1, F_, v.device)
+    _lib.call("vt_raster_fwd", _lib.ptr(v), _lib.ptr(rend.faces), 1, v.shape[1], F_, rend.mode, _lib.ptr(rend.K4), S, _lib.ptr(faces_ndc), _lib.ptr(fidx),
+              None, _lib.ptr(depth), _lib.ptr(cull), _lib.stream_ptr())
+    torch.cuda.synchronize()
+    idx_ref, alpha_ref, depth_ref = R.rasterize_fast(R.faces_of(verts.astype(np.float64), faces), S)
+    fv = R.faces_of(verts.astype(np.float64), faces)
+    per_face = np.stack([R.rasterize_fast(q[None], S)[2][::-1] for q in fv])      # [2F, S, S] depth of every face alone, y-up like the index map
+    n_cover = (per_face < R.FAR).sum(0)
+    assert n_cover.max() >= 9                                                     # more than two queues' worth of faces over some pixels
+    d = depth[0].cpu().numpy()
+    assert np.array_equal(d < R.FAR, depth_ref < R.FAR)
+    assert np.abs(d - depth_ref).max() < 1e-5
+    # the index map: exact wherever the nearest face is nearest by a margin; where two faces sit at the same depth (9 / 10 and 5 / 7 by
+    # construction) fp32 rounding of the weights may order them either way, so there the winner only has to be one of the tied faces
+    two = np.sort(per_face, 0)[:2]
+    clear = (two[1] - two[0]) > 1e-4
+    got = fidx[0].cpu().numpy()
+    assert clear.sum() > 200 and (~clear & (n_cover > 1)).sum() > 20
+    assert np.array_equal(got[clear], idx_ref[clear]), f"{(got[clear] != idx_ref[clear]).sum()} pixels with a clear nearest face differ"
+    amb = ~clear & (n_cover > 0)
+    yy, xx = np.nonzero(amb)
+    assert all(abs(per_face[got[y, x], y, x] - two[0][y, x]) < 1e-5 for y, x in zip(yy, xx))
