@@ -213,43 +213,65 @@ __global__ void __launch_bounds__(64) smpl_pose_bwd_kernel(SmplModel m, const fl
 
 // ------------------------------------------------------------------------------------------------ tiled FFMA GEMM
 // C[M,N] = A[M,K] Bm[K,N] (+ bias[N]) (+ add[M,N]); gridDim.z > 1 splits K and accumulates with atomics into a zeroed C.
-constexpr int GM = 32, GN = 128, GK = 16;
+// M is the number of frames (tens to a few hundred), N / K the 20 670 vertex coordinates / 472 blend coefficients: the tile height GM is picked
+// per launch (sgemm_gm; thread = TM x 4 outputs, TM = GM / 8), and the next K step's operands are fetched into registers while the current one is
+// multiplied (the first version waited for every 16-deep step's global loads in turn: 35 TFLOP/s fp32).
+constexpr int GN = 128, GK = 16;
+template <int GM>
 __global__ void __launch_bounds__(256) sgemm_kernel(const float* __restrict__ A, int lda, const float* __restrict__ Bm, int ldb,
                                                     float* __restrict__ C, int ldc, int M, int N, int K, int k_per_split,
                                                     const float* __restrict__ bias, const float* __restrict__ add, int ldadd) {
+  constexpr int TM = GM / 8;                                // rows per thread
+  constexpr int NA = (GM * 4 + 255) / 256;                  // float4 loads of the A tile per thread
+  static_assert(GM % 8 == 0 && TM % 2 == 0, "tile height");
   __shared__ __align__(16) float sA[GK][GM + 4];
   __shared__ __align__(16) float sB[GK][GN];
   const int tid = threadIdx.x, tx = tid % 32, ty = tid / 32;
   const int n0 = blockIdx.x * GN, m0 = blockIdx.y * GM;
   const int kb = blockIdx.z * k_per_split, ke = min(K, kb + k_per_split);
-  float acc[4][4];
+  float acc[TM][4];
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < TM; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-  const int a_row = tid / 4, a_k4 = tid % 4;
-  for (int k0 = kb; k0 < ke; k0 += GK) {
-    float4 av = make_float4(0, 0, 0, 0);
-    if (tid < 128 && m0 + a_row < M && k0 + a_k4 * 4 < ke) av = ld4(A + (size_t)(m0 + a_row) * lda + k0 + a_k4 * 4);
-    float4 bv[2];
+  float4 av[NA], bv[2];
+  auto fetch = [&](int k0) {
+#pragma unroll
+    for (int r = 0; r < NA; ++r) {
+      const int idx = tid + r * 256, a_row = idx / 4, a_k4 = idx % 4;
+      av[r] = make_float4(0, 0, 0, 0);
+      if (idx < GM * 4 && m0 + a_row < M && k0 + a_k4 * 4 < ke) av[r] = ld4(A + (size_t)(m0 + a_row) * lda + k0 + a_k4 * 4);
+    }
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
       const int row = tid / 32 + r * 8, c = n0 + tx * 4;
       bv[r] = make_float4(0, 0, 0, 0);
       if (k0 + row < ke && c < N) bv[r] = ld4(Bm + (size_t)(k0 + row) * ldb + c);
     }
-    __syncthreads();
-    if (tid < 128) { sA[a_k4 * 4 + 0][a_row] = av.x; sA[a_k4 * 4 + 1][a_row] = av.y; sA[a_k4 * 4 + 2][a_row] = av.z; sA[a_k4 * 4 + 3][a_row] = av.w; }
+  };
+  fetch(kb);
+  for (int k0 = kb; k0 < ke; k0 += GK) {
+    __syncthreads();                                        // the previous step's reads of sA / sB are done
+#pragma unroll
+    for (int r = 0; r < NA; ++r) {
+      const int idx = tid + r * 256, a_row = idx / 4, a_k4 = idx % 4;
+      if (idx < GM * 4) { sA[a_k4 * 4 + 0][a_row] = av[r].x; sA[a_k4 * 4 + 1][a_row] = av[r].y; sA[a_k4 * 4 + 2][a_row] = av[r].z; sA[a_k4 * 4 + 3][a_row] = av[r].w; }
+    }
 #pragma unroll
     for (int r = 0; r < 2; ++r) *reinterpret_cast<float4*>(&sB[tid / 32 + r * 8][tx * 4]) = bv[r];
     __syncthreads();
+    if (k0 + GK < ke) fetch(k0 + GK);                       // in flight during the products below
 #pragma unroll
     for (int kk = 0; kk < GK; ++kk) {
-      const float4 a4 = *reinterpret_cast<const float4*>(&sA[kk][ty * 4]);
       const float4 b4 = *reinterpret_cast<const float4*>(&sB[kk][tx * 4]);
-      const float a[4] = {a4.x, a4.y, a4.z, a4.w};
+      float a[TM];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
+      for (int i = 0; i < TM; i += 2) {
+        const float2 a2 = *reinterpret_cast<const float2*>(&sA[kk][ty * TM + i]);
+        a[i] = a2.x; a[i + 1] = a2.y;
+      }
+#pragma unroll
+      for (int i = 0; i < TM; ++i) {
         acc[i][0] = fmaf(a[i], b4.x, acc[i][0]); acc[i][1] = fmaf(a[i], b4.y, acc[i][1]);
         acc[i][2] = fmaf(a[i], b4.z, acc[i][2]); acc[i][3] = fmaf(a[i], b4.w, acc[i][3]);
       }
@@ -257,8 +279,8 @@ __global__ void __launch_bounds__(256) sgemm_kernel(const float* __restrict__ A,
   }
   const bool split = gridDim.z > 1;
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int mrow = m0 + ty * 4 + i;
+  for (int i = 0; i < TM; ++i) {
+    const int mrow = m0 + ty * TM + i;
     if (mrow >= M) continue;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -272,6 +294,30 @@ __global__ void __launch_bounds__(256) sgemm_kernel(const float* __restrict__ A,
       if (split) atomicAdd(C + (size_t)mrow * ldc + n, v); else C[(size_t)mrow * ldc + n] = v;
     }
   }
+}
+
+// tile height for M rows: the one with the shortest makespan -- waves of CTAs over the SMs x rows per tile (a 96-row tile would read the Bm panel
+// once, but 96 frames x 162 column tiles are 162 CTAs = two rounds on 148 SMs, while 486 tiles of 32 rows are four rounds of a third of the work);
+// ties go to the taller tile (fewer panel reads)
+static int sgemm_gm(int M, int ctas_per_row_tile) {
+  static int sms = 0;
+  if (!sms) { cudaDeviceProp p; int dev = 0; cudaGetDevice(&dev); sms = (cudaGetDeviceProperties(&p, dev) == cudaSuccess && p.multiProcessorCount > 0) ? p.multiProcessorCount : 148; }
+  const int cand[2] = {48, 32};                            // (64- and 96-row tiles never win at SMPL-H's 162 column tiles: not instantiated)
+  int best = 32;
+  long long best_cost = -1;
+  for (int gm : cand) {
+    const long long ctas = (long long)ctas_per_row_tile * ceil_div(M, gm);
+    const long long cost = ((ctas + sms - 1) / sms) * gm;
+    if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = gm; }
+  }
+  return best;
+}
+static void sgemm_launch(int n_tiles, int k_splits, cudaStream_t s, const float* A, int lda, const float* Bm, int ldb, float* C, int ldc, int M, int N,
+                         int K, int k_per_split, const float* bias, const float* add, int ldadd) {
+  const int gm = sgemm_gm(M, n_tiles * k_splits);
+  const dim3 grid(n_tiles, ceil_div(M, gm), k_splits);
+  if (gm == 32) sgemm_kernel<32><<<grid, 256, 0, s>>>(A, lda, Bm, ldb, C, ldc, M, N, K, k_per_split, bias, add, ldadd);
+  else sgemm_kernel<48><<<grid, 256, 0, s>>>(A, lda, Bm, ldb, C, ldc, M, N, K, k_per_split, bias, add, ldadd);
 }
 
 __global__ void vec_add_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ c, size_t n) {
@@ -448,9 +494,8 @@ int vt_smpl_fwd(const vt_smpl_model* model, const float* pose, const float* beta
   smpl_pose_fwd_kernel<<<B, 64, 0, s>>>(m, pose, betas, trans, scale, coef, R, J, G, A, jtr);
   VT_CHECK_LAUNCH("vt_smpl_fwd(pose)");
   const int N = 3 * m.V;
-  dim3 grid(ceil_div(N, GN), ceil_div(B, GM), 1);
   // naked = template + coef x dirs ; v_posed = naked + offsets (smpl_layer.py:98-106)
-  sgemm_kernel<<<grid, 256, 0, s>>>(coef, m.kdp, m.dirs, m.nv3p, naked, N, B, N, m.kdp, m.kdp, m.templ, nullptr, 0);
+  sgemm_launch(ceil_div(N, GN), 1, s, coef, m.kdp, m.dirs, m.nv3p, naked, N, B, N, m.kdp, m.kdp, m.templ, nullptr, 0);
   VT_CHECK_LAUNCH("vt_smpl_fwd(blend)");
   if (offsets) {
     const size_t total = (size_t)B * N;
@@ -481,8 +526,7 @@ int vt_smpl_bwd(const vt_smpl_model* model, const float* pose, const float* R, c
     smpl_skin_bwd_kernel<<<g2, 256, 0, s>>>(m, A, v_posed, g_verts, scale, g_vposed, m.nv3p, gA, g_trans_skin);
     VT_CHECK_LAUNCH("vt_smpl_bwd(skin)");
     const int ksplit = 512;
-    dim3 grid(ceil_div(m.kdp, GN), ceil_div(B, GM), ceil_div(m.nv3p, ksplit));
-    sgemm_kernel<<<grid, 256, 0, s>>>(g_vposed, m.nv3p, m.dirsT, m.kdp, g_coef, m.kdp, B, m.kdp, m.nv3p, ksplit, nullptr, nullptr, 0);
+    sgemm_launch(ceil_div(m.kdp, GN), ceil_div(m.nv3p, ksplit), s, g_vposed, m.nv3p, m.dirsT, m.kdp, g_coef, m.kdp, B, m.kdp, m.nv3p, ksplit, nullptr, nullptr, 0);
     VT_CHECK_LAUNCH("vt_smpl_bwd(blend)");
   }
   smpl_pose_bwd_kernel<<<B, 64, 0, s>>>(m, pose, R, J, G, gA, g_jtr, g_verts ? g_coef : nullptr, g_trans_skin, scale, g_pose, g_betas, g_trans);
