@@ -257,6 +257,9 @@ __global__ void __launch_bounds__(128) raster_bwd_kernel(const float* __restrict
       else direction = (p[0][0] < p[1][0]) ? 1 : -1;
       const int d0_from = (int)fmaxf(ceilf(fminf(p[0][0], p[1][0])), 0.f);
       const int d0_to = (int)fminf(fmaxf(p[0][0], p[1][0]), (float)(is - 1));
+      // the two edge vertices' sums of this (edge, axis) in registers: grad_face is indexed by run-time values and lives in local memory --
+      // a load / add / store through it per contributing pixel chained the walks on memory latency
+      float acc0 = 0.f, acc1 = 0.f;
       for (int d0 = d0_from + lane; d0 <= d0_to; d0 += RB_LANES) {
         const float d1_cross = (p[1][1] - p[0][1]) / (p[1][0] - p[0][0]) * (d0 - p[0][0]) + p[0][1];
         const int d1_in = direction > 0 ? (int)floorf(d1_cross) : (int)ceilf(d1_cross);
@@ -298,12 +301,12 @@ __global__ void __launch_bounds__(128) raster_bwd_kernel(const float* __restrict
             if (p[1][0] != d0) {
               float dist = (p[1][0] - p[0][0]) / (p[1][0] - d0) * (d1 - d1_cross) * 2.f / is;
               dist = (0 < dist) ? dist + R_EPS : dist - R_EPS;
-              grad_face[pi[0] * 3 + (1 - axis)] -= diff_grad / dist;
+              acc0 -= diff_grad / dist;
             }
             if (p[0][0] != d0) {
               float dist = (p[1][0] - p[0][0]) / (d0 - p[0][0]) * (d1 - d1_cross) * 2.f / is;
               dist = (0 < dist) ? dist + R_EPS : dist - R_EPS;
-              grad_face[pi[1] * 3 + (1 - axis)] -= diff_grad / dist;
+              acc1 -= diff_grad / dist;
             }
           }
         }
@@ -325,16 +328,18 @@ __global__ void __launch_bounds__(128) raster_bwd_kernel(const float* __restrict
             if (p[1][0] != d0) {
               float dist = (p[1][0] - p[0][0]) / (p[1][0] - d0) * (d1 - d1_cross) * 2.f / is;
               dist = (0 < dist) ? dist + R_EPS : dist - R_EPS;
-              grad_face[pi[0] * 3 + (1 - axis)] -= diff_grad / dist;
+              acc0 -= diff_grad / dist;
             }
             if (p[0][0] != d0) {
               float dist = (p[1][0] - p[0][0]) / (d0 - p[0][0]) * (d1 - d1_cross) * 2.f / is;
               dist = (0 < dist) ? dist + R_EPS : dist - R_EPS;
-              grad_face[pi[1] * 3 + (1 - axis)] -= diff_grad / dist;
+              acc1 -= diff_grad / dist;
             }
           }
         }
       }
+      grad_face[pi[0] * 3 + (1 - axis)] += acc0;
+      grad_face[pi[1] * 3 + (1 - axis)] += acc1;
     }
   }
 #pragma unroll
